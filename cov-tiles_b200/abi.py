@@ -1,0 +1,121 @@
+"""ctypes mirror of include/covt_b200.h (enums, POD structs). Interface definitions only — no compute.
+
+Enum values are the ordinals of the reference Java enums (J/converter/StreamEncoding.java:3-16,
+StreamType.java:3-16, ColumnType.java:3-9, ColumnDataType.java:3-21; GeometryType CovtParser.java:20-27).
+"""
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+
+# covt_stream_encoding
+ENC_PLAIN, ENC_VARINT, ENC_VARINT_ZIG_ZAG, ENC_VARINT_DELTA, ENC_VARINT_DELTA_ZIG_ZAG = 0, 1, 2, 3, 4
+ENC_RLE, ENC_BOOLEAN_RLE, ENC_BYTE_RLE, ENC_FAST_PFOR_DELTA, ENC_FAST_PFOR_DELTA_ZIG_ZAG = 5, 6, 7, 8, 9
+ENC_ABSENT = 0xFF
+# covt_stream_type
+(ST_PRESENT, ST_DATA, ST_LENGTH, ST_DICTIONARY, ST_GEOMETRY_TYPES, ST_GEOMETRY_OFFSETS, ST_PART_OFFSETS,
+ ST_RING_OFFSETS, ST_VERTEX_OFFSETS, ST_VERTEX_BUFFER, ST_Z_VALUE, ST_M_VALUE, ST_INDEX_BUFFER) = range(13)
+# covt_column_type
+CT_PLAIN, CT_DICTIONARY, CT_LOCALIZED_DICTIONARY, CT_ICE, CT_ICE_MORTON_CODE = range(5)
+# covt_column_data_type (gen-3)
+DT_BOOLEAN, DT_INT_32, DT_UINT_32, DT_INT_64, DT_UINT_64, DT_FLOAT, DT_DOUBLE, DT_STRING, DT_GEOMETRY = range(9)
+# covt_geometry_type
+GT_POINT, GT_LINESTRING, GT_POLYGON, GT_MULTIPOINT, GT_MULTILINESTRING, GT_MULTIPOLYGON = range(6)
+# covt_container
+CONTAINER_GEN2B, CONTAINER_GEN3 = 0, 1
+# covt_status
+(OK, ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_TRUNCATED, ERR_BAD_METADATA, ERR_UNSUPPORTED_ENCODING,
+ ERR_UNSUPPORTED_GEOMETRY, ERR_VARINT_OVERLONG, ERR_COUNT_MISMATCH, ERR_TOPOLOGY) = range(11)
+STATUS_NAMES = ["OK", "INVALID_ARG", "CUDA", "OOM", "TRUNCATED", "BAD_METADATA", "UNSUPPORTED_ENCODING",
+                "UNSUPPORTED_GEOMETRY", "VARINT_OVERLONG", "COUNT_MISMATCH", "TOPOLOGY"]
+# flags
+FLAG_CLOSE_RINGS = 0x0001
+FLAG_ID_DVZZ_IS_RLE = 0x0002
+FLAG_MORTON_NO_SHIFT = 0x0004
+FLAG_ID_WIDTH_32 = 0x0008
+FLAG_ICE_VB_COUNT_IS_INTS = 0x0010
+FLAG_SKIP_ASSEMBLY = 0x0020
+FLAG_PROFILE_KERNELS = 0x0040
+FLAG_DEFAULT = FLAG_CLOSE_RINGS
+# slots
+(SLOT_ID, SLOT_TYPES, SLOT_GEOM, SLOT_PART, SLOT_RING, SLOT_VOFF, SLOT_VBUF, SLOT_INDEX) = range(8)
+NUM_SLOTS = 8
+SLOT_NAMES = ["id", "geometry_types", "geometry_offsets", "part_offsets", "ring_offsets", "vertex_offsets",
+              "vertex_buffer", "index_buffer"]
+# buffers
+(BUF_S_GEOMETRY_TYPES, BUF_S_IDS, BUF_S_GEOMETRY_OFFSETS, BUF_S_PART_OFFSETS, BUF_S_RING_OFFSETS,
+ BUF_S_VERTEX_OFFSETS, BUF_S_VERTEX_BUFFER, BUF_S_INDEX_BUFFER, BUF_A_GEOM_OFFSETS, BUF_A_PART_OFFSETS,
+ BUF_A_RING_OFFSETS, BUF_A_COORDS, BUF_STREAM_ARENA) = range(13)
+NUM_BUFFERS = 13
+BUF_NAMES = ["s_geometry_types", "s_ids", "s_geometry_offsets", "s_part_offsets", "s_ring_offsets",
+             "s_vertex_offsets", "s_vertex_buffer", "s_index_buffer", "a_geom_offsets", "a_part_offsets",
+             "a_ring_offsets", "a_coords", "stream_arena"]
+BUF_DTYPES = [np.uint8, np.int64, np.int32, np.int32, np.int32, np.int32, np.int32, np.int32, np.int32,
+              np.int32, np.int32, np.int32, np.uint8]
+SLOT_BUF = [BUF_S_IDS, BUF_S_GEOMETRY_TYPES, BUF_S_GEOMETRY_OFFSETS, BUF_S_PART_OFFSETS, BUF_S_RING_OFFSETS,
+            BUF_S_VERTEX_OFFSETS, BUF_S_VERTEX_BUFFER, BUF_S_INDEX_BUFFER]
+# ops
+(OP_NONE, OP_BYTE_RLE, OP_RLE_U32, OP_RLE_U64, OP_RLE_S64, OP_VARINT_U32, OP_VARINT_ZZ, OP_VARINT_ZZ_DELTA,
+ OP_VARINT_ZZ_DELTA_XY, OP_VARINT_DELTA_MORTON, OP_VARINT_U64, OP_VARINT_ZZ_DELTA_64, OP_PFOR_ZZ_DELTA,
+ OP_PFOR_ZZ_DELTA_XY, OP_PFOR_DELTA_MORTON, OP_VARINT_U32_AS_I64, OP_VARINT_ZZ_DELTA_AS_I64) = range(17)
+OP_NAMES = ["none", "byte_rle", "rle_u32", "rle_u64", "rle_s64", "varint_u32", "varint_zz", "varint_zz_delta",
+            "varint_zz_delta_xy", "varint_delta_morton", "varint_u64", "varint_zz_delta_64", "pfor_zz_delta",
+            "pfor_zz_delta_xy", "pfor_delta_morton", "varint_u32_as_i64", "varint_zz_delta_as_i64"]
+
+
+def op_elem_size(op):
+    if op == OP_BYTE_RLE:
+        return 1
+    if op in (OP_RLE_U64, OP_RLE_S64, OP_VARINT_U64, OP_VARINT_ZZ_DELTA_64, OP_VARINT_U32_AS_I64,
+              OP_VARINT_ZZ_DELTA_AS_I64):
+        return 8
+    return 4
+
+
+def op_dtype(op):
+    return {1: np.uint8, 8: np.int64, 4: np.int32}[op_elem_size(op)]
+
+
+class StreamRef(C.Structure):
+    _fields_ = [("byte_offset", C.c_uint64), ("byte_length", C.c_uint32), ("num_values", C.c_uint32),
+                ("encoding", C.c_uint8), ("op", C.c_uint8), ("reserved", C.c_uint8 * 2), ("status", C.c_uint32)]
+
+
+class Layer(C.Structure):
+    _fields_ = [("tile", C.c_uint32), ("layer_index", C.c_uint32), ("extent", C.c_uint32),
+                ("num_features", C.c_uint32), ("num_columns", C.c_uint32), ("status", C.c_uint32),
+                ("geom_column_type", C.c_uint8), ("num_bits", C.c_uint8), ("has_id", C.c_uint8),
+                ("reserved", C.c_uint8), ("name_length", C.c_uint32), ("name_offset", C.c_uint64),
+                ("streams", StreamRef * NUM_SLOTS), ("out", C.c_uint64 * NUM_BUFFERS),
+                ("n_parts", C.c_uint32), ("n_rings", C.c_uint32), ("n_vertices", C.c_uint32),
+                ("n_coords", C.c_uint32), ("cap_parts", C.c_uint32), ("cap_rings", C.c_uint32),
+                ("reserved2", C.c_uint32 * 2)]
+
+
+class StreamDesc(C.Structure):
+    _fields_ = [("byte_offset", C.c_uint64), ("byte_length", C.c_uint32), ("num_values", C.c_uint32),
+                ("stream_type", C.c_uint8), ("encoding", C.c_uint8), ("column_type", C.c_uint8),
+                ("column_data_type", C.c_uint8), ("num_bits", C.c_uint8), ("op", C.c_uint8),
+                ("reserved", C.c_uint8 * 2), ("status", C.c_uint32), ("bytes_consumed", C.c_uint32),
+                ("out_offset", C.c_uint64), ("out_count", C.c_uint64)]
+
+
+class TileJson(C.Structure):
+    _fields_ = [("n_vector_layers", C.c_uint32), ("n_fields", C.POINTER(C.c_uint32))]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("decode_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("kernel_launches", C.c_uint32), ("payload_bytes", C.c_uint64), ("output_bytes", C.c_uint64),
+                ("vertices", C.c_uint64)]
+
+
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("launches", C.c_uint32),
+                ("algorithmic_bytes", C.c_uint64)]
+
+
+LAYER_DTYPE = np.dtype(Layer)
+STREAM_DESC_DTYPE = np.dtype(StreamDesc)
+assert C.sizeof(StreamRef) == 24 and C.sizeof(StreamDesc) == 48, (C.sizeof(StreamRef), C.sizeof(StreamDesc))
