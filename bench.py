@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py — COVT tile-batch decode on N B200s (BASELINE.json metric: compressed GB/s & Mvertices/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tiles|fixtures|varint1g|index] [--impl reference]
+
+One "step" = one pass of the hot path (container walk, every stream codec, geometry assembly) over one batch.
+Default workload = BASELINE config 5: 1 048 576 synthetic mixed-geometry gen-2b tiles per GPU, seed = tile index
+(weak scaling: rank r decodes tiles [r*T, (r+1)*T); tiles share nothing, so there is no collective on the data path).
+
+  value      compressed GB/s, whole job, inputs already resident in HBM, timed with CUDA events on the library's
+             launching stream (first kernel start -> last kernel end), max over ranks
+  e2e        the same metric through the reference-facing C-ABI call covt_decode_batch with HOST (pinned) buffers:
+             host->device copy, decode and the device->host read of the per-tile status + layer index inside the timed region
+  roofline   dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM copy peak
+  cpu_baseline / --impl reference: the CPU oracle (C restatement of the reference Java decoder; no JVM in this image)
+             timed on the box's host cores — test infrastructure used only as the checker/baseline, never as the product.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "covt_tile_batch_decode_compressed_GBps"
+CACHE_DIR = os.environ.get("COVT_BENCH_CACHE", "/tmp/covt_bench_cache")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def make_tiles(first_tile, n_tiles, container=0):
+    """Config 5 tiles; cached on local disk because the driver runs several arms back to back on one box."""
+    from tools.gen import gen as G
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    key = os.path.join(CACHE_DIR, "tiles_c%d_%d_%d" % (container, first_tile, n_tiles))
+    if os.path.exists(key + ".json"):
+        try:
+            meta = json.load(open(key + ".json"))
+            blob = np.fromfile(key + ".blob", dtype=np.uint8)
+            offs = np.fromfile(key + ".offs", dtype=np.uint64)
+            if len(blob) == meta["bytes"] and len(offs) == n_tiles + 1:
+                return blob, offs, meta["truth"]
+        except Exception:
+            pass
+    t0 = time.time()
+    blob, offs, truth = G.tiles(first_tile, n_tiles, G.default_params(container=container))
+    log("[bench] generated %d tiles (%.1f MB) in %.1f s" % (n_tiles, len(blob) / 1e6, time.time() - t0))
+    try:
+        blob.tofile(key + ".blob")
+        offs.tofile(key + ".offs")
+        json.dump({"bytes": int(len(blob)), "truth": truth}, open(key + ".json", "w"))
+    except Exception as e:  # a full disk must not fail the bench
+        log("[bench] cache write failed:", e)
+    return blob, offs, truth
+
+
+def make_fixture_sweep(replicas):
+    """Config 2: the reference's gen-2b OMT fixture tiles z2-z14 in one batch, replicated for timing."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    tiles = [b for n, b in util.load_fixture_tiles() if n.startswith("omt/")]
+    blob1, offs1 = util.concat_tiles(tiles)
+    blob = np.tile(blob1, replicas)
+    sizes = np.tile(np.diff(offs1), replicas)
+    offs = np.zeros(len(sizes) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(sizes)
+    return blob, offs, None
+
+
+def read_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        sm = []
+        reasons = set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path, restated in C (oracle/), on the host cores."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    abi = O.abi
+    blob, offs, truth, cfg, container, flags = build_workload(args, 0, for_cpu=True)
+    threads = os.cpu_count() or 1
+    if args.workload == "varint1g":
+        threads = 1  # one delta chain: sequential on the CPU
+        sample = min(len(blob), 128 << 20)
+        nv = min(truth["stream_values"], (sample // 4) & ~1)
+
+        def one_step():
+            vals, st_, cons = O.decode_stream(blob[:sample + 8], abi.OP_VARINT_ZZ_DELTA_XY, num_values=nv)
+            return cons, len(vals) // 2
+        cfg["sample"] = "the first %d values of the stream per step, one thread" % nv
+    else:
+        def one_step():
+            rc, p, v, _cs = O.decode_batch_timed(blob, offs, container, flags, n_threads=threads)
+            return p, v
+        cfg["sample"] = "%d tiles per step (the rank-0 batch of the GPU arm)" % (len(offs) - 1)
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    pb = vx = 0
+    for _ in range(args.steps):
+        p, v = one_step()
+        pb += p
+        vx += v
+    dt = time.perf_counter() - t0
+    gbps = pb / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": cfg.get("data", "synthetic"), "config": cfg,
+            "mvertices_per_s": vx / dt / 1e6,
+            "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": threads, "kind": "port",
+                             "sample": cfg["sample"] + "; C restatement of the Java decoder (JVM unavailable), -O2, pthreads"},
+            "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def build_workload(args, rank, for_cpu=False):
+    import covt_loader
+    abi = covt_loader.load().abi
+    flags = abi.FLAG_DEFAULT
+    container = abi.CONTAINER_GEN2B
+    if args.workload == "tiles":
+        n = args.tiles
+        blob, offs, truth = make_tiles(rank * n, n)
+        cfg = {"workload": "config5: %d synthetic mixed-geometry gen-2b tiles per GPU, seed = tile index, 2 layers/tile" % n,
+               "tiles_per_gpu": n, "partition": "tile index ranges, no collective", "l2": "inputs (%.2f GB) and outputs far larger than the 126 MB L2" % (len(blob) / 1e9)}
+    elif args.workload == "fixtures":
+        blob, offs, truth = make_fixture_sweep(args.replicas)
+        flags |= abi.FLAG_ID_DVZZ_IS_RLE
+        cfg = {"workload": "config2: the reference's 91 gen-2b OMT fixture tiles z2-z14 in one batch, x%d replicas" % args.replicas,
+               "l2": "inputs larger than L2"}
+    elif args.workload == "varint1g":
+        from tools.gen import gen as G
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        key = os.path.join(CACHE_DIR, "varint_%d_%d" % (args.stream_bytes, rank))
+        if os.path.exists(key + ".json"):
+            blob = np.fromfile(key + ".blob", dtype=np.uint8)
+            nvals = json.load(open(key + ".json"))["n"]
+        else:
+            t0 = time.time()
+            blob, nvals = G.varint_stream(args.stream_bytes, seed=0xC0717 + rank)
+            log("[bench] generated a %d-byte varint stream in %.1f s" % (len(blob), time.time() - t0))
+            try:
+                blob.tofile(key + ".blob")
+                json.dump({"n": nvals}, open(key + ".json", "w"))
+            except Exception as e:
+                log("[bench] cache write failed:", e)
+        offs = np.array([0, len(blob)], dtype=np.uint64)
+        truth = {"stream_values": nvals}
+        cfg = {"workload": "config3: one PLAIN VERTEX_BUFFER / VARINT_DELTA_ZIG_ZAG stream of %d bytes per GPU (%d ints), seed 0xC0717" % (len(blob), nvals),
+               "l2": "input 1 GiB and output 2.8 GB far larger than the 126 MB L2"}
+    else:
+        raise SystemExit("unknown workload " + args.workload)
+    cfg["data"] = "reference fixtures (replicated)" if args.workload == "fixtures" else "synthetic"
+    return blob, offs, truth, cfg, container, flags
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import covt_loader
+    covt = covt_loader.load()
+    abi = covt.abi
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dec = covt.Decoder(local_rank)  # raises without the CUDA library / device: no CPU fallback
+
+    blob_np, offs, truth, cfg, container, flags = build_workload(args, rank)
+    n_tiles = len(offs) - 1
+    # pinned host copy of the inputs (what a caller hands to covt_decode_batch)
+    pinned = torch.empty(len(blob_np), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = blob_np
+    offs_pinned = torch.empty(len(offs), dtype=torch.int64, pin_memory=True)
+    offs_pinned.numpy().view(np.uint64)[:] = offs
+    del blob_np
+    blob_ptr, offs_ptr = pinned.data_ptr(), offs_pinned.data_ptr()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream_mode = args.workload == "varint1g"
+    if stream_mode:
+        import ctypes as C
+        descs = (abi.StreamDesc * 1)()
+
+        def fresh_descs():
+            descs[0] = abi.StreamDesc(byte_offset=0, byte_length=pinned.numel(), num_values=truth["stream_values"],
+                                      op=abi.OP_VARINT_ZZ_DELTA_XY)
+            return descs
+
+        class _D:  # same call shapes as the batch path
+            @staticmethod
+            def decode(batch, container, fl):
+                return dec.decode_streams(batch, fresh_descs(), fl)
+
+            @staticmethod
+            def decode_batch_raw(bp, op_, n, container, fl):
+                h = C.c_void_p()
+                dec._check(covt.lib().covt_decode_streams(dec._h, bp, pinned.numel(), fresh_descs(), 1, fl, C.byref(h)))
+                return covt.Result(dec, h)
+        runner = _D
+    else:
+        runner = dec
+
+    # ---------------- device-resident decode: inputs already in HBM ----------------
+    batch = dec.upload_raw(blob_ptr, offs_ptr, n_tiles, pinned.numel())
+    pflags = flags | abi.FLAG_PROFILE_KERNELS
+    for _ in range(max(args.warmup, 3)):
+        r = runner.decode(batch, container, pflags)
+        r.free()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    dev_ms = 0.0
+    launches = 0
+    ktimes = {}
+    payload = verts = outb = 0
+    bad_tiles = 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = runner.decode(batch, container, pflags)
+        t = r.timing()
+        dev_ms += t["decode_ms"]
+        launches += t["kernel_launches"]
+        payload, verts, outb = t["payload_bytes"], t["vertices"], t["output_bytes"]
+        for k in r.kernel_times():
+            e = ktimes.setdefault(k["name"], {"ms": 0.0, "launches": 0, "bytes": 0})
+            e["ms"] += k["ms"]
+            e["launches"] += k["launches"]
+            e["bytes"] += k["algorithmic_bytes"]
+        r.free()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    clocks = sampler.stop()
+    # parity guard outside the timed region: every tile decoded, totals equal what was encoded
+    r = runner.decode(batch, container, flags)
+    if stream_mode:
+        assert descs[0].status == 0 and descs[0].out_count == truth["stream_values"], "stream decode failed"
+        verts = truth["stream_values"] // 2
+        st = np.zeros(1, np.uint32)
+    else:
+        st, _first = r.tile_status()
+    bad_tiles = int((st != 0).sum())
+    if truth is not None and not stream_mode:
+        L = r.layers
+        assert int(L["n_vertices"].sum()) == truth["vertices"], "decoded vertex count differs from what was encoded"
+        assert int(L["n_rings"].sum()) == truth["rings"] and int(L["n_parts"].sum()) == truth["parts"]
+    r.free()
+    batch.free()
+
+    # ---------------- end to end through the C-ABI call with host buffers ----------------
+    for _ in range(2):
+        r = runner.decode_batch_raw(blob_ptr, offs_ptr, n_tiles, container, flags)
+        r.touch_tile_status()
+        r.free()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = runner.decode_batch_raw(blob_ptr, offs_ptr, n_tiles, container, flags)
+        r.touch_tile_status()  # device->host read of the step's result index: per-tile status + first-layer table
+        r.free()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d_bytes = pinned.numel() + offs_pinned.numel() * 8
+    d2h_bytes = n_tiles * 4 + (n_tiles + 1) * 4 + (1 + abi.NUM_BUFFERS + 4) * 8
+
+    # ---------------- reduce over ranks ----------------
+    tt = torch.tensor([dev_ms, e2e_s * 1e3, wall_ms], dtype=torch.float64, device="cuda")
+    ss = torch.tensor([payload, verts, outb, launches, bad_tiles], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max, wall_ms_max = [float(x) for x in tt.tolist()]
+    payload_all, verts_all, outb_all, launches_all, bad_all = [float(x) for x in ss.tolist()]
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        steps = args.steps
+        value = payload_all * steps / (dev_ms_max * 1e-3) / 1e9
+        mverts = verts_all * steps / (dev_ms_max * 1e-3) / 1e6
+        top = max(ktimes.items(), key=lambda kv: kv[1]["ms"]) if ktimes else (None, None)
+        roof = None
+        if top[0]:
+            k = top[1]
+            achieved = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(top[0])
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": k["bytes"] / max(k["launches"], 1),
+                    "ms_per_launch": k["ms"] / max(k["launches"], 1), "share_of_step": k["ms"] / max(dev_ms, 1e-9),
+                    "kernels": {n: {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps} for n, v in ktimes.items()}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline and stream_mode:
+            from oracle import oracle as O
+            hb = pinned.numpy()
+            sample = min(len(hb), 256 << 20)
+            t0 = time.perf_counter()
+            vals, st_, cons = O.decode_stream(hb[:sample + 8], abi.OP_VARINT_ZZ_DELTA_XY, num_values=min(truth["stream_values"], (sample // 4) & ~1))
+            dt = time.perf_counter() - t0
+            cpu = {"value": cons / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port", "mvertices_per_s": len(vals) / 2 / dt / 1e6,
+                   "sample": "the first %d values (%.0f MB) of the same stream, one thread (a single delta chain is sequential on "
+                             "the CPU); C restatement of DecodingUtils.decodeZigZagDeltaVarintCoordinates" % (len(vals), cons / 1e6)}
+        elif world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            threads = os.cpu_count() or 1
+            hb = pinned.numpy()
+            O.decode_batch_timed(hb[: int(offs[min(2048, n_tiles)])], offs[: min(2048, n_tiles) + 1], container, flags, n_threads=threads)
+            t0 = time.perf_counter()
+            rc, pb, vx, _cs = O.decode_batch_timed(hb, offs, container, flags, n_threads=threads)
+            dt = time.perf_counter() - t0
+            cpu = {"value": pb / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port", "mvertices_per_s": vx / dt / 1e6,
+                   "sample": "one pass over the same %d tiles (%.2f GB payload, %.1f s); C restatement of the reference Java "
+                             "decoder (JVM unavailable), -O2, pthreads" % (n_tiles, pb / 1e9, dt)}
+        cfg.update({"container": "gen-2b", "flags": "CLOSE_RINGS", "payload_bytes_per_gpu": payload, "vertices_per_gpu": verts,
+                    "output_bytes_per_gpu": outb, "bad_tiles": bad_all})
+        line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                "data": cfg.pop("data"), "config": cfg, "mvertices_per_s": mverts, "wall_ms_per_step": wall_ms_max / steps,
+                "roofline": roof, "cpu_baseline": cpu,
+                "e2e": {"value": payload_all * steps / (e2e_ms_max * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms_max / steps,
+                        "mvertices_per_s": verts_all * steps / (e2e_ms_max * 1e-3) / 1e6,
+                        "note": "results stay device-resident (GeoArrow-style buffers); the device->host read is the per-tile status + layer index"},
+                "gpu_launches": int(launches_all), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="tiles", choices=["tiles", "fixtures", "varint1g"])
+    ap.add_argument("--stream-bytes", type=int, default=1 << 30, help="config 3 stream size")
+    ap.add_argument("--tiles", type=int, default=1 << 20, help="tiles per GPU (config 5: 1 048 576)")
+    ap.add_argument("--replicas", type=int, default=256, help="fixture-sweep replicas (config 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,415 @@
+"""cov-tiles_b200 — B200-native COVT tile-batch decoder (host-side binding of libcovt_b200.so).
+
+This package is plumbing over the C ABI in include/covt_b200.h: it loads the in-tree shared library
+(hand-written sm_100a kernels) with ctypes and mirrors the reference decoder's interface for the
+tile-decode path:
+
+    CovtParser.decode_covt(...)      <- CovtParser.decodeCovt(byte[], TileJson)   J/decoder/CovtParser.java:53
+    DecodingUtils.decode_*(...)      <- the static codecs of DecodingUtils        J/decoder/DecodingUtils.java:35-444
+
+There is no CPU fallback: if the library or a CUDA device is missing, construction raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi  # noqa: F401
+from .abi import *  # noqa: F401,F403
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libcovt_b200.so")
+_lib = None
+
+
+class CovtError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("covt error %d (%s): %s" % (code, abi.STATUS_NAMES[code] if 0 <= code < len(abi.STATUS_NAMES) else "?", message))
+        self.code = code
+
+
+def build(force=False, verbose=False):
+    """Compile libcovt_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "covt_b200.h"))
+    if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs):
+        subprocess.check_call(["make", "-C", csrc, "-j2"], stdout=None if verbose else subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+# every symbol include/covt_b200.h declares
+ABI_SYMBOLS = [
+    "covt_abi_version", "covt_create", "covt_destroy", "covt_last_error", "covt_decode_batch", "covt_batch_upload",
+    "covt_batch_decode", "covt_batch_free", "covt_decode_streams", "covt_batch_decode_streams", "covt_resolve_op",
+    "covt_result_num_tiles", "covt_result_num_layers", "covt_result_layers", "covt_result_tile_status",
+    "covt_result_buffer", "covt_result_read", "covt_result_timing", "covt_result_kernel_times", "covt_result_free",
+    "covt_host_register", "covt_host_unregister", "covt_partition_tiles",
+]
+
+
+def lib():
+    """Loads libcovt_b200.so (must have been built: see build() / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise CovtError(abi.ERR_CUDA, "libcovt_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(_LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+    L.covt_abi_version.restype = i32
+    L.covt_create.argtypes = [i32, C.POINTER(vp)]
+    L.covt_destroy.argtypes = [vp]
+    L.covt_destroy.restype = None
+    L.covt_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.covt_decode_batch.argtypes = [vp, vp, vp, u32, u32, C.POINTER(abi.TileJson), u32, C.POINTER(vp)]
+    L.covt_batch_upload.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
+    L.covt_batch_decode.argtypes = [vp, vp, u32, C.POINTER(abi.TileJson), u32, C.POINTER(vp)]
+    L.covt_batch_free.argtypes = [vp]
+    L.covt_batch_free.restype = None
+    L.covt_decode_streams.argtypes = [vp, vp, u64, C.POINTER(abi.StreamDesc), u32, u32, C.POINTER(vp)]
+    L.covt_batch_decode_streams.argtypes = [vp, vp, C.POINTER(abi.StreamDesc), u32, u32, C.POINTER(vp)]
+    L.covt_resolve_op.argtypes = [u32, u32, u32, u32]
+    L.covt_result_num_tiles.argtypes = [vp]
+    L.covt_result_num_tiles.restype = u32
+    L.covt_result_num_layers.argtypes = [vp]
+    L.covt_result_num_layers.restype = u32
+    L.covt_result_layers.argtypes = [vp, C.POINTER(C.POINTER(abi.Layer))]
+    L.covt_result_tile_status.argtypes = [vp, C.POINTER(C.POINTER(u32)), C.POINTER(C.POINTER(u32))]
+    L.covt_result_buffer.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)]
+    L.covt_result_read.argtypes = [vp, u32, u64, u64, vp]
+    L.covt_result_timing.argtypes = [vp, C.POINTER(abi.Timing)]
+    L.covt_result_kernel_times.argtypes = [vp, C.POINTER(abi.KernelTime), u32, C.POINTER(u32)]
+    L.covt_result_free.argtypes = [vp]
+    L.covt_result_free.restype = None
+    L.covt_host_register.argtypes = [vp, vp, C.c_size_t]
+    L.covt_host_unregister.argtypes = [vp, vp]
+    L.covt_partition_tiles.argtypes = [vp, u32, u32, vp]
+    for name in ABI_SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int:
+            fn.restype = i32
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None and a.size else None
+
+
+def partition_tiles(tile_offsets, n_parts):
+    """Batch scheduler: contiguous tile ranges balanced by payload bytes (no collective; tiles share nothing)."""
+    offs = np.ascontiguousarray(tile_offsets, dtype=np.uint64)
+    starts = np.zeros(n_parts + 1, dtype=np.uint32)
+    rc = lib().covt_partition_tiles(offs.ctypes.data, len(offs) - 1, n_parts, starts.ctypes.data)
+    if rc:
+        raise CovtError(rc, "covt_partition_tiles")
+    return starts
+
+
+class Result:
+    """Owns a covt_result (device-resident buffers + layer table)."""
+
+    def __init__(self, dec, handle):
+        self._dec = dec
+        self._h = handle
+        self._layers = None
+
+    def free(self):
+        if self._h:
+            lib().covt_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    @property
+    def n_tiles(self):
+        return lib().covt_result_num_tiles(self._h)
+
+    @property
+    def n_layers(self):
+        return lib().covt_result_num_layers(self._h)
+
+    @property
+    def layers(self):
+        """numpy structured array of covt_layer (device->host on first use)."""
+        if self._layers is None:
+            p = C.POINTER(abi.Layer)()
+            self._dec._check(lib().covt_result_layers(self._h, C.byref(p)))
+            n = self.n_layers
+            if n:
+                self._layers = np.frombuffer(C.string_at(p, n * C.sizeof(abi.Layer)), dtype=abi.LAYER_DTYPE).copy()
+            else:
+                self._layers = np.zeros(0, dtype=abi.LAYER_DTYPE)
+        return self._layers
+
+    def tile_status(self):
+        s = C.POINTER(C.c_uint32)()
+        f = C.POINTER(C.c_uint32)()
+        self._dec._check(lib().covt_result_tile_status(self._h, C.byref(s), C.byref(f)))
+        n = self.n_tiles
+        status = np.ctypeslib.as_array(s, shape=(max(n, 1),))[:n].copy()
+        first = np.ctypeslib.as_array(f, shape=(n + 1,)).copy()
+        return status, first
+
+    def touch_tile_status(self):
+        """Device->host copy of the per-tile status + layer index without materialising numpy copies."""
+        s = C.POINTER(C.c_uint32)()
+        f = C.POINTER(C.c_uint32)()
+        self._dec._check(lib().covt_result_tile_status(self._h, C.byref(s), C.byref(f)))
+
+    def device_buffer(self, which):
+        """(device pointer, element count, element size) of one result buffer."""
+        p, n, es = C.c_void_p(), C.c_uint64(), C.c_uint32()
+        self._dec._check(lib().covt_result_buffer(self._h, which, C.byref(p), C.byref(n), C.byref(es)))
+        return p.value or 0, n.value, es.value
+
+    def buffer(self, which, offset=0, count=None):
+        """Host copy (numpy) of a result buffer or a slice of it."""
+        _, n, _ = self.device_buffer(which)
+        if count is None:
+            count = n - offset
+        out = np.empty(count, dtype=abi.BUF_DTYPES[which])
+        if count:
+            self._dec._check(lib().covt_result_read(self._h, which, offset, count, out.ctypes.data))
+        return out
+
+    def read_into(self, which, offset, count, host_ptr):
+        self._dec._check(lib().covt_result_read(self._h, which, offset, count, host_ptr))
+
+    def timing(self):
+        t = abi.Timing()
+        self._dec._check(lib().covt_result_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in abi.Timing._fields_}
+
+    def kernel_times(self):
+        arr = (abi.KernelTime * 32)()
+        n = C.c_uint32()
+        self._dec._check(lib().covt_result_kernel_times(self._h, arr, 32, C.byref(n)))
+        return [{"name": arr[i].name.decode(), "ms": arr[i].ms, "launches": arr[i].launches,
+                 "algorithmic_bytes": arr[i].algorithmic_bytes} for i in range(min(n.value, 32))]
+
+
+class Batch:
+    """A blob of tiles resident in HBM (covt_batch)."""
+
+    def __init__(self, dec, handle, n_tiles, nbytes):
+        self._dec, self._h, self.n_tiles, self.nbytes = dec, handle, n_tiles, nbytes
+
+    def free(self):
+        if self._h:
+            lib().covt_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Decoder:
+    """One decoder context per GPU (covt_ctx). Raises CovtError if no B200 / library is available."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().covt_create(device, C.byref(self._h))
+        if rc:
+            buf = C.create_string_buffer(512)
+            lib().covt_last_error(None, buf, 512)
+            self._h = None
+            raise CovtError(rc, buf.value.decode())
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().covt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            buf = C.create_string_buffer(512)
+            lib().covt_last_error(self._h, buf, 512)
+            raise CovtError(rc, buf.value.decode())
+
+    @staticmethod
+    def _tilejson(n_fields):
+        if n_fields is None:
+            return None, None
+        arr = (C.c_uint32 * max(1, len(n_fields)))(*n_fields)
+        return abi.TileJson(len(n_fields), C.cast(arr, C.POINTER(C.c_uint32))), arr
+
+    # ---- batch path -------------------------------------------------------------------------
+    def upload(self, blob, tile_offsets):
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        offs = np.ascontiguousarray(tile_offsets, dtype=np.uint64)
+        h = C.c_void_p()
+        self._check(lib().covt_batch_upload(self._h, _ptr(b), offs.ctypes.data, len(offs) - 1, C.byref(h)))
+        return Batch(self, h, len(offs) - 1, int(offs[-1]))
+
+    def upload_raw(self, blob_ptr, tile_offsets_ptr, n_tiles, nbytes):
+        """Upload from raw host pointers (pinned memory owned by the caller)."""
+        h = C.c_void_p()
+        self._check(lib().covt_batch_upload(self._h, blob_ptr, tile_offsets_ptr, n_tiles, C.byref(h)))
+        return Batch(self, h, n_tiles, nbytes)
+
+    def decode(self, batch, container=abi.CONTAINER_GEN2B, flags=abi.FLAG_DEFAULT, n_fields=None):
+        tj, keep = self._tilejson(n_fields)
+        h = C.c_void_p()
+        self._check(lib().covt_batch_decode(self._h, batch._h, container, C.byref(tj) if tj is not None else None, flags, C.byref(h)))
+        return Result(self, h)
+
+    def decode_batch(self, blob, tile_offsets, container=abi.CONTAINER_GEN2B, flags=abi.FLAG_DEFAULT, n_fields=None):
+        """The reference-facing call with HOST buffers: upload + decode (covt_decode_batch)."""
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        offs = np.ascontiguousarray(tile_offsets, dtype=np.uint64)
+        tj, keep = self._tilejson(n_fields)
+        h = C.c_void_p()
+        self._check(lib().covt_decode_batch(self._h, _ptr(b), offs.ctypes.data, len(offs) - 1, container,
+                                            C.byref(tj) if tj is not None else None, flags, C.byref(h)))
+        return Result(self, h)
+
+    def decode_batch_raw(self, blob_ptr, tile_offsets_ptr, n_tiles, container=abi.CONTAINER_GEN2B, flags=abi.FLAG_DEFAULT):
+        h = C.c_void_p()
+        self._check(lib().covt_decode_batch(self._h, blob_ptr, tile_offsets_ptr, n_tiles, container, None, flags, C.byref(h)))
+        return Result(self, h)
+
+    # ---- stream path ------------------------------------------------------------------------
+    def decode_streams(self, blob_or_batch, descs, flags=abi.FLAG_DEFAULT):
+        """descs: ctypes array of abi.StreamDesc (filled in place). Returns a Result holding BUF_STREAM_ARENA."""
+        h = C.c_void_p()
+        n = len(descs)
+        if isinstance(blob_or_batch, Batch):
+            self._check(lib().covt_batch_decode_streams(self._h, blob_or_batch._h, descs, n, flags, C.byref(h)))
+        else:
+            b = np.ascontiguousarray(blob_or_batch, dtype=np.uint8)
+            self._check(lib().covt_decode_streams(self._h, _ptr(b), b.size, descs, n, flags, C.byref(h)))
+        return Result(self, h)
+
+    def decode_stream(self, blob, op=0, *, byte_offset=0, byte_length=None, num_values, stream_type=0, encoding=0,
+                      column_type=0, num_bits=0, flags=abi.FLAG_DEFAULT):
+        """One DecodingUtils call. Returns (values ndarray, status, bytes_consumed)."""
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        if byte_length is None:
+            byte_length = b.size - byte_offset
+        descs = (abi.StreamDesc * 1)()
+        descs[0] = abi.StreamDesc(byte_offset=byte_offset, byte_length=byte_length, num_values=num_values,
+                                  stream_type=stream_type, encoding=encoding, column_type=column_type,
+                                  num_bits=num_bits, op=op)
+        res = self.decode_streams(b, descs, flags)
+        d = descs[0]
+        rop = op or lib().covt_resolve_op(stream_type, encoding, column_type, flags)
+        dt = np.dtype(abi.op_dtype(rop))
+        raw = res.buffer(abi.BUF_STREAM_ARENA, d.out_offset, d.out_count * dt.itemsize) if d.out_count else np.zeros(0, np.uint8)
+        res.free()
+        return raw.view(dt).copy(), d.status, d.bytes_consumed
+
+
+# ---- mirrors of the reference's static interface -----------------------------------------------------
+_default = {}
+
+
+def default_decoder(device=0):
+    if device not in _default:
+        _default[device] = Decoder(device)
+    return _default[device]
+
+
+class DecodingUtils:
+    """Same names and argument meaning as J/decoder/DecodingUtils.java; `pos` is a one-element list used like
+    me.lemire.integercompression.IntWrapper (advanced by the call)."""
+
+    @staticmethod
+    def _run(op, buf, pos, n, byte_length=None, num_bits=0, advance_by_length=False):
+        vals, st, consumed = default_decoder().decode_stream(buf, op, byte_offset=pos[0], byte_length=byte_length,
+                                                             num_values=n, num_bits=num_bits)
+        if st not in (abi.OK,):
+            raise CovtError(st, "stream decode failed")
+        pos[0] += byte_length if advance_by_length else consumed
+        return vals
+
+    @staticmethod
+    def decodeVarint(src, pos, numValues):  # DecodingUtils.java:35
+        return DecodingUtils._run(abi.OP_VARINT_U32, src, pos, numValues)
+
+    @staticmethod
+    def decodeZigZagVarint(buf, pos, numValues):  # :46
+        return DecodingUtils._run(abi.OP_VARINT_ZZ, buf, pos, numValues)
+
+    @staticmethod
+    def decodeZigZagDeltaVarint(buf, pos, numValues):  # :55
+        return DecodingUtils._run(abi.OP_VARINT_ZZ_DELTA, buf, pos, numValues)
+
+    @staticmethod
+    def decodeZigZagDeltaVarintCoordinates(buf, pos, numValues):  # :95
+        return DecodingUtils._run(abi.OP_VARINT_ZZ_DELTA_XY, buf, pos, numValues)
+
+    @staticmethod
+    def decodeRle(buf, numValues, pos, signed):  # :257
+        return DecodingUtils._run(abi.OP_RLE_S64 if signed else abi.OP_RLE_U64, buf, pos, numValues)
+
+    @staticmethod
+    def decodeByteRle(buf, numValues, pos, byteLength=None):  # :275 / :290
+        return DecodingUtils._run(abi.OP_BYTE_RLE, buf, pos, numValues, byte_length=byteLength,
+                                  advance_by_length=byteLength is not None)
+
+    @staticmethod
+    def decodeFastPfor128ZigZagDelta(buf, numValues, byteLength, pos):  # :316
+        return DecodingUtils._run(abi.OP_PFOR_ZZ_DELTA, buf, pos, numValues, byte_length=byteLength, advance_by_length=True)
+
+    @staticmethod
+    def decodeFastPfor128DeltaCoordinates(buf, numValues, byteLength, pos):  # :349
+        return DecodingUtils._run(abi.OP_PFOR_ZZ_DELTA_XY, buf, pos, numValues, byte_length=byteLength, advance_by_length=True)
+
+    @staticmethod
+    def decodeDeltaVarintMortonCodes(buf, pos, numVertices, numBits):  # :394
+        return DecodingUtils._run(abi.OP_VARINT_DELTA_MORTON, buf, pos, numVertices, num_bits=numBits)
+
+    @staticmethod
+    def decodeFastPfor128DeltaMortonCodes(buf, numVertices, byteLength, pos, numBits):  # :411
+        return DecodingUtils._run(abi.OP_PFOR_DELTA_MORTON, buf, pos, numVertices, byte_length=byteLength,
+                                  num_bits=numBits, advance_by_length=True)
+
+
+class CovtParser:
+    """CovtParser.decodeCovt (J/decoder/CovtParser.java:53) for one tile; returns flat buffers per layer instead of
+    JTS objects (SURVEY §8b output contract)."""
+
+    @staticmethod
+    def decodeCovt(covtBuffer, tileJson=None, container=abi.CONTAINER_GEN3, flags=abi.FLAG_DEFAULT):
+        b = np.ascontiguousarray(np.frombuffer(covtBuffer, dtype=np.uint8) if not isinstance(covtBuffer, np.ndarray) else covtBuffer)
+        dec = default_decoder()
+        res = dec.decode_batch(b, np.array([0, b.size], dtype=np.uint64), container, flags, n_fields=tileJson)
+        status, _ = res.tile_status()
+        if status[0]:
+            res.free()
+            raise CovtError(int(status[0]), "tile decode failed")
+        layers = []
+        bufs = [res.buffer(i) for i in range(abi.NUM_BUFFERS - 1)]
+        for L in res.layers:
+            F = int(L["streams"][abi.SLOT_TYPES]["num_values"])
+            o = L["out"]
+            name = bytes(b[int(L["name_offset"]):int(L["name_offset"]) + int(L["name_length"])]).decode("utf-8", "replace")
+            layers.append({
+                "name": name if L["name_length"] else int(L["name_offset"]),
+                "extent": int(L["extent"]),
+                "geometry_types": bufs[abi.BUF_S_GEOMETRY_TYPES][int(o[abi.BUF_S_GEOMETRY_TYPES]):][:F],
+                "ids": bufs[abi.BUF_S_IDS][int(o[abi.BUF_S_IDS]):][:F] if L["has_id"] else None,
+                "geom_offsets": bufs[abi.BUF_A_GEOM_OFFSETS][int(o[abi.BUF_A_GEOM_OFFSETS]):][:F + 1],
+                "part_offsets": bufs[abi.BUF_A_PART_OFFSETS][int(o[abi.BUF_A_PART_OFFSETS]):][:int(L["n_parts"]) + 1],
+                "ring_offsets": bufs[abi.BUF_A_RING_OFFSETS][int(o[abi.BUF_A_RING_OFFSETS]):][:int(L["n_rings"]) + 1],
+                "coords": bufs[abi.BUF_A_COORDS][int(o[abi.BUF_A_COORDS]):][:2 * int(L["n_coords"])],
+            })
+        res.free()
+        return layers

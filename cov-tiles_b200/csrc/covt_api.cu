@@ -1,0 +1,718 @@
+// covt_api.cu — host side of libcovt_b200: contexts, batches, results and the C ABI of include/covt_b200.h.
+//
+// The host does no per-tile work: it uploads the blob, launches the device-side container walk,
+// reads back ONE small totals record to size the result buffers, launches the decode kernels and
+// hands out device pointers. There is no CPU fallback: without a CUDA device every call fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "covt_internal.h"
+
+using namespace covt;
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_create_error;
+
+struct KernelRecord {
+    std::string name;
+    cudaEvent_t a, b;
+    uint64_t alg_bytes;
+};
+
+}  // namespace
+
+struct covt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t* h_totals = nullptr;  // pinned scratch for the one device->host size read-back
+    std::vector<cudaEvent_t> event_pool;
+};
+
+struct covt_batch {
+    covt_ctx* ctx = nullptr;
+    uint8_t* d_blob = nullptr;
+    uint64_t blob_len = 0;
+    uint64_t* d_tile_offsets = nullptr;
+    uint32_t n_tiles = 0;
+    float h2d_ms = 0.f;
+};
+
+struct covt_result {
+    covt_ctx* ctx = nullptr;
+    uint32_t n_tiles = 0, n_layers = 0;
+    covt_layer* d_layers = nullptr;
+    uint32_t* d_tile_status = nullptr;
+    uint32_t* d_first_layer = nullptr;
+    void* bufs[COVT_NUM_BUFFERS] = {};
+    uint64_t counts[COVT_NUM_BUFFERS] = {};
+    covt_layer* h_layers = nullptr;      // pinned, lazily fetched
+    uint32_t* h_tile_status = nullptr;   // pinned, lazily fetched
+    uint32_t* h_first_layer = nullptr;
+    covt_timing timing = {};
+    std::vector<covt_kernel_time> kernel_times;
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char m_[512];                                                                             \
+            snprintf(m_, sizeof(m_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = m_;                                                                            \
+            return e_ == cudaErrorMemoryAllocation ? COVT_ERR_OOM : COVT_ERR_CUDA;                    \
+        }                                                                                             \
+    } while (0)
+
+namespace {
+
+int32_t fail(covt_ctx* ctx, int32_t code, const char* msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+template <class T>
+cudaError_t dev_alloc(covt_ctx* ctx, T** p, uint64_t count)
+{
+    return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<uint64_t>(count, 1) * sizeof(T) + 64, ctx->stream);
+}
+void dev_free(covt_ctx* ctx, void* p)
+{
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// per-kernel timing (COVT_FLAG_PROFILE_KERNELS)
+struct Profiler {
+    covt_ctx* ctx;
+    bool on;
+    std::vector<KernelRecord> recs;
+    void begin(const char* name, uint64_t alg_bytes)
+    {
+        if (!on) return;
+        KernelRecord r;
+        r.name = name;
+        r.alg_bytes = alg_bytes;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, ctx->stream);
+        recs.push_back(r);
+    }
+    void end()
+    {
+        if (!on) return;
+        cudaEventRecord(recs.back().b, ctx->stream);
+    }
+    void collect(std::vector<covt_kernel_time>& out)
+    {
+        for (auto& r : recs) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+            bool merged = false;
+            for (auto& k : out)
+                if (r.name == k.name) { k.ms += ms; k.launches++; k.algorithmic_bytes += r.alg_bytes; merged = true; break; }
+            if (!merged) {
+                covt_kernel_time k;
+                memset(&k, 0, sizeof(k));
+                snprintf(k.name, sizeof(k.name), "%s", r.name.c_str());
+                k.ms = ms;
+                k.launches = 1;
+                k.algorithmic_bytes = r.alg_bytes;
+                out.push_back(k);
+            }
+        }
+        recs.clear();
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int32_t covt_abi_version(void) { return COVT_ABI_VERSION; }
+
+int32_t covt_create(int32_t device, covt_ctx** out)
+{
+    if (!out) return COVT_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
+        std::lock_guard<std::mutex> g(g_err_mutex);
+        g_create_error = e != cudaSuccess ? std::string("no CUDA device: ") + cudaGetErrorString(e)
+                                          : "CUDA device ordinal out of range (libcovt_b200 has no CPU fallback)";
+        return COVT_ERR_CUDA;
+    }
+    covt_ctx* ctx = new covt_ctx();
+    ctx->device = device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        std::lock_guard<std::mutex> g(g_err_mutex);
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete ctx;
+        return COVT_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        std::lock_guard<std::mutex> g(g_err_mutex);
+        g_create_error = "libcovt_b200 carries sm_100a kernels only; this device is not a Blackwell B200";
+        delete ctx;
+        return COVT_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_totals), 64 * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMallocHost", e);
+    // keep freed result buffers in the stream-ordered pool: batches are decoded back to back
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return COVT_OK;
+}
+
+void covt_destroy(covt_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int32_t covt_last_error(covt_ctx* ctx, char* buf, size_t buf_len)
+{
+    if (!buf || !buf_len) return COVT_ERR_INVALID_ARG;
+    std::string m;
+    if (ctx) m = ctx->err;
+    else { std::lock_guard<std::mutex> g(g_err_mutex); m = g_create_error; }
+    snprintf(buf, buf_len, "%s", m.c_str());
+    return COVT_OK;
+}
+
+int32_t covt_host_register(covt_ctx* ctx, void* ptr, size_t bytes)
+{
+    if (!ctx || !ptr) return COVT_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return COVT_OK;
+}
+int32_t covt_host_unregister(covt_ctx* ctx, void* ptr)
+{
+    if (!ctx || !ptr) return COVT_ERR_INVALID_ARG;
+    CK(cudaHostUnregister(ptr));
+    return COVT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload
+// ------------------------------------------------------------------------------------------------
+int32_t covt_batch_upload(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, covt_batch** out)
+{
+    if (!ctx || !out || (!blob && n_tiles) || !tile_offsets) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_batch_upload: null argument");
+    *out = nullptr;
+    for (uint32_t i = 0; i < n_tiles; i++)
+        if (tile_offsets[i + 1] < tile_offsets[i]) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_batch_upload: tile_offsets must be non-decreasing");
+    CK(cudaSetDevice(ctx->device));
+    covt_batch* b = new covt_batch();
+    b->ctx = ctx;
+    b->n_tiles = n_tiles;
+    b->blob_len = tile_offsets[n_tiles];
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    cudaError_t e;
+    // 256 bytes of zero padding: kernels read whole 16-byte windows and one word past unaligned words
+    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&b->d_blob), b->blob_len + 256, ctx->stream)) != cudaSuccess ||
+        (e = dev_alloc(ctx, &b->d_tile_offsets, (uint64_t)n_tiles + 1)) != cudaSuccess) {
+        delete b;
+        CK(e);
+    }
+    CK(cudaEventRecord(e0, ctx->stream));
+    CK(cudaMemsetAsync(b->d_blob + b->blob_len, 0, 256, ctx->stream));
+    if (b->blob_len) CK(cudaMemcpyAsync(b->d_blob, blob, b->blob_len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b->d_tile_offsets, tile_offsets, ((uint64_t)n_tiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&b->h2d_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *out = b;
+    return COVT_OK;
+}
+
+void covt_batch_free(covt_batch* b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    dev_free(b->ctx, b->d_blob);
+    dev_free(b->ctx, b->d_tile_offsets);
+    delete b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident decode of a whole batch
+// ------------------------------------------------------------------------------------------------
+int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, const covt_tilejson* tilejson, uint32_t flags,
+                          covt_result** out)
+{
+    if (!ctx || !batch || !out || batch->ctx != ctx) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_batch_decode: bad argument");
+    if (container != COVT_CONTAINER_GEN2B && container != COVT_CONTAINER_GEN3) return fail(ctx, COVT_ERR_INVALID_ARG, "unknown container kind");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n_tiles = batch->n_tiles;
+    cudaStream_t st = ctx->stream;
+    covt_result* R = new covt_result();
+    R->ctx = ctx;
+    R->n_tiles = n_tiles;
+    Profiler prof = {ctx, (flags & COVT_FLAG_PROFILE_KERNELS) != 0, {}};
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+
+    uint64_t *d_cols = nullptr, *d_block_sums = nullptr, *d_totals = nullptr;
+    uint32_t *d_tj = nullptr, *d_counter = nullptr;
+    const uint32_t nb = (n_tiles + 255) / 256;
+    int32_t rc = COVT_OK;
+    auto cleanup_tmp = [&]() {
+        dev_free(ctx, d_cols);
+        dev_free(ctx, d_block_sums);
+        dev_free(ctx, d_totals);
+        dev_free(ctx, d_tj);
+        dev_free(ctx, d_counter);
+    };
+#define CKR(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char m_[512];                                                                             \
+            snprintf(m_, sizeof(m_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = m_;                                                                            \
+            rc = e_ == cudaErrorMemoryAllocation ? COVT_ERR_OOM : COVT_ERR_CUDA;                      \
+            cleanup_tmp();                                                                            \
+            covt_result_free(R);                                                                      \
+            return rc;                                                                                \
+        }                                                                                             \
+    } while (0)
+
+    CKR(dev_alloc(ctx, &d_cols, (uint64_t)TILE_COLS * std::max(n_tiles, 1u)));
+    CKR(dev_alloc(ctx, &d_block_sums, (uint64_t)TILE_COLS * std::max(nb, 1u)));
+    CKR(dev_alloc(ctx, &d_totals, 32));
+    CKR(dev_alloc(ctx, &d_counter, 4));
+    CKR(dev_alloc(ctx, &R->d_tile_status, (uint64_t)n_tiles + 1));
+    CKR(dev_alloc(ctx, &R->d_first_layer, (uint64_t)n_tiles + 2));
+    uint32_t tj_layers = 0;
+    if (tilejson && tilejson->n_vector_layers && tilejson->n_fields) {
+        tj_layers = tilejson->n_vector_layers;
+        CKR(dev_alloc(ctx, &d_tj, tj_layers));
+        CKR(cudaMemcpyAsync(d_tj, tilejson->n_fields, tj_layers * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    CKR(cudaMemsetAsync(d_totals, 0, 32 * sizeof(uint64_t), st));
+    CKR(cudaMemsetAsync(d_counter, 0, 4 * sizeof(uint32_t), st));
+
+    CKR(cudaEventRecord(ev0, st));
+    // ---- K0 pass 1: layers per tile + slice sizes; scan; one small read-back sizes everything ----
+    prof.begin("k0_scan_tiles", 0);
+    CKR(launch_k0_scan_tiles(batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, flags, d_cols, R->d_tile_status, st));
+    prof.end();
+    prof.begin("scan_tile_cols", 0);
+    CKR(launch_scan_tile_cols(d_cols, n_tiles, d_block_sums, d_totals, st));
+    prof.end();
+    CKR(cudaMemcpyAsync(ctx->h_totals, d_totals, TILE_COLS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    if (ctx->h_totals[0] > 0xfffffff0ull) { cleanup_tmp(); covt_result_free(R); return fail(ctx, COVT_ERR_INVALID_ARG, "too many layers in one batch"); }
+    R->n_layers = (uint32_t)ctx->h_totals[0];
+    uint64_t out_bytes_alloc = 0;
+    for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
+        R->counts[b] = ctx->h_totals[1 + b];
+        const uint64_t bytes = R->counts[b] * kBufElemSize[b];
+        out_bytes_alloc += bytes;
+        if (bytes) CKR(cudaMallocAsync(&R->bufs[b], bytes + 64, st));
+    }
+    CKR(dev_alloc(ctx, &R->d_layers, (uint64_t)R->n_layers));
+    // ---- K0 pass 2: the layer table ----
+    prof.begin("k0_fill_layers", 0);
+    CKR(launch_k0_fill_layers(batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, flags, d_cols, R->d_layers, R->d_first_layer, st));
+    prof.end();
+    CKR(cudaMemcpyAsync(R->d_first_layer + n_tiles, &R->n_layers, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // ---- every stream of every layer + assembly ----
+    ResultBuffers rb;
+    for (int b = 0; b < COVT_NUM_BUFFERS; b++) rb.ptr[b] = R->bufs[b];
+    prof.begin("k_decode_layers", 0);
+    CKR(launch_decode_layers(batch->d_blob, R->d_layers, R->n_layers, rb, flags, d_counter, ctx->sm_count, st));
+    prof.end();
+    prof.begin("k_finalize", 0);
+    CKR(launch_finalize(R->d_layers, R->d_first_layer, n_tiles, flags, R->d_tile_status, d_totals + 16, st));
+    prof.end();
+    CKR(cudaEventRecord(ev1, st));
+    CKR(cudaMemcpyAsync(ctx->h_totals + 16, d_totals + 16, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&R->timing.decode_ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    R->timing.h2d_ms = batch->h2d_ms;
+    R->timing.vertices = ctx->h_totals[16];
+    R->timing.payload_bytes = ctx->h_totals[17];
+    R->timing.output_bytes = ctx->h_totals[18];
+    R->timing.kernel_launches = 8;  // k0_scan_tiles, 3 scan kernels, k0_fill_layers, k_decode_layers, k_finalize (+0 when empty)
+    if (prof.on) {
+        prof.collect(R->kernel_times);
+        for (auto& k : R->kernel_times)
+            if (!strcmp(k.name, "k_decode_layers")) k.algorithmic_bytes = R->timing.payload_bytes + R->timing.output_bytes;
+    }
+    R->timing.kernel_launches = n_tiles ? 7 : 0;
+    (void)out_bytes_alloc;
+    cleanup_tmp();
+#undef CKR
+    *out = R;
+    return COVT_OK;
+}
+
+int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                          const covt_tilejson* tilejson, uint32_t flags, covt_result** out)
+{
+    covt_batch* b = nullptr;
+    int32_t rc = covt_batch_upload(ctx, blob, tile_offsets, n_tiles, &b);
+    if (rc != COVT_OK) return rc;
+    rc = covt_batch_decode(ctx, b, container, tilejson, flags, out);
+    covt_batch_free(b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream path
+// ------------------------------------------------------------------------------------------------
+static uint32_t op_elem_size(uint32_t op)
+{
+    switch (op) {
+    case COVT_OP_BYTE_RLE: return 1;
+    case COVT_OP_RLE_U64: case COVT_OP_RLE_S64: case COVT_OP_VARINT_U64: case COVT_OP_VARINT_ZZ_DELTA_64:
+    case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: return 8;
+    default: return 4;
+    }
+}
+static int op_big_post(uint32_t op)
+{
+    switch (op) {
+    case COVT_OP_VARINT_U32: return POST_PLAIN;
+    case COVT_OP_VARINT_ZZ: return POST_ZZ;
+    case COVT_OP_VARINT_ZZ_DELTA: return POST_ZZ_DELTA;
+    case COVT_OP_VARINT_ZZ_DELTA_XY: return POST_ZZ_DELTA_XY;
+    case COVT_OP_VARINT_DELTA_MORTON: return POST_DELTA_MORTON;
+    default: return -1;
+    }
+}
+
+int32_t covt_resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags)
+{
+    return (int32_t)host_resolve_op(stream_type, encoding, column_type, flags);
+}
+
+int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_desc* descs, uint32_t n, uint32_t flags, covt_result** out)
+{
+    if (!ctx || !batch || !out || (!descs && n) || batch->ctx != ctx) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_batch_decode_streams: bad argument");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    covt_result* R = new covt_result();
+    R->ctx = ctx;
+    Profiler prof = {ctx, (flags & COVT_FLAG_PROFILE_KERNELS) != 0, {}};
+    std::vector<DeviceTask> tasks(n);
+    std::vector<BigStream> bigs;
+    std::vector<ChunkRef> chunks;
+    std::vector<uint32_t> big_task;
+    uint64_t arena = 0, payload = 0, out_bytes = 0, big_alg = 0, small_alg = 0;
+    const uint64_t BIG_BYTES = 1u << 18;  // streams of >= 256 KiB take the multi-CTA look-back kernel
+    for (uint32_t i = 0; i < n; i++) {
+        covt_stream_desc& d = descs[i];
+        DeviceTask& t = tasks[i];
+        memset(&t, 0, sizeof(t));
+        uint32_t op = d.op ? d.op : host_resolve_op(d.stream_type, d.encoding, d.column_type, flags);
+        d.status = COVT_OK;
+        d.bytes_consumed = 0;
+        d.out_count = 0;
+        d.out_offset = arena;
+        if (op == COVT_OP_NONE || op >= COVT_NUM_OPS) { d.status = COVT_ERR_UNSUPPORTED_ENCODING; t.status = d.status; continue; }
+        if (d.byte_offset + d.byte_length > batch->blob_len) { d.status = COVT_ERR_TRUNCATED; t.status = d.status; continue; }
+        const bool morton = op == COVT_OP_VARINT_DELTA_MORTON || op == COVT_OP_PFOR_DELTA_MORTON;
+        const uint64_t cnt = morton ? 2ull * d.num_values : d.num_values;
+        d.out_count = cnt;
+        t.src_offset = d.byte_offset;
+        t.dst_offset = arena;
+        t.byte_length = d.byte_length;
+        t.num_values = d.num_values;
+        t.op = (uint8_t)op;
+        t.num_bits = d.num_bits;
+        t.no_shift = (flags & COVT_FLAG_MORTON_NO_SHIFT) ? 1 : 0;
+        // FastPFOR calls carry an exact byteLength (DecodingUtils.java:316); varint/RLE calls only a start position
+        t.exact_length = (op == COVT_OP_PFOR_ZZ_DELTA || op == COVT_OP_PFOR_ZZ_DELTA_XY || op == COVT_OP_PFOR_DELTA_MORTON) ? 1 : 0;
+        const uint64_t ob = cnt * op_elem_size(op);
+        arena += (ob + 15) & ~15ull;
+        payload += d.byte_length;
+        out_bytes += ob;
+        const int post = op_big_post(op);
+        if (post >= 0 && d.byte_length >= BIG_BYTES && !((op == COVT_OP_VARINT_ZZ_DELTA_XY) && (d.num_values & 1u))) {
+            // large varint stream: byte_length is taken as exact (documented in DESIGN.md)
+            BigStream b;
+            memset(&b, 0, sizeof(b));
+            b.src_offset = d.byte_offset;
+            b.byte_length = d.byte_length;
+            b.num_values = d.num_values;
+            b.first_chunk = (uint32_t)chunks.size();
+            const uint64_t window = (d.byte_offset & 15) + d.byte_length;  // blob base is 256-byte aligned
+            b.n_chunks = (uint32_t)((window + K1_TILE_BYTES - 1) / K1_TILE_BYTES);
+            b.post = (uint8_t)post;
+            b.num_bits = d.num_bits;
+            b.no_shift = t.no_shift;
+            for (uint32_t c = 0; c < b.n_chunks; c++) chunks.push_back(ChunkRef{(uint32_t)bigs.size(), c});
+            bigs.push_back(b);
+            big_task.push_back(i);
+            t.op = COVT_OP_NONE;  // the warp-per-stream kernel skips it
+            big_alg += d.byte_length + ob;
+        } else {
+            small_alg += d.byte_length + ob;
+        }
+    }
+    DeviceTask* d_tasks = nullptr;
+    BigStream* d_bigs = nullptr;
+    ChunkRef* d_chunks = nullptr;
+    ChunkState* d_states = nullptr;
+    uint32_t* d_counter = nullptr;
+    int32_t rc = COVT_OK;
+    auto cleanup_tmp = [&]() {
+        dev_free(ctx, d_tasks);
+        dev_free(ctx, d_bigs);
+        dev_free(ctx, d_chunks);
+        dev_free(ctx, d_states);
+        dev_free(ctx, d_counter);
+    };
+#define CKR(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char m_[512];                                                                             \
+            snprintf(m_, sizeof(m_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = m_;                                                                            \
+            rc = e_ == cudaErrorMemoryAllocation ? COVT_ERR_OOM : COVT_ERR_CUDA;                      \
+            cleanup_tmp();                                                                            \
+            covt_result_free(R);                                                                      \
+            return rc;                                                                                \
+        }                                                                                             \
+    } while (0)
+    cudaEvent_t ev0, ev1;
+    CKR(cudaEventCreate(&ev0));
+    CKR(cudaEventCreate(&ev1));
+    R->counts[COVT_BUF_STREAM_ARENA] = arena;
+    CKR(cudaMallocAsync(&R->bufs[COVT_BUF_STREAM_ARENA], arena + 64, st));
+    CKR(dev_alloc(ctx, &d_tasks, n));
+    CKR(dev_alloc(ctx, &d_counter, 4));
+    if (!bigs.empty()) {
+        CKR(dev_alloc(ctx, &d_bigs, bigs.size()));
+        CKR(dev_alloc(ctx, &d_chunks, chunks.size()));
+        CKR(dev_alloc(ctx, &d_states, chunks.size()));
+        for (size_t k = 0; k < bigs.size(); k++) {
+            const uint32_t i = big_task[k];
+            bigs[k].dst = reinterpret_cast<uint8_t*>(R->bufs[COVT_BUF_STREAM_ARENA]) + tasks[i].dst_offset;
+            bigs[k].status_out = &d_tasks[i].status;
+            bigs[k].consumed_out = &d_tasks[i].consumed;
+        }
+        CKR(cudaMemcpyAsync(d_bigs, bigs.data(), bigs.size() * sizeof(BigStream), cudaMemcpyHostToDevice, st));
+        CKR(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
+    }
+    if (n) CKR(cudaMemcpyAsync(d_tasks, tasks.data(), (uint64_t)n * sizeof(DeviceTask), cudaMemcpyHostToDevice, st));
+    CKR(cudaMemsetAsync(d_counter, 0, 4 * sizeof(uint32_t), st));
+    CKR(cudaEventRecord(ev0, st));
+    uint32_t launches = 0;
+    if (!bigs.empty()) {
+        CKR(cudaMemsetAsync(d_states, 0, chunks.size() * sizeof(ChunkState), st));
+        prof.begin("k1_varint_stream", big_alg);
+        CKR(launch_k1_varint_stream(batch->d_blob, d_bigs, d_chunks, (uint32_t)chunks.size(), d_states, d_counter + 1, st));
+        prof.end();
+        launches++;
+    }
+    if (n > bigs.size()) {
+        prof.begin("k_decode_tasks", small_alg);
+        CKR(launch_decode_tasks(batch->d_blob, d_tasks, n, reinterpret_cast<uint8_t*>(R->bufs[COVT_BUF_STREAM_ARENA]), d_counter, ctx->sm_count, st));
+        prof.end();
+        launches++;
+    }
+    CKR(cudaEventRecord(ev1, st));
+    if (n) CKR(cudaMemcpyAsync(tasks.data(), d_tasks, (uint64_t)n * sizeof(DeviceTask), cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&R->timing.decode_ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    for (uint32_t i = 0; i < n; i++) {
+        if (descs[i].status != COVT_OK) { descs[i].out_count = 0; continue; }
+        descs[i].status = tasks[i].status;
+        descs[i].bytes_consumed = tasks[i].consumed;
+        if (tasks[i].status != COVT_OK && tasks[i].status != COVT_ERR_VARINT_OVERLONG) descs[i].out_count = 0;
+    }
+    R->timing.h2d_ms = batch->h2d_ms;
+    R->timing.payload_bytes = payload;
+    R->timing.output_bytes = out_bytes;
+    R->timing.kernel_launches = launches;
+    if (prof.on) prof.collect(R->kernel_times);
+    cleanup_tmp();
+#undef CKR
+    *out = R;
+    return COVT_OK;
+}
+
+int32_t covt_decode_streams(covt_ctx* ctx, const uint8_t* blob, uint64_t blob_len, covt_stream_desc* descs, uint32_t n_streams,
+                            uint32_t flags, covt_result** out)
+{
+    uint64_t offs[2] = {0, blob_len};
+    covt_batch* b = nullptr;
+    int32_t rc = covt_batch_upload(ctx, blob, offs, 1, &b);
+    if (rc != COVT_OK) return rc;
+    rc = covt_batch_decode_streams(ctx, b, descs, n_streams, flags, out);
+    covt_batch_free(b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+uint32_t covt_result_num_tiles(const covt_result* res) { return res ? res->n_tiles : 0; }
+uint32_t covt_result_num_layers(const covt_result* res) { return res ? res->n_layers : 0; }
+
+int32_t covt_result_layers(covt_result* res, const covt_layer** layers)
+{
+    if (!res || !layers) return COVT_ERR_INVALID_ARG;
+    covt_ctx* ctx = res->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (!res->h_layers) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        CK(cudaMallocHost(reinterpret_cast<void**>(&res->h_layers), std::max<uint64_t>(res->n_layers, 1) * sizeof(covt_layer)));
+        cudaEventRecord(e0, ctx->stream);
+        if (res->n_layers) CK(cudaMemcpyAsync(res->h_layers, res->d_layers, (uint64_t)res->n_layers * sizeof(covt_layer), cudaMemcpyDeviceToHost, ctx->stream));
+        cudaEventRecord(e1, ctx->stream);
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        res->timing.d2h_ms += ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    *layers = res->h_layers;
+    return COVT_OK;
+}
+
+int32_t covt_result_tile_status(covt_result* res, const uint32_t** status, const uint32_t** first_layer)
+{
+    if (!res) return COVT_ERR_INVALID_ARG;
+    covt_ctx* ctx = res->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (!res->h_tile_status) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        CK(cudaMallocHost(reinterpret_cast<void**>(&res->h_tile_status), ((uint64_t)res->n_tiles + 1) * sizeof(uint32_t)));
+        CK(cudaMallocHost(reinterpret_cast<void**>(&res->h_first_layer), ((uint64_t)res->n_tiles + 2) * sizeof(uint32_t)));
+        cudaEventRecord(e0, ctx->stream);
+        if (res->n_tiles && res->d_tile_status) {
+            CK(cudaMemcpyAsync(res->h_tile_status, res->d_tile_status, (uint64_t)res->n_tiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(res->h_first_layer, res->d_first_layer, ((uint64_t)res->n_tiles + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            res->h_first_layer[0] = 0;
+        }
+        cudaEventRecord(e1, ctx->stream);
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        res->timing.d2h_ms += ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    if (status) *status = res->h_tile_status;
+    if (first_layer) *first_layer = res->h_first_layer;
+    return COVT_OK;
+}
+
+int32_t covt_result_buffer(const covt_result* res, uint32_t which, const void** device_ptr, uint64_t* count, uint32_t* elem_size)
+{
+    if (!res || which >= COVT_NUM_BUFFERS) return COVT_ERR_INVALID_ARG;
+    if (device_ptr) *device_ptr = res->bufs[which];
+    if (count) *count = res->counts[which];
+    if (elem_size) *elem_size = kBufElemSize[which];
+    return COVT_OK;
+}
+
+int32_t covt_result_read(covt_result* res, uint32_t which, uint64_t elem_offset, uint64_t count, void* host_dst)
+{
+    if (!res || which >= COVT_NUM_BUFFERS || (!host_dst && count)) return COVT_ERR_INVALID_ARG;
+    covt_ctx* ctx = res->ctx;
+    if (elem_offset + count > res->counts[which]) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_result_read: range outside the buffer");
+    if (!count) return COVT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t es = kBufElemSize[which];
+    CK(cudaMemcpyAsync(host_dst, reinterpret_cast<const uint8_t*>(res->bufs[which]) + elem_offset * es, count * es, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return COVT_OK;
+}
+
+int32_t covt_result_timing(const covt_result* res, covt_timing* out)
+{
+    if (!res || !out) return COVT_ERR_INVALID_ARG;
+    *out = res->timing;
+    return COVT_OK;
+}
+
+int32_t covt_result_kernel_times(const covt_result* res, covt_kernel_time* out, uint32_t cap, uint32_t* n)
+{
+    if (!res || !n) return COVT_ERR_INVALID_ARG;
+    *n = (uint32_t)res->kernel_times.size();
+    for (uint32_t i = 0; i < cap && i < *n; i++) out[i] = res->kernel_times[i];
+    return COVT_OK;
+}
+
+void covt_result_free(covt_result* res)
+{
+    if (!res) return;
+    covt_ctx* ctx = res->ctx;
+    cudaSetDevice(ctx->device);
+    for (int b = 0; b < COVT_NUM_BUFFERS; b++) dev_free(ctx, res->bufs[b]);
+    dev_free(ctx, res->d_layers);
+    dev_free(ctx, res->d_tile_status);
+    dev_free(ctx, res->d_first_layer);
+    if (res->h_layers) cudaFreeHost(res->h_layers);
+    if (res->h_tile_status) cudaFreeHost(res->h_tile_status);
+    if (res->h_first_layer) cudaFreeHost(res->h_first_layer);
+    delete res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch scheduler helper: contiguous tile ranges balanced by payload bytes (no collective: tiles share nothing)
+// ------------------------------------------------------------------------------------------------
+int32_t covt_partition_tiles(const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t n_parts, uint32_t* starts)
+{
+    if (!tile_offsets || !starts || !n_parts) return COVT_ERR_INVALID_ARG;
+    const uint64_t base = tile_offsets[0], total = tile_offsets[n_tiles] - base;
+    starts[0] = 0;
+    uint32_t t = 0;
+    for (uint32_t p = 1; p < n_parts; p++) {
+        // first tile whose start offset reaches p/n_parts of the bytes
+        const uint64_t target = base + (uint64_t)(((__uint128_t)total * p) / n_parts);
+        while (t < n_tiles && tile_offsets[t] < target) t++;
+        starts[p] = t;
+    }
+    starts[n_parts] = n_tiles;
+    return COVT_OK;
+}
+
+}  // extern "C"

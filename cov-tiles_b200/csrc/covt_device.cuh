@@ -1,0 +1,313 @@
+// covt_device.cuh — device-side building blocks shared by the COVT decode kernels (sm_100a).
+//
+// Everything here is warp-granular: one warp owns one stream (or one 512-byte sub-chunk of a large
+// stream) and moves data with 128-bit coalesced loads; intermediate values live in a warp-private
+// shared-memory stage so that the final global stores are coalesced. No tensor cores: the path is
+// byte/integer work bound by HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/covt_b200.h"
+#include "covt_internal.h"
+
+namespace covt {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARP_CHUNK_BYTES = 512;        // 32 lanes x 16 B
+constexpr int STAGE_WORDS = 512 + 16;        // swizzled index i + (i >> 5), i < 512
+
+// What one decode call has to do; derived from a covt_layer slot or a covt_stream_desc.
+struct StreamTask {
+    const uint8_t* src;    // first payload byte (any alignment)
+    void* dst;             // output slice (16-byte aligned)
+    uint32_t byte_length;  // bytes available to the stream
+    uint32_t num_values;   // values to produce (vertices for the Morton ops)
+    uint8_t op;            // covt_op
+    uint8_t num_bits;      // Morton bits
+    uint8_t no_shift;      // COVT_FLAG_MORTON_NO_SHIFT
+    uint8_t exact_length;  // 1: byte_length is the stream's exact size (container path); 0: an upper bound (DecodingUtils "pos" semantics)
+};
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+struct StreamOutcome {
+    uint32_t status;    // covt_status
+    uint32_t consumed;  // bytes the reference reader would have advanced `pos` by
+};
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// 128-bit streaming load (read-once data: do not allocate in L1)
+__device__ __forceinline__ uint4 ldg_stream128(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream128(void* p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// unaligned little-endian 32-bit load (reads the two aligned words that cover it; buffers are padded)
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p)
+{
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    unsigned s = (unsigned)(a & 3u) * 8u;
+    uint32_t lo = __ldg(w);
+    uint32_t hi = s ? __ldg(w + 1) : 0u;
+    return __funnelshift_r(lo, hi, s);
+}
+// word i of a big-endian serialised int[] that starts at `base` (FastPFOR payloads, DecodingUtils.java:319-327)
+__device__ __forceinline__ uint32_t ld_be_word(const uint8_t* base, uint32_t i)
+{
+    return __byte_perm(ld_u32_unaligned(base + 4ull * i), 0, 0x0123);
+}
+
+__device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, uint32_t& total)
+{
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL, x, d);
+        if (lane_id() >= (unsigned)d) x += y;
+    }
+    total = __shfl_sync(FULL, x, 31);
+    return x - v;
+}
+__device__ __forceinline__ int32_t warp_exclusive_scan_i32(int32_t v, int32_t& total)
+{
+    uint32_t t;
+    uint32_t e = warp_exclusive_scan((uint32_t)v, t);
+    total = (int32_t)t;
+    return (int32_t)e;
+}
+__device__ __forceinline__ uint64_t warp_exclusive_scan_u64(uint64_t v, uint64_t& total)
+{
+    uint64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t y = __shfl_up_sync(FULL, x, d);
+        if (lane_id() >= (unsigned)d) x += y;
+    }
+    total = __shfl_sync(FULL, x, 31);
+    return x - v;
+}
+
+// 4 validity bits -> 4 byte masks
+__device__ __forceinline__ uint32_t nibble_to_bytemask(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xffu; }
+
+__device__ __forceinline__ int32_t zigzag_decode32(uint32_t e) { return (int32_t)((e >> 1) ^ (0u - (e & 1u))); }
+__device__ __forceinline__ int64_t zigzag_decode64(uint64_t e) { return (int64_t)((e >> 1) ^ (0ull - (e & 1ull))); }
+
+// GeometryUtils.decodeMorton (J/converter/GeometryUtils.java:34-47) for num_bits <= 16: gather even bits.
+__device__ __forceinline__ uint32_t compact_even_bits(uint32_t v)
+{
+    v &= 0x55555555u;
+    v = (v | (v >> 1)) & 0x33333333u;
+    v = (v | (v >> 2)) & 0x0f0f0f0fu;
+    v = (v | (v >> 4)) & 0x00ff00ffu;
+    v = (v | (v >> 8)) & 0x0000ffffu;
+    return v;
+}
+// Exact restatement incl. the Java long/int quirks for num_bits > 16 (sign-extended code, 1L << 2i).
+__device__ __forceinline__ int32_t morton_compact_java(int32_t code, uint32_t num_bits)
+{
+    if (num_bits <= 16) return (int32_t)(compact_even_bits((uint32_t)code) & ((1u << num_bits) - 1u));
+    int64_t lc = (int64_t)code;
+    int32_t c = 0;
+    for (uint32_t i = 0; i < num_bits; i++) {
+        int64_t bit = lc & (int64_t)(1ull << ((2 * i) & 63));
+        c = (int32_t)((int64_t)c | (bit >> (i & 63)));
+    }
+    return c;
+}
+__device__ __forceinline__ int2 morton_decode(int32_t code, uint32_t num_bits, bool no_shift)
+{
+    int32_t cx = morton_compact_java(code, num_bits);
+    int32_t cy = morton_compact_java(code >> 1, num_bits);
+    if (no_shift) {  // fixture-era converter: sign-extend the num_bits-bit value (SURVEY §A.6 MORTON_SHIFT)
+        if (num_bits >= 1 && num_bits < 32) {
+            int sh = 32 - (int)num_bits;
+            cx = (int32_t)((uint32_t)cx << sh) >> sh;
+            cy = (int32_t)((uint32_t)cy << sh) >> sh;
+        }
+        return make_int2(cx, cy);
+    }
+    int32_t half = (int32_t)(2u << ((num_bits - 2u) & 31u)) / 2;
+    return make_int2((int32_t)((uint32_t)cx - (uint32_t)half), (int32_t)((uint32_t)cy - (uint32_t)half));
+}
+
+__device__ __forceinline__ uint32_t stage_index(uint32_t i) { return i + (i >> 5); }
+
+// value post-processing selectors (PostKind) live in covt_internal.h: the host picks them for large streams
+
+__device__ __forceinline__ int post_kind_of_op(uint32_t op)
+{
+    switch (op) {
+    case COVT_OP_VARINT_U32: return POST_PLAIN;
+    case COVT_OP_VARINT_ZZ: return POST_ZZ;
+    case COVT_OP_VARINT_ZZ_DELTA: case COVT_OP_PFOR_ZZ_DELTA: return POST_ZZ_DELTA;
+    case COVT_OP_VARINT_ZZ_DELTA_XY: case COVT_OP_PFOR_ZZ_DELTA_XY: return POST_ZZ_DELTA_XY;
+    case COVT_OP_VARINT_DELTA_MORTON: case COVT_OP_PFOR_DELTA_MORTON: return POST_DELTA_MORTON;
+    default: return POST_PLAIN;
+    }
+}
+
+// Running state of a delta chain that is carried from chunk to chunk of one stream.
+struct DeltaCarry {
+    int32_t x, y;       // running sums (x only for single-accumulator ops)
+    uint32_t produced;  // values emitted so far
+};
+
+// -----------------------------------------------------------------------------------------------
+// One 512-byte chunk of 32-bit varints, decoded by one warp.
+//   w          : this lane's 16 bytes as loaded (bytes outside the stream may hold anything)
+//   valid16    : bit j set <=> byte j of this lane's window lies inside the stream
+//   carry_halo : in: the 4 bytes preceding lane 0's window; out: lane 31's last word (next chunk's halo)
+//   limit      : values with chunk-local index >= limit are counted but not staged
+//   VB         : VariableByte convention (MSB SET terminates, up to 5 bytes) instead of
+//                LEB128 with the Java reader's 4-byte cap (DecodingUtils.java:157-186)
+// Stages raw (zigzag-decoded when ZZ) values compacted into stage[]; returns the lane's emit mask, its
+// warp-exclusive count and the chunk total; flags values longer than the Java cap.
+// -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gather_msb16(const uint32_t words[4])
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t m = words[q] & 0x80808080u;
+        uint32_t g = ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+        r |= g << (4 * q);
+    }
+    return r;
+}
+
+template <bool VB, bool ZZ>
+__device__ __forceinline__ void varint32_chunk_decode(uint4 w, uint32_t valid16, uint32_t& carry_halo, uint32_t limit,
+                                                      uint32_t* stage, uint32_t& emit, uint32_t& lane_excl,
+                                                      uint32_t& chunk_total, bool& overlong)
+{
+    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) words[q] &= nibble_to_bytemask((valid16 >> (4 * q)) & 0xfu);
+    const uint32_t msb16 = gather_msb16(words);
+    emit = (VB ? msb16 : (~msb16 & 0xffffu)) & valid16;
+    uint32_t halo = __shfl_up_sync(FULL, words[3], 1);
+    if (lane_id() == 0) halo = carry_halo;
+    carry_halo = __shfl_sync(FULL, words[3], 31);
+
+    uint32_t cnt = __popc(emit);
+    lane_excl = warp_exclusive_scan(cnt, chunk_total);
+
+    // carry-in from the halo: k trailing continuation bytes
+    const uint32_t hcont = VB ? (~halo & 0x80808080u) : (halo & 0x80808080u);
+    const uint32_t hterm = hcont ^ 0x80808080u;
+    const uint32_t k = hterm ? (uint32_t)(__clz(hterm) >> 3) : 4u;
+    uint32_t acc = 0, shift = 0;
+    if (k) {
+        uint32_t hv = k >= 4 ? halo : (halo >> (8u * (4u - k)));
+        acc = (hv & 0x7fu) | ((hv >> 1) & 0x3f80u) | ((hv >> 2) & 0x1fc000u) | ((hv >> 3) & 0x0fe00000u);
+        if (k < 4) acc &= (1u << (7u * k)) - 1u;
+        shift = 7u * k;
+    }
+    if (!VB) {
+        // Java cap: a value may not have 4 continuation bytes. Look at halo bytes 1..3 + the 16 window bytes.
+        const uint32_t h3 = ((hcont >> 15) & 1u) | ((hcont >> 22) & 2u) | ((hcont >> 29) & 4u);
+        const uint32_t c19 = h3 | (msb16 << 3);
+        if (c19 & (c19 >> 1) & (c19 >> 2) & (c19 >> 3)) overlong = true;
+    }
+    uint32_t idx = lane_excl;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        acc |= (b & 0x7fu) << (shift & 31u);
+        const bool cont = VB ? !(b & 0x80u) : (b & 0x80u) != 0;
+        if (cont) {
+            shift += 7;
+        } else {
+            if ((emit >> j) & 1u) {
+                if (idx < limit) stage[stage_index(idx)] = ZZ ? (uint32_t)zigzag_decode32(acc) : acc;
+                idx++;
+            }
+            acc = 0;
+            shift = 0;
+        }
+    }
+}
+
+// Blocked delta pass over the values staged by varint32_chunk_decode / the FastPFOR unpacker:
+// stage[0..n) holds deltas; on return it holds final values. carry is advanced.
+// PER = values per lane (16 for a 512-value chunk, 8 for a FastPFOR block of 256).
+// ZZ_AT_LOAD: the staged values are still zigzag-encoded (FastPFOR path, DecodingUtils.java:335-343).
+template <int POST, int PER, bool ZZ_AT_LOAD>
+__device__ __forceinline__ void warp_delta_pass(uint32_t* stage, uint32_t n, DeltaCarry& carry)
+{
+    if (POST == POST_PLAIN || POST == POST_ZZ) return;
+    const unsigned lane = lane_id();
+    int32_t v[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        uint32_t i = lane * PER + j;
+        uint32_t raw = i < n ? stage[stage_index(i)] : 0u;
+        v[j] = ZZ_AT_LOAD ? zigzag_decode32(raw) : (int32_t)raw;
+    }
+    if (POST == POST_ZZ_DELTA_XY) {
+        // global index parity of position i is (produced + j) & 1 because lane*PER is even
+        const bool swap = carry.produced & 1u;
+        int32_t a = 0, b = 0;  // a: even j, b: odd j
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            if (j & 1) b += v[j]; else a += v[j];
+        }
+        int32_t ta, tb;
+        int32_t ea = warp_exclusive_scan_i32(a, ta);
+        int32_t eb = warp_exclusive_scan_i32(b, tb);
+        int32_t pa = ea + (swap ? carry.y : carry.x);
+        int32_t pb = eb + (swap ? carry.x : carry.y);
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            uint32_t i = lane * PER + j;
+            if (j & 1) { pb += v[j]; v[j] = pb; } else { pa += v[j]; v[j] = pa; }
+            if (i < n) stage[stage_index(i)] = (uint32_t)v[j];
+        }
+        if (swap) { carry.y += ta; carry.x += tb; } else { carry.x += ta; carry.y += tb; }
+    } else {
+        int32_t a = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) a += v[j];
+        int32_t ta;
+        int32_t pa = warp_exclusive_scan_i32(a, ta) + carry.x;
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            uint32_t i = lane * PER + j;
+            pa += v[j];
+            if (i < n) stage[stage_index(i)] = (uint32_t)pa;
+        }
+        carry.x += ta;
+    }
+}
+
+// Coalesced copy of stage[0..n) to dst[first ..] (Morton: expands each code to an (x,y) pair).
+template <int POST, int PER>
+__device__ __forceinline__ void warp_copy_out(const uint32_t* stage, uint32_t n, int32_t* dst, uint64_t first,
+                                              uint32_t num_bits, bool no_shift)
+{
+    const unsigned lane = lane_id();
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        uint32_t i = lane + 32u * k;
+        if (i < n) {
+            uint32_t val = stage[stage_index(i)];
+            if (POST == POST_DELTA_MORTON) {
+                int2 xy = morton_decode((int32_t)val, num_bits, no_shift);
+                reinterpret_cast<int2*>(dst)[first + i] = xy;
+            } else {
+                dst[first + i] = (int32_t)val;
+            }
+        }
+    }
+}
+
+}  // namespace covt

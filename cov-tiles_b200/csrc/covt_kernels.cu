@@ -1,0 +1,890 @@
+// covt_kernels.cu — the sm_100a kernels of the COVT batch decoder and their launchers.
+//
+//   k0_scan_tiles / k0_fill_layers : device-side container walk (gen-2b, gen-3) -> covt_layer table
+//                                    (CovtParser.decodeLayerMetadata, J/decoder/CovtParser.java:574-652)
+//   scan_*                         : result layout = exclusive prefix sums of 16-byte-rounded slice sizes
+//   k_decode_layers                : one warp per layer: every stream of the layer, then the assembler
+//                                    (CovtParser.decodeGeometryColumn :392-511, decodedIds :552-572, convertGeometryColumn :135-274)
+//   k_decode_tasks                 : one warp per stream request (the static codecs of DecodingUtils.java)
+//   k1_varint_stream               : multi-CTA single-pass decode of one large varint stream with a decoupled
+//                                    look-back over (count, sumEven, sumOdd) (DecodingUtils.java:55-112,394-409)
+//   k_finalize                     : per-tile status + totals
+#include "covt_assemble.cuh"
+#include "covt_internal.h"
+#include "covt_streams.cuh"
+
+namespace covt {
+
+// =================================================================================================
+// result layout (DESIGN.md "result layout"): slice sizes of one layer in every result buffer
+// =================================================================================================
+__host__ __device__ inline uint32_t kBufElemSizeDev(int b)
+{
+    return (b == COVT_BUF_S_GEOMETRY_TYPES || b == COVT_BUF_STREAM_ARENA) ? 1u : (b == COVT_BUF_S_IDS ? 8u : 4u);
+}
+__host__ __device__ inline uint64_t align_elems(uint64_t n, uint32_t elem_size)
+{
+    uint64_t per = 16 / elem_size;
+    return (n + per - 1) / per * per;
+}
+
+__device__ __forceinline__ uint64_t slot_nv(const covt_layer& L, int slot)
+{
+    return L.streams[slot].encoding == COVT_ENC_ABSENT ? 0ull : (uint64_t)L.streams[slot].num_values;
+}
+__device__ __forceinline__ uint64_t vbuf_ints_of(const covt_layer& L, uint32_t flags)
+{
+    uint64_t n = slot_nv(L, COVT_SLOT_VBUF);
+    if (L.geom_column_type == COVT_CT_ICE_MORTON_CODE) n *= 2;
+    else if (L.geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) n *= 2;
+    return n;
+}
+
+__device__ void layer_slice_sizes(covt_layer& L, uint32_t flags, uint64_t sz[COVT_NUM_BUFFERS])
+{
+    for (int b = 0; b < COVT_NUM_BUFFERS; b++) sz[b] = 0;
+    if (L.status == COVT_ERR_BAD_METADATA) return;
+    const uint64_t F = slot_nv(L, COVT_SLOT_TYPES);
+    sz[COVT_BUF_S_GEOMETRY_TYPES] = F;
+    sz[COVT_BUF_S_IDS] = slot_nv(L, COVT_SLOT_ID);
+    sz[COVT_BUF_S_GEOMETRY_OFFSETS] = slot_nv(L, COVT_SLOT_GEOM);
+    sz[COVT_BUF_S_PART_OFFSETS] = slot_nv(L, COVT_SLOT_PART);
+    sz[COVT_BUF_S_RING_OFFSETS] = slot_nv(L, COVT_SLOT_RING);
+    sz[COVT_BUF_S_VERTEX_OFFSETS] = slot_nv(L, COVT_SLOT_VOFF);
+    const uint64_t vb_ints = vbuf_ints_of(L, flags);
+    sz[COVT_BUF_S_VERTEX_BUFFER] = vb_ints;
+    sz[COVT_BUF_S_INDEX_BUFFER] = slot_nv(L, COVT_SLOT_INDEX);
+    if (!(flags & COVT_FLAG_SKIP_ASSEMBLY)) {
+        const uint64_t V = L.streams[COVT_SLOT_VOFF].encoding != COVT_ENC_ABSENT ? slot_nv(L, COVT_SLOT_VOFF) : vb_ints / 2;
+        const uint64_t cap_parts = F + slot_nv(L, COVT_SLOT_PART);
+        const uint64_t cap_rings = cap_parts + slot_nv(L, COVT_SLOT_RING);
+        L.cap_parts = (uint32_t)cap_parts;
+        L.cap_rings = (uint32_t)cap_rings;
+        sz[COVT_BUF_A_GEOM_OFFSETS] = F + 1;
+        sz[COVT_BUF_A_PART_OFFSETS] = cap_parts + 1;
+        sz[COVT_BUF_A_RING_OFFSETS] = cap_rings + 1;
+        sz[COVT_BUF_A_COORDS] = 2 * (V + ((flags & COVT_FLAG_CLOSE_RINGS) ? slot_nv(L, COVT_SLOT_RING) : 0));
+    }
+}
+
+// dispatch table of CovtParser.decodeGeometryColumn (:405-510) and decodedIds (:552-572), SURVEY §8a
+__host__ __device__ inline uint32_t resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags)
+{
+    switch (stream_type) {
+    case COVT_ST_GEOMETRY_TYPES: return COVT_OP_BYTE_RLE;  // always Byte-RLE whatever the label (:405-406)
+    case COVT_ST_GEOMETRY_OFFSETS: case COVT_ST_PART_OFFSETS: case COVT_ST_RING_OFFSETS:
+        if (encoding == COVT_ENC_RLE) return COVT_OP_RLE_U32;
+        if (encoding == COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_OP_PFOR_ZZ_DELTA;
+        return COVT_OP_NONE;
+    case COVT_ST_VERTEX_OFFSETS: case COVT_ST_INDEX_BUFFER:
+        if (encoding == COVT_ENC_VARINT_DELTA_ZIG_ZAG) return COVT_OP_VARINT_ZZ_DELTA;
+        if (encoding == COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_OP_PFOR_ZZ_DELTA;
+        return COVT_OP_NONE;
+    case COVT_ST_VERTEX_BUFFER:
+        if (column_type == COVT_CT_ICE_MORTON_CODE) {
+            if (encoding == COVT_ENC_VARINT_DELTA_ZIG_ZAG) return COVT_OP_VARINT_DELTA_MORTON;
+            if (encoding == COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_OP_PFOR_DELTA_MORTON;
+            return COVT_OP_NONE;
+        }
+        if (encoding == COVT_ENC_VARINT_DELTA_ZIG_ZAG) return COVT_OP_VARINT_ZZ_DELTA_XY;
+        if (encoding == COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_OP_PFOR_ZZ_DELTA_XY;
+        return COVT_OP_NONE;
+    case COVT_ST_DATA:
+        if (encoding == COVT_ENC_RLE) return COVT_OP_RLE_U64;
+        if (encoding == COVT_ENC_VARINT) return (flags & COVT_FLAG_ID_WIDTH_32) ? COVT_OP_VARINT_U32_AS_I64 : COVT_OP_VARINT_U64;
+        if (encoding == COVT_ENC_VARINT_DELTA_ZIG_ZAG) {
+            if (flags & COVT_FLAG_ID_DVZZ_IS_RLE) return COVT_OP_RLE_U64;
+            return (flags & COVT_FLAG_ID_WIDTH_32) ? COVT_OP_VARINT_ZZ_DELTA_AS_I64 : COVT_OP_VARINT_ZZ_DELTA_64;
+        }
+        return COVT_OP_NONE;
+    default: return COVT_OP_NONE;
+    }
+}
+uint32_t host_resolve_op(uint32_t st, uint32_t enc, uint32_t ct, uint32_t flags) { return resolve_op(st, enc, ct, flags); }
+
+// =================================================================================================
+// K0: container walk, one thread per tile
+// =================================================================================================
+struct Cursor { const uint8_t* b; uint64_t p, end; bool err; };
+
+// DecodingUtils.decodeVarint (DecodingUtils.java:157-186): at most 4 bytes
+__device__ uint32_t c_varint(Cursor& c)
+{
+    uint32_t v = 0;
+    for (int i = 0; i < 4; i++) {
+        if (c.p >= c.end) { c.err = true; return 0; }
+        uint32_t b = c.b[c.p++];
+        v |= (b & 0x7fu) << (7 * i);
+        if (!(b & 0x80u)) break;
+    }
+    return v;
+}
+__device__ uint32_t c_byte(Cursor& c)
+{
+    if (c.p >= c.end) { c.err = true; return 0; }
+    return c.b[c.p++];
+}
+// DecodingUtils.decodeString (:21-26)
+__device__ void c_string(Cursor& c, uint64_t& off, uint32_t& len)
+{
+    uint32_t n = c_varint(c);
+    if (c.err || c.p + n > c.end) { c.err = true; off = 0; len = 0; return; }
+    off = c.p;
+    len = n;
+    c.p += n;
+}
+template <int N>
+__device__ bool name_is(const uint8_t* b, uint64_t off, uint32_t len, const char (&lit)[N])
+{
+    if (len != N - 1) return false;
+    for (int i = 0; i < N - 1; i++)
+        if (b[off + i] != (uint8_t)lit[i]) return false;
+    return true;
+}
+
+__device__ void layer_init(covt_layer& L, uint32_t tile, uint32_t idx)
+{
+    uint32_t* w = reinterpret_cast<uint32_t*>(&L);
+    for (unsigned i = 0; i < sizeof(covt_layer) / 4; i++) w[i] = 0;
+    L.tile = tile;
+    L.layer_index = idx;
+    for (int s = 0; s < COVT_NUM_SLOTS; s++) L.streams[s].encoding = COVT_ENC_ABSENT;
+}
+
+__constant__ uint8_t c_slot_stream_type[COVT_NUM_SLOTS] = {
+    COVT_ST_DATA, COVT_ST_GEOMETRY_TYPES, COVT_ST_GEOMETRY_OFFSETS, COVT_ST_PART_OFFSETS,
+    COVT_ST_RING_OFFSETS, COVT_ST_VERTEX_OFFSETS, COVT_ST_VERTEX_BUFFER, COVT_ST_INDEX_BUFFER};
+
+// payload order is fixed (CovtParser.java:405-510): [id] | types, geometry_offsets, part_offsets, ring_offsets,
+// vertex_offsets, vertex_buffer [, index_buffer]
+__device__ uint64_t layer_place_streams(covt_layer& L, uint64_t payload, uint32_t flags)
+{
+    for (int s = 0; s < COVT_NUM_SLOTS; s++) {
+        covt_stream_ref& r = L.streams[s];
+        if (r.encoding == COVT_ENC_ABSENT) continue;
+        r.byte_offset = payload;
+        payload += r.byte_length;
+        r.op = (uint8_t)resolve_op(c_slot_stream_type[s], r.encoding, L.geom_column_type, flags);
+        if (r.op == COVT_OP_NONE) {
+            r.status = COVT_ERR_UNSUPPORTED_ENCODING;
+            if (!L.status) L.status = COVT_ERR_UNSUPPORTED_ENCODING;
+        }
+    }
+    return payload;
+}
+
+// gen-2b. on_layer(L) is called for every complete layer. Returns the tile status.
+template <class OnLayer>
+__device__ uint32_t walk_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, uint32_t flags, uint32_t tile, OnLayer&& on_layer)
+{
+    Cursor c = {blob, begin, end, false};
+    (void)c_varint(c);  // version
+    const uint32_t num_layers = c_varint(c);
+    if (c.err) return COVT_ERR_TRUNCATED;
+    __align__(16) covt_layer L;
+    for (uint32_t li = 0; li < num_layers; li++) {
+        layer_init(L, tile, li);
+        c_string(c, L.name_offset, L.name_length);
+        L.extent = c_varint(c);
+        L.num_features = c_varint(c);
+        L.num_columns = c_varint(c);
+        if (c.err) return COVT_ERR_TRUNCATED;
+        L.num_bits = (uint8_t)(32 - __clz(L.extent));
+        uint64_t property_bytes = 0;
+        bool have_geometry = false;
+        for (uint32_t ci = 0; ci < L.num_columns; ci++) {
+            uint64_t noff; uint32_t nlen;
+            c_string(c, noff, nlen);
+            (void)c_byte(c);  // gen-2 data type
+            const uint32_t column_type = c_byte(c);
+            const uint32_t num_streams = c_varint(c);
+            if (c.err) return COVT_ERR_TRUNCATED;
+            const bool is_id = name_is(blob, noff, nlen, "id");
+            const bool is_geom = name_is(blob, noff, nlen, "geometry");
+            if (ci == 0 && !is_id && !is_geom) return COVT_ERR_BAD_METADATA;  // CovtParser.java:67-69
+            if (is_geom) { L.geom_column_type = (uint8_t)column_type; have_geometry = true; }
+            if (is_geom && column_type > COVT_CT_ICE_MORTON_CODE) return COVT_ERR_BAD_METADATA;
+            for (uint32_t si = 0; si < num_streams; si++) {
+                uint64_t soff; uint32_t slen;
+                c_string(c, soff, slen);
+                const uint32_t nv = c_varint(c);
+                const uint32_t bl = c_varint(c);
+                const uint32_t enc = c_byte(c);
+                if (c.err) return COVT_ERR_TRUNCATED;
+                int slot = -1;
+                if (is_id) { if (name_is(blob, soff, slen, "data")) slot = COVT_SLOT_ID; }
+                else if (is_geom) {
+                    if (name_is(blob, soff, slen, "geometry_types")) slot = COVT_SLOT_TYPES;
+                    else if (name_is(blob, soff, slen, "geometry_offsets")) slot = COVT_SLOT_GEOM;
+                    else if (name_is(blob, soff, slen, "part_offsets")) slot = COVT_SLOT_PART;
+                    else if (name_is(blob, soff, slen, "ring_offsets")) slot = COVT_SLOT_RING;
+                    else if (name_is(blob, soff, slen, "vertex_offsets")) slot = COVT_SLOT_VOFF;
+                    else if (name_is(blob, soff, slen, "vertex_buffer")) slot = COVT_SLOT_VBUF;
+                    else if (name_is(blob, soff, slen, "index_buffer")) slot = COVT_SLOT_INDEX;
+                }
+                if (slot >= 0) {
+                    if (enc > COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_ERR_BAD_METADATA;
+                    L.streams[slot].num_values = nv;
+                    L.streams[slot].byte_length = bl;
+                    L.streams[slot].encoding = (uint8_t)enc;
+                    if (slot == COVT_SLOT_ID) L.has_id = 1;
+                } else if (is_id || is_geom) {
+                    return COVT_ERR_BAD_METADATA;
+                } else {
+                    property_bytes += bl;
+                }
+            }
+        }
+        if (!have_geometry || L.streams[COVT_SLOT_TYPES].encoding == COVT_ENC_ABSENT ||
+            L.streams[COVT_SLOT_VBUF].encoding == COVT_ENC_ABSENT)
+            return COVT_ERR_BAD_METADATA;
+        const uint64_t payload_end = layer_place_streams(L, c.p, flags) + property_bytes;
+        if (payload_end > end) return COVT_ERR_TRUNCATED;
+        c.p = payload_end;
+        on_layer(L);
+    }
+    return c.p == end ? COVT_OK : COVT_ERR_TRUNCATED;
+}
+
+// bytes of a Byte-RLE stream that decodes to n bytes: unlisted PRESENT streams of gen-3 property columns
+// (CovtConverter.java:434-436, DecodingUtils.java:290-306)
+__device__ bool byte_rle_span(const uint8_t* b, uint64_t& p, uint64_t end, uint32_t n)
+{
+    uint32_t done = 0;
+    while (done < n) {
+        if (p >= end) return false;
+        const uint32_t c = b[p++];
+        if (c < 0x80u) { done += c + 3u; p += 1; }
+        else { done += 256u - c; p += 256u - c; }
+        if (p > end) return false;
+    }
+    return true;
+}
+
+// gen-3 = CovtParser.decodeLayerMetadata (CovtParser.java:574-652); no tile header, loop until EOF (:56)
+template <class OnLayer>
+__device__ uint32_t walk_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, const uint32_t* tj_fields, uint32_t tj_layers,
+                              uint32_t flags, uint32_t tile, OnLayer&& on_layer)
+{
+    Cursor c = {blob, begin, end, false};
+    __align__(16) covt_layer L;
+    uint32_t li = 0;
+    while (c.p < end) {
+        layer_init(L, tile, li);
+        const uint32_t header = c_byte(c);
+        const bool optimized = header & 1u;  // :575-578
+        uint32_t n_fields = 0;
+        if (optimized) {
+            const uint32_t layer_id = c_varint(c);  // :584-589
+            if (c.err) return COVT_ERR_TRUNCATED;
+            if (!tj_fields || layer_id >= tj_layers) return COVT_ERR_BAD_METADATA;
+            n_fields = tj_fields[layer_id];
+            L.name_offset = layer_id;
+            L.name_length = 0;
+        } else {
+            c_string(c, L.name_offset, L.name_length);  // :592
+        }
+        L.extent = c_varint(c);  // :595-598
+        L.num_features = c_varint(c);
+        L.num_columns = c_varint(c);
+        if (c.err) return COVT_ERR_TRUNCATED;
+        L.num_bits = (uint8_t)(32 - __clz(L.extent));  // CovtParser.java:77
+        // property columns: their payload follows the geometry payload; remember how to hop over it.
+        // Walked twice (metadata now, payload sizes after the geometry streams are placed), so keep a cursor.
+        uint64_t prop_listed_total = 0;     // listed stream bytes of all property columns
+        uint32_t n_present_streams = 0;     // columns with an unlisted Byte-RLE present stream, in order
+        uint64_t present_mask_lo = 0;       // bit k set: k-th property column is BOOLEAN (no present stream); first 64 columns
+        uint64_t prop_listed[8];            // per-column listed bytes for the first 8 property columns (interleaving matters)
+        uint32_t n_props = 0;
+        bool have_geometry = false;
+        for (uint32_t ci = 0; ci < L.num_columns; ci++) {
+            bool is_id = false, is_geom = false;
+            if (optimized || ci == 0) {  // :604-614
+                const uint32_t column_id = c_varint(c);
+                if (column_id > 1) {
+                    if (!optimized || column_id - 2 >= n_fields) return COVT_ERR_BAD_METADATA;
+                } else if (column_id == 0) is_id = true;
+                else is_geom = true;
+            } else {
+                uint64_t noff; uint32_t nlen;
+                c_string(c, noff, nlen);  // :616
+                if (!c.err) { is_id = name_is(blob, noff, nlen, "id"); is_geom = name_is(blob, noff, nlen, "geometry"); }
+            }
+            const uint32_t column_desc = c_byte(c);  // :619-624
+            if (c.err) return COVT_ERR_TRUNCATED;
+            const uint32_t data_type = (column_desc >> 3) & 0xFu;
+            const uint32_t column_type = column_desc & 0x7u;
+            if (column_type > COVT_CT_ICE_MORTON_CODE) return COVT_ERR_BAD_METADATA;
+            if (ci == 0 && !is_id && !is_geom) return COVT_ERR_BAD_METADATA;  // :67-69
+            if (is_geom) { L.geom_column_type = (uint8_t)column_type; have_geometry = true; }
+            uint64_t listed = 0;
+            for (;;) {  // :628-648
+                const uint32_t stream_desc = c_byte(c);
+                const uint32_t stream_type = stream_desc >> 4;
+                const uint32_t enc = stream_desc & 0xFu;
+                const uint32_t nv = c_varint(c);
+                const uint32_t bl = c_varint(c);
+                if (c.err) return COVT_ERR_TRUNCATED;
+                if (stream_type > COVT_ST_INDEX_BUFFER || enc > COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_ERR_BAD_METADATA;
+                int slot = -1;
+                if (is_id && stream_type == COVT_ST_DATA) slot = COVT_SLOT_ID;
+                else if (is_geom && stream_type >= COVT_ST_GEOMETRY_TYPES && stream_type <= COVT_ST_VERTEX_BUFFER)
+                    slot = COVT_SLOT_TYPES + (int)(stream_type - COVT_ST_GEOMETRY_TYPES);
+                else if (is_geom && stream_type == COVT_ST_INDEX_BUFFER) slot = COVT_SLOT_INDEX;
+                if (slot >= 0) {
+                    L.streams[slot].num_values = nv;
+                    L.streams[slot].byte_length = bl;
+                    L.streams[slot].encoding = (uint8_t)enc;
+                    if (slot == COVT_SLOT_ID) L.has_id = 1;
+                } else if (is_id || is_geom) return COVT_ERR_BAD_METADATA;
+                else listed += bl;
+                if (data_type == COVT_DT_GEOMETRY && stream_type == COVT_ST_VERTEX_BUFFER) break;  // :639-647
+                else if (stream_type == COVT_ST_DATA && column_type == COVT_CT_PLAIN) break;
+                else if (stream_type == COVT_ST_DICTIONARY) break;
+            }
+            if (!is_id && !is_geom) {
+                if (n_props < 8) prop_listed[n_props] = listed;
+                else return COVT_ERR_BAD_METADATA;  // more than 8 property columns: see DESIGN.md (property columns are "next")
+                if (data_type == COVT_DT_BOOLEAN && n_props < 64) present_mask_lo |= 1ull << n_props;
+                else n_present_streams++;
+                prop_listed_total += listed;
+                n_props++;
+            }
+        }
+        if (!have_geometry || L.streams[COVT_SLOT_TYPES].encoding == COVT_ENC_ABSENT ||
+            L.streams[COVT_SLOT_VBUF].encoding == COVT_ENC_ABSENT)
+            return COVT_ERR_BAD_METADATA;
+        uint64_t p = layer_place_streams(L, c.p, flags);
+        if (p > end) return COVT_ERR_TRUNCATED;
+        // hop over property columns: BOOLEAN = listed data only (CovtParser.java:280-290); others = unlisted Byte-RLE
+        // present stream of ceil(numFeatures/8) bytes (:295) followed by their listed streams
+        for (uint32_t k = 0; k < n_props; k++) {
+            if (!((present_mask_lo >> k) & 1ull)) {
+                if (!byte_rle_span(blob, p, end, (L.num_features + 7u) / 8u)) return COVT_ERR_TRUNCATED;
+            }
+            p += prop_listed[k];
+            if (p > end) return COVT_ERR_TRUNCATED;
+        }
+        (void)prop_listed_total; (void)n_present_streams;
+        c.p = p;
+        on_layer(L);
+        li++;
+    }
+    return COVT_OK;
+}
+
+template <class OnLayer>
+__device__ uint32_t walk_tile(const uint8_t* blob, uint64_t begin, uint64_t end, uint32_t container, const uint32_t* tj_fields,
+                              uint32_t tj_layers, uint32_t flags, uint32_t tile, OnLayer&& on_layer)
+{
+    if (container == COVT_CONTAINER_GEN2B) return walk_gen2b(blob, begin, end, flags, tile, on_layer);
+    return walk_gen3(blob, begin, end, tj_fields, tj_layers, flags, tile, on_layer);
+}
+
+// pass 1: layers per tile + slice sizes per result buffer (column-major: col * n_tiles + tile)
+__global__ void k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                              const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols,
+                              uint32_t* tile_status)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint64_t acc[TILE_COLS];
+    for (int i = 0; i < TILE_COLS; i++) acc[i] = 0;
+    const uint32_t st = walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, flags, t,
+                                  [&](covt_layer& L) {
+                                      uint64_t sz[COVT_NUM_BUFFERS];
+                                      layer_slice_sizes(L, flags, sz);
+                                      acc[0] += 1;
+                                      for (int b = 0; b < COVT_NUM_BUFFERS; b++) acc[1 + b] += align_elems(sz[b], kBufElemSizeDev(b));
+                                  });
+    tile_status[t] = st;
+    for (int i = 0; i < TILE_COLS; i++) tile_cols[(uint64_t)i * n_tiles + t] = acc[i];
+}
+
+// pass 2: write the covt_layer table with result offsets (tile_cols now holds exclusive prefixes)
+__global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                               const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
+                               covt_layer* layers, uint32_t* first_layer)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint64_t run[TILE_COLS];
+    for (int i = 0; i < TILE_COLS; i++) run[i] = tile_cols[(uint64_t)i * n_tiles + t];
+    first_layer[t] = (uint32_t)run[0];
+    walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, flags, t, [&](covt_layer& L) {
+        uint64_t sz[COVT_NUM_BUFFERS];
+        layer_slice_sizes(L, flags, sz);
+        for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
+            L.out[b] = run[1 + b];
+            run[1 + b] += align_elems(sz[b], kBufElemSizeDev(b));
+        }
+        // coalescing does not matter here: 368 B per layer, written once
+        uint4* dst = reinterpret_cast<uint4*>(&layers[run[0]]);
+        const uint4* src = reinterpret_cast<const uint4*>(&L);
+        for (unsigned i = 0; i < sizeof(covt_layer) / 16; i++) dst[i] = src[i];
+        run[0] += 1;
+    });
+}
+
+// =================================================================================================
+// exclusive scan of the TILE_COLS columns over tiles (three small kernels)
+// =================================================================================================
+constexpr int SCAN_BLOCK = 256;
+
+__device__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* total, uint64_t* sm /*[SCAN_BLOCK/32]*/)
+{
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint64_t wt;
+    uint64_t e = warp_exclusive_scan_u64(v, wt);
+    if (lane == 31) sm[warp] = wt;
+    __syncthreads();
+    uint64_t base = 0, tot = 0;
+    for (unsigned w = 0; w < SCAN_BLOCK / 32; w++) {
+        if (w < warp) base += sm[w];
+        tot += sm[w];
+    }
+    __syncthreads();
+    *total = tot;
+    return e + base;
+}
+
+__global__ void scan_block_sums(const uint64_t* cols, uint32_t n, uint64_t* block_sums)
+{
+    __shared__ uint64_t sm[SCAN_BLOCK / 32];
+    const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t col = blockIdx.y;
+    uint64_t v = i < n ? cols[(uint64_t)col * n + i] : 0;
+    uint64_t tot;
+    block_exclusive_scan_u64(v, &tot, sm);
+    if (threadIdx.x == 0) block_sums[(uint64_t)col * gridDim.x + blockIdx.x] = tot;
+}
+// one block per column walks the block sums
+__global__ void scan_block_prefix(uint64_t* block_sums, uint32_t n_blocks, uint64_t* totals)
+{
+    __shared__ uint64_t sm[SCAN_BLOCK / 32];
+    const uint32_t col = blockIdx.x;
+    uint64_t running = 0;
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += SCAN_BLOCK) {
+        const uint32_t b = b0 + threadIdx.x;
+        uint64_t v = b < n_blocks ? block_sums[(uint64_t)col * n_blocks + b] : 0;
+        uint64_t tot;
+        uint64_t e = block_exclusive_scan_u64(v, &tot, sm);
+        if (b < n_blocks) block_sums[(uint64_t)col * n_blocks + b] = running + e;
+        running += tot;
+    }
+    if (threadIdx.x == 0) totals[col] = running;
+}
+__global__ void scan_apply(uint64_t* cols, uint32_t n, const uint64_t* block_sums)
+{
+    __shared__ uint64_t sm[SCAN_BLOCK / 32];
+    const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t col = blockIdx.y;
+    uint64_t v = i < n ? cols[(uint64_t)col * n + i] : 0;
+    uint64_t tot;
+    uint64_t e = block_exclusive_scan_u64(v, &tot, sm);
+    if (i < n) cols[(uint64_t)col * n + i] = e + block_sums[(uint64_t)col * gridDim.x + blockIdx.x];
+}
+
+// =================================================================================================
+// one warp per layer: all streams, then the assembler
+// =================================================================================================
+constexpr int LAYER_WARPS = 4;
+constexpr int LAYER_WARP_SMEM = WARP_SMEM_BYTES + 384;  // stage + a private copy of the covt_layer (368 B)
+
+__device__ __forceinline__ uint32_t warp_next_work(uint32_t* counter)
+{
+    uint32_t v = 0;
+    if (lane_id() == 0) v = atomicAdd(counter, 1u);
+    return __shfl_sync(FULL, v, 0);
+}
+
+__global__ void __launch_bounds__(LAYER_WARPS * 32)
+k_decode_layers(const uint8_t* blob, covt_layer* layers, uint32_t n_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    uint8_t* wsm = smem + warp * LAYER_WARP_SMEM;
+    covt_layer* L = reinterpret_cast<covt_layer*>(wsm + WARP_SMEM_BYTES);
+    const uint8_t slot_buf[COVT_NUM_SLOTS] = {COVT_BUF_S_IDS, COVT_BUF_S_GEOMETRY_TYPES, COVT_BUF_S_GEOMETRY_OFFSETS,
+                                              COVT_BUF_S_PART_OFFSETS, COVT_BUF_S_RING_OFFSETS, COVT_BUF_S_VERTEX_OFFSETS,
+                                              COVT_BUF_S_VERTEX_BUFFER, COVT_BUF_S_INDEX_BUFFER};
+    for (;;) {
+        const uint32_t l = warp_next_work(work_counter);
+        if (l >= n_layers) break;
+        // private copy of the layer record (23 x 16 B)
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(&layers[l]);
+            uint4* dst = reinterpret_cast<uint4*>(L);
+            if (lane < sizeof(covt_layer) / 16) dst[lane] = src[lane];
+        }
+        __syncwarp();
+        uint32_t layer_status = L->status;
+        if (layer_status == COVT_ERR_BAD_METADATA) continue;
+        void* dst[COVT_NUM_SLOTS];
+#pragma unroll
+        for (int s = 0; s < COVT_NUM_SLOTS; s++) {
+            dst[s] = nullptr;
+            const covt_stream_ref r = L->streams[s];
+            if (r.encoding == COVT_ENC_ABSENT) continue;
+            const uint32_t b = slot_buf[s];
+            dst[s] = reinterpret_cast<uint8_t*>(bufs.ptr[b]) + L->out[b] * kBufElemSizeDev(b);
+            if (r.op == COVT_OP_NONE) continue;
+            StreamTask t;
+            t.src = blob + r.byte_offset;
+            t.dst = dst[s];
+            t.byte_length = r.byte_length;
+            t.num_values = r.num_values;
+            if (s == COVT_SLOT_VBUF && L->geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) t.num_values *= 2;
+            t.op = r.op;
+            t.num_bits = L->num_bits;
+            t.no_shift = (flags & COVT_FLAG_MORTON_NO_SHIFT) ? 1 : 0;
+            t.exact_length = 1;
+            StreamOutcome o;
+            warp_decode_stream(t, wsm, o);
+            __syncwarp();
+            if (lane == 0) layers[l].streams[s].status = o.status;
+            if (o.status != COVT_OK && !layer_status) layer_status = o.status;
+        }
+        AsmResult ar = {COVT_OK, 0, 0, 0, 0};
+        if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && layer_status == COVT_OK) {
+            LayerIO io;
+            io.types = reinterpret_cast<const uint8_t*>(dst[COVT_SLOT_TYPES]);
+            io.F = L->streams[COVT_SLOT_TYPES].num_values;
+            io.geom = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_GEOM]);
+            io.n_geom = io.geom ? L->streams[COVT_SLOT_GEOM].num_values : 0;
+            io.part = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_PART]);
+            io.n_part = io.part ? L->streams[COVT_SLOT_PART].num_values : 0;
+            io.ring = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_RING]);
+            io.n_ring = io.ring ? L->streams[COVT_SLOT_RING].num_values : 0;
+            io.voff = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_VOFF]);
+            io.n_voff = io.voff ? L->streams[COVT_SLOT_VOFF].num_values : 0;
+            io.vbuf = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_VBUF]);
+            uint64_t vb_ints = L->streams[COVT_SLOT_VBUF].num_values;
+            if (L->geom_column_type == COVT_CT_ICE_MORTON_CODE) vb_ints *= 2;
+            else if (L->geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) vb_ints *= 2;
+            io.vbuf_ints = vb_ints;
+            io.a_geom = reinterpret_cast<int32_t*>(bufs.ptr[COVT_BUF_A_GEOM_OFFSETS]) + L->out[COVT_BUF_A_GEOM_OFFSETS];
+            io.a_part = reinterpret_cast<int32_t*>(bufs.ptr[COVT_BUF_A_PART_OFFSETS]) + L->out[COVT_BUF_A_PART_OFFSETS];
+            io.a_ring = reinterpret_cast<int32_t*>(bufs.ptr[COVT_BUF_A_RING_OFFSETS]) + L->out[COVT_BUF_A_RING_OFFSETS];
+            io.a_coords = reinterpret_cast<int32_t*>(bufs.ptr[COVT_BUF_A_COORDS]) + L->out[COVT_BUF_A_COORDS];
+            io.cap_parts = L->cap_parts;
+            io.cap_rings = L->cap_rings;
+            const uint64_t V = io.voff ? io.n_voff : vb_ints / 2;
+            io.cap_coords = V + ((flags & COVT_FLAG_CLOSE_RINGS) ? io.n_ring : 0);
+            io.close_rings = (flags & COVT_FLAG_CLOSE_RINGS) != 0;
+            __syncwarp();
+            warp_assemble(io, reinterpret_cast<uint32_t*>(wsm), ar);
+            if (ar.status != COVT_OK) layer_status = ar.status;
+        }
+        if (lane == 0) {
+            layers[l].status = layer_status;
+            layers[l].n_parts = ar.n_parts;
+            layers[l].n_rings = ar.n_rings;
+            layers[l].n_vertices = ar.n_vertices;
+            layers[l].n_coords = ar.n_coords;
+        }
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
+// one warp per stream request (stream path)
+// =================================================================================================
+__global__ void __launch_bounds__(LAYER_WARPS * 32)
+k_decode_tasks(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint8_t* arena, uint32_t* work_counter)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    uint8_t* wsm = smem + warp * LAYER_WARP_SMEM;
+    for (;;) {
+        const uint32_t i = warp_next_work(work_counter);
+        if (i >= n_tasks) break;
+        const DeviceTask d = tasks[i];
+        if (d.op == COVT_OP_NONE) continue;  // handled elsewhere (big stream) or unsupported: status preset by the host
+        StreamTask t;
+        t.src = blob + d.src_offset;
+        t.dst = arena + d.dst_offset;
+        t.byte_length = d.byte_length;
+        t.num_values = d.num_values;
+        t.op = d.op;
+        t.num_bits = d.num_bits;
+        t.no_shift = d.no_shift;
+        t.exact_length = d.exact_length;
+        StreamOutcome o;
+        warp_decode_stream(t, wsm, o);
+        __syncwarp();
+        if (lane == 0) { tasks[i].status = o.status; tasks[i].consumed = o.consumed; }
+    }
+}
+
+// =================================================================================================
+// K1: one large 32-bit varint stream over many CTAs, single pass, decoupled look-back
+// =================================================================================================
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// (count, a, b): a / b = sums at even / odd positions relative to the segment start.
+// left ⊕ right: the right segment's parity flips when the left count is odd.
+struct Trip { uint32_t c; int32_t a, b; };
+__device__ __forceinline__ Trip trip_combine(const Trip& l, const Trip& r)
+{
+    Trip o;
+    o.c = l.c + r.c;
+    const bool odd = l.c & 1u;
+    o.a = l.a + (odd ? r.b : r.a);
+    o.b = l.b + (odd ? r.a : r.b);
+    return o;
+}
+
+template <int POST>
+__device__ void k1_body(const uint8_t* blob, const BigStream& S, uint32_t chunk_global, uint32_t ci, ChunkState* states,
+                        uint32_t (*s_stage)[STAGE_WORDS], Trip* s_warp, Trip* s_prefix)
+{
+    constexpr bool ZZ = (POST == POST_ZZ || POST == POST_ZZ_DELTA || POST == POST_ZZ_DELTA_XY);
+    constexpr bool XY = (POST == POST_ZZ_DELTA_XY);
+    constexpr bool DELTA = (POST == POST_ZZ_DELTA || POST == POST_ZZ_DELTA_XY || POST == POST_DELTA_MORTON);
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint8_t* src = blob + S.src_offset;
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15);
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(src) - a0);
+    const uint64_t total = (uint64_t)head + S.byte_length;
+    const uint64_t off = (uint64_t)ci * K1_TILE_BYTES + warp * 512u + lane * 16u;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (off < total) w = ldg_stream128(reinterpret_cast<const void*>(a0 + off));
+    const uint32_t lo16 = off >= head ? 0u : (uint32_t)umin64(16, head - off);
+    const uint32_t hi16 = off >= total ? 0u : (uint32_t)umin64(16, total - off);
+    const uint32_t valid16 = ((1u << hi16) - 1u) & ~((1u << lo16) - 1u);
+    // halo of lane 0 = the 4 bytes before this warp's sub-chunk (always inside the stream when off >= 512)
+    uint32_t halo = 0;
+    if (lane == 0 && off > 0 && off < total + 4) halo = __ldg(reinterpret_cast<const uint32_t*>(a0 + off - 4));
+    if (lane == 0 && off > 0 && off - 4 < head) halo &= ~((1u << (8u * (head - (uint32_t)(off - 4)))) - 1u);
+    uint32_t emit, excl, wtotal;
+    bool overlong = false;
+    uint32_t* stage = s_stage[warp];
+    varint32_chunk_decode<false, ZZ>(w, valid16, halo, 0xffffffffu, stage, emit, excl, wtotal, overlong);
+    __syncwarp();
+    // blocked local sums (values stay in registers across the two block barriers)
+    int32_t v[16];
+    int32_t la = 0, lb = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t i = lane * 16 + j;
+        v[j] = i < wtotal ? (int32_t)stage[stage_index(i)] : 0;
+        if (DELTA) { if (XY && (j & 1)) lb += v[j]; else la += v[j]; }
+    }
+    int32_t ta = 0, tb = 0, ea = 0, eb = 0;
+    if (DELTA) {
+        ea = warp_exclusive_scan_i32(la, ta);
+        if (XY) eb = warp_exclusive_scan_i32(lb, tb);
+    }
+    if (lane == 0) { s_warp[warp].c = wtotal; s_warp[warp].a = ta; s_warp[warp].b = tb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Trip agg = s_warp[0];
+        for (int k = 1; k < K1_WARPS; k++) agg = XY ? trip_combine(agg, s_warp[k]) : Trip{agg.c + s_warp[k].c, agg.a + s_warp[k].a, 0};
+        ChunkState* me = &states[chunk_global];
+        Trip prefix = {0, 0, 0};
+        if (ci > 0) {
+            me->agg_count = agg.c; me->agg_a = agg.a; me->agg_b = agg.b;
+            __threadfence();
+            st_release_u32(&me->flag, 1u);
+            // decoupled look-back over the predecessors of the same stream
+            Trip acc = {0, 0, 0};
+            uint32_t j = chunk_global - 1;
+            for (;;) {
+                const ChunkState* pj = &states[j];
+                uint32_t f;
+                while ((f = ld_acquire_u32(&pj->flag)) == 0u) __nanosleep(20);
+                if (f == 2u) {
+                    Trip inc = {*(volatile const uint32_t*)&pj->inc_count, *(volatile const int32_t*)&pj->inc_x, *(volatile const int32_t*)&pj->inc_y};
+                    prefix = XY ? trip_combine(inc, acc) : Trip{inc.c + acc.c, inc.a + acc.a, 0};
+                    break;
+                }
+                Trip a = {*(volatile const uint32_t*)&pj->agg_count, *(volatile const int32_t*)&pj->agg_a, *(volatile const int32_t*)&pj->agg_b};
+                acc = XY ? trip_combine(a, acc) : Trip{a.c + acc.c, a.a + acc.a, 0};
+                j--;
+            }
+        }
+        const Trip inc = XY ? trip_combine(prefix, agg) : Trip{prefix.c + agg.c, prefix.a + agg.a, 0};
+        me->inc_count = inc.c; me->inc_x = inc.a; me->inc_y = inc.b;
+        __threadfence();
+        st_release_u32(&me->flag, 2u);
+        *s_prefix = prefix;
+        if (ci == S.n_chunks - 1) {  // last chunk of the stream: totals are known
+            if (inc.c < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
+            if (S.consumed_out) *S.consumed_out = S.byte_length;
+        }
+    }
+    if (__any_sync(FULL, overlong) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
+    __syncthreads();
+    // this warp's exclusive prefix
+    Trip P = *s_prefix;
+    for (unsigned k = 0; k < warp; k++) P = XY ? trip_combine(P, s_warp[k]) : Trip{P.c + s_warp[k].c, P.a + s_warp[k].a, 0};
+    if (DELTA) {
+        if (XY) {
+            const bool swap = P.c & 1u;  // position i of this warp has global parity (P.c + i) & 1 and lane*16 is even
+            int32_t pa = ea + (swap ? P.b : P.a);
+            int32_t pb = eb + (swap ? P.a : P.b);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j & 1) { pb += v[j]; v[j] = pb; } else { pa += v[j]; v[j] = pa; }
+            }
+        } else {
+            int32_t pa = ea + P.a;
+#pragma unroll
+            for (int j = 0; j < 16; j++) { pa += v[j]; v[j] = pa; }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t i = lane * 16 + j;
+            if (i < wtotal) stage[stage_index(i)] = (uint32_t)v[j];
+        }
+        __syncwarp();
+    }
+    // coalesced copy-out, clipped to num_values
+    const uint32_t room = P.c < S.num_values ? S.num_values - P.c : 0u;
+    warp_copy_out<POST, 16>(stage, min(wtotal, room), reinterpret_cast<int32_t*>(S.dst), P.c, S.num_bits, S.no_shift != 0);
+}
+
+__global__ void __launch_bounds__(K1_WARPS * 32)
+k1_varint_stream(const uint8_t* blob, const BigStream* streams, const ChunkRef* chunks, uint32_t n_chunks, ChunkState* states,
+                 uint32_t* ticket)
+{
+    __shared__ uint32_t s_stage[K1_WARPS][STAGE_WORDS];
+    __shared__ Trip s_warp[K1_WARPS];
+    __shared__ Trip s_prefix;
+    __shared__ uint32_t s_chunk;
+    // a ticket (not blockIdx) orders the chunks so that a predecessor has always been scheduled
+    if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t chunk = s_chunk;
+    if (chunk >= n_chunks) return;
+    const ChunkRef ref = chunks[chunk];
+    const BigStream S = streams[ref.stream];
+    switch (S.post) {
+    case POST_PLAIN: k1_body<POST_PLAIN>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
+    case POST_ZZ: k1_body<POST_ZZ>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
+    case POST_ZZ_DELTA: k1_body<POST_ZZ_DELTA>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
+    case POST_ZZ_DELTA_XY: k1_body<POST_ZZ_DELTA_XY>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
+    default: k1_body<POST_DELTA_MORTON>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
+    }
+}
+
+// =================================================================================================
+// finalize: tile status = first layer error (unless the container walk already failed), totals
+// =================================================================================================
+__global__ void k_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags, uint32_t* tile_status, uint64_t* totals)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t verts = 0, payload = 0, outb = 0;
+    if (t < n_tiles) {
+        uint32_t st = tile_status[t];
+        for (uint32_t l = first_layer[t]; l < first_layer[t + 1]; l++) {
+            const covt_layer& L = layers[l];
+            if (L.status && !st) st = L.status;
+            verts += L.n_vertices;
+            for (int s = 0; s < COVT_NUM_SLOTS; s++)
+                if (L.streams[s].encoding != COVT_ENC_ABSENT) payload += L.streams[s].byte_length;
+            // algorithmic output bytes: every decoded stream + the assembled buffers, no padding
+            const uint64_t F = slot_nv(L, COVT_SLOT_TYPES);
+            outb += F + 8 * slot_nv(L, COVT_SLOT_ID) +
+                    4 * (slot_nv(L, COVT_SLOT_GEOM) + slot_nv(L, COVT_SLOT_PART) + slot_nv(L, COVT_SLOT_RING) +
+                         slot_nv(L, COVT_SLOT_VOFF) + vbuf_ints_of(L, flags) + slot_nv(L, COVT_SLOT_INDEX));
+            if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && L.status == COVT_OK)
+                outb += 4ull * ((F + 1) + (L.n_parts + 1ull) + (L.n_rings + 1ull)) + 8ull * L.n_coords;
+        }
+        tile_status[t] = st;
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        verts += __shfl_down_sync(FULL, verts, d);
+        payload += __shfl_down_sync(FULL, payload, d);
+        outb += __shfl_down_sync(FULL, outb, d);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[0]), (unsigned long long)verts);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[1]), (unsigned long long)payload);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[2]), (unsigned long long)outb);
+    }
+}
+
+// =================================================================================================
+// launchers
+// =================================================================================================
+cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                                 const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols,
+                                 uint32_t* tile_status, cudaStream_t st)
+{
+    if (!n_tiles) return cudaSuccess;
+    k0_scan_tiles<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, flags, tile_cols, tile_status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_t* block_sums, uint64_t* totals, cudaStream_t st)
+{
+    if (!n_tiles) return cudaSuccess;
+    const uint32_t nb = (n_tiles + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    scan_block_sums<<<dim3(nb, TILE_COLS), SCAN_BLOCK, 0, st>>>(tile_cols, n_tiles, block_sums);
+    scan_block_prefix<<<TILE_COLS, SCAN_BLOCK, 0, st>>>(block_sums, nb, totals);
+    scan_apply<<<dim3(nb, TILE_COLS), SCAN_BLOCK, 0, st>>>(tile_cols, n_tiles, block_sums);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                                  const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
+                                  covt_layer* layers, uint32_t* first_layer, cudaStream_t st)
+{
+    if (!n_tiles) return cudaSuccess;
+    k0_fill_layers<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, flags, tile_cols, layers, first_layer);
+    return cudaGetLastError();
+}
+
+static int grid_for(int sm_count, int per_sm, uint32_t n_items, int warps_per_block)
+{
+    int64_t want = ((int64_t)n_items + warps_per_block - 1) / warps_per_block;
+    int64_t cap = (int64_t)sm_count * per_sm;
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+cudaError_t launch_decode_layers(const uint8_t* blob, covt_layer* layers, uint32_t n_layers, ResultBuffers bufs, uint32_t flags,
+                                 uint32_t* work_counter, int sm_count, cudaStream_t st)
+{
+    if (!n_layers) return cudaSuccess;
+    const int smem = LAYER_WARPS * LAYER_WARP_SMEM;
+    k_decode_layers<<<grid_for(sm_count, 12, n_layers, LAYER_WARPS), LAYER_WARPS * 32, smem, st>>>(blob, layers, n_layers, bufs, flags, work_counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_tasks(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint8_t* arena, uint32_t* work_counter,
+                                int sm_count, cudaStream_t st)
+{
+    if (!n_tasks) return cudaSuccess;
+    const int smem = LAYER_WARPS * LAYER_WARP_SMEM;
+    k_decode_tasks<<<grid_for(sm_count, 12, n_tasks, LAYER_WARPS), LAYER_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, arena, work_counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, const ChunkRef* chunks, uint32_t n_chunks,
+                                    ChunkState* states, uint32_t* ticket, cudaStream_t st)
+{
+    if (!n_chunks) return cudaSuccess;
+    k1_varint_stream<<<n_chunks, K1_WARPS * 32, 0, st>>>(blob, streams, chunks, n_chunks, states, ticket);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags,
+                            uint32_t* tile_status, uint64_t* totals, cudaStream_t st)
+{
+    if (!n_tiles) return cudaSuccess;
+    k_finalize<<<(n_tiles + 127) / 128, 128, 0, st>>>(layers, first_layer, n_tiles, flags, tile_status, totals);
+    return cudaGetLastError();
+}
+
+}  // namespace covt

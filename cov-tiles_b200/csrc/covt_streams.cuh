@@ -1,0 +1,515 @@
+// covt_streams.cuh — warp-per-stream decoders for the four COVT column-stream codecs.
+//
+// Each function is executed by ONE full warp with uniform control flow and decodes one stream
+// described by a StreamTask. They replace, one to one, the static codecs of the reference
+// J/decoder/DecodingUtils.java (cited per function). Large delta-varint streams take the
+// multi-CTA decoupled-look-back kernel in k1_varint_stream.cu instead.
+#pragma once
+#include "covt_device.cuh"
+
+namespace covt {
+
+// bytes of shared memory one warp needs for any stream op (u64 stage for the 64-bit id ops)
+constexpr int WARP_SMEM_BYTES = STAGE_WORDS * 8;
+
+// =================================================================================================
+// 32-bit varints: DecodingUtils.decodeVarint :35, decodeZigZagVarint :46, decodeZigZagDeltaVarint :55,
+// decodeZigZagDeltaVarintCoordinates :95, decodeDeltaVarintMortonCodes :394
+// =================================================================================================
+template <bool VB>
+struct ChunkCut {
+    uint32_t cut_pos;  // 1-based byte position inside the chunk window of the terminator of value #limit, 0 if none
+};
+
+// Position (1-based, in chunk-window bytes) right after the `limit`-th emitted value of this chunk, or 0.
+__device__ __forceinline__ uint32_t chunk_cut_position(uint32_t emit, uint32_t lane_excl, uint32_t limit)
+{
+    uint32_t cnt = __popc(emit);
+    bool mine = limit > 0 && lane_excl < limit && limit <= lane_excl + cnt;
+    uint32_t pos = 0;
+    if (mine) pos = lane_id() * 16u + __fns(emit, 0, (int)(limit - lane_excl)) + 1u;
+    unsigned b = __ballot_sync(FULL, mine);
+    if (!b) return 0;
+    return __shfl_sync(FULL, pos, __ffs(b) - 1);
+}
+
+template <int POST, bool WIDEN>
+__device__ __forceinline__ void copy_out_select(const uint32_t* stage, uint32_t n, void* dst, uint64_t first, const StreamTask& t)
+{
+    if (WIDEN) {
+        const unsigned lane = lane_id();
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            uint32_t i = lane + 32u * k;
+            if (i < n) reinterpret_cast<int64_t*>(dst)[first + i] = (int64_t)(int32_t)stage[stage_index(i)];
+        }
+    } else {
+        warp_copy_out<POST, 16>(stage, n, reinterpret_cast<int32_t*>(dst), first, t.num_bits, t.no_shift != 0);
+    }
+}
+
+template <int POST, bool WIDEN>
+__device__ void warp_varint32_stream(const StreamTask& t, uint32_t* stage, StreamOutcome& out)
+{
+    const unsigned lane = lane_id();
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(t.src) & ~uintptr_t(15);
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(t.src) - a0);
+    const uint64_t total = (uint64_t)head + t.byte_length;
+    DeltaCarry carry = {0, 0, 0};
+    uint32_t halo = 0;
+    bool overlong = false;
+    uint32_t consumed = 0;
+    constexpr bool ZZ = (POST == POST_ZZ || POST == POST_ZZ_DELTA || POST == POST_ZZ_DELTA_XY);
+    for (uint64_t base = 0; base < total && carry.produced < t.num_values; base += WARP_CHUNK_BYTES) {
+        const uint64_t off = base + lane * 16u;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (off < total) w = ldg_stream128(reinterpret_cast<const void*>(a0 + off));
+        const uint32_t lo16 = off >= head ? 0u : (uint32_t)umin64(16, head - off);
+        const uint32_t hi16 = off >= total ? 0u : (uint32_t)umin64(16, total - off);
+        uint32_t valid16 = ((1u << hi16) - 1u) & ~((1u << lo16) - 1u);
+        const uint32_t remaining = t.num_values - carry.produced;
+        // bytes after the last value the caller asked for belong to somebody else: find the cut first
+        uint32_t emit, excl, ctotal;
+        if (!t.exact_length) {
+            uint32_t words[4] = {w.x, w.y, w.z, w.w};
+            uint32_t e0 = (~gather_msb16(words) & 0xffffu) & valid16;
+            uint32_t tot0;
+            uint32_t ex0 = warp_exclusive_scan(__popc(e0), tot0);
+            uint32_t cut = chunk_cut_position(e0, ex0, remaining);
+            if (cut) {
+                consumed = (uint32_t)(base + cut - head);
+                uint32_t keep = cut > lane * 16u ? min(16u, cut - lane * 16u) : 0u;
+                valid16 &= (1u << keep) - 1u;
+            }
+        }
+        varint32_chunk_decode<false, ZZ>(w, valid16, halo, remaining, stage, emit, excl, ctotal, overlong);
+        const uint32_t n = min(ctotal, remaining);
+        __syncwarp();
+        warp_delta_pass<POST, 16, false>(stage, n, carry);
+        __syncwarp();
+        copy_out_select<POST, WIDEN>(stage, n, t.dst, carry.produced, t);
+        __syncwarp();
+        carry.produced += n;
+    }
+    out.consumed = t.exact_length ? t.byte_length : consumed;
+    if (carry.produced < t.num_values) out.status = COVT_ERR_TRUNCATED;  // Java: ArrayIndexOutOfBounds
+    else if (__any_sync(FULL, overlong)) out.status = COVT_ERR_VARINT_OVERLONG;
+    else out.status = COVT_OK;
+}
+
+// =================================================================================================
+// 64-bit varints for ids (ID_WIDTH 64): inverse of EncodingUtils.encodeVarints (EncodingUtils.java:39-55)
+// =================================================================================================
+template <bool ZZ_DELTA>
+__device__ void warp_varint64_stream(const StreamTask& t, uint64_t* stage, StreamOutcome& out)
+{
+    const unsigned lane = lane_id();
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(t.src) & ~uintptr_t(15);
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(t.src) - a0);
+    const uint64_t total = (uint64_t)head + t.byte_length;
+    uint32_t produced = 0;
+    int64_t running = 0;
+    uint32_t h1 = 0, h2 = 0, h3 = 0;  // previous 12 bytes for lane 0
+    bool overlong = false;
+    uint32_t consumed = 0;
+    for (uint64_t base = 0; base < total && produced < t.num_values; base += WARP_CHUNK_BYTES) {
+        const uint64_t off = base + lane * 16u;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (off < total) w = ldg_stream128(reinterpret_cast<const void*>(a0 + off));
+        const uint32_t lo16 = off >= head ? 0u : (uint32_t)umin64(16, head - off);
+        const uint32_t hi16 = off >= total ? 0u : (uint32_t)umin64(16, total - off);
+        uint32_t valid16 = ((1u << hi16) - 1u) & ~((1u << lo16) - 1u);
+        uint32_t words[4] = {w.x, w.y, w.z, w.w};
+        const uint32_t remaining = t.num_values - produced;
+        uint32_t emit = (~gather_msb16(words) & 0xffffu) & valid16;
+        uint32_t ctotal;
+        uint32_t excl = warp_exclusive_scan(__popc(emit), ctotal);
+        uint32_t cut = chunk_cut_position(emit, excl, remaining);
+        if (cut) {
+            consumed = (uint32_t)(base + cut - head);
+            uint32_t keep = cut > lane * 16u ? min(16u, cut - lane * 16u) : 0u;
+            valid16 &= (1u << keep) - 1u;
+            emit &= valid16;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) words[q] &= nibble_to_bytemask((valid16 >> (4 * q)) & 0xfu);
+        // halo: the 12 bytes before this lane's window
+        uint32_t p1 = __shfl_up_sync(FULL, words[1], 1), p2 = __shfl_up_sync(FULL, words[2], 1), p3 = __shfl_up_sync(FULL, words[3], 1);
+        if (lane == 0) { p1 = h1; p2 = h2; p3 = h3; }
+        h1 = __shfl_sync(FULL, words[1], 31); h2 = __shfl_sync(FULL, words[2], 31); h3 = __shfl_sync(FULL, words[3], 31);
+        const uint32_t hw[3] = {p1, p2, p3};
+        uint32_t k = 0;  // trailing continuation bytes of the halo
+#pragma unroll
+        for (int i = 11; i >= 0; i--) {
+            uint32_t b = (hw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            if (k == (uint32_t)(11 - i) && (b & 0x80u)) k++;
+        }
+        uint64_t acc = 0;
+        uint32_t shift = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            if ((uint32_t)i >= 12u - k) {
+                uint32_t b = (hw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                acc |= (uint64_t)(b & 0x7fu) << (shift & 63u);
+                shift += 7;
+            }
+        }
+        if (k >= 10) overlong = true;
+        uint32_t idx = excl;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            acc |= (uint64_t)(b & 0x7fu) << (shift & 63u);
+            if (b & 0x80u) {
+                if (shift >= 63) overlong = true;  // a 10th byte that still continues
+                shift += 7;
+            } else {
+                if ((emit >> j) & 1u) {
+                    if (idx < remaining) stage[stage_index(idx)] = ZZ_DELTA ? (uint64_t)zigzag_decode64(acc) : acc;
+                    idx++;
+                }
+                acc = 0;
+                shift = 0;
+            }
+        }
+        const uint32_t n = min(ctotal, remaining);
+        __syncwarp();
+        if (ZZ_DELTA) {
+            int64_t v[16];
+            int64_t a = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                uint32_t i = lane * 16 + j;
+                v[j] = i < n ? (int64_t)stage[stage_index(i)] : 0;
+                a += v[j];
+            }
+            uint64_t tot;
+            int64_t pa = (int64_t)warp_exclusive_scan_u64((uint64_t)a, tot) + running;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                uint32_t i = lane * 16 + j;
+                pa += v[j];
+                if (i < n) stage[stage_index(i)] = (uint64_t)pa;
+            }
+            running += (int64_t)tot;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            uint32_t i = lane + 32u * kk;
+            if (i < n) reinterpret_cast<int64_t*>(t.dst)[produced + i] = (int64_t)stage[stage_index(i)];
+        }
+        __syncwarp();
+        produced += n;
+    }
+    out.consumed = consumed;
+    if (produced < t.num_values) out.status = COVT_ERR_TRUNCATED;
+    else if (__any_sync(FULL, overlong)) out.status = COVT_ERR_VARINT_OVERLONG;
+    else out.status = COVT_OK;
+}
+
+// =================================================================================================
+// ORC RLE v1: DecodingUtils.decodeRle :257 (orc-core RunLengthIntegerReader) and decodeByteRle :275/:290
+// (RunLengthByteReader). The header chain is sequential; all lanes walk it redundantly (broadcast
+// loads) and expand runs / store literal groups cooperatively with coalesced stores.
+// =================================================================================================
+__device__ __forceinline__ void warp_touch_lines(const uint8_t* src, uint32_t len)
+{
+    // pull the stream's cache lines in with independent loads so that the dependent header walk hits L1/L2
+    uint32_t acc = 0;
+    for (uint32_t o = lane_id() * 128u; o < len; o += 32u * 128u) acc += __ldg(src + o);
+    if (acc == 0xffffffffu) __nanosleep(1);  // keep the loads alive
+}
+
+// unsigned LEB128 up to 10 bytes at src[pos..len); uniform across the warp. Returns false on truncation.
+__device__ __forceinline__ bool read_vulong(const uint8_t* src, uint32_t len, uint32_t& pos, uint64_t& v)
+{
+    v = 0;
+    uint32_t shift = 0;
+    for (int i = 0; i < 10; i++) {
+        if (pos >= len) return false;
+        uint32_t b = __ldg(src + pos);
+        pos++;
+        v |= (uint64_t)(b & 0x7fu) << (shift & 63u);
+        shift += 7;
+        if (!(b & 0x80u)) break;
+    }
+    return true;
+}
+
+template <typename OutT, bool SIGNED>
+__device__ void warp_rle_stream(const StreamTask& t, StreamOutcome& out)
+{
+    const unsigned lane = lane_id();
+    const uint8_t* src = t.src;
+    const uint32_t len = t.byte_length, n = t.num_values;
+    OutT* dst = reinterpret_cast<OutT*>(t.dst);
+    warp_touch_lines(src, len);
+    uint32_t pos = 0, done = 0;
+    uint32_t status = COVT_OK;
+    while (done < n) {
+        if (pos >= len) { status = COVT_ERR_TRUNCATED; break; }
+        const uint32_t c = __ldg(src + pos);
+        pos++;
+        if (c < 0x80u) {
+            const uint32_t run = c + 3u;
+            if (pos >= len) { status = COVT_ERR_TRUNCATED; break; }
+            const int64_t delta = (int8_t)__ldg(src + pos);
+            pos++;
+            uint64_t raw;
+            if (!read_vulong(src, len, pos, raw)) { status = COVT_ERR_TRUNCATED; break; }
+            const uint64_t base = SIGNED ? (uint64_t)zigzag_decode64(raw) : raw;
+            const uint32_t m = min(run, n - done);
+            for (uint32_t i = lane; i < m; i += 32) dst[done + i] = (OutT)(base + (uint64_t)i * (uint64_t)delta);
+            done += m;
+        } else {
+            const uint32_t lit = 256u - c;
+            uint64_t mine = 0;
+            bool bad = false;
+            for (uint32_t i = 0; i < lit; i++) {
+                uint64_t raw;
+                if (!read_vulong(src, len, pos, raw)) { bad = true; break; }
+                if ((i & 31u) == lane) mine = SIGNED ? (uint64_t)zigzag_decode64(raw) : raw;
+                if ((i & 31u) == 31u || i + 1 == lit) {
+                    const uint32_t idx = done + (i & ~31u) + lane;
+                    if (lane <= (i & 31u) && idx < n) dst[idx] = (OutT)mine;
+                }
+            }
+            if (bad) { status = COVT_ERR_TRUNCATED; break; }
+            done += min(lit, n - done);
+        }
+    }
+    out.status = status;
+    out.consumed = pos;
+}
+
+__device__ void warp_byte_rle_stream(const StreamTask& t, StreamOutcome& out)
+{
+    const unsigned lane = lane_id();
+    const uint8_t* src = t.src;
+    const uint32_t len = t.byte_length, n = t.num_values;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(t.dst);
+    warp_touch_lines(src, len);
+    uint32_t pos = 0, done = 0;
+    uint32_t status = COVT_OK;
+    while (done < n) {
+        if (pos >= len) { status = COVT_ERR_TRUNCATED; break; }
+        const uint32_t c = __ldg(src + pos);
+        pos++;
+        if (c < 0x80u) {
+            const uint32_t run = c + 3u;
+            if (pos >= len) { status = COVT_ERR_TRUNCATED; break; }
+            const uint8_t v = __ldg(src + pos);
+            pos++;
+            const uint32_t m = min(run, n - done);
+            for (uint32_t i = lane; i < m; i += 32) dst[done + i] = v;
+            done += m;
+        } else {
+            const uint32_t lit = 256u - c;
+            if (pos + lit > len) { status = COVT_ERR_TRUNCATED; break; }
+            const uint32_t m = min(lit, n - done);
+            for (uint32_t i = lane; i < m; i += 32) dst[done + i] = __ldg(src + pos + i);
+            pos += lit;
+            done += m;
+        }
+    }
+    out.status = status;
+    out.consumed = pos;
+}
+
+// =================================================================================================
+// Composition(FastPFOR-256, VariableByte) over big-endian words + fused post pass:
+// DecodingUtils.decodeFastPfor128ZigZagDelta :316, decodeFastPfor128DeltaCoordinates :349,
+// decodeFastPfor128DeltaMortonCodes :411 (JavaFastPFOR 0.1.12)
+// =================================================================================================
+// k-bit value number q of an array packed in groups of 32 (BitPacking.fastpack layout) starting at word `w0`
+__device__ __forceinline__ uint32_t unpack_packed(const uint8_t* base, uint32_t w0, uint32_t q, uint32_t k)
+{
+    if (k == 0) return 0;
+    const uint32_t bo = (q & 31u) * k;
+    const uint32_t wi = w0 + (q >> 5) * k + (bo >> 5);
+    const uint32_t sh = bo & 31u;
+    const uint32_t lo = ld_be_word(base, wi);
+    const uint32_t hi = (sh + k > 32u) ? ld_be_word(base, wi + 1) : 0u;
+    const uint32_t v = __funnelshift_r(lo, hi, sh);
+    return k >= 32u ? v : (v & ((1u << k) - 1u));
+}
+
+template <int POST>
+__device__ void warp_pfor_stream(const StreamTask& t, uint32_t* stage, StreamOutcome& out)
+{
+    const unsigned lane = lane_id();
+    const uint8_t* base = t.src;
+    const uint32_t n_words = t.byte_length / 4u;  // (int)Math.ceil(byteLength / 4): integer division, DecodingUtils.java:324
+    const uint32_t n = t.num_values;
+    constexpr bool ZZ = (POST == POST_ZZ_DELTA || POST == POST_ZZ_DELTA_XY);
+    DeltaCarry carry = {0, 0, 0};
+    uint32_t status = COVT_OK;
+    uint32_t inpos = 0;
+    out.consumed = t.byte_length;
+#define PFOR_FAIL(code) { status = (code); goto finish; }
+    if (n_words == 0) {
+        // Composition.uncompress returns at once: the output stays all zeros, the post passes still run
+        for (uint32_t b0 = 0; b0 < n; b0 += 512) {
+            uint32_t m = min(512u, n - b0);
+            for (uint32_t i = lane; i < m; i += 32) stage[stage_index(i)] = 0;
+            __syncwarp();
+            warp_copy_out<POST, 16>(stage, m, reinterpret_cast<int32_t*>(t.dst), b0, t.num_bits, t.no_shift != 0);
+            __syncwarp();
+        }
+        out.status = COVT_OK;
+        return;
+    }
+    {
+        const uint32_t mynvalue = ld_be_word(base, 0);
+        inpos = 1;
+        if (mynvalue > n || (mynvalue & 255u)) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);
+        uint32_t outpos = 0;
+        while (outpos < mynvalue) {
+            const uint32_t thissize = min(65536u, mynvalue - outpos);
+            // ---- page header (FastPFOR.decodePage) ----
+            const uint32_t initpos = inpos;
+            if (initpos >= n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+            const uint32_t wheremeta = ld_be_word(base, initpos);
+            uint64_t inexcept = (uint64_t)initpos + wheremeta;
+            if (inexcept >= n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+            const uint32_t bytesize = ld_be_word(base, (uint32_t)inexcept);
+            inexcept++;
+            const uint64_t bc_words = ((uint64_t)bytesize + 3u) / 4u;
+            if (inexcept + bc_words > n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+            const uint32_t bc_word0 = (uint32_t)inexcept;
+            inexcept += bc_words;
+            if (inexcept >= n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+            const uint32_t bitmap = ld_be_word(base, (uint32_t)inexcept);
+            inexcept++;
+            // exception array of width k lives in lane k-1: first word, size, cursor (cursors reset per page)
+            uint32_t exc_base = 0, exc_size = 0, exc_ptr = 0;
+            for (uint32_t k = 2; k <= 32; k++) {
+                if (!(bitmap & (1u << (k - 1)))) continue;
+                if (inexcept >= n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                const uint32_t size = ld_be_word(base, (uint32_t)inexcept);
+                inexcept++;
+                const uint64_t need = ((uint64_t)size * k + 31u) / 32u;
+                if (inexcept + need > n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                if (lane == k - 1) { exc_base = (uint32_t)inexcept; exc_size = size; }
+                inexcept += need;
+            }
+            uint32_t tmpin = initpos + 1;
+            uint32_t bcpos = 0;
+            // byte i of the byte container: bytes are little-endian inside each (big-endian serialised) word
+#define BC_BYTE(i) ((ld_be_word(base, bc_word0 + ((i) >> 2)) >> (8u * ((i) & 3u))) & 0xffu)
+            for (uint32_t run = 0, run_end = thissize / 256u; run < run_end; run++) {
+                if (bcpos + 2 > bytesize) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                const uint32_t b = BC_BYTE(bcpos);
+                const uint32_t cexcept = BC_BYTE(bcpos + 1);
+                bcpos += 2;
+                if (b > 32u) PFOR_FAIL(COVT_ERR_BAD_METADATA);
+                if ((uint64_t)tmpin + 8ull * b > (uint64_t)initpos + wheremeta) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                // ---- unpack 256 values of b bits: value (g, lane) ----
+#pragma unroll
+                for (int g = 0; g < 8; g++) stage[stage_index(g * 32 + lane)] = unpack_packed(base, tmpin + g * b, lane, b);
+                tmpin += 8u * b;
+                if (cexcept > 0) {
+                    if (bcpos + 1 + cexcept > bytesize) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                    const uint32_t maxbits = BC_BYTE(bcpos);
+                    bcpos++;
+                    const int index = (int)maxbits - (int)b;
+                    __syncwarp();
+                    if (index == 1) {
+                        for (uint32_t e = lane; e < cexcept; e += 32) {
+                            const uint32_t p = BC_BYTE(bcpos + e);
+                            stage[stage_index(p)] |= 1u << (b & 31u);
+                        }
+                    } else {
+                        if (index < 2 || index > 32 || !(bitmap & (1u << (index - 1)))) PFOR_FAIL(COVT_ERR_BAD_METADATA);
+                        const uint32_t ebase = __shfl_sync(FULL, exc_base, index - 1);
+                        const uint32_t esize = __shfl_sync(FULL, exc_size, index - 1);
+                        const uint32_t eptr = __shfl_sync(FULL, exc_ptr, index - 1);
+                        if (eptr + cexcept > esize) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                        for (uint32_t e = lane; e < cexcept; e += 32) {
+                            const uint32_t p = BC_BYTE(bcpos + e);
+                            const uint32_t ev = unpack_packed(base, ebase, eptr + e, (uint32_t)index);
+                            stage[stage_index(p)] |= ev << (b & 31u);
+                        }
+                        if (lane == (unsigned)(index - 1)) exc_ptr += cexcept;
+                    }
+                    bcpos += cexcept;
+                }
+                __syncwarp();
+                warp_delta_pass<POST, 8, ZZ>(stage, 256, carry);
+                __syncwarp();
+                warp_copy_out<POST, 8>(stage, 256, reinterpret_cast<int32_t*>(t.dst), carry.produced, t.num_bits, t.no_shift != 0);
+                __syncwarp();
+                carry.produced += 256;
+            }
+#undef BC_BYTE
+            outpos += thissize;
+            inpos = (uint32_t)inexcept;
+        }
+        // ---- VariableByte tail over ALL remaining words (VariableByte.uncompress) ----
+        uint32_t halo = 0x80808080u;  // VB: MSB set = terminator, so nothing is carried in
+        bool overlong = false;
+        for (uint32_t wbase = inpos; wbase < n_words; wbase += 128) {
+            uint32_t words[4];
+            uint32_t valid16 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t wi = wbase + lane * 4u + q;
+                words[q] = wi < n_words ? ld_be_word(base, wi) : 0u;
+                if (wi < n_words) valid16 |= 0xfu << (4 * q);
+            }
+            uint32_t emit, excl, ctotal;
+            const uint32_t remaining = n - carry.produced;
+            varint32_chunk_decode<true, false>(make_uint4(words[0], words[1], words[2], words[3]), valid16, halo, remaining,
+                                               stage, emit, excl, ctotal, overlong);
+            if (ctotal > remaining) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);  // Java: ArrayIndexOutOfBounds
+            __syncwarp();
+            warp_delta_pass<POST, 16, ZZ>(stage, ctotal, carry);
+            __syncwarp();
+            warp_copy_out<POST, 16>(stage, ctotal, reinterpret_cast<int32_t*>(t.dst), carry.produced, t.num_bits, t.no_shift != 0);
+            __syncwarp();
+            carry.produced += ctotal;
+        }
+        if (carry.produced != n) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);
+    }
+finish:
+#undef PFOR_FAIL
+    out.status = status;
+}
+
+// =================================================================================================
+// dispatch on covt_op (rows a1..a10 of SURVEY §8a)
+// =================================================================================================
+__device__ void warp_decode_stream(const StreamTask& t, void* warp_smem, StreamOutcome& out)
+{
+    uint32_t* stage = reinterpret_cast<uint32_t*>(warp_smem);
+    out.status = COVT_OK;
+    out.consumed = 0;
+    switch (t.op) {
+    case COVT_OP_BYTE_RLE: warp_byte_rle_stream(t, out); break;
+    case COVT_OP_RLE_U32: warp_rle_stream<int32_t, false>(t, out); break;
+    case COVT_OP_RLE_U64: warp_rle_stream<int64_t, false>(t, out); break;
+    case COVT_OP_RLE_S64: warp_rle_stream<int64_t, true>(t, out); break;
+    case COVT_OP_VARINT_U32: warp_varint32_stream<POST_PLAIN, false>(t, stage, out); break;
+    case COVT_OP_VARINT_ZZ: warp_varint32_stream<POST_ZZ, false>(t, stage, out); break;
+    case COVT_OP_VARINT_ZZ_DELTA: warp_varint32_stream<POST_ZZ_DELTA, false>(t, stage, out); break;
+    case COVT_OP_VARINT_ZZ_DELTA_XY:
+        if (t.num_values & 1u) { out.status = COVT_ERR_COUNT_MISMATCH; break; }
+        warp_varint32_stream<POST_ZZ_DELTA_XY, false>(t, stage, out);
+        break;
+    case COVT_OP_VARINT_DELTA_MORTON: warp_varint32_stream<POST_DELTA_MORTON, false>(t, stage, out); break;
+    case COVT_OP_VARINT_U32_AS_I64: warp_varint32_stream<POST_PLAIN, true>(t, stage, out); break;
+    case COVT_OP_VARINT_ZZ_DELTA_AS_I64: warp_varint32_stream<POST_ZZ_DELTA, true>(t, stage, out); break;
+    case COVT_OP_VARINT_U64: warp_varint64_stream<false>(t, reinterpret_cast<uint64_t*>(warp_smem), out); break;
+    case COVT_OP_VARINT_ZZ_DELTA_64: warp_varint64_stream<true>(t, reinterpret_cast<uint64_t*>(warp_smem), out); break;
+    case COVT_OP_PFOR_ZZ_DELTA: warp_pfor_stream<POST_ZZ_DELTA>(t, stage, out); break;
+    case COVT_OP_PFOR_ZZ_DELTA_XY:
+        if (t.num_values & 1u) { out.status = COVT_ERR_COUNT_MISMATCH; break; }
+        warp_pfor_stream<POST_ZZ_DELTA_XY>(t, stage, out);
+        break;
+    case COVT_OP_PFOR_DELTA_MORTON: warp_pfor_stream<POST_DELTA_MORTON>(t, stage, out); break;
+    default: out.status = COVT_ERR_UNSUPPORTED_ENCODING; break;
+    }
+}
+
+}  // namespace covt

@@ -310,6 +310,11 @@ int32_t covt_result_timing(const covt_result* res, covt_timing* out);
 int32_t covt_result_kernel_times(const covt_result* res, covt_kernel_time* out, uint32_t cap, uint32_t* n);
 void    covt_result_free(covt_result* res);
 
+/* ---- host memory helpers ----------------------------------------------------------------------- */
+/* Page-locks a caller-owned host range (e.g. a Java MemorySegment) so that uploads run at full PCIe rate. */
+int32_t covt_host_register(covt_ctx* ctx, void* ptr, size_t bytes);
+int32_t covt_host_unregister(covt_ctx* ctx, void* ptr);
+
 /* ---- batch scheduler helper (host only) ------------------------------------------------------ */
 /* Splits tiles [0,n_tiles) into n_parts contiguous ranges balanced by payload bytes
  * (prefix sum over tile_offsets). starts has n_parts+1 entries. No collective: tiles share nothing. */

@@ -1,0 +1,218 @@
+"""GPU parity tests of the batch path (covt_decode_batch / covt_batch_decode) against the CPU oracle,
+the reference's own fixture tiles and the MVT ground-truth digests. All calls go through the C ABI."""
+import numpy as np
+import pytest
+
+import canon
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _decode_both(covt, oracle, decoder, blob, offs, container=0, flags=None, n_fields=None):
+    abi = covt.abi
+    if flags is None:
+        flags = abi.FLAG_DEFAULT
+    res = decoder.decode_batch(blob, offs, container, flags, n_fields=n_fields)
+    ref = oracle.decode_batch(blob, offs, container, flags, n_fields=n_fields)
+    st, first = res.tile_status()
+    assert np.array_equal(first, ref.first_layer), "first_layer differs"
+    assert np.array_equal(st == 0, ref.tile_status == 0), "tile status OK-ness differs: %s vs %s" % (st, ref.tile_status)
+    return res, ref
+
+
+def test_config1_zoom5_transportation(covt, oracle, decoder, fixtures):
+    """BASELINE config 1: the zoom-5 OMT transportation layer (and its three z5 siblings), every stream bit-exact."""
+    abi = covt.abi
+    tiles = [(n, b) for n, b in fixtures if n in ("omt/5_16_20", "omt/5_16_21", "omt/5_17_20", "omt/5_17_21")]
+    assert len(tiles) == 4
+    blob, offs = util.concat_tiles([b for _, b in tiles])
+    flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+    res, ref = _decode_both(covt, oracle, decoder, blob, offs, flags=flags)
+    n = util.compare_results(abi, res, ref)
+    names = [util.layer_name(blob, L) for L in res.layers]
+    assert names.count("transportation") == 4
+    # the layer BASELINE.md names: 45 232 features, 92 378 assembled vertices
+    for L in res.layers:
+        if util.layer_name(blob, L) == "transportation" and tiles[L["tile"]][0] == "omt/5_16_21":
+            assert L["num_features"] == 45232 and L["n_vertices"] == 92378 and L["status"] == 0
+    assert n == len(res.layers)
+    res.free()
+
+
+def test_config2_fixture_sweep_vs_oracle(covt, oracle, decoder, fixtures):
+    """BASELINE config 2: all 129 gen-2b fixture tiles (omt z2-z14, bing, amazon) in ONE batched launch."""
+    abi = covt.abi
+    blob, offs = util.concat_tiles([b for _, b in fixtures])
+    flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+    res, ref = _decode_both(covt, oracle, decoder, blob, offs, flags=flags)
+    n = util.compare_results(abi, res, ref)
+    assert n >= 1375
+    t = res.timing()
+    assert t["payload_bytes"] == ref.payload_bytes and t["vertices"] == ref.vertices
+    res.free()
+
+
+@pytest.mark.parametrize("flags_extra", [0, 0x0004, 0x0008, 0x0010, 0x0020])
+def test_fixture_sweep_flag_variants(covt, oracle, decoder, fixtures, flags_extra):
+    """Quirk switches: no ring closing, MORTON_NO_SHIFT, ID_WIDTH_32, ICE_VB_COUNT_IS_INTS, SKIP_ASSEMBLY."""
+    abi = covt.abi
+    sub = [b for n, b in fixtures if n.startswith(("omt/8_", "omt/4_", "amazon/", "omt/14_"))]
+    blob, offs = util.concat_tiles(sub)
+    res, ref = _decode_both(covt, oracle, decoder, blob, offs, flags=flags_extra | abi.FLAG_ID_DVZZ_IS_RLE)
+    util.compare_results(abi, res, ref, check_assembled=not (flags_extra & abi.FLAG_SKIP_ASSEMBLY))
+    res.free()
+
+
+def test_fixture_geometry_equals_mvt(covt, decoder, fixtures):
+    """Assembled geometry from the GPU equals the partner .mvt/.pbf of the reference fixtures (committed digests)."""
+    abi = covt.abi
+    digests = util.mvt_digests()
+    checked = 0
+    for z8 in (False, True):
+        tiles = [(n, b) for n, b in fixtures if n.startswith("omt/8_") == z8 and not n.startswith("bing/")]
+        blob, offs = util.concat_tiles([b for _, b in tiles])
+        flags = abi.FLAG_ID_DVZZ_IS_RLE | (abi.FLAG_MORTON_NO_SHIFT if z8 else 0)
+        res = decoder.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags)
+        bufs = [res.buffer(b) for b in range(abi.NUM_BUFFERS - 1)]
+        for L in res.layers:
+            key = "%s/%s" % (tiles[L["tile"]][0], util.layer_name(blob, L))
+            if key in util.KNOWN_MISLABELLED:
+                assert L["status"] != 0
+                continue
+            assert L["status"] == 0, key
+            if key in util.KNOWN_MVT_MISMATCH or key not in digests:
+                continue
+            c = canon.canonical_from_assembled(*canon.layer_slices(L, bufs, abi))
+            d = digests[key]
+            assert (len(c[0]), len(c[1]), len(c[2]) // 2) == (d["features"], d["rings"], d["vertices"]), key
+            assert canon.digest(c) == d["digest"], key
+            checked += 1
+        res.free()
+    assert checked >= 1100
+
+
+def test_gen3_rewrapped_fixtures(covt, oracle, decoder, fixtures):
+    """gen-3 (HEAD CovtParser grammar) inputs made by a metadata-only re-wrap of the gen-2b fixtures decode to the
+    same streams and geometry as the gen-2b originals; optimised metadata goes through the TileJSON side-car."""
+    abi = covt.abi
+    names = ["omt/5_16_21", "omt/2_2_2", "omt/7_66_84", "omt/14_8298_10748", "amazon/5_5_11", "bing/4-8-5"]
+    have = dict(fixtures)
+    tiles = [have[n] for n in names if n in have]
+    assert len(tiles) >= 4
+    flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+    for optimized in (False, True):
+        wrapped = [util.rewrap_gen3(abi, oracle, t, optimized) for t in tiles]
+        nf = max(len(w[1]) for w in wrapped) * [0] if optimized else None
+        blob3, offs3 = util.concat_tiles([w[0] for w in wrapped])
+        res3, ref3 = _decode_both(covt, oracle, decoder, blob3, offs3, container=abi.CONTAINER_GEN3, flags=flags, n_fields=nf)
+        util.compare_results(abi, res3, ref3)
+        # and against the gen-2b decode of the same tiles: identical decoded buffers
+        blob2, offs2 = util.concat_tiles(tiles)
+        res2 = decoder.decode_batch(blob2, offs2, abi.CONTAINER_GEN2B, flags)
+        util.compare_results(abi, res3, res2, same_container=False)
+        res2.free()
+        res3.free()
+
+
+@pytest.mark.parametrize("container", [0, 1, 2])
+def test_synthetic_tiles_vs_oracle_and_truth(covt, oracle, gen, decoder, container):
+    """Config-5 style synthetic mixed-geometry tiles: GPU == oracle bit for bit, and both == what was encoded."""
+    abi = covt.abi
+    n_tiles = 3000
+    p = gen.default_params(container=container)
+    blob, offs, truth = gen.tiles(1000, n_tiles, p)
+    cont = abi.CONTAINER_GEN2B if container == 0 else abi.CONTAINER_GEN3
+    nf = [0] * 16 if container == 2 else None
+    res, ref = _decode_both(covt, oracle, decoder, blob, offs, container=cont, n_fields=nf)
+    assert np.all(ref.tile_status == 0)
+    util.compare_results(abi, res, ref)
+    L = res.layers
+    assert int(L["n_vertices"].sum()) == truth["vertices"]
+    assert int(L["n_parts"].sum()) == truth["parts"] and int(L["n_rings"].sum()) == truth["rings"]
+    assert int(L["num_features"].sum()) == truth["features"]
+    # order-insensitive checksum of all assembled coordinates (closing vertices included)
+    coords = res.buffer(abi.BUF_A_COORDS)
+    sx = sy = 0
+    for row in L:
+        o, n = int(row["out"][abi.BUF_A_COORDS]), int(row["n_coords"])
+        c = coords[o:o + 2 * n].astype(np.int64)
+        sx += int(c[0::2].sum())
+        sy += int(c[1::2].sum())
+    assert (sx, sy) == (truth["sum_x_closed"], truth["sum_y_closed"])
+    res.free()
+
+
+def test_synthetic_index_buffer_config4(covt, oracle, gen, decoder):
+    """Config 4: polygon-heavy tiles carrying the INDEX_BUFFER extension stream (FAST_PFOR_DELTA_ZIG_ZAG); parity
+    is against the oracle only (the reference defines IndexBuffer in prose, README.md:114-121)."""
+    abi = covt.abi
+    p = gen.default_params(with_index_buffer=1, p_point=0.05, p_line=0.15, p_polygon=0.6, p_multiline=0.05,
+                           p_multipolygon=0.15, mean_features=120, mean_ring_extra=12)
+    blob, offs, truth = gen.tiles(7, 600, p)
+    res, ref = _decode_both(covt, oracle, decoder, blob, offs)
+    util.compare_results(abi, res, ref)
+    assert res.device_buffer(abi.BUF_S_INDEX_BUFFER)[1] > 0
+    res.free()
+
+
+def test_large_layers(covt, oracle, gen, decoder):
+    """Layers far larger than one warp chunk / FastPFOR page (multi-page streams, > 65 536 values)."""
+    abi = covt.abi
+    p = gen.default_params(mean_features=30000, layers_per_tile=2)
+    blob, offs, truth = gen.tiles(5, 6, p)
+    res, ref = _decode_both(covt, oracle, decoder, blob, offs)
+    util.compare_results(abi, res, ref)
+    assert int(res.layers["n_vertices"].sum()) == truth["vertices"]
+    res.free()
+
+
+def test_malformed_tiles_do_not_poison_the_batch(covt, oracle, gen, decoder, fixtures):
+    """Truncated tiles, garbage, an empty tile and a gen-2a tile between good ones: per-tile status, neighbours intact."""
+    abi = covt.abi
+    good = dict(fixtures)["omt/5_17_21"]
+    rng = np.random.default_rng(5)
+    tiles = [good, good[: len(good) // 2], bytes(rng.integers(0, 256, 5000, dtype=np.uint8)), b"", good[:37], good,
+             good[:-1], bytes(200), good + b"\x00"]
+    blob, offs = util.concat_tiles(tiles)
+    flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+    res, ref = _decode_both(covt, oracle, decoder, blob, offs, flags=flags)
+    st, _ = res.tile_status()
+    assert st[0] == 0 and st[5] == 0 and st[1] != 0 and st[3] != 0
+    util.compare_results(abi, res, ref)
+    res.free()
+    # corrupt single bytes inside stream payloads: status may be anything, but the call must survive and
+    # every tile the oracle accepts must match
+    for seed in range(6):
+        r = np.random.default_rng(seed)
+        b = bytearray(good)
+        for _ in range(4):
+            b[int(r.integers(200, len(b)))] ^= int(r.integers(1, 256))
+        blob, offs = util.concat_tiles([good, bytes(b), good])
+        res = decoder.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags)
+        ref = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags)
+        st, _ = res.tile_status()
+        assert st[0] == 0 and st[2] == 0
+        ok = (res.layers["status"] == 0) & (ref.layers["status"] == 0)
+        assert ok.sum() >= 2 * (len(ok) // 3)
+        res.free()
+
+
+def test_empty_batch_and_split_api(covt, oracle, decoder, fixtures):
+    abi = covt.abi
+    res = decoder.decode_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert res.n_tiles == 0 and res.n_layers == 0
+    res.free()
+    # upload once, decode twice (device-resident timing path): identical results
+    blob, offs = util.concat_tiles([b for n, b in fixtures if n.startswith("omt/6_")])
+    batch = decoder.upload(blob, offs)
+    r1 = decoder.decode(batch, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT | abi.FLAG_ID_DVZZ_IS_RLE | abi.FLAG_PROFILE_KERNELS)
+    r2 = decoder.decode(batch, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT | abi.FLAG_ID_DVZZ_IS_RLE)
+    util.compare_results(abi, r1, r2)
+    kt = {k["name"]: k for k in r1.kernel_times()}
+    assert "k_decode_layers" in kt and kt["k_decode_layers"]["ms"] > 0
+    t = r1.timing()
+    assert t["decode_ms"] > 0 and t["payload_bytes"] > 0 and t["vertices"] > 0
+    r1.free()
+    r2.free()
+    batch.free()

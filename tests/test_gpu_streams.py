@@ -1,0 +1,211 @@
+"""GPU parity tests of the stream path (covt_decode_streams = the static codecs of DecodingUtils.java)
+against the CPU oracle: every op, lengths straddling the 16/32/256/512/65 536 boundaries, every byte alignment,
+the reference's known-answer vectors, and large streams through the multi-CTA look-back kernel."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import vectors
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 2, 15, 16, 17, 31, 32, 33, 255, 256, 257, 300, 511, 512, 513, 1023, 1024, 4097, 65535, 65536, 65537, 70000, 140000]
+
+
+def _rand_values(rng, n, kind):
+    if kind == "small":
+        return rng.integers(0, 100, n)
+    if kind == "walk":
+        return np.cumsum(rng.integers(-300, 300, n))
+    if kind == "wide":
+        return rng.integers(-(1 << 26), 1 << 26, n)
+    if kind == "runs":
+        out = []
+        while len(out) < n:
+            if rng.random() < 0.5:
+                base, d, k = int(rng.integers(0, 1000)), int(rng.integers(-3, 4)), int(rng.integers(3, 200))
+                out += [base + d * i for i in range(k)]
+            else:
+                out += list(rng.integers(0, 1 << 20, int(rng.integers(1, 40))))
+        return np.asarray(out[:n])
+    raise ValueError(kind)
+
+
+def _batch_check(covt, oracle, decoder, cases, flags=None):
+    """cases: list of (op, payload bytes ndarray, num_values, num_bits, exact). Runs them all in ONE covt_decode_streams
+    call (each at a different byte alignment) and compares every output with the oracle."""
+    abi = covt.abi
+    if flags is None:
+        flags = abi.FLAG_DEFAULT
+    blob = bytearray()
+    descs = (abi.StreamDesc * len(cases))()
+    for i, (op, payload, n, nbits, exact) in enumerate(cases):
+        blob += bytes((i * 7 + 3) % 16 + (1 if i % 3 == 0 else 0))  # vary the alignment
+        off = len(blob)
+        blob += bytes(payload)
+        slack = 0 if exact else 37  # varint/RLE calls only know where the stream starts (DecodingUtils "pos")
+        descs[i] = abi.StreamDesc(byte_offset=off, byte_length=len(payload) + slack, num_values=n, num_bits=nbits, op=op)
+        if not exact:
+            blob += bytes([0x80] * 3) + bytes(slack - 3)  # trailing garbage that must not be touched
+    blob += bytes(64)
+    blob = np.frombuffer(bytes(blob), dtype=np.uint8)
+    res = decoder.decode_streams(blob, descs, flags)
+    arena = res.buffer(abi.BUF_STREAM_ARENA)
+    for i, (op, payload, n, nbits, exact) in enumerate(cases):
+        d = descs[i]
+        want, wst, wcons = oracle.decode_stream(blob, op, byte_offset=d.byte_offset, byte_length=d.byte_length, num_values=n,
+                                                num_bits=nbits, flags=flags)
+        assert (d.status == 0) == (wst == 0), "case %d op %s: status %d vs oracle %d" % (i, abi.OP_NAMES[op], d.status, wst)
+        if wst != 0:
+            continue
+        dt = np.dtype(abi.op_dtype(op))
+        got = arena[d.out_offset:d.out_offset + d.out_count * dt.itemsize].view(dt)
+        assert d.out_count == len(want), "case %d op %s count %d vs %d" % (i, abi.OP_NAMES[op], d.out_count, len(want))
+        if not np.array_equal(got, want):
+            bad = np.nonzero(got != want)[0]
+            raise AssertionError("case %d op %s n=%d differs at %s: got %s want %s" % (i, abi.OP_NAMES[op], n, bad[:6], got[bad[:6]], want[bad[:6]]))
+        assert d.bytes_consumed == wcons, "case %d op %s consumed %d vs %d" % (i, abi.OP_NAMES[op], d.bytes_consumed, wcons)
+    res.free()
+
+
+def test_known_answer_vectors(covt, oracle, decoder):
+    """The reference's own vectors (parser/js/test/unit/decoder/decodingUtils.spec.ts) through the GPU path."""
+    abi = covt.abi
+    for v in vectors.VECTORS:
+        op = getattr(abi, v["op"])
+        got, st, cons = decoder.decode_stream(np.asarray(v["bytes"], dtype=np.uint8), op, byte_offset=v.get("offset", 0),
+                                              num_values=v["n"])
+        assert st == 0, v["name"]
+        assert list(got) == v["expect"], v["name"]
+        assert cons == v["consumed"], v["name"]
+
+
+def test_varint32_ops(covt, oracle, gen, decoder):
+    abi = covt.abi
+    rng = np.random.default_rng(1)
+    cases = []
+    for n in SIZES:
+        for kind in ("small", "walk", "wide"):
+            v = _rand_values(rng, n, kind).astype(np.int64)
+            cases.append((abi.OP_VARINT_U32, gen.encode_varints(np.abs(v) & 0x0FFFFFFF), n, 0, False))
+            cases.append((abi.OP_VARINT_ZZ, gen.encode_varints(v, zigzag=True), n, 0, False))
+            cases.append((abi.OP_VARINT_ZZ_DELTA, gen.encode_varints(v, zigzag=True, delta=True), n, 0, False))
+            n2 = n & ~1
+            xy = _rand_values(rng, n2, kind).astype(np.int32)
+            zz = gen.encode_zigzag_delta_coordinates(xy).astype(np.int64) & 0xFFFFFFFF
+            cases.append((abi.OP_VARINT_ZZ_DELTA_XY, gen.encode_varints(zz), n2, 0, False))
+        codes = np.sort(rng.integers(0, 1 << 26, n)).astype(np.int64)
+        for nbits in (13, 14):
+            cases.append((abi.OP_VARINT_DELTA_MORTON, gen.encode_varints(codes, delta=True), n, nbits, False))
+    _batch_check(covt, oracle, decoder, cases)
+    _batch_check(covt, oracle, decoder, [c for c in cases if c[0] == abi.OP_VARINT_DELTA_MORTON][:12], flags=abi.FLAG_MORTON_NO_SHIFT)
+
+
+def test_varint64_and_id_ops(covt, oracle, gen, decoder):
+    abi = covt.abi
+    rng = np.random.default_rng(2)
+    cases = []
+    for n in SIZES[:20]:
+        big = rng.integers(0, 1 << 62, n).astype(np.int64)
+        cases.append((abi.OP_VARINT_U64, gen.encode_varints(big), n, 0, False))
+        walk = np.cumsum(rng.integers(-(1 << 40), 1 << 40, n)).astype(np.int64)
+        cases.append((abi.OP_VARINT_ZZ_DELTA_64, gen.encode_varints(walk, zigzag=True, delta=True), n, 0, False))
+        small = rng.integers(0, 1 << 27, n).astype(np.int64)
+        cases.append((abi.OP_VARINT_U32_AS_I64, gen.encode_varints(small), n, 0, False))
+        cases.append((abi.OP_VARINT_ZZ_DELTA_AS_I64, gen.encode_varints(np.cumsum(rng.integers(-99, 99, n)), zigzag=True, delta=True), n, 0, False))
+    # extremes
+    ext = np.array([0, 1, -1, (1 << 63) - 1, -(1 << 63), 1 << 35, 127, 128], dtype=np.int64)
+    cases.append((abi.OP_VARINT_U64, gen.encode_varints(ext), len(ext), 0, False))
+    cases.append((abi.OP_VARINT_ZZ_DELTA_64, gen.encode_varints(ext, zigzag=True, delta=True), len(ext), 0, False))
+    _batch_check(covt, oracle, decoder, cases)
+
+
+def test_rle_ops(covt, oracle, gen, decoder):
+    abi = covt.abi
+    rng = np.random.default_rng(3)
+    cases = []
+    for n in SIZES[:21]:
+        for kind in ("runs", "small", "wide"):
+            v = _rand_values(rng, n, kind).astype(np.int64)
+            cases.append((abi.OP_RLE_U32, gen.encode_rle(np.abs(v)), n, 0, False))
+            cases.append((abi.OP_RLE_U64, gen.encode_rle(np.abs(v) << 20), n, 0, False))
+            cases.append((abi.OP_RLE_S64, gen.encode_rle(v, signed=True), n, 0, False))
+        b = _rand_values(rng, n, "runs").astype(np.uint8) % 6
+        cases.append((abi.OP_BYTE_RLE, gen.encode_byte_rle(b), n, 0, False))
+        cases.append((abi.OP_BYTE_RLE, gen.encode_byte_rle(rng.integers(0, 256, n).astype(np.uint8)), n, 0, True))
+    _batch_check(covt, oracle, decoder, cases)
+
+
+def test_fastpfor_ops(covt, oracle, gen, decoder):
+    abi = covt.abi
+    rng = np.random.default_rng(4)
+    cases = []
+    for n in SIZES:
+        for kind in ("small", "walk", "wide"):
+            v = _rand_values(rng, n, kind).astype(np.int32)
+            cases.append((abi.OP_PFOR_ZZ_DELTA, gen.encode_fastpfor(v, zigzag=True, delta=True), n, 0, True))
+            n2 = n & ~1
+            zz = gen.encode_zigzag_delta_coordinates(v[:n2])
+            cases.append((abi.OP_PFOR_ZZ_DELTA_XY, gen.encode_fastpfor(zz), n2, 0, True))
+        # exception-heavy: mostly small values with outliers of many widths
+        v = rng.integers(0, 8, n).astype(np.int64)
+        idx = rng.random(n) < 0.12
+        v[idx] = rng.integers(0, 1 << 30, int(idx.sum())) >> rng.integers(0, 29, int(idx.sum()))
+        cases.append((abi.OP_PFOR_ZZ_DELTA, gen.encode_fastpfor(np.cumsum(v).astype(np.int32), zigzag=True, delta=True), n, 0, True))
+        codes = np.sort(rng.integers(0, 1 << 27, n)).astype(np.int32)
+        cases.append((abi.OP_PFOR_DELTA_MORTON, gen.encode_fastpfor(codes, delta=True), n, 13, True))
+        cases.append((abi.OP_PFOR_DELTA_MORTON, gen.encode_fastpfor(codes, delta=True), n, 14, True))
+    # full 32-bit values (b = 32) and all-zero blocks (b = 0)
+    cases.append((abi.OP_PFOR_ZZ_DELTA, gen.encode_fastpfor(rng.integers(-(1 << 31), 1 << 31, 1024).astype(np.int32), zigzag=True), 1024, 0, True))
+    cases.append((abi.OP_PFOR_ZZ_DELTA, gen.encode_fastpfor(np.zeros(700, np.int32), zigzag=True, delta=True), 700, 0, True))
+    _batch_check(covt, oracle, decoder, cases)
+
+
+def test_malformed_streams(covt, oracle, gen, decoder):
+    """Truncated / overlong / miscounted streams: the GPU flags exactly what the oracle flags."""
+    abi = covt.abi
+    rng = np.random.default_rng(6)
+    v = np.cumsum(rng.integers(-500, 500, 2000)).astype(np.int64)
+    enc = gen.encode_varints(v, zigzag=True, delta=True)
+    cases = [
+        (abi.OP_VARINT_ZZ_DELTA, enc[:1000], 2000, 0, True),                                   # truncated
+        (abi.OP_VARINT_ZZ_DELTA, np.array([0x80, 0x80, 0x80, 0x80, 0x01] * 10, np.uint8), 10, 0, True),  # 5-byte varints
+        (abi.OP_VARINT_ZZ_DELTA_XY, enc, 1999, 0, True),                                       # odd coordinate count
+        (abi.OP_RLE_U32, gen.encode_rle(np.arange(500))[:-1], 500, 0, True),
+        (abi.OP_BYTE_RLE, gen.encode_byte_rle(np.arange(300).astype(np.uint8))[:-5], 300, 0, True),
+        (abi.OP_PFOR_ZZ_DELTA, gen.encode_fastpfor(v.astype(np.int32), True, True), 2100, 0, True),  # numValues too large
+        (abi.OP_PFOR_ZZ_DELTA, gen.encode_fastpfor(v.astype(np.int32), True, True), 1900, 0, True),  # numValues too small
+        (abi.OP_PFOR_ZZ_DELTA, gen.encode_fastpfor(v.astype(np.int32), True, True)[:2000], 2000, 0, True),
+        (abi.OP_PFOR_ZZ_DELTA, rng.integers(0, 256, 3000).astype(np.uint8), 1000, 0, True),      # garbage
+        (abi.OP_VARINT_ZZ_DELTA, enc, 2000, 0, True),                                          # and a good one
+    ]
+    _batch_check(covt, oracle, decoder, cases)
+
+
+@pytest.mark.parametrize("post", ["OP_VARINT_ZZ_DELTA_XY", "OP_VARINT_ZZ_DELTA", "OP_VARINT_DELTA_MORTON", "OP_VARINT_ZZ", "OP_VARINT_U32"])
+def test_large_varint_streams_lookback_kernel(covt, oracle, gen, decoder, post):
+    """Streams >= 256 KiB take the multi-CTA decoupled-look-back kernel; several streams per launch, any alignment."""
+    abi = covt.abi
+    op = getattr(abi, post)
+    cases = []
+    for k, target in enumerate([1 << 18, (1 << 20) + 13, 3 * (1 << 20) + 4095]):
+        if op == abi.OP_VARINT_DELTA_MORTON:
+            rng = np.random.default_rng(k)
+            n = target // 2
+            enc = gen.encode_varints(np.cumsum(rng.integers(0, 40000, n)).astype(np.int64) & 0x3FFFFFF, delta=False)
+            vals = n
+        else:
+            enc, vals = gen.varint_stream(target & ~1 if op == abi.OP_VARINT_ZZ_DELTA_XY else target, seed=0xC0717 + k)
+        cases.append((op, enc, vals, 14, True))
+    _batch_check(covt, oracle, decoder, cases)
+
+
+def test_config3_shape_roundtrip(covt, gen, decoder):
+    """Config 3 at 64 MiB: decode -> re-encode the coordinates -> identical bytes (size-independent round trip)."""
+    abi = covt.abi
+    enc, n = gen.varint_stream(64 << 20, seed=0xC0717)
+    got, st, cons = decoder.decode_stream(enc, abi.OP_VARINT_ZZ_DELTA_XY, num_values=n, byte_length=len(enc))
+    assert st == 0 and len(got) == n
+    zz = gen.encode_zigzag_delta_coordinates(got).astype(np.int64) & 0xFFFFFFFF
+    assert np.array_equal(gen.encode_varints(zz), enc)
