@@ -284,6 +284,7 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
 
     uint64_t *d_cols = nullptr, *d_block_sums = nullptr, *d_totals = nullptr;
     uint32_t *d_tj = nullptr, *d_counter = nullptr;
+    DeviceTask* d_tasks = nullptr;
     const uint32_t nb = (n_tiles + 255) / 256;
     int32_t rc = COVT_OK;
     auto cleanup_tmp = [&]() {
@@ -292,6 +293,7 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
         dev_free(ctx, d_totals);
         dev_free(ctx, d_tj);
         dev_free(ctx, d_counter);
+        dev_free(ctx, d_tasks);
     };
 #define CKR(call)                                                                                     \
     do {                                                                                              \
@@ -310,7 +312,7 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
     CKR(dev_alloc(ctx, &d_cols, (uint64_t)TILE_COLS * std::max(n_tiles, 1u)));
     CKR(dev_alloc(ctx, &d_block_sums, (uint64_t)TILE_COLS * std::max(nb, 1u)));
     CKR(dev_alloc(ctx, &d_totals, 32));
-    CKR(dev_alloc(ctx, &d_counter, 4));
+    CKR(dev_alloc(ctx, &d_counter, 16));
     CKR(dev_alloc(ctx, &R->d_tile_status, (uint64_t)n_tiles + 1));
     CKR(dev_alloc(ctx, &R->d_first_layer, (uint64_t)n_tiles + 2));
     uint32_t tj_layers = 0;
@@ -320,7 +322,7 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
         CKR(cudaMemcpyAsync(d_tj, tilejson->n_fields, tj_layers * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     }
     CKR(cudaMemsetAsync(d_totals, 0, 32 * sizeof(uint64_t), st));
-    CKR(cudaMemsetAsync(d_counter, 0, 4 * sizeof(uint32_t), st));
+    CKR(cudaMemsetAsync(d_counter, 0, 16 * sizeof(uint32_t), st));
 
     CKR(cudaEventRecord(ev0, st));
     // ---- K0 pass 1: layers per tile + slice sizes; scan; one small read-back sizes everything ----
@@ -342,20 +344,31 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
         if (bytes) CKR(cudaMallocAsync(&R->bufs[b], bytes + 64, st));
     }
     CKR(dev_alloc(ctx, &R->d_layers, (uint64_t)R->n_layers));
-    // ---- K0 pass 2: the layer table ----
-    prof.begin("k0_fill_layers", 0);
-    CKR(launch_k0_fill_layers(batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, flags, d_cols, R->d_layers, R->d_first_layer, st));
-    prof.end();
-    CKR(cudaMemcpyAsync(R->d_first_layer + n_tiles, &R->n_layers, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    // ---- every stream of every layer + assembly ----
+    CKR(dev_alloc(ctx, &d_tasks, (uint64_t)R->n_layers * COVT_NUM_SLOTS));
     ResultBuffers rb;
     for (int b = 0; b < COVT_NUM_BUFFERS; b++) rb.ptr[b] = R->bufs[b];
-    prof.begin("k_decode_layers", 0);
-    CKR(launch_decode_layers(batch->d_blob, R->d_layers, R->n_layers, rb, flags, d_counter, ctx->sm_count, st));
+    // ---- K0 pass 2: the layer table + eight decode tasks per layer ----
+    prof.begin("k0_fill_layers", 0);
+    CKR(launch_k0_fill_layers(batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, flags, d_cols, rb, R->d_layers, d_tasks, R->d_first_layer, st));
+    prof.end();
+    CKR(cudaMemcpyAsync(R->d_first_layer + n_tiles, &R->n_layers, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // ---- every stream of every layer: one kernel per codec class ----
+    const uint32_t n_tasks = R->n_layers * COVT_NUM_SLOTS;
+    uint32_t launches = 5;
+    for (int c = 0; c < NUM_OP_CLASSES; c++) {
+        prof.begin(op_class_name(c), 0);
+        CKR(launch_decode_class(c, batch->d_blob, d_tasks, n_tasks, d_counter + c, ctx->sm_count, st));
+        prof.end();
+        launches++;
+    }
+    // ---- geometry assembly ----
+    prof.begin("k_assemble_layers", 0);
+    CKR(launch_assemble_layers(R->d_layers, d_tasks, R->n_layers, rb, flags, d_counter + 8, ctx->sm_count, st));
     prof.end();
     prof.begin("k_finalize", 0);
     CKR(launch_finalize(R->d_layers, R->d_first_layer, n_tiles, flags, R->d_tile_status, d_totals + 16, st));
     prof.end();
+    launches += 2;
     CKR(cudaEventRecord(ev1, st));
     CKR(cudaMemcpyAsync(ctx->h_totals + 16, d_totals + 16, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CKR(cudaStreamSynchronize(st));
@@ -366,13 +379,8 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
     R->timing.vertices = ctx->h_totals[16];
     R->timing.payload_bytes = ctx->h_totals[17];
     R->timing.output_bytes = ctx->h_totals[18];
-    R->timing.kernel_launches = 8;  // k0_scan_tiles, 3 scan kernels, k0_fill_layers, k_decode_layers, k_finalize (+0 when empty)
-    if (prof.on) {
-        prof.collect(R->kernel_times);
-        for (auto& k : R->kernel_times)
-            if (!strcmp(k.name, "k_decode_layers")) k.algorithmic_bytes = R->timing.payload_bytes + R->timing.output_bytes;
-    }
-    R->timing.kernel_launches = n_tiles ? 7 : 0;
+    if (prof.on) prof.collect(R->kernel_times);
+    R->timing.kernel_launches = n_tiles ? launches : 0;  // k0_scan_tiles, 3 scan kernels, k0_fill_layers, 5 codec classes, assemble, finalize
     (void)out_bytes_alloc;
     cleanup_tmp();
 #undef CKR
@@ -433,7 +441,8 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     std::vector<BigStream> bigs;
     std::vector<ChunkRef> chunks;
     std::vector<uint32_t> big_task;
-    uint64_t arena = 0, payload = 0, out_bytes = 0, big_alg = 0, small_alg = 0;
+    uint64_t arena = 0, payload = 0, out_bytes = 0, big_alg = 0;
+    uint64_t class_alg[NUM_OP_CLASSES] = {};
     const uint64_t BIG_BYTES = 1u << 18;  // streams of >= 256 KiB take the multi-CTA look-back kernel
     for (uint32_t i = 0; i < n; i++) {
         covt_stream_desc& d = descs[i];
@@ -450,7 +459,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
         const uint64_t cnt = morton ? 2ull * d.num_values : d.num_values;
         d.out_count = cnt;
         t.src_offset = d.byte_offset;
-        t.dst_offset = arena;
+        t.dst = reinterpret_cast<uint8_t*>(arena);  // offset for now, rebased once the arena is allocated
         t.byte_length = d.byte_length;
         t.num_values = d.num_values;
         t.op = (uint8_t)op;
@@ -482,7 +491,15 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
             t.op = COVT_OP_NONE;  // the warp-per-stream kernel skips it
             big_alg += d.byte_length + ob;
         } else {
-            small_alg += d.byte_length + ob;
+            int c = -1;
+            switch (op) {
+            case COVT_OP_BYTE_RLE: c = CLASS_BYTE_RLE; break;
+            case COVT_OP_RLE_U32: case COVT_OP_RLE_U64: case COVT_OP_RLE_S64: c = CLASS_RLE; break;
+            case COVT_OP_VARINT_U64: case COVT_OP_VARINT_ZZ_DELTA_64: c = CLASS_VARINT64; break;
+            case COVT_OP_PFOR_ZZ_DELTA: case COVT_OP_PFOR_ZZ_DELTA_XY: case COVT_OP_PFOR_DELTA_MORTON: c = CLASS_PFOR; break;
+            default: c = CLASS_VARINT32; break;
+            }
+            class_alg[c] += d.byte_length + ob;
         }
     }
     DeviceTask* d_tasks = nullptr;
@@ -517,14 +534,16 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     R->counts[COVT_BUF_STREAM_ARENA] = arena;
     CKR(cudaMallocAsync(&R->bufs[COVT_BUF_STREAM_ARENA], arena + 64, st));
     CKR(dev_alloc(ctx, &d_tasks, n));
-    CKR(dev_alloc(ctx, &d_counter, 4));
+    CKR(dev_alloc(ctx, &d_counter, 16));
+    for (uint32_t i = 0; i < n; i++)
+        tasks[i].dst = reinterpret_cast<uint8_t*>(R->bufs[COVT_BUF_STREAM_ARENA]) + reinterpret_cast<uintptr_t>(tasks[i].dst);
     if (!bigs.empty()) {
         CKR(dev_alloc(ctx, &d_bigs, bigs.size()));
         CKR(dev_alloc(ctx, &d_chunks, chunks.size()));
         CKR(dev_alloc(ctx, &d_states, chunks.size()));
         for (size_t k = 0; k < bigs.size(); k++) {
             const uint32_t i = big_task[k];
-            bigs[k].dst = reinterpret_cast<uint8_t*>(R->bufs[COVT_BUF_STREAM_ARENA]) + tasks[i].dst_offset;
+            bigs[k].dst = tasks[i].dst;
             bigs[k].status_out = &d_tasks[i].status;
             bigs[k].consumed_out = &d_tasks[i].consumed;
         }
@@ -532,19 +551,20 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
         CKR(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
     }
     if (n) CKR(cudaMemcpyAsync(d_tasks, tasks.data(), (uint64_t)n * sizeof(DeviceTask), cudaMemcpyHostToDevice, st));
-    CKR(cudaMemsetAsync(d_counter, 0, 4 * sizeof(uint32_t), st));
+    CKR(cudaMemsetAsync(d_counter, 0, 16 * sizeof(uint32_t), st));
     CKR(cudaEventRecord(ev0, st));
     uint32_t launches = 0;
     if (!bigs.empty()) {
         CKR(cudaMemsetAsync(d_states, 0, chunks.size() * sizeof(ChunkState), st));
         prof.begin("k1_varint_stream", big_alg);
-        CKR(launch_k1_varint_stream(batch->d_blob, d_bigs, d_chunks, (uint32_t)chunks.size(), d_states, d_counter + 1, st));
+        CKR(launch_k1_varint_stream(batch->d_blob, d_bigs, d_chunks, (uint32_t)chunks.size(), d_states, d_counter + 8, st));
         prof.end();
         launches++;
     }
-    if (n > bigs.size()) {
-        prof.begin("k_decode_tasks", small_alg);
-        CKR(launch_decode_tasks(batch->d_blob, d_tasks, n, reinterpret_cast<uint8_t*>(R->bufs[COVT_BUF_STREAM_ARENA]), d_counter, ctx->sm_count, st));
+    for (int c = 0; c < NUM_OP_CLASSES; c++) {
+        if (!class_alg[c]) continue;
+        prof.begin(op_class_name(c), class_alg[c]);
+        CKR(launch_decode_class(c, batch->d_blob, d_tasks, n, d_counter + c, ctx->sm_count, st));
         prof.end();
         launches++;
     }

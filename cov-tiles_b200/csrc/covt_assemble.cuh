@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t search32(const uint32_t* arr, uint32_t key)
     return lo;
 }
 
-__device__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmResult& res)
+__device__ __noinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmResult& res)
 {
     const unsigned lane = lane_id();
     uint32_t* f_start = sm;            // [33] exclusive prefix of parts per feature

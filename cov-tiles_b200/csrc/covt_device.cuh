@@ -184,10 +184,10 @@ __device__ __forceinline__ uint32_t gather_msb16(const uint32_t words[4])
     return r;
 }
 
-template <bool VB, bool ZZ>
+template <bool VB>
 __device__ __forceinline__ void varint32_chunk_decode(uint4 w, uint32_t valid16, uint32_t& carry_halo, uint32_t limit,
                                                       uint32_t* stage, uint32_t& emit, uint32_t& lane_excl,
-                                                      uint32_t& chunk_total, bool& overlong)
+                                                      uint32_t& chunk_total, bool& overlong, const bool ZZ)
 {
     uint32_t words[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -240,20 +240,21 @@ __device__ __forceinline__ void varint32_chunk_decode(uint4 w, uint32_t valid16,
 // Blocked delta pass over the values staged by varint32_chunk_decode / the FastPFOR unpacker:
 // stage[0..n) holds deltas; on return it holds final values. carry is advanced.
 // PER = values per lane (16 for a 512-value chunk, 8 for a FastPFOR block of 256).
-// ZZ_AT_LOAD: the staged values are still zigzag-encoded (FastPFOR path, DecodingUtils.java:335-343).
-template <int POST, int PER, bool ZZ_AT_LOAD>
-__device__ __forceinline__ void warp_delta_pass(uint32_t* stage, uint32_t n, DeltaCarry& carry)
+// zz_at_load: the staged values are still zigzag-encoded (FastPFOR path, DecodingUtils.java:335-343).
+// `post` is warp-uniform, so the branches below do not diverge.
+template <int PER>
+__device__ __forceinline__ void warp_delta_pass(uint32_t* stage, uint32_t n, DeltaCarry& carry, const int post, const bool zz_at_load)
 {
-    if (POST == POST_PLAIN || POST == POST_ZZ) return;
+    if (post == POST_PLAIN || post == POST_ZZ) return;
     const unsigned lane = lane_id();
     int32_t v[PER];
 #pragma unroll
     for (int j = 0; j < PER; j++) {
         uint32_t i = lane * PER + j;
         uint32_t raw = i < n ? stage[stage_index(i)] : 0u;
-        v[j] = ZZ_AT_LOAD ? zigzag_decode32(raw) : (int32_t)raw;
+        v[j] = zz_at_load ? zigzag_decode32(raw) : (int32_t)raw;
     }
-    if (POST == POST_ZZ_DELTA_XY) {
+    if (post == POST_ZZ_DELTA_XY) {
         // global index parity of position i is (produced + j) & 1 because lane*PER is even
         const bool swap = carry.produced & 1u;
         int32_t a = 0, b = 0;  // a: even j, b: odd j
@@ -289,23 +290,30 @@ __device__ __forceinline__ void warp_delta_pass(uint32_t* stage, uint32_t n, Del
     }
 }
 
-// Coalesced copy of stage[0..n) to dst[first ..] (Morton: expands each code to an (x,y) pair).
-template <int POST, int PER>
-__device__ __forceinline__ void warp_copy_out(const uint32_t* stage, uint32_t n, int32_t* dst, uint64_t first,
+// Coalesced copy of stage[0..n) to dst[first ..]: int32, widened to int64 (ids), or expanded Morton (x,y) pairs.
+enum CopyKind { COPY_I32 = 0, COPY_I64 = 1, COPY_MORTON = 2 };
+template <int PER>
+__device__ __forceinline__ void warp_copy_out(const uint32_t* stage, uint32_t n, void* dst, uint64_t first, const int kind,
                                               uint32_t num_bits, bool no_shift)
 {
     const unsigned lane = lane_id();
+    if (kind == COPY_MORTON) {
+#pragma unroll 4
+        for (int k = 0; k < PER; k++) {
+            uint32_t i = lane + 32u * k;
+            if (i < n) reinterpret_cast<int2*>(dst)[first + i] = morton_decode((int32_t)stage[stage_index(i)], num_bits, no_shift);
+        }
+    } else if (kind == COPY_I64) {
+#pragma unroll 4
+        for (int k = 0; k < PER; k++) {
+            uint32_t i = lane + 32u * k;
+            if (i < n) reinterpret_cast<int64_t*>(dst)[first + i] = (int64_t)(int32_t)stage[stage_index(i)];
+        }
+    } else {
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-        uint32_t i = lane + 32u * k;
-        if (i < n) {
-            uint32_t val = stage[stage_index(i)];
-            if (POST == POST_DELTA_MORTON) {
-                int2 xy = morton_decode((int32_t)val, num_bits, no_shift);
-                reinterpret_cast<int2*>(dst)[first + i] = xy;
-            } else {
-                dst[first + i] = (int32_t)val;
-            }
+        for (int k = 0; k < PER; k++) {
+            uint32_t i = lane + 32u * k;
+            if (i < n) reinterpret_cast<int32_t*>(dst)[first + i] = (int32_t)stage[stage_index(i)];
         }
     }
 }

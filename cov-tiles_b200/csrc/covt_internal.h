@@ -14,16 +14,22 @@ constexpr int TILE_COLS = 1 + COVT_NUM_BUFFERS;  // column 0 = layers per tile, 
 
 struct ResultBuffers { void* ptr[COVT_NUM_BUFFERS]; };
 
-// one decode request of the stream path (device copy of a covt_stream_desc, ops resolved on the host)
+// One stream to decode. The batch path keeps COVT_NUM_SLOTS of them per layer (task index = layer * 8 + slot,
+// written by k0_fill_layers); the stream path builds them on the host from covt_stream_desc.
 struct DeviceTask {
     uint64_t src_offset;   // into the batch blob
-    uint64_t dst_offset;   // byte offset into the stream arena
+    uint8_t* dst;          // absolute device pointer of the output slice (16-byte aligned)
     uint32_t byte_length;
     uint32_t num_values;
-    uint8_t op, num_bits, no_shift, exact_length;
+    uint8_t op;            // covt_op; COVT_OP_NONE = nothing to do (absent slot, unsupported, or taken by the look-back kernel)
+    uint8_t num_bits, no_shift, exact_length;
     uint32_t status;       // out
     uint32_t consumed;     // out
+    uint32_t pad;
 };
+
+// codec classes = one small kernel each (the instruction working set of a kernel must stay cache-resident)
+enum OpClass { CLASS_BYTE_RLE = 0, CLASS_RLE = 1, CLASS_VARINT32 = 2, CLASS_VARINT64 = 3, CLASS_PFOR = 4, NUM_OP_CLASSES = 5 };
 
 // a large 32-bit delta-varint stream handled by the multi-CTA look-back kernel
 struct BigStream {
@@ -38,13 +44,10 @@ struct BigStream {
     uint8_t post, num_bits, no_shift, pad;
 };
 struct ChunkRef { uint32_t stream, chunk; };
-// look-back record of one chunk: flag 0 = nothing, 1 = aggregate, 2 = inclusive prefix
-struct ChunkState {
-    uint32_t flag;
-    uint32_t pad[3];
-    uint32_t agg_count; int32_t agg_a, agg_b; uint32_t pad1;  // local parity: a = sum at even local positions
-    uint32_t inc_count; int32_t inc_x, inc_y; uint32_t pad2;
-};
+// look-back record of one chunk, read and written with ONE 128-bit access (flag + payload are never torn):
+// flag 0 = nothing yet, 1 = aggregate of this chunk (a/b = sums at even/odd positions relative to the chunk start),
+// 2 = inclusive prefix of the stream up to and including this chunk (a/b = running x/y)
+struct __align__(16) ChunkState { uint32_t flag, count; int32_t a, b; };
 constexpr int K1_WARPS = 8;
 constexpr int K1_TILE_BYTES = K1_WARPS * 512;
 
@@ -57,11 +60,13 @@ cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offse
 cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_t* block_sums, uint64_t* totals, cudaStream_t st);
 cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
                                   const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                                  covt_layer* layers, uint32_t* first_layer, cudaStream_t st);
-cudaError_t launch_decode_layers(const uint8_t* blob, covt_layer* layers, uint32_t n_layers, ResultBuffers bufs, uint32_t flags,
-                                 uint32_t* work_counter, int sm_count, cudaStream_t st);
-cudaError_t launch_decode_tasks(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint8_t* arena, uint32_t* work_counter,
+                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, cudaStream_t st);
+// one codec class over a task table; work_counter must be zero
+cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
                                 int sm_count, cudaStream_t st);
+const char* op_class_name(int op_class);
+cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers, ResultBuffers bufs, uint32_t flags,
+                                   uint32_t* work_counter, int sm_count, cudaStream_t st);
 cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, const ChunkRef* chunks, uint32_t n_chunks,
                                     ChunkState* states, uint32_t* ticket, cudaStream_t st);
 cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags,

@@ -404,8 +404,11 @@ __global__ void k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets,
 // pass 2: write the covt_layer table with result offsets (tile_cols now holds exclusive prefixes)
 __global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
                                const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                               covt_layer* layers, uint32_t* first_layer)
+                               ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer)
 {
+    const uint8_t slot_buf[COVT_NUM_SLOTS] = {COVT_BUF_S_IDS, COVT_BUF_S_GEOMETRY_TYPES, COVT_BUF_S_GEOMETRY_OFFSETS,
+                                              COVT_BUF_S_PART_OFFSETS, COVT_BUF_S_RING_OFFSETS, COVT_BUF_S_VERTEX_OFFSETS,
+                                              COVT_BUF_S_VERTEX_BUFFER, COVT_BUF_S_INDEX_BUFFER};
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     uint64_t run[TILE_COLS];
@@ -422,6 +425,29 @@ __global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets
         uint4* dst = reinterpret_cast<uint4*>(&layers[run[0]]);
         const uint4* src = reinterpret_cast<const uint4*>(&L);
         for (unsigned i = 0; i < sizeof(covt_layer) / 16; i++) dst[i] = src[i];
+        // the layer's eight decode tasks
+        for (int s = 0; s < COVT_NUM_SLOTS; s++) {
+            const covt_stream_ref& r = L.streams[s];
+            DeviceTask t;
+            t.src_offset = r.byte_offset;
+            t.dst = nullptr;
+            t.byte_length = r.byte_length;
+            t.num_values = r.num_values;
+            t.op = COVT_OP_NONE;
+            t.num_bits = L.num_bits;
+            t.no_shift = (flags & COVT_FLAG_MORTON_NO_SHIFT) ? 1 : 0;
+            t.exact_length = 1;
+            t.status = r.status;
+            t.consumed = 0;
+            t.pad = 0;
+            if (r.encoding != COVT_ENC_ABSENT && L.status != COVT_ERR_BAD_METADATA) {
+                const uint32_t b = slot_buf[s];
+                t.dst = reinterpret_cast<uint8_t*>(bufs.ptr[b]) + L.out[b] * kBufElemSizeDev(b);
+                t.op = r.op;
+                if (s == COVT_SLOT_VBUF && L.geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) t.num_values *= 2;
+            }
+            tasks[run[0] * COVT_NUM_SLOTS + s] = t;
+        }
         run[0] += 1;
     });
 }
@@ -486,10 +512,14 @@ __global__ void scan_apply(uint64_t* cols, uint32_t n, const uint64_t* block_sum
 }
 
 // =================================================================================================
-// one warp per layer: all streams, then the assembler
+// Stream decode: ONE KERNEL PER CODEC CLASS over a task table (one warp per stream).
+// Each kernel carries a single codec, so its instructions stay cache-resident and every warp of an SM runs the same
+// code; an earlier all-codecs-in-one-kernel version stalled ~85 % of its issue slots on instruction fetch
+// (profiles/r01_layers_fused_ncu.txt). A warp scans 32 task slots at a time, ballots the ones of its class and
+// decodes them one after the other; 32-slot groups are handed out dynamically for load balance.
 // =================================================================================================
-constexpr int LAYER_WARPS = 4;
-constexpr int LAYER_WARP_SMEM = WARP_SMEM_BYTES + 384;  // stage + a private copy of the covt_layer (368 B)
+constexpr int DEC_WARPS = 4;
+constexpr int DEC_WARP_SMEM = WARP_SMEM_BYTES;
 
 __device__ __forceinline__ uint32_t warp_next_work(uint32_t* counter)
 {
@@ -498,70 +528,123 @@ __device__ __forceinline__ uint32_t warp_next_work(uint32_t* counter)
     return __shfl_sync(FULL, v, 0);
 }
 
-__global__ void __launch_bounds__(LAYER_WARPS * 32)
-k_decode_layers(const uint8_t* blob, covt_layer* layers, uint32_t n_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter)
+__host__ __device__ inline int op_class_of(uint32_t op)
+{
+    switch (op) {
+    case COVT_OP_BYTE_RLE: return CLASS_BYTE_RLE;
+    case COVT_OP_RLE_U32: case COVT_OP_RLE_U64: case COVT_OP_RLE_S64: return CLASS_RLE;
+    case COVT_OP_VARINT_U32: case COVT_OP_VARINT_ZZ: case COVT_OP_VARINT_ZZ_DELTA: case COVT_OP_VARINT_ZZ_DELTA_XY:
+    case COVT_OP_VARINT_DELTA_MORTON: case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: return CLASS_VARINT32;
+    case COVT_OP_VARINT_U64: case COVT_OP_VARINT_ZZ_DELTA_64: return CLASS_VARINT64;
+    case COVT_OP_PFOR_ZZ_DELTA: case COVT_OP_PFOR_ZZ_DELTA_XY: case COVT_OP_PFOR_DELTA_MORTON: return CLASS_PFOR;
+    default: return -1;
+    }
+}
+
+template <int CLASS>
+__device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, StreamOutcome& o)
+{
+    uint32_t* stage = reinterpret_cast<uint32_t*>(wsm);
+    o.status = COVT_OK;
+    o.consumed = 0;
+    if (CLASS == CLASS_BYTE_RLE) warp_byte_rle_stream(t, o);
+    else if (CLASS == CLASS_RLE) {
+        if (t.op == COVT_OP_RLE_U32) warp_rle_stream<int32_t, false>(t, o);
+        else if (t.op == COVT_OP_RLE_U64) warp_rle_stream<int64_t, false>(t, o);
+        else warp_rle_stream<int64_t, true>(t, o);
+    } else if (CLASS == CLASS_VARINT32) {
+        if (t.op == COVT_OP_VARINT_ZZ_DELTA_XY && (t.num_values & 1u)) { o.status = COVT_ERR_COUNT_MISMATCH; return; }
+        const bool widen = t.op == COVT_OP_VARINT_U32_AS_I64 || t.op == COVT_OP_VARINT_ZZ_DELTA_AS_I64;
+        const int post = t.op == COVT_OP_VARINT_U32_AS_I64 ? POST_PLAIN : (t.op == COVT_OP_VARINT_ZZ_DELTA_AS_I64 ? POST_ZZ_DELTA : post_kind_of_op(t.op));
+        warp_varint32_stream(t, stage, o, post, widen);
+    } else if (CLASS == CLASS_VARINT64) {
+        if (t.op == COVT_OP_VARINT_U64) warp_varint64_stream<false>(t, reinterpret_cast<uint64_t*>(wsm), o);
+        else warp_varint64_stream<true>(t, reinterpret_cast<uint64_t*>(wsm), o);
+    } else {
+        if (t.op == COVT_OP_PFOR_ZZ_DELTA_XY && (t.num_values & 1u)) { o.status = COVT_ERR_COUNT_MISMATCH; return; }
+        warp_pfor_stream(t, stage, o, post_kind_of_op(t.op));
+    }
+}
+
+template <int CLASS>
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t* wsm = smem + warp * LAYER_WARP_SMEM;
-    covt_layer* L = reinterpret_cast<covt_layer*>(wsm + WARP_SMEM_BYTES);
-    const uint8_t slot_buf[COVT_NUM_SLOTS] = {COVT_BUF_S_IDS, COVT_BUF_S_GEOMETRY_TYPES, COVT_BUF_S_GEOMETRY_OFFSETS,
-                                              COVT_BUF_S_PART_OFFSETS, COVT_BUF_S_RING_OFFSETS, COVT_BUF_S_VERTEX_OFFSETS,
-                                              COVT_BUF_S_VERTEX_BUFFER, COVT_BUF_S_INDEX_BUFFER};
+    uint8_t* wsm = smem + warp * DEC_WARP_SMEM;
+    const uint32_t n_groups = (n_tasks + 31u) / 32u;
+    for (;;) {
+        const uint32_t g = warp_next_work(work_counter);
+        if (g >= n_groups) break;
+        const uint32_t mine = g * 32u + lane;
+        uint32_t op = COVT_OP_NONE;
+        if (mine < n_tasks) op = tasks[mine].op;
+        unsigned todo = __ballot_sync(FULL, op_class_of(op) == CLASS);
+        while (todo) {
+            const int src_lane = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t i = g * 32u + src_lane;
+            const DeviceTask d = tasks[i];
+            StreamTask t;
+            t.src = blob + d.src_offset;
+            t.dst = d.dst;
+            t.byte_length = d.byte_length;
+            t.num_values = d.num_values;
+            t.op = d.op;
+            t.num_bits = d.num_bits;
+            t.no_shift = d.no_shift;
+            t.exact_length = d.exact_length;
+            StreamOutcome o;
+            decode_one<CLASS>(t, wsm, o);
+            __syncwarp();
+            if (lane == 0) { tasks[i].status = o.status; tasks[i].consumed = o.consumed; }
+        }
+    }
+}
+
+// =================================================================================================
+// geometry assembly: one warp per layer (after every stream of the batch has been decoded)
+// =================================================================================================
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+k_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter)
+{
+    __shared__ uint32_t s_asm[DEC_WARPS][ASM_SMEM_WORDS + 6];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     for (;;) {
         const uint32_t l = warp_next_work(work_counter);
         if (l >= n_layers) break;
-        // private copy of the layer record (23 x 16 B)
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(&layers[l]);
-            uint4* dst = reinterpret_cast<uint4*>(L);
-            if (lane < sizeof(covt_layer) / 16) dst[lane] = src[lane];
-        }
-        __syncwarp();
+        covt_layer* L = &layers[l];
         uint32_t layer_status = L->status;
         if (layer_status == COVT_ERR_BAD_METADATA) continue;
-        void* dst[COVT_NUM_SLOTS];
-#pragma unroll
-        for (int s = 0; s < COVT_NUM_SLOTS; s++) {
-            dst[s] = nullptr;
-            const covt_stream_ref r = L->streams[s];
-            if (r.encoding == COVT_ENC_ABSENT) continue;
-            const uint32_t b = slot_buf[s];
-            dst[s] = reinterpret_cast<uint8_t*>(bufs.ptr[b]) + L->out[b] * kBufElemSizeDev(b);
-            if (r.op == COVT_OP_NONE) continue;
-            StreamTask t;
-            t.src = blob + r.byte_offset;
-            t.dst = dst[s];
-            t.byte_length = r.byte_length;
-            t.num_values = r.num_values;
-            if (s == COVT_SLOT_VBUF && L->geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) t.num_values *= 2;
-            t.op = r.op;
-            t.num_bits = L->num_bits;
-            t.no_shift = (flags & COVT_FLAG_MORTON_NO_SHIFT) ? 1 : 0;
-            t.exact_length = 1;
-            StreamOutcome o;
-            warp_decode_stream(t, wsm, o);
-            __syncwarp();
-            if (lane == 0) layers[l].streams[s].status = o.status;
-            if (o.status != COVT_OK && !layer_status) layer_status = o.status;
+        // fold the stream outcomes into the layer record: first error in slot order is the layer's status
+        uint32_t st = 0;
+        if (lane < COVT_NUM_SLOTS) {
+            st = tasks[(uint64_t)l * COVT_NUM_SLOTS + lane].status;
+            if (L->streams[lane].encoding != COVT_ENC_ABSENT) L->streams[lane].status = st;
+            else st = 0;
         }
+        const unsigned bad = __ballot_sync(FULL, st != 0);
+        if (bad && !layer_status) layer_status = __shfl_sync(FULL, st, __ffs(bad) - 1);
         AsmResult ar = {COVT_OK, 0, 0, 0, 0};
         if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && layer_status == COVT_OK) {
             LayerIO io;
-            io.types = reinterpret_cast<const uint8_t*>(dst[COVT_SLOT_TYPES]);
+            auto slice = [&](int slot, int b) -> const void* {
+                if (L->streams[slot].encoding == COVT_ENC_ABSENT) return nullptr;
+                return reinterpret_cast<const uint8_t*>(bufs.ptr[b]) + L->out[b] * kBufElemSizeDev(b);
+            };
+            io.types = reinterpret_cast<const uint8_t*>(slice(COVT_SLOT_TYPES, COVT_BUF_S_GEOMETRY_TYPES));
             io.F = L->streams[COVT_SLOT_TYPES].num_values;
-            io.geom = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_GEOM]);
+            io.geom = reinterpret_cast<const int32_t*>(slice(COVT_SLOT_GEOM, COVT_BUF_S_GEOMETRY_OFFSETS));
             io.n_geom = io.geom ? L->streams[COVT_SLOT_GEOM].num_values : 0;
-            io.part = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_PART]);
+            io.part = reinterpret_cast<const int32_t*>(slice(COVT_SLOT_PART, COVT_BUF_S_PART_OFFSETS));
             io.n_part = io.part ? L->streams[COVT_SLOT_PART].num_values : 0;
-            io.ring = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_RING]);
+            io.ring = reinterpret_cast<const int32_t*>(slice(COVT_SLOT_RING, COVT_BUF_S_RING_OFFSETS));
             io.n_ring = io.ring ? L->streams[COVT_SLOT_RING].num_values : 0;
-            io.voff = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_VOFF]);
+            io.voff = reinterpret_cast<const int32_t*>(slice(COVT_SLOT_VOFF, COVT_BUF_S_VERTEX_OFFSETS));
             io.n_voff = io.voff ? L->streams[COVT_SLOT_VOFF].num_values : 0;
-            io.vbuf = reinterpret_cast<const int32_t*>(dst[COVT_SLOT_VBUF]);
-            uint64_t vb_ints = L->streams[COVT_SLOT_VBUF].num_values;
-            if (L->geom_column_type == COVT_CT_ICE_MORTON_CODE) vb_ints *= 2;
-            else if (L->geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) vb_ints *= 2;
+            io.vbuf = reinterpret_cast<const int32_t*>(slice(COVT_SLOT_VBUF, COVT_BUF_S_VERTEX_BUFFER));
+            const uint64_t vb_ints = vbuf_ints_of(*L, flags);
             io.vbuf_ints = vb_ints;
             io.a_geom = reinterpret_cast<int32_t*>(bufs.ptr[COVT_BUF_A_GEOM_OFFSETS]) + L->out[COVT_BUF_A_GEOM_OFFSETS];
             io.a_part = reinterpret_cast<int32_t*>(bufs.ptr[COVT_BUF_A_PART_OFFSETS]) + L->out[COVT_BUF_A_PART_OFFSETS];
@@ -572,76 +655,88 @@ k_decode_layers(const uint8_t* blob, covt_layer* layers, uint32_t n_layers, Resu
             const uint64_t V = io.voff ? io.n_voff : vb_ints / 2;
             io.cap_coords = V + ((flags & COVT_FLAG_CLOSE_RINGS) ? io.n_ring : 0);
             io.close_rings = (flags & COVT_FLAG_CLOSE_RINGS) != 0;
-            __syncwarp();
-            warp_assemble(io, reinterpret_cast<uint32_t*>(wsm), ar);
+            warp_assemble(io, s_asm[warp], ar);
             if (ar.status != COVT_OK) layer_status = ar.status;
         }
         if (lane == 0) {
-            layers[l].status = layer_status;
-            layers[l].n_parts = ar.n_parts;
-            layers[l].n_rings = ar.n_rings;
-            layers[l].n_vertices = ar.n_vertices;
-            layers[l].n_coords = ar.n_coords;
+            L->status = layer_status;
+            L->n_parts = ar.n_parts;
+            L->n_rings = ar.n_rings;
+            L->n_vertices = ar.n_vertices;
+            L->n_coords = ar.n_coords;
         }
         __syncwarp();
-    }
-}
-
-// =================================================================================================
-// one warp per stream request (stream path)
-// =================================================================================================
-__global__ void __launch_bounds__(LAYER_WARPS * 32)
-k_decode_tasks(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint8_t* arena, uint32_t* work_counter)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t* wsm = smem + warp * LAYER_WARP_SMEM;
-    for (;;) {
-        const uint32_t i = warp_next_work(work_counter);
-        if (i >= n_tasks) break;
-        const DeviceTask d = tasks[i];
-        if (d.op == COVT_OP_NONE) continue;  // handled elsewhere (big stream) or unsupported: status preset by the host
-        StreamTask t;
-        t.src = blob + d.src_offset;
-        t.dst = arena + d.dst_offset;
-        t.byte_length = d.byte_length;
-        t.num_values = d.num_values;
-        t.op = d.op;
-        t.num_bits = d.num_bits;
-        t.no_shift = d.no_shift;
-        t.exact_length = d.exact_length;
-        StreamOutcome o;
-        warp_decode_stream(t, wsm, o);
-        __syncwarp();
-        if (lane == 0) { tasks[i].status = o.status; tasks[i].consumed = o.consumed; }
     }
 }
 
 // =================================================================================================
 // K1: one large 32-bit varint stream over many CTAs, single pass, decoupled look-back
 // =================================================================================================
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+__device__ __forceinline__ uint4 ld_state(const ChunkState* p)
 {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
 }
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+__device__ __forceinline__ void st_state(ChunkState* p, uint32_t flag, uint32_t count, int32_t a, int32_t b)
 {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(flag), "r"(count), "r"(a), "r"(b) : "memory");
 }
 
 // (count, a, b): a / b = sums at even / odd positions relative to the segment start.
-// left ⊕ right: the right segment's parity flips when the left count is odd.
+// left (+) right: the right segment's parity flips when the left count is odd. Associative, not commutative.
 struct Trip { uint32_t c; int32_t a, b; };
+template <bool XY>
 __device__ __forceinline__ Trip trip_combine(const Trip& l, const Trip& r)
 {
     Trip o;
     o.c = l.c + r.c;
-    const bool odd = l.c & 1u;
-    o.a = l.a + (odd ? r.b : r.a);
-    o.b = l.b + (odd ? r.a : r.b);
+    if (XY) {
+        const bool odd = l.c & 1u;
+        o.a = l.a + (odd ? r.b : r.a);
+        o.b = l.b + (odd ? r.a : r.b);
+    } else {
+        o.a = l.a + r.a;
+        o.b = 0;
+    }
     return o;
+}
+__device__ __forceinline__ Trip trip_shfl(const Trip& t, int src)
+{
+    Trip o;
+    o.c = __shfl_sync(FULL, t.c, src);
+    o.a = __shfl_sync(FULL, t.a, src);
+    o.b = __shfl_sync(FULL, t.b, src);
+    return o;
+}
+
+// Decoupled look-back executed by warp 0: lane k inspects predecessor (chunk - 1 - k) of the same stream, 32 at a time.
+// Returns the exclusive prefix of this chunk (uniform across the warp).
+template <bool XY>
+__device__ __forceinline__ Trip k1_lookback(ChunkState* states, uint32_t chunk_global, uint32_t ci)
+{
+    const unsigned lane = lane_id();
+    Trip acc = {0, 0, 0};        // combined aggregates of the chunks between the window and this chunk
+    uint32_t back = 0;           // predecessors already consumed
+    for (;;) {
+        const uint32_t k = back + lane;          // this lane looks at predecessor number k (0 = nearest)
+        const bool valid = k < ci;               // never leave the stream: chunk 0 of the stream publishes an inclusive record
+        uint4 st = make_uint4(0, 0, 0, 0);
+        if (valid) {
+            const ChunkState* pj = &states[chunk_global - 1 - k];
+            while ((st = ld_state(pj)).x == 0u) __nanosleep(40);
+        }
+        const unsigned inc_mask = __ballot_sync(FULL, valid && st.x == 2u);
+        const unsigned valid_mask = __ballot_sync(FULL, valid);
+        // lanes [0, stop] take part: `stop` is the nearest inclusive record, or the last valid lane
+        const int stop = inc_mask ? (__ffs(inc_mask) - 1) : (31 - __clz(valid_mask));
+        Trip mine = {st.y, (int32_t)st.z, (int32_t)st.w};
+        Trip w = trip_shfl(mine, stop);
+        for (int q = stop - 1; q >= 0; q--) w = trip_combine<XY>(w, trip_shfl(mine, q));
+        acc = trip_combine<XY>(w, acc);
+        if (inc_mask) return acc;
+        back += 32;
+    }
 }
 
 template <int POST>
@@ -662,14 +757,13 @@ __device__ void k1_body(const uint8_t* blob, const BigStream& S, uint32_t chunk_
     const uint32_t lo16 = off >= head ? 0u : (uint32_t)umin64(16, head - off);
     const uint32_t hi16 = off >= total ? 0u : (uint32_t)umin64(16, total - off);
     const uint32_t valid16 = ((1u << hi16) - 1u) & ~((1u << lo16) - 1u);
-    // halo of lane 0 = the 4 bytes before this warp's sub-chunk (always inside the stream when off >= 512)
+    // halo of lane 0 = the 4 bytes before this warp's sub-chunk (inside the stream whenever off >= 512)
     uint32_t halo = 0;
     if (lane == 0 && off > 0 && off < total + 4) halo = __ldg(reinterpret_cast<const uint32_t*>(a0 + off - 4));
-    if (lane == 0 && off > 0 && off - 4 < head) halo &= ~((1u << (8u * (head - (uint32_t)(off - 4)))) - 1u);
     uint32_t emit, excl, wtotal;
     bool overlong = false;
     uint32_t* stage = s_stage[warp];
-    varint32_chunk_decode<false, ZZ>(w, valid16, halo, 0xffffffffu, stage, emit, excl, wtotal, overlong);
+    varint32_chunk_decode<false>(w, valid16, halo, 0xffffffffu, stage, emit, excl, wtotal, overlong, ZZ);
     __syncwarp();
     // blocked local sums (values stay in registers across the two block barriers)
     int32_t v[16];
@@ -687,47 +781,34 @@ __device__ void k1_body(const uint8_t* blob, const BigStream& S, uint32_t chunk_
     }
     if (lane == 0) { s_warp[warp].c = wtotal; s_warp[warp].a = ta; s_warp[warp].b = tb; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
         Trip agg = s_warp[0];
-        for (int k = 1; k < K1_WARPS; k++) agg = XY ? trip_combine(agg, s_warp[k]) : Trip{agg.c + s_warp[k].c, agg.a + s_warp[k].a, 0};
+#pragma unroll
+        for (int k = 1; k < K1_WARPS; k++) agg = trip_combine<XY>(agg, s_warp[k]);
         ChunkState* me = &states[chunk_global];
         Trip prefix = {0, 0, 0};
         if (ci > 0) {
-            me->agg_count = agg.c; me->agg_a = agg.a; me->agg_b = agg.b;
-            __threadfence();
-            st_release_u32(&me->flag, 1u);
-            // decoupled look-back over the predecessors of the same stream
-            Trip acc = {0, 0, 0};
-            uint32_t j = chunk_global - 1;
-            for (;;) {
-                const ChunkState* pj = &states[j];
-                uint32_t f;
-                while ((f = ld_acquire_u32(&pj->flag)) == 0u) __nanosleep(20);
-                if (f == 2u) {
-                    Trip inc = {*(volatile const uint32_t*)&pj->inc_count, *(volatile const int32_t*)&pj->inc_x, *(volatile const int32_t*)&pj->inc_y};
-                    prefix = XY ? trip_combine(inc, acc) : Trip{inc.c + acc.c, inc.a + acc.a, 0};
-                    break;
-                }
-                Trip a = {*(volatile const uint32_t*)&pj->agg_count, *(volatile const int32_t*)&pj->agg_a, *(volatile const int32_t*)&pj->agg_b};
-                acc = XY ? trip_combine(a, acc) : Trip{a.c + acc.c, a.a + acc.a, 0};
-                j--;
-            }
+            if (lane == 0) st_state(me, 1u, agg.c, agg.a, agg.b);
+            prefix = k1_lookback<XY>(states, chunk_global, ci);
         }
-        const Trip inc = XY ? trip_combine(prefix, agg) : Trip{prefix.c + agg.c, prefix.a + agg.a, 0};
-        me->inc_count = inc.c; me->inc_x = inc.a; me->inc_y = inc.b;
-        __threadfence();
-        st_release_u32(&me->flag, 2u);
-        *s_prefix = prefix;
-        if (ci == S.n_chunks - 1) {  // last chunk of the stream: totals are known
-            if (inc.c < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
-            if (S.consumed_out) *S.consumed_out = S.byte_length;
+        const Trip inc = trip_combine<XY>(prefix, agg);
+        if (lane == 0) {
+            st_state(me, 2u, inc.c, inc.a, inc.b);
+            *s_prefix = prefix;
+            if (ci == S.n_chunks - 1 && inc.c < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
         }
     }
     if (__any_sync(FULL, overlong) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
     __syncthreads();
     // this warp's exclusive prefix
     Trip P = *s_prefix;
-    for (unsigned k = 0; k < warp; k++) P = XY ? trip_combine(P, s_warp[k]) : Trip{P.c + s_warp[k].c, P.a + s_warp[k].a, 0};
+    for (unsigned k = 0; k < warp; k++) P = trip_combine<XY>(P, s_warp[k]);
+    // bytes the reference reader consumes = position right after the terminator of value #num_values
+    {
+        const uint32_t first = P.c + excl, cnt = __popc(emit);
+        if (S.consumed_out && S.num_values > first && S.num_values <= first + cnt)
+            *S.consumed_out = (uint32_t)(off + __fns(emit, 0, (int)(S.num_values - first)) + 1u - head);
+    }
     if (DELTA) {
         if (XY) {
             const bool swap = P.c & 1u;  // position i of this warp has global parity (P.c + i) & 1 and lane*16 is even
@@ -751,7 +832,7 @@ __device__ void k1_body(const uint8_t* blob, const BigStream& S, uint32_t chunk_
     }
     // coalesced copy-out, clipped to num_values
     const uint32_t room = P.c < S.num_values ? S.num_values - P.c : 0u;
-    warp_copy_out<POST, 16>(stage, min(wtotal, room), reinterpret_cast<int32_t*>(S.dst), P.c, S.num_bits, S.no_shift != 0);
+    warp_copy_out<16>(stage, min(wtotal, room), S.dst, P.c, POST == POST_DELTA_MORTON ? COPY_MORTON : COPY_I32, S.num_bits, S.no_shift != 0);
 }
 
 __global__ void __launch_bounds__(K1_WARPS * 32)
@@ -839,35 +920,48 @@ cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_
 
 cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
                                   const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                                  covt_layer* layers, uint32_t* first_layer, cudaStream_t st)
+                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    k0_fill_layers<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, flags, tile_cols, layers, first_layer);
+    k0_fill_layers<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, flags, tile_cols, bufs, layers, tasks, first_layer);
     return cudaGetLastError();
 }
 
-static int grid_for(int sm_count, int per_sm, uint32_t n_items, int warps_per_block)
+static int grid_for(int sm_count, int per_sm, uint64_t n_items, int items_per_block)
 {
-    int64_t want = ((int64_t)n_items + warps_per_block - 1) / warps_per_block;
+    int64_t want = ((int64_t)n_items + items_per_block - 1) / items_per_block;
     int64_t cap = (int64_t)sm_count * per_sm;
     return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
-cudaError_t launch_decode_layers(const uint8_t* blob, covt_layer* layers, uint32_t n_layers, ResultBuffers bufs, uint32_t flags,
-                                 uint32_t* work_counter, int sm_count, cudaStream_t st)
+const char* op_class_name(int c)
 {
-    if (!n_layers) return cudaSuccess;
-    const int smem = LAYER_WARPS * LAYER_WARP_SMEM;
-    k_decode_layers<<<grid_for(sm_count, 12, n_layers, LAYER_WARPS), LAYER_WARPS * 32, smem, st>>>(blob, layers, n_layers, bufs, flags, work_counter);
-    return cudaGetLastError();
+    static const char* names[NUM_OP_CLASSES] = {"k_decode_byte_rle", "k_decode_rle", "k_decode_varint32", "k_decode_varint64", "k_decode_pfor"};
+    return c >= 0 && c < NUM_OP_CLASSES ? names[c] : "?";
 }
 
-cudaError_t launch_decode_tasks(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint8_t* arena, uint32_t* work_counter,
+cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
                                 int sm_count, cudaStream_t st)
 {
     if (!n_tasks) return cudaSuccess;
-    const int smem = LAYER_WARPS * LAYER_WARP_SMEM;
-    k_decode_tasks<<<grid_for(sm_count, 12, n_tasks, LAYER_WARPS), LAYER_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, arena, work_counter);
+    const int smem = DEC_WARPS * DEC_WARP_SMEM;
+    const int grid = grid_for(sm_count, 12, ((uint64_t)n_tasks + 31) / 32, DEC_WARPS);
+    switch (op_class) {
+    case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
+    case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
+    case CLASS_VARINT32: k_decode_class<CLASS_VARINT32><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
+    case CLASS_VARINT64: k_decode_class<CLASS_VARINT64><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
+    case CLASS_PFOR: k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers, ResultBuffers bufs, uint32_t flags,
+                                   uint32_t* work_counter, int sm_count, cudaStream_t st)
+{
+    if (!n_layers) return cudaSuccess;
+    k_assemble_layers<<<grid_for(sm_count, 12, n_layers, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, tasks, n_layers, bufs, flags, work_counter);
     return cudaGetLastError();
 }
 

@@ -33,23 +33,7 @@ __device__ __forceinline__ uint32_t chunk_cut_position(uint32_t emit, uint32_t l
     return __shfl_sync(FULL, pos, __ffs(b) - 1);
 }
 
-template <int POST, bool WIDEN>
-__device__ __forceinline__ void copy_out_select(const uint32_t* stage, uint32_t n, void* dst, uint64_t first, const StreamTask& t)
-{
-    if (WIDEN) {
-        const unsigned lane = lane_id();
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            uint32_t i = lane + 32u * k;
-            if (i < n) reinterpret_cast<int64_t*>(dst)[first + i] = (int64_t)(int32_t)stage[stage_index(i)];
-        }
-    } else {
-        warp_copy_out<POST, 16>(stage, n, reinterpret_cast<int32_t*>(dst), first, t.num_bits, t.no_shift != 0);
-    }
-}
-
-template <int POST, bool WIDEN>
-__device__ void warp_varint32_stream(const StreamTask& t, uint32_t* stage, StreamOutcome& out)
+__device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t* stage, StreamOutcome& out, const int post, const bool widen)
 {
     const unsigned lane = lane_id();
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(t.src) & ~uintptr_t(15);
@@ -59,7 +43,8 @@ __device__ void warp_varint32_stream(const StreamTask& t, uint32_t* stage, Strea
     uint32_t halo = 0;
     bool overlong = false;
     uint32_t consumed = 0;
-    constexpr bool ZZ = (POST == POST_ZZ || POST == POST_ZZ_DELTA || POST == POST_ZZ_DELTA_XY);
+    const bool zz = (post == POST_ZZ || post == POST_ZZ_DELTA || post == POST_ZZ_DELTA_XY);
+    const int copy_kind = widen ? COPY_I64 : (post == POST_DELTA_MORTON ? COPY_MORTON : COPY_I32);
     for (uint64_t base = 0; base < total && carry.produced < t.num_values; base += WARP_CHUNK_BYTES) {
         const uint64_t off = base + lane * 16u;
         uint4 w = make_uint4(0, 0, 0, 0);
@@ -82,12 +67,12 @@ __device__ void warp_varint32_stream(const StreamTask& t, uint32_t* stage, Strea
                 valid16 &= (1u << keep) - 1u;
             }
         }
-        varint32_chunk_decode<false, ZZ>(w, valid16, halo, remaining, stage, emit, excl, ctotal, overlong);
+        varint32_chunk_decode<false>(w, valid16, halo, remaining, stage, emit, excl, ctotal, overlong, zz);
         const uint32_t n = min(ctotal, remaining);
         __syncwarp();
-        warp_delta_pass<POST, 16, false>(stage, n, carry);
+        warp_delta_pass<16>(stage, n, carry, post, false);
         __syncwarp();
-        copy_out_select<POST, WIDEN>(stage, n, t.dst, carry.produced, t);
+        warp_copy_out<16>(stage, n, t.dst, carry.produced, copy_kind, t.num_bits, t.no_shift != 0);
         __syncwarp();
         carry.produced += n;
     }
@@ -101,7 +86,7 @@ __device__ void warp_varint32_stream(const StreamTask& t, uint32_t* stage, Strea
 // 64-bit varints for ids (ID_WIDTH 64): inverse of EncodingUtils.encodeVarints (EncodingUtils.java:39-55)
 // =================================================================================================
 template <bool ZZ_DELTA>
-__device__ void warp_varint64_stream(const StreamTask& t, uint64_t* stage, StreamOutcome& out)
+__device__ __noinline__ void warp_varint64_stream(const StreamTask& t, uint64_t* stage, StreamOutcome& out)
 {
     const unsigned lane = lane_id();
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(t.src) & ~uintptr_t(15);
@@ -238,7 +223,7 @@ __device__ __forceinline__ bool read_vulong(const uint8_t* src, uint32_t len, ui
 }
 
 template <typename OutT, bool SIGNED>
-__device__ void warp_rle_stream(const StreamTask& t, StreamOutcome& out)
+__device__ __noinline__ void warp_rle_stream(const StreamTask& t, StreamOutcome& out)
 {
     const unsigned lane = lane_id();
     const uint8_t* src = t.src;
@@ -283,7 +268,7 @@ __device__ void warp_rle_stream(const StreamTask& t, StreamOutcome& out)
     out.consumed = pos;
 }
 
-__device__ void warp_byte_rle_stream(const StreamTask& t, StreamOutcome& out)
+__device__ __noinline__ void warp_byte_rle_stream(const StreamTask& t, StreamOutcome& out)
 {
     const unsigned lane = lane_id();
     const uint8_t* src = t.src;
@@ -335,14 +320,14 @@ __device__ __forceinline__ uint32_t unpack_packed(const uint8_t* base, uint32_t 
     return k >= 32u ? v : (v & ((1u << k) - 1u));
 }
 
-template <int POST>
-__device__ void warp_pfor_stream(const StreamTask& t, uint32_t* stage, StreamOutcome& out)
+__device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* stage, StreamOutcome& out, const int post)
 {
     const unsigned lane = lane_id();
     const uint8_t* base = t.src;
     const uint32_t n_words = t.byte_length / 4u;  // (int)Math.ceil(byteLength / 4): integer division, DecodingUtils.java:324
     const uint32_t n = t.num_values;
-    constexpr bool ZZ = (POST == POST_ZZ_DELTA || POST == POST_ZZ_DELTA_XY);
+    const bool ZZ = (post == POST_ZZ_DELTA || post == POST_ZZ_DELTA_XY);
+    const int copy_kind = post == POST_DELTA_MORTON ? COPY_MORTON : COPY_I32;
     DeltaCarry carry = {0, 0, 0};
     uint32_t status = COVT_OK;
     uint32_t inpos = 0;
@@ -354,7 +339,7 @@ __device__ void warp_pfor_stream(const StreamTask& t, uint32_t* stage, StreamOut
             uint32_t m = min(512u, n - b0);
             for (uint32_t i = lane; i < m; i += 32) stage[stage_index(i)] = 0;
             __syncwarp();
-            warp_copy_out<POST, 16>(stage, m, reinterpret_cast<int32_t*>(t.dst), b0, t.num_bits, t.no_shift != 0);
+            warp_copy_out<16>(stage, m, t.dst, b0, copy_kind, t.num_bits, t.no_shift != 0);
             __syncwarp();
         }
         out.status = COVT_OK;
@@ -436,9 +421,9 @@ __device__ void warp_pfor_stream(const StreamTask& t, uint32_t* stage, StreamOut
                     bcpos += cexcept;
                 }
                 __syncwarp();
-                warp_delta_pass<POST, 8, ZZ>(stage, 256, carry);
+                warp_delta_pass<8>(stage, 256, carry, post, ZZ);
                 __syncwarp();
-                warp_copy_out<POST, 8>(stage, 256, reinterpret_cast<int32_t*>(t.dst), carry.produced, t.num_bits, t.no_shift != 0);
+                warp_copy_out<8>(stage, 256, t.dst, carry.produced, copy_kind, t.num_bits, t.no_shift != 0);
                 __syncwarp();
                 carry.produced += 256;
             }
@@ -460,13 +445,13 @@ __device__ void warp_pfor_stream(const StreamTask& t, uint32_t* stage, StreamOut
             }
             uint32_t emit, excl, ctotal;
             const uint32_t remaining = n - carry.produced;
-            varint32_chunk_decode<true, false>(make_uint4(words[0], words[1], words[2], words[3]), valid16, halo, remaining,
-                                               stage, emit, excl, ctotal, overlong);
+            varint32_chunk_decode<true>(make_uint4(words[0], words[1], words[2], words[3]), valid16, halo, remaining,
+                                        stage, emit, excl, ctotal, overlong, false);
             if (ctotal > remaining) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);  // Java: ArrayIndexOutOfBounds
             __syncwarp();
-            warp_delta_pass<POST, 16, ZZ>(stage, ctotal, carry);
+            warp_delta_pass<16>(stage, ctotal, carry, post, ZZ);
             __syncwarp();
-            warp_copy_out<POST, 16>(stage, ctotal, reinterpret_cast<int32_t*>(t.dst), carry.produced, t.num_bits, t.no_shift != 0);
+            warp_copy_out<16>(stage, ctotal, t.dst, carry.produced, copy_kind, t.num_bits, t.no_shift != 0);
             __syncwarp();
             carry.produced += ctotal;
         }
@@ -475,41 +460,6 @@ __device__ void warp_pfor_stream(const StreamTask& t, uint32_t* stage, StreamOut
 finish:
 #undef PFOR_FAIL
     out.status = status;
-}
-
-// =================================================================================================
-// dispatch on covt_op (rows a1..a10 of SURVEY §8a)
-// =================================================================================================
-__device__ void warp_decode_stream(const StreamTask& t, void* warp_smem, StreamOutcome& out)
-{
-    uint32_t* stage = reinterpret_cast<uint32_t*>(warp_smem);
-    out.status = COVT_OK;
-    out.consumed = 0;
-    switch (t.op) {
-    case COVT_OP_BYTE_RLE: warp_byte_rle_stream(t, out); break;
-    case COVT_OP_RLE_U32: warp_rle_stream<int32_t, false>(t, out); break;
-    case COVT_OP_RLE_U64: warp_rle_stream<int64_t, false>(t, out); break;
-    case COVT_OP_RLE_S64: warp_rle_stream<int64_t, true>(t, out); break;
-    case COVT_OP_VARINT_U32: warp_varint32_stream<POST_PLAIN, false>(t, stage, out); break;
-    case COVT_OP_VARINT_ZZ: warp_varint32_stream<POST_ZZ, false>(t, stage, out); break;
-    case COVT_OP_VARINT_ZZ_DELTA: warp_varint32_stream<POST_ZZ_DELTA, false>(t, stage, out); break;
-    case COVT_OP_VARINT_ZZ_DELTA_XY:
-        if (t.num_values & 1u) { out.status = COVT_ERR_COUNT_MISMATCH; break; }
-        warp_varint32_stream<POST_ZZ_DELTA_XY, false>(t, stage, out);
-        break;
-    case COVT_OP_VARINT_DELTA_MORTON: warp_varint32_stream<POST_DELTA_MORTON, false>(t, stage, out); break;
-    case COVT_OP_VARINT_U32_AS_I64: warp_varint32_stream<POST_PLAIN, true>(t, stage, out); break;
-    case COVT_OP_VARINT_ZZ_DELTA_AS_I64: warp_varint32_stream<POST_ZZ_DELTA, true>(t, stage, out); break;
-    case COVT_OP_VARINT_U64: warp_varint64_stream<false>(t, reinterpret_cast<uint64_t*>(warp_smem), out); break;
-    case COVT_OP_VARINT_ZZ_DELTA_64: warp_varint64_stream<true>(t, reinterpret_cast<uint64_t*>(warp_smem), out); break;
-    case COVT_OP_PFOR_ZZ_DELTA: warp_pfor_stream<POST_ZZ_DELTA>(t, stage, out); break;
-    case COVT_OP_PFOR_ZZ_DELTA_XY:
-        if (t.num_values & 1u) { out.status = COVT_ERR_COUNT_MISMATCH; break; }
-        warp_pfor_stream<POST_ZZ_DELTA_XY>(t, stage, out);
-        break;
-    case COVT_OP_PFOR_DELTA_MORTON: warp_pfor_stream<POST_DELTA_MORTON>(t, stage, out); break;
-    default: out.status = COVT_ERR_UNSUPPORTED_ENCODING; break;
-    }
 }
 
 }  // namespace covt

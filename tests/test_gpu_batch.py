@@ -210,7 +210,7 @@ def test_empty_batch_and_split_api(covt, oracle, decoder, fixtures):
     r2 = decoder.decode(batch, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT | abi.FLAG_ID_DVZZ_IS_RLE)
     util.compare_results(abi, r1, r2)
     kt = {k["name"]: k for k in r1.kernel_times()}
-    assert "k_decode_layers" in kt and kt["k_decode_layers"]["ms"] > 0
+    assert "k_assemble_layers" in kt and kt["k_assemble_layers"]["ms"] > 0 and "k_decode_varint32" in kt
     t = r1.timing()
     assert t["decode_ms"] > 0 and t["payload_bytes"] > 0 and t["vertices"] > 0
     r1.free()
