@@ -439,7 +439,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     Profiler prof = {ctx, (flags & COVT_FLAG_PROFILE_KERNELS) != 0, {}};
     std::vector<DeviceTask> tasks(n);
     std::vector<BigStream> bigs;
-    std::vector<ChunkRef> chunks;
+    uint32_t n_big_chunks = 0;
     std::vector<uint32_t> big_task;
     uint64_t arena = 0, payload = 0, out_bytes = 0, big_alg = 0;
     uint64_t class_alg[NUM_OP_CLASSES] = {};
@@ -479,13 +479,13 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
             b.src_offset = d.byte_offset;
             b.byte_length = d.byte_length;
             b.num_values = d.num_values;
-            b.first_chunk = (uint32_t)chunks.size();
+            b.first_chunk = n_big_chunks;
             const uint64_t window = (d.byte_offset & 15) + d.byte_length;  // blob base is 256-byte aligned
-            b.n_chunks = (uint32_t)((window + K1_TILE_BYTES - 1) / K1_TILE_BYTES);
+            b.n_chunks = (uint32_t)((window + 511) / 512);
+            n_big_chunks += b.n_chunks;
             b.post = (uint8_t)post;
             b.num_bits = d.num_bits;
             b.no_shift = t.no_shift;
-            for (uint32_t c = 0; c < b.n_chunks; c++) chunks.push_back(ChunkRef{(uint32_t)bigs.size(), c});
             bigs.push_back(b);
             big_task.push_back(i);
             t.op = COVT_OP_NONE;  // the warp-per-stream kernel skips it
@@ -504,14 +504,14 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     }
     DeviceTask* d_tasks = nullptr;
     BigStream* d_bigs = nullptr;
-    ChunkRef* d_chunks = nullptr;
+    ChunkState* d_block_states = nullptr;
     ChunkState* d_states = nullptr;
     uint32_t* d_counter = nullptr;
     int32_t rc = COVT_OK;
     auto cleanup_tmp = [&]() {
         dev_free(ctx, d_tasks);
         dev_free(ctx, d_bigs);
-        dev_free(ctx, d_chunks);
+        dev_free(ctx, d_block_states);
         dev_free(ctx, d_states);
         dev_free(ctx, d_counter);
     };
@@ -539,8 +539,8 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
         tasks[i].dst = reinterpret_cast<uint8_t*>(R->bufs[COVT_BUF_STREAM_ARENA]) + reinterpret_cast<uintptr_t>(tasks[i].dst);
     if (!bigs.empty()) {
         CKR(dev_alloc(ctx, &d_bigs, bigs.size()));
-        CKR(dev_alloc(ctx, &d_chunks, chunks.size()));
-        CKR(dev_alloc(ctx, &d_states, chunks.size()));
+        CKR(dev_alloc(ctx, &d_block_states, (uint64_t)n_big_chunks / K1_SCAN_BLOCK + 2));
+        CKR(dev_alloc(ctx, &d_states, n_big_chunks));
         for (size_t k = 0; k < bigs.size(); k++) {
             const uint32_t i = big_task[k];
             bigs[k].dst = tasks[i].dst;
@@ -548,18 +548,16 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
             bigs[k].consumed_out = &d_tasks[i].consumed;
         }
         CKR(cudaMemcpyAsync(d_bigs, bigs.data(), bigs.size() * sizeof(BigStream), cudaMemcpyHostToDevice, st));
-        CKR(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
     }
     if (n) CKR(cudaMemcpyAsync(d_tasks, tasks.data(), (uint64_t)n * sizeof(DeviceTask), cudaMemcpyHostToDevice, st));
     CKR(cudaMemsetAsync(d_counter, 0, 16 * sizeof(uint32_t), st));
     CKR(cudaEventRecord(ev0, st));
     uint32_t launches = 0;
     if (!bigs.empty()) {
-        CKR(cudaMemsetAsync(d_states, 0, chunks.size() * sizeof(ChunkState), st));
         prof.begin("k1_varint_stream", big_alg);
-        CKR(launch_k1_varint_stream(batch->d_blob, d_bigs, d_chunks, (uint32_t)chunks.size(), d_states, d_counter + 8, st));
+        CKR(launch_k1_varint_stream(batch->d_blob, d_bigs, (uint32_t)bigs.size(), n_big_chunks, d_states, d_block_states, st));
         prof.end();
-        launches++;
+        launches += 5;
     }
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
         if (!class_alg[c]) continue;

@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t search32(const uint32_t* arr, uint32_t key)
     return lo;
 }
 
-__device__ __noinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmResult& res)
+__device__ __forceinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmResult& res)
 {
     const unsigned lane = lane_id();
     uint32_t* f_start = sm;            // [33] exclusive prefix of parts per feature
@@ -65,14 +65,14 @@ __device__ __noinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmR
     for (uint32_t f0 = 0; f0 < io.F; f0 += 32) {
         const uint32_t f = f0 + lane;
         const bool fvalid = f < io.F;
-        const uint32_t t = fvalid ? io.types[f] : 0xffu;
+        const uint32_t t = fvalid ? __ldg(io.types + f) : 0xffu;
         ASM_CHECK(fvalid && (t == COVT_GT_MULTIPOINT || t > COVT_GT_MULTIPOLYGON), COVT_ERR_UNSUPPORTED_GEOMETRY);
         const bool uses_g = fvalid && (t == COVT_GT_MULTILINESTRING || t == COVT_GT_MULTIPOLYGON);
         uint32_t tot_g;
         const uint32_t gidx = gc + warp_exclusive_scan(uses_g ? 1u : 0u, tot_g);
         ASM_CHECK(uses_g && gidx >= io.n_geom, COVT_ERR_TOPOLOGY);
         int32_t nparts_s = fvalid ? 1 : 0;
-        if (uses_g) nparts_s = io.geom[gidx];
+        if (uses_g) nparts_s = __ldg(io.geom + gidx);
         ASM_CHECK(nparts_s < 0, COVT_ERR_TOPOLOGY);
         const uint32_t nparts = (uint32_t)nparts_s;
         const uint32_t part_entries = (fvalid && t != COVT_GT_POINT) ? nparts : 0u;
@@ -95,7 +95,7 @@ __device__ __noinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmR
                 const uint32_t tt = f_type[fi];
                 poly = (tt == COVT_GT_POLYGON || tt == COVT_GT_MULTIPOLYGON);
                 int32_t cnt = 1;
-                if (tt != COVT_GT_POINT) cnt = io.part[f_pe[fi] + (k - f_start[fi])];
+                if (tt != COVT_GT_POINT) cnt = __ldg(io.part + f_pe[fi] + (k - f_start[fi]));
                 if (cnt < 0) nrings = 0xffffffffu;  // flagged below
                 else if (poly) { nrings = (uint32_t)cnt; ring_entries = (uint32_t)cnt; }
                 else { nrings = 1; line_n = (uint32_t)cnt; }
@@ -119,7 +119,7 @@ __device__ __noinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmR
                 if (rvalid) {
                     const uint32_t pi = search32(p_start, q);
                     if (p_poly[pi]) {
-                        const int32_t c = io.ring[p_re[pi] + (q - p_start[pi])];
+                        const int32_t c = __ldg(io.ring + p_re[pi] + (q - p_start[pi]));
                         if (c < 0) bad = true;
                         else { nv = (uint32_t)c; outn = nv + ((io.close_rings && nv > 0) ? 1u : 0u); }
                     } else {
@@ -139,19 +139,39 @@ __device__ __noinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmR
                 __syncwarp();
                 const uint32_t n_out = (uint32_t)tot_ov;
                 bool oob = false;
-                for (uint32_t u0 = 0; u0 < n_out; u0 += 32) {
-                    const uint32_t u = u0 + lane;
-                    if (u < n_out) {
-                        const uint32_t ri = search32(r_start, u);
-                        const uint32_t i = u - r_start[ri];
-                        uint64_t si = (uint64_t)r_src[ri] + (i == r_n[ri] ? 0u : i);
-                        if (ice) {
-                            const int32_t o = io.voff[si];
-                            if (o < 0 || (uint64_t)o >= dict) { oob = true; si = 0; }
-                            else si = (uint64_t)o;
+                // 4 batches of 32 output vertices per trip: the index loads, then the coordinate gathers, are issued
+                // back to back so that their latencies overlap (the decoded streams were written by earlier kernels,
+                // so the read-only path is safe here)
+                for (uint32_t u0 = 0; u0 < n_out; u0 += 128) {
+                    uint64_t si[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int b4 = 0; b4 < 4; b4++) {
+                        const uint32_t u = u0 + 32u * b4 + lane;
+                        ok[b4] = u < n_out;
+                        si[b4] = 0;
+                        if (ok[b4]) {
+                            const uint32_t ri = search32(r_start, u);
+                            const uint32_t i = u - r_start[ri];
+                            si[b4] = (uint64_t)r_src[ri] + (i == r_n[ri] ? 0u : i);
                         }
-                        if (!oob) reinterpret_cast<int2*>(io.a_coords)[v + u] = reinterpret_cast<const int2*>(io.vbuf)[si];
                     }
+                    if (ice) {
+                        int32_t o[4];
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; b4++) o[b4] = ok[b4] ? __ldg(io.voff + si[b4]) : 0;
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; b4++) {
+                            if (ok[b4] && (o[b4] < 0 || (uint64_t)o[b4] >= dict)) { oob = true; ok[b4] = false; }
+                            si[b4] = (uint64_t)(uint32_t)o[b4];
+                        }
+                    }
+                    int2 xy[4];
+#pragma unroll
+                    for (int b4 = 0; b4 < 4; b4++) xy[b4] = ok[b4] ? __ldg(reinterpret_cast<const int2*>(io.vbuf) + si[b4]) : make_int2(0, 0);
+#pragma unroll
+                    for (int b4 = 0; b4 < 4; b4++)
+                        if (ok[b4]) reinterpret_cast<int2*>(io.a_coords)[v + u0 + 32u * b4 + lane] = xy[b4];
                 }
                 ASM_CHECK(oob, COVT_ERR_TOPOLOGY);
                 v += tot_ov;

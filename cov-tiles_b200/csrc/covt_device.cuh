@@ -15,7 +15,8 @@ namespace covt {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARP_CHUNK_BYTES = 512;        // 32 lanes x 16 B
-constexpr int STAGE_WORDS = 512 + 16;        // swizzled index i + (i >> 5), i < 512
+constexpr int STAGE_ROW = 34;                // words per row of the transposed stage (34 keeps every access pattern conflict-free)
+constexpr int STAGE_WORDS = 16 * STAGE_ROW;  // value i lives at row i & 15, column i >> 4
 
 // What one decode call has to do; derived from a covt_layer slot or a covt_stream_desc.
 struct StreamTask {
@@ -139,7 +140,10 @@ __device__ __forceinline__ int2 morton_decode(int32_t code, uint32_t num_bits, b
     return make_int2((int32_t)((uint32_t)cx - (uint32_t)half), (int32_t)((uint32_t)cy - (uint32_t)half));
 }
 
-__device__ __forceinline__ uint32_t stage_index(uint32_t i) { return i + (i >> 5); }
+// Transposed stage: value i of a chunk (i < 512) lives at (i & 15) * 34 + (i >> 4). The three access patterns of a chunk
+// are then bank-conflict free with compile-time offsets: blocked (lane*16 + j -> j*34 + lane), blocked by 8
+// (FastPFOR blocks) and striped (lane + 32k -> (lane & 15)*34 + (lane >> 4) + 2k).
+__device__ __forceinline__ uint32_t stage_index(uint32_t i) { return (i & 15u) * STAGE_ROW + (i >> 4); }
 
 // value post-processing selectors (PostKind) live in covt_internal.h: the host picks them for large streams
 
@@ -184,12 +188,12 @@ __device__ __forceinline__ uint32_t gather_msb16(const uint32_t words[4])
     return r;
 }
 
+// Common prologue of a chunk: zero the bytes outside the stream, find this lane's terminators and halo.
 template <bool VB>
-__device__ __forceinline__ void varint32_chunk_decode(uint4 w, uint32_t valid16, uint32_t& carry_halo, uint32_t limit,
-                                                      uint32_t* stage, uint32_t& emit, uint32_t& lane_excl,
-                                                      uint32_t& chunk_total, bool& overlong, const bool ZZ)
+__device__ __forceinline__ void varint32_chunk_prologue(uint4 w, uint32_t valid16, uint32_t& carry_halo, uint32_t words[4],
+                                                        uint32_t& emit, uint32_t& acc, uint32_t& shift, bool& overlong)
 {
-    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+    words[0] = w.x; words[1] = w.y; words[2] = w.z; words[3] = w.w;
 #pragma unroll
     for (int q = 0; q < 4; q++) words[q] &= nibble_to_bytemask((valid16 >> (4 * q)) & 0xfu);
     const uint32_t msb16 = gather_msb16(words);
@@ -197,15 +201,12 @@ __device__ __forceinline__ void varint32_chunk_decode(uint4 w, uint32_t valid16,
     uint32_t halo = __shfl_up_sync(FULL, words[3], 1);
     if (lane_id() == 0) halo = carry_halo;
     carry_halo = __shfl_sync(FULL, words[3], 31);
-
-    uint32_t cnt = __popc(emit);
-    lane_excl = warp_exclusive_scan(cnt, chunk_total);
-
     // carry-in from the halo: k trailing continuation bytes
     const uint32_t hcont = VB ? (~halo & 0x80808080u) : (halo & 0x80808080u);
     const uint32_t hterm = hcont ^ 0x80808080u;
     const uint32_t k = hterm ? (uint32_t)(__clz(hterm) >> 3) : 4u;
-    uint32_t acc = 0, shift = 0;
+    acc = 0;
+    shift = 0;
     if (k) {
         uint32_t hv = k >= 4 ? halo : (halo >> (8u * (4u - k)));
         acc = (hv & 0x7fu) | ((hv >> 1) & 0x3f80u) | ((hv >> 2) & 0x1fc000u) | ((hv >> 3) & 0x0fe00000u);
@@ -218,28 +219,66 @@ __device__ __forceinline__ void varint32_chunk_decode(uint4 w, uint32_t valid16,
         const uint32_t c19 = h3 | (msb16 << 3);
         if (c19 & (c19 >> 1) & (c19 >> 2) & (c19 >> 3)) overlong = true;
     }
+}
+
+// Decode + stage. RAW values are staged (zigzag is applied by the delta pass or the copy-out): the byte loop is
+// branch-free — a predicated store plus selects — because every byte position has a terminator in SOME lane.
+template <bool VB, bool LIMIT>
+__device__ __forceinline__ void varint32_chunk_decode(uint4 w, uint32_t valid16, uint32_t& carry_halo, uint32_t limit,
+                                                      uint32_t* stage, uint32_t& emit, uint32_t& lane_excl,
+                                                      uint32_t& chunk_total, bool& overlong)
+{
+    uint32_t words[4], acc, shift;
+    varint32_chunk_prologue<VB>(w, valid16, carry_halo, words, emit, acc, shift, overlong);
+    lane_excl = warp_exclusive_scan(__popc(emit), chunk_total);
     uint32_t idx = lane_excl;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xffu;
-        acc |= (b & 0x7fu) << (shift & 31u);
-        const bool cont = VB ? !(b & 0x80u) : (b & 0x80u) != 0;
-        if (cont) {
-            shift += 7;
-        } else {
-            if ((emit >> j) & 1u) {
-                if (idx < limit) stage[stage_index(idx)] = ZZ ? (uint32_t)zigzag_decode32(acc) : acc;
-                idx++;
-            }
-            acc = 0;
-            shift = 0;
-        }
+        const uint32_t b = __byte_perm(words[j >> 2], 0u, 0x4440u | (uint32_t)(j & 3));
+        const uint32_t v = acc | ((b & 0x7fu) << (shift & 31u));
+        const bool term = VB ? (b & 0x80u) != 0u : (b & 0x80u) == 0u;
+        const bool em = (emit >> j) & 1u;
+        if (em && (!LIMIT || idx < limit)) stage[stage_index(idx)] = v;
+        idx += em ? 1u : 0u;
+        acc = term ? 0u : v;
+        shift = term ? 0u : shift + 7u;
     }
 }
 
-// Blocked delta pass over the values staged by varint32_chunk_decode / the FastPFOR unpacker:
-// stage[0..n) holds deltas; on return it holds final values. carry is advanced.
-// PER = values per lane (16 for a 512-value chunk, 8 for a FastPFOR block of 256).
+// Pass-1 flavour for large streams: only this lane's (count, sum at even local positions, sum at odd local positions).
+template <bool ZZ>
+__device__ __forceinline__ void varint32_chunk_sums(uint4 w, uint32_t valid16, uint32_t head_fakes, uint32_t& carry_halo,
+                                                    uint32_t& cnt, int32_t& a, int32_t& b, bool& overlong)
+{
+    uint32_t words[4], emit, acc, shift;
+    varint32_chunk_prologue<false>(w, valid16, carry_halo, words, emit, acc, shift, overlong);
+    cnt = __popc(emit);
+    // Zeroed bytes outside the stream look like 1-byte zeros: they add nothing to the sums and only toggle the parity,
+    // which is undone below (trailing ones never matter, leading ones are counted in head_fakes).
+    int32_t s0 = 0, s1 = 0;  // s0 = accumulator of the NEXT value's parity class
+    uint32_t toggles = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t bb = __byte_perm(words[j >> 2], 0u, 0x4440u | (uint32_t)(j & 3));
+        const uint32_t v = acc | ((bb & 0x7fu) << (shift & 31u));
+        const bool term = (bb & 0x80u) == 0u;
+        const int32_t d = ZZ ? zigzag_decode32(v) : (int32_t)v;
+        const int32_t t = s0 + d;
+        s0 = term ? s1 : s0;
+        s1 = term ? t : s1;
+        toggles += term ? 1u : 0u;
+        acc = term ? 0u : v;
+        shift = term ? 0u : shift + 7u;
+    }
+    // after an even number of toggles s0 is again the class of local position 0
+    const bool flip = (toggles ^ head_fakes) & 1u;  // leading fakes shifted every real value by head_fakes positions
+    const bool odd = toggles & 1u;
+    const int32_t e0 = odd ? s1 : s0, e1 = odd ? s0 : s1;  // sums at even / odd positions counted from the first (fake or real) value
+    (void)flip;
+    a = (head_fakes & 1u) ? e1 : e0;
+    b = (head_fakes & 1u) ? e0 : e1;
+}
+
 // zz_at_load: the staged values are still zigzag-encoded (FastPFOR path, DecodingUtils.java:335-343).
 // `post` is warp-uniform, so the branches below do not diverge.
 template <int PER>
@@ -291,7 +330,7 @@ __device__ __forceinline__ void warp_delta_pass(uint32_t* stage, uint32_t n, Del
 }
 
 // Coalesced copy of stage[0..n) to dst[first ..]: int32, widened to int64 (ids), or expanded Morton (x,y) pairs.
-enum CopyKind { COPY_I32 = 0, COPY_I64 = 1, COPY_MORTON = 2 };
+enum CopyKind { COPY_I32 = 0, COPY_I64 = 1, COPY_MORTON = 2, COPY_I32_ZZ = 3 };
 template <int PER>
 __device__ __forceinline__ void warp_copy_out(const uint32_t* stage, uint32_t n, void* dst, uint64_t first, const int kind,
                                               uint32_t num_bits, bool no_shift)
@@ -308,6 +347,12 @@ __device__ __forceinline__ void warp_copy_out(const uint32_t* stage, uint32_t n,
         for (int k = 0; k < PER; k++) {
             uint32_t i = lane + 32u * k;
             if (i < n) reinterpret_cast<int64_t*>(dst)[first + i] = (int64_t)(int32_t)stage[stage_index(i)];
+        }
+    } else if (kind == COPY_I32_ZZ) {
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            uint32_t i = lane + 32u * k;
+            if (i < n) reinterpret_cast<int32_t*>(dst)[first + i] = zigzag_decode32(stage[stage_index(i)]);
         }
     } else {
 #pragma unroll

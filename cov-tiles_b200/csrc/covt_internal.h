@@ -31,25 +31,24 @@ struct DeviceTask {
 // codec classes = one small kernel each (the instruction working set of a kernel must stay cache-resident)
 enum OpClass { CLASS_BYTE_RLE = 0, CLASS_RLE = 1, CLASS_VARINT32 = 2, CLASS_VARINT64 = 3, CLASS_PFOR = 4, NUM_OP_CLASSES = 5 };
 
-// a large 32-bit delta-varint stream handled by the multi-CTA look-back kernel
+// A large 32-bit varint stream, decoded by many CTAs in two wait-free passes (k1a aggregates -> segmented scan -> k1b).
 struct BigStream {
     uint64_t src_offset;   // into the blob
     uint8_t* dst;          // absolute device pointer of the output slice
     uint32_t byte_length;
     uint32_t num_values;
-    uint32_t first_chunk;  // index of its first chunk in the global chunk list
+    uint32_t first_chunk;  // index of its first 512-byte warp chunk in the launch-wide chunk numbering
     uint32_t n_chunks;
-    uint32_t* status_out;  // where to report the status (task or layer stream slot)
+    uint32_t* status_out;  // where to report the status (a DeviceTask)
     uint32_t* consumed_out;
     uint8_t post, num_bits, no_shift, pad;
 };
-struct ChunkRef { uint32_t stream, chunk; };
-// look-back record of one chunk, read and written with ONE 128-bit access (flag + payload are never torn):
-// flag 0 = nothing yet, 1 = aggregate of this chunk (a/b = sums at even/odd positions relative to the chunk start),
-// 2 = inclusive prefix of the stream up to and including this chunk (a/b = running x/y)
-struct __align__(16) ChunkState { uint32_t flag, count; int32_t a, b; };
+// Per-chunk record: after k1a the chunk's aggregate (count, sum at even positions, sum at odd positions),
+// after the scan the exclusive prefix of the chunk inside its stream (count, running x, running y).
+// flags: bit 0 = first chunk of its stream, bit 1 = x/y interleaved sums
+struct __align__(16) ChunkState { uint32_t count; int32_t a, b; uint32_t flags; };
 constexpr int K1_WARPS = 8;
-constexpr int K1_TILE_BYTES = K1_WARPS * 512;
+constexpr int K1_SCAN_BLOCK = 1024;
 
 static const uint8_t kBufElemSize[COVT_NUM_BUFFERS] = {1, 8, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 1};
 
@@ -67,8 +66,9 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
 const char* op_class_name(int op_class);
 cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers, ResultBuffers bufs, uint32_t flags,
                                    uint32_t* work_counter, int sm_count, cudaStream_t st);
-cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, const ChunkRef* chunks, uint32_t n_chunks,
-                                    ChunkState* states, uint32_t* ticket, cudaStream_t st);
+// k1a_aggregate + 3 segmented-scan kernels + k1b_decode; block_states needs ceil(n_chunks / K1_SCAN_BLOCK) entries
+cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks,
+                                    ChunkState* states, ChunkState* block_states, cudaStream_t st);
 cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags,
                             uint32_t* tile_status, uint64_t* totals /* [0]=vertices [1]=payload bytes [2]=output bytes */,
                             cudaStream_t st);

@@ -566,6 +566,29 @@ __device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, Strea
     }
 }
 
+// which streams of a class a single thread decodes on its own
+template <int CLASS>
+__device__ __forceinline__ bool is_small_task(uint32_t num_values, uint32_t byte_length)
+{
+    if (CLASS == CLASS_BYTE_RLE || CLASS == CLASS_RLE || CLASS == CLASS_VARINT64)
+        return num_values <= SMALL_STREAM_VALUES && byte_length <= SMALL_STREAM_BYTES;
+    return false;
+}
+
+__device__ __forceinline__ StreamTask make_stream_task(const uint8_t* blob, const DeviceTask& d)
+{
+    StreamTask t;
+    t.src = blob + d.src_offset;
+    t.dst = d.dst;
+    t.byte_length = d.byte_length;
+    t.num_values = d.num_values;
+    t.op = d.op;
+    t.num_bits = d.num_bits;
+    t.no_shift = d.no_shift;
+    t.exact_length = d.exact_length;
+    return t;
+}
+
 template <int CLASS>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter)
@@ -573,32 +596,45 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     uint8_t* wsm = smem + warp * DEC_WARP_SMEM;
-    const uint32_t n_groups = (n_tasks + 31u) / 32u;
+    // A work group = 256 consecutive task slots = 32 layers x 8 slots in the batch path. Lane L looks at slot s of
+    // "its" layer, so that the 32 lanes hold 32 streams of the SAME kind (same slot) at a time.
+    const uint32_t n_groups = (n_tasks + 255u) / 256u;
     for (;;) {
         const uint32_t g = warp_next_work(work_counter);
         if (g >= n_groups) break;
-        const uint32_t mine = g * 32u + lane;
-        uint32_t op = COVT_OP_NONE;
-        if (mine < n_tasks) op = tasks[mine].op;
-        unsigned todo = __ballot_sync(FULL, op_class_of(op) == CLASS);
-        while (todo) {
-            const int src_lane = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t i = g * 32u + src_lane;
-            const DeviceTask d = tasks[i];
-            StreamTask t;
-            t.src = blob + d.src_offset;
-            t.dst = d.dst;
-            t.byte_length = d.byte_length;
-            t.num_values = d.num_values;
-            t.op = d.op;
-            t.num_bits = d.num_bits;
-            t.no_shift = d.no_shift;
-            t.exact_length = d.exact_length;
-            StreamOutcome o;
-            decode_one<CLASS>(t, wsm, o);
+#pragma unroll 1
+        for (uint32_t s = 0; s < COVT_NUM_SLOTS; s++) {
+            const uint32_t mine = g * 256u + lane * COVT_NUM_SLOTS + s;
+            uint32_t op = COVT_OP_NONE, nv = 0, bl = 0;
+            if (mine < n_tasks) { op = tasks[mine].op; nv = tasks[mine].num_values; bl = tasks[mine].byte_length; }
+            const bool match = op_class_of(op) == CLASS;
+            // small sequential streams: one thread each, up to 32 at a time
+            if (match && is_small_task<CLASS>(nv, bl)) {
+                const DeviceTask d = tasks[mine];
+                const StreamTask t = make_stream_task(blob, d);
+                StreamOutcome o = {COVT_OK, 0};
+                if (CLASS == CLASS_BYTE_RLE) thread_byte_rle_stream(t, o);
+                else if (CLASS == CLASS_RLE) {
+                    if (t.op == COVT_OP_RLE_U32) thread_rle_stream<int32_t>(t, false, o);
+                    else thread_rle_stream<int64_t>(t, t.op == COVT_OP_RLE_S64, o);
+                } else if (CLASS == CLASS_VARINT64) thread_varint64_stream(t, t.op == COVT_OP_VARINT_ZZ_DELTA_64, o);
+                tasks[mine].status = o.status;
+                tasks[mine].consumed = o.consumed;
+            }
             __syncwarp();
-            if (lane == 0) { tasks[i].status = o.status; tasks[i].consumed = o.consumed; }
+            // everything else: one warp per stream
+            unsigned todo = __ballot_sync(FULL, match && !is_small_task<CLASS>(nv, bl));
+            while (todo) {
+                const int src_lane = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t i = g * 256u + src_lane * COVT_NUM_SLOTS + s;
+                const DeviceTask d = tasks[i];
+                const StreamTask t = make_stream_task(blob, d);
+                StreamOutcome o;
+                decode_one<CLASS>(t, wsm, o);
+                __syncwarp();
+                if (lane == 0) { tasks[i].status = o.status; tasks[i].consumed = o.consumed; }
+            }
         }
     }
 }
@@ -670,193 +706,209 @@ k_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers
 }
 
 // =================================================================================================
-// K1: one large 32-bit varint stream over many CTAs, single pass, decoupled look-back
+// K1: large 32-bit varint streams over many CTAs, wait-free.
+//   k1a_aggregate : every warp reads one 512-byte chunk and reduces it to (count, sumEven, sumOdd)
+//   k1_scan_*     : segmented exclusive scan of those triples (the x/y combine is associative, not commutative)
+//   k1b_decode    : every warp decodes its chunk again, now knowing its exclusive prefix, and writes final values
+// A single-pass decoupled look-back version (profiles/r01_a_k1_lookback_4k_tiles_ncu.txt) kept 7 of 8 warps at the
+// barrier and is capped near 256 GB/s by the look-back round trip; two cheap passes with no waiting beat it.
 // =================================================================================================
-__device__ __forceinline__ uint4 ld_state(const ChunkState* p)
+__device__ __forceinline__ ChunkState cs_combine(const ChunkState& l, const ChunkState& r)
 {
-    uint4 r;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
-}
-__device__ __forceinline__ void st_state(ChunkState* p, uint32_t flag, uint32_t count, int32_t a, int32_t b)
-{
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(flag), "r"(count), "r"(a), "r"(b) : "memory");
-}
-
-// (count, a, b): a / b = sums at even / odd positions relative to the segment start.
-// left (+) right: the right segment's parity flips when the left count is odd. Associative, not commutative.
-struct Trip { uint32_t c; int32_t a, b; };
-template <bool XY>
-__device__ __forceinline__ Trip trip_combine(const Trip& l, const Trip& r)
-{
-    Trip o;
-    o.c = l.c + r.c;
-    if (XY) {
-        const bool odd = l.c & 1u;
+    if (r.flags & 1u) return r;  // r starts a new stream
+    if ((r.count | (uint32_t)r.a | (uint32_t)r.b) == 0u) return l;  // empty / padding element
+    ChunkState o;
+    o.count = l.count + r.count;
+    if (r.flags & 2u) {
+        const bool odd = l.count & 1u;
         o.a = l.a + (odd ? r.b : r.a);
         o.b = l.b + (odd ? r.a : r.b);
     } else {
         o.a = l.a + r.a;
         o.b = 0;
     }
+    o.flags = (l.flags & 1u) | (r.flags & 2u);
     return o;
 }
-__device__ __forceinline__ Trip trip_shfl(const Trip& t, int src)
+__device__ __forceinline__ ChunkState cs_shfl_up(const ChunkState& t, int d)
 {
-    Trip o;
-    o.c = __shfl_sync(FULL, t.c, src);
-    o.a = __shfl_sync(FULL, t.a, src);
-    o.b = __shfl_sync(FULL, t.b, src);
+    ChunkState o;
+    o.count = __shfl_up_sync(FULL, t.count, d);
+    o.a = __shfl_up_sync(FULL, t.a, d);
+    o.b = __shfl_up_sync(FULL, t.b, d);
+    o.flags = __shfl_up_sync(FULL, t.flags, d);
     return o;
 }
-
-// Decoupled look-back executed by warp 0: lane k inspects predecessor (chunk - 1 - k) of the same stream, 32 at a time.
-// Returns the exclusive prefix of this chunk (uniform across the warp).
-template <bool XY>
-__device__ __forceinline__ Trip k1_lookback(ChunkState* states, uint32_t chunk_global, uint32_t ci)
+__device__ __forceinline__ ChunkState cs_warp_inclusive(ChunkState v)
 {
-    const unsigned lane = lane_id();
-    Trip acc = {0, 0, 0};        // combined aggregates of the chunks between the window and this chunk
-    uint32_t back = 0;           // predecessors already consumed
-    for (;;) {
-        const uint32_t k = back + lane;          // this lane looks at predecessor number k (0 = nearest)
-        const bool valid = k < ci;               // never leave the stream: chunk 0 of the stream publishes an inclusive record
-        uint4 st = make_uint4(0, 0, 0, 0);
-        if (valid) {
-            const ChunkState* pj = &states[chunk_global - 1 - k];
-            while ((st = ld_state(pj)).x == 0u) __nanosleep(40);
-        }
-        const unsigned inc_mask = __ballot_sync(FULL, valid && st.x == 2u);
-        const unsigned valid_mask = __ballot_sync(FULL, valid);
-        // lanes [0, stop] take part: `stop` is the nearest inclusive record, or the last valid lane
-        const int stop = inc_mask ? (__ffs(inc_mask) - 1) : (31 - __clz(valid_mask));
-        Trip mine = {st.y, (int32_t)st.z, (int32_t)st.w};
-        Trip w = trip_shfl(mine, stop);
-        for (int q = stop - 1; q >= 0; q--) w = trip_combine<XY>(w, trip_shfl(mine, q));
-        acc = trip_combine<XY>(w, acc);
-        if (inc_mask) return acc;
-        back += 32;
-    }
-}
-
-template <int POST>
-__device__ void k1_body(const uint8_t* blob, const BigStream& S, uint32_t chunk_global, uint32_t ci, ChunkState* states,
-                        uint32_t (*s_stage)[STAGE_WORDS], Trip* s_warp, Trip* s_prefix)
-{
-    constexpr bool ZZ = (POST == POST_ZZ || POST == POST_ZZ_DELTA || POST == POST_ZZ_DELTA_XY);
-    constexpr bool XY = (POST == POST_ZZ_DELTA_XY);
-    constexpr bool DELTA = (POST == POST_ZZ_DELTA || POST == POST_ZZ_DELTA_XY || POST == POST_DELTA_MORTON);
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint8_t* src = blob + S.src_offset;
-    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15);
-    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(src) - a0);
-    const uint64_t total = (uint64_t)head + S.byte_length;
-    const uint64_t off = (uint64_t)ci * K1_TILE_BYTES + warp * 512u + lane * 16u;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (off < total) w = ldg_stream128(reinterpret_cast<const void*>(a0 + off));
-    const uint32_t lo16 = off >= head ? 0u : (uint32_t)umin64(16, head - off);
-    const uint32_t hi16 = off >= total ? 0u : (uint32_t)umin64(16, total - off);
-    const uint32_t valid16 = ((1u << hi16) - 1u) & ~((1u << lo16) - 1u);
-    // halo of lane 0 = the 4 bytes before this warp's sub-chunk (inside the stream whenever off >= 512)
-    uint32_t halo = 0;
-    if (lane == 0 && off > 0 && off < total + 4) halo = __ldg(reinterpret_cast<const uint32_t*>(a0 + off - 4));
-    uint32_t emit, excl, wtotal;
-    bool overlong = false;
-    uint32_t* stage = s_stage[warp];
-    varint32_chunk_decode<false>(w, valid16, halo, 0xffffffffu, stage, emit, excl, wtotal, overlong, ZZ);
-    __syncwarp();
-    // blocked local sums (values stay in registers across the two block barriers)
-    int32_t v[16];
-    int32_t la = 0, lb = 0;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const uint32_t i = lane * 16 + j;
-        v[j] = i < wtotal ? (int32_t)stage[stage_index(i)] : 0;
-        if (DELTA) { if (XY && (j & 1)) lb += v[j]; else la += v[j]; }
+    for (int d = 1; d < 32; d <<= 1) {
+        const ChunkState u = cs_shfl_up(v, d);
+        if (lane_id() >= (unsigned)d) v = cs_combine(u, v);
     }
-    int32_t ta = 0, tb = 0, ea = 0, eb = 0;
-    if (DELTA) {
-        ea = warp_exclusive_scan_i32(la, ta);
-        if (XY) eb = warp_exclusive_scan_i32(lb, tb);
-    }
-    if (lane == 0) { s_warp[warp].c = wtotal; s_warp[warp].a = ta; s_warp[warp].b = tb; }
+    return v;
+}
+// inclusive scan over the block; returns this thread's inclusive value, *total = the block's aggregate
+__device__ ChunkState cs_block_inclusive(ChunkState v, ChunkState* total, ChunkState* sm /*[32]*/)
+{
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    v = cs_warp_inclusive(v);
+    if (lane == 31) sm[warp] = v;
     __syncthreads();
     if (warp == 0) {
-        Trip agg = s_warp[0];
-#pragma unroll
-        for (int k = 1; k < K1_WARPS; k++) agg = trip_combine<XY>(agg, s_warp[k]);
-        ChunkState* me = &states[chunk_global];
-        Trip prefix = {0, 0, 0};
-        if (ci > 0) {
-            if (lane == 0) st_state(me, 1u, agg.c, agg.a, agg.b);
-            prefix = k1_lookback<XY>(states, chunk_global, ci);
-        }
-        const Trip inc = trip_combine<XY>(prefix, agg);
-        if (lane == 0) {
-            st_state(me, 2u, inc.c, inc.a, inc.b);
-            *s_prefix = prefix;
-            if (ci == S.n_chunks - 1 && inc.c < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
-        }
+        ChunkState w = lane < n_warps ? sm[lane] : ChunkState{0, 0, 0, 0};
+        w = cs_warp_inclusive(w);
+        if (lane < n_warps) sm[lane] = w;
     }
-    if (__any_sync(FULL, overlong) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
     __syncthreads();
-    // this warp's exclusive prefix
-    Trip P = *s_prefix;
-    for (unsigned k = 0; k < warp; k++) P = trip_combine<XY>(P, s_warp[k]);
-    // bytes the reference reader consumes = position right after the terminator of value #num_values
-    {
-        const uint32_t first = P.c + excl, cnt = __popc(emit);
-        if (S.consumed_out && S.num_values > first && S.num_values <= first + cnt)
-            *S.consumed_out = (uint32_t)(off + __fns(emit, 0, (int)(S.num_values - first)) + 1u - head);
+    if (warp > 0) v = cs_combine(sm[warp - 1], v);
+    *total = sm[n_warps - 1];
+    __syncthreads();
+    return v;
+}
+
+// which large stream a launch-wide chunk index belongs to (few streams: a short binary search)
+__device__ __forceinline__ uint32_t k1_find_stream(const BigStream* streams, uint32_t n_streams, uint32_t g)
+{
+    uint32_t lo = 0, hi = n_streams;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (streams[mid].first_chunk <= g) lo = mid; else hi = mid;
     }
-    if (DELTA) {
-        if (XY) {
-            const bool swap = P.c & 1u;  // position i of this warp has global parity (P.c + i) & 1 and lane*16 is even
-            int32_t pa = ea + (swap ? P.b : P.a);
-            int32_t pb = eb + (swap ? P.a : P.b);
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (j & 1) { pb += v[j]; v[j] = pb; } else { pa += v[j]; v[j] = pa; }
-            }
-        } else {
-            int32_t pa = ea + P.a;
-#pragma unroll
-            for (int j = 0; j < 16; j++) { pa += v[j]; v[j] = pa; }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const uint32_t i = lane * 16 + j;
-            if (i < wtotal) stage[stage_index(i)] = (uint32_t)v[j];
-        }
-        __syncwarp();
-    }
-    // coalesced copy-out, clipped to num_values
-    const uint32_t room = P.c < S.num_values ? S.num_values - P.c : 0u;
-    warp_copy_out<16>(stage, min(wtotal, room), S.dst, P.c, POST == POST_DELTA_MORTON ? COPY_MORTON : COPY_I32, S.num_bits, S.no_shift != 0);
+    return lo;
+}
+
+struct K1Window {
+    uint4 w;
+    uint32_t valid16, halo, head_fakes, head;
+    uint64_t off;
+};
+__device__ __forceinline__ K1Window k1_load_window(const uint8_t* blob, const BigStream& S, uint32_t ci)
+{
+    K1Window k;
+    const unsigned lane = lane_id();
+    const uint8_t* src = blob + S.src_offset;
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15);
+    k.head = (uint32_t)(reinterpret_cast<uintptr_t>(src) - a0);
+    const uint64_t total = (uint64_t)k.head + S.byte_length;
+    k.off = (uint64_t)ci * WARP_CHUNK_BYTES + lane * 16u;
+    k.w = make_uint4(0, 0, 0, 0);
+    if (k.off < total) k.w = ldg_stream128(reinterpret_cast<const void*>(a0 + k.off));
+    const uint32_t lo16 = k.off >= k.head ? 0u : (uint32_t)umin64(16, k.head - k.off);
+    const uint32_t hi16 = k.off >= total ? 0u : (uint32_t)umin64(16, total - k.off);
+    k.valid16 = ((1u << hi16) - 1u) & ~((1u << lo16) - 1u);
+    k.head_fakes = lo16;
+    // halo of lane 0 = the 4 bytes before this chunk (always inside the stream when ci > 0)
+    k.halo = 0;
+    if (lane == 0 && ci > 0) k.halo = __ldg(reinterpret_cast<const uint32_t*>(a0 + k.off - 4));
+    return k;
 }
 
 __global__ void __launch_bounds__(K1_WARPS * 32)
-k1_varint_stream(const uint8_t* blob, const BigStream* streams, const ChunkRef* chunks, uint32_t n_chunks, ChunkState* states,
-                 uint32_t* ticket)
+k1a_aggregate(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks, ChunkState* states)
+{
+    const unsigned lane = lane_id();
+    const uint32_t g = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
+    if (g >= n_chunks) return;
+    const uint32_t si = k1_find_stream(streams, n_streams, g);
+    const BigStream S = streams[si];
+    const uint32_t ci = g - S.first_chunk;
+    K1Window k = k1_load_window(blob, S, ci);
+    uint32_t cnt;
+    int32_t a, b;
+    bool overlong = false;
+    const bool zz = (S.post == POST_ZZ || S.post == POST_ZZ_DELTA || S.post == POST_ZZ_DELTA_XY);
+    if (zz) varint32_chunk_sums<true>(k.w, k.valid16, k.head_fakes, k.halo, cnt, a, b, overlong);
+    else varint32_chunk_sums<false>(k.w, k.valid16, k.head_fakes, k.halo, cnt, a, b, overlong);
+    const bool xy = S.post == POST_ZZ_DELTA_XY;
+    ChunkState v = {cnt, xy ? a : a + b, xy ? b : 0, xy ? 2u : 0u};
+    v = cs_warp_inclusive(v);
+    if (lane == 31) {
+        v.flags = (xy ? 2u : 0u) | (ci == 0 ? 1u : 0u);
+        states[g] = v;
+    }
+    if (__any_sync(FULL, overlong) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
+}
+
+__global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_reduce(const ChunkState* states, uint32_t n, ChunkState* block_states)
+{
+    __shared__ ChunkState sm[32];
+    const uint32_t i = blockIdx.x * K1_SCAN_BLOCK + threadIdx.x;
+    ChunkState v = i < n ? states[i] : ChunkState{0, 0, 0, 0};
+    ChunkState tot;
+    cs_block_inclusive(v, &tot, sm);
+    if (threadIdx.x == 0) block_states[blockIdx.x] = tot;
+}
+// one block: exclusive scan of the block aggregates (in place)
+__global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_blocks(ChunkState* block_states, uint32_t nb)
+{
+    __shared__ ChunkState sm[32];
+    ChunkState running = {0, 0, 0, 0};
+    for (uint32_t b0 = 0; b0 < nb; b0 += K1_SCAN_BLOCK) {
+        const uint32_t b = b0 + threadIdx.x;
+        ChunkState v = b < nb ? block_states[b] : ChunkState{0, 0, 0, 0};
+        ChunkState tot;
+        const ChunkState inc = cs_block_inclusive(v, &tot, sm);
+        // exclusive = running (+) inclusive of the previous element
+        ChunkState prev = cs_shfl_up(inc, 1);
+        __shared__ ChunkState warp_last[32];
+        if (lane_id() == 31) warp_last[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (lane_id() == 0) prev = (threadIdx.x == 0) ? ChunkState{0, 0, 0, 0} : warp_last[(threadIdx.x >> 5) - 1];
+        const ChunkState excl = threadIdx.x == 0 ? running : cs_combine(running, prev);
+        if (b < nb) block_states[b] = excl;
+        running = cs_combine(running, tot);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_apply(ChunkState* states, uint32_t n, const ChunkState* block_states)
+{
+    __shared__ ChunkState sm[32];
+    __shared__ ChunkState warp_last[32];
+    const uint32_t i = blockIdx.x * K1_SCAN_BLOCK + threadIdx.x;
+    const ChunkState v = i < n ? states[i] : ChunkState{0, 0, 0, 0};
+    ChunkState tot;
+    const ChunkState inc = cs_block_inclusive(v, &tot, sm);
+    ChunkState prev = cs_shfl_up(inc, 1);
+    if (lane_id() == 31) warp_last[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (lane_id() == 0) prev = (threadIdx.x == 0) ? ChunkState{0, 0, 0, 0} : warp_last[(threadIdx.x >> 5) - 1];
+    ChunkState excl = threadIdx.x == 0 ? block_states[blockIdx.x] : cs_combine(block_states[blockIdx.x], prev);
+    if (v.flags & 1u) excl = ChunkState{0, 0, 0, v.flags};  // first chunk of a stream: nothing before it
+    if (i < n) states[i] = excl;
+}
+
+__global__ void __launch_bounds__(K1_WARPS * 32)
+k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks, const ChunkState* states)
 {
     __shared__ uint32_t s_stage[K1_WARPS][STAGE_WORDS];
-    __shared__ Trip s_warp[K1_WARPS];
-    __shared__ Trip s_prefix;
-    __shared__ uint32_t s_chunk;
-    // a ticket (not blockIdx) orders the chunks so that a predecessor has always been scheduled
-    if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t chunk = s_chunk;
-    if (chunk >= n_chunks) return;
-    const ChunkRef ref = chunks[chunk];
-    const BigStream S = streams[ref.stream];
-    switch (S.post) {
-    case POST_PLAIN: k1_body<POST_PLAIN>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
-    case POST_ZZ: k1_body<POST_ZZ>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
-    case POST_ZZ_DELTA: k1_body<POST_ZZ_DELTA>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
-    case POST_ZZ_DELTA_XY: k1_body<POST_ZZ_DELTA_XY>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
-    default: k1_body<POST_DELTA_MORTON>(blob, S, chunk, ref.chunk, states, s_stage, s_warp, &s_prefix); break;
+    const unsigned lane = lane_id();
+    const uint32_t g = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
+    if (g >= n_chunks) return;
+    const uint32_t si = k1_find_stream(streams, n_streams, g);
+    const BigStream S = streams[si];
+    const uint32_t ci = g - S.first_chunk;
+    const ChunkState P = states[g];
+    K1Window k = k1_load_window(blob, S, ci);
+    uint32_t* stage = s_stage[threadIdx.x >> 5];
+    uint32_t emit, excl, wtotal;
+    bool overlong = false;
+    varint32_chunk_decode<false, false>(k.w, k.valid16, k.halo, 0xffffffffu, stage, emit, excl, wtotal, overlong);
+    __syncwarp();
+    const int post = S.post;
+    DeltaCarry carry = {P.a, P.b, P.count};
+    warp_delta_pass<16>(stage, wtotal, carry, post, post == POST_ZZ_DELTA || post == POST_ZZ_DELTA_XY);
+    __syncwarp();
+    // bytes the reference reader consumes = position right after the terminator of value #num_values
+    {
+        const uint32_t first = P.count + excl, cnt = __popc(emit);
+        if (S.consumed_out && S.num_values > first && S.num_values <= first + cnt)
+            *S.consumed_out = (uint32_t)(k.off + __fns(emit, 0, (int)(S.num_values - first)) + 1u - k.head);
     }
+    if (ci == S.n_chunks - 1 && lane == 0 && P.count + wtotal < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
+    const uint32_t room = P.count < S.num_values ? S.num_values - P.count : 0u;
+    const int copy_kind = post == POST_DELTA_MORTON ? COPY_MORTON : (post == POST_ZZ ? COPY_I32_ZZ : COPY_I32);
+    warp_copy_out<16>(stage, min(wtotal, room), S.dst, P.count, copy_kind, S.num_bits, S.no_shift != 0);
 }
 
 // =================================================================================================
@@ -945,7 +997,7 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
 {
     if (!n_tasks) return cudaSuccess;
     const int smem = DEC_WARPS * DEC_WARP_SMEM;
-    const int grid = grid_for(sm_count, 12, ((uint64_t)n_tasks + 31) / 32, DEC_WARPS);
+    const int grid = grid_for(sm_count, 12, ((uint64_t)n_tasks + 255) / 256, DEC_WARPS);
     switch (op_class) {
     case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
     case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
@@ -965,11 +1017,17 @@ cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, const ChunkRef* chunks, uint32_t n_chunks,
-                                    ChunkState* states, uint32_t* ticket, cudaStream_t st)
+cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks,
+                                    ChunkState* states, ChunkState* block_states, cudaStream_t st)
 {
     if (!n_chunks) return cudaSuccess;
-    k1_varint_stream<<<n_chunks, K1_WARPS * 32, 0, st>>>(blob, streams, chunks, n_chunks, states, ticket);
+    const uint32_t grid = (n_chunks + K1_WARPS - 1) / K1_WARPS;
+    const uint32_t nb = (n_chunks + K1_SCAN_BLOCK - 1) / K1_SCAN_BLOCK;
+    k1a_aggregate<<<grid, K1_WARPS * 32, 0, st>>>(blob, streams, n_streams, n_chunks, states);
+    k1_scan_reduce<<<nb, K1_SCAN_BLOCK, 0, st>>>(states, n_chunks, block_states);
+    k1_scan_blocks<<<1, K1_SCAN_BLOCK, 0, st>>>(block_states, nb);
+    k1_scan_apply<<<nb, K1_SCAN_BLOCK, 0, st>>>(states, n_chunks, block_states);
+    k1b_decode<<<grid, K1_WARPS * 32, 0, st>>>(blob, streams, n_streams, n_chunks, states);
     return cudaGetLastError();
 }
 

@@ -43,8 +43,8 @@ __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t*
     uint32_t halo = 0;
     bool overlong = false;
     uint32_t consumed = 0;
-    const bool zz = (post == POST_ZZ || post == POST_ZZ_DELTA || post == POST_ZZ_DELTA_XY);
-    const int copy_kind = widen ? COPY_I64 : (post == POST_DELTA_MORTON ? COPY_MORTON : COPY_I32);
+    const bool zz_delta = (post == POST_ZZ_DELTA || post == POST_ZZ_DELTA_XY);
+    const int copy_kind = widen ? COPY_I64 : (post == POST_DELTA_MORTON ? COPY_MORTON : (post == POST_ZZ ? COPY_I32_ZZ : COPY_I32));
     for (uint64_t base = 0; base < total && carry.produced < t.num_values; base += WARP_CHUNK_BYTES) {
         const uint64_t off = base + lane * 16u;
         uint4 w = make_uint4(0, 0, 0, 0);
@@ -67,10 +67,10 @@ __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t*
                 valid16 &= (1u << keep) - 1u;
             }
         }
-        varint32_chunk_decode<false>(w, valid16, halo, remaining, stage, emit, excl, ctotal, overlong, zz);
+        varint32_chunk_decode<false, true>(w, valid16, halo, remaining, stage, emit, excl, ctotal, overlong);
         const uint32_t n = min(ctotal, remaining);
         __syncwarp();
-        warp_delta_pass<16>(stage, n, carry, post, false);
+        warp_delta_pass<16>(stage, n, carry, post, zz_delta);
         __syncwarp();
         warp_copy_out<16>(stage, n, t.dst, carry.produced, copy_kind, t.num_bits, t.no_shift != 0);
         __syncwarp();
@@ -303,6 +303,138 @@ __device__ __noinline__ void warp_byte_rle_stream(const StreamTask& t, StreamOut
 }
 
 // =================================================================================================
+// Thread-per-stream flavours of the sequential codecs for SMALL streams (the common case in tile batches:
+// ~50 values per topology / id stream). A warp-cooperative walk spends a whole warp instruction per
+// header byte (ncu: k_decode_rle 82 % issue-bound at 650 warp-instructions per stream); here 32 streams advance
+// in one instruction stream. Stores go out 4/8 bytes at a time and merge in L2.
+// =================================================================================================
+constexpr uint32_t SMALL_STREAM_VALUES = 256;  // streams up to this many values take the thread-per-stream path
+constexpr uint32_t SMALL_STREAM_BYTES = 2048;
+
+__device__ __forceinline__ bool thread_read_vulong(const uint8_t* src, uint32_t len, uint32_t& pos, uint64_t& v)
+{
+    v = 0;
+    uint32_t shift = 0;
+    for (int i = 0; i < 10; i++) {
+        if (pos >= len) return false;
+        const uint32_t b = __ldg(src + pos);
+        pos++;
+        v |= (uint64_t)(b & 0x7fu) << (shift & 63u);
+        shift += 7;
+        if (!(b & 0x80u)) break;
+    }
+    return true;
+}
+
+// DecodingUtils.decodeRle :257 — one thread, one stream
+template <typename OutT>
+__device__ __forceinline__ void thread_rle_stream(const StreamTask& t, bool is_signed, StreamOutcome& out)
+{
+    const uint8_t* src = t.src;
+    const uint32_t len = t.byte_length, n = t.num_values;
+    OutT* dst = reinterpret_cast<OutT*>(t.dst);
+    uint32_t pos = 0, done = 0, status = COVT_OK;
+    while (done < n) {
+        if (pos >= len) { status = COVT_ERR_TRUNCATED; break; }
+        const uint32_t c = __ldg(src + pos);
+        pos++;
+        if (c < 0x80u) {
+            if (pos >= len) { status = COVT_ERR_TRUNCATED; break; }
+            const int64_t delta = (int8_t)__ldg(src + pos);
+            pos++;
+            uint64_t raw;
+            if (!thread_read_vulong(src, len, pos, raw)) { status = COVT_ERR_TRUNCATED; break; }
+            uint64_t v = is_signed ? (uint64_t)zigzag_decode64(raw) : raw;
+            const uint32_t m = min(c + 3u, n - done);
+            for (uint32_t i = 0; i < m; i++) { dst[done + i] = (OutT)v; v += (uint64_t)delta; }
+            done += m;
+        } else {
+            const uint32_t lit = 256u - c;
+            bool bad = false;
+            for (uint32_t i = 0; i < lit; i++) {
+                uint64_t raw;
+                if (!thread_read_vulong(src, len, pos, raw)) { bad = true; break; }
+                if (done + i < n) dst[done + i] = (OutT)(is_signed ? (uint64_t)zigzag_decode64(raw) : raw);
+            }
+            if (bad) { status = COVT_ERR_TRUNCATED; break; }
+            done += min(lit, n - done);
+        }
+    }
+    out.status = status;
+    out.consumed = pos;
+}
+
+// DecodingUtils.decodeByteRle :275/:290 — one thread, one stream; output packed into 32-bit stores (dst is 16-byte aligned)
+__device__ __forceinline__ void thread_byte_rle_stream(const StreamTask& t, StreamOutcome& out)
+{
+    const uint8_t* src = t.src;
+    const uint32_t len = t.byte_length, n = t.num_values;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(t.dst);
+    uint32_t pos = 0, done = 0, status = COVT_OK;
+    uint32_t word = 0;  // bytes [done & ~3, done) already produced
+#define BRLE_PUT(val)                                                              \
+    {                                                                              \
+        word |= (uint32_t)(val) << (8u * (done & 3u));                             \
+        done++;                                                                    \
+        if ((done & 3u) == 0u) { *reinterpret_cast<uint32_t*>(dst + done - 4) = word; word = 0; } \
+    }
+    while (done < n) {
+        if (pos >= len) { status = COVT_ERR_TRUNCATED; break; }
+        const uint32_t c = __ldg(src + pos);
+        pos++;
+        if (c < 0x80u) {
+            if (pos >= len) { status = COVT_ERR_TRUNCATED; break; }
+            const uint32_t v = __ldg(src + pos);
+            pos++;
+            const uint32_t m = min(c + 3u, n - done);
+            for (uint32_t i = 0; i < m; i++) BRLE_PUT(v);
+        } else {
+            const uint32_t lit = 256u - c;
+            if (pos + lit > len) { status = COVT_ERR_TRUNCATED; break; }
+            const uint32_t m = min(lit, n - done);
+            for (uint32_t i = 0; i < m; i++) BRLE_PUT(__ldg(src + pos + i));
+            pos += lit;
+        }
+    }
+#undef BRLE_PUT
+    // tail bytes of the last partial word (never crosses the slice: slices are 16-byte padded)
+    for (uint32_t k = done & ~3u; k < done; k++) dst[k] = (uint8_t)(word >> (8u * (k & 3u)));
+    out.status = status;
+    out.consumed = pos;
+}
+
+// 64-bit LEB128 ids (ID_WIDTH 64) — one thread, one stream
+__device__ __forceinline__ void thread_varint64_stream(const StreamTask& t, bool zz_delta, StreamOutcome& out)
+{
+    const uint8_t* src = t.src;
+    const uint32_t len = t.byte_length, n = t.num_values;
+    int64_t* dst = reinterpret_cast<int64_t*>(t.dst);
+    uint32_t pos = 0, status = COVT_OK;
+    int64_t running = 0;
+    bool overlong = false;
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t v = 0;
+        uint32_t shift = 0;
+        bool ok = false;
+        for (int k = 0; k < 10; k++) {
+            if (pos >= len) break;
+            const uint32_t b = __ldg(src + pos);
+            pos++;
+            v |= (uint64_t)(b & 0x7fu) << (shift & 63u);
+            shift += 7;
+            if (!(b & 0x80u)) { ok = true; break; }
+            if (k == 9) { overlong = true; ok = true; }
+        }
+        if (!ok) { status = COVT_ERR_TRUNCATED; break; }
+        if (zz_delta) { running += zigzag_decode64(v); dst[i] = running; }
+        else dst[i] = (int64_t)v;
+    }
+    if (status == COVT_OK && overlong) status = COVT_ERR_VARINT_OVERLONG;
+    out.status = status;
+    out.consumed = t.exact_length ? t.byte_length : pos;
+}
+
+// =================================================================================================
 // Composition(FastPFOR-256, VariableByte) over big-endian words + fused post pass:
 // DecodingUtils.decodeFastPfor128ZigZagDelta :316, decodeFastPfor128DeltaCoordinates :349,
 // decodeFastPfor128DeltaMortonCodes :411 (JavaFastPFOR 0.1.12)
@@ -445,8 +577,8 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* sta
             }
             uint32_t emit, excl, ctotal;
             const uint32_t remaining = n - carry.produced;
-            varint32_chunk_decode<true>(make_uint4(words[0], words[1], words[2], words[3]), valid16, halo, remaining,
-                                        stage, emit, excl, ctotal, overlong, false);
+            varint32_chunk_decode<true, true>(make_uint4(words[0], words[1], words[2], words[3]), valid16, halo, remaining,
+                                              stage, emit, excl, ctotal, overlong);
             if (ctotal > remaining) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);  // Java: ArrayIndexOutOfBounds
             __syncwarp();
             warp_delta_pass<16>(stage, ctotal, carry, post, ZZ);

@@ -16,12 +16,12 @@ fixtures)
 ncu_layers)
   CMD="python bench.py --tiles 65536 --steps 1 --warmup 3 --no-cpu-baseline"
   $CMD > gpurun_out/plain_layers.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:k_decode_layers -s 3 -c 1 -f -o gpurun_out/prof_layers $CMD > gpurun_out/ncu_layers.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "regex:k_decode_class|k_assemble_layers|k0_" -s 16 -c 8 -f -o gpurun_out/prof_layers $CMD > gpurun_out/ncu_layers.log 2>&1
   echo "ncu_layers_exit=$?"; tail -3 gpurun_out/ncu_layers.log;;
 ncu_k1)
   CMD="python bench.py --workload varint1g --stream-bytes 268435456 --steps 1 --warmup 3 --no-cpu-baseline"
   $CMD > gpurun_out/plain_k1.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:k1_varint -s 3 -c 1 -f -o gpurun_out/prof_k1 $CMD > gpurun_out/ncu_k1.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "regex:k1a_|k1b_" -s 4 -c 2 -f -o gpurun_out/prof_k1 $CMD > gpurun_out/ncu_k1.log 2>&1
   echo "ncu_k1_exit=$?"; tail -3 gpurun_out/ncu_k1.log;;
 launches)
   CMD="python bench.py --tiles 65536 --steps 2 --warmup 3 --no-cpu-baseline"
