@@ -85,21 +85,65 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): an NVML polling thread
+    (same counters nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.* prints; a 100 ms nvidia-smi loop is too coarse
+    for a timed region of a few hundred milliseconds), with the nvidia-smi loop as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.stop_flag = threading.Event()
+        self.thread = self.p = self.f = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as N
+            N.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps ordinals: resolve through the PCI bus id of the CUDA device
+            try:
+                import torch
+                bus = torch.cuda.get_device_properties(device).pci_bus_id
+                h = N.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (torch.cuda.get_device_properties(device).pci_domain_id, bus,
+                                                                            torch.cuda.get_device_properties(device).pci_device_id)).encode())
+            except Exception:
+                h = N.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            names = (("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap))
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for nm, bit in names:
+                            if r & bit:
+                                self.reasons.add(nm)
+                        self.power.append(N.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.005)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.p = None
+            self.thread = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                          stdout=self.f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                out.update({"sm_mhz": float(np.median(self.samples)), "sm_min_mhz": float(min(self.samples)), "sm_max_mhz": self.max_mhz,
+                            "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml",
+                            "power_w_max": max(self.power) if self.power else None})
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -125,6 +169,7 @@ class ClockSampler:
             out["sm_mhz"] = float(np.median(sm))
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
+        out["source"] = "nvidia-smi"
         return out
 
 
@@ -353,7 +398,11 @@ def run_gpu(args, rank, world, local_rank):
             roof = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": k["bytes"] / max(k["launches"], 1),
                     "ms_per_launch": k["ms"] / max(k["launches"], 1), "share_of_step": k["ms"] / max(dev_ms, 1e-9),
-                    "kernels": {n: {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps} for n, v in ktimes.items()}}
+                    "step": {"algorithmic_bytes": payload + outb, "achieved": (payload + outb) * steps / (dev_ms * 1e-3) / 1e9,
+                             "frac": (payload + outb) * steps / (dev_ms * 1e-3) / 1e9 / peak,
+                             "note": "whole step on rank 0: (payload read + final outputs written) / device time of all kernels"},
+                    "kernels": {n: {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps,
+                                        "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0)} for n, v in ktimes.items()}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline and stream_mode:
             from oracle import oracle as O

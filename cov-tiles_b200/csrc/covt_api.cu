@@ -370,7 +370,7 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
     prof.end();
     launches += 2;
     CKR(cudaEventRecord(ev1, st));
-    CKR(cudaMemcpyAsync(ctx->h_totals + 16, d_totals + 16, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CKR(cudaMemcpyAsync(ctx->h_totals + 16, d_totals + 16, FINAL_TOTALS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CKR(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&R->timing.decode_ms, ev0, ev1);
     cudaEventDestroy(ev0);
@@ -379,7 +379,19 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
     R->timing.vertices = ctx->h_totals[16];
     R->timing.payload_bytes = ctx->h_totals[17];
     R->timing.output_bytes = ctx->h_totals[18];
-    if (prof.on) prof.collect(R->kernel_times);
+    if (prof.on) {
+        // algorithmic bytes per kernel: known only now that k_finalize has summed them on the device
+        const uint64_t meta_bytes = batch->blob_len > R->timing.payload_bytes ? batch->blob_len - R->timing.payload_bytes : 0;
+        for (auto& r : prof.recs) {
+            if (r.name == "k0_scan_tiles") r.alg_bytes = meta_bytes + (uint64_t)n_tiles * (8 + TILE_COLS * 8 + 4);
+            else if (r.name == "scan_tile_cols") r.alg_bytes = 2ull * n_tiles * TILE_COLS * 8;
+            else if (r.name == "k0_fill_layers") r.alg_bytes = meta_bytes + (uint64_t)n_tiles * (8 + TILE_COLS * 8) + (uint64_t)R->n_layers * (sizeof(covt_layer) + COVT_NUM_SLOTS * sizeof(DeviceTask));
+            else if (r.name == "k_assemble_layers") r.alg_bytes = ctx->h_totals[16 + 8];
+            else if (r.name == "k_finalize") r.alg_bytes = (uint64_t)R->n_layers * sizeof(covt_layer);
+            else for (int c = 0; c < NUM_OP_CLASSES; c++) if (r.name == op_class_name(c)) r.alg_bytes = ctx->h_totals[16 + 3 + c];
+        }
+        prof.collect(R->kernel_times);
+    }
     R->timing.kernel_launches = n_tiles ? launches : 0;  // k0_scan_tiles, 3 scan kernels, k0_fill_layers, 5 codec classes, assemble, finalize
     (void)out_bytes_alloc;
     cleanup_tmp();

@@ -47,6 +47,7 @@ struct BigStream {
 // after the scan the exclusive prefix of the chunk inside its stream (count, running x, running y).
 // flags: bit 0 = first chunk of its stream, bit 1 = x/y interleaved sums
 struct __align__(16) ChunkState { uint32_t count; int32_t a, b; uint32_t flags; };
+constexpr int FINAL_TOTALS = 9;  // k_finalize: vertices, payload, output bytes, 5 codec classes, assembler
 constexpr int K1_WARPS = 8;
 constexpr int K1_SCAN_BLOCK = 1024;
 
@@ -70,7 +71,7 @@ cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, 
 cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks,
                                     ChunkState* states, ChunkState* block_states, cudaStream_t st);
 cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags,
-                            uint32_t* tile_status, uint64_t* totals /* [0]=vertices [1]=payload bytes [2]=output bytes */,
+                            uint32_t* tile_status, uint64_t* totals /* [FINAL_TOTALS], see k_finalize */,
                             cudaStream_t st);
 uint32_t host_resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags);
 

@@ -916,35 +916,43 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
 // =================================================================================================
 __global__ void k_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags, uint32_t* tile_status, uint64_t* totals)
 {
+    const uint8_t slot_es[COVT_NUM_SLOTS] = {8, 1, 4, 4, 4, 4, 4, 4};
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t verts = 0, payload = 0, outb = 0;
+    // [0] vertices [1] payload bytes [2] output bytes [3..7] algorithmic bytes per codec class [8] assembler algorithmic bytes
+    uint64_t acc[FINAL_TOTALS];
+    for (int i = 0; i < FINAL_TOTALS; i++) acc[i] = 0;
     if (t < n_tiles) {
         uint32_t st = tile_status[t];
         for (uint32_t l = first_layer[t]; l < first_layer[t + 1]; l++) {
             const covt_layer& L = layers[l];
             if (L.status && !st) st = L.status;
-            verts += L.n_vertices;
-            for (int s = 0; s < COVT_NUM_SLOTS; s++)
-                if (L.streams[s].encoding != COVT_ENC_ABSENT) payload += L.streams[s].byte_length;
-            // algorithmic output bytes: every decoded stream + the assembled buffers, no padding
-            const uint64_t F = slot_nv(L, COVT_SLOT_TYPES);
-            outb += F + 8 * slot_nv(L, COVT_SLOT_ID) +
-                    4 * (slot_nv(L, COVT_SLOT_GEOM) + slot_nv(L, COVT_SLOT_PART) + slot_nv(L, COVT_SLOT_RING) +
-                         slot_nv(L, COVT_SLOT_VOFF) + vbuf_ints_of(L, flags) + slot_nv(L, COVT_SLOT_INDEX));
-            if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && L.status == COVT_OK)
-                outb += 4ull * ((F + 1) + (L.n_parts + 1ull) + (L.n_rings + 1ull)) + 8ull * L.n_coords;
+            acc[0] += L.n_vertices;
+            // algorithmic bytes: payload read + decoded stream written, no padding, no intermediates
+            for (int s = 0; s < COVT_NUM_SLOTS; s++) {
+                if (L.streams[s].encoding == COVT_ENC_ABSENT) continue;
+                const uint64_t nv = s == COVT_SLOT_VBUF ? vbuf_ints_of(L, flags) : (uint64_t)L.streams[s].num_values;
+                const uint64_t ob = nv * slot_es[s];
+                acc[1] += L.streams[s].byte_length;
+                acc[2] += ob;
+                const int c = op_class_of(L.streams[s].op);
+                if (c >= 0) acc[3 + c] += L.streams[s].byte_length + ob;
+            }
+            if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && L.status == COVT_OK) {
+                const uint64_t F = slot_nv(L, COVT_SLOT_TYPES);
+                const uint64_t wr = 4ull * ((F + 1) + (L.n_parts + 1ull) + (L.n_rings + 1ull)) + 8ull * L.n_coords;
+                // reads: types, the three count streams, one offset per vertex for ICE layers, one (x,y) per output vertex
+                const uint64_t rd = F + 4ull * (slot_nv(L, COVT_SLOT_GEOM) + slot_nv(L, COVT_SLOT_PART) + slot_nv(L, COVT_SLOT_RING)) +
+                                    (L.streams[COVT_SLOT_VOFF].encoding != COVT_ENC_ABSENT ? 4ull * L.n_vertices : 0ull) + 8ull * L.n_coords;
+                acc[2] += wr;
+                acc[8] += wr + rd;
+            }
         }
         tile_status[t] = st;
     }
-    for (int d = 16; d >= 1; d >>= 1) {
-        verts += __shfl_down_sync(FULL, verts, d);
-        payload += __shfl_down_sync(FULL, payload, d);
-        outb += __shfl_down_sync(FULL, outb, d);
-    }
-    if ((threadIdx.x & 31u) == 0) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[0]), (unsigned long long)verts);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[1]), (unsigned long long)payload);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[2]), (unsigned long long)outb);
+    for (int i = 0; i < FINAL_TOTALS; i++) {
+        uint64_t v = acc[i];
+        for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(FULL, v, d);
+        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(reinterpret_cast<unsigned long long*>(&totals[i]), (unsigned long long)v);
     }
 }
 

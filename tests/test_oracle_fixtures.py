@@ -1,0 +1,135 @@
+"""CPU: pins the oracle (oracle/covt_oracle.c, the checker of every GPU parity test) against the reference's own data.
+
+The JVM is absent, so the Java decoder cannot run here; what the reference ships instead are 129 gen-2b `.covt`
+fixture tiles with `.mvt`/`.pbf` partners (test/fixtures/{omt,amazon,bing}) — committed under tests/golden/ by
+tests/golden/make_golden.py. The oracle must
+  * walk every tile's container EOF-exactly,
+  * consume exactly the declared byteLength of every stream (17 758 RLE, 14 879 Byte-RLE, 1 045 FastPFOR, ... streams),
+  * assemble geometry equal to the partner MVT (blake2b digests of the canonical form, tests/canon.py),
+  * and its decoded values must re-encode (tools/gen = restatement of EncodingUtils.java) to the very bytes in the fixture.
+"""
+import numpy as np
+
+import canon
+import util
+
+
+def _flags(abi, name):
+    return util.fixture_flags(abi, name)
+
+
+def test_container_walk_is_eof_exact(oracle, fixtures):
+    abi = oracle.abi
+    n_layers = 0
+    for name, data in fixtures:
+        rc, layers, end_pos = oracle.parse_tile(np.frombuffer(data, np.uint8), abi.CONTAINER_GEN2B, flags=_flags(abi, name))
+        assert rc == 0, name
+        assert end_pos == len(data), "%s: walk ended at %d of %d" % (name, end_pos, len(data))
+        n_layers += len(layers)
+    assert len(fixtures) == 129 and n_layers >= 1375
+
+
+def test_every_stream_consumes_its_declared_length_and_reencodes(oracle, gen, fixtures):
+    abi = oracle.abi
+    seen = {}
+    identical = {}
+    for name, data in fixtures:
+        blob = np.frombuffer(data, np.uint8)
+        flags = _flags(abi, name)
+        rc, layers, _ = oracle.parse_tile(blob, abi.CONTAINER_GEN2B, flags=flags)
+        for L in layers:
+            key = "%s/%s" % (name, util.layer_name(blob, L))
+            for s in range(abi.NUM_SLOTS):
+                S = L["streams"][s]
+                if S["encoding"] == abi.ENC_ABSENT or S["op"] == abi.OP_NONE:
+                    continue
+                op, off, bl, nv = int(S["op"]), int(S["byte_offset"]), int(S["byte_length"]), int(S["num_values"])
+                if s == abi.SLOT_VBUF and L["geom_column_type"] == abi.CT_ICE:
+                    nv *= 2  # encoder wrote #vertices (SURVEY §8a dispatch table)
+                vals, st, cons = oracle.decode_stream(blob, op, byte_offset=off, byte_length=bl, num_values=nv,
+                                                      num_bits=int(L["num_bits"]), flags=flags)
+                cname = abi.OP_NAMES[op].upper()
+                if key in util.KNOWN_MISLABELLED and s == abi.SLOT_VBUF:
+                    assert st != 0, key
+                    continue
+                assert st == 0, "%s slot %d op %s status %d" % (key, s, cname, st)
+                assert cons == bl, "%s slot %d op %s consumed %d of %d" % (key, s, cname, cons, bl)
+                seen[cname] = seen.get(cname, 0) + 1
+                # re-encode with the restated EncodingUtils encoders: must give back the fixture bytes
+                payload = blob[off:off + bl]
+                enc = None
+                if op == abi.OP_BYTE_RLE:
+                    enc = gen.encode_byte_rle(vals)
+                elif op in (abi.OP_RLE_U32, abi.OP_RLE_U64):
+                    enc = gen.encode_rle(vals.astype(np.int64), signed=False)
+                elif op == abi.OP_VARINT_ZZ_DELTA:
+                    enc = gen.encode_varints(vals.astype(np.int64), zigzag=True, delta=True)
+                elif op == abi.OP_VARINT_ZZ_DELTA_XY:
+                    zz = gen.encode_zigzag_delta_coordinates(vals.astype(np.int32)).astype(np.int64) & 0xFFFFFFFF
+                    enc = gen.encode_varints(zz)
+                elif op == abi.OP_PFOR_ZZ_DELTA:
+                    enc = gen.encode_fastpfor(vals.astype(np.int32), zigzag=True, delta=True)
+                elif op == abi.OP_PFOR_ZZ_DELTA_XY:
+                    enc = gen.encode_fastpfor(gen.encode_zigzag_delta_coordinates(vals.astype(np.int32)), zigzag=False, delta=False)
+                if enc is None:
+                    continue
+                same = len(enc) == bl and np.array_equal(enc, payload)
+                tot, ok = identical.get(cname, (0, 0))
+                identical[cname] = (tot + 1, ok + int(same))
+                if not same and not (cname.startswith("PFOR") and nv > 65536):
+                    # JavaFastPFOR leaks stale exception-array contents into padding bits of pages >= 2
+                    raise AssertionError("%s slot %d op %s: re-encoding differs (%d vs %d bytes)" % (key, s, cname, len(enc), bl))
+    # the fixture corpus exercises every codec family of the path
+    for fam in ("BYTE_RLE", "RLE_U32", "RLE_U64", "VARINT_ZZ_DELTA", "VARINT_DELTA_MORTON", "PFOR_ZZ_DELTA"):
+        assert seen.get(fam, 0) > 0, (fam, seen)
+    assert seen["BYTE_RLE"] >= 1375 and seen["RLE_U32"] + seen["RLE_U64"] >= 1000
+    pf_tot = sum(v[0] for k, v in identical.items() if k.startswith("PFOR"))
+    pf_ok = sum(v[1] for k, v in identical.items() if k.startswith("PFOR"))
+    assert pf_tot >= 900 and pf_tot - pf_ok <= 30, identical
+    for k, (tot, ok) in identical.items():
+        if not k.startswith("PFOR"):
+            assert tot == ok, (k, tot, ok)
+
+
+def test_assembled_geometry_equals_partner_mvt(oracle, fixtures):
+    abi = oracle.abi
+    digests = util.mvt_digests()
+    checked = 0
+    for z8 in (False, True):
+        tiles = [(n, b) for n, b in fixtures if n.startswith("omt/8_") == z8 and not n.startswith("bing/")]
+        blob, offs = util.concat_tiles([b for _, b in tiles])
+        flags = abi.FLAG_ID_DVZZ_IS_RLE | (abi.FLAG_MORTON_NO_SHIFT if z8 else 0)
+        ref = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags)
+        assert np.all(ref.tile_status[[i for i, (n, _) in enumerate(tiles)
+                                        if not any(k.startswith(n + "/") for k in util.KNOWN_MISLABELLED)]] == 0)
+        for L in ref.layers:
+            key = "%s/%s" % (tiles[L["tile"]][0], util.layer_name(blob, L))
+            if key in util.KNOWN_MISLABELLED:
+                assert L["status"] != 0
+                continue
+            assert L["status"] == 0, key
+            if key in util.KNOWN_MVT_MISMATCH or key not in digests:
+                continue
+            c = canon.canonical_from_assembled(*canon.layer_slices(L, ref.buffers, abi))
+            d = digests[key]
+            assert (len(c[0]), len(c[1]), len(c[2]) // 2) == (d["features"], d["rings"], d["vertices"]), key
+            assert canon.digest(c) == d["digest"], key
+            checked += 1
+    assert checked >= 1100
+
+
+def test_config1_layer_shape(oracle, fixtures):
+    """BASELINE config 1 (SURVEY §8a sizes): transportation layer of omt/5_16_21."""
+    abi = oracle.abi
+    data = dict(fixtures)["omt/5_16_21"]
+    blob = np.frombuffer(data, np.uint8)
+    ref = oracle.decode_batch(blob, np.array([0, len(blob)], np.uint64), abi.CONTAINER_GEN2B, abi.FLAG_ID_DVZZ_IS_RLE)
+    for L in ref.layers:
+        if util.layer_name(blob, L) == "transportation":
+            assert L["num_features"] == 45232 and L["n_vertices"] == 92378
+            assert L["streams"][abi.SLOT_VOFF]["num_values"] == 92378 and L["streams"][abi.SLOT_VOFF]["byte_length"] == 121267
+            assert L["streams"][abi.SLOT_VBUF]["num_values"] == 19704 and L["streams"][abi.SLOT_VBUF]["byte_length"] == 26176
+            assert L["streams"][abi.SLOT_PART]["num_values"] == 45234 and L["streams"][abi.SLOT_PART]["byte_length"] == 3504
+            assert L["streams"][abi.SLOT_TYPES]["byte_length"] == 702 and L["streams"][abi.SLOT_ID]["byte_length"] == 1656
+            return
+    raise AssertionError("transportation layer not found")
