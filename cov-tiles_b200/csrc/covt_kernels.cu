@@ -778,29 +778,37 @@ __device__ __forceinline__ uint32_t k1_find_stream(const BigStream* streams, uin
     return lo;
 }
 
-struct K1Window {
-    uint4 w;
-    uint32_t valid16, halo, head_fakes, head;
-    uint64_t off;
+// One warp chunk of a large stream: the lane window, what is outside the stream, and the halo of lane 0.
+struct K1Chunk {
+    uint4 win;
+    uint64_t off;       // window-relative byte offset of this lane's 16 bytes (stream start = head)
+    uint32_t head;      // bytes between the 16-byte aligned window origin and the first stream byte
+    uint32_t head_f;    // leading fake values of this chunk (= head for chunk 0)
+    uint32_t tail_f;    // trailing fake values (zeroed bytes after the stream end)
+    uint32_t lo16, hi16;
+    uint32_t halo0;     // the 4 bytes before the chunk (lane 0)
+    bool partial;
 };
-__device__ __forceinline__ K1Window k1_load_window(const uint8_t* blob, const BigStream& S, uint32_t ci)
+__device__ __forceinline__ K1Chunk k1_load_chunk(const uint8_t* blob, const BigStream& S, uint32_t ci)
 {
-    K1Window k;
+    K1Chunk k;
     const unsigned lane = lane_id();
     const uint8_t* src = blob + S.src_offset;
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15);
     k.head = (uint32_t)(reinterpret_cast<uintptr_t>(src) - a0);
     const uint64_t total = (uint64_t)k.head + S.byte_length;
-    k.off = (uint64_t)ci * WARP_CHUNK_BYTES + lane * 16u;
-    k.w = make_uint4(0, 0, 0, 0);
-    if (k.off < total) k.w = ldg_stream128(reinterpret_cast<const void*>(a0 + k.off));
-    const uint32_t lo16 = k.off >= k.head ? 0u : (uint32_t)umin64(16, k.head - k.off);
-    const uint32_t hi16 = k.off >= total ? 0u : (uint32_t)umin64(16, total - k.off);
-    k.valid16 = ((1u << hi16) - 1u) & ~((1u << lo16) - 1u);
-    k.head_fakes = lo16;
-    // halo of lane 0 = the 4 bytes before this chunk (always inside the stream when ci > 0)
-    k.halo = 0;
-    if (lane == 0 && ci > 0) k.halo = __ldg(reinterpret_cast<const uint32_t*>(a0 + k.off - 4));
+    const uint64_t base = (uint64_t)ci * WARP_CHUNK_BYTES;
+    k.off = base + lane * 16u;
+    k.win = make_uint4(0, 0, 0, 0);
+    if (k.off < total) k.win = ldg_stream128(reinterpret_cast<const void*>(a0 + k.off));
+    k.head_f = ci == 0 ? k.head : 0u;
+    const uint32_t end_in_chunk = (uint32_t)umin64(WARP_CHUNK_BYTES, total - base);
+    k.tail_f = WARP_CHUNK_BYTES - end_in_chunk;
+    k.partial = k.head_f != 0u || k.tail_f != 0u;
+    k.lo16 = k.head_f > lane * 16u ? min(16u, k.head_f - lane * 16u) : 0u;
+    k.hi16 = end_in_chunk > lane * 16u ? min(16u, end_in_chunk - lane * 16u) : 0u;
+    k.halo0 = 0;
+    if (lane == 0 && ci > 0) k.halo0 = __ldg(reinterpret_cast<const uint32_t*>(a0 + base - 4));
     return k;
 }
 
@@ -813,21 +821,33 @@ k1a_aggregate(const uint8_t* blob, const BigStream* streams, uint32_t n_streams,
     const uint32_t si = k1_find_stream(streams, n_streams, g);
     const BigStream S = streams[si];
     const uint32_t ci = g - S.first_chunk;
-    K1Window k = k1_load_window(blob, S, ci);
-    uint32_t cnt;
-    int32_t a, b;
-    bool overlong = false;
+    K1Chunk k = k1_load_chunk(blob, S, ci);
+    uint32_t w[4], acc, mul, ov = 0;
+    const LeanLane L = lean_front(k.win, k.partial, k.lo16, k.hi16, k.halo0, w, acc, mul, ov);
+    int32_t cur, oth;
     const bool zz = (S.post == POST_ZZ || S.post == POST_ZZ_DELTA || S.post == POST_ZZ_DELTA_XY);
-    if (zz) varint32_chunk_sums<true>(k.w, k.valid16, k.head_fakes, k.halo, cnt, a, b, overlong);
-    else varint32_chunk_sums<false>(k.w, k.valid16, k.head_fakes, k.halo, cnt, a, b, overlong);
+    if (zz) lean_sum_lane<true>(w, L.cm, acc, mul, cur, oth, ov);
+    else lean_sum_lane<false>(w, L.cm, acc, mul, cur, oth, ov);
+    // cur = sum of the class of the lane's NEXT value, oth = the other class (see lean_sum_lane)
+    const bool cnt_odd = L.cnt & 1u;
+    const int32_t e = cnt_odd ? oth : cur, o = cnt_odd ? cur : oth;  // sums at even / odd lane-local positions
+    // chunk-local parity of the lane's first value = parity of the values in the lanes before it
+    const unsigned odd_lanes = __ballot_sync(FULL, cnt_odd);
+    const bool first_odd = __popc(odd_lanes & ((1u << lane) - 1u)) & 1u;
+    int32_t ta = (int32_t)__reduce_add_sync(FULL, (unsigned)(first_odd ? o : e));
+    int32_t tb = (int32_t)__reduce_add_sync(FULL, (unsigned)(first_odd ? e : o));
+    const uint32_t tc = __reduce_add_sync(FULL, L.cnt);
+    if (k.head_f & 1u) { const int32_t t = ta; ta = tb; tb = t; }  // leading fakes shifted every real value by head_f positions
     const bool xy = S.post == POST_ZZ_DELTA_XY;
-    ChunkState v = {cnt, xy ? a : a + b, xy ? b : 0, xy ? 2u : 0u};
-    v = cs_warp_inclusive(v);
-    if (lane == 31) {
+    if (lane == 0) {
+        ChunkState v;
+        v.count = tc - k.head_f - k.tail_f;
+        v.a = xy ? ta : ta + tb;
+        v.b = xy ? tb : 0;
         v.flags = (xy ? 2u : 0u) | (ci == 0 ? 1u : 0u);
         states[g] = v;
     }
-    if (__any_sync(FULL, overlong) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
+    if (__any_sync(FULL, (ov >> 28) & 1u) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
 }
 
 __global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_reduce(const ChunkState* states, uint32_t n, ChunkState* block_states)
@@ -881,7 +901,7 @@ __global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_apply(ChunkState* state
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks, const ChunkState* states)
 {
-    __shared__ uint32_t s_stage[K1_WARPS][STAGE_WORDS];
+    __shared__ uint32_t s_stage[K1_WARPS][LEAN_STAGE_WORDS];
     const unsigned lane = lane_id();
     const uint32_t g = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
     if (g >= n_chunks) return;
@@ -889,26 +909,24 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
     const BigStream S = streams[si];
     const uint32_t ci = g - S.first_chunk;
     const ChunkState P = states[g];
-    K1Window k = k1_load_window(blob, S, ci);
+    K1Chunk k = k1_load_chunk(blob, S, ci);
     uint32_t* stage = s_stage[threadIdx.x >> 5];
-    uint32_t emit, excl, wtotal;
-    bool overlong = false;
-    varint32_chunk_decode<false, false>(k.w, k.valid16, k.halo, 0xffffffffu, stage, emit, excl, wtotal, overlong);
+    uint32_t w[4], acc, mul, ov = 0;
+    LeanLane L = lean_front(k.win, k.partial, k.lo16, k.hi16, k.halo0, w, acc, mul, ov);
+    L.excl = warp_exclusive_scan(L.cnt, L.total);
+    lean_stage_lane(w, L.cm, acc, mul, stage + LEAN_FRONT + L.excl - k.head_f, ov);
     __syncwarp();
-    const int post = S.post;
-    DeltaCarry carry = {P.a, P.b, P.count};
-    warp_delta_pass<16>(stage, wtotal, carry, post, post == POST_ZZ_DELTA || post == POST_ZZ_DELTA_XY);
-    __syncwarp();
+    const uint32_t n_here = L.total - k.head_f - k.tail_f;
     // bytes the reference reader consumes = position right after the terminator of value #num_values
     {
-        const uint32_t first = P.count + excl, cnt = __popc(emit);
-        if (S.consumed_out && S.num_values > first && S.num_values <= first + cnt)
-            *S.consumed_out = (uint32_t)(k.off + __fns(emit, 0, (int)(S.num_values - first)) + 1u - k.head);
+        const int64_t first = (int64_t)P.count + L.excl - k.head_f;  // stream index of the lane's first terminator (fakes negative)
+        if (S.consumed_out && S.num_values > 0u && (int64_t)S.num_values > first && (int64_t)S.num_values <= first + (int64_t)L.cnt)
+            *S.consumed_out = (uint32_t)(k.off + lean_nth_terminator(L.cm, (uint32_t)((int64_t)S.num_values - first)) - k.head);
     }
-    if (ci == S.n_chunks - 1 && lane == 0 && P.count + wtotal < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
+    if (ci == S.n_chunks - 1 && lane == 0 && P.count + n_here < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
     const uint32_t room = P.count < S.num_values ? S.num_values - P.count : 0u;
-    const int copy_kind = post == POST_DELTA_MORTON ? COPY_MORTON : (post == POST_ZZ ? COPY_I32_ZZ : COPY_I32);
-    warp_copy_out<16>(stage, min(wtotal, room), S.dst, P.count, copy_kind, S.num_bits, S.no_shift != 0);
+    int32_t cx = P.a, cy = P.b;
+    lean_rows_dispatch(S.post, false, stage + LEAN_FRONT, min(n_here, room), S.dst, P.count, cx, cy, S.num_bits, S.no_shift != 0);
 }
 
 // =================================================================================================

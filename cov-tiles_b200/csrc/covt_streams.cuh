@@ -6,6 +6,7 @@
 // multi-CTA decoupled-look-back kernel in k1_varint_stream.cu instead.
 #pragma once
 #include "covt_device.cuh"
+#include "covt_varint.cuh"
 
 namespace covt {
 
@@ -39,46 +40,56 @@ __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t*
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(t.src) & ~uintptr_t(15);
     const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(t.src) - a0);
     const uint64_t total = (uint64_t)head + t.byte_length;
-    DeltaCarry carry = {0, 0, 0};
-    uint32_t halo = 0;
-    bool overlong = false;
-    uint32_t consumed = 0;
-    const bool zz_delta = (post == POST_ZZ_DELTA || post == POST_ZZ_DELTA_XY);
-    const int copy_kind = widen ? COPY_I64 : (post == POST_DELTA_MORTON ? COPY_MORTON : (post == POST_ZZ ? COPY_I32_ZZ : COPY_I32));
-    for (uint64_t base = 0; base < total && carry.produced < t.num_values; base += WARP_CHUNK_BYTES) {
+    uint32_t carry_halo = 0, ov = 0, produced = 0, consumed = 0;
+    int32_t cx = 0, cy = 0;
+    for (uint64_t base = 0; base < total && produced < t.num_values; base += WARP_CHUNK_BYTES) {
         const uint64_t off = base + lane * 16u;
-        uint4 w = make_uint4(0, 0, 0, 0);
-        if (off < total) w = ldg_stream128(reinterpret_cast<const void*>(a0 + off));
-        const uint32_t lo16 = off >= head ? 0u : (uint32_t)umin64(16, head - off);
-        const uint32_t hi16 = off >= total ? 0u : (uint32_t)umin64(16, total - off);
-        uint32_t valid16 = ((1u << hi16) - 1u) & ~((1u << lo16) - 1u);
-        const uint32_t remaining = t.num_values - carry.produced;
-        // bytes after the last value the caller asked for belong to somebody else: find the cut first
-        uint32_t emit, excl, ctotal;
+        uint4 win = make_uint4(0, 0, 0, 0);
+        if (off < total) win = ldg_stream128(reinterpret_cast<const void*>(a0 + off));
+        const uint32_t head_f = base == 0 ? head : 0u;
+        uint32_t end_in_chunk = (uint32_t)umin64(WARP_CHUNK_BYTES, total - base);  // window-relative end of the stream
+        const uint32_t remaining = t.num_values - produced;
+        uint32_t w[4], acc, mul, lane_ov = 0;
+        uint32_t halo_in = carry_halo;
+        auto bounds = [&](uint32_t& lo16, uint32_t& hi16) {
+            lo16 = head_f > lane * 16u ? min(16u, head_f - lane * 16u) : 0u;
+            hi16 = end_in_chunk > lane * 16u ? min(16u, end_in_chunk - lane * 16u) : 0u;
+        };
+        uint32_t lo16, hi16;
+        bounds(lo16, hi16);
+        LeanLane L = lean_front(win, head_f != 0u || end_in_chunk < WARP_CHUNK_BYTES, lo16, hi16, halo_in, w, acc, mul, lane_ov);
+        L.excl = warp_exclusive_scan(L.cnt, L.total);
         if (!t.exact_length) {
-            uint32_t words[4] = {w.x, w.y, w.z, w.w};
-            uint32_t e0 = (~gather_msb16(words) & 0xffffu) & valid16;
-            uint32_t tot0;
-            uint32_t ex0 = warp_exclusive_scan(__popc(e0), tot0);
-            uint32_t cut = chunk_cut_position(e0, ex0, remaining);
-            if (cut) {
-                consumed = (uint32_t)(base + cut - head);
-                uint32_t keep = cut > lane * 16u ? min(16u, cut - lane * 16u) : 0u;
-                valid16 &= (1u << keep) - 1u;
+            // DecodingUtils "pos" semantics: bytes after the last requested value belong to somebody else. Find the terminator
+            // of value #remaining; if it lies in this chunk, the stream ends there.
+            const int32_t first = (int32_t)L.excl - (int32_t)head_f;  // chunk-local index of the lane's first value
+            const bool mine = remaining > 0u && (int32_t)remaining > first && (int32_t)remaining <= first + (int32_t)L.cnt;
+            const unsigned b = __ballot_sync(FULL, mine);
+            if (b) {
+                uint32_t pos = 0;
+                if (mine) pos = lane * 16u + lean_nth_terminator(L.cm, remaining - (uint32_t)first);
+                end_in_chunk = __shfl_sync(FULL, pos, __ffs(b) - 1);
+                consumed = (uint32_t)(base + end_in_chunk - head);
+                bounds(lo16, hi16);
+                halo_in = carry_halo;
+                lane_ov = 0;
+                L = lean_front(win, true, lo16, hi16, halo_in, w, acc, mul, lane_ov);
+                L.excl = warp_exclusive_scan(L.cnt, L.total);
             }
         }
-        varint32_chunk_decode<false, true>(w, valid16, halo, remaining, stage, emit, excl, ctotal, overlong);
-        const uint32_t n = min(ctotal, remaining);
+        carry_halo = halo_in;
+        ov |= lane_ov;
+        const uint32_t tail_f = WARP_CHUNK_BYTES - end_in_chunk;
+        lean_stage_lane(w, L.cm, acc, mul, stage + LEAN_FRONT + L.excl - head_f, ov);
         __syncwarp();
-        warp_delta_pass<16>(stage, n, carry, post, zz_delta);
+        const uint32_t n = min(L.total - head_f - tail_f, remaining);
+        lean_rows_dispatch(post, widen, stage + LEAN_FRONT, n, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
         __syncwarp();
-        warp_copy_out<16>(stage, n, t.dst, carry.produced, copy_kind, t.num_bits, t.no_shift != 0);
-        __syncwarp();
-        carry.produced += n;
+        produced += n;
     }
     out.consumed = t.exact_length ? t.byte_length : consumed;
-    if (carry.produced < t.num_values) out.status = COVT_ERR_TRUNCATED;  // Java: ArrayIndexOutOfBounds
-    else if (__any_sync(FULL, overlong)) out.status = COVT_ERR_VARINT_OVERLONG;
+    if (produced < t.num_values) out.status = COVT_ERR_TRUNCATED;  // Java: ArrayIndexOutOfBounds
+    else if (__any_sync(FULL, (ov >> 28) & 1u)) out.status = COVT_ERR_VARINT_OVERLONG;
     else out.status = COVT_OK;
 }
 
