@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
 
 # every symbol include/covt_b200.h declares
 ABI_SYMBOLS = [
-    "covt_abi_version", "covt_create", "covt_destroy", "covt_last_error", "covt_decode_batch", "covt_batch_upload",
+    "covt_abi_version", "covt_create", "covt_destroy", "covt_last_error", "covt_trim", "covt_decode_batch", "covt_batch_upload",
     "covt_batch_decode", "covt_batch_free", "covt_decode_streams", "covt_batch_decode_streams", "covt_resolve_op",
     "covt_result_num_tiles", "covt_result_num_layers", "covt_result_layers", "covt_result_tile_status",
     "covt_result_buffer", "covt_result_read", "covt_result_timing", "covt_result_kernel_times", "covt_result_free",
@@ -63,6 +63,7 @@ def lib():
     L.covt_destroy.argtypes = [vp]
     L.covt_destroy.restype = None
     L.covt_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.covt_trim.argtypes = [vp]
     L.covt_decode_batch.argtypes = [vp, vp, vp, u32, u32, C.POINTER(abi.TileJson), u32, C.POINTER(vp)]
     L.covt_batch_upload.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
     L.covt_batch_decode.argtypes = [vp, vp, u32, C.POINTER(abi.TileJson), u32, C.POINTER(vp)]
@@ -236,6 +237,10 @@ class Decoder:
             self.close()
         except Exception:
             pass
+
+    def trim(self):
+        """Return the device blocks parked by finished decodes to the driver (covt_trim)."""
+        self._check(lib().covt_trim(self._h))
 
     def _check(self, rc):
         if rc:

@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # covt_stream_encoding
 ENC_PLAIN, ENC_VARINT, ENC_VARINT_ZIG_ZAG, ENC_VARINT_DELTA, ENC_VARINT_DELTA_ZIG_ZAG = 0, 1, 2, 3, 4
@@ -108,7 +108,7 @@ class TileJson(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("decode_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("payload_bytes", C.c_uint64), ("output_bytes", C.c_uint64),
-                ("vertices", C.c_uint64)]
+                ("vertices", C.c_uint64), ("segments", C.c_uint32), ("capacity_retries", C.c_uint32)]
 
 
 class KernelTime(C.Structure):

@@ -5,9 +5,13 @@
 // hands out device pointers. There is no CPU fallback: without a CUDA device every call fails.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "covt_internal.h"
@@ -30,9 +34,18 @@ struct KernelRecord {
 struct covt_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // kernels, allocations, result read-backs
+    cudaStream_t copy_stream = nullptr;  // host->device segments of covt_decode_batch, overlapped with the kernels
     std::string err;
     uint64_t* h_totals = nullptr;  // pinned scratch for the one device->host size read-back
+    covt::SegState* h_seg = nullptr;     // pinned mirror of the device-side segment state
+    uint64_t seg_bytes = 64ull << 20;    // minimum upload/decode segment size of covt_decode_batch (env COVT_SEG_BYTES overrides: tests)
+    uint32_t max_segments = 8;           // env COVT_MAX_SEGMENTS overrides
+    bool debug = false;                  // env COVT_DEBUG: host-side phase times on stderr
+    std::vector<std::pair<void*, uint64_t>> dev_cache;   // parked device blocks (see dev_alloc_bytes)
+    std::unordered_map<void*, uint64_t> dev_live;         // cache-eligible blocks in use
+    std::vector<std::pair<void*, size_t>> pinned_cache;  // page-locked host blocks handed to results and taken back on free
+    uint32_t overflow_retries = 0;       // how often an extrapolated capacity was too small (diagnostics, tests)
     std::vector<cudaEvent_t> event_pool;
 };
 
@@ -51,6 +64,7 @@ struct covt_result {
     covt_layer* d_layers = nullptr;
     uint32_t* d_tile_status = nullptr;
     uint32_t* d_first_layer = nullptr;
+    void* arena = nullptr;               // ONE device allocation behind bufs[] (fewer, larger pool blocks: stable reuse)
     void* bufs[COVT_NUM_BUFFERS] = {};
     uint64_t counts[COVT_NUM_BUFFERS] = {};
     covt_layer* h_layers = nullptr;      // pinned, lazily fetched
@@ -73,20 +87,97 @@ struct covt_result {
 
 namespace {
 
+double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 int32_t fail(covt_ctx* ctx, int32_t code, const char* msg)
 {
     if (ctx) ctx->err = msg;
     return code;
 }
 
+// Device memory. Large blocks (>= 1 MiB) are kept by the context after use and handed out again: the stream-ordered pool
+// alone re-maps physical memory whenever the sizes of successive requests differ (measured: 4 .. 640 ms for the 19.7 GB
+// result arena of a 1 M tile batch), which would dominate the end-to-end time of back-to-back decode calls. Reuse is in
+// stream order on ctx->stream, so no synchronisation is needed.
+constexpr uint64_t DEV_CACHE_MIN = 1ull << 20;
+constexpr size_t DEV_CACHE_BLOCKS = 24;
+
+cudaError_t dev_alloc_bytes(covt_ctx* ctx, void** p, uint64_t bytes)
+{
+    bytes = std::max<uint64_t>(bytes, 64);
+    if (bytes >= DEV_CACHE_MIN) {
+        size_t best = SIZE_MAX;
+        for (size_t i = 0; i < ctx->dev_cache.size(); i++) {
+            const uint64_t have = ctx->dev_cache[i].second;
+            if (have >= bytes && have <= bytes + bytes / 2 && (best == SIZE_MAX || have < ctx->dev_cache[best].second)) best = i;
+        }
+        if (best != SIZE_MAX) {
+            *p = ctx->dev_cache[best].first;
+            ctx->dev_live[*p] = ctx->dev_cache[best].second;
+            ctx->dev_cache.erase(ctx->dev_cache.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e == cudaErrorMemoryAllocation && !ctx->dev_cache.empty()) {
+        // out of memory with blocks parked in the cache: give them back and try once more
+        (void)cudaGetLastError();
+        for (auto& b : ctx->dev_cache) cudaFreeAsync(b.first, ctx->stream);
+        ctx->dev_cache.clear();
+        cudaStreamSynchronize(ctx->stream);
+        e = cudaMallocAsync(p, bytes, ctx->stream);
+    }
+    if (e == cudaSuccess && bytes >= DEV_CACHE_MIN) ctx->dev_live[*p] = bytes;
+    return e;
+}
 template <class T>
 cudaError_t dev_alloc(covt_ctx* ctx, T** p, uint64_t count)
 {
-    return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<uint64_t>(count, 1) * sizeof(T) + 64, ctx->stream);
+    return dev_alloc_bytes(ctx, reinterpret_cast<void**>(p), std::max<uint64_t>(count, 1) * sizeof(T) + 64);
 }
 void dev_free(covt_ctx* ctx, void* p)
 {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (!p) return;
+    auto it = ctx->dev_live.find(p);
+    if (it != ctx->dev_live.end()) {
+        const uint64_t bytes = it->second;
+        ctx->dev_live.erase(it);
+        if (ctx->dev_cache.size() < DEV_CACHE_BLOCKS) { ctx->dev_cache.emplace_back(p, bytes); return; }
+        // cache full: drop the smallest parked block instead if this one is larger
+        size_t smallest = 0;
+        for (size_t i = 1; i < ctx->dev_cache.size(); i++) if (ctx->dev_cache[i].second < ctx->dev_cache[smallest].second) smallest = i;
+        if (ctx->dev_cache[smallest].second < bytes) {
+            cudaFreeAsync(ctx->dev_cache[smallest].first, ctx->stream);
+            ctx->dev_cache[smallest] = {p, bytes};
+            return;
+        }
+    }
+    cudaFreeAsync(p, ctx->stream);
+}
+
+// Page-locked host memory is expensive to allocate (milliseconds): results borrow blocks from the context and give them back.
+cudaError_t pinned_take(covt_ctx* ctx, void** p, size_t bytes)
+{
+    size_t best = SIZE_MAX;
+    for (size_t i = 0; i < ctx->pinned_cache.size(); i++)
+        if (ctx->pinned_cache[i].second >= bytes && (best == SIZE_MAX || ctx->pinned_cache[i].second < ctx->pinned_cache[best].second)) best = i;
+    if (best != SIZE_MAX && ctx->pinned_cache[best].second <= 2 * bytes + 4096) {
+        *p = ctx->pinned_cache[best].first;
+        ctx->pinned_cache.erase(ctx->pinned_cache.begin() + best);
+        return cudaSuccess;
+    }
+    return cudaMallocHost(p, std::max<size_t>(bytes, 64));
+}
+void pinned_give(covt_ctx* ctx, void* p, size_t bytes)
+{
+    if (!p) return;
+    if (ctx->pinned_cache.size() >= 8) { cudaFreeHost(p); return; }
+    ctx->pinned_cache.emplace_back(p, std::max<size_t>(bytes, 64));
 }
 
 // per-kernel timing (COVT_FLAG_PROFILE_KERNELS)
@@ -170,8 +261,13 @@ int32_t covt_create(int32_t device, covt_ctx** out)
         return COVT_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* sb = getenv("COVT_SEG_BYTES")) { const long long v = atoll(sb); if (v > 0) ctx->seg_bytes = (uint64_t)v; }
+    ctx->debug = getenv("COVT_DEBUG") != nullptr;
+    if (const char* ms = getenv("COVT_MAX_SEGMENTS")) { const long long v = atoll(ms); if (v > 0) ctx->max_segments = (uint32_t)std::min<long long>(v, 4096); }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_totals), 64 * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_seg), sizeof(SegState))) != cudaSuccess) return bail("cudaMallocHost", e);
     // keep freed result buffers in the stream-ordered pool: batches are decoded back to back
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -187,7 +283,12 @@ void covt_destroy(covt_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->dev_cache) cudaFreeAsync(b.first, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    if (ctx->h_seg) cudaFreeHost(ctx->h_seg);
+    for (auto& b : ctx->pinned_cache) cudaFreeHost(b.first);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -199,6 +300,18 @@ int32_t covt_last_error(covt_ctx* ctx, char* buf, size_t buf_len)
     if (ctx) m = ctx->err;
     else { std::lock_guard<std::mutex> g(g_err_mutex); m = g_create_error; }
     snprintf(buf, buf_len, "%s", m.c_str());
+    return COVT_OK;
+}
+
+int32_t covt_trim(covt_ctx* ctx)
+{
+    if (!ctx) return COVT_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    for (auto& b : ctx->dev_cache) cudaFreeAsync(b.first, ctx->stream);
+    ctx->dev_cache.clear();
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     return COVT_OK;
 }
 
@@ -235,7 +348,7 @@ int32_t covt_batch_upload(covt_ctx* ctx, const uint8_t* blob, const uint64_t* ti
     CK(cudaEventCreate(&e1));
     cudaError_t e;
     // 256 bytes of zero padding: kernels read whole 16-byte windows and one word past unaligned words
-    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&b->d_blob), b->blob_len + 256, ctx->stream)) != cudaSuccess ||
+    if ((e = dev_alloc_bytes(ctx, reinterpret_cast<void**>(&b->d_blob), b->blob_len + 256)) != cudaSuccess ||
         (e = dev_alloc(ctx, &b->d_tile_offsets, (uint64_t)n_tiles + 1)) != cudaSuccess) {
         delete b;
         CK(e);
@@ -263,29 +376,34 @@ void covt_batch_free(covt_batch* b)
 }
 
 // ------------------------------------------------------------------------------------------------
-// device-resident decode of a whole batch
+// decode of a batch resident in (or on its way to) HBM, one or more segments of tiles
 // ------------------------------------------------------------------------------------------------
-int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, const covt_tilejson* tilejson, uint32_t flags,
-                          covt_result** out)
+// seg_starts: S+1 tile indices, every segment non-empty. uploaded: nullptr (the whole blob is resident) or one event per
+// segment, recorded on the copy stream after that segment's bytes and tile offsets arrived.
+// With S > 1 the capacities of the result buffers are extrapolated from segment 0 (bytes ratio + 10 %); if a later segment
+// does not fit, the device raises SegState::overflow, every later kernel becomes a no-op and the batch is decoded again as one
+// segment with exact sizes (correct, only slower).
+static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t container, const covt_tilejson* tilejson, uint32_t flags,
+                               const std::vector<uint32_t>& seg_starts, const uint64_t* h_tile_offsets,
+                               const std::vector<cudaEvent_t>* uploaded, covt_result** out)
 {
-    if (!ctx || !batch || !out || batch->ctx != ctx) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_batch_decode: bad argument");
-    if (container != COVT_CONTAINER_GEN2B && container != COVT_CONTAINER_GEN3) return fail(ctx, COVT_ERR_INVALID_ARG, "unknown container kind");
     *out = nullptr;
-    CK(cudaSetDevice(ctx->device));
     const uint32_t n_tiles = batch->n_tiles;
+    const uint32_t S = (uint32_t)seg_starts.size() - 1;
     cudaStream_t st = ctx->stream;
     covt_result* R = new covt_result();
     R->ctx = ctx;
     R->n_tiles = n_tiles;
     Profiler prof = {ctx, (flags & COVT_FLAG_PROFILE_KERNELS) != 0, {}};
-    cudaEvent_t ev0, ev1;
-    CK(cudaEventCreate(&ev0));
-    CK(cudaEventCreate(&ev1));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     uint64_t *d_cols = nullptr, *d_block_sums = nullptr, *d_totals = nullptr;
     uint32_t *d_tj = nullptr, *d_counter = nullptr;
+    SegState* d_seg = nullptr;
     DeviceTask* d_tasks = nullptr;
-    const uint32_t nb = (n_tiles + 255) / 256;
+    uint32_t max_seg_tiles = 1;
+    for (uint32_t i = 0; i < S; i++) max_seg_tiles = std::max(max_seg_tiles, seg_starts[i + 1] - seg_starts[i]);
+    const uint32_t nb = (max_seg_tiles + 255) / 256;
     int32_t rc = COVT_OK;
     auto cleanup_tmp = [&]() {
         dev_free(ctx, d_cols);
@@ -294,6 +412,9 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
         dev_free(ctx, d_tj);
         dev_free(ctx, d_counter);
         dev_free(ctx, d_tasks);
+        dev_free(ctx, d_seg);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
     };
 #define CKR(call)                                                                                     \
     do {                                                                                              \
@@ -303,16 +424,20 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
             snprintf(m_, sizeof(m_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
             ctx->err = m_;                                                                            \
             rc = e_ == cudaErrorMemoryAllocation ? COVT_ERR_OOM : COVT_ERR_CUDA;                      \
+            cudaStreamSynchronize(st);                                                                \
             cleanup_tmp();                                                                            \
             covt_result_free(R);                                                                      \
             return rc;                                                                                \
         }                                                                                             \
     } while (0)
 
-    CKR(dev_alloc(ctx, &d_cols, (uint64_t)TILE_COLS * std::max(n_tiles, 1u)));
-    CKR(dev_alloc(ctx, &d_block_sums, (uint64_t)TILE_COLS * std::max(nb, 1u)));
+    CKR(cudaEventCreate(&ev0));
+    CKR(cudaEventCreate(&ev1));
+    CKR(dev_alloc(ctx, &d_cols, (uint64_t)TILE_COLS * max_seg_tiles));
+    CKR(dev_alloc(ctx, &d_block_sums, (uint64_t)TILE_COLS * nb));
     CKR(dev_alloc(ctx, &d_totals, 32));
     CKR(dev_alloc(ctx, &d_counter, 16));
+    CKR(dev_alloc(ctx, &d_seg, 1));
     CKR(dev_alloc(ctx, &R->d_tile_status, (uint64_t)n_tiles + 1));
     CKR(dev_alloc(ctx, &R->d_first_layer, (uint64_t)n_tiles + 2));
     uint32_t tj_layers = 0;
@@ -323,66 +448,114 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
     }
     CKR(cudaMemsetAsync(d_totals, 0, 32 * sizeof(uint64_t), st));
     CKR(cudaMemsetAsync(d_counter, 0, 16 * sizeof(uint32_t), st));
+    CKR(cudaMemsetAsync(d_seg, 0, sizeof(SegState), st));
+    CKR(cudaMemsetAsync(R->d_first_layer, 0, ((uint64_t)n_tiles + 2) * sizeof(uint32_t), st));
 
     CKR(cudaEventRecord(ev0, st));
-    // ---- K0 pass 1: layers per tile + slice sizes; scan; one small read-back sizes everything ----
-    prof.begin("k0_scan_tiles", 0);
-    CKR(launch_k0_scan_tiles(batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, flags, d_cols, R->d_tile_status, st));
-    prof.end();
-    prof.begin("scan_tile_cols", 0);
-    CKR(launch_scan_tile_cols(d_cols, n_tiles, d_block_sums, d_totals, st));
-    prof.end();
-    CKR(cudaMemcpyAsync(ctx->h_totals, d_totals, TILE_COLS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CKR(cudaStreamSynchronize(st));
-    if (ctx->h_totals[0] > 0xfffffff0ull) { cleanup_tmp(); covt_result_free(R); return fail(ctx, COVT_ERR_INVALID_ARG, "too many layers in one batch"); }
-    R->n_layers = (uint32_t)ctx->h_totals[0];
-    uint64_t out_bytes_alloc = 0;
-    for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
-        R->counts[b] = ctx->h_totals[1 + b];
-        const uint64_t bytes = R->counts[b] * kBufElemSize[b];
-        out_bytes_alloc += bytes;
-        if (bytes) CKR(cudaMallocAsync(&R->bufs[b], bytes + 64, st));
-    }
-    CKR(dev_alloc(ctx, &R->d_layers, (uint64_t)R->n_layers));
-    CKR(dev_alloc(ctx, &d_tasks, (uint64_t)R->n_layers * COVT_NUM_SLOTS));
-    ResultBuffers rb;
-    for (int b = 0; b < COVT_NUM_BUFFERS; b++) rb.ptr[b] = R->bufs[b];
-    // ---- K0 pass 2: the layer table + eight decode tasks per layer ----
-    prof.begin("k0_fill_layers", 0);
-    CKR(launch_k0_fill_layers(batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, flags, d_cols, rb, R->d_layers, d_tasks, R->d_first_layer, st));
-    prof.end();
-    CKR(cudaMemcpyAsync(R->d_first_layer + n_tiles, &R->n_layers, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    // ---- every stream of every layer: one kernel per codec class ----
-    const uint32_t n_tasks = R->n_layers * COVT_NUM_SLOTS;
-    uint32_t launches = 5;
-    for (int c = 0; c < NUM_OP_CLASSES; c++) {
-        prof.begin(op_class_name(c), 0);
-        CKR(launch_decode_class(c, batch->d_blob, d_tasks, n_tasks, d_counter + c, ctx->sm_count, st));
+    uint32_t launches = 0;
+    ResultBuffers rb = {};
+    uint64_t task_cap_layers = 0;
+    for (uint32_t sg = 0; sg < S && n_tiles; sg++) {
+        const uint32_t t0 = seg_starts[sg], nt = seg_starts[sg + 1] - t0;
+        if (uploaded) CKR(cudaStreamWaitEvent(st, (*uploaded)[sg], 0));
+        // ---- K0 pass 1: layers per tile + slice sizes; column scan -> this segment's totals ----
+        prof.begin("k0_scan_tiles", 0);
+        CKR(launch_k0_scan_tiles(batch->d_blob, batch->d_tile_offsets + t0, nt, t0, container, d_tj, tj_layers, flags, d_cols, R->d_tile_status + t0, st));
         prof.end();
-        launches++;
+        prof.begin("scan_tile_cols", 0);
+        CKR(launch_scan_tile_cols(d_cols, nt, d_block_sums, d_seg->seg_total, st));
+        prof.end();
+        launches += 4;
+        if (sg == 0) {
+            // the ONE size read-back of the call: segment 0's totals size (or, for several segments, extrapolate) everything
+            CKR(cudaMemcpyAsync(ctx->h_totals, d_seg->seg_total, TILE_COLS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CKR(cudaStreamSynchronize(st));
+            SegState* hs = ctx->h_seg;
+            memset(hs, 0, sizeof(SegState));
+            double scale = 1.0;
+            if (S > 1) {
+                const double seg_bytes = (double)(h_tile_offsets[seg_starts[1]] - h_tile_offsets[0]);
+                scale = seg_bytes > 0 ? (double)batch->blob_len / seg_bytes * 1.10 : 1e9;
+            }
+            for (int c = 0; c < TILE_COLS; c++)
+                hs->cap[c] = S > 1 ? (uint64_t)((double)ctx->h_totals[c] * scale) + 65536 : ctx->h_totals[c];
+            if (hs->cap[0] > 0xfffffff0ull) { cleanup_tmp(); covt_result_free(R); return fail(ctx, COVT_ERR_INVALID_ARG, "too many layers in one batch"); }
+            task_cap_layers = S > 1 ? (uint64_t)((double)ctx->h_totals[0] / nt * max_seg_tiles * 1.25) + 4096 : ctx->h_totals[0];
+            // the task table is per segment: a segment with more layers than it holds counts as an overflow too
+            uint64_t arena_bytes = 0, buf_off[COVT_NUM_BUFFERS];
+            for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
+                buf_off[b] = arena_bytes;
+                arena_bytes += (hs->cap[1 + b] * kBufElemSize[b] + 64 + 255) & ~255ull;
+            }
+            const double t_alloc0 = now_ms();
+            CKR(dev_alloc_bytes(ctx, &R->arena, arena_bytes + 256));
+            for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
+                R->bufs[b] = hs->cap[1 + b] ? static_cast<uint8_t*>(R->arena) + buf_off[b] : nullptr;
+                rb.ptr[b] = R->bufs[b];
+            }
+            if (ctx->debug) fprintf(stderr, "[covt] result arena %.2f GB allocated in %.2f ms (segments %u)\n", arena_bytes / 1e9, now_ms() - t_alloc0, S);
+            CKR(dev_alloc(ctx, &R->d_layers, hs->cap[0]));
+            CKR(dev_alloc(ctx, &d_tasks, task_cap_layers * COVT_NUM_SLOTS));
+            CKR(cudaMemcpyAsync(d_seg->cap, hs->cap, sizeof(hs->cap), cudaMemcpyHostToDevice, st));
+        }
+        CKR(launch_seg_begin(d_seg, d_counter, task_cap_layers, st));
+        // ---- K0 pass 2: the layer table + eight decode tasks per layer ----
+        prof.begin("k0_fill_layers", 0);
+        CKR(launch_k0_fill_layers(batch->d_blob, batch->d_tile_offsets + t0, nt, t0, container, d_tj, tj_layers, flags, d_cols, rb, R->d_layers, d_tasks,
+                                  R->d_first_layer + t0, d_seg, st));
+        prof.end();
+        // ---- every stream of every layer: one kernel per codec class ----
+        const uint32_t n_tasks_bound = (uint32_t)std::min<uint64_t>(task_cap_layers * COVT_NUM_SLOTS, 0xffffff00ull);
+        for (int c = 0; c < NUM_OP_CLASSES; c++) {
+            prof.begin(op_class_name(c), 0);
+            CKR(launch_decode_class(c, batch->d_blob, d_tasks, n_tasks_bound, d_counter + c, d_seg, ctx->sm_count, st));
+            prof.end();
+        }
+        // ---- geometry assembly ----
+        prof.begin("k_assemble_layers", 0);
+        CKR(launch_assemble_layers(R->d_layers, d_tasks, (uint32_t)std::min<uint64_t>(task_cap_layers, 0xffffff00ull), rb, flags, d_counter + 8, d_seg, ctx->sm_count, st));
+        prof.end();
+        CKR(launch_seg_end(d_seg, sg + 1 == S ? R->d_first_layer + n_tiles : nullptr, st));
+        launches += 9;
     }
-    // ---- geometry assembly ----
-    prof.begin("k_assemble_layers", 0);
-    CKR(launch_assemble_layers(R->d_layers, d_tasks, R->n_layers, rb, flags, d_counter + 8, ctx->sm_count, st));
-    prof.end();
-    prof.begin("k_finalize", 0);
-    CKR(launch_finalize(R->d_layers, R->d_first_layer, n_tiles, flags, R->d_tile_status, d_totals + 16, st));
-    prof.end();
-    launches += 2;
+    if (n_tiles) {
+        prof.begin("k_finalize", 0);
+        CKR(launch_finalize(R->d_layers, R->d_first_layer, n_tiles, flags, R->d_tile_status, d_totals + 16, d_seg, st));
+        prof.end();
+        launches += 1;
+    }
     CKR(cudaEventRecord(ev1, st));
     CKR(cudaMemcpyAsync(ctx->h_totals + 16, d_totals + 16, FINAL_TOTALS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CKR(cudaMemcpyAsync(ctx->h_seg, d_seg, sizeof(SegState), cudaMemcpyDeviceToHost, st));
     CKR(cudaStreamSynchronize(st));
+    if (ctx->h_seg->overflow) {
+        // an extrapolated capacity was too small: decode again as ONE segment with exact sizes
+        if (uploaded) cudaStreamSynchronize(ctx->copy_stream);
+        prof.collect(R->kernel_times);
+        cleanup_tmp();
+        covt_result_free(R);
+        if (S == 1) return fail(ctx, COVT_ERR_CUDA, "internal error: exact capacities overflowed");
+        ctx->overflow_retries++;
+        std::vector<uint32_t> one = {0u, n_tiles};
+        rc = decode_segments(ctx, batch, container, tilejson, flags, one, h_tile_offsets, nullptr, out);
+        if (rc == COVT_OK) (*out)->timing.capacity_retries = 1;
+        return rc;
+    }
     cudaEventElapsedTime(&R->timing.decode_ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
+    R->n_layers = (uint32_t)ctx->h_seg->base[0];
+    for (int b = 0; b < COVT_NUM_BUFFERS; b++) R->counts[b] = ctx->h_seg->base[1 + b];
     R->timing.h2d_ms = batch->h2d_ms;
     R->timing.vertices = ctx->h_totals[16];
     R->timing.payload_bytes = ctx->h_totals[17];
     R->timing.output_bytes = ctx->h_totals[18];
     if (prof.on) {
-        // algorithmic bytes per kernel: known only now that k_finalize has summed them on the device
+        // algorithmic bytes per kernel: known only now that k_finalize has summed them on the device;
+        // booked on the first launch of each kernel (the records of one kernel are merged by name)
         const uint64_t meta_bytes = batch->blob_len > R->timing.payload_bytes ? batch->blob_len - R->timing.payload_bytes : 0;
+        std::vector<std::string> seen;
         for (auto& r : prof.recs) {
+            if (std::find(seen.begin(), seen.end(), r.name) != seen.end()) continue;
+            seen.push_back(r.name);
             if (r.name == "k0_scan_tiles") r.alg_bytes = meta_bytes + (uint64_t)n_tiles * (8 + TILE_COLS * 8 + 4);
             else if (r.name == "scan_tile_cols") r.alg_bytes = 2ull * n_tiles * TILE_COLS * 8;
             else if (r.name == "k0_fill_layers") r.alg_bytes = meta_bytes + (uint64_t)n_tiles * (8 + TILE_COLS * 8) + (uint64_t)R->n_layers * (sizeof(covt_layer) + COVT_NUM_SLOTS * sizeof(DeviceTask));
@@ -392,21 +565,105 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
         }
         prof.collect(R->kernel_times);
     }
-    R->timing.kernel_launches = n_tiles ? launches : 0;  // k0_scan_tiles, 3 scan kernels, k0_fill_layers, 5 codec classes, assemble, finalize
-    (void)out_bytes_alloc;
+    R->timing.kernel_launches = launches;
+    R->timing.segments = S;
     cleanup_tmp();
 #undef CKR
     *out = R;
     return COVT_OK;
 }
 
+int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, const covt_tilejson* tilejson, uint32_t flags,
+                          covt_result** out)
+{
+    if (!ctx || !batch || !out || batch->ctx != ctx) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_batch_decode: bad argument");
+    if (container != COVT_CONTAINER_GEN2B && container != COVT_CONTAINER_GEN3) return fail(ctx, COVT_ERR_INVALID_ARG, "unknown container kind");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> one = {0u, batch->n_tiles};
+    return decode_segments(ctx, batch, container, tilejson, flags, one, nullptr, nullptr, out);
+}
+
+// Host input: the blob goes up in segments on the copy stream while earlier segments are being decoded.
 int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
                           const covt_tilejson* tilejson, uint32_t flags, covt_result** out)
 {
-    covt_batch* b = nullptr;
-    int32_t rc = covt_batch_upload(ctx, blob, tile_offsets, n_tiles, &b);
-    if (rc != COVT_OK) return rc;
-    rc = covt_batch_decode(ctx, b, container, tilejson, flags, out);
+    if (!ctx || !out || (!blob && n_tiles) || !tile_offsets) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_decode_batch: null argument");
+    if (container != COVT_CONTAINER_GEN2B && container != COVT_CONTAINER_GEN3) return fail(ctx, COVT_ERR_INVALID_ARG, "unknown container kind");
+    *out = nullptr;
+    for (uint32_t i = 0; i < n_tiles; i++)
+        if (tile_offsets[i + 1] < tile_offsets[i]) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_decode_batch: tile_offsets must be non-decreasing");
+    const uint64_t blob_len = tile_offsets[n_tiles];
+    // segments of ~SEG_BYTES, balanced by payload bytes, every one non-empty
+    // Every segment costs ~1 ms of fixed kernel time (13 launches that are latency-bound at small sizes), so use few, large
+    // segments: at most 8, at least seg_bytes each (measured on B200, 1 M tiles / 2.77 GB: 1 segment 76.5 ms, 6 segments
+    // 57.0 ms, 57 segments 84 ms per call; the host->device copy alone takes 50.4 ms)
+    const uint64_t SEG_BYTES = std::max<uint64_t>(ctx->seg_bytes, 4096);
+    uint32_t want = (uint32_t)std::min<uint64_t>(ctx->max_segments, std::max<uint64_t>(1, (blob_len - tile_offsets[0]) / SEG_BYTES));
+    if (tile_offsets[0] != 0) want = 1;  // the segment extrapolation assumes the blob starts at its first tile
+    std::vector<uint32_t> starts(want + 1);
+    covt_partition_tiles(tile_offsets, n_tiles, want, starts.data());
+    starts.erase(std::unique(starts.begin(), starts.end()), starts.end());
+    if (starts.size() < 2) starts = {0u, n_tiles};
+    const uint32_t S = (uint32_t)starts.size() - 1;
+    if (S == 1) {
+        covt_batch* b = nullptr;
+        int32_t rc = covt_batch_upload(ctx, blob, tile_offsets, n_tiles, &b);
+        if (rc != COVT_OK) return rc;
+        rc = covt_batch_decode(ctx, b, container, tilejson, flags, out);
+        covt_batch_free(b);
+        return rc;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const double t_call0 = now_ms();
+    covt_batch* b = new covt_batch();
+    b->ctx = ctx;
+    b->n_tiles = n_tiles;
+    b->blob_len = blob_len;
+    std::vector<cudaEvent_t> evs(S, nullptr);
+    cudaEvent_t e_alloc = nullptr, e0 = nullptr, e1 = nullptr;
+    auto destroy_events = [&]() {
+        for (auto e : evs) if (e) cudaEventDestroy(e);
+        if (e_alloc) cudaEventDestroy(e_alloc);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    step(dev_alloc_bytes(ctx, reinterpret_cast<void**>(&b->d_blob), blob_len + 256));
+    step(dev_alloc(ctx, &b->d_tile_offsets, (uint64_t)n_tiles + 1));
+    step(cudaEventCreateWithFlags(&e_alloc, cudaEventDisableTiming));
+    step(cudaEventCreate(&e0));
+    step(cudaEventCreate(&e1));
+    step(cudaEventRecord(e_alloc, ctx->stream));
+    step(cudaStreamWaitEvent(ctx->copy_stream, e_alloc, 0));
+    step(cudaEventRecord(e0, ctx->copy_stream));
+    step(cudaMemsetAsync(b->d_blob + blob_len, 0, 256, ctx->copy_stream));
+    for (uint32_t sg = 0; sg < S && e == cudaSuccess; sg++) {
+        const uint32_t t0 = starts[sg], t1 = starts[sg + 1];
+        const uint64_t o0 = tile_offsets[t0], o1 = tile_offsets[t1];
+        if (o1 > o0) step(cudaMemcpyAsync(b->d_blob + o0, blob + o0, o1 - o0, cudaMemcpyHostToDevice, ctx->copy_stream));
+        // tile offsets of the segment, plus the end offset of its last tile
+        step(cudaMemcpyAsync(b->d_tile_offsets + t0, tile_offsets + t0, ((uint64_t)(t1 - t0) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        step(cudaEventCreateWithFlags(&evs[sg], cudaEventDisableTiming));
+        step(cudaEventRecord(evs[sg], ctx->copy_stream));
+    }
+    step(cudaEventRecord(e1, ctx->copy_stream));
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_events();
+        covt_batch_free(b);
+        CK(e);
+    }
+    const double t_enq = now_ms();
+    int32_t rc = decode_segments(ctx, b, container, tilejson, flags, starts, tile_offsets, &evs, out);
+    cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->debug) fprintf(stderr, "[covt] covt_decode_batch: enqueue uploads %.2f ms, decode_segments %.2f ms\n", t_enq - t_call0, now_ms() - t_enq);
+    if (rc == COVT_OK) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) (*out)->timing.h2d_ms = ms;
+    }
+    destroy_events();
     covt_batch_free(b);
     return rc;
 }
@@ -544,7 +801,8 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     CKR(cudaEventCreate(&ev0));
     CKR(cudaEventCreate(&ev1));
     R->counts[COVT_BUF_STREAM_ARENA] = arena;
-    CKR(cudaMallocAsync(&R->bufs[COVT_BUF_STREAM_ARENA], arena + 64, st));
+    CKR(dev_alloc_bytes(ctx, &R->arena, arena + 64));
+    R->bufs[COVT_BUF_STREAM_ARENA] = R->arena;
     CKR(dev_alloc(ctx, &d_tasks, n));
     CKR(dev_alloc(ctx, &d_counter, 16));
     for (uint32_t i = 0; i < n; i++)
@@ -574,7 +832,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
         if (!class_alg[c]) continue;
         prof.begin(op_class_name(c), class_alg[c]);
-        CKR(launch_decode_class(c, batch->d_blob, d_tasks, n, d_counter + c, ctx->sm_count, st));
+        CKR(launch_decode_class(c, batch->d_blob, d_tasks, n, d_counter + c, nullptr, ctx->sm_count, st));
         prof.end();
         launches++;
     }
@@ -628,7 +886,7 @@ int32_t covt_result_layers(covt_result* res, const covt_layer** layers)
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        CK(cudaMallocHost(reinterpret_cast<void**>(&res->h_layers), std::max<uint64_t>(res->n_layers, 1) * sizeof(covt_layer)));
+        CK(pinned_take(ctx, reinterpret_cast<void**>(&res->h_layers), std::max<uint64_t>(res->n_layers, 1) * sizeof(covt_layer)));
         cudaEventRecord(e0, ctx->stream);
         if (res->n_layers) CK(cudaMemcpyAsync(res->h_layers, res->d_layers, (uint64_t)res->n_layers * sizeof(covt_layer), cudaMemcpyDeviceToHost, ctx->stream));
         cudaEventRecord(e1, ctx->stream);
@@ -652,8 +910,8 @@ int32_t covt_result_tile_status(covt_result* res, const uint32_t** status, const
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        CK(cudaMallocHost(reinterpret_cast<void**>(&res->h_tile_status), ((uint64_t)res->n_tiles + 1) * sizeof(uint32_t)));
-        CK(cudaMallocHost(reinterpret_cast<void**>(&res->h_first_layer), ((uint64_t)res->n_tiles + 2) * sizeof(uint32_t)));
+        CK(pinned_take(ctx, reinterpret_cast<void**>(&res->h_tile_status), ((uint64_t)res->n_tiles + 1) * sizeof(uint32_t)));
+        CK(pinned_take(ctx, reinterpret_cast<void**>(&res->h_first_layer), ((uint64_t)res->n_tiles + 2) * sizeof(uint32_t)));
         cudaEventRecord(e0, ctx->stream);
         if (res->n_tiles && res->d_tile_status) {
             CK(cudaMemcpyAsync(res->h_tile_status, res->d_tile_status, (uint64_t)res->n_tiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -716,13 +974,13 @@ void covt_result_free(covt_result* res)
     if (!res) return;
     covt_ctx* ctx = res->ctx;
     cudaSetDevice(ctx->device);
-    for (int b = 0; b < COVT_NUM_BUFFERS; b++) dev_free(ctx, res->bufs[b]);
+    dev_free(ctx, res->arena);
     dev_free(ctx, res->d_layers);
     dev_free(ctx, res->d_tile_status);
     dev_free(ctx, res->d_first_layer);
-    if (res->h_layers) cudaFreeHost(res->h_layers);
-    if (res->h_tile_status) cudaFreeHost(res->h_tile_status);
-    if (res->h_first_layer) cudaFreeHost(res->h_first_layer);
+    pinned_give(ctx, res->h_layers, std::max<uint64_t>(res->n_layers, 1) * sizeof(covt_layer));
+    pinned_give(ctx, res->h_tile_status, ((uint64_t)res->n_tiles + 1) * sizeof(uint32_t));
+    pinned_give(ctx, res->h_first_layer, ((uint64_t)res->n_tiles + 2) * sizeof(uint32_t));
     delete res;
 }
 

@@ -28,6 +28,16 @@ struct DeviceTask {
     uint32_t pad;
 };
 
+// Device-side state of one batch decode. A batch is decoded in one or more SEGMENTS (contiguous tile ranges): with host
+// input the upload of segment i+1 overlaps the decode of segment i, and the host never waits to learn a segment's sizes.
+struct SegState {
+    uint64_t base[TILE_COLS];       // totals of the segments already decoded (col 0 = layers, 1.. = result-buffer elements)
+    uint64_t cap[TILE_COLS];        // capacity of the layer table / result buffers (exact for one segment, an estimate otherwise)
+    uint64_t seg_total[TILE_COLS];  // totals of the current segment (written by the column scan)
+    uint32_t overflow;              // sticky: an estimate was too small -> every later kernel is a no-op, the host decodes again
+    uint32_t seg_layers, seg_layer_base, pad;
+};
+
 // codec classes = one small kernel each (the instruction working set of a kernel must stay cache-resident)
 enum OpClass { CLASS_BYTE_RLE = 0, CLASS_RLE = 1, CLASS_VARINT32 = 2, CLASS_VARINT64 = 3, CLASS_PFOR = 4, NUM_OP_CLASSES = 5 };
 
@@ -54,24 +64,28 @@ constexpr int K1_SCAN_BLOCK = 1024;
 static const uint8_t kBufElemSize[COVT_NUM_BUFFERS] = {1, 8, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 1};
 
 // launchers (covt_kernels.cu); every launcher returns the kernel's launch error
-cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                  const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols,
                                  uint32_t* tile_status, cudaStream_t st);
 cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_t* block_sums, uint64_t* totals, cudaStream_t st);
-cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+cudaError_t launch_seg_begin(SegState* seg, uint32_t* work_counters /*[16]*/, uint64_t task_cap_layers, cudaStream_t st);
+cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end /*nullable*/, cudaStream_t st);
+cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                   const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, cudaStream_t st);
-// one codec class over a task table; work_counter must be zero
+                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, const SegState* seg,
+                                  cudaStream_t st);
+// one codec class over a task table; work_counter must be zero. seg != nullptr: the task count is seg->seg_layers * 8 and
+// n_tasks only bounds the grid
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
-                                int sm_count, cudaStream_t st);
+                                const SegState* seg, int sm_count, cudaStream_t st);
 const char* op_class_name(int op_class);
-cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers, ResultBuffers bufs, uint32_t flags,
-                                   uint32_t* work_counter, int sm_count, cudaStream_t st);
+cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
+                                   uint32_t* work_counter, const SegState* seg, int sm_count, cudaStream_t st);
 // k1a_aggregate + 3 segmented-scan kernels + k1b_decode; block_states needs ceil(n_chunks / K1_SCAN_BLOCK) entries
 cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks,
                                     ChunkState* states, ChunkState* block_states, cudaStream_t st);
 cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags,
-                            uint32_t* tile_status, uint64_t* totals /* [FINAL_TOTALS], see k_finalize */,
+                            uint32_t* tile_status, uint64_t* totals /* [FINAL_TOTALS], see k_finalize */, const SegState* seg,
                             cudaStream_t st);
 uint32_t host_resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags);
 

@@ -382,7 +382,7 @@ __device__ uint32_t walk_tile(const uint8_t* blob, uint64_t begin, uint64_t end,
 }
 
 // pass 1: layers per tile + slice sizes per result buffer (column-major: col * n_tiles + tile)
-__global__ void k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+__global__ void k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                               const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols,
                               uint32_t* tile_status)
 {
@@ -390,7 +390,7 @@ __global__ void k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets,
     if (t >= n_tiles) return;
     uint64_t acc[TILE_COLS];
     for (int i = 0; i < TILE_COLS; i++) acc[i] = 0;
-    const uint32_t st = walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, flags, t,
+    const uint32_t st = walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, flags, t + tile_base,
                                   [&](covt_layer& L) {
                                       uint64_t sz[COVT_NUM_BUFFERS];
                                       layer_slice_sizes(L, flags, sz);
@@ -402,19 +402,21 @@ __global__ void k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets,
 }
 
 // pass 2: write the covt_layer table with result offsets (tile_cols now holds exclusive prefixes)
-__global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+__global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                               ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer)
+                               ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, const SegState* seg)
 {
     const uint8_t slot_buf[COVT_NUM_SLOTS] = {COVT_BUF_S_IDS, COVT_BUF_S_GEOMETRY_TYPES, COVT_BUF_S_GEOMETRY_OFFSETS,
                                               COVT_BUF_S_PART_OFFSETS, COVT_BUF_S_RING_OFFSETS, COVT_BUF_S_VERTEX_OFFSETS,
                                               COVT_BUF_S_VERTEX_BUFFER, COVT_BUF_S_INDEX_BUFFER};
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
+    if (t >= n_tiles || seg->overflow) return;
+    // tile_cols holds exclusive prefixes inside this segment; seg->base = totals of the segments before it
     uint64_t run[TILE_COLS];
-    for (int i = 0; i < TILE_COLS; i++) run[i] = tile_cols[(uint64_t)i * n_tiles + t];
+    for (int i = 0; i < TILE_COLS; i++) run[i] = tile_cols[(uint64_t)i * n_tiles + t] + seg->base[i];
+    const uint64_t layer_base = seg->base[0];
     first_layer[t] = (uint32_t)run[0];
-    walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, flags, t, [&](covt_layer& L) {
+    walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, flags, t + tile_base, [&](covt_layer& L) {
         uint64_t sz[COVT_NUM_BUFFERS];
         layer_slice_sizes(L, flags, sz);
         for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
@@ -446,7 +448,7 @@ __global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets
                 t.op = r.op;
                 if (s == COVT_SLOT_VBUF && L.geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) t.num_values *= 2;
             }
-            tasks[run[0] * COVT_NUM_SLOTS + s] = t;
+            tasks[(run[0] - layer_base) * COVT_NUM_SLOTS + s] = t;
         }
         run[0] += 1;
     });
@@ -591,8 +593,11 @@ __device__ __forceinline__ StreamTask make_stream_task(const uint8_t* blob, cons
 
 template <int CLASS>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter)
+k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uint32_t* work_counter, const SegState* seg)
 {
+    // batch path: the task count of the current segment lives on the device (the host never learns it in the pipelined mode)
+    if (seg && seg->overflow) return;
+    const uint32_t n_tasks = seg ? seg->seg_layers * COVT_NUM_SLOTS : n_tasks_arg;
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     uint8_t* wsm = smem + warp * DEC_WARP_SMEM;
@@ -643,8 +648,11 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_
 // geometry assembly: one warp per layer (after every stream of the batch has been decoded)
 // =================================================================================================
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-k_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter)
+k_assemble_layers(covt_layer* all_layers, const DeviceTask* tasks, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter, const SegState* seg)
 {
+    if (seg->overflow) return;
+    covt_layer* layers = all_layers + seg->seg_layer_base;
+    const uint32_t n_layers = seg->seg_layers;
     __shared__ uint32_t s_asm[DEC_WARPS][ASM_SMEM_WORDS + 6];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     for (;;) {
@@ -932,8 +940,35 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
 // =================================================================================================
 // finalize: tile status = first layer error (unless the container walk already failed), totals
 // =================================================================================================
-__global__ void k_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags, uint32_t* tile_status, uint64_t* totals)
+// per segment, before its fill/decode kernels: publish the segment's layer range, check the capacities, clear the work counters
+__global__ void k_seg_begin(SegState* seg, uint32_t* work_counters, uint64_t task_cap_layers)
 {
+    const unsigned i = threadIdx.x;
+    if (i < 16) work_counters[i] = 0;
+    bool over = false;
+    if (i < TILE_COLS) over = seg->base[i] + seg->seg_total[i] > seg->cap[i];
+    if (i == 0 && seg->seg_total[0] > task_cap_layers) over = true;
+    over = __any_sync(FULL, over);
+    if (i == 0) {
+        if (over) seg->overflow = 1;
+        seg->seg_layer_base = (uint32_t)seg->base[0];
+        seg->seg_layers = (uint32_t)seg->seg_total[0];
+    }
+}
+// per segment, after its kernels: advance the running totals
+__global__ void k_seg_end(SegState* seg, uint32_t* first_layer_end)
+{
+    const unsigned i = threadIdx.x;
+    if (seg->overflow) return;
+    if (i < TILE_COLS) seg->base[i] += seg->seg_total[i];
+    __syncwarp();
+    if (i == 0 && first_layer_end) *first_layer_end = (uint32_t)seg->base[0];
+}
+
+__global__ void k_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags, uint32_t* tile_status, uint64_t* totals,
+                           const SegState* seg)
+{
+    if (seg->overflow) return;
     const uint8_t slot_es[COVT_NUM_SLOTS] = {8, 1, 4, 4, 4, 4, 4, 4};
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     // [0] vertices [1] payload bytes [2] output bytes [3..7] algorithmic bytes per codec class [8] assembler algorithmic bytes
@@ -977,12 +1012,12 @@ __global__ void k_finalize(const covt_layer* layers, const uint32_t* first_layer
 // =================================================================================================
 // launchers
 // =================================================================================================
-cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                  const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols,
                                  uint32_t* tile_status, cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    k0_scan_tiles<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, flags, tile_cols, tile_status);
+    k0_scan_tiles<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, tile_base, container, tj_fields, tj_layers, flags, tile_cols, tile_status);
     return cudaGetLastError();
 }
 
@@ -996,12 +1031,13 @@ cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_
     return cudaGetLastError();
 }
 
-cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                   const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, cudaStream_t st)
+                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, const SegState* seg,
+                                  cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    k0_fill_layers<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, flags, tile_cols, bufs, layers, tasks, first_layer);
+    k0_fill_layers<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, tile_base, container, tj_fields, tj_layers, flags, tile_cols, bufs, layers, tasks, first_layer, seg);
     return cudaGetLastError();
 }
 
@@ -1018,28 +1054,41 @@ const char* op_class_name(int c)
     return c >= 0 && c < NUM_OP_CLASSES ? names[c] : "?";
 }
 
+cudaError_t launch_seg_begin(SegState* seg, uint32_t* work_counters, uint64_t task_cap_layers, cudaStream_t st)
+{
+    k_seg_begin<<<1, 32, 0, st>>>(seg, work_counters, task_cap_layers);
+    return cudaGetLastError();
+}
+cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end, cudaStream_t st)
+{
+    k_seg_end<<<1, 32, 0, st>>>(seg, first_layer_end);
+    return cudaGetLastError();
+}
+
+// n_tasks: the exact task count (stream path, seg == nullptr) or an upper bound used for the grid size only (batch path)
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
-                                int sm_count, cudaStream_t st)
+                                const SegState* seg, int sm_count, cudaStream_t st)
 {
     if (!n_tasks) return cudaSuccess;
     const int smem = DEC_WARPS * DEC_WARP_SMEM;
     const int grid = grid_for(sm_count, 12, ((uint64_t)n_tasks + 255) / 256, DEC_WARPS);
     switch (op_class) {
-    case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
-    case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
-    case CLASS_VARINT32: k_decode_class<CLASS_VARINT32><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
-    case CLASS_VARINT64: k_decode_class<CLASS_VARINT64><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
-    case CLASS_PFOR: k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter); break;
+    case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
+    case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
+    case CLASS_VARINT32: k_decode_class<CLASS_VARINT32><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
+    case CLASS_VARINT64: k_decode_class<CLASS_VARINT64><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
+    case CLASS_PFOR: k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers, ResultBuffers bufs, uint32_t flags,
-                                   uint32_t* work_counter, int sm_count, cudaStream_t st)
+// n_layers_bound: upper bound of the segment's layer count (grid size only)
+cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
+                                   uint32_t* work_counter, const SegState* seg, int sm_count, cudaStream_t st)
 {
-    if (!n_layers) return cudaSuccess;
-    k_assemble_layers<<<grid_for(sm_count, 12, n_layers, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, tasks, n_layers, bufs, flags, work_counter);
+    if (!n_layers_bound) return cudaSuccess;
+    k_assemble_layers<<<grid_for(sm_count, 12, n_layers_bound, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, tasks, bufs, flags, work_counter, seg);
     return cudaGetLastError();
 }
 
@@ -1058,10 +1107,10 @@ cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* stream
 }
 
 cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags,
-                            uint32_t* tile_status, uint64_t* totals, cudaStream_t st)
+                            uint32_t* tile_status, uint64_t* totals, const SegState* seg, cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    k_finalize<<<(n_tiles + 127) / 128, 128, 0, st>>>(layers, first_layer, n_tiles, flags, tile_status, totals);
+    k_finalize<<<(n_tiles + 127) / 128, 128, 0, st>>>(layers, first_layer, n_tiles, flags, tile_status, totals, seg);
     return cudaGetLastError();
 }
 

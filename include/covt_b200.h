@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define COVT_ABI_VERSION 1
+#define COVT_ABI_VERSION 2
 
 /* ---- wire enums (ordinals identical to the Java enums) ------------------------------------ */
 
@@ -253,6 +253,8 @@ typedef struct covt_timing {
     uint64_t payload_bytes;   /* sum of byteLength of every decoded stream */
     uint64_t output_bytes;    /* bytes of all result buffers written */
     uint64_t vertices;        /* sum of covt_layer.n_vertices */
+    uint32_t segments;        /* upload/decode segments the call was pipelined over (1 = not pipelined) */
+    uint32_t capacity_retries;/* 1 if an extrapolated result capacity was too small and the batch was decoded again with exact sizes */
 } covt_timing;
 
 /* per-kernel times, available when COVT_FLAG_PROFILE_KERNELS was set */
@@ -274,9 +276,14 @@ int32_t covt_create(int32_t device, covt_ctx** out);
 void    covt_destroy(covt_ctx* ctx);
 /* Copies the last error message of this context (or of a failed covt_create when ctx == NULL). */
 int32_t covt_last_error(covt_ctx* ctx, char* buf, size_t buf_len);
+/* The context parks the large device blocks of finished decodes (input blob, result arena, layer table) for the next call;
+ * covt_trim returns them to the driver. */
+int32_t covt_trim(covt_ctx* ctx);
 
 /* ---- batch path: replaces CovtParser.decodeCovt (CovtParser.java:53), batched over tiles ---- */
-/* blob holds n_tiles tiles back to back; tile i occupies [tile_offsets[i], tile_offsets[i+1]). Host memory. */
+/* blob holds n_tiles tiles back to back; tile i occupies [tile_offsets[i], tile_offsets[i+1]). Host memory (pinned or
+ * covt_host_register-ed for full PCIe rate). Large batches go up in ~48 MB segments on a copy stream while earlier segments are
+ * being decoded; the result is one set of buffers whatever the segmentation. */
 int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles,
                           uint32_t container, const covt_tilejson* tilejson, uint32_t flags, covt_result** out);
 /* The same in two steps so that host->device transfer is timed apart from device-resident decode. */

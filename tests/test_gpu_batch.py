@@ -216,3 +216,36 @@ def test_empty_batch_and_split_api(covt, oracle, decoder, fixtures):
     r1.free()
     r2.free()
     batch.free()
+
+
+def test_pipelined_segments_equal_one_shot(covt, oracle, gen, fixtures, monkeypatch):
+    """covt_decode_batch with host input uploads and decodes in segments (upload of segment i+1 overlaps the decode of segment i;
+    result capacities are extrapolated from segment 0). Whatever the segmentation, the result is bit-identical to the oracle's."""
+    abi = covt.abi
+    monkeypatch.setenv("COVT_SEG_BYTES", str(1 << 20))
+    monkeypatch.setenv("COVT_MAX_SEGMENTS", "64")
+    dec = covt.Decoder(0)
+    try:
+        blob, offs, truth = gen.tiles(31, 4000, gen.default_params())
+        res = dec.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT)
+        t = res.timing()
+        assert t["segments"] >= 4 and t["capacity_retries"] == 0
+        ref = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT)
+        st, first = res.tile_status()
+        assert np.array_equal(first, ref.first_layer) and np.all(st == 0)
+        util.compare_results(abi, res, ref)
+        assert int(res.layers["n_vertices"].sum()) == truth["vertices"] and t["vertices"] == truth["vertices"]
+        res.free()
+        # a batch whose first segment is NOT representative (small tiles first, the big fixture tiles last): the extrapolated
+        # capacities overflow on the device, and the call transparently decodes again with exact sizes
+        small, soffs, _ = gen.tiles(5, 1500, gen.default_params(mean_features=4))
+        big = [b for n, b in fixtures if n.startswith(("omt/5_", "omt/6_", "omt/7_"))]
+        blob2, offs2 = util.concat_tiles([bytes(small[int(soffs[i]):int(soffs[i + 1])]) for i in range(1500)] + big)
+        flags = abi.FLAG_DEFAULT | abi.FLAG_ID_DVZZ_IS_RLE
+        res2 = dec.decode_batch(blob2, offs2, abi.CONTAINER_GEN2B, flags)
+        assert res2.timing()["capacity_retries"] == 1
+        ref2 = oracle.decode_batch(blob2, offs2, abi.CONTAINER_GEN2B, flags)
+        util.compare_results(abi, res2, ref2)
+        res2.free()
+    finally:
+        dec.close()
