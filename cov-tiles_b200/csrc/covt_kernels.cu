@@ -522,6 +522,9 @@ __global__ void scan_apply(uint64_t* cols, uint32_t n, const uint64_t* block_sum
 // =================================================================================================
 constexpr int DEC_WARPS = 4;
 constexpr int DEC_WARP_SMEM = WARP_SMEM_BYTES;
+// the FastPFOR kernel stages whole streams: payload window + value stage per warp
+constexpr int PFOR_WARP_SMEM = (PFOR_SMEM_WORDS + 4 + LEAN_STAGE_WORDS) * 4;
+template <int CLASS> __host__ __device__ constexpr int class_warp_smem() { return CLASS == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM; }
 
 __device__ __forceinline__ uint32_t warp_next_work(uint32_t* counter)
 {
@@ -564,7 +567,8 @@ __device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, Strea
         else warp_varint64_stream<true>(t, reinterpret_cast<uint64_t*>(wsm), o);
     } else {
         if (t.op == COVT_OP_PFOR_ZZ_DELTA_XY && (t.num_values & 1u)) { o.status = COVT_ERR_COUNT_MISMATCH; return; }
-        warp_pfor_stream(t, stage, o, post_kind_of_op(t.op));
+        if (t.byte_length / 4u <= PFOR_SMEM_WORDS) warp_pfor_stream_smem(t, stage, stage + PFOR_SMEM_WORDS + 4, o, post_kind_of_op(t.op));
+        else warp_pfor_stream(t, stage, o, post_kind_of_op(t.op));  // larger than the window: read the page through global memory
     }
 }
 
@@ -600,7 +604,7 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
     const uint32_t n_tasks = seg ? seg->seg_layers * COVT_NUM_SLOTS : n_tasks_arg;
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t* wsm = smem + warp * DEC_WARP_SMEM;
+    uint8_t* wsm = smem + warp * class_warp_smem<CLASS>();
     // A work group = 256 consecutive task slots = 32 layers x 8 slots in the batch path. Lane L looks at slot s of
     // "its" layer, so that the 32 lanes hold 32 streams of the SAME kind (same slot) at a time.
     const uint32_t n_groups = (n_tasks + 255u) / 256u;
@@ -1070,8 +1074,8 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
                                 const SegState* seg, int sm_count, cudaStream_t st)
 {
     if (!n_tasks) return cudaSuccess;
-    const int smem = DEC_WARPS * DEC_WARP_SMEM;
-    const int grid = grid_for(sm_count, 12, ((uint64_t)n_tasks + 255) / 256, DEC_WARPS);
+    const int smem = DEC_WARPS * (op_class == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM);
+    const int grid = grid_for(sm_count, op_class == CLASS_PFOR ? 5 : 12, ((uint64_t)n_tasks + 255) / 256, DEC_WARPS);
     switch (op_class) {
     case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
     case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;

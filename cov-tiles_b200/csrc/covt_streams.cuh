@@ -605,4 +605,159 @@ finish:
     out.status = status;
 }
 
+// =================================================================================================
+// The same codec for streams that fit a warp's shared-memory window (PFOR_SMEM_WORDS words; every FastPFOR stream of a
+// typical tile does): the payload is staged ONCE as native-endian words with coalesced loads, so that the page header, the
+// byte container, the packed blocks and the exception arrays — which the format scatters over the page — are all read from
+// shared memory instead of through dependent unaligned global loads, and zigzag/delta/Morton run striped (covt_varint.cuh).
+// =================================================================================================
+constexpr uint32_t PFOR_SMEM_WORDS = 2048;  // 8 KiB of payload per warp
+
+__device__ __forceinline__ uint32_t sm_unpack(const uint32_t* sw, uint32_t w0, uint32_t q, uint32_t k)
+{
+    const uint32_t bo = (q & 31u) * k;
+    const uint32_t wi = w0 + (q >> 5) * k + (bo >> 5);
+    const uint32_t v = __funnelshift_r(sw[wi], sw[wi + 1], bo & 31u);
+    return k >= 32u ? v : (v & ((1u << k) - 1u));
+}
+
+// sw: PFOR_SMEM_WORDS + 4 words, stage: LEAN_STAGE_WORDS words (both warp-private)
+__device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t* sw, uint32_t* stage, StreamOutcome& out, const int post)
+{
+    const unsigned lane = lane_id();
+    const uint8_t* base = t.src;
+    const uint32_t n_words = t.byte_length / 4u;  // (int)Math.ceil(byteLength / 4): integer division, DecodingUtils.java:324
+    const uint32_t n = t.num_values;
+    uint32_t produced = 0;
+    int32_t cx = 0, cy = 0;
+    uint32_t status = COVT_OK;
+    out.consumed = t.byte_length;
+    // ---- stage the payload: word j of the stream, byte-swapped to native order ----
+    for (uint32_t j = lane; j < n_words; j += 32) sw[j] = ld_be_word(base, j);
+    if (lane < 4) sw[n_words + lane] = 0;
+    __syncwarp();
+#define PFOR_FAIL(code) { status = (code); goto finish; }
+    if (n_words == 0) {
+        // Composition.uncompress returns at once: the output stays all zeros, the post passes still run
+        for (uint32_t i = lane; i < 512; i += 32) stage[i] = 0;
+        __syncwarp();
+        for (uint32_t b0 = 0; b0 < n; b0 += 512) {
+            lean_rows_dispatch(post, false, stage, min(512u, n - b0), t.dst, b0, cx, cy, t.num_bits, t.no_shift != 0);
+        }
+        out.status = COVT_OK;
+        return;
+    }
+    {
+        const uint32_t mynvalue = sw[0];
+        uint32_t inpos = 1;
+        if (mynvalue > n || (mynvalue & 255u)) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);
+        uint32_t outpos = 0;
+        while (outpos < mynvalue) {
+            const uint32_t thissize = min(65536u, mynvalue - outpos);
+            // ---- page header (FastPFOR.decodePage) ----
+            const uint32_t initpos = inpos;
+            if (initpos >= n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+            const uint32_t wheremeta = sw[initpos];
+            uint64_t inexcept = (uint64_t)initpos + wheremeta;
+            if (inexcept >= n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+            const uint32_t bytesize = sw[(uint32_t)inexcept];
+            inexcept++;
+            const uint64_t bc_words = ((uint64_t)bytesize + 3u) / 4u;
+            if (inexcept + bc_words > n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+            const uint32_t bc_word0 = (uint32_t)inexcept;
+            inexcept += bc_words;
+            if (inexcept >= n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+            const uint32_t bitmap = sw[(uint32_t)inexcept];
+            inexcept++;
+            // exception array of width k lives in lane k-1: first word, size, cursor (cursors reset per page)
+            uint32_t exc_base = 0, exc_size = 0, exc_ptr = 0;
+            for (uint32_t rest = bitmap & ~1u; rest; rest &= rest - 1u) {
+                const uint32_t k = (uint32_t)__ffs(rest);  // bit k-1 set
+                if (inexcept >= n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                const uint32_t size = sw[(uint32_t)inexcept];
+                inexcept++;
+                const uint64_t need = ((uint64_t)size * k + 31u) / 32u;
+                if (inexcept + need > n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                if (lane == k - 1) { exc_base = (uint32_t)inexcept; exc_size = size; }
+                inexcept += need;
+            }
+            uint32_t tmpin = initpos + 1;
+            uint32_t bcpos = 0;
+            // byte i of the byte container: bytes are little-endian inside each (big-endian serialised) word
+#define BC_BYTE(i) ((sw[bc_word0 + ((i) >> 2)] >> (8u * ((i) & 3u))) & 0xffu)
+            for (uint32_t run = 0, run_end = thissize / 256u; run < run_end; run++) {
+                if (bcpos + 2 > bytesize) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                const uint32_t b = BC_BYTE(bcpos);
+                const uint32_t cexcept = BC_BYTE(bcpos + 1);
+                bcpos += 2;
+                if (b > 32u) PFOR_FAIL(COVT_ERR_BAD_METADATA);
+                if ((uint64_t)tmpin + 8ull * b > (uint64_t)initpos + wheremeta) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                // ---- unpack 256 values of b bits: value (g, lane) ----
+                {
+                    const uint32_t bo = lane * b, wi = tmpin + (bo >> 5), sh = bo & 31u;
+                    const uint32_t mask = b >= 32u ? 0xffffffffu : ((1u << b) - 1u);
+#pragma unroll
+                    for (int g = 0; g < 8; g++) stage[g * 32 + lane] = __funnelshift_r(sw[wi + g * b], sw[wi + g * b + 1], sh) & mask;
+                }
+                tmpin += 8u * b;
+                if (cexcept > 0) {
+                    if (bcpos + 1 + cexcept > bytesize) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                    const uint32_t maxbits = BC_BYTE(bcpos);
+                    bcpos++;
+                    const int index = (int)maxbits - (int)b;
+                    __syncwarp();
+                    if (index == 1) {
+                        for (uint32_t e = lane; e < cexcept; e += 32) stage[BC_BYTE(bcpos + e)] |= 1u << (b & 31u);
+                    } else {
+                        if (index < 2 || index > 32 || !(bitmap & (1u << (index - 1)))) PFOR_FAIL(COVT_ERR_BAD_METADATA);
+                        const uint32_t ebase = __shfl_sync(FULL, exc_base, index - 1);
+                        const uint32_t esize = __shfl_sync(FULL, exc_size, index - 1);
+                        const uint32_t eptr = __shfl_sync(FULL, exc_ptr, index - 1);
+                        if (eptr + cexcept > esize) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                        for (uint32_t e = lane; e < cexcept; e += 32)
+                            stage[BC_BYTE(bcpos + e)] |= sm_unpack(sw, ebase, eptr + e, (uint32_t)index) << (b & 31u);
+                        if (lane == (unsigned)(index - 1)) exc_ptr += cexcept;
+                    }
+                    bcpos += cexcept;
+                }
+                __syncwarp();
+                lean_rows_dispatch(post, false, stage, 256, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
+                __syncwarp();
+                produced += 256;
+            }
+#undef BC_BYTE
+            outpos += thissize;
+            inpos = (uint32_t)inexcept;
+        }
+        // ---- VariableByte tail over ALL remaining words (VariableByte.uncompress): MSB SET ends a value, so flipping
+        // the MSBs turns it into LEB128 for the chunk decoder (up to 5 bytes per value; the carry logic covers 4 + 1)
+        uint32_t carry_halo = 0, ov = 0;
+        for (uint32_t wbase = inpos; wbase < n_words; wbase += 128) {
+            const uint32_t first_w = wbase + lane * 4u;
+            uint4 win;
+            win.x = first_w + 0 < n_words ? sw[first_w + 0] ^ 0x80808080u : 0u;
+            win.y = first_w + 1 < n_words ? sw[first_w + 1] ^ 0x80808080u : 0u;
+            win.z = first_w + 2 < n_words ? sw[first_w + 2] ^ 0x80808080u : 0u;
+            win.w = first_w + 3 < n_words ? sw[first_w + 3] ^ 0x80808080u : 0u;
+            const uint32_t valid_words = min(128u, n_words - wbase);
+            const uint32_t tail_f = 512u - 4u * valid_words;  // zeroed bytes decode to fake 1-byte zeros behind the real values
+            uint32_t w[4], acc, mul;
+            LeanLane L = lean_front(win, false, 0, 16, carry_halo, w, acc, mul, ov);
+            L.excl = warp_exclusive_scan(L.cnt, L.total);
+            const uint32_t ctotal = L.total - tail_f;
+            const uint32_t remaining = n - produced;
+            if (ctotal > remaining) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);  // Java: ArrayIndexOutOfBounds
+            lean_stage_lane(w, L.cm, acc, mul, stage + L.excl, ov);
+            __syncwarp();
+            lean_rows_dispatch(post, false, stage, ctotal, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
+            __syncwarp();
+            produced += ctotal;
+        }
+        if (produced != n) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);
+    }
+finish:
+#undef PFOR_FAIL
+    out.status = status;
+}
+
 }  // namespace covt
