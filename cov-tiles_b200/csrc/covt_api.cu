@@ -42,6 +42,11 @@ struct covt_ctx {
     uint64_t seg_bytes = 64ull << 20;    // minimum upload/decode segment size of covt_decode_batch (env COVT_SEG_BYTES overrides: tests)
     uint32_t max_segments = 8;           // env COVT_MAX_SEGMENTS overrides
     bool debug = false;                  // env COVT_DEBUG: host-side phase times on stderr
+    bool serial_classes = true;          // env COVT_CONCURRENT=1 runs the five codec kernels side by side on their own streams
+                                         // (measured SLOWER on B200, 6.61 vs 5.75 ms per 262k tiles: each kernel alone already
+                                         // fills the SMs' register file, so the grids only get in each other's way)
+    cudaStream_t class_stream[covt::NUM_OP_CLASSES] = {};  // the codec kernels of a segment run side by side
+    cudaEvent_t ev_fork = nullptr, ev_join[covt::NUM_OP_CLASSES] = {};
     std::vector<std::pair<void*, uint64_t>> dev_cache;   // parked device blocks (see dev_alloc_bytes)
     std::unordered_map<void*, uint64_t> dev_live;         // cache-eligible blocks in use
     std::vector<std::pair<void*, size_t>> pinned_cache;  // page-locked host blocks handed to results and taken back on free
@@ -263,6 +268,12 @@ int32_t covt_create(int32_t device, covt_ctx** out)
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* sb = getenv("COVT_SEG_BYTES")) { const long long v = atoll(sb); if (v > 0) ctx->seg_bytes = (uint64_t)v; }
     ctx->debug = getenv("COVT_DEBUG") != nullptr;
+    ctx->serial_classes = getenv("COVT_CONCURRENT") == nullptr;
+    for (int c = 0; c < NUM_OP_CLASSES; c++) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->class_stream[c], cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_join[c], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if (const char* ms = getenv("COVT_MAX_SEGMENTS")) { const long long v = atoll(ms); if (v > 0) ctx->max_segments = (uint32_t)std::min<long long>(v, 4096); }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
@@ -289,6 +300,11 @@ void covt_destroy(covt_ctx* ctx)
     if (ctx->h_seg) cudaFreeHost(ctx->h_seg);
     for (auto& b : ctx->pinned_cache) cudaFreeHost(b.first);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int c = 0; c < NUM_OP_CLASSES; c++) {
+        if (ctx->class_stream[c]) cudaStreamDestroy(ctx->class_stream[c]);
+        if (ctx->ev_join[c]) cudaEventDestroy(ctx->ev_join[c]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -506,10 +522,25 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         prof.end();
         // ---- every stream of every layer: one kernel per codec class ----
         const uint32_t n_tasks_bound = (uint32_t)std::min<uint64_t>(task_cap_layers * COVT_NUM_SLOTS, 0xffffff00ull);
-        for (int c = 0; c < NUM_OP_CLASSES; c++) {
-            prof.begin(op_class_name(c), 0);
-            CKR(launch_decode_class(c, batch->d_blob, d_tasks, n_tasks_bound, d_counter + c, d_seg, ctx->sm_count, st));
-            prof.end();
+        if (prof.on || ctx->serial_classes) {
+            for (int c = 0; c < NUM_OP_CLASSES; c++) {
+                prof.begin(op_class_name(c), 0);
+                CKR(launch_decode_class(c, batch->d_blob, d_tasks, n_tasks_bound, d_counter + c, d_seg, ctx->sm_count, 0, st));
+                prof.end();
+            }
+        } else {
+            // experiment (off by default, see covt_ctx::serial_classes): the five codec kernels are independent, run them
+            // side by side
+            static const int order[NUM_OP_CLASSES] = {CLASS_VARINT32, CLASS_PFOR, CLASS_RLE, CLASS_VARINT64, CLASS_BYTE_RLE};
+            static const int share[NUM_OP_CLASSES] = {/*BYTE_RLE*/ 2, /*RLE*/ 3, /*VARINT32*/ 5, /*VARINT64*/ 1, /*PFOR*/ 2};
+            CKR(cudaEventRecord(ctx->ev_fork, st));
+            for (int i = 0; i < NUM_OP_CLASSES; i++) {
+                const int c = order[i];
+                CKR(cudaStreamWaitEvent(ctx->class_stream[c], ctx->ev_fork, 0));
+                CKR(launch_decode_class(c, batch->d_blob, d_tasks, n_tasks_bound, d_counter + c, d_seg, ctx->sm_count, share[c], ctx->class_stream[c]));
+                CKR(cudaEventRecord(ctx->ev_join[c], ctx->class_stream[c]));
+                CKR(cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
+            }
         }
         // ---- geometry assembly ----
         prof.begin("k_assemble_layers", 0);
@@ -832,7 +863,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
         if (!class_alg[c]) continue;
         prof.begin(op_class_name(c), class_alg[c]);
-        CKR(launch_decode_class(c, batch->d_blob, d_tasks, n, d_counter + c, nullptr, ctx->sm_count, st));
+        CKR(launch_decode_class(c, batch->d_blob, d_tasks, n, d_counter + c, nullptr, ctx->sm_count, 0, st));
         prof.end();
         launches++;
     }

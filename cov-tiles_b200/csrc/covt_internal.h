@@ -76,8 +76,9 @@ cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offs
                                   cudaStream_t st);
 // one codec class over a task table; work_counter must be zero. seg != nullptr: the task count is seg->seg_layers * 8 and
 // n_tasks only bounds the grid
+// blocks_per_sm: 0 = fill the GPU with this kernel alone; > 0 = its share when the class kernels run concurrently
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
-                                const SegState* seg, int sm_count, cudaStream_t st);
+                                const SegState* seg, int sm_count, int blocks_per_sm, cudaStream_t st);
 const char* op_class_name(int op_class);
 cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
                                    uint32_t* work_counter, const SegState* seg, int sm_count, cudaStream_t st);

@@ -1071,11 +1071,13 @@ cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end, cudaStream_
 
 // n_tasks: the exact task count (stream path, seg == nullptr) or an upper bound used for the grid size only (batch path)
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
-                                const SegState* seg, int sm_count, cudaStream_t st)
+                                const SegState* seg, int sm_count, int blocks_per_sm, cudaStream_t st)
 {
     if (!n_tasks) return cudaSuccess;
-    const int smem = DEC_WARPS * (op_class == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM);
-    const int grid = grid_for(sm_count, op_class == CLASS_PFOR ? 5 : 12, ((uint64_t)n_tasks + 255) / 256, DEC_WARPS);
+    // Byte-RLE and RLE never touch the warp stage
+    const int smem = (op_class == CLASS_BYTE_RLE || op_class == CLASS_RLE) ? 0 : DEC_WARPS * (op_class == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM);
+    const int per_sm = blocks_per_sm > 0 ? blocks_per_sm : (op_class == CLASS_PFOR ? 5 : 12);
+    const int grid = grid_for(sm_count, per_sm, ((uint64_t)n_tasks + 255) / 256, DEC_WARPS);
     switch (op_class) {
     case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
     case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
