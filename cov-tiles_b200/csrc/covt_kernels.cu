@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_apply(ChunkState* state
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks, const ChunkState* states)
 {
-    __shared__ uint32_t s_stage[K1_WARPS][LEAN_STAGE_WORDS];
+    __shared__ __align__(16) uint32_t s_stage[K1_WARPS][LEAN_STAGE_WORDS];
     const unsigned lane = lane_id();
     const uint32_t g = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
     if (g >= n_chunks) return;
@@ -926,7 +926,10 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
     uint32_t w[4], acc, mul, ov = 0;
     LeanLane L = lean_front(k.win, k.partial, k.lo16, k.hi16, k.halo0, w, acc, mul, ov);
     L.excl = warp_exclusive_scan(L.cnt, L.total);
-    lean_stage_lane(w, L.cm, acc, mul, stage + LEAN_FRONT + L.excl - k.head_f, ov);
+    const uint32_t s4 = P.count & 3u;  // see lean_rows4: the chunk's values are staged at A[s4 + i]
+    uint32_t* A = stage + LEAN_FRONT;
+    if (lane < s4) A[lane] = 0;
+    lean_stage_lane(w, L.cm, acc, mul, A + s4 + L.excl - k.head_f, ov);
     __syncwarp();
     const uint32_t n_here = L.total - k.head_f - k.tail_f;
     // bytes the reference reader consumes = position right after the terminator of value #num_values
@@ -938,7 +941,7 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
     if (ci == S.n_chunks - 1 && lane == 0 && P.count + n_here < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
     const uint32_t room = P.count < S.num_values ? S.num_values - P.count : 0u;
     int32_t cx = P.a, cy = P.b;
-    lean_rows_dispatch(S.post, false, stage + LEAN_FRONT, min(n_here, room), S.dst, P.count, cx, cy, S.num_bits, S.no_shift != 0);
+    lean_rows4_dispatch(S.post, false, A, s4, min(n_here, room), S.dst, P.count, cx, cy, S.num_bits, S.no_shift != 0);
 }
 
 // =================================================================================================

@@ -80,10 +80,13 @@ __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t*
         carry_halo = halo_in;
         ov |= lane_ov;
         const uint32_t tail_f = WARP_CHUNK_BYTES - end_in_chunk;
-        lean_stage_lane(w, L.cm, acc, mul, stage + LEAN_FRONT + L.excl - head_f, ov);
+        const uint32_t s4 = produced & 3u;  // see lean_rows4: the chunk's values are staged at A[s4 + i]
+        uint32_t* A = stage + LEAN_FRONT;
+        if (lane < s4) A[lane] = 0;
+        lean_stage_lane(w, L.cm, acc, mul, A + s4 + L.excl - head_f, ov);
         __syncwarp();
         const uint32_t n = min(L.total - head_f - tail_f, remaining);
-        lean_rows_dispatch(post, widen, stage + LEAN_FRONT, n, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
+        lean_rows4_dispatch(post, widen, A, s4, n, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
         __syncwarp();
         produced += n;
     }
@@ -642,7 +645,7 @@ __device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t
         for (uint32_t i = lane; i < 512; i += 32) stage[i] = 0;
         __syncwarp();
         for (uint32_t b0 = 0; b0 < n; b0 += 512) {
-            lean_rows_dispatch(post, false, stage, min(512u, n - b0), t.dst, b0, cx, cy, t.num_bits, t.no_shift != 0);
+            lean_rows4_dispatch(post, false, stage, 0, min(512u, n - b0), t.dst, b0, cx, cy, t.num_bits, t.no_shift != 0);
         }
         out.status = COVT_OK;
         return;
@@ -721,7 +724,7 @@ __device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t
                     bcpos += cexcept;
                 }
                 __syncwarp();
-                lean_rows_dispatch(post, false, stage, 256, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
+                lean_rows4_dispatch(post, false, stage, 0, 256, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
                 __syncwarp();
                 produced += 256;
             }
@@ -747,9 +750,11 @@ __device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t
             const uint32_t ctotal = L.total - tail_f;
             const uint32_t remaining = n - produced;
             if (ctotal > remaining) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);  // Java: ArrayIndexOutOfBounds
-            lean_stage_lane(w, L.cm, acc, mul, stage + L.excl, ov);
+            const uint32_t s4 = produced & 3u;
+            if (lane < s4) stage[lane] = 0;
+            lean_stage_lane(w, L.cm, acc, mul, stage + s4 + L.excl, ov);
             __syncwarp();
-            lean_rows_dispatch(post, false, stage, ctotal, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
+            lean_rows4_dispatch(post, false, stage, s4, ctotal, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
             __syncwarp();
             produced += ctotal;
         }

@@ -12,8 +12,8 @@
 //     running shared-memory pointer (linear stage, no index arithmetic);
 //   * bytes outside the stream are zeroed: they decode to fake 1-byte zeros that add nothing to the sums; leading fakes land
 //     in a front slack of the stage, trailing fakes behind the real values;
-//   * zigzag + delta run on the STRIPED layout (value i in lane i & 31): a stride-2 (x,y) or stride-1 warp scan per row of 32
-//     values, followed directly by the coalesced global store — the values cross shared memory once.
+//   * zigzag + delta run on four consecutive values per lane (one LDS.128, one warp scan per 128 values, one STG.128): the
+//     values cross shared memory once and leave with 16-byte coalesced stores (lean_rows4).
 #pragma once
 #include "covt_device.cuh"
 
@@ -61,17 +61,22 @@ __device__ __forceinline__ uint32_t lean_halo(uint32_t last_word, uint32_t& carr
 // The byte loop, staging flavour: stores every value whose terminator lies in this lane at *sp++ (raw, not zigzag-decoded).
 __device__ __forceinline__ void lean_stage_lane(const uint32_t w[4], uint32_t cm, uint32_t acc, uint32_t mul, uint32_t* sp, uint32_t& ov)
 {
+    uint32_t so = (uint32_t)__cvta_generic_to_shared(sp);  // 32-bit shared address: one predicated add per terminator
 #pragma unroll
     for (int j = 0; j < 16; j++) {
         const uint32_t p = (w[j >> 2] >> (8 * (j & 3))) & 0x7fu;
-        const uint32_t v = p * mul + acc;
-        const bool term = (cm & cont_bit_of_byte(j)) == 0u;
-        if (term) *sp = v;
-        sp += term ? 1 : 0;
-        acc = term ? 0u : v;
-        mul = term ? 1u : mul << 7;
+        acc = p * mul + acc;
         ov |= mul;
+        if ((cm & cont_bit_of_byte(j)) == 0u) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(so), "r"(acc) : "memory");
+            so += 4;
+            acc = 0;
+            mul = 1;
+        } else {
+            mul <<= 7;
+        }
     }
+    ov |= mul;
 }
 
 // The byte loop, aggregate flavour: two accumulators that swap at every terminator, so that no parity bookkeeping and no
@@ -129,86 +134,105 @@ __device__ __forceinline__ uint32_t lean_nth_terminator(uint32_t cm, uint32_t m)
     return 0;
 }
 
-// ---- striped zigzag / delta / store ------------------------------------------------------------------------------
-// stage[i], i < n: raw values of one chunk in stream order. `index0` = stream index of stage[0]; (cx, cy) = running sums of
-// the values before stage[0] at even / odd STREAM positions (cy unused for single-accumulator posts). Updated on return.
+// ---- zigzag / delta / store, four values per lane ---------------------------------------------------------------
+// A: 16-byte aligned shared array. A[s4 + i], i < n, are the raw values of one chunk in stream order, where
+// s4 = index0 & 3 (index0 = stream index of the chunk's first value) and A[0 .. s4) are zero: A[j] then belongs to stream index
+// base + j with base = index0 - s4 a multiple of 4, so that a lane's four consecutive values are (x, y, x, y), its 16 output
+// bytes are 16-byte aligned in dst, and one LDS.128 / STG.128 moves them. One warp scan per 128 values.
+// (cx, cy) = running sums of the values before the chunk at even / odd stream positions; updated on return.
 template <int POST, bool WIDEN>
-__device__ __forceinline__ void lean_rows(const uint32_t* stage, uint32_t n, void* dst, uint64_t index0, int32_t& cx, int32_t& cy,
-                                          uint32_t num_bits, bool no_shift)
+__device__ __forceinline__ void lean_rows4(const uint32_t* A, uint32_t s4, uint32_t n, void* dst, uint64_t index0, int32_t& cx, int32_t& cy,
+                                           uint32_t num_bits, bool no_shift)
 {
     const unsigned lane = lane_id();
-    if (POST == POST_PLAIN || POST == POST_ZZ) {
-        for (uint32_t r = 0; r < n; r += 32) {
-            const uint32_t i = r + lane;
-            if (i < n) {
-                const uint32_t raw = stage[i];
-                const int32_t v = POST == POST_ZZ ? zigzag_decode32(raw) : (int32_t)raw;
-                if (WIDEN) reinterpret_cast<int64_t*>(dst)[index0 + i] = (int64_t)v;
-                else reinterpret_cast<int32_t*>(dst)[index0 + i] = v;
-            }
+    const uint64_t base = index0 - s4;
+    const uint32_t end = s4 + n;
+    for (uint32_t r = 0; r < end; r += 128) {
+        const uint32_t j = r + 4u * lane;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (j < end) raw = *reinterpret_cast<const uint4*>(A + j);  // entries past `end` inside the vector are masked below
+        int32_t d0, d1, d2, d3;
+        if (POST == POST_PLAIN || POST == POST_DELTA_MORTON) { d0 = (int32_t)raw.x; d1 = (int32_t)raw.y; d2 = (int32_t)raw.z; d3 = (int32_t)raw.w; }
+        else { d0 = zigzag_decode32(raw.x); d1 = zigzag_decode32(raw.y); d2 = zigzag_decode32(raw.z); d3 = zigzag_decode32(raw.w); }
+        // validity of the four elements: [s4, end)
+        const bool v0 = j + 0 >= s4 && j + 0 < end, v1 = j + 1 >= s4 && j + 1 < end, v2 = j + 2 >= s4 && j + 2 < end, v3 = j + 3 >= s4 && j + 3 < end;
+        if (POST == POST_ZZ_DELTA_XY || POST == POST_ZZ_DELTA || POST == POST_DELTA_MORTON) {
+            if (!v0) d0 = 0;
+            if (!v1) d1 = 0;
+            if (!v2) d2 = 0;
+            if (!v3) d3 = 0;
         }
-        return;
-    }
-    if (POST == POST_ZZ_DELTA_XY) {
-        // lane parity == chunk-local index parity (rows are 32 wide); stream parity adds index0
-        const bool odd_first = (index0 & 1ull) != 0ull;
-        const bool is_y = ((lane & 1u) != 0u) != odd_first;
-        int32_t carry = is_y ? cy : cx;
-        for (uint32_t r = 0; r < n; r += 32) {
-            const uint32_t i = r + lane;
-            int32_t v = i < n ? zigzag_decode32(stage[i]) : 0;
+        int32_t o0, o1, o2, o3;
+        if (POST == POST_ZZ_DELTA_XY) {
+            int32_t sx = d0 + d2, sy = d1 + d3;
+            int32_t ix = sx, iy = sy;
 #pragma unroll
-            for (int d = 2; d < 32; d <<= 1) {
-                const int32_t t = __shfl_up_sync(FULL, v, d);
-                if (lane >= (unsigned)d) v += t;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int32_t tx = __shfl_up_sync(FULL, ix, d), ty = __shfl_up_sync(FULL, iy, d);
+                if (lane >= (unsigned)d) { ix += tx; iy += ty; }
             }
-            v += carry;
-            if (i < n) reinterpret_cast<int32_t*>(dst)[index0 + i] = v;
-            carry = __shfl_sync(FULL, v, 30 + (lane & 1u));
-        }
-        const int32_t c_even_lane = __shfl_sync(FULL, carry, 0), c_odd_lane = __shfl_sync(FULL, carry, 1);
-        cx = odd_first ? c_odd_lane : c_even_lane;
-        cy = odd_first ? c_even_lane : c_odd_lane;
-        return;
-    }
-    // single accumulator: POST_ZZ_DELTA, POST_DELTA_MORTON
-    int32_t carry = cx;
-    for (uint32_t r = 0; r < n; r += 32) {
-        const uint32_t i = r + lane;
-        const uint32_t raw = i < n ? stage[i] : 0u;
-        int32_t v = POST == POST_ZZ_DELTA ? zigzag_decode32(raw) : (int32_t)raw;
+            o0 = cx + (ix - sx) + d0;
+            o1 = cy + (iy - sy) + d1;
+            o2 = o0 + d2;
+            o3 = o1 + d3;
+            cx += __shfl_sync(FULL, ix, 31);
+            cy += __shfl_sync(FULL, iy, 31);
+        } else if (POST == POST_ZZ_DELTA || POST == POST_DELTA_MORTON) {
+            const int32_t sm = d0 + d1 + d2 + d3;
+            int32_t is = sm;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int32_t t = __shfl_up_sync(FULL, v, d);
-            if (lane >= (unsigned)d) v += t;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int32_t t = __shfl_up_sync(FULL, is, d);
+                if (lane >= (unsigned)d) is += t;
+            }
+            o0 = cx + (is - sm) + d0;
+            o1 = o0 + d1;
+            o2 = o1 + d2;
+            o3 = o2 + d3;
+            cx += __shfl_sync(FULL, is, 31);
+        } else {
+            o0 = d0; o1 = d1; o2 = d2; o3 = d3;
         }
-        v += carry;
-        if (i < n) {
-            if (POST == POST_DELTA_MORTON) reinterpret_cast<int2*>(dst)[index0 + i] = morton_decode(v, num_bits, no_shift);
-            else if (WIDEN) reinterpret_cast<int64_t*>(dst)[index0 + i] = (int64_t)v;
-            else reinterpret_cast<int32_t*>(dst)[index0 + i] = v;
+        if (j >= end) continue;
+        const uint64_t e = base + j;  // stream index of element 0 of this lane (multiple of 4)
+        if (POST == POST_DELTA_MORTON) {
+            int2* out = reinterpret_cast<int2*>(dst) + e;
+            const int2 m0 = morton_decode(o0, num_bits, no_shift), m1 = morton_decode(o1, num_bits, no_shift);
+            const int2 m2 = morton_decode(o2, num_bits, no_shift), m3 = morton_decode(o3, num_bits, no_shift);
+            if (v0 && v1) *reinterpret_cast<int4*>(out) = make_int4(m0.x, m0.y, m1.x, m1.y);
+            else { if (v0) out[0] = m0; if (v1) out[1] = m1; }
+            if (v2 && v3) *reinterpret_cast<int4*>(out + 2) = make_int4(m2.x, m2.y, m3.x, m3.y);
+            else { if (v2) out[2] = m2; if (v3) out[3] = m3; }
+        } else if (WIDEN) {
+            int64_t* out = reinterpret_cast<int64_t*>(dst) + e;
+            if (v0 && v1) *reinterpret_cast<longlong2*>(out) = make_longlong2((long long)o0, (long long)o1);
+            else { if (v0) out[0] = o0; if (v1) out[1] = o1; }
+            if (v2 && v3) *reinterpret_cast<longlong2*>(out + 2) = make_longlong2((long long)o2, (long long)o3);
+            else { if (v2) out[2] = o2; if (v3) out[3] = o3; }
+        } else {
+            int32_t* out = reinterpret_cast<int32_t*>(dst) + e;
+            if (v0 && v3) *reinterpret_cast<int4*>(out) = make_int4(o0, o1, o2, o3);
+            else { if (v0) out[0] = o0; if (v1) out[1] = o1; if (v2) out[2] = o2; if (v3) out[3] = o3; }
         }
-        carry = __shfl_sync(FULL, v, 31);
     }
-    cx = carry;
 }
 
 // runtime dispatch on the (warp-uniform) post kind
-__device__ __forceinline__ void lean_rows_dispatch(int post, bool widen, const uint32_t* stage, uint32_t n, void* dst, uint64_t index0,
-                                                   int32_t& cx, int32_t& cy, uint32_t num_bits, bool no_shift)
+__device__ __forceinline__ void lean_rows4_dispatch(int post, bool widen, const uint32_t* A, uint32_t s4, uint32_t n, void* dst, uint64_t index0,
+                                                    int32_t& cx, int32_t& cy, uint32_t num_bits, bool no_shift)
 {
     switch (post) {
     case POST_PLAIN:
-        if (widen) lean_rows<POST_PLAIN, true>(stage, n, dst, index0, cx, cy, num_bits, no_shift);
-        else lean_rows<POST_PLAIN, false>(stage, n, dst, index0, cx, cy, num_bits, no_shift);
+        if (widen) lean_rows4<POST_PLAIN, true>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);
+        else lean_rows4<POST_PLAIN, false>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);
         break;
-    case POST_ZZ: lean_rows<POST_ZZ, false>(stage, n, dst, index0, cx, cy, num_bits, no_shift); break;
+    case POST_ZZ: lean_rows4<POST_ZZ, false>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift); break;
     case POST_ZZ_DELTA:
-        if (widen) lean_rows<POST_ZZ_DELTA, true>(stage, n, dst, index0, cx, cy, num_bits, no_shift);
-        else lean_rows<POST_ZZ_DELTA, false>(stage, n, dst, index0, cx, cy, num_bits, no_shift);
+        if (widen) lean_rows4<POST_ZZ_DELTA, true>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);
+        else lean_rows4<POST_ZZ_DELTA, false>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);
         break;
-    case POST_ZZ_DELTA_XY: lean_rows<POST_ZZ_DELTA_XY, false>(stage, n, dst, index0, cx, cy, num_bits, no_shift); break;
-    default: lean_rows<POST_DELTA_MORTON, false>(stage, n, dst, index0, cx, cy, num_bits, no_shift); break;
+    case POST_ZZ_DELTA_XY: lean_rows4<POST_ZZ_DELTA_XY, false>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift); break;
+    default: lean_rows4<POST_DELTA_MORTON, false>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift); break;
     }
 }
 
