@@ -141,30 +141,25 @@ __device__ __forceinline__ uint32_t lean_nth_terminator(uint32_t cm, uint32_t m)
 // bytes are 16-byte aligned in dst, and one LDS.128 / STG.128 moves them. One warp scan per 128 values.
 // (cx, cy) = running sums of the values before the chunk at even / odd stream positions; updated on return.
 template <int POST, bool WIDEN>
-__device__ __forceinline__ void lean_rows4(const uint32_t* A, uint32_t s4, uint32_t n, void* dst, uint64_t index0, int32_t& cx, int32_t& cy,
+__device__ __forceinline__ void lean_rows4(uint32_t* A, uint32_t s4, uint32_t n, void* dst, uint64_t index0, int32_t& cx, int32_t& cy,
                                            uint32_t num_bits, bool no_shift)
 {
     const unsigned lane = lane_id();
     const uint64_t base = index0 - s4;
     const uint32_t end = s4 + n;
+    // zero the tail of the last 4-vector so that no delta has to be masked below (A[0 .. s4) is zero by contract)
+    if (lane < 3u && ((end + lane) >> 2) == (end >> 2) && (end & 3u)) A[end + lane] = 0;
+    __syncwarp();
     for (uint32_t r = 0; r < end; r += 128) {
         const uint32_t j = r + 4u * lane;
         uint4 raw = make_uint4(0, 0, 0, 0);
-        if (j < end) raw = *reinterpret_cast<const uint4*>(A + j);  // entries past `end` inside the vector are masked below
+        if (j < end) raw = *reinterpret_cast<const uint4*>(A + j);
         int32_t d0, d1, d2, d3;
         if (POST == POST_PLAIN || POST == POST_DELTA_MORTON) { d0 = (int32_t)raw.x; d1 = (int32_t)raw.y; d2 = (int32_t)raw.z; d3 = (int32_t)raw.w; }
         else { d0 = zigzag_decode32(raw.x); d1 = zigzag_decode32(raw.y); d2 = zigzag_decode32(raw.z); d3 = zigzag_decode32(raw.w); }
-        // validity of the four elements: [s4, end)
-        const bool v0 = j + 0 >= s4 && j + 0 < end, v1 = j + 1 >= s4 && j + 1 < end, v2 = j + 2 >= s4 && j + 2 < end, v3 = j + 3 >= s4 && j + 3 < end;
-        if (POST == POST_ZZ_DELTA_XY || POST == POST_ZZ_DELTA || POST == POST_DELTA_MORTON) {
-            if (!v0) d0 = 0;
-            if (!v1) d1 = 0;
-            if (!v2) d2 = 0;
-            if (!v3) d3 = 0;
-        }
         int32_t o0, o1, o2, o3;
         if (POST == POST_ZZ_DELTA_XY) {
-            int32_t sx = d0 + d2, sy = d1 + d3;
+            const int32_t sx = d0 + d2, sy = d1 + d3;
             int32_t ix = sx, iy = sy;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -195,30 +190,32 @@ __device__ __forceinline__ void lean_rows4(const uint32_t* A, uint32_t s4, uint3
         }
         if (j >= end) continue;
         const uint64_t e = base + j;  // stream index of element 0 of this lane (multiple of 4)
+        const bool full = j >= s4 && j + 4u <= end;
+        const bool v0 = j + 0 >= s4, v1 = j + 1 >= s4 && j + 1 < end, v2 = j + 2 >= s4 && j + 2 < end, v3 = j + 3 >= s4 && j + 3 < end;
         if (POST == POST_DELTA_MORTON) {
             int2* out = reinterpret_cast<int2*>(dst) + e;
             const int2 m0 = morton_decode(o0, num_bits, no_shift), m1 = morton_decode(o1, num_bits, no_shift);
             const int2 m2 = morton_decode(o2, num_bits, no_shift), m3 = morton_decode(o3, num_bits, no_shift);
-            if (v0 && v1) *reinterpret_cast<int4*>(out) = make_int4(m0.x, m0.y, m1.x, m1.y);
-            else { if (v0) out[0] = m0; if (v1) out[1] = m1; }
-            if (v2 && v3) *reinterpret_cast<int4*>(out + 2) = make_int4(m2.x, m2.y, m3.x, m3.y);
-            else { if (v2) out[2] = m2; if (v3) out[3] = m3; }
+            if (full) {
+                *reinterpret_cast<int4*>(out) = make_int4(m0.x, m0.y, m1.x, m1.y);
+                *reinterpret_cast<int4*>(out + 2) = make_int4(m2.x, m2.y, m3.x, m3.y);
+            } else { if (v0) out[0] = m0; if (v1) out[1] = m1; if (v2) out[2] = m2; if (v3) out[3] = m3; }
         } else if (WIDEN) {
             int64_t* out = reinterpret_cast<int64_t*>(dst) + e;
-            if (v0 && v1) *reinterpret_cast<longlong2*>(out) = make_longlong2((long long)o0, (long long)o1);
-            else { if (v0) out[0] = o0; if (v1) out[1] = o1; }
-            if (v2 && v3) *reinterpret_cast<longlong2*>(out + 2) = make_longlong2((long long)o2, (long long)o3);
-            else { if (v2) out[2] = o2; if (v3) out[3] = o3; }
+            if (full) {
+                *reinterpret_cast<longlong2*>(out) = make_longlong2((long long)o0, (long long)o1);
+                *reinterpret_cast<longlong2*>(out + 2) = make_longlong2((long long)o2, (long long)o3);
+            } else { if (v0) out[0] = o0; if (v1) out[1] = o1; if (v2) out[2] = o2; if (v3) out[3] = o3; }
         } else {
             int32_t* out = reinterpret_cast<int32_t*>(dst) + e;
-            if (v0 && v3) *reinterpret_cast<int4*>(out) = make_int4(o0, o1, o2, o3);
+            if (full) *reinterpret_cast<int4*>(out) = make_int4(o0, o1, o2, o3);
             else { if (v0) out[0] = o0; if (v1) out[1] = o1; if (v2) out[2] = o2; if (v3) out[3] = o3; }
         }
     }
 }
 
 // runtime dispatch on the (warp-uniform) post kind
-__device__ __forceinline__ void lean_rows4_dispatch(int post, bool widen, const uint32_t* A, uint32_t s4, uint32_t n, void* dst, uint64_t index0,
+__device__ __forceinline__ void lean_rows4_dispatch(int post, bool widen, uint32_t* A, uint32_t s4, uint32_t n, void* dst, uint64_t index0,
                                                     int32_t& cx, int32_t& cy, uint32_t num_bits, bool no_shift)
 {
     switch (post) {
