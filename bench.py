@@ -213,7 +213,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": threads, "kind": "port",
                              "sample": cfg["sample"] + "; C restatement of the Java decoder (JVM unavailable), -O2, pthreads"},
             "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def build_workload(args, rank, for_cpu=False):
@@ -445,13 +445,26 @@ def run_gpu(args, rank, world, local_rank):
                         "mvertices_per_s": verts_all * steps / (e2e_ms_max * 1e-3) / 1e6,
                         "note": "results stay device-resident (GeoArrow-style buffers); the device->host read is the per-tile status + layer index"},
                 "gpu_launches": int(launches_all), "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else any library prints (NCCL's version banner,
+    make output of the in-tree builds) was redirected to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
