@@ -41,6 +41,7 @@ struct covt_ctx {
     covt::SegState* h_seg = nullptr;     // pinned mirror of the device-side segment state
     uint64_t seg_bytes = 64ull << 20;    // minimum upload/decode segment size of covt_decode_batch (env COVT_SEG_BYTES overrides: tests)
     uint32_t max_segments = 8;           // env COVT_MAX_SEGMENTS overrides
+    uint32_t seg_min_tiles = 32768;      // env COVT_SEG_MIN_TILES overrides
     bool debug = false;                  // env COVT_DEBUG: host-side phase times on stderr
     bool serial_classes = true;          // env COVT_CONCURRENT=1 runs the five codec kernels side by side on their own streams
                                          // (measured SLOWER on B200, 6.61 vs 5.75 ms per 262k tiles: each kernel alone already
@@ -274,6 +275,7 @@ int32_t covt_create(int32_t device, covt_ctx** out)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_join[c], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
     if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if (const char* mt = getenv("COVT_SEG_MIN_TILES")) { const long long v = atoll(mt); if (v > 0) ctx->seg_min_tiles = (uint32_t)std::min<long long>(v, 1ll << 30); }
     if (const char* ms = getenv("COVT_MAX_SEGMENTS")) { const long long v = atoll(ms); if (v > 0) ctx->max_segments = (uint32_t)std::min<long long>(v, 4096); }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
@@ -625,11 +627,14 @@ int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* ti
         if (tile_offsets[i + 1] < tile_offsets[i]) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_decode_batch: tile_offsets must be non-decreasing");
     const uint64_t blob_len = tile_offsets[n_tiles];
     // segments of ~SEG_BYTES, balanced by payload bytes, every one non-empty
-    // Every segment costs ~1 ms of fixed kernel time (13 launches that are latency-bound at small sizes), so use few, large
-    // segments: at most 8, at least seg_bytes each (measured on B200, 1 M tiles / 2.77 GB: 1 segment 76.5 ms, 6 segments
-    // 57.0 ms, 57 segments 84 ms per call; the host->device copy alone takes 50.4 ms)
+    // Every segment costs ~1 ms of fixed kernel time (13 launches that are latency-bound at small sizes), and a segment must hold
+    // enough tiles to fill the GPU (a kernel cannot finish before its largest stream, which one warp decodes), so use few, large
+    // segments: at most 8, at least seg_bytes and 32768 tiles each. Measured on B200: 1 M tiles / 2.77 GB — 1 segment 76.5 ms,
+    // 8 segments 56.4 ms, 57 segments 84 ms per call (the host->device copy alone takes 50.4 ms); the 91 OMT fixture tiles x256
+    // (23 296 tiles of 122 KB, layers of up to 60 000 features) — 8 segments 199 ms, 1 segment ~90 ms.
     const uint64_t SEG_BYTES = std::max<uint64_t>(ctx->seg_bytes, 4096);
     uint32_t want = (uint32_t)std::min<uint64_t>(ctx->max_segments, std::max<uint64_t>(1, (blob_len - tile_offsets[0]) / SEG_BYTES));
+    want = std::max<uint32_t>(1, std::min<uint32_t>(want, n_tiles / ctx->seg_min_tiles));
     if (tile_offsets[0] != 0) want = 1;  // the segment extrapolation assumes the blob starts at its first tile
     std::vector<uint32_t> starts(want + 1);
     covt_partition_tiles(tile_offsets, n_tiles, want, starts.data());

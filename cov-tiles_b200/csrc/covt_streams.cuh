@@ -466,31 +466,27 @@ __device__ __forceinline__ uint32_t unpack_packed(const uint8_t* base, uint32_t 
     return k >= 32u ? v : (v & ((1u << k) - 1u));
 }
 
-__device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* stage, StreamOutcome& out, const int post)
+// Streams larger than the shared-memory window (PFOR_SMEM_WORDS): the page is walked through global memory, but everything the
+// inner loop touches is staged first with coalesced loads — the 8*b packed words of the current block, and a sliding 512-byte
+// window of the byte container (consumed front to back) — so that no lane chases dependent unaligned global loads. Only the
+// exception VALUES (a few percent of the stream) are fetched from global memory directly.
+// wsm: PFOR_WARP_SMEM bytes of warp-private shared memory.
+__device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* wsm, StreamOutcome& out, const int post)
 {
+    uint32_t* pk = wsm;           // [272] packed words of one block (+1 for the funnel shift)
+    uint32_t* bcw = wsm + 272;    // [132] byte-container window
+    uint32_t* stage = wsm + 404;  // [LEAN_STAGE_WORDS] values, 16-byte aligned
     const unsigned lane = lane_id();
     const uint8_t* base = t.src;
     const uint32_t n_words = t.byte_length / 4u;  // (int)Math.ceil(byteLength / 4): integer division, DecodingUtils.java:324
     const uint32_t n = t.num_values;
-    const bool ZZ = (post == POST_ZZ_DELTA || post == POST_ZZ_DELTA_XY);
-    const int copy_kind = post == POST_DELTA_MORTON ? COPY_MORTON : COPY_I32;
-    DeltaCarry carry = {0, 0, 0};
+    uint32_t produced = 0;
+    int32_t cx = 0, cy = 0;
     uint32_t status = COVT_OK;
     uint32_t inpos = 0;
     out.consumed = t.byte_length;
 #define PFOR_FAIL(code) { status = (code); goto finish; }
-    if (n_words == 0) {
-        // Composition.uncompress returns at once: the output stays all zeros, the post passes still run
-        for (uint32_t b0 = 0; b0 < n; b0 += 512) {
-            uint32_t m = min(512u, n - b0);
-            for (uint32_t i = lane; i < m; i += 32) stage[stage_index(i)] = 0;
-            __syncwarp();
-            warp_copy_out<16>(stage, m, t.dst, b0, copy_kind, t.num_bits, t.no_shift != 0);
-            __syncwarp();
-        }
-        out.status = COVT_OK;
-        return;
-    }
+    if (n_words == 0) PFOR_FAIL(COVT_ERR_TRUNCATED);  // cannot happen: streams this large have words (kept for symmetry)
     {
         const uint32_t mynvalue = ld_be_word(base, 0);
         inpos = 1;
@@ -515,8 +511,8 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* sta
             inexcept++;
             // exception array of width k lives in lane k-1: first word, size, cursor (cursors reset per page)
             uint32_t exc_base = 0, exc_size = 0, exc_ptr = 0;
-            for (uint32_t k = 2; k <= 32; k++) {
-                if (!(bitmap & (1u << (k - 1)))) continue;
+            for (uint32_t rest = bitmap & ~1u; rest; rest &= rest - 1u) {
+                const uint32_t k = (uint32_t)__ffs(rest);  // bit k-1 set
                 if (inexcept >= n_words) PFOR_FAIL(COVT_ERR_TRUNCATED);
                 const uint32_t size = ld_be_word(base, (uint32_t)inexcept);
                 inexcept++;
@@ -527,18 +523,35 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* sta
             }
             uint32_t tmpin = initpos + 1;
             uint32_t bcpos = 0;
+            uint32_t bc_lo = 0, bc_hi = 0;  // byte range of the container held in bcw (bc_lo a multiple of 4)
             // byte i of the byte container: bytes are little-endian inside each (big-endian serialised) word
-#define BC_BYTE(i) ((ld_be_word(base, bc_word0 + ((i) >> 2)) >> (8u * ((i) & 3u))) & 0xffu)
+#define BC_BYTE(i) ((bcw[((i) - bc_lo) >> 2] >> (8u * ((i) & 3u))) & 0xffu)
             for (uint32_t run = 0, run_end = thissize / 256u; run < run_end; run++) {
                 if (bcpos + 2 > bytesize) PFOR_FAIL(COVT_ERR_TRUNCATED);
+                if (bcpos < bc_lo || bcpos + 260u > bc_hi) {  // a block reads at most 2 + 1 + 255 container bytes
+                    __syncwarp();
+                    bc_lo = bcpos & ~3u;
+                    bc_hi = bc_lo + 512u;
+                    for (uint32_t i = lane; i < 128u; i += 32) {
+                        const uint64_t wi = (uint64_t)bc_word0 + (bc_lo >> 2) + i;
+                        bcw[i] = wi < (uint64_t)bc_word0 + bc_words ? ld_be_word(base, (uint32_t)wi) : 0u;
+                    }
+                    __syncwarp();
+                }
                 const uint32_t b = BC_BYTE(bcpos);
                 const uint32_t cexcept = BC_BYTE(bcpos + 1);
                 bcpos += 2;
                 if (b > 32u) PFOR_FAIL(COVT_ERR_BAD_METADATA);
                 if ((uint64_t)tmpin + 8ull * b > (uint64_t)initpos + wheremeta) PFOR_FAIL(COVT_ERR_TRUNCATED);
-                // ---- unpack 256 values of b bits: value (g, lane) ----
+                // ---- stage the block's 8*b packed words, then unpack 256 values of b bits: value (g, lane) ----
+                for (uint32_t i = lane; i < 8u * b + 1u; i += 32) pk[i] = tmpin + i < n_words ? ld_be_word(base, tmpin + i) : 0u;
+                __syncwarp();
+                {
+                    const uint32_t bo = lane * b, wi = bo >> 5, sh = bo & 31u;
+                    const uint32_t mask = b >= 32u ? 0xffffffffu : ((1u << b) - 1u);
 #pragma unroll
-                for (int g = 0; g < 8; g++) stage[stage_index(g * 32 + lane)] = unpack_packed(base, tmpin + g * b, lane, b);
+                    for (int g = 0; g < 8; g++) stage[g * 32 + lane] = __funnelshift_r(pk[wi + g * b], pk[wi + g * b + 1], sh) & mask;
+                }
                 tmpin += 8u * b;
                 if (cexcept > 0) {
                     if (bcpos + 1 + cexcept > bytesize) PFOR_FAIL(COVT_ERR_TRUNCATED);
@@ -547,61 +560,54 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* sta
                     const int index = (int)maxbits - (int)b;
                     __syncwarp();
                     if (index == 1) {
-                        for (uint32_t e = lane; e < cexcept; e += 32) {
-                            const uint32_t p = BC_BYTE(bcpos + e);
-                            stage[stage_index(p)] |= 1u << (b & 31u);
-                        }
+                        for (uint32_t e = lane; e < cexcept; e += 32) stage[BC_BYTE(bcpos + e)] |= 1u << (b & 31u);
                     } else {
                         if (index < 2 || index > 32 || !(bitmap & (1u << (index - 1)))) PFOR_FAIL(COVT_ERR_BAD_METADATA);
                         const uint32_t ebase = __shfl_sync(FULL, exc_base, index - 1);
                         const uint32_t esize = __shfl_sync(FULL, exc_size, index - 1);
                         const uint32_t eptr = __shfl_sync(FULL, exc_ptr, index - 1);
                         if (eptr + cexcept > esize) PFOR_FAIL(COVT_ERR_TRUNCATED);
-                        for (uint32_t e = lane; e < cexcept; e += 32) {
-                            const uint32_t p = BC_BYTE(bcpos + e);
-                            const uint32_t ev = unpack_packed(base, ebase, eptr + e, (uint32_t)index);
-                            stage[stage_index(p)] |= ev << (b & 31u);
-                        }
+                        for (uint32_t e = lane; e < cexcept; e += 32)
+                            stage[BC_BYTE(bcpos + e)] |= unpack_packed(base, ebase, eptr + e, (uint32_t)index) << (b & 31u);
                         if (lane == (unsigned)(index - 1)) exc_ptr += cexcept;
                     }
                     bcpos += cexcept;
                 }
                 __syncwarp();
-                warp_delta_pass<8>(stage, 256, carry, post, ZZ);
+                lean_rows4_dispatch(post, false, stage, 0, 256, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
                 __syncwarp();
-                warp_copy_out<8>(stage, 256, t.dst, carry.produced, copy_kind, t.num_bits, t.no_shift != 0);
-                __syncwarp();
-                carry.produced += 256;
+                produced += 256;
             }
 #undef BC_BYTE
             outpos += thissize;
             inpos = (uint32_t)inexcept;
         }
-        // ---- VariableByte tail over ALL remaining words (VariableByte.uncompress) ----
-        uint32_t halo = 0x80808080u;  // VB: MSB set = terminator, so nothing is carried in
-        bool overlong = false;
+        // ---- VariableByte tail over ALL remaining words (see warp_pfor_stream_smem) ----
+        uint32_t carry_halo = 0, ov = 0;
         for (uint32_t wbase = inpos; wbase < n_words; wbase += 128) {
-            uint32_t words[4];
-            uint32_t valid16 = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t wi = wbase + lane * 4u + q;
-                words[q] = wi < n_words ? ld_be_word(base, wi) : 0u;
-                if (wi < n_words) valid16 |= 0xfu << (4 * q);
-            }
-            uint32_t emit, excl, ctotal;
-            const uint32_t remaining = n - carry.produced;
-            varint32_chunk_decode<true, true>(make_uint4(words[0], words[1], words[2], words[3]), valid16, halo, remaining,
-                                              stage, emit, excl, ctotal, overlong);
+            const uint32_t first_w = wbase + lane * 4u;
+            uint4 win;
+            win.x = first_w + 0 < n_words ? ld_be_word(base, first_w + 0) ^ 0x80808080u : 0u;
+            win.y = first_w + 1 < n_words ? ld_be_word(base, first_w + 1) ^ 0x80808080u : 0u;
+            win.z = first_w + 2 < n_words ? ld_be_word(base, first_w + 2) ^ 0x80808080u : 0u;
+            win.w = first_w + 3 < n_words ? ld_be_word(base, first_w + 3) ^ 0x80808080u : 0u;
+            const uint32_t valid_words = min(128u, n_words - wbase);
+            const uint32_t tail_f = 512u - 4u * valid_words;
+            uint32_t w[4], acc, mul;
+            LeanLane L = lean_front(win, false, 0, 16, carry_halo, w, acc, mul, ov);
+            L.excl = warp_exclusive_scan(L.cnt, L.total);
+            const uint32_t ctotal = L.total - tail_f;
+            const uint32_t remaining = n - produced;
             if (ctotal > remaining) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);  // Java: ArrayIndexOutOfBounds
+            const uint32_t s4 = produced & 3u;
+            if (lane < s4) stage[lane] = 0;
+            lean_stage_lane(w, L.cm, acc, mul, stage + s4 + L.excl, ov);
             __syncwarp();
-            warp_delta_pass<16>(stage, ctotal, carry, post, ZZ);
+            lean_rows4_dispatch(post, false, stage, s4, ctotal, t.dst, produced, cx, cy, t.num_bits, t.no_shift != 0);
             __syncwarp();
-            warp_copy_out<16>(stage, ctotal, t.dst, carry.produced, copy_kind, t.num_bits, t.no_shift != 0);
-            __syncwarp();
-            carry.produced += ctotal;
+            produced += ctotal;
         }
-        if (carry.produced != n) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);
+        if (produced != n) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);
     }
 finish:
 #undef PFOR_FAIL

@@ -224,6 +224,7 @@ def test_pipelined_segments_equal_one_shot(covt, oracle, gen, fixtures, monkeypa
     abi = covt.abi
     monkeypatch.setenv("COVT_SEG_BYTES", str(1 << 20))
     monkeypatch.setenv("COVT_MAX_SEGMENTS", "64")
+    monkeypatch.setenv("COVT_SEG_MIN_TILES", "16")
     dec = covt.Decoder(0)
     try:
         blob, offs, truth = gen.tiles(31, 4000, gen.default_params())
