@@ -472,7 +472,9 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
     CKR(cudaEventRecord(ev0, st));
     uint32_t launches = 0;
     ResultBuffers rb = {};
-    uint64_t task_cap_layers = 0;
+    ClassOffsets class_off = {};
+    uint64_t task_cap[NUM_OP_CLASSES] = {};
+    uint64_t layers_per_seg_bound = 0;
     for (uint32_t sg = 0; sg < S && n_tiles; sg++) {
         const uint32_t t0 = seg_starts[sg], nt = seg_starts[sg + 1] - t0;
         if (uploaded) CKR(cudaStreamWaitEvent(st, (*uploaded)[sg], 0));
@@ -495,11 +497,19 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
                 const double seg_bytes = (double)(h_tile_offsets[seg_starts[1]] - h_tile_offsets[0]);
                 scale = seg_bytes > 0 ? (double)batch->blob_len / seg_bytes * 1.10 : 1e9;
             }
-            for (int c = 0; c < TILE_COLS; c++)
+            for (int c = 0; c < COL_CLASS0; c++)
                 hs->cap[c] = S > 1 ? (uint64_t)((double)ctx->h_totals[c] * scale) + 65536 : ctx->h_totals[c];
             if (hs->cap[0] > 0xfffffff0ull) { cleanup_tmp(); covt_result_free(R); return fail(ctx, COVT_ERR_INVALID_ARG, "too many layers in one batch"); }
-            task_cap_layers = S > 1 ? (uint64_t)((double)ctx->h_totals[0] / nt * max_seg_tiles * 1.25) + 4096 : ctx->h_totals[0];
-            // the task table is per segment: a segment with more layers than it holds counts as an overflow too
+            // the task lists are per segment: a segment that needs more entries than extrapolated counts as an overflow too
+            const double seg_scale = S > 1 ? (double)max_seg_tiles / nt * 1.25 : 1.0;
+            uint64_t task_total = 0;
+            for (int c = 0; c < NUM_OP_CLASSES; c++) {
+                task_cap[c] = S > 1 ? (uint64_t)((double)ctx->h_totals[COL_CLASS0 + c] * seg_scale) + 4096 : ctx->h_totals[COL_CLASS0 + c];
+                hs->cap[COL_CLASS0 + c] = task_cap[c];
+                class_off.off[c] = task_total;
+                task_total += task_cap[c];
+            }
+            layers_per_seg_bound = S > 1 ? (uint64_t)((double)ctx->h_totals[0] * seg_scale) + 4096 : ctx->h_totals[0];
             uint64_t arena_bytes = 0, buf_off[COVT_NUM_BUFFERS];
             for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
                 buf_off[b] = arena_bytes;
@@ -513,21 +523,21 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             }
             if (ctx->debug) fprintf(stderr, "[covt] result arena %.2f GB allocated in %.2f ms (segments %u)\n", arena_bytes / 1e9, now_ms() - t_alloc0, S);
             CKR(dev_alloc(ctx, &R->d_layers, hs->cap[0]));
-            CKR(dev_alloc(ctx, &d_tasks, task_cap_layers * COVT_NUM_SLOTS));
+            CKR(dev_alloc(ctx, &d_tasks, task_total));
             CKR(cudaMemcpyAsync(d_seg->cap, hs->cap, sizeof(hs->cap), cudaMemcpyHostToDevice, st));
         }
-        CKR(launch_seg_begin(d_seg, d_counter, task_cap_layers, st));
+        CKR(launch_seg_begin(d_seg, d_counter, st));
         // ---- K0 pass 2: the layer table + eight decode tasks per layer ----
         prof.begin("k0_fill_layers", 0);
         CKR(launch_k0_fill_layers(batch->d_blob, batch->d_tile_offsets + t0, nt, t0, container, d_tj, tj_layers, flags, d_cols, rb, R->d_layers, d_tasks,
-                                  R->d_first_layer + t0, d_seg, st));
+                                  class_off, R->d_first_layer + t0, d_seg, st));
         prof.end();
         // ---- every stream of every layer: one kernel per codec class ----
-        const uint32_t n_tasks_bound = (uint32_t)std::min<uint64_t>(task_cap_layers * COVT_NUM_SLOTS, 0xffffff00ull);
         if (prof.on || ctx->serial_classes) {
             for (int c = 0; c < NUM_OP_CLASSES; c++) {
                 prof.begin(op_class_name(c), 0);
-                CKR(launch_decode_class(c, batch->d_blob, d_tasks, n_tasks_bound, d_counter + c, d_seg, ctx->sm_count, 0, st));
+                CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_off.off[c], (uint32_t)std::min<uint64_t>(task_cap[c], 0xffffff00ull), d_counter + c, d_seg,
+                                        R->d_layers, ctx->sm_count, 0, st));
                 prof.end();
             }
         } else {
@@ -539,14 +549,15 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             for (int i = 0; i < NUM_OP_CLASSES; i++) {
                 const int c = order[i];
                 CKR(cudaStreamWaitEvent(ctx->class_stream[c], ctx->ev_fork, 0));
-                CKR(launch_decode_class(c, batch->d_blob, d_tasks, n_tasks_bound, d_counter + c, d_seg, ctx->sm_count, share[c], ctx->class_stream[c]));
+                CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_off.off[c], (uint32_t)std::min<uint64_t>(task_cap[c], 0xffffff00ull), d_counter + c, d_seg,
+                                        R->d_layers, ctx->sm_count, share[c], ctx->class_stream[c]));
                 CKR(cudaEventRecord(ctx->ev_join[c], ctx->class_stream[c]));
                 CKR(cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
             }
         }
         // ---- geometry assembly ----
         prof.begin("k_assemble_layers", 0);
-        CKR(launch_assemble_layers(R->d_layers, d_tasks, (uint32_t)std::min<uint64_t>(task_cap_layers, 0xffffff00ull), rb, flags, d_counter + 8, d_seg, ctx->sm_count, st));
+        CKR(launch_assemble_layers(R->d_layers, (uint32_t)std::min<uint64_t>(layers_per_seg_bound, 0xffffff00ull), rb, flags, d_counter + 8, d_seg, ctx->sm_count, st));
         prof.end();
         CKR(launch_seg_end(d_seg, sg + 1 == S ? R->d_first_layer + n_tiles : nullptr, st));
         launches += 9;
@@ -558,7 +569,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         launches += 1;
     }
     CKR(cudaEventRecord(ev1, st));
-    CKR(cudaMemcpyAsync(ctx->h_totals + 16, d_totals + 16, FINAL_TOTALS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CKR(cudaMemcpyAsync(ctx->h_totals + 32, d_totals + 16, FINAL_TOTALS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CKR(cudaMemcpyAsync(ctx->h_seg, d_seg, sizeof(SegState), cudaMemcpyDeviceToHost, st));
     CKR(cudaStreamSynchronize(st));
     if (ctx->h_seg->overflow) {
@@ -578,23 +589,25 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
     R->n_layers = (uint32_t)ctx->h_seg->base[0];
     for (int b = 0; b < COVT_NUM_BUFFERS; b++) R->counts[b] = ctx->h_seg->base[1 + b];
     R->timing.h2d_ms = batch->h2d_ms;
-    R->timing.vertices = ctx->h_totals[16];
-    R->timing.payload_bytes = ctx->h_totals[17];
-    R->timing.output_bytes = ctx->h_totals[18];
+    R->timing.vertices = ctx->h_totals[32];
+    R->timing.payload_bytes = ctx->h_totals[33];
+    R->timing.output_bytes = ctx->h_totals[34];
     if (prof.on) {
         // algorithmic bytes per kernel: known only now that k_finalize has summed them on the device;
         // booked on the first launch of each kernel (the records of one kernel are merged by name)
         const uint64_t meta_bytes = batch->blob_len > R->timing.payload_bytes ? batch->blob_len - R->timing.payload_bytes : 0;
+        uint64_t n_task_entries = 0;
+        for (int c = 0; c < NUM_OP_CLASSES; c++) n_task_entries += ctx->h_seg->base[COL_CLASS0 + c];
         std::vector<std::string> seen;
         for (auto& r : prof.recs) {
             if (std::find(seen.begin(), seen.end(), r.name) != seen.end()) continue;
             seen.push_back(r.name);
             if (r.name == "k0_scan_tiles") r.alg_bytes = meta_bytes + (uint64_t)n_tiles * (8 + TILE_COLS * 8 + 4);
             else if (r.name == "scan_tile_cols") r.alg_bytes = 2ull * n_tiles * TILE_COLS * 8;
-            else if (r.name == "k0_fill_layers") r.alg_bytes = meta_bytes + (uint64_t)n_tiles * (8 + TILE_COLS * 8) + (uint64_t)R->n_layers * (sizeof(covt_layer) + COVT_NUM_SLOTS * sizeof(DeviceTask));
-            else if (r.name == "k_assemble_layers") r.alg_bytes = ctx->h_totals[16 + 8];
+            else if (r.name == "k0_fill_layers") r.alg_bytes = meta_bytes + (uint64_t)n_tiles * (8 + TILE_COLS * 8) + (uint64_t)R->n_layers * sizeof(covt_layer) + n_task_entries * sizeof(DeviceTask);
+            else if (r.name == "k_assemble_layers") r.alg_bytes = ctx->h_totals[32 + 8];
             else if (r.name == "k_finalize") r.alg_bytes = (uint64_t)R->n_layers * sizeof(covt_layer);
-            else for (int c = 0; c < NUM_OP_CLASSES; c++) if (r.name == op_class_name(c)) r.alg_bytes = ctx->h_totals[16 + 3 + c];
+            else for (int c = 0; c < NUM_OP_CLASSES; c++) if (r.name == op_class_name(c)) r.alg_bytes = ctx->h_totals[32 + 3 + c];
         }
         prof.collect(R->kernel_times);
     }
@@ -841,8 +854,27 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     R->bufs[COVT_BUF_STREAM_ARENA] = R->arena;
     CKR(dev_alloc(ctx, &d_tasks, n));
     CKR(dev_alloc(ctx, &d_counter, 16));
-    for (uint32_t i = 0; i < n; i++)
+    // dense task list per codec class (the class kernels walk their own list); tasks taken by the large-stream kernel and
+    // rejected requests go last. ref = index of the covt_stream_desc the outcome belongs to.
+    std::vector<DeviceTask> sorted(n);
+    uint32_t class_count[NUM_OP_CLASSES] = {}, class_first[NUM_OP_CLASSES + 1] = {};
+    for (uint32_t i = 0; i < n; i++) {
         tasks[i].dst = reinterpret_cast<uint8_t*>(R->bufs[COVT_BUF_STREAM_ARENA]) + reinterpret_cast<uintptr_t>(tasks[i].dst);
+        tasks[i].ref = i;
+        const int c = host_op_class_of(tasks[i].op);
+        if (c >= 0) class_count[c]++;
+    }
+    for (int c = 0; c < NUM_OP_CLASSES; c++) class_first[c + 1] = class_first[c] + class_count[c];
+    std::vector<uint32_t> pos_of(n);
+    {
+        uint32_t cursor[NUM_OP_CLASSES + 1];
+        for (int c = 0; c <= NUM_OP_CLASSES; c++) cursor[c] = class_first[c];
+        for (uint32_t i = 0; i < n; i++) {
+            const int c = host_op_class_of(tasks[i].op);
+            pos_of[i] = cursor[c >= 0 ? c : NUM_OP_CLASSES]++;
+            sorted[pos_of[i]] = tasks[i];
+        }
+    }
     if (!bigs.empty()) {
         CKR(dev_alloc(ctx, &d_bigs, bigs.size()));
         CKR(dev_alloc(ctx, &d_block_states, (uint64_t)n_big_chunks / K1_SCAN_BLOCK + 2));
@@ -850,12 +882,12 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
         for (size_t k = 0; k < bigs.size(); k++) {
             const uint32_t i = big_task[k];
             bigs[k].dst = tasks[i].dst;
-            bigs[k].status_out = &d_tasks[i].status;
-            bigs[k].consumed_out = &d_tasks[i].consumed;
+            bigs[k].status_out = &d_tasks[pos_of[i]].status;
+            bigs[k].consumed_out = &d_tasks[pos_of[i]].consumed;
         }
         CKR(cudaMemcpyAsync(d_bigs, bigs.data(), bigs.size() * sizeof(BigStream), cudaMemcpyHostToDevice, st));
     }
-    if (n) CKR(cudaMemcpyAsync(d_tasks, tasks.data(), (uint64_t)n * sizeof(DeviceTask), cudaMemcpyHostToDevice, st));
+    if (n) CKR(cudaMemcpyAsync(d_tasks, sorted.data(), (uint64_t)n * sizeof(DeviceTask), cudaMemcpyHostToDevice, st));
     CKR(cudaMemsetAsync(d_counter, 0, 16 * sizeof(uint32_t), st));
     CKR(cudaEventRecord(ev0, st));
     uint32_t launches = 0;
@@ -866,23 +898,24 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
         launches += 5;
     }
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
-        if (!class_alg[c]) continue;
+        if (!class_count[c]) continue;
         prof.begin(op_class_name(c), class_alg[c]);
-        CKR(launch_decode_class(c, batch->d_blob, d_tasks, n, d_counter + c, nullptr, ctx->sm_count, 0, st));
+        CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_first[c], class_count[c], d_counter + c, nullptr, nullptr, ctx->sm_count, 0, st));
         prof.end();
         launches++;
     }
     CKR(cudaEventRecord(ev1, st));
-    if (n) CKR(cudaMemcpyAsync(tasks.data(), d_tasks, (uint64_t)n * sizeof(DeviceTask), cudaMemcpyDeviceToHost, st));
+    if (n) CKR(cudaMemcpyAsync(sorted.data(), d_tasks, (uint64_t)n * sizeof(DeviceTask), cudaMemcpyDeviceToHost, st));
     CKR(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&R->timing.decode_ms, ev0, ev1);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
     for (uint32_t i = 0; i < n; i++) {
         if (descs[i].status != COVT_OK) { descs[i].out_count = 0; continue; }
-        descs[i].status = tasks[i].status;
-        descs[i].bytes_consumed = tasks[i].consumed;
-        if (tasks[i].status != COVT_OK && tasks[i].status != COVT_ERR_VARINT_OVERLONG) descs[i].out_count = 0;
+        const DeviceTask& t = sorted[pos_of[i]];
+        descs[i].status = t.status;
+        descs[i].bytes_consumed = t.consumed;
+        if (t.status != COVT_OK && t.status != COVT_ERR_VARINT_OVERLONG) descs[i].out_count = 0;
     }
     R->timing.h2d_ms = batch->h2d_ms;
     R->timing.payload_bytes = payload;

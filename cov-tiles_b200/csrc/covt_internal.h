@@ -10,12 +10,15 @@ namespace covt {
 // value post-processing of the varint / FastPFOR pipelines
 enum PostKind { POST_PLAIN = 0, POST_ZZ = 1, POST_ZZ_DELTA = 2, POST_ZZ_DELTA_XY = 3, POST_DELTA_MORTON = 4 };
 
-constexpr int TILE_COLS = 1 + COVT_NUM_BUFFERS;  // column 0 = layers per tile, 1.. = slice sizes per result buffer
+constexpr int NUM_OP_CLASSES_C = 5;
+// column 0 = layers per tile, 1 .. 13 = slice sizes per result buffer, 14 .. 18 = decode tasks per codec class
+constexpr int TILE_COLS = 1 + COVT_NUM_BUFFERS + NUM_OP_CLASSES_C;
+constexpr int COL_CLASS0 = 1 + COVT_NUM_BUFFERS;
 
 struct ResultBuffers { void* ptr[COVT_NUM_BUFFERS]; };
 
-// One stream to decode. The batch path keeps COVT_NUM_SLOTS of them per layer (task index = layer * 8 + slot,
-// written by k0_fill_layers); the stream path builds them on the host from covt_stream_desc.
+// One stream to decode. Tasks are kept in one dense list per codec class (the batch path counts them per tile in k0_scan_tiles
+// and writes them in k0_fill_layers; the stream path sorts them on the host), so that every lane of a class kernel has work.
 struct DeviceTask {
     uint64_t src_offset;   // into the batch blob
     uint8_t* dst;          // absolute device pointer of the output slice (16-byte aligned)
@@ -25,14 +28,15 @@ struct DeviceTask {
     uint8_t num_bits, no_shift, exact_length;
     uint32_t status;       // out
     uint32_t consumed;     // out
-    uint32_t pad;
+    uint32_t ref;          // batch path: layer * 8 + slot (where the status goes); stream path: index of the covt_stream_desc
 };
 
 // Device-side state of one batch decode. A batch is decoded in one or more SEGMENTS (contiguous tile ranges): with host
 // input the upload of segment i+1 overlaps the decode of segment i, and the host never waits to learn a segment's sizes.
 struct SegState {
     uint64_t base[TILE_COLS];       // totals of the segments already decoded (col 0 = layers, 1.. = result-buffer elements)
-    uint64_t cap[TILE_COLS];        // capacity of the layer table / result buffers (exact for one segment, an estimate otherwise)
+    uint64_t cap[TILE_COLS];        // capacity of the layer table / result buffers (exact for one segment, an estimate otherwise);
+                                    // for the class columns: capacity of the class's task list, which is per segment
     uint64_t seg_total[TILE_COLS];  // totals of the current segment (written by the column scan)
     uint32_t overflow;              // sticky: an estimate was too small -> every later kernel is a no-op, the host decodes again
     uint32_t seg_layers, seg_layer_base, pad;
@@ -40,6 +44,9 @@ struct SegState {
 
 // codec classes = one small kernel each (the instruction working set of a kernel must stay cache-resident)
 enum OpClass { CLASS_BYTE_RLE = 0, CLASS_RLE = 1, CLASS_VARINT32 = 2, CLASS_VARINT64 = 3, CLASS_PFOR = 4, NUM_OP_CLASSES = 5 };
+static_assert(NUM_OP_CLASSES == NUM_OP_CLASSES_C, "TILE_COLS counts the codec classes");
+// first task of every class in the task table
+struct ClassOffsets { uint64_t off[NUM_OP_CLASSES]; };
 
 // A large 32-bit varint stream, decoded by many CTAs in two wait-free passes (k1a aggregates -> segmented scan -> k1b).
 struct BigStream {
@@ -68,19 +75,20 @@ cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offse
                                  const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols,
                                  uint32_t* tile_status, cudaStream_t st);
 cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_t* block_sums, uint64_t* totals, cudaStream_t st);
-cudaError_t launch_seg_begin(SegState* seg, uint32_t* work_counters /*[16]*/, uint64_t task_cap_layers, cudaStream_t st);
+cudaError_t launch_seg_begin(SegState* seg, uint32_t* work_counters /*[16]*/, cudaStream_t st);
 cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end /*nullable*/, cudaStream_t st);
 cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                   const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, const SegState* seg,
-                                  cudaStream_t st);
-// one codec class over a task table; work_counter must be zero. seg != nullptr: the task count is seg->seg_layers * 8 and
-// n_tasks only bounds the grid
+                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer,
+                                  const SegState* seg, cudaStream_t st);
+// one codec class over ITS dense task list; work_counter must be zero. seg != nullptr (batch path): the task count is
+// seg->seg_total[COL_CLASS0 + class], n_tasks only bounds the grid, and every stream's status is also written to
+// layers[ref / 8].streams[ref % 8].
 // blocks_per_sm: 0 = fill the GPU with this kernel alone; > 0 = its share when the class kernels run concurrently
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
-                                const SegState* seg, int sm_count, int blocks_per_sm, cudaStream_t st);
+                                const SegState* seg, covt_layer* layers, int sm_count, int blocks_per_sm, cudaStream_t st);
 const char* op_class_name(int op_class);
-cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
+cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
                                    uint32_t* work_counter, const SegState* seg, int sm_count, cudaStream_t st);
 // k1a_aggregate + 3 segmented-scan kernels + k1b_decode; block_states needs ceil(n_chunks / K1_SCAN_BLOCK) entries
 cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks,
@@ -89,5 +97,6 @@ cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_laye
                             uint32_t* tile_status, uint64_t* totals /* [FINAL_TOTALS], see k_finalize */, const SegState* seg,
                             cudaStream_t st);
 uint32_t host_resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags);
+int host_op_class_of(uint32_t op);  // OpClass of a covt_op, -1 for COVT_OP_NONE
 
 }  // namespace covt

@@ -102,6 +102,21 @@ __host__ __device__ inline uint32_t resolve_op(uint32_t stream_type, uint32_t en
 }
 uint32_t host_resolve_op(uint32_t st, uint32_t enc, uint32_t ct, uint32_t flags) { return resolve_op(st, enc, ct, flags); }
 
+__host__ __device__ inline int op_class_of(uint32_t op)
+{
+    switch (op) {
+    case COVT_OP_BYTE_RLE: return CLASS_BYTE_RLE;
+    case COVT_OP_RLE_U32: case COVT_OP_RLE_U64: case COVT_OP_RLE_S64: return CLASS_RLE;
+    case COVT_OP_VARINT_U32: case COVT_OP_VARINT_ZZ: case COVT_OP_VARINT_ZZ_DELTA: case COVT_OP_VARINT_ZZ_DELTA_XY:
+    case COVT_OP_VARINT_DELTA_MORTON: case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: return CLASS_VARINT32;
+    case COVT_OP_VARINT_U64: case COVT_OP_VARINT_ZZ_DELTA_64: return CLASS_VARINT64;
+    case COVT_OP_PFOR_ZZ_DELTA: case COVT_OP_PFOR_ZZ_DELTA_XY: case COVT_OP_PFOR_DELTA_MORTON: return CLASS_PFOR;
+    default: return -1;
+    }
+}
+
+int host_op_class_of(uint32_t op) { return op_class_of(op); }
+
 // =================================================================================================
 // K0: container walk, one thread per tile
 // =================================================================================================
@@ -396,6 +411,11 @@ __global__ void k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets,
                                       layer_slice_sizes(L, flags, sz);
                                       acc[0] += 1;
                                       for (int b = 0; b < COVT_NUM_BUFFERS; b++) acc[1 + b] += align_elems(sz[b], kBufElemSizeDev(b));
+                                      if (L.status != COVT_ERR_BAD_METADATA)
+                                          for (int s = 0; s < COVT_NUM_SLOTS; s++) {
+                                              const int c = L.streams[s].encoding != COVT_ENC_ABSENT ? op_class_of(L.streams[s].op) : -1;
+                                              if (c >= 0) acc[COL_CLASS0 + c] += 1;
+                                          }
                                   });
     tile_status[t] = st;
     for (int i = 0; i < TILE_COLS; i++) tile_cols[(uint64_t)i * n_tiles + t] = acc[i];
@@ -404,7 +424,8 @@ __global__ void k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets,
 // pass 2: write the covt_layer table with result offsets (tile_cols now holds exclusive prefixes)
 __global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                               ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, const SegState* seg)
+                               ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer,
+                               const SegState* seg)
 {
     const uint8_t slot_buf[COVT_NUM_SLOTS] = {COVT_BUF_S_IDS, COVT_BUF_S_GEOMETRY_TYPES, COVT_BUF_S_GEOMETRY_OFFSETS,
                                               COVT_BUF_S_PART_OFFSETS, COVT_BUF_S_RING_OFFSETS, COVT_BUF_S_VERTEX_OFFSETS,
@@ -413,8 +434,8 @@ __global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets
     if (t >= n_tiles || seg->overflow) return;
     // tile_cols holds exclusive prefixes inside this segment; seg->base = totals of the segments before it
     uint64_t run[TILE_COLS];
-    for (int i = 0; i < TILE_COLS; i++) run[i] = tile_cols[(uint64_t)i * n_tiles + t] + seg->base[i];
-    const uint64_t layer_base = seg->base[0];
+    // (the class columns stay segment-local: the task lists are rebuilt for every segment)
+    for (int i = 0; i < TILE_COLS; i++) run[i] = tile_cols[(uint64_t)i * n_tiles + t] + (i < COL_CLASS0 ? seg->base[i] : class_off.off[i - COL_CLASS0]);
     first_layer[t] = (uint32_t)run[0];
     walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, flags, t + tile_base, [&](covt_layer& L) {
         uint64_t sz[COVT_NUM_BUFFERS];
@@ -427,28 +448,28 @@ __global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets
         uint4* dst = reinterpret_cast<uint4*>(&layers[run[0]]);
         const uint4* src = reinterpret_cast<const uint4*>(&L);
         for (unsigned i = 0; i < sizeof(covt_layer) / 16; i++) dst[i] = src[i];
-        // the layer's eight decode tasks
-        for (int s = 0; s < COVT_NUM_SLOTS; s++) {
-            const covt_stream_ref& r = L.streams[s];
-            DeviceTask t;
-            t.src_offset = r.byte_offset;
-            t.dst = nullptr;
-            t.byte_length = r.byte_length;
-            t.num_values = r.num_values;
-            t.op = COVT_OP_NONE;
-            t.num_bits = L.num_bits;
-            t.no_shift = (flags & COVT_FLAG_MORTON_NO_SHIFT) ? 1 : 0;
-            t.exact_length = 1;
-            t.status = r.status;
-            t.consumed = 0;
-            t.pad = 0;
-            if (r.encoding != COVT_ENC_ABSENT && L.status != COVT_ERR_BAD_METADATA) {
+        // one decode task per present stream, appended to the dense list of its codec class
+        if (L.status != COVT_ERR_BAD_METADATA) {
+            for (int s = 0; s < COVT_NUM_SLOTS; s++) {
+                const covt_stream_ref& r = L.streams[s];
+                const int c = r.encoding != COVT_ENC_ABSENT ? op_class_of(r.op) : -1;
+                if (c < 0) continue;
                 const uint32_t b = slot_buf[s];
+                DeviceTask t;
+                t.src_offset = r.byte_offset;
                 t.dst = reinterpret_cast<uint8_t*>(bufs.ptr[b]) + L.out[b] * kBufElemSizeDev(b);
-                t.op = r.op;
+                t.byte_length = r.byte_length;
+                t.num_values = r.num_values;
                 if (s == COVT_SLOT_VBUF && L.geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) t.num_values *= 2;
+                t.op = r.op;
+                t.num_bits = L.num_bits;
+                t.no_shift = (flags & COVT_FLAG_MORTON_NO_SHIFT) ? 1 : 0;
+                t.exact_length = 1;
+                t.status = COVT_OK;
+                t.consumed = 0;
+                t.ref = (uint32_t)run[0] * COVT_NUM_SLOTS + (uint32_t)s;
+                tasks[run[COL_CLASS0 + c]++] = t;
             }
-            tasks[(run[0] - layer_base) * COVT_NUM_SLOTS + s] = t;
         }
         run[0] += 1;
     });
@@ -533,19 +554,6 @@ __device__ __forceinline__ uint32_t warp_next_work(uint32_t* counter)
     return __shfl_sync(FULL, v, 0);
 }
 
-__host__ __device__ inline int op_class_of(uint32_t op)
-{
-    switch (op) {
-    case COVT_OP_BYTE_RLE: return CLASS_BYTE_RLE;
-    case COVT_OP_RLE_U32: case COVT_OP_RLE_U64: case COVT_OP_RLE_S64: return CLASS_RLE;
-    case COVT_OP_VARINT_U32: case COVT_OP_VARINT_ZZ: case COVT_OP_VARINT_ZZ_DELTA: case COVT_OP_VARINT_ZZ_DELTA_XY:
-    case COVT_OP_VARINT_DELTA_MORTON: case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: return CLASS_VARINT32;
-    case COVT_OP_VARINT_U64: case COVT_OP_VARINT_ZZ_DELTA_64: return CLASS_VARINT64;
-    case COVT_OP_PFOR_ZZ_DELTA: case COVT_OP_PFOR_ZZ_DELTA_XY: case COVT_OP_PFOR_DELTA_MORTON: return CLASS_PFOR;
-    default: return -1;
-    }
-}
-
 template <int CLASS>
 __device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, StreamOutcome& o)
 {
@@ -597,53 +605,52 @@ __device__ __forceinline__ StreamTask make_stream_task(const uint8_t* blob, cons
 
 template <int CLASS>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uint32_t* work_counter, const SegState* seg)
+k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uint32_t* work_counter, const SegState* seg, covt_layer* layers)
 {
     // batch path: the task count of the current segment lives on the device (the host never learns it in the pipelined mode)
     if (seg && seg->overflow) return;
-    const uint32_t n_tasks = seg ? seg->seg_layers * COVT_NUM_SLOTS : n_tasks_arg;
+    const uint32_t n_tasks = seg ? (uint32_t)seg->seg_total[COL_CLASS0 + CLASS] : n_tasks_arg;
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     uint8_t* wsm = smem + warp * class_warp_smem<CLASS>();
-    // A work group = 256 consecutive task slots = 32 layers x 8 slots in the batch path. Lane L looks at slot s of
-    // "its" layer, so that the 32 lanes hold 32 streams of the SAME kind (same slot) at a time.
-    const uint32_t n_groups = (n_tasks + 255u) / 256u;
+    auto report = [&](uint32_t i, const DeviceTask& d, const StreamOutcome& o) {
+        tasks[i].status = o.status;
+        tasks[i].consumed = o.consumed;
+        if (layers) layers[d.ref / COVT_NUM_SLOTS].streams[d.ref % COVT_NUM_SLOTS].status = o.status;
+    };
+    // A work group = 32 consecutive tasks of this class, handed out dynamically: small sequential streams are decoded by one
+    // thread each (32 at a time), everything else by the whole warp, one stream after the other.
+    const uint32_t n_groups = (n_tasks + 31u) / 32u;
     for (;;) {
         const uint32_t g = warp_next_work(work_counter);
         if (g >= n_groups) break;
-#pragma unroll 1
-        for (uint32_t s = 0; s < COVT_NUM_SLOTS; s++) {
-            const uint32_t mine = g * 256u + lane * COVT_NUM_SLOTS + s;
-            uint32_t op = COVT_OP_NONE, nv = 0, bl = 0;
-            if (mine < n_tasks) { op = tasks[mine].op; nv = tasks[mine].num_values; bl = tasks[mine].byte_length; }
-            const bool match = op_class_of(op) == CLASS;
-            // small sequential streams: one thread each, up to 32 at a time
-            if (match && is_small_task<CLASS>(nv, bl)) {
-                const DeviceTask d = tasks[mine];
-                const StreamTask t = make_stream_task(blob, d);
-                StreamOutcome o = {COVT_OK, 0};
-                if (CLASS == CLASS_BYTE_RLE) thread_byte_rle_stream(t, o);
-                else if (CLASS == CLASS_RLE) {
-                    if (t.op == COVT_OP_RLE_U32) thread_rle_stream<int32_t>(t, false, o);
-                    else thread_rle_stream<int64_t>(t, t.op == COVT_OP_RLE_S64, o);
-                } else if (CLASS == CLASS_VARINT64) thread_varint64_stream(t, t.op == COVT_OP_VARINT_ZZ_DELTA_64, o);
-                tasks[mine].status = o.status;
-                tasks[mine].consumed = o.consumed;
-            }
+        const uint32_t mine = g * 32u + lane;
+        const bool have = mine < n_tasks;
+        DeviceTask d;
+        if (have) d = tasks[mine];
+        const bool small = have && is_small_task<CLASS>(d.num_values, d.byte_length);
+        if (small) {
+            const StreamTask t = make_stream_task(blob, d);
+            StreamOutcome o = {COVT_OK, 0};
+            if (CLASS == CLASS_BYTE_RLE) thread_byte_rle_stream(t, o);
+            else if (CLASS == CLASS_RLE) {
+                if (t.op == COVT_OP_RLE_U32) thread_rle_stream<int32_t>(t, false, o);
+                else thread_rle_stream<int64_t>(t, t.op == COVT_OP_RLE_S64, o);
+            } else if (CLASS == CLASS_VARINT64) thread_varint64_stream(t, t.op == COVT_OP_VARINT_ZZ_DELTA_64, o);
+            report(mine, d, o);
+        }
+        __syncwarp();
+        unsigned todo = __ballot_sync(FULL, have && !small);
+        while (todo) {
+            const int src_lane = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t i = g * 32u + src_lane;
+            const DeviceTask dw = tasks[i];
+            const StreamTask t = make_stream_task(blob, dw);
+            StreamOutcome o;
+            decode_one<CLASS>(t, wsm, o);
             __syncwarp();
-            // everything else: one warp per stream
-            unsigned todo = __ballot_sync(FULL, match && !is_small_task<CLASS>(nv, bl));
-            while (todo) {
-                const int src_lane = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t i = g * 256u + src_lane * COVT_NUM_SLOTS + s;
-                const DeviceTask d = tasks[i];
-                const StreamTask t = make_stream_task(blob, d);
-                StreamOutcome o;
-                decode_one<CLASS>(t, wsm, o);
-                __syncwarp();
-                if (lane == 0) { tasks[i].status = o.status; tasks[i].consumed = o.consumed; }
-            }
+            if (lane == 0) report(i, dw, o);
         }
     }
 }
@@ -652,7 +659,7 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
 // geometry assembly: one warp per layer (after every stream of the batch has been decoded)
 // =================================================================================================
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-k_assemble_layers(covt_layer* all_layers, const DeviceTask* tasks, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter, const SegState* seg)
+k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter, const SegState* seg)
 {
     if (seg->overflow) return;
     covt_layer* layers = all_layers + seg->seg_layer_base;
@@ -665,13 +672,9 @@ k_assemble_layers(covt_layer* all_layers, const DeviceTask* tasks, ResultBuffers
         covt_layer* L = &layers[l];
         uint32_t layer_status = L->status;
         if (layer_status == COVT_ERR_BAD_METADATA) continue;
-        // fold the stream outcomes into the layer record: first error in slot order is the layer's status
+        // the decoders wrote every stream's outcome into the layer record: first error in slot order is the layer's status
         uint32_t st = 0;
-        if (lane < COVT_NUM_SLOTS) {
-            st = tasks[(uint64_t)l * COVT_NUM_SLOTS + lane].status;
-            if (L->streams[lane].encoding != COVT_ENC_ABSENT) L->streams[lane].status = st;
-            else st = 0;
-        }
+        if (lane < COVT_NUM_SLOTS && L->streams[lane].encoding != COVT_ENC_ABSENT) st = L->streams[lane].status;
         const unsigned bad = __ballot_sync(FULL, st != 0);
         if (bad && !layer_status) layer_status = __shfl_sync(FULL, st, __ffs(bad) - 1);
         AsmResult ar = {COVT_OK, 0, 0, 0, 0};
@@ -948,13 +951,12 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
 // finalize: tile status = first layer error (unless the container walk already failed), totals
 // =================================================================================================
 // per segment, before its fill/decode kernels: publish the segment's layer range, check the capacities, clear the work counters
-__global__ void k_seg_begin(SegState* seg, uint32_t* work_counters, uint64_t task_cap_layers)
+__global__ void k_seg_begin(SegState* seg, uint32_t* work_counters)
 {
     const unsigned i = threadIdx.x;
     if (i < 16) work_counters[i] = 0;
     bool over = false;
-    if (i < TILE_COLS) over = seg->base[i] + seg->seg_total[i] > seg->cap[i];
-    if (i == 0 && seg->seg_total[0] > task_cap_layers) over = true;
+    if (i < TILE_COLS) over = (i < COL_CLASS0 ? seg->base[i] : 0ull) + seg->seg_total[i] > seg->cap[i];  // task lists are per segment
     over = __any_sync(FULL, over);
     if (i == 0) {
         if (over) seg->overflow = 1;
@@ -1040,11 +1042,11 @@ cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_
 
 cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                   const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, uint32_t* first_layer, const SegState* seg,
-                                  cudaStream_t st)
+                                  ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer,
+                                  const SegState* seg, cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    k0_fill_layers<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, tile_base, container, tj_fields, tj_layers, flags, tile_cols, bufs, layers, tasks, first_layer, seg);
+    k0_fill_layers<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, tile_base, container, tj_fields, tj_layers, flags, tile_cols, bufs, layers, tasks, class_off, first_layer, seg);
     return cudaGetLastError();
 }
 
@@ -1061,9 +1063,9 @@ const char* op_class_name(int c)
     return c >= 0 && c < NUM_OP_CLASSES ? names[c] : "?";
 }
 
-cudaError_t launch_seg_begin(SegState* seg, uint32_t* work_counters, uint64_t task_cap_layers, cudaStream_t st)
+cudaError_t launch_seg_begin(SegState* seg, uint32_t* work_counters, cudaStream_t st)
 {
-    k_seg_begin<<<1, 32, 0, st>>>(seg, work_counters, task_cap_layers);
+    k_seg_begin<<<1, 32, 0, st>>>(seg, work_counters);
     return cudaGetLastError();
 }
 cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end, cudaStream_t st)
@@ -1074,30 +1076,30 @@ cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end, cudaStream_
 
 // n_tasks: the exact task count (stream path, seg == nullptr) or an upper bound used for the grid size only (batch path)
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
-                                const SegState* seg, int sm_count, int blocks_per_sm, cudaStream_t st)
+                                const SegState* seg, covt_layer* layers, int sm_count, int blocks_per_sm, cudaStream_t st)
 {
     if (!n_tasks) return cudaSuccess;
     // Byte-RLE and RLE never touch the warp stage
     const int smem = (op_class == CLASS_BYTE_RLE || op_class == CLASS_RLE) ? 0 : DEC_WARPS * (op_class == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM);
     const int per_sm = blocks_per_sm > 0 ? blocks_per_sm : (op_class == CLASS_PFOR ? 5 : 12);
-    const int grid = grid_for(sm_count, per_sm, ((uint64_t)n_tasks + 255) / 256, DEC_WARPS);
+    const int grid = grid_for(sm_count, per_sm, ((uint64_t)n_tasks + 31) / 32, DEC_WARPS);
     switch (op_class) {
-    case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
-    case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
-    case CLASS_VARINT32: k_decode_class<CLASS_VARINT32><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
-    case CLASS_VARINT64: k_decode_class<CLASS_VARINT64><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
-    case CLASS_PFOR: k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg); break;
+    case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
+    case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
+    case CLASS_VARINT32: k_decode_class<CLASS_VARINT32><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
+    case CLASS_VARINT64: k_decode_class<CLASS_VARINT64><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
+    case CLASS_PFOR: k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 // n_layers_bound: upper bound of the segment's layer count (grid size only)
-cudaError_t launch_assemble_layers(covt_layer* layers, const DeviceTask* tasks, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
+cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
                                    uint32_t* work_counter, const SegState* seg, int sm_count, cudaStream_t st)
 {
     if (!n_layers_bound) return cudaSuccess;
-    k_assemble_layers<<<grid_for(sm_count, 12, n_layers_bound, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, tasks, bufs, flags, work_counter, seg);
+    k_assemble_layers<<<grid_for(sm_count, 12, n_layers_bound, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
     return cudaGetLastError();
 }
 
