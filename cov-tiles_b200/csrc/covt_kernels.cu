@@ -545,6 +545,7 @@ constexpr int DEC_WARPS = 4;
 constexpr int DEC_WARP_SMEM = WARP_SMEM_BYTES;
 // the FastPFOR kernel stages whole streams: payload window + value stage per warp
 constexpr int PFOR_WARP_SMEM = (PFOR_SMEM_WORDS + 4 + LEAN_STAGE_WORDS) * 4;
+template <int CLASS> __host__ __device__ constexpr uint32_t class_group() { return (CLASS == CLASS_VARINT32 || CLASS == CLASS_PFOR) ? 1u : 32u; }
 template <int CLASS> __host__ __device__ constexpr int class_warp_smem() { return CLASS == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM; }
 
 __device__ __forceinline__ uint32_t warp_next_work(uint32_t* counter)
@@ -618,14 +619,16 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
         tasks[i].consumed = o.consumed;
         if (layers) layers[d.ref / COVT_NUM_SLOTS].streams[d.ref % COVT_NUM_SLOTS].status = o.status;
     };
-    // A work group = 32 consecutive tasks of this class, handed out dynamically: small sequential streams are decoded by one
-    // thread each (32 at a time), everything else by the whole warp, one stream after the other.
-    const uint32_t n_groups = (n_tasks + 31u) / 32u;
+    // A work group = GROUP consecutive tasks of this class, handed out dynamically: small sequential streams are decoded by one
+    // thread each (32 at a time), everything else by the whole warp, one stream after the other. The classes that always take
+    // a whole warp per stream get one stream per work item (ncu: with 32 streams per item k_decode_pfor ran 11 warps per SM).
+    constexpr uint32_t GROUP = class_group<CLASS>();
+    const uint32_t n_groups = (n_tasks + GROUP - 1u) / GROUP;
     for (;;) {
         const uint32_t g = warp_next_work(work_counter);
         if (g >= n_groups) break;
-        const uint32_t mine = g * 32u + lane;
-        const bool have = mine < n_tasks;
+        const uint32_t mine = g * GROUP + lane;
+        const bool have = lane < GROUP && mine < n_tasks;
         DeviceTask d;
         if (have) d = tasks[mine];
         const bool small = have && is_small_task<CLASS>(d.num_values, d.byte_length);
@@ -644,7 +647,7 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
         while (todo) {
             const int src_lane = __ffs(todo) - 1;
             todo &= todo - 1;
-            const uint32_t i = g * 32u + src_lane;
+            const uint32_t i = g * GROUP + src_lane;
             const DeviceTask dw = tasks[i];
             const StreamTask t = make_stream_task(blob, dw);
             StreamOutcome o;
@@ -1082,7 +1085,8 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
     // Byte-RLE and RLE never touch the warp stage
     const int smem = (op_class == CLASS_BYTE_RLE || op_class == CLASS_RLE) ? 0 : DEC_WARPS * (op_class == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM);
     const int per_sm = blocks_per_sm > 0 ? blocks_per_sm : (op_class == CLASS_PFOR ? 5 : 12);
-    const int grid = grid_for(sm_count, per_sm, ((uint64_t)n_tasks + 31) / 32, DEC_WARPS);
+    const uint32_t group = (op_class == CLASS_VARINT32 || op_class == CLASS_PFOR) ? 1u : 32u;
+    const int grid = grid_for(sm_count, per_sm, ((uint64_t)n_tasks + group - 1) / group, DEC_WARPS);
     switch (op_class) {
     case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
     case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
