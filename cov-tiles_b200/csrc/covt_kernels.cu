@@ -1,13 +1,15 @@
 // covt_kernels.cu — the sm_100a kernels of the COVT batch decoder and their launchers.
 //
-//   k0_scan_tiles / k0_fill_layers : device-side container walk (gen-2b, gen-3) -> covt_layer table
-//                                    (CovtParser.decodeLayerMetadata, J/decoder/CovtParser.java:574-652)
+//   k0_scan_tiles / k0_fill_layers : device-side container walk (gen-2b, gen-3) -> covt_layer table + one dense decode-task
+//                                    list per codec class (CovtParser.decodeLayerMetadata, J/decoder/CovtParser.java:574-652;
+//                                    SURVEY §A.1)
 //   scan_*                         : result layout = exclusive prefix sums of 16-byte-rounded slice sizes
-//   k_decode_layers                : one warp per layer: every stream of the layer, then the assembler
-//                                    (CovtParser.decodeGeometryColumn :392-511, decodedIds :552-572, convertGeometryColumn :135-274)
-//   k_decode_tasks                 : one warp per stream request (the static codecs of DecodingUtils.java)
-//   k1_varint_stream               : multi-CTA single-pass decode of one large varint stream with a decoupled
-//                                    look-back over (count, sumEven, sumOdd) (DecodingUtils.java:55-112,394-409)
+//   k_seg_begin / k_seg_end        : running totals of a batch decoded in segments (upload of segment i+1 overlaps decode of i)
+//   k_decode_class<C>              : one kernel per codec class (Byte-RLE, RLE, 32-bit varint, 64-bit varint, FastPFOR):
+//                                    the static codecs of DecodingUtils.java, a thread or a warp per stream
+//   k_assemble_layers              : one warp per layer (CovtParser.convertGeometryColumn :135-274)
+//   k1a_aggregate / k1b_decode     : large varint streams of the stream API in 512-byte chunks over the whole GPU, with a
+//                                    segmented scan over (count, sumEven, sumOdd) in between (DecodingUtils.java:55-112,394-409)
 //   k_finalize                     : per-tile status + totals
 #include "covt_assemble.cuh"
 #include "covt_internal.h"

@@ -2,8 +2,8 @@
 //
 // Each function is executed by ONE full warp with uniform control flow and decodes one stream
 // described by a StreamTask. They replace, one to one, the static codecs of the reference
-// J/decoder/DecodingUtils.java (cited per function). Large delta-varint streams take the
-// multi-CTA decoupled-look-back kernel in k1_varint_stream.cu instead.
+// J/decoder/DecodingUtils.java (cited per function). Large delta-varint streams of the stream API take the
+// multi-CTA two-pass kernels (k1a_aggregate / k1b_decode in covt_kernels.cu) instead.
 #pragma once
 #include "covt_device.cuh"
 #include "covt_varint.cuh"
@@ -17,11 +17,6 @@ constexpr int WARP_SMEM_BYTES = STAGE_WORDS * 8;
 // 32-bit varints: DecodingUtils.decodeVarint :35, decodeZigZagVarint :46, decodeZigZagDeltaVarint :55,
 // decodeZigZagDeltaVarintCoordinates :95, decodeDeltaVarintMortonCodes :394
 // =================================================================================================
-template <bool VB>
-struct ChunkCut {
-    uint32_t cut_pos;  // 1-based byte position inside the chunk window of the terminator of value #limit, 0 if none
-};
-
 // Position (1-based, in chunk-window bytes) right after the `limit`-th emitted value of this chunk, or 0.
 __device__ __forceinline__ uint32_t chunk_cut_position(uint32_t emit, uint32_t lane_excl, uint32_t limit)
 {

@@ -23,8 +23,18 @@ ncu_k1)
   $CMD > gpurun_out/plain_k1.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k "regex:k1a_|k1b_" -s 4 -c 2 -f -o gpurun_out/prof_k1 $CMD > gpurun_out/ncu_k1.log 2>&1
   echo "ncu_k1_exit=$?"; tail -3 gpurun_out/ncu_k1.log;;
+traffic)
+  # dram bytes per launch of the dominant kernels at the bench's own sizes (profiles/traffic.json)
+  CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+  timeout 600 $CMD > gpurun_out/plain_traffic_tiles.log 2>&1 && \
+  timeout 1500 ncu --set full --clock-control none -k "regex:k_assemble_layers" -s 3 -c 1 -f -o gpurun_out/prof_traffic_tiles $CMD > gpurun_out/ncu_traffic_tiles.log 2>&1
+  echo "traffic_tiles_exit=$?"; tail -2 gpurun_out/ncu_traffic_tiles.log
+  CMD="python bench.py --workload varint1g --steps 1 --warmup 3 --no-cpu-baseline"
+  timeout 600 $CMD > gpurun_out/plain_traffic_k1.log 2>&1 && \
+  timeout 1500 ncu --set full --clock-control none -k "regex:k1a_|k1b_" -s 6 -c 2 -f -o gpurun_out/prof_traffic_k1 $CMD > gpurun_out/ncu_traffic_k1.log 2>&1
+  echo "traffic_k1_exit=$?"; tail -2 gpurun_out/ncu_traffic_k1.log;;
 launches)
-  CMD="python bench.py --tiles 65536 --steps 2 --warmup 3 --no-cpu-baseline"
+  CMD="python bench.py --tiles 65536 --steps 1 --warmup 3 --no-cpu-baseline"
   $CMD > gpurun_out/plain_launches.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
   echo "launches_exit=$?";;
