@@ -419,6 +419,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
     uint32_t *d_tj = nullptr, *d_counter = nullptr;
     SegState* d_seg = nullptr;
     DeviceTask* d_tasks = nullptr;
+    uint32_t* d_queue = nullptr;  // large streams handed from pass 1 to pass 2 of a codec class (same layout as d_tasks)
     uint32_t max_seg_tiles = 1;
     for (uint32_t i = 0; i < S; i++) max_seg_tiles = std::max(max_seg_tiles, seg_starts[i + 1] - seg_starts[i]);
     const uint32_t nb = (max_seg_tiles + 255) / 256;
@@ -430,6 +431,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         dev_free(ctx, d_tj);
         dev_free(ctx, d_counter);
         dev_free(ctx, d_tasks);
+        dev_free(ctx, d_queue);
         dev_free(ctx, d_seg);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -524,6 +526,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             if (ctx->debug) fprintf(stderr, "[covt] result arena %.2f GB allocated in %.2f ms (segments %u)\n", arena_bytes / 1e9, now_ms() - t_alloc0, S);
             CKR(dev_alloc(ctx, &R->d_layers, hs->cap[0]));
             CKR(dev_alloc(ctx, &d_tasks, task_total));
+            CKR(dev_alloc(ctx, &d_queue, task_total));
             CKR(cudaMemcpyAsync(d_seg->cap, hs->cap, sizeof(hs->cap), cudaMemcpyHostToDevice, st));
         }
         CKR(launch_seg_begin(d_seg, d_counter, st));
@@ -536,8 +539,8 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         if (prof.on || ctx->serial_classes) {
             for (int c = 0; c < NUM_OP_CLASSES; c++) {
                 prof.begin(op_class_name(c), 0);
-                CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_off.off[c], (uint32_t)std::min<uint64_t>(task_cap[c], 0xffffff00ull), d_counter + c, d_seg,
-                                        R->d_layers, ctx->sm_count, 0, st));
+                CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_off.off[c], (uint32_t)std::min<uint64_t>(task_cap[c], 0xffffff00ull), d_counter + 3 * c,
+                                        d_queue + class_off.off[c], d_seg, R->d_layers, ctx->sm_count, 0, st));
                 prof.end();
             }
         } else {
@@ -549,18 +552,18 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             for (int i = 0; i < NUM_OP_CLASSES; i++) {
                 const int c = order[i];
                 CKR(cudaStreamWaitEvent(ctx->class_stream[c], ctx->ev_fork, 0));
-                CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_off.off[c], (uint32_t)std::min<uint64_t>(task_cap[c], 0xffffff00ull), d_counter + c, d_seg,
-                                        R->d_layers, ctx->sm_count, share[c], ctx->class_stream[c]));
+                CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_off.off[c], (uint32_t)std::min<uint64_t>(task_cap[c], 0xffffff00ull), d_counter + 3 * c,
+                                        d_queue + class_off.off[c], d_seg, R->d_layers, ctx->sm_count, share[c], ctx->class_stream[c]));
                 CKR(cudaEventRecord(ctx->ev_join[c], ctx->class_stream[c]));
                 CKR(cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
             }
         }
         // ---- geometry assembly ----
         prof.begin("k_assemble_layers", 0);
-        CKR(launch_assemble_layers(R->d_layers, (uint32_t)std::min<uint64_t>(layers_per_seg_bound, 0xffffff00ull), rb, flags, d_counter + 8, d_seg, ctx->sm_count, st));
+        CKR(launch_assemble_layers(R->d_layers, (uint32_t)std::min<uint64_t>(layers_per_seg_bound, 0xffffff00ull), rb, flags, d_counter + 15, d_seg, ctx->sm_count, st));
         prof.end();
         CKR(launch_seg_end(d_seg, sg + 1 == S ? R->d_first_layer + n_tiles : nullptr, st));
-        launches += 9;
+        launches += 12;
     }
     if (n_tiles) {
         prof.begin("k_finalize", 0);
@@ -825,6 +828,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     ChunkState* d_block_states = nullptr;
     ChunkState* d_states = nullptr;
     uint32_t* d_counter = nullptr;
+    uint32_t* d_queue = nullptr;
     int32_t rc = COVT_OK;
     auto cleanup_tmp = [&]() {
         dev_free(ctx, d_tasks);
@@ -832,6 +836,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
         dev_free(ctx, d_block_states);
         dev_free(ctx, d_states);
         dev_free(ctx, d_counter);
+        dev_free(ctx, d_queue);
     };
 #define CKR(call)                                                                                     \
     do {                                                                                              \
@@ -853,6 +858,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     CKR(dev_alloc_bytes(ctx, &R->arena, arena + 64));
     R->bufs[COVT_BUF_STREAM_ARENA] = R->arena;
     CKR(dev_alloc(ctx, &d_tasks, n));
+    CKR(dev_alloc(ctx, &d_queue, n));
     CKR(dev_alloc(ctx, &d_counter, 16));
     // dense task list per codec class (the class kernels walk their own list); tasks taken by the large-stream kernel and
     // rejected requests go last. ref = index of the covt_stream_desc the outcome belongs to.
@@ -900,7 +906,8 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
         if (!class_count[c]) continue;
         prof.begin(op_class_name(c), class_alg[c]);
-        CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_first[c], class_count[c], d_counter + c, nullptr, nullptr, ctx->sm_count, 0, st));
+        CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_first[c], class_count[c], d_counter + 3 * c, d_queue + class_first[c], nullptr, nullptr,
+                                ctx->sm_count, 0, st));
         prof.end();
         launches++;
     }

@@ -64,6 +64,7 @@ struct BigStream {
 // after the scan the exclusive prefix of the chunk inside its stream (count, running x, running y).
 // flags: bit 0 = first chunk of its stream, bit 1 = x/y interleaved sums
 struct __align__(16) ChunkState { uint32_t count; int32_t a, b; uint32_t flags; };
+constexpr int WORK_COUNTERS = 16;  // 3 per codec class (pass-1 ticket, queue length, pass-2 ticket) + the assembler's ticket
 constexpr int FINAL_TOTALS = 9;  // k_finalize: vertices, payload, output bytes, 5 codec classes, assembler
 constexpr int K1_WARPS = 8;
 constexpr int K1_SCAN_BLOCK = 1024;
@@ -75,17 +76,17 @@ cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offse
                                  const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols,
                                  uint32_t* tile_status, cudaStream_t st);
 cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_t* block_sums, uint64_t* totals, cudaStream_t st);
-cudaError_t launch_seg_begin(SegState* seg, uint32_t* work_counters /*[16]*/, cudaStream_t st);
+cudaError_t launch_seg_begin(SegState* seg, uint32_t* work_counters /*[WORK_COUNTERS]*/, cudaStream_t st);
 cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end /*nullable*/, cudaStream_t st);
 cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                   const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
                                   ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer,
                                   const SegState* seg, cudaStream_t st);
-// one codec class over ITS dense task list; work_counter must be zero. seg != nullptr (batch path): the task count is
-// seg->seg_total[COL_CLASS0 + class], n_tasks only bounds the grid, and every stream's status is also written to
-// layers[ref / 8].streams[ref % 8].
-// blocks_per_sm: 0 = fill the GPU with this kernel alone; > 0 = its share when the class kernels run concurrently
-cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
+// One codec class over ITS dense task list (pass 1: small streams by threads; pass 2: queued large streams, a warp each).
+// counters: 3 zeroed words (see covt_kernels.cu); big_queue: n_tasks words. seg != nullptr (batch path): the task count is
+// seg->seg_total[COL_CLASS0 + class], n_tasks only bounds the grids, and every stream's status is also written to
+// layers[ref / 8].streams[ref % 8]. blocks_per_sm: 0 = fill the GPU with this kernel alone.
+cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* counters, uint32_t* big_queue,
                                 const SegState* seg, covt_layer* layers, int sm_count, int blocks_per_sm, cudaStream_t st);
 const char* op_class_name(int op_class);
 cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,

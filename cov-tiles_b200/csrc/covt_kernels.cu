@@ -606,9 +606,15 @@ __device__ __forceinline__ StreamTask make_stream_task(const uint8_t* blob, cons
     return t;
 }
 
+// Pass 1 of a codec class. A work group = GROUP consecutive tasks of the class, handed out dynamically. Small sequential
+// streams are decoded right here by one thread each (32 at a time). Streams that need a whole warp are decoded here only by
+// the classes that always take a warp per stream (GROUP == 1); the other classes push them onto big_queue for pass 2 — a warp
+// that decoded the large streams of its own group one after the other made the whole kernel wait for the unluckiest group
+// (fixture sweep: k_decode_rle 7.2 ms for 2.3 GB of output, the 60 000-value id streams of one tile land in one group).
 template <int CLASS>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uint32_t* work_counter, const SegState* seg, covt_layer* layers)
+k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uint32_t* work_counter, const SegState* seg, covt_layer* layers,
+               uint32_t* big_queue, uint32_t* big_count)
 {
     // batch path: the task count of the current segment lives on the device (the host never learns it in the pipelined mode)
     if (seg && seg->overflow) return;
@@ -621,9 +627,6 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
         tasks[i].consumed = o.consumed;
         if (layers) layers[d.ref / COVT_NUM_SLOTS].streams[d.ref % COVT_NUM_SLOTS].status = o.status;
     };
-    // A work group = GROUP consecutive tasks of this class, handed out dynamically: small sequential streams are decoded by one
-    // thread each (32 at a time), everything else by the whole warp, one stream after the other. The classes that always take
-    // a whole warp per stream get one stream per work item (ncu: with 32 streams per item k_decode_pfor ran 11 warps per SM).
     constexpr uint32_t GROUP = class_group<CLASS>();
     const uint32_t n_groups = (n_tasks + GROUP - 1u) / GROUP;
     for (;;) {
@@ -646,16 +649,54 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
         }
         __syncwarp();
         unsigned todo = __ballot_sync(FULL, have && !small);
-        while (todo) {
-            const int src_lane = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t i = g * GROUP + src_lane;
-            const DeviceTask dw = tasks[i];
-            const StreamTask t = make_stream_task(blob, dw);
-            StreamOutcome o;
-            decode_one<CLASS>(t, wsm, o);
-            __syncwarp();
-            if (lane == 0) report(i, dw, o);
+        if (GROUP > 1) {
+            // hand the large streams of this group to pass 2
+            if (todo) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(big_count, (uint32_t)__popc(todo));
+                base = __shfl_sync(FULL, base, 0);
+                if ((todo >> lane) & 1u) big_queue[base + __popc(todo & ((1u << lane) - 1u))] = mine;
+            }
+        } else {
+            while (todo) {
+                const int src_lane = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t i = g * GROUP + src_lane;
+                const DeviceTask dw = tasks[i];
+                const StreamTask t = make_stream_task(blob, dw);
+                StreamOutcome o;
+                decode_one<CLASS>(t, wsm, o);
+                __syncwarp();
+                if (lane == 0) report(i, dw, o);
+            }
+        }
+    }
+}
+
+// Pass 2: one warp per queued large stream
+template <int CLASS>
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counter, const SegState* seg, covt_layer* layers,
+                   const uint32_t* big_queue, const uint32_t* big_count)
+{
+    if (seg && seg->overflow) return;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    uint8_t* wsm = smem + warp * class_warp_smem<CLASS>();
+    const uint32_t n = *big_count;
+    for (;;) {
+        const uint32_t q = warp_next_work(work_counter);
+        if (q >= n) break;
+        const uint32_t i = big_queue[q];
+        const DeviceTask dw = tasks[i];
+        const StreamTask t = make_stream_task(blob, dw);
+        StreamOutcome o;
+        decode_one<CLASS>(t, wsm, o);
+        __syncwarp();
+        if (lane == 0) {
+            tasks[i].status = o.status;
+            tasks[i].consumed = o.consumed;
+            if (layers) layers[dw.ref / COVT_NUM_SLOTS].streams[dw.ref % COVT_NUM_SLOTS].status = o.status;
         }
     }
 }
@@ -959,7 +1000,7 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
 __global__ void k_seg_begin(SegState* seg, uint32_t* work_counters)
 {
     const unsigned i = threadIdx.x;
-    if (i < 16) work_counters[i] = 0;
+    if (i < WORK_COUNTERS) work_counters[i] = 0;
     bool over = false;
     if (i < TILE_COLS) over = (i < COL_CLASS0 ? seg->base[i] : 0ull) + seg->seg_total[i] > seg->cap[i];  // task lists are per segment
     over = __any_sync(FULL, over);
@@ -1079,8 +1120,10 @@ cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end, cudaStream_
     return cudaGetLastError();
 }
 
-// n_tasks: the exact task count (stream path, seg == nullptr) or an upper bound used for the grid size only (batch path)
-cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* work_counter,
+// n_tasks: the exact task count (stream path, seg == nullptr) or an upper bound used for the grid size only (batch path).
+// counters: [0] group ticket of pass 1, [1] queue length, [2] ticket of pass 2 (all zero before the launch).
+// big_queue: n_tasks words (unused by the classes that decode every stream with a warp in pass 1).
+cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* counters, uint32_t* big_queue,
                                 const SegState* seg, covt_layer* layers, int sm_count, int blocks_per_sm, cudaStream_t st)
 {
     if (!n_tasks) return cudaSuccess;
@@ -1089,12 +1132,23 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
     const int per_sm = blocks_per_sm > 0 ? blocks_per_sm : (op_class == CLASS_PFOR ? 5 : 12);
     const uint32_t group = (op_class == CLASS_VARINT32 || op_class == CLASS_PFOR) ? 1u : 32u;
     const int grid = grid_for(sm_count, per_sm, ((uint64_t)n_tasks + group - 1) / group, DEC_WARPS);
+    const int grid_big = grid_for(sm_count, per_sm, n_tasks, DEC_WARPS);
+    uint32_t *c0 = counters, *c1 = counters + 1, *c2 = counters + 2;
     switch (op_class) {
-    case CLASS_BYTE_RLE: k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
-    case CLASS_RLE: k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
-    case CLASS_VARINT32: k_decode_class<CLASS_VARINT32><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
-    case CLASS_VARINT64: k_decode_class<CLASS_VARINT64><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
-    case CLASS_PFOR: k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, work_counter, seg, layers); break;
+    case CLASS_BYTE_RLE:
+        k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, big_queue, c1);
+        k_decode_class_big<CLASS_BYTE_RLE><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
+        break;
+    case CLASS_RLE:
+        k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, big_queue, c1);
+        k_decode_class_big<CLASS_RLE><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
+        break;
+    case CLASS_VARINT32: k_decode_class<CLASS_VARINT32><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, nullptr, nullptr); break;
+    case CLASS_VARINT64:
+        k_decode_class<CLASS_VARINT64><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, big_queue, c1);
+        k_decode_class_big<CLASS_VARINT64><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
+        break;
+    case CLASS_PFOR: k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, nullptr, nullptr); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
