@@ -547,6 +547,7 @@ constexpr int DEC_WARPS = 4;
 constexpr int DEC_WARP_SMEM = WARP_SMEM_BYTES;
 // the FastPFOR kernel stages whole streams: payload window + value stage per warp
 constexpr int PFOR_WARP_SMEM = (PFOR_SMEM_WORDS + 4 + LEAN_STAGE_WORDS) * 4;
+constexpr int PFOR_BIG_WARP_SMEM = (404 + LEAN_STAGE_WORDS) * 4;  // pass 2: block window + container window + value stage (warp_pfor_stream)
 template <int CLASS> __host__ __device__ constexpr uint32_t class_group() { return (CLASS == CLASS_VARINT32 || CLASS == CLASS_PFOR) ? 1u : 32u; }
 template <int CLASS> __host__ __device__ constexpr int class_warp_smem() { return CLASS == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM; }
 
@@ -557,7 +558,7 @@ __device__ __forceinline__ uint32_t warp_next_work(uint32_t* counter)
     return __shfl_sync(FULL, v, 0);
 }
 
-template <int CLASS>
+template <int CLASS, bool BIG = false>
 __device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, StreamOutcome& o)
 {
     uint32_t* stage = reinterpret_cast<uint32_t*>(wsm);
@@ -578,7 +579,7 @@ __device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, Strea
         else warp_varint64_stream<true>(t, reinterpret_cast<uint64_t*>(wsm), o);
     } else {
         if (t.op == COVT_OP_PFOR_ZZ_DELTA_XY && (t.num_values & 1u)) { o.status = COVT_ERR_COUNT_MISMATCH; return; }
-        if (t.byte_length / 4u <= PFOR_SMEM_WORDS) warp_pfor_stream_smem(t, stage, stage + PFOR_SMEM_WORDS + 4, o, post_kind_of_op(t.op));
+        if (!BIG) warp_pfor_stream_smem(t, stage, stage + PFOR_SMEM_WORDS + 4, o, post_kind_of_op(t.op));
         else warp_pfor_stream(t, stage, o, post_kind_of_op(t.op));  // larger than the window: read the page through global memory
     }
 }
@@ -657,17 +658,19 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
                 base = __shfl_sync(FULL, base, 0);
                 if ((todo >> lane) & 1u) big_queue[base + __popc(todo & ((1u << lane) - 1u))] = mine;
             }
-        } else {
-            while (todo) {
-                const int src_lane = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t i = g * GROUP + src_lane;
-                const DeviceTask dw = tasks[i];
+        } else if (todo) {
+            // GROUP == 1: lane 0 holds the stream
+            const DeviceTask dw = tasks[g];
+            if (CLASS == CLASS_PFOR && dw.byte_length / 4u > PFOR_SMEM_WORDS) {
+                // too large for the shared-memory window: pass 2 walks it through global memory, and needs so little shared
+                // memory that twice as many warps fit an SM
+                if (lane == 0) big_queue[atomicAdd(big_count, 1u)] = g;
+            } else {
                 const StreamTask t = make_stream_task(blob, dw);
                 StreamOutcome o;
                 decode_one<CLASS>(t, wsm, o);
                 __syncwarp();
-                if (lane == 0) report(i, dw, o);
+                if (lane == 0) report(g, dw, o);
             }
         }
     }
@@ -682,7 +685,7 @@ k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counte
     if (seg && seg->overflow) return;
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t* wsm = smem + warp * class_warp_smem<CLASS>();
+    uint8_t* wsm = smem + warp * (CLASS == CLASS_PFOR ? PFOR_BIG_WARP_SMEM : class_warp_smem<CLASS>());
     const uint32_t n = *big_count;
     for (;;) {
         const uint32_t q = warp_next_work(work_counter);
@@ -691,7 +694,7 @@ k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counte
         const DeviceTask dw = tasks[i];
         const StreamTask t = make_stream_task(blob, dw);
         StreamOutcome o;
-        decode_one<CLASS>(t, wsm, o);
+        decode_one<CLASS, true>(t, wsm, o);
         __syncwarp();
         if (lane == 0) {
             tasks[i].status = o.status;
@@ -1148,7 +1151,11 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
         k_decode_class<CLASS_VARINT64><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, big_queue, c1);
         k_decode_class_big<CLASS_VARINT64><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
         break;
-    case CLASS_PFOR: k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, nullptr, nullptr); break;
+    case CLASS_PFOR:
+        k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, big_queue, c1);
+        k_decode_class_big<CLASS_PFOR><<<grid_for(sm_count, 12, n_tasks, DEC_WARPS), DEC_WARPS * 32, DEC_WARPS * PFOR_BIG_WARP_SMEM, st>>>(blob, tasks, c2, seg, layers,
+                                                                                                                                      big_queue, c1);
+        break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
