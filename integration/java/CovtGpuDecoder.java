@@ -1,37 +1,9 @@
-# INTEGRATION — dropping `libcovt_b200.so` under the reference Java decoder
-
-The reference decode path is two static entry points (`CovtParser.decodeCovt(byte[], TileJson)`,
-`evaluation/java/src/main/java/com/covt/decoder/CovtParser.java:53`) and the static stream codecs of
-`DecodingUtils` (`.../decoder/DecodingUtils.java:35-444`). The drop-in is a C-ABI shared library
-(`include/covt_b200.h`: `extern "C"`, plain pointers and sizes, no callbacks, no structs by value) that a Java host
-binds through **Panama FFM** (`java.lang.foreign`, JDK 22+) with no JNI-side logic.
-
-This image has no JDK (`javac: command not found`), so the Java stub below is shipped **un-built**; the same symbols are
-exercised by the Python `ctypes` binding (`cov-tiles_b200/__init__.py`) in every `-m gpu` test, and
-`tests/test_abi_host.py` checks on CPU that the library exports every declared symbol and that the struct layouts below match
-what a C compiler sees.
-
-## Entry points and what they replace
-
-| C symbol | Replaces (reference file:line) |
-|---|---|
-| `covt_create(device, &ctx)` / `covt_destroy` | — (one context per GPU; the reference is stateless static code) |
-| `covt_decode_batch(ctx, blob, tile_offsets, n_tiles, container, tilejson, flags, &res)` | `CovtParser.decodeCovt` `CovtParser.java:53`, batched over tiles; `container` selects the gen-3 grammar of `decodeLayerMetadata` `:574-652` or the gen-2b grammar of the committed fixtures |
-| `covt_batch_upload` + `covt_batch_decode` + `covt_batch_free` | the same in two steps (H2D timed apart from the device-resident decode) |
-| `covt_decode_streams(ctx, blob, len, descs, n, flags, &res)` | `DecodingUtils.decodeVarint :35`, `decodeZigZagVarint :46`, `decodeZigZagDeltaVarint :55`, `decodeZigZagDeltaVarintCoordinates :95`, `decodeRle :257`, `decodeByteRle :275/:290`, `decodeFastPfor128ZigZagDelta :316`, `decodeFastPfor128DeltaCoordinates :349`, `decodeDeltaVarintMortonCodes :394`, `decodeFastPfor128DeltaMortonCodes :411` — one `covt_stream_desc` per call; `bytes_consumed` is how far the Java `IntWrapper pos` advances |
-| `covt_resolve_op(streamType, encoding, columnType, flags)` | the `if/else` dispatch of `CovtParser.decodeGeometryColumn :405-510` and `decodedIds :552-572` |
-| `covt_result_layers / _tile_status / _buffer / _read / _timing / _kernel_times / _free` | the returned `List<Layer>` / `GeometryColumn` record `:29-36` (GeoArrow-style buffers instead of JTS objects) |
-| `covt_host_register / _unregister` | page-locks the caller's `MemorySegment` so uploads run at PCIe rate |
-| `covt_partition_tiles` | batch scheduler: tile ranges per GPU |
-| `covt_trim` | — (returns the device blocks a context parks between calls) |
-| `covt_last_error`, `covt_abi_version` | exceptions → status codes + message |
-
-Enum ordinals (`covt_stream_encoding`, `covt_stream_type`, `covt_column_type`, `covt_column_data_type`,
-`covt_geometry_type`) are the Java ordinals, so `StreamMetadata.streamEncoding().ordinal()` can be passed straight through.
-
-## The Java binding a maintainer would add (`evaluation/java/src/main/java/com/covt/decoder/CovtGpuDecoder.java`; also shipped as `integration/java/CovtGpuDecoder.java`)
-
-```java
+/*
+ * CovtGpuDecoder.java — Panama FFM (java.lang.foreign, JDK 22+) binding of libcovt_b200.so for the reference's Java tree
+ * (evaluation/java/src/main/java/com/covt/decoder/). SHIPPED UN-BUILT: this image has no JDK (javac: command not found); the
+ * same C symbols are exercised by the Python ctypes binding in every -m gpu test, and tests/test_abi_host.py checks that the
+ * library exports every symbol bound here and that the struct layouts match what a C compiler sees. See INTEGRATION.md.
+ */
 package com.covt.decoder;
 
 import java.lang.foreign.*;
@@ -152,28 +124,3 @@ public final class CovtGpuDecoder implements AutoCloseable {
     @Override public void close() { try { DESTROY.invokeExact(ctx); } catch (Throwable t) { throw sneaky(t); } }
     private static RuntimeException sneaky(Throwable t) { return t instanceof RuntimeException r ? r : new RuntimeException(t); }
 }
-```
-
-Call-site change in the reference (`CovtParserTest.java:55`, `BingCovtDemo.java:171`): replace
-`CovtParser.decodeCovt(covtTile, tileJson)` by `gpu.decodeCovt(new byte[][]{covtTile}, fieldCounts, CONTAINER_GEN3)` and build
-JTS geometries, if wanted, from the four offset buffers + `coords` (`A_GEOM_OFFSETS → A_PART_OFFSETS → A_RING_OFFSETS →
-A_COORDS`, layer-local offsets; `geometry_types[f]` says how many levels feature *f* uses).
-
-## Error mapping
-
-| Reference | Library |
-|---|---|
-| `IllegalArgumentException` "… encoding not supported" (`CovtParser.java:425-427,442-444,…,571`) | stream/layer status `COVT_ERR_UNSUPPORTED_ENCODING` |
-| `IllegalArgumentException` geometry type (`CovtParser.java:268-270`) | `COVT_ERR_UNSUPPORTED_GEOMETRY` |
-| `ArrayIndexOutOfBoundsException` on truncated input | `COVT_ERR_TRUNCATED` (never reads outside the tile) |
-| first column not id/geometry (`CovtParser.java:67-69`) | `COVT_ERR_BAD_METADATA` |
-| (silent) varint longer than the Java reader's 4-byte cap (`DecodingUtils.java:157-186`) | stream status `COVT_ERR_VARINT_OVERLONG` (such streams are never produced by the reference encoder; the values of a flagged stream are unspecified) |
-
-## Python mirror (what the tests call)
-
-```python
-import covt_loader; covt = covt_loader.load()          # package directory cov-tiles_b200/
-layers = covt.CovtParser.decodeCovt(tile_bytes, tileJson=None, container=covt.CONTAINER_GEN2B)
-pos = [0]; vals = covt.DecodingUtils.decodeZigZagDeltaVarint(buf, pos, numValues)   # DecodingUtils.java:55
-dec = covt.Decoder(0); res = dec.decode_batch(blob, tile_offsets)                    # batched, device-resident buffers
-```

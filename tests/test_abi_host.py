@@ -112,3 +112,13 @@ def test_partition_tiles(covt):
     assert s[0] == 0 and s[-1] == 3 and np.all(np.diff(s.astype(np.int64)) >= 0)
     s = covt.partition_tiles(np.array([0], np.uint64), 4)
     assert list(s) == [0, 0, 0, 0, 0]
+
+
+def test_java_binding_names_every_symbol_it_binds(covt):
+    """integration/java/CovtGpuDecoder.java (un-built: no JDK here) binds only symbols the library exports."""
+    src = open(os.path.join(ROOT, "integration", "java", "CovtGpuDecoder.java")).read()
+    bound = set(re.findall(r'h\("(covt_[a-z0-9_]+)"', src))
+    assert len(bound) >= 10
+    for name in bound:
+        assert hasattr(covt.lib(), name), name
+    assert "sizeof(covt_layer)" in src and str(C.sizeof(covt.abi.Layer)) in src

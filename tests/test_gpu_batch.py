@@ -250,3 +250,30 @@ def test_pipelined_segments_equal_one_shot(covt, oracle, gen, fixtures, monkeypa
         res2.free()
     finally:
         dec.close()
+
+
+def test_partitioned_decode_and_trim(covt, oracle, gen):
+    """The batch scheduler's per-rank slices (cov-tiles_b200/scheduler.py), decoded one after the other on this GPU, cover the
+    batch exactly; covt_trim hands the parked device blocks back without disturbing later calls."""
+    abi = covt.abi
+    from cov_tiles_b200 import scheduler
+    dec = covt.Decoder(0)
+    try:
+        blob, offs, truth = gen.tiles(900, 1500, gen.default_params())
+        whole = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT)
+        verts = 0
+        for rank in range(3):
+            res, t0 = scheduler.decode_partitioned(dec, blob, offs, rank, 3)
+            sub, sub_offs, t0b = scheduler.rank_slice(blob, offs, rank, 3)
+            assert t0 == t0b
+            ref = oracle.decode_batch(sub, sub_offs, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT)
+            util.compare_results(abi, res, ref)
+            rows = whole.layers[(whole.layers["tile"] >= t0) & (whole.layers["tile"] < t0 + len(sub_offs) - 1)]
+            assert np.array_equal(rows["n_vertices"], res.layers["n_vertices"])
+            verts += int(res.layers["n_vertices"].sum())
+            res.free()
+            if rank == 1:
+                dec.trim()
+        assert verts == truth["vertices"]
+    finally:
+        dec.close()
