@@ -400,7 +400,9 @@ def run_gpu(args, rank, world, local_rank):
             achieved = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
             traffic = None
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(top[0])
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+                size_now = {"tiles_per_gpu": n_tiles, "payload_bytes_per_gpu": payload}.get(tj.get("size_key"))
+                traffic = tj.get(top[0]) if tj.get("size") == size_now else None  # measured under ncu at exactly this size
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
