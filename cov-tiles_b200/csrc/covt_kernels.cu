@@ -613,7 +613,7 @@ __device__ __forceinline__ StreamTask make_stream_task(const uint8_t* blob, cons
 // that decoded the large streams of its own group one after the other made the whole kernel wait for the unluckiest group
 // (fixture sweep: k_decode_rle 7.2 ms for 2.3 GB of output, the 60 000-value id streams of one tile land in one group).
 template <int CLASS>
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+__global__ void __launch_bounds__(DEC_WARPS * 32, CLASS == CLASS_VARINT32 ? 8 : 1)
 k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uint32_t* work_counter, const SegState* seg, covt_layer* layers,
                uint32_t* big_queue, uint32_t* big_count)
 {
@@ -1132,7 +1132,7 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
     if (!n_tasks) return cudaSuccess;
     // Byte-RLE and RLE never touch the warp stage
     const int smem = (op_class == CLASS_BYTE_RLE || op_class == CLASS_RLE) ? 0 : DEC_WARPS * (op_class == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM);
-    const int per_sm = blocks_per_sm > 0 ? blocks_per_sm : (op_class == CLASS_PFOR ? 5 : 12);
+    const int per_sm = blocks_per_sm > 0 ? blocks_per_sm : (op_class == CLASS_PFOR ? 8 : 12);
     const uint32_t group = (op_class == CLASS_VARINT32 || op_class == CLASS_PFOR) ? 1u : 32u;
     const int grid = grid_for(sm_count, per_sm, ((uint64_t)n_tasks + group - 1) / group, DEC_WARPS);
     const int grid_big = grid_for(sm_count, per_sm, n_tasks, DEC_WARPS);

@@ -662,7 +662,7 @@ finish:
 // byte container, the packed blocks and the exception arrays — which the format scatters over the page — are all read from
 // shared memory instead of through dependent unaligned global loads, and zigzag/delta/Morton run striped (covt_varint.cuh).
 // =================================================================================================
-constexpr uint32_t PFOR_SMEM_WORDS = 2048;  // 8 KiB of payload per warp
+constexpr uint32_t PFOR_SMEM_WORDS = 1024;  // 4 KiB of payload per warp
 
 __device__ __forceinline__ uint32_t sm_unpack(const uint32_t* sw, uint32_t w0, uint32_t q, uint32_t k)
 {
