@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — COVT tile-batch decode on N B200s (BASELINE.json metric: compressed GB/s & Mvertices/s).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tiles|fixtures|varint1g|index] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tiles|fixtures|varint1g] [--impl reference]
 
 One "step" = one pass of the hot path (container walk, every stream codec, geometry assembly) over one batch.
 Default workload = BASELINE config 5: 1 048 576 synthetic mixed-geometry gen-2b tiles per GPU, seed = tile index
@@ -55,9 +55,11 @@ def make_tiles(first_tile, n_tiles, container=0):
     blob, offs, truth = G.tiles(first_tile, n_tiles, G.default_params(container=container))
     log("[bench] generated %d tiles (%.1f MB) in %.1f s" % (n_tiles, len(blob) / 1e6, time.time() - t0))
     try:
-        blob.tofile(key + ".blob")
-        offs.tofile(key + ".offs")
-        json.dump({"bytes": int(len(blob)), "truth": truth}, open(key + ".json", "w"))
+        import shutil
+        if shutil.disk_usage(CACHE_DIR).free > 4 * len(blob) + (8 << 30):  # never fill the box's disk (or a RAM-backed /tmp)
+            blob.tofile(key + ".blob")
+            offs.tofile(key + ".offs")
+            json.dump({"bytes": int(len(blob)), "truth": truth}, open(key + ".json", "w"))
     except Exception as e:  # a full disk must not fail the bench
         log("[bench] cache write failed:", e)
     return blob, offs, truth
@@ -243,8 +245,10 @@ def build_workload(args, rank, for_cpu=False):
             blob, nvals = G.varint_stream(args.stream_bytes, seed=0xC0717 + rank)
             log("[bench] generated a %d-byte varint stream in %.1f s" % (len(blob), time.time() - t0))
             try:
-                blob.tofile(key + ".blob")
-                json.dump({"n": nvals}, open(key + ".json", "w"))
+                import shutil
+                if shutil.disk_usage(CACHE_DIR).free > 4 * len(blob) + (8 << 30):
+                    blob.tofile(key + ".blob")
+                    json.dump({"n": nvals}, open(key + ".json", "w"))
             except Exception as e:
                 log("[bench] cache write failed:", e)
         offs = np.array([0, len(blob)], dtype=np.uint64)
