@@ -501,7 +501,8 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             }
             for (int c = 0; c < COL_CLASS0; c++)
                 hs->cap[c] = S > 1 ? (uint64_t)((double)ctx->h_totals[c] * scale) + 65536 : ctx->h_totals[c];
-            if (hs->cap[0] > 0xfffffff0ull) { cleanup_tmp(); covt_result_free(R); return fail(ctx, COVT_ERR_INVALID_ARG, "too many layers in one batch"); }
+            if (hs->cap[0] > 0x1ffffff0ull)  // DeviceTask::ref = layer * 8 + slot must fit 32 bits
+                { cleanup_tmp(); covt_result_free(R); return fail(ctx, COVT_ERR_INVALID_ARG, "too many layers in one batch"); }
             // the task lists are per segment: a segment that needs more entries than extrapolated counts as an overflow too
             const double seg_scale = S > 1 ? (double)max_seg_tiles / nt * 1.25 : 1.0;
             uint64_t task_total = 0;

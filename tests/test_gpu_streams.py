@@ -1,11 +1,12 @@
 """GPU parity tests of the stream path (covt_decode_streams = the static codecs of DecodingUtils.java)
 against the CPU oracle: every op, lengths straddling the 16/32/256/512/65 536 boundaries, every byte alignment,
-the reference's known-answer vectors, and large streams through the multi-CTA look-back kernel."""
+the reference's known-answer vectors, and large streams through the multi-CTA two-pass kernels."""
 import ctypes as C
 
 import numpy as np
 import pytest
 
+import util
 import vectors
 
 pytestmark = pytest.mark.gpu
@@ -209,3 +210,52 @@ def test_config3_shape_roundtrip(covt, gen, decoder):
     assert st == 0 and len(got) == n
     zz = gen.encode_zigzag_delta_coordinates(got).astype(np.int64) & 0xFFFFFFFF
     assert np.array_equal(gen.encode_varints(zz), enc)
+
+
+def test_config4_index_buffers_of_fixture_polygons(covt, oracle, gen, decoder, fixtures):
+    """BASELINE config 4: the polygon layers of the zoom 5-8 fixtures with a synthetic INDEX_BUFFER per layer — fan triangulation
+    (v0, v0+i, v0+i+1) of every ring, FAST_PFOR_DELTA_ZIG_ZAG, stream type 12 (an EXTENSION: the reference defines IndexBuffer in
+    README prose only, parity unpinned beyond the oracle) — decoded by the FastPFOR routine through the descriptor dispatch."""
+    abi = covt.abi
+    tiles = [(n, b) for n, b in fixtures if n.startswith(("omt/5_", "omt/6_", "omt/7_", "omt/8_"))]
+    assert len(tiles) >= 8
+    blob, offs = util.concat_tiles([b for _, b in tiles])
+    ref = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_ID_DVZZ_IS_RLE | abi.FLAG_MORTON_NO_SHIFT)
+    payload = bytearray()
+    wanted = []
+    for L in ref.layers:
+        if L["status"] != 0 or L["n_rings"] == 0:
+            continue
+        types = ref.buffer(abi.BUF_S_GEOMETRY_TYPES)[int(L["out"][abi.BUF_S_GEOMETRY_TYPES]):][:int(L["num_features"])]
+        if not np.isin(types, (abi.GT_POLYGON, abi.GT_MULTIPOLYGON)).all():
+            continue
+        ring = ref.buffer(abi.BUF_A_RING_OFFSETS)[int(L["out"][abi.BUF_A_RING_OFFSETS]):][:int(L["n_rings"]) + 1].astype(np.int64)
+        idx = []
+        for r in range(len(ring) - 1):
+            v0, n = ring[r], ring[r + 1] - ring[r]
+            if n >= 3:
+                i = np.arange(1, n - 1)
+                idx.append(np.stack([np.full_like(i, v0), v0 + i, v0 + i + 1], axis=1).ravel())
+        if not idx:
+            continue
+        idx = np.concatenate(idx).astype(np.int32)
+        enc = gen.encode_fastpfor(idx, zigzag=True, delta=True)
+        wanted.append((len(payload), len(enc), idx))
+        payload += bytes(enc)
+    assert len(wanted) >= 8 and sum(len(w[2]) for w in wanted) > 100000
+    payload = np.frombuffer(bytes(payload) + bytes(64), dtype=np.uint8)
+    descs = (abi.StreamDesc * len(wanted))()
+    for i, (off, ln, idx) in enumerate(wanted):
+        descs[i] = abi.StreamDesc(byte_offset=off, byte_length=ln, num_values=len(idx), stream_type=abi.ST_INDEX_BUFFER,
+                                  encoding=abi.ENC_FAST_PFOR_DELTA_ZIG_ZAG, column_type=abi.CT_PLAIN)
+    res = decoder.decode_streams(payload, descs, abi.FLAG_DEFAULT)
+    arena = res.buffer(abi.BUF_STREAM_ARENA)
+    for i, (off, ln, idx) in enumerate(wanted):
+        d = descs[i]
+        assert d.status == 0 and d.out_count == len(idx) and d.bytes_consumed == ln
+        got = arena[d.out_offset:d.out_offset + 4 * d.out_count].view(np.int32)
+        assert np.array_equal(got, idx), i
+        want, wst, _ = oracle.decode_stream(payload, 0, byte_offset=off, byte_length=ln, num_values=len(idx),
+                                            stream_type=abi.ST_INDEX_BUFFER, encoding=abi.ENC_FAST_PFOR_DELTA_ZIG_ZAG)
+        assert wst == 0 and np.array_equal(want, idx)
+    res.free()
