@@ -262,6 +262,29 @@ def build_workload(args, rank, for_cpu=False):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs (and, by first touch, the host memory) of the NUMA node its GPU hangs off: with 8 ranks
+    uploading at once, pinned buffers on the wrong socket halve the host->device rate."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -270,6 +293,7 @@ def run_gpu(args, rank, world, local_rank):
     covt = covt_loader.load()
     abi = covt.abi
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dec = covt.Decoder(local_rank)  # raises without the CUDA library / device: no CPU fallback
@@ -440,6 +464,8 @@ def run_gpu(args, rank, world, local_rank):
             cpu = {"value": pb / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port", "mvertices_per_s": vx / dt / 1e6,
                    "sample": "one pass over the same %d tiles (%.2f GB payload, %.1f s); C restatement of the reference Java "
                              "decoder (JVM unavailable), -O2, pthreads" % (n_tiles, pb / 1e9, dt)}
+        if numa_node is not None:
+            cfg["host_binding"] = "each rank bound to the NUMA node of its GPU"
         cfg.update({"container": "gen-2b", "flags": "CLOSE_RINGS", "payload_bytes_per_gpu": payload, "vertices_per_gpu": verts,
                     "output_bytes_per_gpu": outb, "bad_tiles": bad_all})
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
