@@ -564,7 +564,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         CKR(launch_assemble_layers(R->d_layers, (uint32_t)std::min<uint64_t>(layers_per_seg_bound, 0xffffff00ull), rb, flags, d_counter + 15, d_seg, ctx->sm_count, st));
         prof.end();
         CKR(launch_seg_end(d_seg, sg + 1 == S ? R->d_first_layer + n_tiles : nullptr, st));
-        launches += 12;
+        launches += 13;  // k_seg_begin, k0_fill_layers, 5 codec kernels + 4 second passes, k_assemble_layers, k_seg_end
     }
     if (n_tiles) {
         prof.begin("k_finalize", 0);
@@ -910,7 +910,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
         CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_first[c], class_count[c], d_counter + 3 * c, d_queue + class_first[c], nullptr, nullptr,
                                 ctx->sm_count, 0, st));
         prof.end();
-        launches++;
+        launches += c == CLASS_VARINT32 ? 1 : 2;  // pass 1 (+ pass 2 over the queued large streams)
     }
     CKR(cudaEventRecord(ev1, st));
     if (n) CKR(cudaMemcpyAsync(sorted.data(), d_tasks, (uint64_t)n * sizeof(DeviceTask), cudaMemcpyDeviceToHost, st));
