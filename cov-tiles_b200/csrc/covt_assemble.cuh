@@ -6,7 +6,7 @@
 // Semantics = what the encoder wrote (CovtConverter.java:580-639,689-758): topology
 // streams hold COUNTS; which streams a feature consumes depends on its type. The sequential cursor
 // walk of the reference becomes three flat passes of warp scans: features -> parts, parts -> rings,
-// rings -> vertices (see warp_assemble).
+// rings -> vertices, 128 items per trip (see warp_assemble).
 #pragma once
 #include "covt_device.cuh"
 
@@ -24,33 +24,25 @@ struct LayerIO {
 };
 struct AsmResult { uint32_t status, n_parts, n_rings, n_vertices, n_coords; };
 
-constexpr int ASM_SMEM_WORDS = 3 * 33;
+constexpr int ASM_IPL = 4;                          // items (features / parts / rings) per lane and trip
+constexpr int ASM_TRIP = 32 * ASM_IPL;              // items per trip
+constexpr int ASM_SMEM_WORDS = 3 * (ASM_TRIP + 1);  // per warp
 
-// last index i in [0,32) with arr[i] <= key (arr nondecreasing, arr[0] == 0)
-__device__ __forceinline__ uint32_t search32(const uint32_t* arr, uint32_t key)
+// last index i in [0, ASM_TRIP) with arr[i] <= key (arr nondecreasing, arr[0] == 0, ASM_TRIP + 1 entries)
+__device__ __forceinline__ uint32_t search_trip(const uint32_t* arr, uint32_t key)
 {
     uint32_t lo = 0;
 #pragma unroll
-    for (int step = 16; step >= 1; step >>= 1)
+    for (int step = ASM_TRIP / 2; step >= 1; step >>= 1)
         if (arr[lo + step] <= key) lo += step;
     return lo;
 }
 
-// exclusive warp scan of small counts: when every lane holds 0 or 1 (the common case: one part per feature, one ring per
-// part) a ballot + popc replaces the 5-step shuffle scan
-__device__ __forceinline__ uint32_t warp_exclusive_scan_small(uint32_t v, uint32_t& total)
-{
-    const unsigned nz = __ballot_sync(FULL, v != 0u), big = __ballot_sync(FULL, v > 1u);
-    if (!big) {
-        total = (uint32_t)__popc(nz);
-        return (uint32_t)__popc(nz & ((1u << lane_id()) - 1u));
-    }
-    return warp_exclusive_scan(v, total);
-}
-
-// The reference walks features with three running cursors (CovtParser.java:135-274). Here the walk is three flat passes, each
-// 32 items per trip with one or two warp scans — features -> parts, parts -> rings, rings -> vertices — instead of a nested
-// cascade that paid ~550 warp instructions per 32 features however simple they were (ncu: 2420 per layer of 49 features):
+// The reference walks features with three running cursors (CovtParser.java:135-274). Here the walk is three flat passes —
+// features -> parts, parts -> rings, rings -> vertices — each covering ASM_TRIP = 128 items per trip, FOUR CONSECUTIVE items per
+// lane: the four count loads of a lane are independent (memory-level parallelism), a lane-local prefix plus ONE warp scan per
+// quantity replaces per-32 scans, and a layer of F features needs F/128 dependent trips per level instead of F/32 (the
+// assembler waits on its dependent loads, not on issue slots).
 //   level 1 writes a_geom and, as scratch in a_part[p + 1], the geometry type of every part's feature;
 //   level 2 reads that, writes the final a_part and, as scratch in a_ring[r + 1], the vertex count of every non-polygon ring
 //           (>= 0) or -1 for a polygon ring (its count comes from the ring stream);
@@ -58,10 +50,9 @@ __device__ __forceinline__ uint32_t warp_exclusive_scan_small(uint32_t v, uint32
 __device__ __forceinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmResult& res)
 {
     const unsigned lane = lane_id();
-    const unsigned lt = (1u << lane) - 1u;
-    uint32_t* r_start = sm;        // [33] first output vertex of the ring, relative to the block of 32 rings
-    uint32_t* r_src = sm + 33;     // [32] first source vertex of the ring
-    uint32_t* r_n = sm + 66;       // [32] source vertex count of the ring
+    uint32_t* r_start = sm;                      // [ASM_TRIP + 1] first output vertex of the ring, relative to the trip
+    uint32_t* r_src = sm + (ASM_TRIP + 1);       // [ASM_TRIP] first source vertex of the ring
+    uint32_t* r_n = sm + 2 * (ASM_TRIP + 1);     // [ASM_TRIP] source vertex count of the ring
 
     const bool ice = io.voff != nullptr;
     const uint64_t src_total = ice ? io.n_voff : io.vbuf_ints / 2;
@@ -77,94 +68,193 @@ __device__ __forceinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, A
     // ---- level 1: features -> parts ------------------------------------------------------------
     {
         uint32_t gc = 0;  // geometry_offsets cursor
-        for (uint32_t f0 = 0; f0 < io.F; f0 += 32) {
-            const uint32_t f = f0 + lane;
-            const bool fvalid = f < io.F;
-            const uint32_t t = fvalid ? (uint32_t)__ldg(io.types + f) : (uint32_t)COVT_GT_POINT;
-            ASM_CHECK(fvalid && (t == COVT_GT_MULTIPOINT || t > COVT_GT_MULTIPOLYGON), COVT_ERR_UNSUPPORTED_GEOMETRY);
-            const bool uses_g = fvalid && (t == COVT_GT_MULTILINESTRING || t == COVT_GT_MULTIPOLYGON);
-            const unsigned gmask = __ballot_sync(FULL, uses_g);
-            const uint32_t gidx = gc + (uint32_t)__popc(gmask & lt);
-            ASM_CHECK(uses_g && gidx >= io.n_geom, COVT_ERR_TOPOLOGY);
-            int32_t nparts_s = fvalid ? 1 : 0;
-            if (uses_g) nparts_s = __ldg(io.geom + gidx);
-            ASM_CHECK(nparts_s < 0 || (uint32_t)nparts_s > io.cap_parts, COVT_ERR_TOPOLOGY);
-            const uint32_t nparts = (uint32_t)nparts_s;
-            uint32_t tot;
-            const uint32_t excl = warp_exclusive_scan_small(nparts, tot);
+        for (uint32_t f0 = 0; f0 < io.F; f0 += ASM_TRIP) {
+            const uint32_t fb = f0 + ASM_IPL * lane;
+            // four types in one word (the slice is 16-byte aligned and padded)
+            const uint32_t tw = fb < io.F ? __ldg(reinterpret_cast<const uint32_t*>(io.types + fb)) : 0u;
+            uint32_t t[ASM_IPL], nparts[ASM_IPL];
+            bool valid[ASM_IPL], uses_g[ASM_IPL];
+            bool bad_type = false;
+            uint32_t n_g = 0;
+#pragma unroll
+            for (int i = 0; i < ASM_IPL; i++) {
+                valid[i] = fb + i < io.F;
+                t[i] = (tw >> (8 * i)) & 0xffu;
+                bad_type = bad_type || (valid[i] && (t[i] == COVT_GT_MULTIPOINT || t[i] > COVT_GT_MULTIPOLYGON));
+                uses_g[i] = valid[i] && (t[i] == COVT_GT_MULTILINESTRING || t[i] == COVT_GT_MULTIPOLYGON);
+                n_g += uses_g[i] ? 1u : 0u;
+            }
+            ASM_CHECK(bad_type, COVT_ERR_UNSUPPORTED_GEOMETRY);
+            uint32_t tot_g = 0, gidx = gc;
+            bool err = false;
+            if (__any_sync(FULL, n_g != 0u)) {  // multi-geometries in this trip: their part counts come from geometry_offsets
+                gidx = gc + warp_exclusive_scan(n_g, tot_g);
+            }
+#pragma unroll
+            for (int i = 0; i < ASM_IPL; i++) {
+                int32_t np = valid[i] ? 1 : 0;
+                if (uses_g[i]) {
+                    if (gidx >= io.n_geom) err = true;
+                    else np = __ldg(io.geom + gidx);
+                    gidx++;
+                }
+                if (np < 0 || (uint32_t)np > io.cap_parts) { err = true; np = 0; }
+                nparts[i] = (uint32_t)np;
+            }
+            ASM_CHECK(err, COVT_ERR_TOPOLOGY);
+            const uint32_t lane_sum = nparts[0] + nparts[1] + nparts[2] + nparts[3];
+            uint32_t tot, excl;
+            if (tot_g == 0) {  // one part per feature: the prefix is the feature index
+                excl = min(fb, io.F) - f0;
+                tot = min((uint32_t)ASM_TRIP, io.F - f0);
+            } else if (__any_sync(FULL, (nparts[0] | nparts[1] | nparts[2] | nparts[3]) >= (1u << 24))) {  // 32-bit sums could wrap
+                uint64_t t64;
+                const uint64_t e64 = warp_exclusive_scan_u64((uint64_t)nparts[0] + nparts[1] + nparts[2] + nparts[3], t64);
+                ASM_CHECK((uint64_t)p + t64 > io.cap_parts, COVT_ERR_TOPOLOGY);
+                excl = (uint32_t)e64;
+                tot = (uint32_t)t64;
+            } else {
+                excl = warp_exclusive_scan(lane_sum, tot);
+            }
             ASM_CHECK((uint64_t)p + tot > io.cap_parts, COVT_ERR_TOPOLOGY);
-            if (fvalid) io.a_geom[f + 1] = (int32_t)(p + excl + nparts);
-            for (uint32_t k = 0; k < nparts; k++) io.a_part[p + excl + k + 1] = (int32_t)t;  // scratch: the part's geometry type
+            uint32_t pw = p + excl;
+#pragma unroll
+            for (int i = 0; i < ASM_IPL; i++) {
+                for (uint32_t k = 0; k < nparts[i]; k++) io.a_part[pw + k + 1] = (int32_t)t[i];  // scratch: the part's geometry type
+                pw += nparts[i];
+                if (valid[i]) io.a_geom[fb + i + 1] = (int32_t)pw;
+            }
             p += tot;
-            gc += (uint32_t)__popc(gmask);
+            gc += tot_g;
         }
     }
     __syncwarp();
     // ---- level 2: parts -> rings ----------------------------------------------------------------
     {
         uint32_t pc = 0;  // part_offsets cursor
-        for (uint32_t k0 = 0; k0 < p; k0 += 32) {
-            const uint32_t k = k0 + lane;
-            const bool pvalid = k < p;
-            const uint32_t tt = pvalid ? (uint32_t)io.a_part[k + 1] : (uint32_t)COVT_GT_POINT;
-            const bool uses_p = pvalid && tt != COVT_GT_POINT;
-            const unsigned pmask = __ballot_sync(FULL, uses_p);
-            const uint32_t pe = pc + (uint32_t)__popc(pmask & lt);
-            ASM_CHECK(uses_p && pe >= io.n_part, COVT_ERR_TOPOLOGY);
-            const int32_t cnt = uses_p ? __ldg(io.part + pe) : 1;
-            const bool poly = pvalid && (tt == COVT_GT_POLYGON || tt == COVT_GT_MULTIPOLYGON);
-            ASM_CHECK(pvalid && (cnt < 0 || (poly && (uint32_t)cnt > io.cap_rings)), COVT_ERR_TOPOLOGY);
-            const uint32_t nrings = pvalid ? (poly ? (uint32_t)cnt : 1u) : 0u;
-            uint32_t tot;
-            const uint32_t excl = warp_exclusive_scan_small(nrings, tot);
+        for (uint32_t k0 = 0; k0 < p; k0 += ASM_TRIP) {
+            const uint32_t kb = k0 + ASM_IPL * lane;
+            uint32_t tt[ASM_IPL], nrings[ASM_IPL];
+            int32_t cnt[ASM_IPL];
+            bool valid[ASM_IPL], poly[ASM_IPL];
+            uint32_t n_p = 0;
+#pragma unroll
+            for (int i = 0; i < ASM_IPL; i++) {
+                valid[i] = kb + i < p;
+                tt[i] = valid[i] ? (uint32_t)io.a_part[kb + i + 1] : (uint32_t)COVT_GT_POINT;
+                n_p += (valid[i] && tt[i] != COVT_GT_POINT) ? 1u : 0u;
+            }
+            uint32_t tot_p;
+            uint32_t pe = pc + warp_exclusive_scan(n_p, tot_p);
+            bool err = false;
+#pragma unroll
+            for (int i = 0; i < ASM_IPL; i++) {
+                cnt[i] = 1;
+                if (valid[i] && tt[i] != COVT_GT_POINT) {
+                    if (pe >= io.n_part) err = true;
+                    else cnt[i] = __ldg(io.part + pe);
+                    pe++;
+                }
+                poly[i] = valid[i] && (tt[i] == COVT_GT_POLYGON || tt[i] == COVT_GT_MULTIPOLYGON);
+                if (valid[i] && (cnt[i] < 0 || (poly[i] && (uint32_t)cnt[i] > io.cap_rings))) { err = true; cnt[i] = 0; }
+                nrings[i] = valid[i] ? (poly[i] ? (uint32_t)cnt[i] : 1u) : 0u;
+            }
+            ASM_CHECK(err, COVT_ERR_TOPOLOGY);
+            const uint32_t lane_sum = nrings[0] + nrings[1] + nrings[2] + nrings[3];
+            uint32_t tot, excl;
+            if (__any_sync(FULL, (nrings[0] | nrings[1] | nrings[2] | nrings[3]) >= (1u << 24))) {  // 32-bit sums could wrap
+                uint64_t t64;
+                const uint64_t e64 = warp_exclusive_scan_u64((uint64_t)nrings[0] + nrings[1] + nrings[2] + nrings[3], t64);
+                ASM_CHECK((uint64_t)r + t64 > io.cap_rings, COVT_ERR_TOPOLOGY);
+                excl = (uint32_t)e64;
+                tot = (uint32_t)t64;
+            } else {
+                excl = warp_exclusive_scan(lane_sum, tot);
+            }
             ASM_CHECK((uint64_t)r + tot > io.cap_rings, COVT_ERR_TOPOLOGY);
-            // scratch: vertex count of a line / point ring, -1 for a polygon ring
-            for (uint32_t j = 0; j < nrings; j++) io.a_ring[r + excl + j + 1] = poly ? -1 : cnt;
-            if (pvalid) io.a_part[k + 1] = (int32_t)(r + excl + nrings);
+            uint32_t rw = r + excl;
+#pragma unroll
+            for (int i = 0; i < ASM_IPL; i++) {
+                // scratch: vertex count of a line / point ring, -1 for a polygon ring
+                for (uint32_t j = 0; j < nrings[i]; j++) io.a_ring[rw + j + 1] = poly[i] ? -1 : cnt[i];
+                rw += nrings[i];
+                if (valid[i]) io.a_part[kb + i + 1] = (int32_t)rw;
+            }
             r += tot;
-            pc += (uint32_t)__popc(pmask);
+            pc += tot_p;
         }
     }
     __syncwarp();
     // ---- level 3: rings -> vertices ---------------------------------------------------------------
     {
         uint32_t rc = 0;  // ring_offsets cursor
-        for (uint32_t q0 = 0; q0 < r; q0 += 32) {
-            const uint32_t q = q0 + lane;
-            const bool rvalid = q < r;
-            const int32_t info = rvalid ? io.a_ring[q + 1] : 0;
-            const bool is_poly = rvalid && info < 0;
-            const unsigned rmask = __ballot_sync(FULL, is_poly);
-            const uint32_t re = rc + (uint32_t)__popc(rmask & lt);
-            ASM_CHECK(is_poly && re >= io.n_ring, COVT_ERR_TOPOLOGY);
-            const int32_t nv_s = is_poly ? __ldg(io.ring + re) : info;
-            ASM_CHECK(rvalid && nv_s < 0, COVT_ERR_TOPOLOGY);
-            const uint32_t nv = rvalid ? (uint32_t)nv_s : 0u;
-            const uint32_t outn = nv + ((is_poly && io.close_rings && nv > 0) ? 1u : 0u);
+        for (uint32_t q0 = 0; q0 < r; q0 += ASM_TRIP) {
+            const uint32_t qb = q0 + ASM_IPL * lane;
+            int32_t info[ASM_IPL];
+            uint32_t nv[ASM_IPL], outn[ASM_IPL];
+            bool valid[ASM_IPL], is_poly[ASM_IPL];
+            uint32_t n_r = 0;
+#pragma unroll
+            for (int i = 0; i < ASM_IPL; i++) {
+                valid[i] = qb + i < r;
+                info[i] = valid[i] ? io.a_ring[qb + i + 1] : 0;
+                is_poly[i] = valid[i] && info[i] < 0;
+                n_r += is_poly[i] ? 1u : 0u;
+            }
+            uint32_t tot_r = 0, re = rc;
+            if (__any_sync(FULL, n_r != 0u)) re = rc + warp_exclusive_scan(n_r, tot_r);
+            bool err = false;
+            bool huge = false;
+            uint32_t lane_sv = 0, lane_ov = 0;
+#pragma unroll
+            for (int i = 0; i < ASM_IPL; i++) {
+                int32_t n = info[i];
+                if (is_poly[i]) {
+                    n = 0;
+                    if (re >= io.n_ring) err = true;
+                    else n = __ldg(io.ring + re);
+                    re++;
+                }
+                if (valid[i] && n < 0) { err = true; n = 0; }
+                nv[i] = valid[i] ? (uint32_t)n : 0u;
+                outn[i] = nv[i] + ((is_poly[i] && io.close_rings && nv[i] > 0) ? 1u : 0u);
+                huge = huge || nv[i] >= (1u << 24);
+                lane_sv += nv[i];
+                lane_ov += outn[i];
+            }
+            ASM_CHECK(err, COVT_ERR_TOPOLOGY);
             uint64_t tot_sv, tot_ov, sv_excl, ov_excl;
-            if (__any_sync(FULL, nv >= (1u << 26))) {
-                sv_excl = warp_exclusive_scan_u64(nv, tot_sv);
-                ov_excl = warp_exclusive_scan_u64(outn, tot_ov);
-            } else {  // 32 counts below 2^26 cannot overflow 32 bits; closing vertices: one per closed ring
-                uint32_t t1;
-                const unsigned closed = __ballot_sync(FULL, outn != nv);
-                sv_excl = warp_exclusive_scan(nv, t1);
-                ov_excl = sv_excl + (uint32_t)__popc(closed & lt);
+            if (__any_sync(FULL, huge)) {
+                sv_excl = warp_exclusive_scan_u64((uint64_t)nv[0] + nv[1] + nv[2] + nv[3], tot_sv);
+                ov_excl = warp_exclusive_scan_u64((uint64_t)outn[0] + outn[1] + outn[2] + outn[3], tot_ov);
+            } else {  // 128 counts below 2^24 cannot overflow 32 bits
+                uint32_t t1, t2;
+                sv_excl = warp_exclusive_scan(lane_sv, t1);
+                ov_excl = warp_exclusive_scan(lane_ov, t2);
                 tot_sv = t1;
-                tot_ov = (uint64_t)t1 + (uint32_t)__popc(closed);
+                tot_ov = t2;
             }
             ASM_CHECK(s + tot_sv > src_total || v + tot_ov > io.cap_coords || tot_ov > 0xffffffffull, COVT_ERR_TOPOLOGY);
-            if (rvalid) io.a_ring[q + 1] = (int32_t)(v + ov_excl + outn);
             __syncwarp();
-            r_start[lane] = (uint32_t)ov_excl;
-            r_src[lane] = (uint32_t)(s + sv_excl);
-            r_n[lane] = nv;
+            {
+                uint64_t so = s + sv_excl, oo = ov_excl;
+#pragma unroll
+                for (int i = 0; i < ASM_IPL; i++) {
+                    r_start[ASM_IPL * lane + i] = (uint32_t)oo;
+                    r_src[ASM_IPL * lane + i] = (uint32_t)so;
+                    r_n[ASM_IPL * lane + i] = nv[i];
+                    so += nv[i];
+                    oo += outn[i];
+                    if (valid[i]) io.a_ring[qb + i + 1] = (int32_t)(v + oo);
+                }
+                if (lane == 31) r_start[ASM_TRIP] = (uint32_t)tot_ov;
+            }
             __syncwarp();
             const uint32_t n_out = (uint32_t)tot_ov;
             bool oob = false;
-            // 4 batches of 32 output vertices per trip: the index loads, then the coordinate gathers, are issued
-            // back to back so that their latencies overlap (the decoded streams were written by earlier kernels,
-            // so the read-only path is safe here)
+            // 4 batches of 32 output vertices per trip of the copy loop: the index loads, then the coordinate gathers, are
+            // issued back to back so that their latencies overlap (the decoded streams were written by earlier kernels, so the
+            // read-only path is safe here)
             for (uint32_t u0 = 0; u0 < n_out; u0 += 128) {
                 uint64_t si[4];
                 bool ok[4];
@@ -174,7 +264,7 @@ __device__ __forceinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, A
                     ok[b4] = u < n_out;
                     si[b4] = 0;
                     if (ok[b4]) {
-                        const uint32_t ri = search32(r_start, u);
+                        const uint32_t ri = search_trip(r_start, u);
                         const uint32_t i = u - r_start[ri];
                         si[b4] = (uint64_t)r_src[ri] + (i == r_n[ri] ? 0u : i);  // i == n: the closing vertex = vertex 0 of the ring
                     }
@@ -199,7 +289,7 @@ __device__ __forceinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, A
             ASM_CHECK(oob, COVT_ERR_TOPOLOGY);
             v += tot_ov;
             s += tot_sv;
-            rc += (uint32_t)__popc(rmask);
+            rc += tot_r;
         }
     }
 done:
