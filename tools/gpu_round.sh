@@ -16,7 +16,7 @@ fixtures)
 ncu_layers)
   CMD="python bench.py --tiles 65536 --steps 1 --warmup 3 --no-cpu-baseline"
   $CMD > gpurun_out/plain_layers.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k "regex:k_decode_class|k_assemble_layers|k0_" -s 16 -c 8 -f -o gpurun_out/prof_layers $CMD > gpurun_out/ncu_layers.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "regex:k_decode_class|k_assemble_layers|k0_|k_finalize|scan_" -s 54 -c 18 -f -o gpurun_out/prof_layers $CMD > gpurun_out/ncu_layers.log 2>&1
   echo "ncu_layers_exit=$?"; tail -3 gpurun_out/ncu_layers.log;;
 ncu_k1)
   CMD="python bench.py --workload varint1g --stream-bytes 268435456 --steps 1 --warmup 3 --no-cpu-baseline"
