@@ -26,17 +26,8 @@ struct AsmResult { uint32_t status, n_parts, n_rings, n_vertices, n_coords; };
 
 constexpr int ASM_IPL = 4;                          // items (features / parts / rings) per lane and trip
 constexpr int ASM_TRIP = 32 * ASM_IPL;              // items per trip
-constexpr int ASM_SMEM_WORDS = 3 * (ASM_TRIP + 1);  // per warp
-
-// last index i in [0, ASM_TRIP) with arr[i] <= key (arr nondecreasing, arr[0] == 0, ASM_TRIP + 1 entries)
-__device__ __forceinline__ uint32_t search_trip(const uint32_t* arr, uint32_t key)
-{
-    uint32_t lo = 0;
-#pragma unroll
-    for (int step = ASM_TRIP / 2; step >= 1; step >>= 1)
-        if (arr[lo + step] <= key) lo += step;
-    return lo;
-}
+constexpr int ASM_WINDOW = 1024;                    // output vertices per ring-mark window (32 mask words)
+constexpr int ASM_SMEM_WORDS = 3 * ASM_TRIP + 32;   // per warp: three ring tables + the mask words
 
 // The reference walks features with three running cursors (CovtParser.java:135-274). Here the walk is three flat passes —
 // features -> parts, parts -> rings, rings -> vertices — each covering ASM_TRIP = 128 items per trip, FOUR CONSECUTIVE items per
@@ -50,9 +41,10 @@ __device__ __forceinline__ uint32_t search_trip(const uint32_t* arr, uint32_t ke
 __device__ __forceinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, AsmResult& res)
 {
     const unsigned lane = lane_id();
-    uint32_t* r_start = sm;                      // [ASM_TRIP + 1] first output vertex of the ring, relative to the trip
-    uint32_t* r_src = sm + (ASM_TRIP + 1);       // [ASM_TRIP] first source vertex of the ring
-    uint32_t* r_n = sm + 2 * (ASM_TRIP + 1);     // [ASM_TRIP] source vertex count of the ring
+    uint32_t* r_start = sm;                // [ASM_TRIP] first output vertex of the k-th vertex-owning ring, relative to the trip
+    uint32_t* r_src = sm + ASM_TRIP;       // [ASM_TRIP] its first source vertex
+    uint32_t* r_n = sm + 2 * ASM_TRIP;     // [ASM_TRIP] its source vertex count
+    uint32_t* marks = sm + 3 * ASM_TRIP;   // [32] ring-start bits of the current window of output vertices
 
     const bool ice = io.voff != nullptr;
     const uint64_t src_total = ice ? io.n_voff : io.vbuf_ints / 2;
@@ -235,56 +227,90 @@ __device__ __forceinline__ void warp_assemble(const LayerIO& io, uint32_t* sm, A
                 tot_ov = t2;
             }
             ASM_CHECK(s + tot_sv > src_total || v + tot_ov > io.cap_coords || tot_ov > 0xffffffffull, COVT_ERR_TOPOLOGY);
+            // ring tables of the trip, compacted over the rings that own output vertices (an empty ring owns none)
+            bool own[ASM_IPL];
+            uint32_t n_own = 0;
+#pragma unroll
+            for (int i = 0; i < ASM_IPL; i++) { own[i] = outn[i] != 0u; n_own += own[i] ? 1u : 0u; }
+            uint32_t tot_own;
+            uint32_t kw = warp_exclusive_scan(n_own, tot_own);
+            uint32_t first_out[ASM_IPL];  // first output vertex of the lane's rings, relative to the trip
             __syncwarp();
             {
                 uint64_t so = s + sv_excl, oo = ov_excl;
 #pragma unroll
                 for (int i = 0; i < ASM_IPL; i++) {
-                    r_start[ASM_IPL * lane + i] = (uint32_t)oo;
-                    r_src[ASM_IPL * lane + i] = (uint32_t)so;
-                    r_n[ASM_IPL * lane + i] = nv[i];
+                    first_out[i] = (uint32_t)oo;
+                    if (own[i]) {
+                        r_start[kw] = (uint32_t)oo;
+                        r_src[kw] = (uint32_t)so;
+                        r_n[kw] = nv[i];
+                        kw++;
+                    }
                     so += nv[i];
                     oo += outn[i];
                     if (valid[i]) io.a_ring[qb + i + 1] = (int32_t)(v + oo);
                 }
-                if (lane == 31) r_start[ASM_TRIP] = (uint32_t)tot_ov;
             }
-            __syncwarp();
             const uint32_t n_out = (uint32_t)tot_ov;
             bool oob = false;
-            // 4 batches of 32 output vertices per trip of the copy loop: the index loads, then the coordinate gathers, are
-            // issued back to back so that their latencies overlap (the decoded streams were written by earlier kernels, so the
-            // read-only path is safe here)
-            for (uint32_t u0 = 0; u0 < n_out; u0 += 128) {
-                uint64_t si[4];
-                bool ok[4];
+            // The ring of an output vertex: windows of ASM_WINDOW = 1024 output vertices. Every owning ring that starts inside
+            // the window sets one bit of a 32-word mask (its positions are distinct); the ring of vertex u is then
+            //   (#starts before the window) + (#bits at or below u) - 1
+            // = one popc and two shuffles per vertex instead of a binary search over the trip's 128 rings.
+            uint32_t k_before = 0;
+            for (uint32_t w0 = 0; w0 < n_out; w0 += ASM_WINDOW) {
+                marks[lane] = 0u;
+                __syncwarp();
 #pragma unroll
-                for (int b4 = 0; b4 < 4; b4++) {
-                    const uint32_t u = u0 + 32u * b4 + lane;
-                    ok[b4] = u < n_out;
-                    si[b4] = 0;
-                    if (ok[b4]) {
-                        const uint32_t ri = search_trip(r_start, u);
-                        const uint32_t i = u - r_start[ri];
-                        si[b4] = (uint64_t)r_src[ri] + (i == r_n[ri] ? 0u : i);  // i == n: the closing vertex = vertex 0 of the ring
-                    }
+                for (int i = 0; i < ASM_IPL; i++) {
+                    const uint32_t d = first_out[i] - w0;
+                    if (own[i] && d < (uint32_t)ASM_WINDOW) atomicOr(&marks[d >> 5], 1u << (d & 31u));
                 }
-                if (ice) {
-                    int32_t o[4];
-#pragma unroll
-                    for (int b4 = 0; b4 < 4; b4++) o[b4] = ok[b4] ? __ldg(io.voff + si[b4]) : 0;
+                __syncwarp();
+                const uint32_t my_mask = marks[lane];
+                uint32_t tot_starts;
+                const uint32_t my_before = k_before + warp_exclusive_scan((uint32_t)__popc(my_mask), tot_starts);
+                const uint32_t w_end = min(n_out, w0 + (uint32_t)ASM_WINDOW);
+                // 4 batches of 32 output vertices per trip of the copy loop: the index loads, then the coordinate gathers, are
+                // issued back to back so that their latencies overlap (the decoded streams were written by earlier kernels, so
+                // the read-only path is safe here)
+                for (uint32_t u0 = w0; u0 < w_end; u0 += 128) {
+                    uint64_t si[4];
+                    bool ok[4];
 #pragma unroll
                     for (int b4 = 0; b4 < 4; b4++) {
-                        if (ok[b4] && (o[b4] < 0 || (uint64_t)o[b4] >= dict)) { oob = true; ok[b4] = false; }
-                        si[b4] = (uint64_t)(uint32_t)o[b4];
+                        const uint32_t u = u0 + 32u * b4 + lane;
+                        const int word = (int)((u0 - w0) >> 5) + b4;  // uniform; < 32 because u0 - w0 <= 896
+                        const uint32_t m = __shfl_sync(FULL, my_mask, word);
+                        const uint32_t kb = __shfl_sync(FULL, my_before, word);
+                        ok[b4] = u < w_end;
+                        si[b4] = 0;
+                        if (ok[b4]) {
+                            const uint32_t k = kb + (uint32_t)__popc(m & lanemask_le()) - 1u;
+                            const uint32_t i = u - r_start[k];
+                            si[b4] = (uint64_t)r_src[k] + (i == r_n[k] ? 0u : i);  // i == n: the closing vertex = vertex 0 of the ring
+                        }
                     }
+                    if (ice) {
+                        int32_t o[4];
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; b4++) o[b4] = ok[b4] ? __ldg(io.voff + si[b4]) : 0;
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; b4++) {
+                            if (ok[b4] && (o[b4] < 0 || (uint64_t)o[b4] >= dict)) { oob = true; ok[b4] = false; }
+                            si[b4] = (uint64_t)(uint32_t)o[b4];
+                        }
+                    }
+                    int2 xy[4];
+#pragma unroll
+                    for (int b4 = 0; b4 < 4; b4++) xy[b4] = ok[b4] ? __ldg(reinterpret_cast<const int2*>(io.vbuf) + si[b4]) : make_int2(0, 0);
+#pragma unroll
+                    for (int b4 = 0; b4 < 4; b4++)
+                        if (ok[b4]) reinterpret_cast<int2*>(io.a_coords)[v + u0 + 32u * b4 + lane] = xy[b4];
                 }
-                int2 xy[4];
-#pragma unroll
-                for (int b4 = 0; b4 < 4; b4++) xy[b4] = ok[b4] ? __ldg(reinterpret_cast<const int2*>(io.vbuf) + si[b4]) : make_int2(0, 0);
-#pragma unroll
-                for (int b4 = 0; b4 < 4; b4++)
-                    if (ok[b4]) reinterpret_cast<int2*>(io.a_coords)[v + u0 + 32u * b4 + lane] = xy[b4];
+                k_before += tot_starts;
+                __syncwarp();
             }
             ASM_CHECK(oob, COVT_ERR_TOPOLOGY);
             v += tot_ov;

@@ -37,6 +37,12 @@ struct StreamOutcome {
 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_le()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
 
 // 128-bit streaming load (read-once data: do not allocate in L1)
 __device__ __forceinline__ uint4 ldg_stream128(const void* p)

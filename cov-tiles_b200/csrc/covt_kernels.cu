@@ -11,6 +11,9 @@
 //   k1a_aggregate / k1b_decode     : large varint streams of the stream API in 512-byte chunks over the whole GPU, with a
 //                                    segmented scan over (count, sumEven, sumOdd) in between (DecodingUtils.java:55-112,394-409)
 //   k_finalize                     : per-tile status + totals
+#include <cstdio>
+#include <cstdlib>
+
 #include "covt_assemble.cuh"
 #include "covt_internal.h"
 #include "covt_streams.cuh"
@@ -612,8 +615,8 @@ __device__ __forceinline__ StreamTask make_stream_task(const uint8_t* blob, cons
 // the classes that always take a warp per stream (GROUP == 1); the other classes push them onto big_queue for pass 2 — a warp
 // that decoded the large streams of its own group one after the other made the whole kernel wait for the unluckiest group
 // (fixture sweep: k_decode_rle 7.2 ms for 2.3 GB of output, the 60 000-value id streams of one tile land in one group).
-template <int CLASS>
-__global__ void __launch_bounds__(DEC_WARPS * 32, CLASS == CLASS_VARINT32 ? 8 : 1)
+template <int CLASS, int MINB>
+__global__ void __launch_bounds__(DEC_WARPS * 32, MINB)
 k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uint32_t* work_counter, const SegState* seg, covt_layer* layers,
                uint32_t* big_queue, uint32_t* big_count)
 {
@@ -707,7 +710,8 @@ k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counte
 // =================================================================================================
 // geometry assembly: one warp per layer (after every stream of the batch has been decoded)
 // =================================================================================================
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+template <int MINB>
+__global__ void __launch_bounds__(DEC_WARPS * 32, MINB)
 k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter, const SegState* seg)
 {
     if (seg->overflow) return;
@@ -1137,27 +1141,44 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
     const int grid = grid_for(sm_count, per_sm, ((uint64_t)n_tasks + group - 1) / group, DEC_WARPS);
     const int grid_big = grid_for(sm_count, per_sm, n_tasks, DEC_WARPS);
     uint32_t *c0 = counters, *c1 = counters + 1, *c2 = counters + 2;
+    // experiment switch: COVT_MINB_C<class>=8|12|16 picks the minimum-resident-blocks variant of the pass-1 kernel
+    static int minb_env[NUM_OP_CLASSES] = {-1, -1, -1, -1, -1};
+    if (minb_env[op_class] < 0) {
+        char name[32];
+        snprintf(name, sizeof name, "COVT_MINB_C%d", op_class);
+        const char* e = getenv(name);
+        minb_env[op_class] = e ? atoi(e) : 0;
+    }
+    const int minb = minb_env[op_class];
+#define COVT_PASS1(C, DEFAULT_MINB, q, qc)                                                                                        \
+    do {                                                                                                                          \
+        if (minb >= 16) k_decode_class<C, 16><<<grid_for(sm_count, 16, ((uint64_t)n_tasks + group - 1) / group, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc); \
+        else if (minb >= 12) k_decode_class<C, 12><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc); \
+        else if (minb >= 8) k_decode_class<C, 8><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc);   \
+        else k_decode_class<C, DEFAULT_MINB><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc);       \
+    } while (0)
     switch (op_class) {
     case CLASS_BYTE_RLE:
-        k_decode_class<CLASS_BYTE_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, big_queue, c1);
+        COVT_PASS1(CLASS_BYTE_RLE, 1, big_queue, c1);
         k_decode_class_big<CLASS_BYTE_RLE><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
         break;
     case CLASS_RLE:
-        k_decode_class<CLASS_RLE><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, big_queue, c1);
+        COVT_PASS1(CLASS_RLE, 1, big_queue, c1);
         k_decode_class_big<CLASS_RLE><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
         break;
-    case CLASS_VARINT32: k_decode_class<CLASS_VARINT32><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, nullptr, nullptr); break;
+    case CLASS_VARINT32: COVT_PASS1(CLASS_VARINT32, 8, nullptr, nullptr); break;
     case CLASS_VARINT64:
-        k_decode_class<CLASS_VARINT64><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, big_queue, c1);
+        COVT_PASS1(CLASS_VARINT64, 1, big_queue, c1);
         k_decode_class_big<CLASS_VARINT64><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
         break;
     case CLASS_PFOR:
-        k_decode_class<CLASS_PFOR><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, big_queue, c1);
+        COVT_PASS1(CLASS_PFOR, 8, big_queue, c1);
         k_decode_class_big<CLASS_PFOR><<<grid_for(sm_count, 12, n_tasks, DEC_WARPS), DEC_WARPS * 32, DEC_WARPS * PFOR_BIG_WARP_SMEM, st>>>(blob, tasks, c2, seg, layers,
                                                                                                                                       big_queue, c1);
         break;
     default: return cudaErrorInvalidValue;
     }
+#undef COVT_PASS1
     return cudaGetLastError();
 }
 
@@ -1166,7 +1187,13 @@ cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, 
                                    uint32_t* work_counter, const SegState* seg, int sm_count, cudaStream_t st)
 {
     if (!n_layers_bound) return cudaSuccess;
-    k_assemble_layers<<<grid_for(sm_count, 12, n_layers_bound, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
+    static const int minb = getenv("COVT_ASM_MINB") ? atoi(getenv("COVT_ASM_MINB")) : 16;
+    const int per_sm = minb > 12 ? minb : 12;
+    const int grid = grid_for(sm_count, per_sm, n_layers_bound, DEC_WARPS);
+    if (minb >= 16) k_assemble_layers<16><<<grid, DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
+    else if (minb >= 12) k_assemble_layers<12><<<grid, DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
+    else if (minb >= 10) k_assemble_layers<10><<<grid, DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
+    else k_assemble_layers<1><<<grid, DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
     return cudaGetLastError();
 }
 

@@ -95,6 +95,12 @@ def decode_stream(blob, op=0, *, byte_offset=0, byte_length=None, num_values, st
     return out[: d.out_count].copy(), d.status, d.bytes_consumed
 
 
+def _copy_from(ptr, nbytes, dtype):
+    """numpy copy of `nbytes` at a ctypes pointer (C.string_at stops at 2 GiB; the 1 M-tile result buffers are larger)."""
+    addr = C.cast(ptr, C.c_void_p).value
+    return np.frombuffer((C.c_uint8 * nbytes).from_address(addr), dtype=dtype).copy()
+
+
 class BatchResult:
     """Owns a covt_oracle_result; exposes numpy views with the same layout as the product's result."""
 
@@ -106,8 +112,7 @@ class BatchResult:
         self.tile_status = np.ctypeslib.as_array(r.tile_status, shape=(max(1, r.n_tiles),))[: r.n_tiles].copy()
         self.first_layer = np.ctypeslib.as_array(r.first_layer, shape=(r.n_tiles + 1,)).copy()
         if r.n_layers:
-            raw = C.string_at(r.layers, r.n_layers * C.sizeof(abi.Layer))
-            self.layers = np.frombuffer(raw, dtype=abi.LAYER_DTYPE).copy()
+            self.layers = _copy_from(r.layers, r.n_layers * C.sizeof(abi.Layer), abi.LAYER_DTYPE)
         else:
             self.layers = np.zeros(0, dtype=abi.LAYER_DTYPE)
         self.buffers = []
@@ -115,7 +120,7 @@ class BatchResult:
             n = r.counts[b]
             dt = np.dtype(abi.BUF_DTYPES[b])
             if n and r.buffers[b]:
-                arr = np.frombuffer(C.string_at(r.buffers[b], n * dt.itemsize), dtype=dt)
+                arr = _copy_from(r.buffers[b], n * dt.itemsize, dt)
             else:
                 arr = np.zeros(0, dtype=dt)
             self.buffers.append(arr)

@@ -151,3 +151,57 @@ def rewrap_gen3(abi, oracle, tile_bytes, optimized=False):
                 continue
             out += bytes(blob[int(s["byte_offset"]):int(s["byte_offset"]) + int(s["byte_length"])])
     return bytes(out), ([0] * len(layers) if optimized else None)
+
+
+# ---- the same comparison without a per-layer Python loop (batches of 10^6 layers) ---------------------------------
+def compare_results_bulk(abi, got, want, chunk_layers=1 << 16):
+    """Bit-exact comparison of every decoded stream and every assembled buffer of two batch results, vectorised: elements that
+    belong to no valid layer slice (alignment padding between slices, slices of failed streams / layers) are masked out.
+    Returns (layers compared, elements compared)."""
+    gl, wl = got.layers, want.layers
+    assert len(gl) == len(wl), "layer count %d != %d" % (len(gl), len(wl))
+    for f in ("tile", "layer_index", "extent", "num_features", "geom_column_type", "num_bits", "has_id", "cap_parts", "cap_rings",
+              "num_columns", "name_length", "name_offset", "status", "n_parts", "n_rings", "n_vertices", "n_coords"):
+        assert np.array_equal(gl[f], wl[f]), "layer field %s differs" % f
+    assert np.array_equal(gl["out"], wl["out"]), "result layout (out offsets) differs"
+    for f in ("byte_offset", "byte_length", "num_values", "encoding", "op", "status"):
+        assert np.array_equal(gl["streams"][f], wl["streams"][f]), "stream field %s differs" % f
+    layer_ok = wl["status"] == 0
+    n_elems = 0
+    # (buffer, start element, element count) of every valid slice, as arrays over layers
+    slices = {b: [] for b in range(abi.NUM_BUFFERS - 1)}
+    for s in range(abi.NUM_SLOTS):
+        b = abi.SLOT_BUF[s]
+        st = wl["streams"][:, s]
+        ok = (st["encoding"] != abi.ENC_ABSENT) & (st["status"] == 0)
+        cnt = st["num_values"].astype(np.int64)
+        if s == abi.SLOT_VBUF:
+            cnt = np.where(np.isin(wl["geom_column_type"], (abi.CT_ICE, abi.CT_ICE_MORTON_CODE)), 2 * cnt, cnt)
+        slices[b].append((wl["out"][:, b].astype(np.int64), np.where(ok, cnt, 0)))
+    F = wl["streams"][:, abi.SLOT_TYPES]["num_values"].astype(np.int64)
+    for b, cnt in ((abi.BUF_A_GEOM_OFFSETS, F + 1), (abi.BUF_A_PART_OFFSETS, wl["n_parts"].astype(np.int64) + 1),
+                   (abi.BUF_A_RING_OFFSETS, wl["n_rings"].astype(np.int64) + 1), (abi.BUF_A_COORDS, 2 * wl["n_coords"].astype(np.int64))):
+        slices[b].append((wl["out"][:, b].astype(np.int64), np.where(layer_ok, cnt, 0)))
+    for b in range(abi.NUM_BUFFERS - 1):
+        g, w = got.buffer(b), want.buffer(b)
+        assert len(g) == len(w), "buffer %s length %d != %d" % (abi.BUF_NAMES[b], len(g), len(w))
+        for start, cnt in slices[b]:
+            end = start + cnt
+            assert (end <= len(w)).all(), "buffer %s: a slice ends outside the buffer" % abi.BUF_NAMES[b]
+            for l0 in range(0, len(wl), chunk_layers):
+                s_, e_ = start[l0:l0 + chunk_layers], end[l0:l0 + chunk_layers]
+                have = e_ > s_
+                if not have.any():
+                    continue
+                lo, hi = int(s_[have].min()), int(e_[have].max())
+                d = np.bincount(s_[have] - lo, minlength=hi - lo + 1) - np.bincount(e_[have] - lo, minlength=hi - lo + 1)
+                inside = np.cumsum(d[:-1]) > 0
+                neq = (g[lo:hi] != w[lo:hi]) & inside
+                if neq.any():
+                    at = lo + int(np.nonzero(neq)[0][0])
+                    li = l0 + int(np.nonzero((s_ <= at) & (e_ > at))[0][0])
+                    raise AssertionError("buffer %s differs at element %d (layer %d, tile %d): got %s want %s" % (
+                        abi.BUF_NAMES[b], at, li, wl["tile"][li], g[at:at + 4], w[at:at + 4]))
+                n_elems += int(inside.sum())
+        del g, w
+    return int(layer_ok.sum()), n_elems

@@ -33,6 +33,14 @@ traffic)
   timeout 600 $CMD > gpurun_out/plain_traffic_k1.log 2>&1 && \
   timeout 1500 ncu --set full --clock-control none -k "regex:k1a_|k1b_" -s 6 -c 2 -f -o gpurun_out/prof_traffic_k1 $CMD > gpurun_out/ncu_traffic_k1.log 2>&1
   echo "traffic_k1_exit=$?"; tail -2 gpurun_out/ncu_traffic_k1.log;;
+exp)
+  # sweep environment variables (comma-separated names share the value): EXP_VAR=COVT_ASM_MINB EXP_VALUES="1 10 12" tools/gpu_round.sh exp
+  for val in $EXP_VALUES; do
+    echo "== $EXP_VAR=$val"
+    ENVS=""; for name in ${EXP_VAR//,/ }; do ENVS="$ENVS $name=$val"; done
+    env $ENVS timeout 600 python bench.py --tiles ${TILES:-262144} --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/exp_tiles_$val.err | python tools/kernel_times.py
+    env $ENVS timeout 600 python bench.py --workload fixtures --replicas 64 --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/exp_fx_$val.err | python tools/kernel_times.py
+  done;;
 launches)
   CMD="python bench.py --tiles 65536 --steps 1 --warmup 3 --no-cpu-baseline"
   $CMD > gpurun_out/plain_launches.log 2>&1 && \
