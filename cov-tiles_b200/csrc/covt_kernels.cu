@@ -690,6 +690,7 @@ k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counte
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     uint8_t* wsm = smem + warp * (CLASS == CLASS_PFOR ? PFOR_BIG_WARP_SMEM : class_warp_smem<CLASS>());
     const uint32_t n = *big_count;
+    if (n == 0u) return;  // nothing queued (batches of small tiles): skip the 7 000 same-address ticket atomics of an idle grid
     for (;;) {
         const uint32_t q = warp_next_work(work_counter);
         if (q >= n) break;

@@ -30,7 +30,8 @@ def test_config5_one_million_tiles_bit_exact(covt, oracle, gen, decoder):
     blob, offs, truth = gen.tiles(0, n_tiles, gen.default_params())
     ref = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT)
     res = decoder.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT)
-    assert np.array_equal(res.tile_status, ref.tile_status) and not res.tile_status.any()
+    st, _ = res.tile_status()
+    assert np.array_equal(st, ref.tile_status) and not st.any()
     n_layers, n_elems = util.compare_results_bulk(abi, res, ref)
     assert n_layers == 2 * n_tiles and n_elems > 4_000_000_000
     L = res.layers
