@@ -282,8 +282,8 @@ int32_t covt_trim(covt_ctx* ctx);
 
 /* ---- batch path: replaces CovtParser.decodeCovt (CovtParser.java:53), batched over tiles ---- */
 /* blob holds n_tiles tiles back to back; tile i occupies [tile_offsets[i], tile_offsets[i+1]). Host memory (pinned or
- * covt_host_register-ed for full PCIe rate). Large batches go up in ~48 MB segments on a copy stream while earlier segments are
- * being decoded; the result is one set of buffers whatever the segmentation. */
+ * covt_host_register-ed for full PCIe rate). Large batches go up in at most 8 segments of >= 64 MiB on a copy stream while earlier segments
+ * are being decoded; the result is one set of buffers whatever the segmentation. */
 int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles,
                           uint32_t container, const covt_tilejson* tilejson, uint32_t flags, covt_result** out);
 /* The same in two steps so that host->device transfer is timed apart from device-resident decode. */
