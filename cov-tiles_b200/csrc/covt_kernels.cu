@@ -11,9 +11,6 @@
 //   k1a_aggregate / k1b_decode     : large varint streams of the stream API in 512-byte chunks over the whole GPU, with a
 //                                    segmented scan over (count, sumEven, sumOdd) in between (DecodingUtils.java:55-112,394-409)
 //   k_finalize                     : per-tile status + totals
-#include <cstdio>
-#include <cstdlib>
-
 #include "covt_assemble.cuh"
 #include "covt_internal.h"
 #include "covt_streams.cuh"
@@ -1142,22 +1139,9 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
     const int grid = grid_for(sm_count, per_sm, ((uint64_t)n_tasks + group - 1) / group, DEC_WARPS);
     const int grid_big = grid_for(sm_count, per_sm, n_tasks, DEC_WARPS);
     uint32_t *c0 = counters, *c1 = counters + 1, *c2 = counters + 2;
-    // experiment switch: COVT_MINB_C<class>=8|12|16 picks the minimum-resident-blocks variant of the pass-1 kernel
-    static int minb_env[NUM_OP_CLASSES] = {-1, -1, -1, -1, -1};
-    if (minb_env[op_class] < 0) {
-        char name[32];
-        snprintf(name, sizeof name, "COVT_MINB_C%d", op_class);
-        const char* e = getenv(name);
-        minb_env[op_class] = e ? atoi(e) : 0;
-    }
-    const int minb = minb_env[op_class];
-#define COVT_PASS1(C, DEFAULT_MINB, q, qc)                                                                                        \
-    do {                                                                                                                          \
-        if (minb >= 16) k_decode_class<C, 16><<<grid_for(sm_count, 16, ((uint64_t)n_tasks + group - 1) / group, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc); \
-        else if (minb >= 12) k_decode_class<C, 12><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc); \
-        else if (minb >= 8) k_decode_class<C, 8><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc);   \
-        else k_decode_class<C, DEFAULT_MINB><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc);       \
-    } while (0)
+    // Minimum resident blocks per SM (profiles/r01_experiments.md): the 32-bit varint and FastPFOR kernels are capped at 64
+    // registers (8 blocks = 32 warps per SM; below that the chunk decoder spills), the thread-per-stream kernels need no cap.
+#define COVT_PASS1(C, MINB, q, qc) k_decode_class<C, MINB><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc)
     switch (op_class) {
     case CLASS_BYTE_RLE:
         COVT_PASS1(CLASS_BYTE_RLE, 1, big_queue, c1);
@@ -1188,13 +1172,8 @@ cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, 
                                    uint32_t* work_counter, const SegState* seg, int sm_count, cudaStream_t st)
 {
     if (!n_layers_bound) return cudaSuccess;
-    static const int minb = getenv("COVT_ASM_MINB") ? atoi(getenv("COVT_ASM_MINB")) : 16;
-    const int per_sm = minb > 12 ? minb : 12;
-    const int grid = grid_for(sm_count, per_sm, n_layers_bound, DEC_WARPS);
-    if (minb >= 16) k_assemble_layers<16><<<grid, DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
-    else if (minb >= 12) k_assemble_layers<12><<<grid, DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
-    else if (minb >= 10) k_assemble_layers<10><<<grid, DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
-    else k_assemble_layers<1><<<grid, DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
+    // 32 registers, 16 blocks = 64 warps per SM: the assembler waits on dependent loads (profiles/r01_experiments.md)
+    k_assemble_layers<16><<<grid_for(sm_count, 16, n_layers_bound, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
     return cudaGetLastError();
 }
 
