@@ -159,6 +159,15 @@ __device__ bool name_is(const uint8_t* b, uint64_t off, uint32_t len, const char
     return true;
 }
 
+// The result buffers are sized from numValues before anything is decoded, so a corrupt header must not be able to claim
+// gigabytes: no codec of the path packs more than 128 values into a byte (FastPFOR at bit width 0: two container bytes per block
+// of 256; Byte-RLE: 130 per 2 bytes; RLE: 130 per 3), so a stream that claims more than 256 values per byte (+ slack for the
+// fixed headers) cannot decode — the reference would run off the end of the array (ArrayIndexOutOfBounds): the tile fails.
+__device__ __forceinline__ bool plausible_count(uint32_t num_values, uint32_t byte_length)
+{
+    return (uint64_t)num_values <= 256ull * ((uint64_t)byte_length + 16ull);
+}
+
 __device__ void layer_init(covt_layer& L, uint32_t tile, uint32_t idx)
 {
     uint32_t* w = reinterpret_cast<uint32_t*>(&L);
@@ -241,6 +250,7 @@ __device__ uint32_t walk_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end
                 }
                 if (slot >= 0) {
                     if (enc > COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_ERR_BAD_METADATA;
+                    if (!plausible_count(nv, bl)) return COVT_ERR_TRUNCATED;
                     L.streams[slot].num_values = nv;
                     L.streams[slot].byte_length = bl;
                     L.streams[slot].encoding = (uint8_t)enc;
@@ -349,6 +359,7 @@ __device__ uint32_t walk_gen3(const uint8_t* blob, uint64_t begin, uint64_t end,
                     slot = COVT_SLOT_TYPES + (int)(stream_type - COVT_ST_GEOMETRY_TYPES);
                 else if (is_geom && stream_type == COVT_ST_INDEX_BUFFER) slot = COVT_SLOT_INDEX;
                 if (slot >= 0) {
+                    if (!plausible_count(nv, bl)) return COVT_ERR_TRUNCATED;
                     L.streams[slot].num_values = nv;
                     L.streams[slot].byte_length = bl;
                     L.streams[slot].encoding = (uint8_t)enc;

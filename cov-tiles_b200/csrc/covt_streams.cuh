@@ -601,8 +601,9 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* wsm
                     bcpos++;
                     const int index = (int)maxbits - (int)b;
                     __syncwarp();
+                    // atomicOr: a (corrupt) stream may list a position twice; the Java patch loop ORs both exceptions in
                     if (index == 1) {
-                        for (uint32_t e = lane; e < cexcept; e += 32) stage[BC_BYTE(bcpos + e)] |= 1u << (b & 31u);
+                        for (uint32_t e = lane; e < cexcept; e += 32) atomicOr(&stage[BC_BYTE(bcpos + e)], 1u << (b & 31u));
                     } else {
                         if (index < 2 || index > 32 || !(bitmap & (1u << (index - 1)))) PFOR_FAIL(COVT_ERR_BAD_METADATA);
                         const uint32_t ebase = __shfl_sync(FULL, exc_base, index - 1);
@@ -610,7 +611,7 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* wsm
                         const uint32_t eptr = __shfl_sync(FULL, exc_ptr, index - 1);
                         if (eptr + cexcept > esize) PFOR_FAIL(COVT_ERR_TRUNCATED);
                         for (uint32_t e = lane; e < cexcept; e += 32)
-                            stage[BC_BYTE(bcpos + e)] |= unpack_packed(base, ebase, eptr + e, (uint32_t)index) << (b & 31u);
+                            atomicOr(&stage[BC_BYTE(bcpos + e)], unpack_packed(base, ebase, eptr + e, (uint32_t)index) << (b & 31u));
                         if (lane == (unsigned)(index - 1)) exc_ptr += cexcept;
                     }
                     bcpos += cexcept;
@@ -758,7 +759,7 @@ __device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t
                     const int index = (int)maxbits - (int)b;
                     __syncwarp();
                     if (index == 1) {
-                        for (uint32_t e = lane; e < cexcept; e += 32) stage[BC_BYTE(bcpos + e)] |= 1u << (b & 31u);
+                        for (uint32_t e = lane; e < cexcept; e += 32) atomicOr(&stage[BC_BYTE(bcpos + e)], 1u << (b & 31u));
                     } else {
                         if (index < 2 || index > 32 || !(bitmap & (1u << (index - 1)))) PFOR_FAIL(COVT_ERR_BAD_METADATA);
                         const uint32_t ebase = __shfl_sync(FULL, exc_base, index - 1);
@@ -766,7 +767,7 @@ __device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t
                         const uint32_t eptr = __shfl_sync(FULL, exc_ptr, index - 1);
                         if (eptr + cexcept > esize) PFOR_FAIL(COVT_ERR_TRUNCATED);
                         for (uint32_t e = lane; e < cexcept; e += 32)
-                            stage[BC_BYTE(bcpos + e)] |= sm_unpack(sw, ebase, eptr + e, (uint32_t)index) << (b & 31u);
+                            atomicOr(&stage[BC_BYTE(bcpos + e)], sm_unpack(sw, ebase, eptr + e, (uint32_t)index) << (b & 31u));
                         if (lane == (unsigned)(index - 1)) exc_ptr += cexcept;
                     }
                     bcpos += cexcept;

@@ -688,6 +688,14 @@ static uint64_t layer_place_streams(covt_layer* L, uint64_t payload, uint32_t fl
     return payload;
 }
 
+/* Library policy shared with the product (result buffers are sized from numValues before anything is decoded): a stream that
+ * claims more than 256 values per payload byte cannot decode with any codec of the path (the densest, FastPFOR at bit width 0,
+ * holds 128 per byte) - the reference would run off the end of its array (ArrayIndexOutOfBounds), so the tile fails. */
+static int plausible_count(uint32_t num_values, uint32_t byte_length)
+{
+    return (uint64_t)num_values <= 256ull * ((uint64_t)byte_length + 16ull);
+}
+
 static uint32_t nlz32(uint32_t v) { return v ? (uint32_t)__builtin_clz(v) : 32u; }
 
 /* gen-2b: varint version, varint numLayers | per layer: string name, varint extent, numFeatures, numColumns |
@@ -746,6 +754,7 @@ static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, ui
                 }
                 if (slot >= 0) {
                     if (enc > COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_ERR_BAD_METADATA;
+                    if (!plausible_count(nv, bl)) return COVT_ERR_TRUNCATED;
                     L->streams[slot].num_values = nv;
                     L->streams[slot].byte_length = bl;
                     L->streams[slot].encoding = (uint8_t)enc;
@@ -855,6 +864,7 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
                     slot = COVT_SLOT_TYPES + (int)(stream_type - COVT_ST_GEOMETRY_TYPES);
                 else if (is_geom && stream_type == COVT_ST_INDEX_BUFFER) slot = COVT_SLOT_INDEX;
                 if (slot >= 0) {
+                    if (!plausible_count(nv, bl)) { rc = COVT_ERR_TRUNCATED; break; }
                     L->streams[slot].num_values = nv;
                     L->streams[slot].byte_length = bl;
                     L->streams[slot].encoding = (uint8_t)enc;

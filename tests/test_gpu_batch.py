@@ -277,3 +277,48 @@ def test_partitioned_decode_and_trim(covt, oracle, gen):
         assert verts == truth["vertices"]
     finally:
         dec.close()
+
+
+@pytest.mark.gpu
+def test_mutation_fuzz_against_oracle(covt, oracle, decoder, fixtures):
+    """1 200 mutants of small fixture tiles (byte flips in metadata and payload, truncations, appended junk) in ONE batch between
+    good tiles: the call survives, tile / layer / stream statuses agree with the oracle on OK-ness, the result layout is
+    identical, every stream and layer both sides accept is bit-exact, and the good tiles are untouched."""
+    abi = covt.abi
+    flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+    small = sorted(((n, b) for n, b in fixtures if n.startswith("omt/") and not n.startswith("omt/8_")
+                    and not any(k.startswith(n + "/") for k in util.KNOWN_MISLABELLED)), key=lambda t: len(t[1]))[:5]
+    assert len(small) == 5
+    rng = np.random.default_rng(2026)
+    tiles, is_good = [], []
+    for k in range(1200):
+        name, data = small[k % len(small)]
+        b = bytearray(data)
+        kind = k % 4
+        if kind == 0:      # anywhere
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, len(b)))] ^= int(rng.integers(1, 256))
+        elif kind == 1:    # the first layer's metadata
+            for _ in range(int(rng.integers(1, 3))):
+                b[int(rng.integers(0, min(len(b), 160)))] ^= int(rng.integers(1, 256))
+        elif kind == 2:    # truncated
+            b = b[: int(rng.integers(0, len(b)))]
+        else:              # junk appended / a byte dropped
+            if rng.integers(0, 2):
+                b += bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8))
+            else:
+                del b[int(rng.integers(0, len(b)))]
+        tiles.append(bytes(b))
+        is_good.append(False)
+        if k % 50 == 0:
+            tiles.append(data)
+            is_good.append(True)
+    blob, offs = util.concat_tiles(tiles)
+    res, ref = _decode_both(covt, oracle, decoder, blob, offs, flags=flags)
+    st, _ = res.tile_status()
+    good = np.array(is_good)
+    assert not st[good].any(), "a good tile was poisoned by its neighbours"
+    assert (st[~good] != 0).sum() > 300 and (st[~good] == 0).sum() > 100  # the corpus exercises both outcomes
+    n = util.compare_results(abi, res, ref)
+    assert n > 1000
+    res.free()
