@@ -60,10 +60,12 @@ __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t*
             const int32_t first = (int32_t)L.excl - (int32_t)head_f;  // chunk-local index of the lane's first value
             const bool mine = remaining > 0u && (int32_t)remaining > first && (int32_t)remaining <= first + (int32_t)L.cnt;
             const unsigned b = __ballot_sync(FULL, mine);
-            if (b) {
-                uint32_t pos = 0;
-                if (mine) pos = lane * 16u + lean_nth_terminator(L.cm, remaining - (uint32_t)first);
-                end_in_chunk = __shfl_sync(FULL, pos, __ffs(b) - 1);
+            uint32_t pos = 0;
+            if (mine) pos = lane * 16u + lean_nth_terminator(L.cm, remaining - (uint32_t)first);
+            pos = __shfl_sync(FULL, pos, b ? __ffs(b) - 1 : 0);
+            // a terminator behind the stream's bytes is one of the fake zeros, not the value asked for: the stream is too short
+            if (b && pos <= end_in_chunk) {
+                end_in_chunk = pos;
                 consumed = (uint32_t)(base + end_in_chunk - head);
                 bounds(lo16, hi16);
                 halo_in = carry_halo;

@@ -259,3 +259,85 @@ def test_config4_index_buffers_of_fixture_polygons(covt, oracle, gen, decoder, f
                                             stream_type=abi.ST_INDEX_BUFFER, encoding=abi.ENC_FAST_PFOR_DELTA_ZIG_ZAG)
         assert wst == 0 and np.array_equal(want, idx)
     res.free()
+
+
+def _fuzz_cases(abi, gen, seed):
+    """Valid streams of every op (small: lane decoders; medium: warp decoders), each mutated four ways."""
+    rng = np.random.default_rng(seed)
+    cases = []
+
+    def base_streams(op, n):
+        if op == abi.OP_BYTE_RLE:
+            v = np.repeat(rng.integers(0, 6, n // 3 + 1), rng.integers(1, 6, n // 3 + 1))[:n].astype(np.uint8)
+            return gen.encode_byte_rle(v), len(v), 0
+        if op in (abi.OP_RLE_U32, abi.OP_RLE_U64, abi.OP_RLE_S64):
+            v = np.repeat(rng.integers(0, 1 << 20, n // 2 + 1), rng.integers(1, 5, n // 2 + 1))[:n].astype(np.int64)
+            if op == abi.OP_RLE_U64:
+                v = v << 30
+            if op == abi.OP_RLE_S64:
+                v = v - (1 << 19)
+            return gen.encode_rle(v, signed=(op == abi.OP_RLE_S64)), len(v), 0
+        if op in (abi.OP_VARINT_U32, abi.OP_VARINT_ZZ, abi.OP_VARINT_ZZ_DELTA, abi.OP_VARINT_ZZ_DELTA_XY):
+            n2 = n + (n & 1)
+            v = rng.integers(-3000, 3000, n2).astype(np.int64)
+            if op == abi.OP_VARINT_U32:
+                return gen.encode_varints(np.abs(v) * 37), n2, 0
+            if op == abi.OP_VARINT_ZZ:
+                return gen.encode_varints(v, zigzag=True), n2, 0
+            if op == abi.OP_VARINT_ZZ_DELTA:
+                return gen.encode_varints(np.cumsum(v), zigzag=True, delta=True), n2, 0
+            zz = gen.encode_zigzag_delta_coordinates(np.cumsum(v.reshape(-1, 2), axis=0).astype(np.int32).ravel()).astype(np.int64) & 0xFFFFFFFF
+            return gen.encode_varints(zz), n2, 0
+        if op == abi.OP_VARINT_DELTA_MORTON:
+            return gen.encode_varints(rng.integers(0, 40000, n).astype(np.int64)), n, 13
+        if op in (abi.OP_VARINT_U64, abi.OP_VARINT_ZZ_DELTA_64):
+            v = np.cumsum(rng.integers(-(1 << 40), 1 << 40, n).astype(np.int64))
+            if op == abi.OP_VARINT_U64:
+                return gen.encode_varints(np.abs(v)), n, 0
+            return gen.encode_varints(v, zigzag=True, delta=True), n, 0
+        if op in (abi.OP_PFOR_ZZ_DELTA, abi.OP_PFOR_ZZ_DELTA_XY):
+            n2 = n + (n & 1)
+            v = np.cumsum(rng.integers(-300, 300, n2)).astype(np.int32)
+            v[rng.integers(0, n2, max(1, n2 // 40))] += 1 << 20  # exceptions
+            if op == abi.OP_PFOR_ZZ_DELTA:
+                return gen.encode_fastpfor(v, zigzag=True, delta=True), n2, 0
+            return gen.encode_fastpfor(gen.encode_zigzag_delta_coordinates(v), zigzag=False, delta=False), n2, 0
+        if op == abi.OP_PFOR_DELTA_MORTON:
+            d = rng.integers(0, 3000, n).astype(np.int32)
+            return gen.encode_fastpfor(d, zigzag=False, delta=False), n, 13
+        raise AssertionError(op)
+
+    ops = [abi.OP_BYTE_RLE, abi.OP_RLE_U32, abi.OP_RLE_U64, abi.OP_RLE_S64, abi.OP_VARINT_U32, abi.OP_VARINT_ZZ, abi.OP_VARINT_ZZ_DELTA,
+           abi.OP_VARINT_ZZ_DELTA_XY, abi.OP_VARINT_DELTA_MORTON, abi.OP_VARINT_U64, abi.OP_VARINT_ZZ_DELTA_64, abi.OP_PFOR_ZZ_DELTA,
+           abi.OP_PFOR_ZZ_DELTA_XY, abi.OP_PFOR_DELTA_MORTON]
+    for op in ops:
+        sizes = [int(x) for x in rng.integers(1, 300, 8)] + [int(x) for x in rng.integers(3000, 20000, 3)]
+        for n in sizes:
+            enc, nv, nbits = base_streams(op, n)
+            enc = np.asarray(enc, dtype=np.uint8)
+            exact = op in (abi.OP_PFOR_ZZ_DELTA, abi.OP_PFOR_ZZ_DELTA_XY, abi.OP_PFOR_DELTA_MORTON) or bool(rng.integers(0, 2))
+            cases.append((op, enc, nv, nbits, exact))  # the unmutated stream
+            for kind in range(4):
+                b = bytearray(enc.tobytes())
+                if kind == 0:
+                    b[int(rng.integers(0, len(b)))] ^= int(rng.integers(1, 256))
+                elif kind == 1:
+                    for _ in range(3):
+                        b[int(rng.integers(0, len(b)))] ^= int(rng.integers(1, 256))
+                elif kind == 2:
+                    b = b[: int(rng.integers(0, len(b)))]
+                elif len(b) > 1:
+                    del b[int(rng.integers(0, len(b)))]
+                if len(b) == 0:
+                    continue
+                cases.append((op, np.frombuffer(bytes(b), dtype=np.uint8), nv, nbits, exact))
+    return cases
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_stream_mutation_fuzz_against_oracle(covt, oracle, gen, decoder, seed):
+    """~750 streams per seed, every op, lane- and warp-decoded sizes, each also flipped / truncated / shortened: one
+    covt_decode_streams call; status OK-ness and every accepted value equal the oracle's (DecodingUtils semantics)."""
+    cases = _fuzz_cases(covt.abi, gen, seed)
+    assert len(cases) > 700
+    _batch_check(covt, oracle, decoder, cases)
