@@ -924,7 +924,7 @@ k1a_aggregate(const uint8_t* blob, const BigStream* streams, uint32_t n_streams,
         v.flags = (xy ? 2u : 0u) | (ci == 0 ? 1u : 0u);
         states[g] = v;
     }
-    if (__any_sync(FULL, (ov >> 28) & 1u) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
+    // (the overlong flag is raised by k1b_decode, which knows where the stream's numValues-th value ends)
 }
 
 __global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_reduce(const ChunkState* states, uint32_t n, ChunkState* block_states)
@@ -989,6 +989,7 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
     K1Chunk k = k1_load_chunk(blob, S, ci);
     uint32_t* stage = s_stage[threadIdx.x >> 5];
     uint32_t w[4], acc, mul, ov = 0;
+    const uint32_t halo_in = k.halo0;  // lean_front replaces it by this chunk's last bytes
     LeanLane L = lean_front(k.win, k.partial, k.lo16, k.hi16, k.halo0, w, acc, mul, ov);
     L.excl = warp_exclusive_scan(L.cnt, L.total);
     const uint32_t s4 = P.count & 3u;  // see lean_rows4: the chunk's values are staged at A[s4 + i]
@@ -997,12 +998,30 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
     lean_stage_lane(w, L.cm, acc, mul, A + s4 + L.excl - k.head_f, ov);
     __syncwarp();
     const uint32_t n_here = L.total - k.head_f - k.tail_f;
-    // bytes the reference reader consumes = position right after the terminator of value #num_values
+    // bytes the reference reader consumes = position right after the terminator of value #num_values; what follows it is not
+    // read (and must not raise the overlong flag)
     {
         const int64_t first = (int64_t)P.count + L.excl - k.head_f;  // stream index of the lane's first terminator (fakes negative)
-        if (S.consumed_out && S.num_values > 0u && (int64_t)S.num_values > first && (int64_t)S.num_values <= first + (int64_t)L.cnt)
-            *S.consumed_out = (uint32_t)(k.off + lean_nth_terminator(L.cm, (uint32_t)((int64_t)S.num_values - first)) - k.head);
+        const bool mine = S.num_values > 0u && (int64_t)S.num_values > first && (int64_t)S.num_values <= first + (int64_t)L.cnt;
+        const unsigned bm = __ballot_sync(FULL, mine);
+        uint32_t cut = 0;
+        if (mine) cut = lane * 16u + lean_nth_terminator(L.cm, (uint32_t)((int64_t)S.num_values - first));
+        cut = __shfl_sync(FULL, cut, bm ? __ffs(bm) - 1 : 0);
+        const uint32_t end_in_chunk = WARP_CHUNK_BYTES - k.tail_f;
+        if (bm && cut <= end_in_chunk) {  // (a terminator behind the stream's bytes is a fake zero)
+            if (S.consumed_out && lane == 0) *S.consumed_out = (uint32_t)(k.off + cut - k.head);
+            if (cut < end_in_chunk) {
+                // rare: the chunk holds values beyond numValues; redo the overlong check on the bytes before the cut
+                const uint32_t hi_cut = cut > lane * 16u ? min(16u, cut - lane * 16u) : 0u;
+                uint32_t w2[4], acc2, mul2, halo2 = halo_in;
+                int32_t c2, o2;
+                ov = 0;
+                const LeanLane L2 = lean_front(k.win, true, k.lo16, hi_cut, halo2, w2, acc2, mul2, ov);
+                lean_sum_lane<false>(w2, L2.cm, acc2, mul2, c2, o2, ov);
+            }
+        }
     }
+    if (P.count < S.num_values && __any_sync(FULL, (ov >> 28) & 1u) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
     if (ci == S.n_chunks - 1 && lane == 0 && P.count + n_here < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
     const uint32_t room = P.count < S.num_values ? S.num_values - P.count : 0u;
     int32_t cx = P.a, cy = P.b;

@@ -54,9 +54,10 @@ __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t*
         bounds(lo16, hi16);
         LeanLane L = lean_front(win, head_f != 0u || end_in_chunk < WARP_CHUNK_BYTES, lo16, hi16, halo_in, w, acc, mul, lane_ov);
         L.excl = warp_exclusive_scan(L.cnt, L.total);
-        if (!t.exact_length) {
-            // DecodingUtils "pos" semantics: bytes after the last requested value belong to somebody else. Find the terminator
-            // of value #remaining; if it lies in this chunk, the stream ends there.
+        if (!t.exact_length || L.total - head_f - (WARP_CHUNK_BYTES - end_in_chunk) > remaining) {
+            // DecodingUtils "pos" semantics: bytes after the last requested value belong to somebody else (and a stream with an
+            // exact length that holds MORE values than numValues is read no further either: what follows must not raise the
+            // overlong flag). Find the terminator of value #remaining; if it lies in this chunk, the stream ends there.
             const int32_t first = (int32_t)L.excl - (int32_t)head_f;  // chunk-local index of the lane's first value
             const bool mine = remaining > 0u && (int32_t)remaining > first && (int32_t)remaining <= first + (int32_t)L.cnt;
             const unsigned b = __ballot_sync(FULL, mine);
@@ -628,7 +629,8 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* wsm
             inpos = (uint32_t)inexcept;
         }
         // ---- VariableByte tail over ALL remaining words (see warp_pfor_stream_smem) ----
-        uint32_t carry_halo = 0, ov = 0;
+        uint32_t carry_halo = 0, ov = 0, vb_carry = 0;
+        bool vb_long = false;
         for (uint32_t wbase = inpos; wbase < n_words; wbase += 128) {
             const uint32_t first_w = wbase + lane * 4u;
             uint4 win;
@@ -640,6 +642,7 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* wsm
             const uint32_t tail_f = 512u - 4u * valid_words;
             uint32_t w[4], acc, mul;
             LeanLane L = lean_front(win, false, 0, 16, carry_halo, w, acc, mul, ov);
+            vb_long |= vb_run_of_five(w, vb_carry);
             L.excl = warp_exclusive_scan(L.cnt, L.total);
             const uint32_t ctotal = L.total - tail_f;
             const uint32_t remaining = n - produced;
@@ -653,6 +656,7 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* wsm
             produced += ctotal;
         }
         if (produced != n) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);
+        if (__any_sync(FULL, vb_long)) PFOR_FAIL(COVT_ERR_VARINT_OVERLONG);
     }
 finish:
 #undef PFOR_FAIL
@@ -785,7 +789,8 @@ __device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t
         }
         // ---- VariableByte tail over ALL remaining words (VariableByte.uncompress): MSB SET ends a value, so flipping
         // the MSBs turns it into LEB128 for the chunk decoder (up to 5 bytes per value; the carry logic covers 4 + 1)
-        uint32_t carry_halo = 0, ov = 0;
+        uint32_t carry_halo = 0, ov = 0, vb_carry = 0;
+        bool vb_long = false;
         for (uint32_t wbase = inpos; wbase < n_words; wbase += 128) {
             const uint32_t first_w = wbase + lane * 4u;
             uint4 win;
@@ -797,6 +802,7 @@ __device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t
             const uint32_t tail_f = 512u - 4u * valid_words;  // zeroed bytes decode to fake 1-byte zeros behind the real values
             uint32_t w[4], acc, mul;
             LeanLane L = lean_front(win, false, 0, 16, carry_halo, w, acc, mul, ov);
+            vb_long |= vb_run_of_five(w, vb_carry);
             L.excl = warp_exclusive_scan(L.cnt, L.total);
             const uint32_t ctotal = L.total - tail_f;
             const uint32_t remaining = n - produced;
@@ -810,6 +816,7 @@ __device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t
             produced += ctotal;
         }
         if (produced != n) PFOR_FAIL(COVT_ERR_COUNT_MISMATCH);
+        if (__any_sync(FULL, vb_long)) PFOR_FAIL(COVT_ERR_VARINT_OVERLONG);
     }
 finish:
 #undef PFOR_FAIL

@@ -124,6 +124,22 @@ __device__ __forceinline__ LeanLane lean_front(uint4 win, bool partial, uint32_t
     return L;
 }
 
+// VariableByte tail of FastPFOR (bytes already flipped to LEB128 convention): a value may span 5 bytes. JavaFastPFOR does not
+// cap it — a 6th byte is added at shift 35 mod 32 = 3 — so a stream with FIVE consecutive non-final bytes decodes to garbage in
+// the reference; the decoder (and the oracle) flag it as COVT_ERR_VARINT_OVERLONG instead of imitating the wrap-around.
+// carry = continuation bits of the 5 bytes before the window (in: previous window, out: this one).
+__device__ __forceinline__ bool vb_run_of_five(const uint32_t w[4], uint32_t& carry)
+{
+    uint32_t m = 0;  // bit j = continuation bit of byte j of the lane's 16 bytes
+#pragma unroll
+    for (int k = 0; k < 4; k++) m |= (((((w[k] & 0x80808080u) >> 7) * 0x00204081u) >> 21) & 0xfu) << (4 * k);
+    uint32_t prev = __shfl_up_sync(FULL, m >> 11, 1);
+    if (lane_id() == 0) prev = carry;
+    carry = __shfl_sync(FULL, m >> 11, 31);
+    const uint32_t M = (m << 5) | (prev & 31u);
+    return (M & (M >> 1) & (M >> 2) & (M >> 3) & (M >> 4)) != 0u;
+}
+
 // Position (1-based byte offset inside the lane window) of the lane's m-th terminator, m >= 1. Rare path.
 __device__ __forceinline__ uint32_t lean_nth_terminator(uint32_t cm, uint32_t m)
 {

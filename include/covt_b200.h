@@ -112,7 +112,9 @@ enum covt_status {
     COVT_ERR_BAD_METADATA = 5,    /* unknown enum ordinal, first column not id/geometry (CovtParser.java:67-69) */
     COVT_ERR_UNSUPPORTED_ENCODING = 6, /* CovtParser.java:425-427,442-444,459-461,474-476,492-494,507-509,571 */
     COVT_ERR_UNSUPPORTED_GEOMETRY = 7, /* MULTIPOINT / ordinal > 5 (CovtParser.java:268-270) */
-    COVT_ERR_VARINT_OVERLONG = 8, /* a varint longer than the Java reader's cap (4 bytes int, 10 bytes long) */
+    COVT_ERR_VARINT_OVERLONG = 8, /* a varint longer than the Java reader's cap (4 bytes int, 10 bytes long; values follow the
+                                   * Java reader), or five consecutive non-final bytes in FastPFOR's VariableByte tail (the
+                                   * reference decodes garbage there; values unspecified) */
     COVT_ERR_COUNT_MISMATCH = 9,  /* stream decodes to a different number of values than numValues */
     COVT_ERR_TOPOLOGY = 10        /* counts in topology streams overrun their streams or the vertex buffer */
 };

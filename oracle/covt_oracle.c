@@ -437,6 +437,7 @@ int32_t covt_oracle_fastpfor_uncompress(const uint8_t* buf, uint32_t byte_length
      * last byte of a value, bytes little-endian inside each word, zero bytes are padding. */
     int32_t v = 0;
     int shift = 0;
+    int run = 0, overlong = 0; /* consecutive non-final bytes */
     for (uint32_t p = inpos; p < n_words; p++) {
         uint32_t val = be32(buf + 4 * (uint64_t)p);
         for (int s = 0; s < 32; s += 8) {
@@ -447,11 +448,17 @@ int32_t covt_oracle_fastpfor_uncompress(const uint8_t* buf, uint32_t byte_length
                 out[outpos++] = v;
                 v = 0;
                 shift = 0;
-            } else
+                run = 0;
+            } else {
                 shift += 7;
+                if (++run >= 5) overlong = 1;
+            }
         }
     }
     if (outpos != n) return COVT_ERR_COUNT_MISMATCH; /* Java would silently leave zeros; flagged instead */
+    /* Library policy shared with the product: VariableByte.uncompress has no length cap - a 6th byte is added at shift
+     * 35 mod 32 = 3 - so five consecutive non-final bytes make the reference decode garbage; flagged instead of imitated. */
+    if (overlong) return COVT_ERR_VARINT_OVERLONG;
     return COVT_OK;
 }
 
