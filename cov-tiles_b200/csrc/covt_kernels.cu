@@ -975,6 +975,30 @@ __global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_apply(ChunkState* state
     if (i < n) states[i] = excl;
 }
 
+// The chunk of a large stream that holds value #num_values: reports the bytes consumed up to its terminator and, when the
+// chunk goes on behind it, redoes the overlong check on the bytes before the cut only (rare; kept out of line).
+__device__ __noinline__ void k1b_stream_end(const BigStream& S, const K1Chunk& k, const LeanLane& L, uint32_t count_before, uint32_t halo_in, uint32_t& ov)
+{
+    const unsigned lane = lane_id();
+    const int64_t first = (int64_t)count_before + L.excl - k.head_f;  // stream index of the lane's first terminator (fakes negative)
+    const bool mine = (int64_t)S.num_values > first && (int64_t)S.num_values <= first + (int64_t)L.cnt;
+    const unsigned bm = __ballot_sync(FULL, mine);
+    uint32_t cut = 0;
+    if (mine) cut = lane * 16u + lean_nth_terminator(L.cm, (uint32_t)((int64_t)S.num_values - first));
+    cut = __shfl_sync(FULL, cut, bm ? __ffs(bm) - 1 : 0);
+    const uint32_t end_in_chunk = WARP_CHUNK_BYTES - k.tail_f;
+    if (!bm || cut > end_in_chunk) return;  // (a terminator behind the stream's bytes is a fake zero)
+    if (S.consumed_out && lane == 0) *S.consumed_out = (uint32_t)(k.off + cut - k.head);
+    if (cut < end_in_chunk) {
+        const uint32_t hi_cut = cut > lane * 16u ? min(16u, cut - lane * 16u) : 0u;
+        uint32_t w2[4], acc2, mul2, halo2 = halo_in;
+        int32_t c2, o2;
+        ov = 0;
+        const LeanLane L2 = lean_front(k.win, true, k.lo16, hi_cut, halo2, w2, acc2, mul2, ov);
+        lean_sum_lane<false>(w2, L2.cm, acc2, mul2, c2, o2, ov);
+    }
+}
+
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks, const ChunkState* states)
 {
@@ -999,28 +1023,8 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
     __syncwarp();
     const uint32_t n_here = L.total - k.head_f - k.tail_f;
     // bytes the reference reader consumes = position right after the terminator of value #num_values; what follows it is not
-    // read (and must not raise the overlong flag)
-    {
-        const int64_t first = (int64_t)P.count + L.excl - k.head_f;  // stream index of the lane's first terminator (fakes negative)
-        const bool mine = S.num_values > 0u && (int64_t)S.num_values > first && (int64_t)S.num_values <= first + (int64_t)L.cnt;
-        const unsigned bm = __ballot_sync(FULL, mine);
-        uint32_t cut = 0;
-        if (mine) cut = lane * 16u + lean_nth_terminator(L.cm, (uint32_t)((int64_t)S.num_values - first));
-        cut = __shfl_sync(FULL, cut, bm ? __ffs(bm) - 1 : 0);
-        const uint32_t end_in_chunk = WARP_CHUNK_BYTES - k.tail_f;
-        if (bm && cut <= end_in_chunk) {  // (a terminator behind the stream's bytes is a fake zero)
-            if (S.consumed_out && lane == 0) *S.consumed_out = (uint32_t)(k.off + cut - k.head);
-            if (cut < end_in_chunk) {
-                // rare: the chunk holds values beyond numValues; redo the overlong check on the bytes before the cut
-                const uint32_t hi_cut = cut > lane * 16u ? min(16u, cut - lane * 16u) : 0u;
-                uint32_t w2[4], acc2, mul2, halo2 = halo_in;
-                int32_t c2, o2;
-                ov = 0;
-                const LeanLane L2 = lean_front(k.win, true, k.lo16, hi_cut, halo2, w2, acc2, mul2, ov);
-                lean_sum_lane<false>(w2, L2.cm, acc2, mul2, c2, o2, ov);
-            }
-        }
-    }
+    // read (and must not raise the overlong flag). Only the chunk that holds that value looks for it.
+    if (P.count < S.num_values && P.count + n_here >= S.num_values) k1b_stream_end(S, k, L, P.count, halo_in, ov);
     if (P.count < S.num_values && __any_sync(FULL, (ov >> 28) & 1u) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
     if (ci == S.n_chunks - 1 && lane == 0 && P.count + n_here < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
     const uint32_t room = P.count < S.num_values ? S.num_values - P.count : 0u;

@@ -604,17 +604,31 @@ __device__ __noinline__ void warp_pfor_stream(const StreamTask& t, uint32_t* wsm
                     bcpos++;
                     const int index = (int)maxbits - (int)b;
                     __syncwarp();
-                    // atomicOr: a (corrupt) stream may list a position twice; the Java patch loop ORs both exceptions in
+                    // A well-formed block lists every position once. A corrupt one may repeat a position, and the Java patch loop ORs
+                    // every listed exception in: only then (two lanes of one batch on one word) must the update be atomic; a
+                    // batch whose positions increase strictly (as every encoder writes them) cannot repeat one.
+                    auto patch = [&](auto val_of) {
+                        for (uint32_t e0 = 0; e0 < cexcept; e0 += 32) {
+                            const uint32_t e = e0 + lane;
+                            const bool have = e < cexcept;
+                            const uint32_t pos = have ? BC_BYTE(bcpos + e) : 256u + lane;
+                            const uint32_t before = __shfl_up_sync(FULL, pos, 1);
+                            const bool repeated = !__all_sync(FULL, lane == 0 || pos > before);  // the encoder lists positions in increasing order
+                            if (have) {
+                                if (repeated) atomicOr(&stage[pos], val_of(e));
+                                else stage[pos] |= val_of(e);
+                            }
+                        }
+                    };
                     if (index == 1) {
-                        for (uint32_t e = lane; e < cexcept; e += 32) atomicOr(&stage[BC_BYTE(bcpos + e)], 1u << (b & 31u));
+                        patch([&](uint32_t) { return 1u << (b & 31u); });
                     } else {
                         if (index < 2 || index > 32 || !(bitmap & (1u << (index - 1)))) PFOR_FAIL(COVT_ERR_BAD_METADATA);
                         const uint32_t ebase = __shfl_sync(FULL, exc_base, index - 1);
                         const uint32_t esize = __shfl_sync(FULL, exc_size, index - 1);
                         const uint32_t eptr = __shfl_sync(FULL, exc_ptr, index - 1);
                         if (eptr + cexcept > esize) PFOR_FAIL(COVT_ERR_TRUNCATED);
-                        for (uint32_t e = lane; e < cexcept; e += 32)
-                            atomicOr(&stage[BC_BYTE(bcpos + e)], unpack_packed(base, ebase, eptr + e, (uint32_t)index) << (b & 31u));
+                        patch([&](uint32_t e) { return unpack_packed(base, ebase, eptr + e, (uint32_t)index) << (b & 31u); });
                         if (lane == (unsigned)(index - 1)) exc_ptr += cexcept;
                     }
                     bcpos += cexcept;
@@ -764,16 +778,29 @@ __device__ __noinline__ void warp_pfor_stream_smem(const StreamTask& t, uint32_t
                     bcpos++;
                     const int index = (int)maxbits - (int)b;
                     __syncwarp();
+                    // (see warp_pfor_stream: atomic only when a corrupt block repeats a position inside one batch of 32)
+                    auto patch = [&](auto val_of) {
+                        for (uint32_t e0 = 0; e0 < cexcept; e0 += 32) {
+                            const uint32_t e = e0 + lane;
+                            const bool have = e < cexcept;
+                            const uint32_t pos = have ? BC_BYTE(bcpos + e) : 256u + lane;
+                            const uint32_t before = __shfl_up_sync(FULL, pos, 1);
+                            const bool repeated = !__all_sync(FULL, lane == 0 || pos > before);  // the encoder lists positions in increasing order
+                            if (have) {
+                                if (repeated) atomicOr(&stage[pos], val_of(e));
+                                else stage[pos] |= val_of(e);
+                            }
+                        }
+                    };
                     if (index == 1) {
-                        for (uint32_t e = lane; e < cexcept; e += 32) atomicOr(&stage[BC_BYTE(bcpos + e)], 1u << (b & 31u));
+                        patch([&](uint32_t) { return 1u << (b & 31u); });
                     } else {
                         if (index < 2 || index > 32 || !(bitmap & (1u << (index - 1)))) PFOR_FAIL(COVT_ERR_BAD_METADATA);
                         const uint32_t ebase = __shfl_sync(FULL, exc_base, index - 1);
                         const uint32_t esize = __shfl_sync(FULL, exc_size, index - 1);
                         const uint32_t eptr = __shfl_sync(FULL, exc_ptr, index - 1);
                         if (eptr + cexcept > esize) PFOR_FAIL(COVT_ERR_TRUNCATED);
-                        for (uint32_t e = lane; e < cexcept; e += 32)
-                            atomicOr(&stage[BC_BYTE(bcpos + e)], sm_unpack(sw, ebase, eptr + e, (uint32_t)index) << (b & 31u));
+                        patch([&](uint32_t e) { return sm_unpack(sw, ebase, eptr + e, (uint32_t)index) << (b & 31u); });
                         if (lane == (unsigned)(index - 1)) exc_ptr += cexcept;
                     }
                     bcpos += cexcept;
