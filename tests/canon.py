@@ -55,3 +55,29 @@ def layer_slices(layers_row, buffers, abi):
     r = buffers[abi.BUF_A_RING_OFFSETS][int(o[abi.BUF_A_RING_OFFSETS]):][:int(L["n_rings"]) + 1]
     c = buffers[abi.BUF_A_COORDS][int(o[abi.BUF_A_COORDS]):][:2 * int(L["n_coords"])]
     return types, g, p, r, c
+
+
+def property_token(v):
+    """Canonical token of one property value (None = the feature has no such property). Numbers: integers in decimal, reals as
+    the hex of their float32 image (COVT FLOAT columns are 32-bit; MVT may carry the same value as float or double)."""
+    import struct
+    if v is None:
+        return "~"
+    if isinstance(v, bool):
+        return "b1" if v else "b0"
+    if isinstance(v, int):
+        return "i%d" % v
+    if isinstance(v, float):
+        return "f" + struct.pack("<f", v).hex()
+    return "s" + str(v)
+
+
+def property_digest(values):
+    """blake2b digest of one property column: the tokens of all features in feature order."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for v in values:
+        t = property_token(v).encode("utf-8")
+        h.update(len(t).to_bytes(4, "little"))
+        h.update(t)
+    return h.hexdigest()

@@ -4,6 +4,7 @@
                             (data files, not sources; the GPU box has no /root/reference)
   mvt_geometry_digests.json per (source, tile, layer): feature / ring / vertex counts + a blake2b digest of the
                             canonical geometry read from the partner .mvt/.pbf (tests/mvt.py, tests/canon.py)
+  mvt_property_digests.json per (source, tile, layer, property key): features carrying the key + a digest of the value column
 
 Usage: python tests/golden/make_golden.py [/root/reference]
 """
@@ -53,6 +54,32 @@ def main(ref):
     with open(out, "w") as fh:
         json.dump(digests, fh, indent=0, sort_keys=True)
     print("wrote", out, len(digests), "layers")
+
+    # property columns: per (source, tile, layer, key) the number of features that carry the key and a digest of
+    # the value column in feature order (tests/canon.property_digest); pins oracle/properties.py
+    pdig = {}
+    for src, ext in (("omt", "mvt"), ("amazon", "pbf")):
+        for f in sorted(glob.glob(os.path.join(fx, src, "mvt", "*." + ext))):
+            tile = os.path.basename(f)[: -len(ext) - 1]
+            if not os.path.exists(os.path.join(fx, src, "covt", tile + ".covt")) or (src == "omt" and tile == "3_4_5"):
+                continue
+            for layer in mvt.read_layers(open(f, "rb").read(), with_properties=True):
+                # the converter folds the two spellings of a localized key (`name:de`, `name_de`) into ONE sub-column; wherever
+                # both exist on a feature of the fixtures their values agree, so the golden column is their union under the
+                # `_` spelling
+                keys = sorted(set(k.replace(":", "_") for pr in layer["properties"] for k in pr))
+                for k in keys:
+                    col = []
+                    for pr in layer["properties"]:
+                        vals = [v[1] for kk, v in pr.items() if kk.replace(":", "_") == k]
+                        assert all(v == vals[0] for v in vals), (f, layer["name"], k, vals)
+                        col.append(vals[0] if vals else None)
+                    pdig["%s/%s/%s/%s" % (src, tile, layer["name"], k)] = {
+                        "present": sum(v is not None for v in col), "digest": canon.property_digest(col)}
+    out = os.path.join(HERE, "mvt_property_digests.json")
+    with open(out, "w") as fh:
+        json.dump(pdig, fh, indent=0, sort_keys=True)
+    print("wrote", out, len(pdig), "property columns")
 
 
 if __name__ == "__main__":

@@ -85,30 +85,62 @@ def _decode_geometry(cmds, gtype):
     return rings
 
 
-def read_layers(data):
-    """-> list of dict(name, extent, features=[(id, gtype, rings)])"""
+def _value(buf, start, end):
+    """vector_tile.Value -> (kind, python value); kind in string/float/double/int/uint/sint/bool."""
+    import struct
+    for fn, wt, v in _fields(buf, start, end):
+        if fn == 1:
+            return "string", bytes(buf[v[0]:v[1]]).decode("utf-8")
+        if fn == 2:
+            return "float", struct.unpack("<f", bytes(buf[v[0]:v[1]]))[0]
+        if fn == 3:
+            return "double", struct.unpack("<d", bytes(buf[v[0]:v[1]]))[0]
+        if fn == 4:
+            return "int", v - (1 << 64) if v >= (1 << 63) else v
+        if fn == 5:
+            return "uint", v
+        if fn == 6:
+            return "sint", (v >> 1) ^ -(v & 1)
+        if fn == 7:
+            return "bool", bool(v)
+    return "none", None
+
+
+def read_layers(data, with_properties=False):
+    """-> list of dict(name, extent, features=[(id, gtype, rings)]); with_properties adds
+    properties=[{key: (kind, value)} per feature] (vector_tile.Layer keys / values / Feature.tags)."""
     buf = memoryview(data)
     layers = []
     for fn, wt, v in _fields(buf, 0, len(buf)):
         if fn != 3 or wt != 2:
             continue
-        name, extent, feats = None, 4096, []
+        name, extent, feats, keys, values, tags = None, 4096, [], [], [], []
         for lfn, lwt, lv in _fields(buf, v[0], v[1]):
             if lfn == 1:
                 name = bytes(buf[lv[0]:lv[1]]).decode("utf-8")
             elif lfn == 5:
                 extent = lv
+            elif lfn == 3 and with_properties:
+                keys.append(bytes(buf[lv[0]:lv[1]]).decode("utf-8"))
+            elif lfn == 4 and with_properties:
+                values.append(_value(buf, lv[0], lv[1]))
             elif lfn == 2:
-                fid, gtype, cmds = 0, 0, []
+                fid, gtype, cmds, ftags = 0, 0, [], []
                 for ffn, fwt, fv in _fields(buf, lv[0], lv[1]):
                     if ffn == 1:
                         fid = fv
+                    elif ffn == 2 and with_properties:
+                        ftags = _packed_uint32(buf, fv[0], fv[1])
                     elif ffn == 3:
                         gtype = fv
                     elif ffn == 4:
                         cmds = _packed_uint32(buf, fv[0], fv[1])
                 feats.append((fid, gtype, _decode_geometry(cmds, gtype)))
-        layers.append({"name": name, "extent": extent, "features": feats})
+                tags.append(ftags)
+        layer = {"name": name, "extent": extent, "features": feats}
+        if with_properties:
+            layer["properties"] = [{keys[t[i]]: values[t[i + 1]] for i in range(0, len(t) - 1, 2)} for t in tags]
+        layers.append(layer)
     return layers
 
 

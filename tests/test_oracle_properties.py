@@ -1,0 +1,63 @@
+"""CPU: pins the property-column oracle (oracle/properties.py, SURVEY §8 f1 — the next row after the geometry + id path) against
+the reference's own data: the property values of the partner .mvt/.pbf tiles of the 102 OMT + Amazon fixtures, committed as
+digests by tests/golden/make_golden.py (the JVM is absent, the Java decoder cannot run here).
+
+Every stream of every property column must consume exactly its declared byteLength, the gen-2b walk must end at EOF, and
+  * every COVT property column whose key exists in the MVT layer must equal the MVT value column feature by feature;
+  * a COVT column whose key the MVT layer does not have must be entirely null (the converter's localized-name splitting
+    creates such empty sub-columns, e.g. `name:xx` for Amazon's `_name_xx` keys).
+The 27 Bing tiles have no partner: their FLOAT and BOOLEAN columns are only checked for clean, byte-exact consumption."""
+import json
+import os
+
+import canon
+import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _golden():
+    with open(os.path.join(HERE, "golden", "mvt_property_digests.json")) as fh:
+        return json.load(fh)
+
+
+def test_property_columns_equal_partner_mvt(oracle, fixtures):
+    from oracle import properties as P
+    gold = _golden()
+    matched = empty = values = 0
+    kinds = set()
+    for name, data in fixtures:
+        src, tile = name.split("/")
+        if src == "bing":
+            continue
+        for layer_name, props in P.decode_property_columns(data):
+            for key, col in props.items():
+                # golden keys use the `_` spelling of localized keys (`name:de` and `name_de` are one sub-column in COVT)
+                g = gold.get("%s/%s/%s/%s" % (src, tile, layer_name, key.replace(":", "_")))
+                if g is None:
+                    assert all(v is None for v in col), "%s/%s: column %s has values but the MVT layer has no such key" % (name, layer_name, key)
+                    empty += 1
+                    continue
+                assert sum(v is not None for v in col) == g["present"], "%s/%s/%s: present count" % (name, layer_name, key)
+                assert canon.property_digest(col) == g["digest"], "%s/%s/%s: values differ from the MVT" % (name, layer_name, key)
+                matched += 1
+                values += g["present"]
+                kinds.update(type(v).__name__ for v in col if v is not None)
+    assert matched >= 9000 and values >= 2_500_000, (matched, values)
+    assert {"str", "int", "bool"} <= kinds
+    # the converter drops a few MVT keys (SURVEY §4.4-style census, facts about the fixture bytes): they must stay few
+    assert empty <= 3600
+
+
+def test_bing_property_columns_decode_cleanly(oracle, fixtures):
+    from oracle import properties as P
+    n_cols = 0
+    kinds = set()
+    for name, data in fixtures:
+        if not name.startswith("bing/"):
+            continue
+        for layer_name, props in P.decode_property_columns(data):
+            for key, col in props.items():
+                n_cols += 1
+                kinds.update(type(v).__name__ for v in col if v is not None)
+    assert n_cols >= 800 and {"str", "int", "float", "bool"} <= kinds
