@@ -341,3 +341,62 @@ def test_stream_mutation_fuzz_against_oracle(covt, oracle, gen, decoder, seed):
     cases = _fuzz_cases(covt.abi, gen, seed)
     assert len(cases) > 700
     _batch_check(covt, oracle, decoder, cases)
+
+
+def test_property_streams_of_the_fixtures(covt, oracle, decoder, fixtures):
+    """SURVEY §8 f1, first GPU step: every listed stream of every property column of the 129 fixture tiles (present bitsets,
+    INT_64 data, dictionary indices and lengths: ~28 000 streams) through covt_decode_streams in ONE call — the codecs are the
+    ones of the geometry path (Byte-RLE, RLE signed / unsigned, zigzag varints). Values and consumed bytes equal the oracle's
+    (which tests/test_oracle_properties.py pins on the MVT property values). FLOAT data and dictionary bytes are plain copies
+    and need no kernel."""
+    from oracle import properties as P
+    abi = covt.abi
+    blob = bytearray()
+    wanted = []  # (op, offset, byte_length, num_values)
+    for name, data in fixtures:
+        base = len(blob)
+        blob += data
+        for L in P.walk_gen2b(bytes(data)):
+            F = L["num_features"]
+            for c in L["columns"]:
+                if c["data_type"] == P.DT2_GEOMETRY or (c["name"] == "id" and c is L["columns"][0]):
+                    continue
+                for s in c["streams"]:
+                    nm, enc, nv = s["name"], s["encoding"], s["num_values"]
+                    if s["byte_length"] == 0:
+                        continue
+                    if nm.startswith("present"):
+                        op, n = abi.OP_BYTE_RLE, (F + 7) // 8
+                    elif c["data_type"] == P.DT2_BOOLEAN:
+                        op, n = abi.OP_BYTE_RLE, (nv + 7) // 8
+                    elif c["data_type"] in (P.DT2_FLOAT, P.DT2_DOUBLE) or nm == "dictionary":
+                        continue
+                    elif c["data_type"] in (P.DT2_INT_64, P.DT2_UINT_64):
+                        signed = c["data_type"] == P.DT2_INT_64
+                        op = {abi.ENC_RLE: abi.OP_RLE_S64 if signed else abi.OP_RLE_U64, abi.ENC_VARINT_ZIG_ZAG: abi.OP_VARINT_ZZ,
+                              abi.ENC_VARINT_DELTA_ZIG_ZAG: abi.OP_VARINT_ZZ_DELTA, abi.ENC_VARINT: abi.OP_VARINT_U32}.get(enc)
+                        if op is None:
+                            continue
+                        n = nv
+                    else:  # dictionary indices (`data` / localized sub-keys) and `length`: unsigned RLE
+                        op, n = abi.OP_RLE_U64, nv
+                    wanted.append((op, base + s["offset"], s["byte_length"], n))
+    assert len(wanted) > 25000
+    blob = np.frombuffer(bytes(blob) + bytes(64), dtype=np.uint8)
+    descs = (abi.StreamDesc * len(wanted))()
+    for i, (op, off, bl, n) in enumerate(wanted):
+        descs[i] = abi.StreamDesc(byte_offset=off, byte_length=bl, num_values=n, op=op)
+    res = decoder.decode_streams(blob, descs, abi.FLAG_DEFAULT)
+    arena = res.buffer(abi.BUF_STREAM_ARENA)
+    seen = {}
+    for i, (op, off, bl, n) in enumerate(wanted):
+        d = descs[i]
+        want, wst, wcons = oracle.decode_stream(blob, op, byte_offset=off, byte_length=bl, num_values=n)
+        assert wst == 0 and wcons == bl, (i, abi.OP_NAMES[op], wst, wcons, bl)
+        assert d.status == 0 and d.bytes_consumed == bl and d.out_count == len(want), (i, abi.OP_NAMES[op], d.status, d.bytes_consumed, bl)
+        dt = np.dtype(abi.op_dtype(op))
+        got = arena[d.out_offset:d.out_offset + d.out_count * dt.itemsize].view(dt)
+        assert np.array_equal(got, want), (i, abi.OP_NAMES[op])
+        seen[abi.OP_NAMES[op]] = seen.get(abi.OP_NAMES[op], 0) + 1
+    assert seen.get("byte_rle", 0) > 10000 and seen.get("rle_u64", 0) > 10000 and seen.get("rle_s64", 0) > 500
+    res.free()
