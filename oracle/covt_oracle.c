@@ -1320,3 +1320,356 @@ void covt_oracle_result_free(covt_oracle_result* r)
     free(r->first_layer);
     free(r);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Property columns, gen-2b                      J/decoder/CovtParser.java:276-390
+ * Layout facts established on the 129 fixtures and pinned on the partner MVT tiles by
+ * tests/test_oracle_properties.py (see oracle/properties.py, the first statement of this code):
+ * property payloads follow the geometry payload of their layer in column-metadata order.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { void* p; uint64_t n, cap; size_t elem; } vec_t;
+static void* vec_grow(vec_t* v, uint64_t add)
+{
+    if (v->n + add > v->cap) {
+        uint64_t cap = v->cap ? v->cap : 1024;
+        while (cap < v->n + add) cap *= 2;
+        void* q = realloc(v->p, (size_t)cap * v->elem);
+        if (!q) return NULL;
+        v->p = q;
+        v->cap = cap;
+    }
+    void* at = (uint8_t*)v->p + (size_t)v->n * v->elem;
+    memset(at, 0, (size_t)add * v->elem);
+    v->n += add;
+    return at;
+}
+
+typedef struct { uint64_t noff; uint32_t nlen; uint32_t nv, bl, enc; uint64_t off; } pstream_t;
+
+/* gen-2 data type byte -> COVT_DT_* */
+static int dt_of_gen2(uint32_t g)
+{
+    switch (g) {
+    case 0: return COVT_DT_STRING;
+    case 1: return COVT_DT_FLOAT;
+    case 2: return COVT_DT_DOUBLE;
+    case 3: return COVT_DT_INT_64;
+    case 4: return COVT_DT_UINT_64;
+    case 5: return COVT_DT_BOOLEAN;
+    default: return -1;
+    }
+}
+
+static uint32_t popcount_bits(const uint8_t* b, uint32_t n_bits)
+{
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < n_bits; i++) c += (b[i >> 3] >> (i & 7)) & 1u;
+    return c;
+}
+
+typedef struct {
+    vec_t cols, dicts, validity, i64, f32, f64, bools, didx, doff;
+} props_build_t;
+
+/* present stream: BOOLEAN_RLE = Byte-RLE of ceil(F / 8) bitset bytes (CovtParser.java:295-296) */
+static int32_t prop_bitset(const uint8_t* blob, const pstream_t* s, uint32_t n_bits, vec_t* dst, uint64_t* at)
+{
+    uint32_t nbytes = (n_bits + 7) / 8;
+    *at = dst->n;
+    uint8_t* out = (uint8_t*)vec_grow(dst, nbytes);
+    if (!out && nbytes) return COVT_ERR_OOM;
+    uint64_t pos = s->off;
+    int32_t rc = covt_oracle_decode_byte_rle(blob, s->off + s->bl, &pos, nbytes, out);
+    if (rc != COVT_OK) return rc;
+    return pos == s->off + s->bl ? COVT_OK : COVT_ERR_COUNT_MISMATCH;
+}
+
+static int32_t prop_rle(const uint8_t* blob, const pstream_t* s, int is_signed, int64_t* out)
+{
+    uint64_t pos = s->off;
+    int32_t rc = covt_oracle_decode_rle(blob, s->off + s->bl, &pos, s->nv, is_signed, out);
+    if (rc != COVT_OK) return rc;
+    return pos == s->off + s->bl ? COVT_OK : COVT_ERR_COUNT_MISMATCH;
+}
+
+static const pstream_t* find_stream(const uint8_t* blob, const pstream_t* ss, uint32_t n, const char* name)
+{
+    for (uint32_t i = 0; i < n; i++)
+        if (name_is(blob, ss[i].noff, ss[i].nlen, name)) return &ss[i];
+    return NULL;
+}
+
+static covt_prop_column* new_column(props_build_t* B, uint32_t tile, uint32_t layer, uint64_t noff, uint32_t nlen, int dt, uint32_t ct, uint32_t F)
+{
+    covt_prop_column* c = (covt_prop_column*)vec_grow(&B->cols, 1);
+    if (!c) return NULL;
+    c->tile = tile;
+    c->layer = layer;
+    c->name_offset = noff;
+    c->name_length = nlen;
+    c->data_type = (uint8_t)dt;
+    c->column_type = (uint8_t)ct;
+    c->num_features = F;
+    return c;
+}
+
+/* RLE dictionary indices of the present features -> dict_index arena (CovtParser.java:350-365) */
+static int32_t prop_indices(const uint8_t* blob, props_build_t* B, covt_prop_column* c, const pstream_t* present, const pstream_t* data,
+                            uint32_t n_dict)
+{
+    c->value_kind = COVT_PV_DICT_INDEX;
+    int32_t rc = prop_bitset(blob, present, c->num_features, &B->validity, &c->validity_offset);
+    if (rc != COVT_OK) return rc;
+    c->num_values = popcount_bits((const uint8_t*)B->validity.p + c->validity_offset, c->num_features);
+    if (data->nv != c->num_values) return COVT_ERR_COUNT_MISMATCH;
+    int64_t* tmp = (int64_t*)malloc(((size_t)data->nv + 1) * sizeof(int64_t));
+    if (!tmp) return COVT_ERR_OOM;
+    rc = prop_rle(blob, data, 0, tmp);
+    c->values_offset = B->didx.n;
+    int32_t* out = (int32_t*)vec_grow(&B->didx, data->nv);
+    if (rc == COVT_OK && !out && data->nv) rc = COVT_ERR_OOM;
+    for (uint32_t i = 0; rc == COVT_OK && i < data->nv; i++) {
+        if (tmp[i] < 0 || (uint64_t)tmp[i] >= n_dict) rc = COVT_ERR_TOPOLOGY; /* Java: ArrayIndexOutOfBounds on dictionaryData[index] */
+        else out[i] = (int32_t)tmp[i];
+    }
+    free(tmp);
+    return rc;
+}
+
+/* length (RLE) + dictionary (UTF-8 bytes) -> dictionaries[], dict_offsets (CovtParser.java:379-390) */
+static int32_t prop_dictionary(const uint8_t* blob, props_build_t* B, uint32_t tile, uint32_t layer, const pstream_t* length, const pstream_t* dict,
+                               uint32_t* index)
+{
+    *index = (uint32_t)B->dicts.n;
+    covt_prop_dictionary* d = (covt_prop_dictionary*)vec_grow(&B->dicts, 1);
+    if (!d) return COVT_ERR_OOM;
+    d->tile = tile;
+    d->layer = layer;
+    d->n_entries = length->nv;
+    d->bytes_offset = dict->off;
+    d->n_bytes = dict->bl;
+    d->offsets_offset = B->doff.n;
+    int64_t* tmp = (int64_t*)malloc(((size_t)length->nv + 1) * sizeof(int64_t));
+    if (!tmp) return COVT_ERR_OOM;
+    int32_t rc = prop_rle(blob, length, 0, tmp);
+    int32_t* off = (int32_t*)vec_grow(&B->doff, (uint64_t)length->nv + 1);
+    if (rc == COVT_OK && !off) rc = COVT_ERR_OOM;
+    uint64_t run = 0;
+    for (uint32_t i = 0; rc == COVT_OK && i < length->nv; i++) {
+        if (tmp[i] < 0 || run + (uint64_t)tmp[i] > dict->bl) rc = COVT_ERR_TRUNCATED;
+        else { off[i] = (int32_t)run; run += (uint64_t)tmp[i]; }
+    }
+    if (rc == COVT_OK) {
+        off[length->nv] = (int32_t)run;
+        if (run != dict->bl) rc = COVT_ERR_COUNT_MISMATCH;
+    }
+    free(tmp);
+    return rc;
+}
+
+static int32_t prop_column(const uint8_t* blob, props_build_t* B, uint32_t tile, uint32_t layer, uint64_t noff, uint32_t nlen, int dt, uint32_t ct,
+                           uint32_t F, const pstream_t* ss, uint32_t n_streams)
+{
+    const pstream_t* present = find_stream(blob, ss, n_streams, "present");
+    const pstream_t* data = find_stream(blob, ss, n_streams, "data");
+    if (dt == COVT_DT_STRING && ct == COVT_CT_LOCALIZED_DICTIONARY) {
+        const pstream_t* length = find_stream(blob, ss, n_streams, "length");
+        const pstream_t* dict = find_stream(blob, ss, n_streams, "dictionary");
+        if (!length || !dict) return COVT_ERR_BAD_METADATA;
+        uint32_t di;
+        int32_t rc = prop_dictionary(blob, B, tile, layer, length, dict, &di);
+        /* pairs (present_<s>, <s>) in listed order */
+        for (uint32_t i = 0; i + 1 < n_streams; i++) {
+            const pstream_t* p = &ss[i];
+            if (p->nlen <= 8 || memcmp(blob + p->noff, "present_", 8) != 0) continue;
+            const pstream_t* sub = NULL;
+            for (uint32_t k = 0; k < n_streams; k++)
+                if (ss[k].nlen == p->nlen - 8 && memcmp(blob + ss[k].noff, blob + p->noff + 8, ss[k].nlen) == 0) { sub = &ss[k]; break; }
+            covt_prop_column* c = new_column(B, tile, layer, noff, nlen, dt, ct, F);
+            if (!c) return COVT_ERR_OOM;
+            c->sub_offset = p->noff + 8;
+            c->sub_length = p->nlen - 8;
+            c->dictionary = di;
+            c->status = rc != COVT_OK ? (uint32_t)rc : (sub ? (uint32_t)prop_indices(blob, B, c, p, sub, length->nv) : COVT_ERR_BAD_METADATA);
+        }
+        return COVT_OK;
+    }
+    covt_prop_column* c = new_column(B, tile, layer, noff, nlen, dt, ct, F);
+    if (!c) return COVT_ERR_OOM;
+    if (!data) { c->status = COVT_ERR_BAD_METADATA; return COVT_OK; }
+    int32_t rc = COVT_OK;
+    if (dt == COVT_DT_BOOLEAN) {
+        /* HEAD: data = bitset over all features, no present stream (CovtParser.java:280-290). The gen-2b fixtures list a present
+         * stream for most boolean columns; data then holds one bit per PRESENT feature (dense, like every other type). */
+        c->value_kind = COVT_PV_BOOL;
+        rc = prop_bitset(blob, data, data->nv, &B->bools, &c->values_offset);
+        if (rc == COVT_OK) {
+            if (present) rc = prop_bitset(blob, present, F, &B->validity, &c->validity_offset);
+            else {
+                c->validity_offset = B->validity.n;
+                uint8_t* v = (uint8_t*)vec_grow(&B->validity, (F + 7) / 8);
+                if (!v && F) rc = COVT_ERR_OOM;
+                for (uint32_t i = 0; rc == COVT_OK && i < F; i++) v[i >> 3] |= (uint8_t)(1u << (i & 7));
+            }
+        }
+        if (rc == COVT_OK) {
+            c->num_values = popcount_bits((const uint8_t*)B->validity.p + c->validity_offset, F);
+            if (data->nv != c->num_values) rc = COVT_ERR_COUNT_MISMATCH;
+        }
+        c->status = (uint32_t)rc;
+        return COVT_OK;
+    }
+    if (!present) { c->status = COVT_ERR_BAD_METADATA; return COVT_OK; }
+    if (dt == COVT_DT_STRING) {
+        if (ct != COVT_CT_DICTIONARY) { c->status = COVT_ERR_UNSUPPORTED_ENCODING; return COVT_OK; } /* CovtParser.java:345-347 */
+        const pstream_t* length = find_stream(blob, ss, n_streams, "length");
+        const pstream_t* dict = find_stream(blob, ss, n_streams, "dictionary");
+        if (!length || !dict) { c->status = COVT_ERR_BAD_METADATA; return COVT_OK; }
+        rc = prop_dictionary(blob, B, tile, layer, length, dict, &c->dictionary);
+        if (rc == COVT_OK) rc = prop_indices(blob, B, c, present, data, length->nv);
+        c->status = (uint32_t)rc;
+        return COVT_OK;
+    }
+    rc = prop_bitset(blob, present, F, &B->validity, &c->validity_offset);
+    if (rc == COVT_OK) {
+        c->num_values = popcount_bits((const uint8_t*)B->validity.p + c->validity_offset, F);
+        if (data->nv != c->num_values) rc = COVT_ERR_COUNT_MISMATCH;
+    }
+    if (rc == COVT_OK && (dt == COVT_DT_INT_64 || dt == COVT_DT_UINT_64)) {
+        c->value_kind = COVT_PV_I64;
+        c->values_offset = B->i64.n;
+        int64_t* out = (int64_t*)vec_grow(&B->i64, data->nv);
+        if (!out && data->nv) rc = COVT_ERR_OOM;
+        else if (data->enc == COVT_ENC_RLE) rc = prop_rle(blob, data, dt == COVT_DT_INT_64, out); /* :299-301 */
+        else if (data->enc == COVT_ENC_VARINT_ZIG_ZAG || data->enc == COVT_ENC_VARINT_DELTA_ZIG_ZAG || data->enc == COVT_ENC_VARINT) {
+            /* int varints widened to long (CovtParser.java:303-311, "TODO: refactor to use long instead of int") */
+            int32_t* tmp = (int32_t*)malloc(((size_t)data->nv + 1) * sizeof(int32_t));
+            uint64_t pos = data->off;
+            int overlong = 0;
+            if (!tmp) rc = COVT_ERR_OOM;
+            else if (data->enc == COVT_ENC_VARINT_ZIG_ZAG) rc = covt_oracle_decode_zigzag_varint(blob, data->off + data->bl, &pos, data->nv, tmp, &overlong);
+            else if (data->enc == COVT_ENC_VARINT_DELTA_ZIG_ZAG) rc = covt_oracle_decode_zigzag_delta_varint(blob, data->off + data->bl, &pos, data->nv, tmp, &overlong);
+            else rc = covt_oracle_decode_varint(blob, data->off + data->bl, &pos, data->nv, tmp, &overlong);
+            if (rc == COVT_OK && pos != data->off + data->bl) rc = COVT_ERR_COUNT_MISMATCH;
+            if (rc == COVT_OK && overlong) rc = COVT_ERR_VARINT_OVERLONG;
+            for (uint32_t i = 0; tmp && i < data->nv; i++) out[i] = (int64_t)tmp[i];
+            free(tmp);
+        } else rc = COVT_ERR_UNSUPPORTED_ENCODING; /* :313-315 */
+    } else if (rc == COVT_OK && (dt == COVT_DT_FLOAT || dt == COVT_DT_DOUBLE)) {
+        /* DecodingUtils.decodeFloatsLE :446-453: little-endian IEEE values of the present features */
+        const uint32_t es = dt == COVT_DT_FLOAT ? 4u : 8u;
+        c->value_kind = dt == COVT_DT_FLOAT ? COVT_PV_F32 : COVT_PV_F64;
+        vec_t* dst = dt == COVT_DT_FLOAT ? &B->f32 : &B->f64;
+        c->values_offset = dst->n;
+        if ((uint64_t)data->nv * es != data->bl) rc = COVT_ERR_COUNT_MISMATCH;
+        else {
+            void* out = vec_grow(dst, data->nv);
+            if (!out && data->nv) rc = COVT_ERR_OOM;
+            else memcpy(out, blob + data->off, data->bl); /* the hosts this runs on are little-endian */
+        }
+    } else if (rc == COVT_OK) rc = COVT_ERR_UNSUPPORTED_ENCODING; /* "Data type not supported", :368-370 */
+    c->status = (uint32_t)rc;
+    return COVT_OK;
+}
+
+static int32_t props_of_tile(const uint8_t* blob, uint64_t begin, uint64_t end, uint32_t tile, props_build_t* B)
+{
+    cur_t c = {blob, begin, end, 0};
+    (void)c_varint(&c);
+    uint32_t num_layers = c_varint(&c);
+    if (c.err) return COVT_ERR_TRUNCATED;
+    for (uint32_t li = 0; li < num_layers; li++) {
+        uint64_t loff; uint32_t llen;
+        c_string(&c, &loff, &llen);
+        (void)c_varint(&c); /* extent */
+        uint32_t F = c_varint(&c);
+        uint32_t n_cols = c_varint(&c);
+        if (c.err) return COVT_ERR_TRUNCATED;
+        /* metadata of all columns first (the payload follows the whole layer header) */
+        typedef struct { uint64_t noff; uint32_t nlen, dt, ct, first, n; int is_id, is_geom; } pcol_t;
+        pcol_t* cols = (pcol_t*)calloc((size_t)n_cols + 1, sizeof(pcol_t));
+        vec_t streams = {NULL, 0, 0, sizeof(pstream_t)};
+        int32_t rc = cols ? COVT_OK : COVT_ERR_OOM;
+        for (uint32_t ci = 0; rc == COVT_OK && ci < n_cols; ci++) {
+            pcol_t* pc = &cols[ci];
+            c_string(&c, &pc->noff, &pc->nlen);
+            pc->dt = c_byte(&c);
+            pc->ct = c_byte(&c);
+            pc->n = c_varint(&c);
+            if (c.err) { rc = COVT_ERR_TRUNCATED; break; }
+            pc->is_id = ci == 0 && name_is(blob, pc->noff, pc->nlen, "id");
+            pc->is_geom = pc->dt == 6;
+            pc->first = (uint32_t)streams.n;
+            for (uint32_t si = 0; si < pc->n; si++) {
+                pstream_t* s = (pstream_t*)vec_grow(&streams, 1);
+                if (!s) { rc = COVT_ERR_OOM; break; }
+                c_string(&c, &s->noff, &s->nlen);
+                s->nv = c_varint(&c);
+                s->bl = c_varint(&c);
+                s->enc = c_byte(&c);
+                if (c.err) { rc = COVT_ERR_TRUNCATED; break; }
+            }
+        }
+        /* payload offsets: [id] | geometry (any order: only its total matters here) | property columns in metadata order */
+        uint64_t p = c.p;
+        for (uint32_t ci = 0; rc == COVT_OK && ci < n_cols; ci++)
+            for (uint32_t si = 0; si < cols[ci].n; si++) {
+                pstream_t* s = (pstream_t*)streams.p + cols[ci].first + si;
+                s->off = p;
+                p += s->bl;
+                if (p > end) { rc = COVT_ERR_TRUNCATED; break; }
+            }
+        for (uint32_t ci = 0; rc == COVT_OK && ci < n_cols; ci++) {
+            const pcol_t* pc = &cols[ci];
+            if (pc->is_id || pc->is_geom) continue;
+            int dt = dt_of_gen2(pc->dt);
+            if (dt < 0 || pc->ct > COVT_CT_ICE_MORTON_CODE) { rc = COVT_ERR_BAD_METADATA; break; }
+            rc = prop_column(blob, B, tile, li, pc->noff, pc->nlen, dt, pc->ct, F, (const pstream_t*)streams.p + pc->first, pc->n);
+        }
+        free(cols);
+        free(streams.p);
+        if (rc != COVT_OK) return rc;
+        c.p = p;
+    }
+    return c.p == end ? COVT_OK : COVT_ERR_TRUNCATED;
+}
+
+int32_t covt_oracle_decode_properties(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, covt_oracle_props** out)
+{
+    covt_oracle_props* R = (covt_oracle_props*)calloc(1, sizeof(covt_oracle_props));
+    if (!R) return COVT_ERR_OOM;
+    props_build_t B;
+    memset(&B, 0, sizeof(B));
+    B.cols.elem = sizeof(covt_prop_column);
+    B.dicts.elem = sizeof(covt_prop_dictionary);
+    B.validity.elem = 1;
+    B.i64.elem = sizeof(int64_t);
+    B.f32.elem = sizeof(float);
+    B.f64.elem = sizeof(double);
+    B.bools.elem = 1;
+    B.didx.elem = sizeof(int32_t);
+    B.doff.elem = sizeof(int32_t);
+    R->n_tiles = n_tiles;
+    R->tile_status = (uint32_t*)calloc((size_t)n_tiles + 1, sizeof(uint32_t));
+    for (uint32_t t = 0; t < n_tiles; t++)
+        R->tile_status[t] = (uint32_t)props_of_tile(blob, tile_offsets[t], tile_offsets[t + 1], t, &B);
+    R->columns = (covt_prop_column*)B.cols.p;        R->n_columns = (uint32_t)B.cols.n;
+    R->dictionaries = (covt_prop_dictionary*)B.dicts.p; R->n_dictionaries = (uint32_t)B.dicts.n;
+    R->validity = (uint8_t*)B.validity.p;            R->validity_bytes = B.validity.n;
+    R->i64 = (int64_t*)B.i64.p;                      R->n_i64 = B.i64.n;
+    R->f32 = (float*)B.f32.p;                        R->n_f32 = B.f32.n;
+    R->f64 = (double*)B.f64.p;                       R->n_f64 = B.f64.n;
+    R->bools = (uint8_t*)B.bools.p;                  R->bool_bytes = B.bools.n;
+    R->dict_index = (int32_t*)B.didx.p;              R->n_dict_index = B.didx.n;
+    R->dict_offsets = (int32_t*)B.doff.p;            R->n_dict_offsets = B.doff.n;
+    *out = R;
+    return COVT_OK;
+}
+
+void covt_oracle_props_free(covt_oracle_props* p)
+{
+    if (!p) return;
+    free(p->tile_status); free(p->columns); free(p->dictionaries); free(p->validity); free(p->i64); free(p->f32); free(p->f64);
+    free(p->bools); free(p->dict_index); free(p->dict_offsets);
+    free(p);
+}

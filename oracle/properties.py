@@ -3,13 +3,16 @@
 Restates CovtParser.decodePropertyColumn (J/decoder/CovtParser.java:276-390) on top of the C stream codecs of covt_oracle.c,
 for the container the committed fixtures use (gen-2b: every stream, the present stream included, is listed with name,
 numValues, byteLength and StreamEncoding ordinal). Pinned by tests/test_oracle_properties.py against the property values of the
-partner .mvt tiles. Not on the GPU path yet: the product decodes geometry + id columns only.
+partner .mvt tiles. Not on the GPU path yet: the product decodes geometry + id columns only. The same decode with a
+columnar result (validity bitmap + dense values + dictionary offsets: the layout meant for the GPU path) is
+covt_oracle_decode_properties in covt_oracle.c; tests/test_oracle_properties.py holds the two against each other.
 
 Layout established on the 129 fixtures (no gen-2b reader or writer exists in the reference at HEAD):
   * property payloads follow the geometry payload of their layer IN COLUMN-METADATA ORDER, stream after stream in listed order;
   * `present`  BOOLEAN_RLE: Byte-RLE of ceil(numValues / 8) bitset bytes, bit i = byte[i >> 3] >> (i & 7) (java.util.BitSet);
   * INT_64 / UINT_64 `data`: RLE (signed / unsigned), VARINT_ZIG_ZAG or VARINT_DELTA_ZIG_ZAG over the PRESENT values only;
-  * BOOLEAN `data`: BOOLEAN_RLE bitset over all features (CovtParser.java:280-290);
+  * BOOLEAN `data`: BOOLEAN_RLE bitset; HEAD reads one bit per feature and no present stream (CovtParser.java:280-290), the
+    fixtures list a present stream for most boolean columns and `data` then holds one bit per PRESENT feature;
   * FLOAT / DOUBLE `data`: little-endian IEEE values of the present features (DecodingUtils.decodeFloatsLE :446-453);
   * STRING, ColumnType.DICTIONARY: `data` = RLE dictionary indices of the present features, `length` = RLE byte lengths of the
     dictionary entries, `dictionary` = the UTF-8 bytes back to back;

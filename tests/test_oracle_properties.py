@@ -61,3 +61,39 @@ def test_bing_property_columns_decode_cleanly(oracle, fixtures):
                 n_cols += 1
                 kinds.update(type(v).__name__ for v in col if v is not None)
     assert n_cols >= 800 and {"str", "int", "float", "bool"} <= kinds
+
+
+def test_c_property_oracle_equals_the_pinned_statement(oracle, fixtures):
+    """covt_oracle_decode_properties (C, columnar: validity bitmap + dense values + dictionary offsets — the layout meant for
+    the GPU path) over all 129 fixture tiles in one batch == oracle/properties.py, which the tests above pin on the MVT."""
+    from oracle import properties as P
+    blob, offs = util.concat_tiles([b for _, b in fixtures])
+    res = oracle.decode_properties(blob, offs)
+    assert not res.tile_status.any()
+    by_tile = {}
+    for c in res.columns:
+        by_tile.setdefault(c.tile, []).append(c)
+    n_cols = 0
+    kinds = set()
+    for t, (name, data) in enumerate(fixtures):
+        want = P.decode_property_columns(data)
+        layers = P.walk_gen2b(bytes(data))
+        got = {}
+        for c in by_tile.get(t, []):
+            assert c.status == 0, (name, c.layer, c.status)
+            key = bytes(blob[int(c.name_offset):int(c.name_offset) + c.name_length]).decode("utf-8")
+            if c.sub_length:
+                sub = bytes(blob[int(c.sub_offset):int(c.sub_offset) + c.sub_length]).decode("utf-8")
+                key = key if sub == key else key + ":" + sub
+            got.setdefault(c.layer, {})[key] = res.column_values(blob, c)
+            kinds.add(c.value_kind)
+        for li, (layer_name, props) in enumerate(want):
+            assert layers[li]["name"] == layer_name
+            g = got.get(li, {})
+            assert set(g) == set(props), (name, layer_name, sorted(set(g) ^ set(props))[:5])
+            for key, col in props.items():
+                a = g[key]
+                assert len(a) == len(col) and all((x is None and y is None) or (x is not None and y is not None and (x == y or abs(x - y) < 1e-6 * max(1.0, abs(y))))
+                                                  if not isinstance(y, (str, bool)) else x == y for x, y in zip(a, col)), (name, layer_name, key)
+                n_cols += 1
+    assert n_cols >= 13000 and {oracle.PV_I64, oracle.PV_F32, oracle.PV_BOOL, oracle.PV_DICT_INDEX} <= kinds
