@@ -65,11 +65,22 @@ def make_tiles(first_tile, n_tiles, container=0):
     return blob, offs, truth
 
 
-def make_fixture_sweep(replicas):
-    """Config 2: the reference's gen-2b OMT fixture tiles z2-z14 in one batch, replicated for timing."""
+def make_fixture_sweep(replicas, decode_pfor=None):
+    """Config 2: the reference's gen-2b OMT fixture tiles z2-z14 in one batch, replicated for timing. decode_pfor(tile array,
+    offset, byte_length, num_values) -> values: when given, the FastPFOR topology streams are transcoded to ORC RLE first
+    (tools/gen/rewrite.py: the "RLE topology streams" variant BASELINE config 2 names)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import util
     tiles = [b for n, b in util.load_fixture_tiles() if n.startswith("omt/")]
+    if decode_pfor is not None:
+        from tools.gen import rewrite
+        n_streams = 0
+        for i, data in enumerate(tiles):
+            arr = np.frombuffer(data + bytes(64), dtype=np.uint8)
+            todo = rewrite.topology_pfor_streams(data)
+            tiles[i] = rewrite.transcode_topology_to_rle(data, {off: decode_pfor(arr, off, bl, nv) for off, bl, nv in todo})
+            n_streams += len(todo)
+        log("[bench] transcoded %d FastPFOR topology streams to ORC RLE" % n_streams)
     blob1, offs1 = util.concat_tiles(tiles)
     blob = np.tile(blob1, replicas)
     sizes = np.tile(np.diff(offs1), replicas)
@@ -229,9 +240,26 @@ def build_workload(args, rank, for_cpu=False):
         cfg = {"workload": "config5: %d synthetic mixed-geometry gen-2b tiles per GPU, seed = tile index, 2 layers/tile" % n,
                "tiles_per_gpu": n, "partition": "tile index ranges, no collective", "l2": "inputs (%.2f GB) and outputs far larger than the 126 MB L2" % (len(blob) / 1e9)}
     elif args.workload == "fixtures":
-        blob, offs, truth = make_fixture_sweep(args.replicas)
+        decode_pfor = None
+        if args.rle_topology and for_cpu:
+            # the reference arm prepares its workload with its own decoder (the oracle)
+            from oracle import oracle as O
+
+            def decode_pfor(arr, off, bl, nv):
+                return O.decode_stream(arr, abi.OP_PFOR_ZZ_DELTA, byte_offset=off, byte_length=bl, num_values=nv)[0]
+        elif args.rle_topology:
+            # the GPU arm prepares it with the product (no oracle on this path)
+            prep = covt_loader.load().Decoder(int(os.environ.get("LOCAL_RANK", 0)))
+
+            def decode_pfor(arr, off, bl, nv):
+                vals, st_, _ = prep.decode_stream(arr, abi.OP_PFOR_ZZ_DELTA, byte_offset=off, byte_length=bl, num_values=nv)
+                if st_ != 0:
+                    raise RuntimeError("transcoding: FastPFOR stream status %d" % st_)
+                return vals
+        blob, offs, truth = make_fixture_sweep(args.replicas, decode_pfor)
         flags |= abi.FLAG_ID_DVZZ_IS_RLE
-        cfg = {"workload": "config2: the reference's 91 gen-2b OMT fixture tiles z2-z14 in one batch, x%d replicas" % args.replicas,
+        cfg = {"workload": "config2%s: the reference's 91 gen-2b OMT fixture tiles z2-z14 in one batch, x%d replicas" % (
+            " (RLE topology streams: FastPFOR topology transcoded to ORC RLE)" if args.rle_topology else "", args.replicas),
                "l2": "inputs larger than L2"}
     elif args.workload == "varint1g":
         from tools.gen import gen as G
@@ -506,6 +534,7 @@ def main():
     ap.add_argument("--stream-bytes", type=int, default=1 << 30, help="config 3 stream size")
     ap.add_argument("--tiles", type=int, default=1 << 20, help="tiles per GPU (config 5: 1 048 576)")
     ap.add_argument("--replicas", type=int, default=256, help="fixture-sweep replicas (config 2)")
+    ap.add_argument("--rle-topology", action="store_true", help="config 2 with every topology stream as ORC RLE (BASELINE wording)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -338,3 +338,47 @@ def test_mutation_fuzz_against_oracle(covt, oracle, decoder, fixtures, corpus):
     n = util.compare_results(abi, res, ref)
     assert n > n_mutants // 2
     res.free()
+
+
+@pytest.mark.gpu
+def test_config2_rle_topology_variant(covt, oracle, gen, decoder, fixtures):
+    """BASELINE config 2 names "RLE topology streams": the 91 OMT tiles with their 273 FastPFOR topology streams transcoded
+    to ORC RLE (tools/gen/rewrite.py; the FastPFOR side decoded by the product itself, as bench.py --rle-topology does).
+    GPU == oracle on the rewritten batch, and every result buffer equals the one of the original batch."""
+    from tools.gen import rewrite
+    abi = covt.abi
+    names = [n for n, _ in fixtures if n.startswith("omt/")]
+    tiles = [b for n, b in fixtures if n.startswith("omt/")]
+    new_tiles, n_streams = [], 0
+    for data in tiles:
+        arr = np.frombuffer(data + bytes(64), dtype=np.uint8)
+        todo = rewrite.topology_pfor_streams(data)
+        decoded = {}
+        if todo:
+            descs = (abi.StreamDesc * len(todo))()
+            for i, (off, bl, nv) in enumerate(todo):
+                descs[i] = abi.StreamDesc(byte_offset=off, byte_length=bl, num_values=nv, op=abi.OP_PFOR_ZZ_DELTA)
+            r = decoder.decode_streams(arr, descs, abi.FLAG_DEFAULT)
+            arena = r.buffer(abi.BUF_STREAM_ARENA)
+            for i, (off, bl, nv) in enumerate(todo):
+                assert descs[i].status == 0 and descs[i].out_count == nv
+                decoded[off] = arena[descs[i].out_offset:descs[i].out_offset + 4 * nv].view(np.int32).copy()
+            r.free()
+        new_tiles.append(rewrite.transcode_topology_to_rle(data, decoded))
+        n_streams += len(todo)
+    assert n_streams >= 270
+    for z8 in (False, True):
+        sel = [i for i, n in enumerate(names) if n.startswith("omt/8_") == z8]
+        flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE | (abi.FLAG_MORTON_NO_SHIFT if z8 else 0)
+        blob, offs = util.concat_tiles([new_tiles[i] for i in sel])
+        res, ref = _decode_both(covt, oracle, decoder, blob, offs, flags=flags)
+        util.compare_results(abi, res, ref)
+        enc = res.layers["streams"]["encoding"][:, [abi.SLOT_GEOM, abi.SLOT_PART, abi.SLOT_RING]]
+        assert not (enc == abi.ENC_FAST_PFOR_DELTA_ZIG_ZAG).any()
+        blob0, offs0 = util.concat_tiles([tiles[i] for i in sel])
+        res0 = decoder.decode_batch(blob0, offs0, abi.CONTAINER_GEN2B, flags)
+        assert np.array_equal(res.layers["out"], res0.layers["out"]) and np.array_equal(res.layers["status"], res0.layers["status"])
+        # valid slices only (padding between slices is unspecified): the bulk comparison with the original batch as reference
+        util.compare_results_bulk(abi, res, res0, chunk_layers=4096, same_container=False)
+        res.free()
+        res0.free()

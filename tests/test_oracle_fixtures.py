@@ -133,3 +133,39 @@ def test_config1_layer_shape(oracle, fixtures):
             assert L["streams"][abi.SLOT_TYPES]["byte_length"] == 702 and L["streams"][abi.SLOT_ID]["byte_length"] == 1656
             return
     raise AssertionError("transportation layer not found")
+
+
+def test_rle_topology_variant_decodes_to_the_same_geometry(oracle, gen, fixtures):
+    """BASELINE config 2 names "RLE topology streams": tools/gen/rewrite.py transcodes the 273 FastPFOR topology streams of the
+    91 OMT fixtures to ORC RLE (metadata + payload re-serialised). The oracle must decode the rewritten tiles to exactly the
+    buffers of the originals (which test_assembled_geometry_equals_partner_mvt pins on the MVT), and a tile without FastPFOR
+    topology must come back byte for byte."""
+    from tools.gen import rewrite
+    abi = oracle.abi
+    n_streams = n_identical = 0
+    for name, data in fixtures:
+        if not name.startswith("omt/"):
+            continue
+        arr = np.frombuffer(data + bytes(64), np.uint8)
+        todo = rewrite.topology_pfor_streams(data)
+        decoded = {}
+        for off, bl, nv in todo:
+            vals, st, cons = oracle.decode_stream(arr, abi.OP_PFOR_ZZ_DELTA, byte_offset=off, byte_length=bl, num_values=nv)
+            assert st == 0 and cons == bl
+            decoded[off] = vals
+        new = rewrite.transcode_topology_to_rle(data, decoded)
+        n_streams += len(todo)
+        if not todo:
+            assert new == data
+            n_identical += 1
+            continue
+        flags = _flags(abi, name)
+        a = oracle.decode_batch(np.frombuffer(data, np.uint8), np.array([0, len(data)], np.uint64), abi.CONTAINER_GEN2B, flags)
+        b = oracle.decode_batch(np.frombuffer(new, np.uint8), np.array([0, len(new)], np.uint64), abi.CONTAINER_GEN2B, flags)
+        assert np.array_equal(a.tile_status, b.tile_status) and np.array_equal(a.layers["status"], b.layers["status"])
+        assert np.array_equal(a.layers["out"], b.layers["out"])
+        for k in range(abi.NUM_BUFFERS - 1):
+            assert np.array_equal(a.buffer(k), b.buffer(k)), (name, abi.BUF_NAMES[k])
+        enc = b.layers["streams"]["encoding"][:, [abi.SLOT_GEOM, abi.SLOT_PART, abi.SLOT_RING]]
+        assert not (enc == abi.ENC_FAST_PFOR_DELTA_ZIG_ZAG).any()
+    assert n_streams >= 270 and n_identical >= 1
