@@ -400,3 +400,43 @@ def test_property_streams_of_the_fixtures(covt, oracle, decoder, fixtures):
         seen[abi.OP_NAMES[op]] = seen.get(abi.OP_NAMES[op], 0) + 1
     assert seen.get("byte_rle", 0) > 10000 and seen.get("rle_u64", 0) > 10000 and seen.get("rle_s64", 0) > 500
     res.free()
+
+
+def test_config2_rle_topology_streams_in_isolation(covt, oracle, decoder, fixtures):
+    """the RLE branch on its own — the RLE-encoded topology streams of the 91 OMT fixtures (geometry_offsets,
+    part_offsets, ring_offsets: the 1 123 streams of SURVEY §4.4) through covt_decode_streams in one call, by descriptor
+    (stream type + encoding + column type -> op, the dispatch table of CovtParser.decodeGeometryColumn)."""
+    from tools.gen import rewrite
+    abi = covt.abi
+    st_of = {"geometry_offsets": abi.ST_GEOMETRY_OFFSETS, "part_offsets": abi.ST_PART_OFFSETS, "ring_offsets": abi.ST_RING_OFFSETS}
+    blob = bytearray()
+    wanted = []
+    for name, data in fixtures:
+        if not name.startswith("omt/"):
+            continue
+        base = len(blob)
+        blob += data
+        for L in rewrite.walk(data)[1]:
+            for c in L["columns"]:
+                if c["data_type"] != rewrite.DT2_GEOMETRY:
+                    continue
+                for s in c["streams"]:
+                    if s["name"] in st_of and s["encoding"] == abi.ENC_RLE:
+                        wanted.append((st_of[s["name"]], c["column_type"], base + s["offset"], s["byte_length"], s["num_values"]))
+    assert len(wanted) >= 1000
+    blob = np.frombuffer(bytes(blob) + bytes(64), dtype=np.uint8)
+    descs = (abi.StreamDesc * len(wanted))()
+    for i, (stype, ct, off, bl, nv) in enumerate(wanted):
+        descs[i] = abi.StreamDesc(byte_offset=off, byte_length=bl, num_values=nv, stream_type=stype, encoding=abi.ENC_RLE, column_type=ct)
+    res = decoder.decode_streams(blob, descs, abi.FLAG_DEFAULT)
+    arena = res.buffer(abi.BUF_STREAM_ARENA)
+    total = 0
+    for i, (stype, ct, off, bl, nv) in enumerate(wanted):
+        d = descs[i]
+        want, wst, wcons = oracle.decode_stream(blob, abi.OP_RLE_U32, byte_offset=off, byte_length=bl, num_values=nv)
+        assert wst == 0 and wcons == bl
+        assert d.status == 0 and d.bytes_consumed == bl and d.out_count == nv, (i, d.status, d.bytes_consumed, bl)
+        assert np.array_equal(arena[d.out_offset:d.out_offset + 4 * nv].view(np.int32), want), i
+        total += nv
+    assert len(wanted) == 1123 and total > 80000  # the census of SURVEY §4.4
+    res.free()
