@@ -24,6 +24,10 @@ abi = _load_abi()
 
 
 def build(force=False):
+    if os.environ.get("COVT_ORACLE_ASAN"):
+        # the AddressSanitizer / UBSan build of the oracle (tools/debug/oracle_asan_fuzz.sh; needs LD_PRELOAD of libasan)
+        subprocess.check_call(["make", "-C", _HERE, "asan"], stdout=subprocess.DEVNULL)
+        return os.path.join(_HERE, "libcovt_oracle_asan.so")
     so = os.path.join(_HERE, "libcovt_oracle.so")
     src = [os.path.join(_HERE, f) for f in ("covt_oracle.c", "covt_oracle.h")] + [os.path.join(_ROOT, "include", "covt_b200.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
