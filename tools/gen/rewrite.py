@@ -97,8 +97,9 @@ def topology_pfor_streams(tile):
     return out
 
 
-def transcode_topology_to_rle(tile, decoded):
-    """decoded: {offset: int32 ndarray} for every entry of topology_pfor_streams(tile). Returns the rewritten tile bytes."""
+def transcode_topology_to_rle(tile, decoded, keep_pfor=False):
+    """decoded: {offset: int32 ndarray} for every entry of topology_pfor_streams(tile). Returns the rewritten tile bytes.
+    keep_pfor=True re-serialises the tile without touching any stream (must give back the input byte for byte)."""
     tile = bytes(tile)
     version, layers = walk(tile)
     out = bytearray(_enc_varint(version) + _enc_varint(len(layers)))
@@ -107,7 +108,7 @@ def transcode_topology_to_rle(tile, decoded):
         for c in L["columns"]:
             for s in c["streams"]:
                 data = tile[s["offset"]:s["offset"] + s["byte_length"]]
-                if c["data_type"] == DT2_GEOMETRY and s["name"] in TOPOLOGY and s["encoding"] == ENC_FAST_PFOR_DELTA_ZIG_ZAG:
+                if not keep_pfor and c["data_type"] == DT2_GEOMETRY and s["name"] in TOPOLOGY and s["encoding"] == ENC_FAST_PFOR_DELTA_ZIG_ZAG:
                     vals = np.asarray(decoded[s["offset"]])
                     assert len(vals) == s["num_values"]
                     data = bytes(gen.encode_rle(vals.astype(np.int64), signed=False))
