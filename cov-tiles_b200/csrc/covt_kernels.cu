@@ -14,6 +14,7 @@
 #include "covt_assemble.cuh"
 #include "covt_internal.h"
 #include "covt_streams.cuh"
+#include "covt_walk.cuh"
 
 namespace covt {
 
@@ -40,33 +41,6 @@ __device__ __forceinline__ uint64_t vbuf_ints_of(const covt_layer& L, uint32_t f
     if (L.geom_column_type == COVT_CT_ICE_MORTON_CODE) n *= 2;
     else if (L.geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) n *= 2;
     return n;
-}
-
-__device__ void layer_slice_sizes(covt_layer& L, uint32_t flags, uint64_t sz[COVT_NUM_BUFFERS])
-{
-    for (int b = 0; b < COVT_NUM_BUFFERS; b++) sz[b] = 0;
-    if (L.status == COVT_ERR_BAD_METADATA) return;
-    const uint64_t F = slot_nv(L, COVT_SLOT_TYPES);
-    sz[COVT_BUF_S_GEOMETRY_TYPES] = F;
-    sz[COVT_BUF_S_IDS] = slot_nv(L, COVT_SLOT_ID);
-    sz[COVT_BUF_S_GEOMETRY_OFFSETS] = slot_nv(L, COVT_SLOT_GEOM);
-    sz[COVT_BUF_S_PART_OFFSETS] = slot_nv(L, COVT_SLOT_PART);
-    sz[COVT_BUF_S_RING_OFFSETS] = slot_nv(L, COVT_SLOT_RING);
-    sz[COVT_BUF_S_VERTEX_OFFSETS] = slot_nv(L, COVT_SLOT_VOFF);
-    const uint64_t vb_ints = vbuf_ints_of(L, flags);
-    sz[COVT_BUF_S_VERTEX_BUFFER] = vb_ints;
-    sz[COVT_BUF_S_INDEX_BUFFER] = slot_nv(L, COVT_SLOT_INDEX);
-    if (!(flags & COVT_FLAG_SKIP_ASSEMBLY)) {
-        const uint64_t V = L.streams[COVT_SLOT_VOFF].encoding != COVT_ENC_ABSENT ? slot_nv(L, COVT_SLOT_VOFF) : vb_ints / 2;
-        const uint64_t cap_parts = F + slot_nv(L, COVT_SLOT_PART);
-        const uint64_t cap_rings = cap_parts + slot_nv(L, COVT_SLOT_RING);
-        L.cap_parts = (uint32_t)cap_parts;
-        L.cap_rings = (uint32_t)cap_rings;
-        sz[COVT_BUF_A_GEOM_OFFSETS] = F + 1;
-        sz[COVT_BUF_A_PART_OFFSETS] = cap_parts + 1;
-        sz[COVT_BUF_A_RING_OFFSETS] = cap_rings + 1;
-        sz[COVT_BUF_A_COORDS] = 2 * (V + ((flags & COVT_FLAG_CLOSE_RINGS) ? slot_nv(L, COVT_SLOT_RING) : 0));
-    }
 }
 
 // dispatch table of CovtParser.decodeGeometryColumn (:405-510) and decodedIds (:552-572), SURVEY §8a
@@ -120,370 +94,179 @@ __host__ __device__ inline int op_class_of(uint32_t op)
 int host_op_class_of(uint32_t op) { return op_class_of(op); }
 
 // =================================================================================================
-// K0: container walk, one thread per tile
+// K0: container walk, one thread per tile (covt_walk.cuh). Two passes over the tile headers: sizes first (the result buffers
+// are allocated from their column sums), then the layer table and the dense per-class task lists.
 // =================================================================================================
-struct Cursor { const uint8_t* b; uint64_t p, end; bool err; };
-
-// DecodingUtils.decodeVarint (DecodingUtils.java:157-186): at most 4 bytes
-__device__ uint32_t c_varint(Cursor& c)
+__host__ __device__ constexpr uint32_t slot_stream_type(int s)
 {
-    uint32_t v = 0;
-    for (int i = 0; i < 4; i++) {
-        if (c.p >= c.end) { c.err = true; return 0; }
-        uint32_t b = c.b[c.p++];
-        v |= (b & 0x7fu) << (7 * i);
-        if (!(b & 0x80u)) break;
+    return s == COVT_SLOT_ID ? COVT_ST_DATA : s == COVT_SLOT_INDEX ? COVT_ST_INDEX_BUFFER : (uint32_t)(COVT_ST_GEOMETRY_TYPES + (s - COVT_SLOT_TYPES));
+}
+__host__ __device__ constexpr int slot_buf(int s)
+{
+    return s == COVT_SLOT_ID ? COVT_BUF_S_IDS : s == COVT_SLOT_TYPES ? COVT_BUF_S_GEOMETRY_TYPES : COVT_BUF_S_GEOMETRY_OFFSETS + (s - COVT_SLOT_GEOM);
+}
+static_assert(slot_buf(COVT_SLOT_VBUF) == COVT_BUF_S_VERTEX_BUFFER && slot_buf(COVT_SLOT_INDEX) == COVT_BUF_S_INDEX_BUFFER, "slot -> buffer");
+static_assert(slot_stream_type(COVT_SLOT_VBUF) == COVT_ST_VERTEX_BUFFER && slot_stream_type(COVT_SLOT_TYPES) == COVT_ST_GEOMETRY_TYPES, "slot -> stream type");
+
+__device__ __forceinline__ uint64_t lite_nv(const Lite& lite, int slot) { return lite.has(slot) ? (uint64_t)lite.nv(slot) : 0ull; }
+__device__ __forceinline__ uint64_t lite_vbuf_ints(const Lite& lite, uint32_t geom_ct, uint32_t flags)
+{
+    uint64_t n = lite_nv(lite, COVT_SLOT_VBUF);
+    if (geom_ct == COVT_CT_ICE_MORTON_CODE) n *= 2;
+    else if (geom_ct == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) n *= 2;
+    return n;
+}
+// slice size (elements, before the 16-byte rounding) of the layer in result buffer b
+__device__ __forceinline__ uint64_t lite_slice_size(const Lite& lite, uint32_t geom_ct, uint32_t flags, int b)
+{
+    const uint64_t F = lite_nv(lite, COVT_SLOT_TYPES);
+    switch (b) {
+    case COVT_BUF_S_GEOMETRY_TYPES: return F;
+    case COVT_BUF_S_IDS: return lite_nv(lite, COVT_SLOT_ID);
+    case COVT_BUF_S_GEOMETRY_OFFSETS: return lite_nv(lite, COVT_SLOT_GEOM);
+    case COVT_BUF_S_PART_OFFSETS: return lite_nv(lite, COVT_SLOT_PART);
+    case COVT_BUF_S_RING_OFFSETS: return lite_nv(lite, COVT_SLOT_RING);
+    case COVT_BUF_S_VERTEX_OFFSETS: return lite_nv(lite, COVT_SLOT_VOFF);
+    case COVT_BUF_S_VERTEX_BUFFER: return lite_vbuf_ints(lite, geom_ct, flags);
+    case COVT_BUF_S_INDEX_BUFFER: return lite_nv(lite, COVT_SLOT_INDEX);
+    default: break;
     }
-    return v;
-}
-__device__ uint32_t c_byte(Cursor& c)
-{
-    if (c.p >= c.end) { c.err = true; return 0; }
-    return c.b[c.p++];
-}
-// DecodingUtils.decodeString (:21-26)
-__device__ void c_string(Cursor& c, uint64_t& off, uint32_t& len)
-{
-    uint32_t n = c_varint(c);
-    if (c.err || c.p + n > c.end) { c.err = true; off = 0; len = 0; return; }
-    off = c.p;
-    len = n;
-    c.p += n;
-}
-template <int N>
-__device__ bool name_is(const uint8_t* b, uint64_t off, uint32_t len, const char (&lit)[N])
-{
-    if (len != N - 1) return false;
-    for (int i = 0; i < N - 1; i++)
-        if (b[off + i] != (uint8_t)lit[i]) return false;
-    return true;
-}
-
-// The result buffers are sized from numValues before anything is decoded, so a corrupt header must not be able to claim
-// gigabytes: no codec of the path packs more than 128 values into a byte (FastPFOR at bit width 0: two container bytes per block
-// of 256; Byte-RLE: 130 per 2 bytes; RLE: 130 per 3), so a stream that claims more than 256 values per byte (+ slack for the
-// fixed headers) cannot decode — the reference would run off the end of the array (ArrayIndexOutOfBounds): the tile fails.
-__device__ __forceinline__ bool plausible_count(uint32_t num_values, uint32_t byte_length)
-{
-    return (uint64_t)num_values <= 256ull * ((uint64_t)byte_length + 16ull);
-}
-
-__device__ void layer_init(covt_layer& L, uint32_t tile, uint32_t idx)
-{
-    uint32_t* w = reinterpret_cast<uint32_t*>(&L);
-    for (unsigned i = 0; i < sizeof(covt_layer) / 4; i++) w[i] = 0;
-    L.tile = tile;
-    L.layer_index = idx;
-    for (int s = 0; s < COVT_NUM_SLOTS; s++) L.streams[s].encoding = COVT_ENC_ABSENT;
-}
-
-__constant__ uint8_t c_slot_stream_type[COVT_NUM_SLOTS] = {
-    COVT_ST_DATA, COVT_ST_GEOMETRY_TYPES, COVT_ST_GEOMETRY_OFFSETS, COVT_ST_PART_OFFSETS,
-    COVT_ST_RING_OFFSETS, COVT_ST_VERTEX_OFFSETS, COVT_ST_VERTEX_BUFFER, COVT_ST_INDEX_BUFFER};
-
-// payload order is fixed (CovtParser.java:405-510): [id] | types, geometry_offsets, part_offsets, ring_offsets,
-// vertex_offsets, vertex_buffer [, index_buffer]
-__device__ uint64_t layer_place_streams(covt_layer& L, uint64_t payload, uint32_t flags)
-{
-    for (int s = 0; s < COVT_NUM_SLOTS; s++) {
-        covt_stream_ref& r = L.streams[s];
-        if (r.encoding == COVT_ENC_ABSENT) continue;
-        r.byte_offset = payload;
-        payload += r.byte_length;
-        r.op = (uint8_t)resolve_op(c_slot_stream_type[s], r.encoding, L.geom_column_type, flags);
-        if (r.op == COVT_OP_NONE) {
-            r.status = COVT_ERR_UNSUPPORTED_ENCODING;
-            if (!L.status) L.status = COVT_ERR_UNSUPPORTED_ENCODING;
-        }
+    if (flags & COVT_FLAG_SKIP_ASSEMBLY) return 0;
+    const uint64_t cap_parts = F + lite_nv(lite, COVT_SLOT_PART);
+    switch (b) {
+    case COVT_BUF_A_GEOM_OFFSETS: return F + 1;
+    case COVT_BUF_A_PART_OFFSETS: return cap_parts + 1;
+    case COVT_BUF_A_RING_OFFSETS: return cap_parts + lite_nv(lite, COVT_SLOT_RING) + 1;
+    case COVT_BUF_A_COORDS: {
+        const uint64_t V = lite.has(COVT_SLOT_VOFF) ? lite_nv(lite, COVT_SLOT_VOFF) : lite_vbuf_ints(lite, geom_ct, flags) / 2;
+        return 2 * (V + ((flags & COVT_FLAG_CLOSE_RINGS) ? lite_nv(lite, COVT_SLOT_RING) : 0));
     }
-    return payload;
-}
-
-// gen-2b. on_layer(L) is called for every complete layer. Returns the tile status.
-template <class OnLayer>
-__device__ uint32_t walk_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, uint32_t flags, uint32_t tile, OnLayer&& on_layer)
-{
-    Cursor c = {blob, begin, end, false};
-    (void)c_varint(c);  // version
-    const uint32_t num_layers = c_varint(c);
-    if (c.err) return COVT_ERR_TRUNCATED;
-    __align__(16) covt_layer L;
-    for (uint32_t li = 0; li < num_layers; li++) {
-        layer_init(L, tile, li);
-        c_string(c, L.name_offset, L.name_length);
-        L.extent = c_varint(c);
-        L.num_features = c_varint(c);
-        L.num_columns = c_varint(c);
-        if (c.err) return COVT_ERR_TRUNCATED;
-        L.num_bits = (uint8_t)(32 - __clz(L.extent));
-        uint64_t property_bytes = 0;
-        bool have_geometry = false;
-        for (uint32_t ci = 0; ci < L.num_columns; ci++) {
-            uint64_t noff; uint32_t nlen;
-            c_string(c, noff, nlen);
-            (void)c_byte(c);  // gen-2 data type
-            const uint32_t column_type = c_byte(c);
-            const uint32_t num_streams = c_varint(c);
-            if (c.err) return COVT_ERR_TRUNCATED;
-            const bool is_id = name_is(blob, noff, nlen, "id");
-            const bool is_geom = name_is(blob, noff, nlen, "geometry");
-            if (ci == 0 && !is_id && !is_geom) return COVT_ERR_BAD_METADATA;  // CovtParser.java:67-69
-            if (is_geom) { L.geom_column_type = (uint8_t)column_type; have_geometry = true; }
-            if (is_geom && column_type > COVT_CT_ICE_MORTON_CODE) return COVT_ERR_BAD_METADATA;
-            for (uint32_t si = 0; si < num_streams; si++) {
-                uint64_t soff; uint32_t slen;
-                c_string(c, soff, slen);
-                const uint32_t nv = c_varint(c);
-                const uint32_t bl = c_varint(c);
-                const uint32_t enc = c_byte(c);
-                if (c.err) return COVT_ERR_TRUNCATED;
-                int slot = -1;
-                if (is_id) { if (name_is(blob, soff, slen, "data")) slot = COVT_SLOT_ID; }
-                else if (is_geom) {
-                    if (name_is(blob, soff, slen, "geometry_types")) slot = COVT_SLOT_TYPES;
-                    else if (name_is(blob, soff, slen, "geometry_offsets")) slot = COVT_SLOT_GEOM;
-                    else if (name_is(blob, soff, slen, "part_offsets")) slot = COVT_SLOT_PART;
-                    else if (name_is(blob, soff, slen, "ring_offsets")) slot = COVT_SLOT_RING;
-                    else if (name_is(blob, soff, slen, "vertex_offsets")) slot = COVT_SLOT_VOFF;
-                    else if (name_is(blob, soff, slen, "vertex_buffer")) slot = COVT_SLOT_VBUF;
-                    else if (name_is(blob, soff, slen, "index_buffer")) slot = COVT_SLOT_INDEX;
-                }
-                if (slot >= 0) {
-                    if (enc > COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_ERR_BAD_METADATA;
-                    if (!plausible_count(nv, bl)) return COVT_ERR_TRUNCATED;
-                    L.streams[slot].num_values = nv;
-                    L.streams[slot].byte_length = bl;
-                    L.streams[slot].encoding = (uint8_t)enc;
-                    if (slot == COVT_SLOT_ID) L.has_id = 1;
-                } else if (is_id || is_geom) {
-                    return COVT_ERR_BAD_METADATA;
-                } else {
-                    property_bytes += bl;
-                }
-            }
-        }
-        if (!have_geometry || L.streams[COVT_SLOT_TYPES].encoding == COVT_ENC_ABSENT ||
-            L.streams[COVT_SLOT_VBUF].encoding == COVT_ENC_ABSENT)
-            return COVT_ERR_BAD_METADATA;
-        const uint64_t payload_end = layer_place_streams(L, c.p, flags) + property_bytes;
-        if (payload_end > end) return COVT_ERR_TRUNCATED;
-        c.p = payload_end;
-        on_layer(L);
+    default: return 0;
     }
-    return c.p == end ? COVT_OK : COVT_ERR_TRUNCATED;
 }
 
-// bytes of a Byte-RLE stream that decodes to n bytes: unlisted PRESENT streams of gen-3 property columns
-// (CovtConverter.java:434-436, DecodingUtils.java:290-306)
-__device__ bool byte_rle_span(const uint8_t* b, uint64_t& p, uint64_t end, uint32_t n)
+// pass 1: layers per tile + slice sizes per result buffer + tasks per codec class (column-major: col * n_tiles + tile)
+__global__ void __launch_bounds__(K0_BLOCK)
+k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
+              const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols, uint32_t* tile_status)
 {
-    uint32_t done = 0;
-    while (done < n) {
-        if (p >= end) return false;
-        const uint32_t c = b[p++];
-        if (c < 0x80u) { done += c + 3u; p += 1; }
-        else { done += 256u - c; p += 256u - c; }
-        if (p > end) return false;
-    }
-    return true;
-}
-
-// gen-3 = CovtParser.decodeLayerMetadata (CovtParser.java:574-652); no tile header, loop until EOF (:56)
-template <class OnLayer>
-__device__ uint32_t walk_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, const uint32_t* tj_fields, uint32_t tj_layers,
-                              uint32_t flags, uint32_t tile, OnLayer&& on_layer)
-{
-    Cursor c = {blob, begin, end, false};
-    __align__(16) covt_layer L;
-    uint32_t li = 0;
-    while (c.p < end) {
-        layer_init(L, tile, li);
-        const uint32_t header = c_byte(c);
-        const bool optimized = header & 1u;  // :575-578
-        uint32_t n_fields = 0;
-        if (optimized) {
-            const uint32_t layer_id = c_varint(c);  // :584-589
-            if (c.err) return COVT_ERR_TRUNCATED;
-            if (!tj_fields || layer_id >= tj_layers) return COVT_ERR_BAD_METADATA;
-            n_fields = tj_fields[layer_id];
-            L.name_offset = layer_id;
-            L.name_length = 0;
-        } else {
-            c_string(c, L.name_offset, L.name_length);  // :592
-        }
-        L.extent = c_varint(c);  // :595-598
-        L.num_features = c_varint(c);
-        L.num_columns = c_varint(c);
-        if (c.err) return COVT_ERR_TRUNCATED;
-        L.num_bits = (uint8_t)(32 - __clz(L.extent));  // CovtParser.java:77
-        // property columns: their payload follows the geometry payload; remember how to hop over it.
-        // Walked twice (metadata now, payload sizes after the geometry streams are placed), so keep a cursor.
-        uint64_t prop_listed_total = 0;     // listed stream bytes of all property columns
-        uint32_t n_present_streams = 0;     // columns with an unlisted Byte-RLE present stream, in order
-        uint64_t present_mask_lo = 0;       // bit k set: k-th property column is BOOLEAN (no present stream); first 64 columns
-        uint64_t prop_listed[8];            // per-column listed bytes for the first 8 property columns (interleaving matters)
-        uint32_t n_props = 0;
-        bool have_geometry = false;
-        for (uint32_t ci = 0; ci < L.num_columns; ci++) {
-            bool is_id = false, is_geom = false;
-            if (optimized || ci == 0) {  // :604-614
-                const uint32_t column_id = c_varint(c);
-                if (column_id > 1) {
-                    if (!optimized || column_id - 2 >= n_fields) return COVT_ERR_BAD_METADATA;
-                } else if (column_id == 0) is_id = true;
-                else is_geom = true;
-            } else {
-                uint64_t noff; uint32_t nlen;
-                c_string(c, noff, nlen);  // :616
-                if (!c.err) { is_id = name_is(blob, noff, nlen, "id"); is_geom = name_is(blob, noff, nlen, "geometry"); }
-            }
-            const uint32_t column_desc = c_byte(c);  // :619-624
-            if (c.err) return COVT_ERR_TRUNCATED;
-            const uint32_t data_type = (column_desc >> 3) & 0xFu;
-            const uint32_t column_type = column_desc & 0x7u;
-            if (column_type > COVT_CT_ICE_MORTON_CODE) return COVT_ERR_BAD_METADATA;
-            if (ci == 0 && !is_id && !is_geom) return COVT_ERR_BAD_METADATA;  // :67-69
-            if (is_geom) { L.geom_column_type = (uint8_t)column_type; have_geometry = true; }
-            uint64_t listed = 0;
-            for (;;) {  // :628-648
-                const uint32_t stream_desc = c_byte(c);
-                const uint32_t stream_type = stream_desc >> 4;
-                const uint32_t enc = stream_desc & 0xFu;
-                const uint32_t nv = c_varint(c);
-                const uint32_t bl = c_varint(c);
-                if (c.err) return COVT_ERR_TRUNCATED;
-                if (stream_type > COVT_ST_INDEX_BUFFER || enc > COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_ERR_BAD_METADATA;
-                int slot = -1;
-                if (is_id && stream_type == COVT_ST_DATA) slot = COVT_SLOT_ID;
-                else if (is_geom && stream_type >= COVT_ST_GEOMETRY_TYPES && stream_type <= COVT_ST_VERTEX_BUFFER)
-                    slot = COVT_SLOT_TYPES + (int)(stream_type - COVT_ST_GEOMETRY_TYPES);
-                else if (is_geom && stream_type == COVT_ST_INDEX_BUFFER) slot = COVT_SLOT_INDEX;
-                if (slot >= 0) {
-                    if (!plausible_count(nv, bl)) return COVT_ERR_TRUNCATED;
-                    L.streams[slot].num_values = nv;
-                    L.streams[slot].byte_length = bl;
-                    L.streams[slot].encoding = (uint8_t)enc;
-                    if (slot == COVT_SLOT_ID) L.has_id = 1;
-                } else if (is_id || is_geom) return COVT_ERR_BAD_METADATA;
-                else listed += bl;
-                if (data_type == COVT_DT_GEOMETRY && stream_type == COVT_ST_VERTEX_BUFFER) break;  // :639-647
-                else if (stream_type == COVT_ST_DATA && column_type == COVT_CT_PLAIN) break;
-                else if (stream_type == COVT_ST_DICTIONARY) break;
-            }
-            if (!is_id && !is_geom) {
-                if (n_props < 8) prop_listed[n_props] = listed;
-                else return COVT_ERR_BAD_METADATA;  // more than 8 property columns: see DESIGN.md (property columns are "next")
-                if (data_type == COVT_DT_BOOLEAN && n_props < 64) present_mask_lo |= 1ull << n_props;
-                else n_present_streams++;
-                prop_listed_total += listed;
-                n_props++;
-            }
-        }
-        if (!have_geometry || L.streams[COVT_SLOT_TYPES].encoding == COVT_ENC_ABSENT ||
-            L.streams[COVT_SLOT_VBUF].encoding == COVT_ENC_ABSENT)
-            return COVT_ERR_BAD_METADATA;
-        uint64_t p = layer_place_streams(L, c.p, flags);
-        if (p > end) return COVT_ERR_TRUNCATED;
-        // hop over property columns: BOOLEAN = listed data only (CovtParser.java:280-290); others = unlisted Byte-RLE
-        // present stream of ceil(numFeatures/8) bytes (:295) followed by their listed streams
-        for (uint32_t k = 0; k < n_props; k++) {
-            if (!((present_mask_lo >> k) & 1ull)) {
-                if (!byte_rle_span(blob, p, end, (L.num_features + 7u) / 8u)) return COVT_ERR_TRUNCATED;
-            }
-            p += prop_listed[k];
-            if (p > end) return COVT_ERR_TRUNCATED;
-        }
-        (void)prop_listed_total; (void)n_present_streams;
-        c.p = p;
-        on_layer(L);
-        li++;
-    }
-    return COVT_OK;
-}
-
-template <class OnLayer>
-__device__ uint32_t walk_tile(const uint8_t* blob, uint64_t begin, uint64_t end, uint32_t container, const uint32_t* tj_fields,
-                              uint32_t tj_layers, uint32_t flags, uint32_t tile, OnLayer&& on_layer)
-{
-    if (container == COVT_CONTAINER_GEN2B) return walk_gen2b(blob, begin, end, flags, tile, on_layer);
-    return walk_gen3(blob, begin, end, tj_fields, tj_layers, flags, tile, on_layer);
-}
-
-// pass 1: layers per tile + slice sizes per result buffer (column-major: col * n_tiles + tile)
-__global__ void k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
-                              const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols,
-                              uint32_t* tile_status)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_lite[LITE_WORDS * K0_BLOCK];
+    __shared__ uint64_t s_acc[TILE_COLS * K0_BLOCK];
+    const uint32_t t = blockIdx.x * K0_BLOCK + threadIdx.x;
     if (t >= n_tiles) return;
-    uint64_t acc[TILE_COLS];
-    for (int i = 0; i < TILE_COLS; i++) acc[i] = 0;
-    const uint32_t st = walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, flags, t + tile_base,
-                                  [&](covt_layer& L) {
-                                      uint64_t sz[COVT_NUM_BUFFERS];
-                                      layer_slice_sizes(L, flags, sz);
+    const Lite lite = {s_lite + threadIdx.x};
+    uint64_t* acc = s_acc + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < TILE_COLS; i++) acc[i * K0_BLOCK] = 0;
+    NoProps props;
+    const uint32_t st = walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, lite, props,
+                                  [&](uint32_t, const LayerHead& H) {
                                       acc[0] += 1;
-                                      for (int b = 0; b < COVT_NUM_BUFFERS; b++) acc[1 + b] += align_elems(sz[b], kBufElemSizeDev(b));
-                                      if (L.status != COVT_ERR_BAD_METADATA)
-                                          for (int s = 0; s < COVT_NUM_SLOTS; s++) {
-                                              const int c = L.streams[s].encoding != COVT_ENC_ABSENT ? op_class_of(L.streams[s].op) : -1;
-                                              if (c >= 0) acc[COL_CLASS0 + c] += 1;
-                                          }
+#pragma unroll
+                                      for (int b = 0; b < COVT_NUM_BUFFERS; b++)
+                                          acc[(1 + b) * K0_BLOCK] += align_elems(lite_slice_size(lite, H.geom_ct, flags, b), kBufElemSizeDev(b));
+#pragma unroll
+                                      for (int s = 0; s < COVT_NUM_SLOTS; s++) {
+                                          const int c = lite.has(s) ? op_class_of(resolve_op(slot_stream_type(s), lite.enc(s), H.geom_ct, flags)) : -1;
+                                          if (c >= 0) acc[(COL_CLASS0 + c) * K0_BLOCK] += 1;
+                                      }
                                   });
     tile_status[t] = st;
-    for (int i = 0; i < TILE_COLS; i++) tile_cols[(uint64_t)i * n_tiles + t] = acc[i];
+#pragma unroll
+    for (int i = 0; i < TILE_COLS; i++) tile_cols[(uint64_t)i * n_tiles + t] = acc[i * K0_BLOCK];
 }
 
-// pass 2: write the covt_layer table with result offsets (tile_cols now holds exclusive prefixes)
-__global__ void k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
-                               const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
-                               ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer,
-                               const SegState* seg)
+// pass 2: the covt_layer table with result offsets (tile_cols now holds exclusive prefixes) and one decode task per present stream,
+// appended to the dense list of its codec class
+__global__ void __launch_bounds__(K0_BLOCK)
+k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
+               const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols, ResultBuffers bufs, covt_layer* layers,
+               DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer, const SegState* seg)
 {
-    const uint8_t slot_buf[COVT_NUM_SLOTS] = {COVT_BUF_S_IDS, COVT_BUF_S_GEOMETRY_TYPES, COVT_BUF_S_GEOMETRY_OFFSETS,
-                                              COVT_BUF_S_PART_OFFSETS, COVT_BUF_S_RING_OFFSETS, COVT_BUF_S_VERTEX_OFFSETS,
-                                              COVT_BUF_S_VERTEX_BUFFER, COVT_BUF_S_INDEX_BUFFER};
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_lite[LITE_WORDS * K0_BLOCK];
+    __shared__ uint64_t s_run[TILE_COLS * K0_BLOCK];
+    const uint32_t t = blockIdx.x * K0_BLOCK + threadIdx.x;
     if (t >= n_tiles || seg->overflow) return;
+    const Lite lite = {s_lite + threadIdx.x};
+    uint64_t* run = s_run + threadIdx.x;
     // tile_cols holds exclusive prefixes inside this segment; seg->base = totals of the segments before it
-    uint64_t run[TILE_COLS];
     // (the class columns stay segment-local: the task lists are rebuilt for every segment)
-    for (int i = 0; i < TILE_COLS; i++) run[i] = tile_cols[(uint64_t)i * n_tiles + t] + (i < COL_CLASS0 ? seg->base[i] : class_off.off[i - COL_CLASS0]);
+#pragma unroll
+    for (int i = 0; i < TILE_COLS; i++)
+        run[i * K0_BLOCK] = tile_cols[(uint64_t)i * n_tiles + t] + (i < COL_CLASS0 ? seg->base[i] : class_off.off[i - COL_CLASS0]);
     first_layer[t] = (uint32_t)run[0];
-    walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, flags, t + tile_base, [&](covt_layer& L) {
-        uint64_t sz[COVT_NUM_BUFFERS];
-        layer_slice_sizes(L, flags, sz);
-        for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
-            L.out[b] = run[1 + b];
-            run[1 + b] += align_elems(sz[b], kBufElemSizeDev(b));
-        }
-        // coalescing does not matter here: 368 B per layer, written once
-        uint4* dst = reinterpret_cast<uint4*>(&layers[run[0]]);
-        const uint4* src = reinterpret_cast<const uint4*>(&L);
-        for (unsigned i = 0; i < sizeof(covt_layer) / 16; i++) dst[i] = src[i];
-        // one decode task per present stream, appended to the dense list of its codec class
-        if (L.status != COVT_ERR_BAD_METADATA) {
-            for (int s = 0; s < COVT_NUM_SLOTS; s++) {
-                const covt_stream_ref& r = L.streams[s];
-                const int c = r.encoding != COVT_ENC_ABSENT ? op_class_of(r.op) : -1;
-                if (c < 0) continue;
-                const uint32_t b = slot_buf[s];
-                DeviceTask t;
-                t.src_offset = r.byte_offset;
-                t.dst = reinterpret_cast<uint8_t*>(bufs.ptr[b]) + L.out[b] * kBufElemSizeDev(b);
-                t.byte_length = r.byte_length;
-                t.num_values = r.num_values;
-                if (s == COVT_SLOT_VBUF && L.geom_column_type == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) t.num_values *= 2;
-                t.op = r.op;
-                t.num_bits = L.num_bits;
-                t.no_shift = (flags & COVT_FLAG_MORTON_NO_SHIFT) ? 1 : 0;
-                t.exact_length = 1;
-                t.status = COVT_OK;
-                t.consumed = 0;
-                t.ref = (uint32_t)run[0] * COVT_NUM_SLOTS + (uint32_t)s;
-                tasks[run[COL_CLASS0 + c]++] = t;
+    const uint32_t tile = t + tile_base;
+    NoProps props;
+    walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, lite, props, [&](uint32_t li, const LayerHead& H) {
+        const uint32_t layer = (uint32_t)run[0];
+        const uint32_t num_bits = 32u - (uint32_t)__clz(H.extent);  // CovtParser.java:77
+        // ops + payload offsets (streams of the geometry column follow each other in slot order)
+        uint32_t layer_status = COVT_OK;
+        uint64_t pay = H.geom_offset;
+        const uint64_t F = lite_nv(lite, COVT_SLOT_TYPES);
+        const uint64_t cap_parts = (flags & COVT_FLAG_SKIP_ASSEMBLY) ? 0 : F + lite_nv(lite, COVT_SLOT_PART);
+        const uint64_t cap_rings = (flags & COVT_FLAG_SKIP_ASSEMBLY) ? 0 : cap_parts + lite_nv(lite, COVT_SLOT_RING);
+        uint4* dst = reinterpret_cast<uint4*>(&layers[layer]);
+        dst[0] = make_uint4(tile, li, H.extent, H.num_features);
+        // (status is patched below once every stream's op is known)
+        uint32_t wq[4];
+        int q = 2;  // 16-byte chunk being assembled, words 8 ..
+        int k = 0;
+        auto push = [&](uint32_t w) {
+            wq[k++] = w;
+            if (k == 4) { dst[q++] = make_uint4(wq[0], wq[1], wq[2], wq[3]); k = 0; }
+        };
+        push((uint32_t)H.name_offset);
+        push((uint32_t)(H.name_offset >> 32));
+#pragma unroll
+        for (int s = 0; s < COVT_NUM_SLOTS; s++) {
+            const bool have = lite.has(s);
+            uint64_t off = 0;
+            uint32_t op = COVT_OP_NONE, status = COVT_OK;
+            if (have) {
+                if (s == COVT_SLOT_ID) off = H.id_offset;
+                else { off = pay; pay += lite.bl(s); }
+                op = resolve_op(slot_stream_type(s), lite.enc(s), H.geom_ct, flags);
+                if (op == COVT_OP_NONE) {
+                    status = COVT_ERR_UNSUPPORTED_ENCODING;
+                    if (!layer_status) layer_status = COVT_ERR_UNSUPPORTED_ENCODING;
+                }
+            }
+            push((uint32_t)off);
+            push((uint32_t)(off >> 32));
+            push(have ? lite.bl(s) : 0u);
+            push(have ? lite.nv(s) : 0u);
+            push((have ? lite.enc(s) : (uint32_t)COVT_ENC_ABSENT) | (op << 8));
+            push(status);
+            // the decode task of the stream
+            const int c = have ? op_class_of(op) : -1;
+            if (c >= 0) {
+                const int b = slot_buf(s);
+                uint32_t nv = lite.nv(s);
+                if (s == COVT_SLOT_VBUF && H.geom_ct == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) nv *= 2;
+                const uint64_t dptr = reinterpret_cast<uint64_t>(bufs.ptr[b]) + run[(1 + b) * K0_BLOCK] * kBufElemSizeDev(b);
+                uint2* tp = reinterpret_cast<uint2*>(&tasks[run[(COL_CLASS0 + c) * K0_BLOCK]]);
+                run[(COL_CLASS0 + c) * K0_BLOCK] += 1;
+                tp[0] = make_uint2((uint32_t)off, (uint32_t)(off >> 32));
+                tp[1] = make_uint2((uint32_t)dptr, (uint32_t)(dptr >> 32));
+                tp[2] = make_uint2(lite.bl(s), nv);
+                tp[3] = make_uint2(op | (num_bits << 8) | ((flags & COVT_FLAG_MORTON_NO_SHIFT) ? 1u << 16 : 0u) | (1u << 24), COVT_OK);
+                tp[4] = make_uint2(0u, layer * COVT_NUM_SLOTS + (uint32_t)s);
             }
         }
+        // out[13]: element offset of the layer's slice in every result buffer
+#pragma unroll
+        for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
+            const uint64_t o = run[(1 + b) * K0_BLOCK];
+            push((uint32_t)o);
+            push((uint32_t)(o >> 32));
+            run[(1 + b) * K0_BLOCK] = o + align_elems(lite_slice_size(lite, H.geom_ct, flags, b), kBufElemSizeDev(b));
+        }
+        push(0u); push(0u); push(0u); push(0u);  // n_parts, n_rings, n_vertices, n_coords: written by the assembler
+        push((uint32_t)cap_parts);
+        push((uint32_t)cap_rings);
+        push(0u); push(0u);
+        dst[1] = make_uint4(H.num_columns, layer_status, H.geom_ct | (num_bits << 8) | (lite.has(COVT_SLOT_ID) ? 1u << 16 : 0u), H.name_length);
         run[0] += 1;
     });
 }

@@ -677,23 +677,41 @@ static const uint8_t slot_stream_type[COVT_NUM_SLOTS] = {
     COVT_ST_DATA, COVT_ST_GEOMETRY_TYPES, COVT_ST_GEOMETRY_OFFSETS, COVT_ST_PART_OFFSETS,
     COVT_ST_RING_OFFSETS, COVT_ST_VERTEX_OFFSETS, COVT_ST_VERTEX_BUFFER, COVT_ST_INDEX_BUFFER};
 
-/* resolve ops + assign payload offsets in the fixed payload order (CovtParser.java:405-510):
- * [id] | types, geometry_offsets, part_offsets, ring_offsets, vertex_offsets, vertex_buffer [, index_buffer] */
-static uint64_t layer_place_streams(covt_layer* L, uint64_t payload, uint32_t flags)
+/* Payload placement. The reference consumes the columns IN METADATA ORDER (CovtParser.java:64-85 iterates a LinkedHashMap),
+ * and the streams of the geometry column in the fixed order types, geometry_offsets, part_offsets, ring_offsets,
+ * vertex_offsets, vertex_buffer [, index_buffer] (CovtParser.java:405-510). */
+static void place_id(covt_layer* L, uint64_t* p)
+{
+    covt_stream_ref* r = &L->streams[COVT_SLOT_ID];
+    if (r->encoding == COVT_ENC_ABSENT) return;
+    r->byte_offset = *p;
+    *p += r->byte_length;
+}
+static void place_geometry(covt_layer* L, uint64_t* p)
+{
+    for (int s = COVT_SLOT_TYPES; s < COVT_NUM_SLOTS; s++) {
+        covt_stream_ref* r = &L->streams[s];
+        if (r->encoding == COVT_ENC_ABSENT) continue;
+        r->byte_offset = *p;
+        *p += r->byte_length;
+    }
+}
+/* dispatch of every present stream (CovtParser.decodeGeometryColumn :392-511, decodedIds :552-572) */
+static void layer_resolve_ops(covt_layer* L, uint32_t flags)
 {
     for (int s = 0; s < COVT_NUM_SLOTS; s++) {
         covt_stream_ref* r = &L->streams[s];
         if (r->encoding == COVT_ENC_ABSENT) continue;
-        r->byte_offset = payload;
-        payload += r->byte_length;
         r->op = (uint8_t)covt_oracle_resolve_op(slot_stream_type[s], r->encoding, L->geom_column_type, flags);
         if (r->op == COVT_OP_NONE) {
             r->status = COVT_ERR_UNSUPPORTED_ENCODING;
             if (!L->status) L->status = COVT_ERR_UNSUPPORTED_ENCODING;
         }
     }
-    return payload;
 }
+/* one entry per column, in metadata order */
+enum { COL_ID = 0, COL_GEOMETRY = 1, COL_PROPERTY = 2 };
+typedef struct { uint8_t kind; uint8_t data_type; uint64_t listed_bytes; } col_t;
 
 /* Library policy shared with the product (result buffers are sized from numValues before anything is decoded): a stream that
  * claims more than 256 values per payload byte cannot decode with any codec of the path (the densest, FastPFOR at bit width 0,
@@ -726,28 +744,35 @@ static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, ui
         L->num_columns = c_varint(&c);
         if (c.err) return COVT_ERR_TRUNCATED;
         L->num_bits = (uint8_t)(32 - nlz32(L->extent));
-        uint64_t property_bytes = 0;
-        int have_geometry = 0;
-        for (uint32_t ci = 0; ci < L->num_columns; ci++) {
+        if ((uint64_t)L->num_columns > end - c.p) return COVT_ERR_TRUNCATED; /* every column takes bytes: bounds the table below */
+        col_t* cols = (col_t*)calloc((size_t)L->num_columns + 1, sizeof(col_t));
+        if (!cols) return COVT_ERR_OOM;
+        int have_geometry = 0, have_id_column = 0;
+        int32_t rc = COVT_OK;
+        for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
             uint64_t noff; uint32_t nlen;
             c_string(&c, &noff, &nlen);
             uint32_t data_type = c_byte(&c);
             uint32_t column_type = c_byte(&c);
             uint32_t num_streams = c_varint(&c);
-            if (c.err) return COVT_ERR_TRUNCATED;
+            if (c.err) { rc = COVT_ERR_TRUNCATED; break; }
             (void)data_type;
             int is_id = name_is(blob, noff, nlen, "id");
             int is_geom = name_is(blob, noff, nlen, "geometry");
-            if (ci == 0 && !is_id && !is_geom) return COVT_ERR_BAD_METADATA; /* CovtParser.java:67-69 */
+            if (ci == 0 && !is_id && !is_geom) { rc = COVT_ERR_BAD_METADATA; break; } /* CovtParser.java:67-69 */
+            /* the reference keeps the columns in a map keyed by name: one id and one geometry column */
+            if ((is_id && have_id_column) || (is_geom && have_geometry)) { rc = COVT_ERR_BAD_METADATA; break; }
+            if (is_id) have_id_column = 1;
             if (is_geom) { L->geom_column_type = (uint8_t)column_type; have_geometry = 1; }
-            if (is_geom && column_type > COVT_CT_ICE_MORTON_CODE) return COVT_ERR_BAD_METADATA;
+            if (is_geom && column_type > COVT_CT_ICE_MORTON_CODE) { rc = COVT_ERR_BAD_METADATA; break; }
+            cols[ci].kind = is_id ? COL_ID : (is_geom ? COL_GEOMETRY : COL_PROPERTY);
             for (uint32_t si = 0; si < num_streams; si++) {
                 uint64_t soff; uint32_t slen;
                 c_string(&c, &soff, &slen);
                 uint32_t nv = c_varint(&c);
                 uint32_t bl = c_varint(&c);
                 uint32_t enc = c_byte(&c);
-                if (c.err) return COVT_ERR_TRUNCATED;
+                if (c.err) { rc = COVT_ERR_TRUNCATED; break; }
                 int slot = -1;
                 if (is_id) { if (name_is(blob, soff, slen, "data")) slot = COVT_SLOT_ID; }
                 else if (is_geom) {
@@ -760,25 +785,35 @@ static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, ui
                     else if (name_is(blob, soff, slen, "index_buffer")) slot = COVT_SLOT_INDEX;
                 }
                 if (slot >= 0) {
-                    if (enc > COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) return COVT_ERR_BAD_METADATA;
-                    if (!plausible_count(nv, bl)) return COVT_ERR_TRUNCATED;
+                    if (enc > COVT_ENC_FAST_PFOR_DELTA_ZIG_ZAG) { rc = COVT_ERR_BAD_METADATA; break; }
+                    if (!plausible_count(nv, bl)) { rc = COVT_ERR_TRUNCATED; break; }
                     L->streams[slot].num_values = nv;
                     L->streams[slot].byte_length = bl;
                     L->streams[slot].encoding = (uint8_t)enc;
                     if (slot == COVT_SLOT_ID) L->has_id = 1;
                 } else if (is_id || is_geom) {
-                    return COVT_ERR_BAD_METADATA;
+                    rc = COVT_ERR_BAD_METADATA;
+                    break;
                 } else {
-                    property_bytes += bl;
+                    cols[ci].listed_bytes += bl;
                 }
             }
         }
-        if (!have_geometry || L->streams[COVT_SLOT_TYPES].encoding == COVT_ENC_ABSENT ||
-            L->streams[COVT_SLOT_VBUF].encoding == COVT_ENC_ABSENT)
-            return COVT_ERR_BAD_METADATA;
-        uint64_t payload_end = layer_place_streams(L, c.p, flags) + property_bytes;
-        if (payload_end > end) return COVT_ERR_TRUNCATED;
-        c.p = payload_end;
+        if (rc == COVT_OK && (!have_geometry || L->streams[COVT_SLOT_TYPES].encoding == COVT_ENC_ABSENT ||
+                              L->streams[COVT_SLOT_VBUF].encoding == COVT_ENC_ABSENT))
+            rc = COVT_ERR_BAD_METADATA;
+        /* payloads in column-metadata order */
+        uint64_t p = c.p;
+        for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
+            if (cols[ci].kind == COL_ID) place_id(L, &p);
+            else if (cols[ci].kind == COL_GEOMETRY) place_geometry(L, &p);
+            else p += cols[ci].listed_bytes;
+            if (p > end) rc = COVT_ERR_TRUNCATED;
+        }
+        free(cols);
+        if (rc != COVT_OK) return rc;
+        layer_resolve_ops(L, flags);
+        c.p = p;
         (*n_layers)++;
     }
     *end_pos = c.p;
@@ -830,11 +865,10 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
         L->num_columns = c_varint(&c);
         if (c.err) return COVT_ERR_TRUNCATED;
         L->num_bits = (uint8_t)(32 - nlz32(L->extent)); /* CovtParser.java:77 */
-        /* property columns: remember what is needed to hop over their payload */
-        typedef struct { uint8_t data_type; uint64_t listed_bytes; } prop_t;
-        prop_t* props = (prop_t*)malloc(((size_t)L->num_columns + 1) * sizeof(prop_t));
-        uint32_t n_props = 0;
-        int have_geometry = 0;
+        if ((uint64_t)L->num_columns > end - c.p) return COVT_ERR_TRUNCATED; /* every column takes bytes: bounds the table below */
+        col_t* cols = (col_t*)calloc((size_t)L->num_columns + 1, sizeof(col_t));
+        if (!cols) return COVT_ERR_OOM;
+        int have_geometry = 0, have_id_column = 0;
         int32_t rc = COVT_OK;
         for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
             int is_id = 0, is_geom = 0;
@@ -855,8 +889,12 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
             uint32_t column_type = column_desc & 0x7;
             if (column_type > COVT_CT_ICE_MORTON_CODE) { rc = COVT_ERR_BAD_METADATA; break; } /* ColumnType.values()[..] throws */
             if (ci == 0 && !is_id && !is_geom) { rc = COVT_ERR_BAD_METADATA; break; } /* :67-69 */
+            /* the reference keeps the columns in a map keyed by name: one id and one geometry column */
+            if ((is_id && have_id_column) || (is_geom && have_geometry)) { rc = COVT_ERR_BAD_METADATA; break; }
+            if (is_id) have_id_column = 1;
             if (is_geom) { L->geom_column_type = (uint8_t)column_type; have_geometry = 1; }
-            uint64_t listed = 0;
+            cols[ci].kind = is_id ? COL_ID : (is_geom ? COL_GEOMETRY : COL_PROPERTY);
+            cols[ci].data_type = (uint8_t)data_type;
             for (;;) { /* :628-648 */
                 uint32_t stream_desc = c_byte(&c);
                 uint32_t stream_type = stream_desc >> 4;
@@ -877,36 +915,35 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
                     L->streams[slot].encoding = (uint8_t)enc;
                     if (slot == COVT_SLOT_ID) L->has_id = 1;
                 } else if (is_id || is_geom) { rc = COVT_ERR_BAD_METADATA; break; }
-                else listed += bl;
+                else cols[ci].listed_bytes += bl;
                 /* last stream of the column, :639-647. (INDEX_BUFFER, when present, precedes VERTEX_BUFFER in the
                  * metadata so that the reference terminator still ends the column.) */
                 if (data_type == COVT_DT_GEOMETRY && stream_type == COVT_ST_VERTEX_BUFFER) break;
                 else if (stream_type == COVT_ST_DATA && column_type == COVT_CT_PLAIN) break;
                 else if (stream_type == COVT_ST_DICTIONARY) break;
             }
-            if (rc != COVT_OK) break;
-            if (!is_id && !is_geom) { props[n_props].data_type = (uint8_t)data_type; props[n_props].listed_bytes = listed; n_props++; }
         }
         if (rc == COVT_OK && (!have_geometry || L->streams[COVT_SLOT_TYPES].encoding == COVT_ENC_ABSENT ||
                               L->streams[COVT_SLOT_VBUF].encoding == COVT_ENC_ABSENT))
             rc = COVT_ERR_BAD_METADATA;
-        uint64_t p = 0;
-        if (rc == COVT_OK) {
-            p = layer_place_streams(L, c.p, flags);
-            if (p > end) rc = COVT_ERR_TRUNCATED;
-        }
-        /* hop over property columns: BOOLEAN = listed data stream only (CovtParser.java:280-290); every other
-         * type = unlisted Byte-RLE present stream of ceil(numFeatures/8) bytes (:295) + listed streams */
-        for (uint32_t k = 0; k < n_props && rc == COVT_OK; k++) {
-            if (props[k].data_type != COVT_DT_BOOLEAN) {
-                uint32_t nbytes = (L->num_features + 7) / 8;
-                if (byte_rle_span(blob, p, end, nbytes, &p)) { rc = COVT_ERR_TRUNCATED; break; }
+        /* payloads in column-metadata order. Property columns: BOOLEAN = listed data stream only (CovtParser.java:280-290);
+         * every other type = unlisted Byte-RLE present stream of ceil(numFeatures/8) bytes (:295) + its listed streams */
+        uint64_t p = c.p;
+        for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
+            if (cols[ci].kind == COL_ID) place_id(L, &p);
+            else if (cols[ci].kind == COL_GEOMETRY) place_geometry(L, &p);
+            else {
+                if (cols[ci].data_type != COVT_DT_BOOLEAN) {
+                    uint32_t nbytes = (L->num_features + 7) / 8;
+                    if (byte_rle_span(blob, p, end, nbytes, &p)) { rc = COVT_ERR_TRUNCATED; break; }
+                }
+                p += cols[ci].listed_bytes;
             }
-            p += props[k].listed_bytes;
             if (p > end) rc = COVT_ERR_TRUNCATED;
         }
-        free(props);
+        free(cols);
         if (rc != COVT_OK) return rc;
+        layer_resolve_ops(L, flags);
         c.p = p;
         (*n_layers)++;
         li++;

@@ -92,20 +92,32 @@ def test_fixture_geometry_equals_mvt(covt, decoder, fixtures):
     assert checked >= 1100
 
 
-def test_gen3_rewrapped_fixtures(covt, oracle, decoder, fixtures):
-    """gen-3 (HEAD CovtParser grammar) inputs made by a metadata-only re-wrap of the gen-2b fixtures decode to the
-    same streams and geometry as the gen-2b originals; optimised metadata goes through the TileJSON side-car."""
+@pytest.mark.parametrize("props,id_last", [(False, False), (True, False), (True, True)])
+def test_gen3_rewrapped_fixtures(covt, oracle, gen, decoder, fixtures, props, id_last):
+    """gen-3 (HEAD CovtParser grammar) inputs made by re-wrapping the gen-2b fixtures decode to the same streams and geometry as
+    the gen-2b originals; optimised metadata goes through the TileJSON side-car. props: the tiles keep their property columns
+    as the HEAD converter writes them (unlisted Byte-RLE present streams, up to 40+ columns per layer: the device walker hops over
+    every one of them); id_last: the id column follows the geometry column (columns are consumed in metadata order)."""
     abi = covt.abi
-    names = ["omt/5_16_21", "omt/2_2_2", "omt/7_66_84", "omt/14_8298_10748", "amazon/5_5_11", "bing/4-8-5"]
+    names = ["omt/5_16_21", "omt/2_2_2", "omt/7_66_84", "omt/14_8298_10748", "amazon/5_5_11", "bing/4-8-5", "omt/12_2132_2734"]
     have = dict(fixtures)
     tiles = [have[n] for n in names if n in have]
     assert len(tiles) >= 4
     flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
     for optimized in (False, True):
-        wrapped = [util.rewrap_gen3(abi, oracle, t, optimized) for t in tiles]
-        nf = max(len(w[1]) for w in wrapped) * [0] if optimized else None
+        wrapped = [util.rewrap_gen3(abi, oracle, t, optimized, props=props, gen=gen, id_last=id_last) for t in tiles]
+        # one TileJSON for the batch: vector layer i carries the largest field count any tile needs for its layer i
+        nf = None
+        if optimized:
+            nf = [0] * max(len(w[1]) for w in wrapped)
+            for w in wrapped:
+                for i, n in enumerate(w[1]):
+                    nf[i] = max(nf[i], n)
         blob3, offs3 = util.concat_tiles([w[0] for w in wrapped])
         res3, ref3 = _decode_both(covt, oracle, decoder, blob3, offs3, container=abi.CONTAINER_GEN3, flags=flags, n_fields=nf)
+        assert np.all(ref3.tile_status == 0)
+        if props:
+            assert int(ref3.layers["num_columns"].max()) > 10
         util.compare_results(abi, res3, ref3)
         # and against the gen-2b decode of the same tiles: identical decoded buffers
         blob2, offs2 = util.concat_tiles(tiles)
@@ -113,6 +125,27 @@ def test_gen3_rewrapped_fixtures(covt, oracle, decoder, fixtures):
         util.compare_results(abi, res3, res2, same_container=False)
         res2.free()
         res3.free()
+
+
+def test_id_column_after_geometry_gen2b(covt, oracle, gen, decoder):
+    """Columns are consumed in METADATA order (CovtParser.java:64-85): a gen-2b tile whose id column follows the geometry column
+    carries the id payload behind the geometry payload."""
+    abi = covt.abi
+    blob, offs, truth = gen.tiles(77, 40, gen.default_params())
+    from oracle import properties as P
+    tiles = []
+    for i in range(40):
+        t = bytes(blob[int(offs[i]):int(offs[i + 1])])
+        tiles.append(util.swap_id_and_geometry_gen2b(P, t))
+    blob2, offs2 = util.concat_tiles(tiles)
+    res, ref = _decode_both(covt, oracle, decoder, blob2, offs2)
+    assert np.all(ref.tile_status == 0) and ref.layers["has_id"].all()
+    L = ref.layers[0]
+    assert L["streams"][abi.SLOT_ID]["byte_offset"] > L["streams"][abi.SLOT_VBUF]["byte_offset"]
+    util.compare_results(abi, res, ref)
+    ref0 = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT)
+    util.compare_results(abi, res, ref0, same_container=False)
+    res.free()
 
 
 @pytest.mark.parametrize("container", [0, 1, 2])
@@ -307,8 +340,8 @@ def _mutants(rng, base, n_mutants, good_every):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("corpus", ["small_gen2b", "large_gen2b", "small_gen3"])
-def test_mutation_fuzz_against_oracle(covt, oracle, decoder, fixtures, corpus):
+@pytest.mark.parametrize("corpus", ["small_gen2b", "large_gen2b", "small_gen3", "small_gen3_props"])
+def test_mutation_fuzz_against_oracle(covt, oracle, gen, decoder, fixtures, corpus):
     """Mutants of fixture tiles (byte flips in metadata and payload, truncations, appended junk, dropped bytes) in ONE batch
     between good tiles: the call survives, tile / layer / stream statuses agree with the oracle on OK-ness, the result layout is
     identical, every stream and layer both sides accept is bit-exact, and the good tiles are untouched. small = 1 200 mutants
@@ -325,8 +358,9 @@ def test_mutation_fuzz_against_oracle(covt, oracle, decoder, fixtures, corpus):
     else:
         base = [b for _, b in sorted(clean, key=lambda t: len(t[1]))[:5]]
         n_mutants, good_every = 1200, 50
-        if corpus == "small_gen3":
-            base = [util.rewrap_gen3(abi, oracle, b)[0] for b in base]
+        if corpus.startswith("small_gen3"):
+            # (_props: the property columns stay in, so that mutations also hit the unlisted present streams and their hop-over)
+            base = [util.rewrap_gen3(abi, oracle, b, props=corpus.endswith("_props"), gen=gen)[0] for b in base]
             container = abi.CONTAINER_GEN3
     assert len(base) >= 3
     tiles, good = _mutants(np.random.default_rng(2026), base, n_mutants, good_every)

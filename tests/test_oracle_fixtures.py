@@ -181,3 +181,34 @@ def test_gen2b_grammar_reserialises_every_fixture_byte_for_byte(fixtures):
         assert rewrite.transcode_topology_to_rle(data, {}, keep_pfor=True) == data, name
         n_streams += sum(len(c["streams"]) for L in rewrite.walk(data)[1] for c in L["columns"])
     assert len(fixtures) == 129 and n_streams == 38449  # the census of SURVEY §4.4
+
+
+def test_gen3_walk_with_property_columns(oracle, gen, fixtures):
+    """gen-3 (HEAD grammar, CovtParser.java:574-652) tiles that KEEP their property columns the way the HEAD converter writes them
+    (unlisted Byte-RLE present streams, CovtConverter.java:434-436; up to 40+ columns per layer): the oracle's walk hops over
+    every property payload, lands on EOF, and decodes the same geometry and ids as from the gen-2b original — with optimised and
+    plain metadata, and with the id column before or after the geometry column (columns are consumed in metadata order,
+    CovtParser.java:64-85)."""
+    abi = oracle.abi
+    pick = [(n, b) for n, b in fixtures if n in ("omt/5_16_21", "omt/2_2_2", "omt/14_8298_10748", "amazon/5_5_11", "amazon/8_136_89",
+                                                  "bing/4-8-5", "bing/5-16-11", "omt/9_265_341", "omt/12_2132_2734")]
+    assert len(pick) >= 6
+    max_cols = 0
+    for k, (name, data) in enumerate(pick):
+        flags = abi.FLAG_CLOSE_RINGS | _flags(abi, name)
+        blob2, offs2 = util.concat_tiles([data])
+        ref2 = oracle.decode_batch(blob2, offs2, abi.CONTAINER_GEN2B, flags)
+        for optimized in (False, True):
+            for id_last in (False, True):
+                w, nf = util.rewrap_gen3(abi, oracle, data, optimized, props=True, gen=gen, id_last=id_last)
+                blob3, offs3 = util.concat_tiles([w])
+                rc, layers, end_pos = oracle.parse_tile(blob3, abi.CONTAINER_GEN3, flags=flags, n_fields=nf)
+                assert rc == 0 and end_pos == len(w), (name, optimized, id_last, rc, end_pos, len(w))
+                max_cols = max(max_cols, int(layers["num_columns"].max()))
+                ref3 = oracle.decode_batch(blob3, offs3, abi.CONTAINER_GEN3, flags, n_fields=nf)
+                assert np.array_equal(ref3.tile_status, ref2.tile_status)
+                util.compare_results(abi, ref3, ref2, same_container=False)
+                if id_last and ref3.layers["has_id"].any():
+                    L = ref3.layers[ref3.layers["has_id"] != 0][0]
+                    assert L["streams"][abi.SLOT_ID]["byte_offset"] > L["streams"][abi.SLOT_VBUF]["byte_offset"]
+    assert max_cols > 10  # more property columns than the 8 the round-1 device walker could hop over

@@ -116,41 +116,142 @@ def _varint(v):
             return bytes(out)
 
 
-def rewrap_gen3(abi, oracle, tile_bytes, optimized=False):
-    """Re-wraps one gen-2b tile as gen-3 (CovtParser.decodeLayerMetadata grammar, CovtParser.java:574-652):
-    same stream payload bytes and order, id + geometry columns only (property columns dropped).
+def _gen3_property_column(abi, P, tile_arr, tile, col, F, gen):
+    """One gen-2b property column as the HEAD converter lays it out (CovtConverter.java:1062-1195): (descriptor byte, listed stream
+    metadata bytes, payload bytes) or None for column kinds HEAD cannot write (localized dictionaries, :1180-1182)."""
+    dt2, ct = col["data_type"], col["column_type"]
+    S = {s["name"]: s for s in col["streams"]}
+
+    def raw(s):
+        return bytes(tile[s["offset"]:s["offset"] + s["byte_length"]])
+
+    def meta(stream_type, s, byte_length=None, encoding=None):
+        return (bytes([(stream_type << 4) | (s["encoding"] if encoding is None else encoding)]) + _varint(s["num_values"]) +
+                _varint(s["byte_length"] if byte_length is None else byte_length))
+    if dt2 == P.DT2_BOOLEAN and ct == abi.CT_PLAIN:
+        # HEAD: data = one bit per FEATURE, Byte-RLE, no present stream (CovtParser.java:280-290, CovtConverter.java:1062-1076)
+        present = P._bitset(tile_arr, S["present"], F) if "present" in S else np.ones(F, bool)
+        dense = P._bitset(tile_arr, S["data"], S["data"]["num_values"])
+        bits = np.zeros(F, bool)
+        bits[np.nonzero(present)[0][:len(dense)]] = dense[:int(present.sum())]
+        payload = bytes(gen.encode_byte_rle(np.packbits(bits, bitorder="little")))
+        return (abi.DT_BOOLEAN << 3) | abi.CT_PLAIN, meta(abi.ST_DATA, S["data"], len(payload), abi.ENC_BOOLEAN_RLE), payload
+    if ct == abi.CT_LOCALIZED_DICTIONARY or "present" not in S or "data" not in S:
+        return None
+    head_dt = {P.DT2_STRING: abi.DT_STRING, P.DT2_FLOAT: abi.DT_FLOAT, P.DT2_DOUBLE: abi.DT_DOUBLE, P.DT2_INT_64: abi.DT_INT_64,
+               P.DT2_UINT_64: abi.DT_UINT_64}.get(dt2)
+    if head_dt is None:
+        return None
+    if dt2 == P.DT2_STRING:
+        if ct != abi.CT_DICTIONARY:
+            return None
+        # payload order present, data, length, dictionary (CovtConverter.java:1152-1167); the present stream is NOT listed (:434-436)
+        return ((head_dt << 3) | ct, meta(abi.ST_DATA, S["data"]) + meta(abi.ST_LENGTH, S["length"]) + meta(abi.ST_DICTIONARY, S["dictionary"]),
+                raw(S["present"]) + raw(S["data"]) + raw(S["length"]) + raw(S["dictionary"]))
+    if ct != abi.CT_PLAIN:
+        return None
+    return (head_dt << 3) | ct, meta(abi.ST_DATA, S["data"]), raw(S["present"]) + raw(S["data"])
+
+
+def rewrap_gen3(abi, oracle, tile_bytes, optimized=False, props=False, gen=None, id_last=False):
+    """Re-wraps one gen-2b tile as gen-3 (CovtParser.decodeLayerMetadata grammar, CovtParser.java:574-652): same stream payload
+    bytes and order. props=False: id + geometry columns only. props=True (needs gen = tools.gen.gen): the property columns are
+    kept the way the HEAD converter writes them — unlisted Byte-RLE present streams, BOOLEAN data as one bit per feature,
+    payloads in column order after the geometry (localized dictionaries, which HEAD cannot write, are dropped).
+    id_last: the id column FOLLOWS the geometry column (metadata and payload), the order CovtParser.java:64-85 also accepts.
     Returns (gen-3 bytes, n_fields list for the TileJSON side-car or None)."""
     blob = np.frombuffer(tile_bytes, dtype=np.uint8)
     rc, layers, ep = oracle.parse_tile(blob, abi.CONTAINER_GEN2B, flags=0)
     assert rc == 0 and ep == len(blob)
+    pl = None
+    if props:
+        from oracle import properties as P
+        pl = P.walk_gen2b(bytes(tile_bytes))
+        tile_arr = np.frombuffer(bytes(tile_bytes) + bytes(64), dtype=np.uint8)
     out = bytearray()
+    n_fields = []
     stream_type_of_slot = [abi.ST_DATA, abi.ST_GEOMETRY_TYPES, abi.ST_GEOMETRY_OFFSETS, abi.ST_PART_OFFSETS,
                            abi.ST_RING_OFFSETS, abi.ST_VERTEX_OFFSETS, abi.ST_VERTEX_BUFFER, abi.ST_INDEX_BUFFER]
     for li, L in enumerate(layers):
         name = bytes(blob[int(L["name_offset"]):int(L["name_offset"]) + int(L["name_length"])])
+        pcols = []
+        if props:
+            for c in pl[li]["columns"]:
+                if c["data_type"] == P.DT2_GEOMETRY or c["name"] == "id":
+                    continue
+                pc = _gen3_property_column(abi, P, tile_arr, bytes(tile_bytes), c, int(L["num_features"]), gen)
+                if pc is not None:
+                    pcols.append((c["name"].encode(),) + pc)
+        n_fields.append(len(pcols))
         out.append((1 << 1) | (1 if optimized else 0))
         out += _varint(li) if optimized else _varint(len(name)) + name
-        out += _varint(int(L["extent"])) + _varint(int(L["num_features"])) + _varint(2 if L["has_id"] else 1)
-        col = 0
-        if L["has_id"]:
+        out += _varint(int(L["extent"])) + _varint(int(L["num_features"])) + _varint((2 if L["has_id"] else 1) + len(pcols))
+
+        def id_column(first):
             s = L["streams"][abi.SLOT_ID]
-            out += _varint(0) + bytes([(abi.DT_UINT_64 << 3) | abi.CT_PLAIN])
-            out += bytes([(abi.ST_DATA << 4) | int(s["encoding"])]) + _varint(int(s["num_values"])) + _varint(int(s["byte_length"]))
-            col += 1
-        out += _varint(1) if (optimized or col == 0) else _varint(8) + b"geometry"
-        out.append((abi.DT_GEOMETRY << 3) | int(L["geom_column_type"]))
-        order = [abi.SLOT_TYPES, abi.SLOT_GEOM, abi.SLOT_PART, abi.SLOT_RING, abi.SLOT_VOFF, abi.SLOT_INDEX, abi.SLOT_VBUF]
-        for slot in order:
-            s = L["streams"][slot]
-            if s["encoding"] == abi.ENC_ABSENT:
-                continue
-            out += bytes([(stream_type_of_slot[slot] << 4) | int(s["encoding"])]) + _varint(int(s["num_values"])) + _varint(int(s["byte_length"]))
-        for slot in range(abi.NUM_SLOTS):  # payload order = slot order
-            s = L["streams"][slot]
-            if s["encoding"] == abi.ENC_ABSENT:
-                continue
-            out += bytes(blob[int(s["byte_offset"]):int(s["byte_offset"]) + int(s["byte_length"])])
-    return bytes(out), ([0] * len(layers) if optimized else None)
+            return ((_varint(0) if (optimized or first) else _varint(2) + b"id") + bytes([(abi.DT_UINT_64 << 3) | abi.CT_PLAIN]) +
+                    bytes([(abi.ST_DATA << 4) | int(s["encoding"])]) + _varint(int(s["num_values"])) + _varint(int(s["byte_length"])))
+
+        def geometry_column(first):
+            m = (_varint(1) if (optimized or first) else _varint(8) + b"geometry") + bytes([(abi.DT_GEOMETRY << 3) | int(L["geom_column_type"])])
+            for slot in [abi.SLOT_TYPES, abi.SLOT_GEOM, abi.SLOT_PART, abi.SLOT_RING, abi.SLOT_VOFF, abi.SLOT_INDEX, abi.SLOT_VBUF]:
+                s = L["streams"][slot]
+                if s["encoding"] != abi.ENC_ABSENT:
+                    m += bytes([(stream_type_of_slot[slot] << 4) | int(s["encoding"])]) + _varint(int(s["num_values"])) + _varint(int(s["byte_length"]))
+            return m
+
+        def payload_of(slots):
+            b = bytearray()
+            for slot in slots:
+                s = L["streams"][slot]
+                if s["encoding"] != abi.ENC_ABSENT:
+                    b += bytes(blob[int(s["byte_offset"]):int(s["byte_offset"]) + int(s["byte_length"])])
+            return b
+        geom_slots = list(range(abi.SLOT_TYPES, abi.NUM_SLOTS))  # payload order = slot order
+        if L["has_id"] and not id_last:
+            out += id_column(True) + geometry_column(False)
+            payload = payload_of([abi.SLOT_ID]) + payload_of(geom_slots)
+        elif L["has_id"]:
+            out += geometry_column(True) + id_column(False)
+            payload = payload_of(geom_slots) + payload_of([abi.SLOT_ID])
+        else:
+            out += geometry_column(True)
+            payload = payload_of(geom_slots)
+        for k, (cname, desc, smeta, spayload) in enumerate(pcols):
+            out += (_varint(2 + k) if optimized else _varint(len(cname)) + cname) + bytes([desc]) + smeta
+            payload += spayload
+        out += payload
+    return bytes(out), (n_fields if optimized else None)
+
+
+def swap_id_and_geometry_gen2b(P, tile):
+    """The same gen-2b tile with the id column moved behind the geometry column, metadata and payload (test input for the
+    metadata-order placement rule)."""
+    tile = bytes(tile)
+    layers = P.walk_gen2b(tile)
+
+    def col_meta(c):
+        m = _varint(len(c["name"].encode())) + c["name"].encode() + bytes([c["data_type"], c["column_type"]]) + _varint(len(c["streams"]))
+        for s in c["streams"]:
+            m += _varint(len(s["name"].encode())) + s["name"].encode() + _varint(s["num_values"]) + _varint(s["byte_length"]) + bytes([s["encoding"]])
+        return m
+
+    def col_payload(c):
+        ss = c["streams"]
+        if c["name"] == "geometry":
+            ss = sorted(ss, key=lambda s: s["offset"])
+        return b"".join(tile[s["offset"]:s["offset"] + s["byte_length"]] for s in ss)
+    out = bytearray(_varint(1) + _varint(len(layers)))
+    for L in layers:
+        cols = list(L["columns"])
+        if len(cols) >= 2 and cols[0]["name"] == "id" and cols[1]["name"] == "geometry":
+            cols[0], cols[1] = cols[1], cols[0]
+        out += _varint(len(L["name"].encode())) + L["name"].encode() + _varint(L["extent"]) + _varint(L["num_features"]) + _varint(len(cols))
+        for c in cols:
+            out += col_meta(c)
+        for c in cols:
+            out += col_payload(c)
+    return bytes(out)
 
 
 # ---- the same comparison without a per-layer Python loop (batches of 10^6 layers) ---------------------------------
