@@ -46,6 +46,9 @@ ABI_SYMBOLS = [
     "covt_result_num_tiles", "covt_result_num_layers", "covt_result_layers", "covt_result_tile_status",
     "covt_result_buffer", "covt_result_read", "covt_result_timing", "covt_result_kernel_times", "covt_result_free",
     "covt_host_register", "covt_host_unregister", "covt_partition_tiles",
+    "covt_create_multi", "covt_destroy_multi", "covt_multi_last_error", "covt_multi_device_count", "covt_multi_context",
+    "covt_decode_batch_multi", "covt_multi_result_parts", "covt_multi_result_part", "covt_multi_result_timing",
+    "covt_multi_result_read", "covt_multi_result_free",
 ]
 
 
@@ -87,6 +90,21 @@ def lib():
     L.covt_host_register.argtypes = [vp, vp, C.c_size_t]
     L.covt_host_unregister.argtypes = [vp, vp]
     L.covt_partition_tiles.argtypes = [vp, u32, u32, vp]
+    L.covt_create_multi.argtypes = [u32, C.POINTER(i32), C.POINTER(vp)]
+    L.covt_destroy_multi.argtypes = [vp]
+    L.covt_destroy_multi.restype = None
+    L.covt_multi_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.covt_multi_device_count.argtypes = [vp]
+    L.covt_multi_device_count.restype = u32
+    L.covt_multi_context.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(i32)]
+    L.covt_decode_batch_multi.argtypes = [vp, vp, vp, u32, u32, C.POINTER(abi.TileJson), u32, C.POINTER(vp)]
+    L.covt_multi_result_parts.argtypes = [vp]
+    L.covt_multi_result_parts.restype = u32
+    L.covt_multi_result_part.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u32), C.POINTER(u32), C.POINTER(i32)]
+    L.covt_multi_result_timing.argtypes = [vp, C.POINTER(abi.Timing)]
+    L.covt_multi_result_read.argtypes = [vp, u32, C.POINTER(vp)]
+    L.covt_multi_result_free.argtypes = [vp]
+    L.covt_multi_result_free.restype = None
     for name in ABI_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:
@@ -319,6 +337,109 @@ class Decoder:
         raw = res.buffer(abi.BUF_STREAM_ARENA, d.out_offset, d.out_count * dt.itemsize) if d.out_count else np.zeros(0, np.uint8)
         res.free()
         return raw.view(dt).copy(), d.status, d.bytes_consumed
+
+
+class MultiResult:
+    """Owns a covt_multi_result: one Result per GPU (device-resident), tile ranges in batch order."""
+
+    def __init__(self, owner, handle):
+        self._owner, self._h = owner, handle
+        self.parts = []
+        for p in range(lib().covt_multi_result_parts(handle)):
+            r, t0, n, dev = C.c_void_p(), C.c_uint32(), C.c_uint32(), C.c_int32()
+            owner._check(lib().covt_multi_result_part(handle, p, C.byref(r), C.byref(t0), C.byref(n), C.byref(dev)))
+            res = Result(owner._part_checker(p), r)
+            res.free = lambda: None  # owned by the multi result
+            self.parts.append({"result": res, "first_tile": t0.value, "n_tiles": n.value, "device": dev.value})
+
+    def timing(self):
+        t = abi.Timing()
+        self._owner._check(lib().covt_multi_result_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in abi.Timing._fields_}
+
+    def read_into(self, which, host_ptrs):
+        """Device->host copy of buffer `which` of every part at once (all GPUs copy side by side): part p -> host_ptrs[p]."""
+        arr = (C.c_void_p * len(host_ptrs))(*host_ptrs)
+        self._owner._check(lib().covt_multi_result_read(self._h, which, arr))
+
+    def free(self):
+        if self._h:
+            for p in self.parts:
+                p["result"]._h = None
+            lib().covt_multi_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _PartChecker:
+    """Error lookup of one per-GPU context of a MultiDecoder (Result only needs _check)."""
+
+    def __init__(self, ctx):
+        self._h = ctx
+
+    def _check(self, rc):
+        if rc:
+            buf = C.create_string_buffer(512)
+            lib().covt_last_error(self._h, buf, 512)
+            raise CovtError(rc, buf.value.decode())
+
+
+class MultiDecoder:
+    """The batch scheduler of the library (covt_create_multi): ONE call decodes a host batch on several GPUs of this box, one
+    persistent host thread + context per GPU, contiguous tile ranges balanced by payload bytes, no collective."""
+
+    def __init__(self, device_ids=None):
+        self._h = C.c_void_p()
+        n = 0 if device_ids is None else len(device_ids)
+        ids = (C.c_int32 * max(n, 1))(*(device_ids or [0]))
+        rc = lib().covt_create_multi(n, ids if device_ids is not None else None, C.byref(self._h))
+        if rc:
+            buf = C.create_string_buffer(512)
+            lib().covt_multi_last_error(None, buf, 512)
+            self._h = None
+            raise CovtError(rc, buf.value.decode())
+        self.n_devices = lib().covt_multi_device_count(self._h)
+
+    def _check(self, rc):
+        if rc:
+            buf = C.create_string_buffer(768)
+            lib().covt_multi_last_error(self._h, buf, 768)
+            raise CovtError(rc, buf.value.decode())
+
+    def _part_checker(self, part):
+        ctx, dev = C.c_void_p(), C.c_int32()
+        self._check(lib().covt_multi_context(self._h, part, C.byref(ctx), C.byref(dev)))
+        return _PartChecker(ctx)
+
+    def decode_batch(self, blob, tile_offsets, container=abi.CONTAINER_GEN2B, flags=abi.FLAG_DEFAULT, n_fields=None):
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        offs = np.ascontiguousarray(tile_offsets, dtype=np.uint64)
+        tj, keep = Decoder._tilejson(n_fields)
+        h = C.c_void_p()
+        self._check(lib().covt_decode_batch_multi(self._h, _ptr(b), offs.ctypes.data, len(offs) - 1, container,
+                                                  C.byref(tj) if tj is not None else None, flags, C.byref(h)))
+        return MultiResult(self, h)
+
+    def decode_batch_raw(self, blob_ptr, tile_offsets_ptr, n_tiles, container=abi.CONTAINER_GEN2B, flags=abi.FLAG_DEFAULT):
+        h = C.c_void_p()
+        self._check(lib().covt_decode_batch_multi(self._h, blob_ptr, tile_offsets_ptr, n_tiles, container, None, flags, C.byref(h)))
+        return MultiResult(self, h)
+
+    def close(self):
+        if self._h:
+            lib().covt_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- mirrors of the reference's static interface -----------------------------------------------------

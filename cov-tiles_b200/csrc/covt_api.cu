@@ -534,7 +534,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         // ---- K0 pass 2: the layer table + eight decode tasks per layer ----
         prof.begin("k0_fill_layers", 0);
         CKR(launch_k0_fill_layers(batch->d_blob, batch->d_tile_offsets + t0, nt, t0, container, d_tj, tj_layers, flags, d_cols, rb, R->d_layers, d_tasks,
-                                  class_off, R->d_first_layer + t0, d_seg, st));
+                                  class_off, R->d_first_layer + t0, d_seg, d_totals + 16, st));
         prof.end();
         // ---- every stream of every layer: one kernel per codec class ----
         if (prof.on || ctx->serial_classes) {
@@ -561,16 +561,16 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         }
         // ---- geometry assembly ----
         prof.begin("k_assemble_layers", 0);
-        CKR(launch_assemble_layers(R->d_layers, (uint32_t)std::min<uint64_t>(layers_per_seg_bound, 0xffffff00ull), rb, flags, d_counter + 15, d_seg, ctx->sm_count, st));
+        CKR(launch_assemble_layers(R->d_layers, (uint32_t)std::min<uint64_t>(layers_per_seg_bound, 0xffffff00ull), rb, flags, d_counter + 15, d_seg, d_totals + 16, ctx->sm_count, st));
         prof.end();
         CKR(launch_seg_end(d_seg, sg + 1 == S ? R->d_first_layer + n_tiles : nullptr, st));
         launches += 13;  // k_seg_begin, k0_fill_layers, 5 codec kernels + 4 second passes, k_assemble_layers, k_seg_end
     }
     if (n_tiles) {
-        prof.begin("k_finalize", 0);
-        CKR(launch_finalize(R->d_layers, R->d_first_layer, n_tiles, flags, R->d_tile_status, d_totals + 16, d_seg, st));
+        prof.begin("k_tile_status", 0);
+        CKR(launch_finalize(R->d_layers, R->d_first_layer, n_tiles, (uint32_t)std::min<uint64_t>(ctx->h_seg->cap[0], 0xffffff00ull), flags, R->d_tile_status, d_totals + 16, d_seg, st));
         prof.end();
-        launches += 1;
+        launches += prof.on ? 2 : 1;  // k_tile_status (+ k_alg_bytes when profiling)
     }
     CKR(cudaEventRecord(ev1, st));
     CKR(cudaMemcpyAsync(ctx->h_totals + 32, d_totals + 16, FINAL_TOTALS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -597,7 +597,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
     R->timing.payload_bytes = ctx->h_totals[33];
     R->timing.output_bytes = ctx->h_totals[34];
     if (prof.on) {
-        // algorithmic bytes per kernel: known only now that k_finalize has summed them on the device;
+        // algorithmic bytes per kernel: known only now that k_alg_bytes has summed them on the device;
         // booked on the first launch of each kernel (the records of one kernel are merged by name)
         const uint64_t meta_bytes = batch->blob_len > R->timing.payload_bytes ? batch->blob_len - R->timing.payload_bytes : 0;
         uint64_t n_task_entries = 0;
@@ -610,7 +610,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             else if (r.name == "scan_tile_cols") r.alg_bytes = 2ull * n_tiles * TILE_COLS * 8;
             else if (r.name == "k0_fill_layers") r.alg_bytes = meta_bytes + (uint64_t)n_tiles * (8 + TILE_COLS * 8) + (uint64_t)R->n_layers * sizeof(covt_layer) + n_task_entries * sizeof(DeviceTask);
             else if (r.name == "k_assemble_layers") r.alg_bytes = ctx->h_totals[32 + 8];
-            else if (r.name == "k_finalize") r.alg_bytes = (uint64_t)R->n_layers * sizeof(covt_layer);
+            else if (r.name == "k_tile_status") r.alg_bytes = (uint64_t)R->n_layers * 4 + (uint64_t)n_tiles * 12;
             else for (int c = 0; c < NUM_OP_CLASSES; c++) if (r.name == op_class_name(c)) r.alg_bytes = ctx->h_totals[32 + 3 + c];
         }
         prof.collect(R->kernel_times);

@@ -65,7 +65,7 @@ struct BigStream {
 // flags: bit 0 = first chunk of its stream, bit 1 = x/y interleaved sums
 struct __align__(16) ChunkState { uint32_t count; int32_t a, b; uint32_t flags; };
 constexpr int WORK_COUNTERS = 16;  // 3 per codec class (pass-1 ticket, queue length, pass-2 ticket) + the assembler's ticket
-constexpr int FINAL_TOTALS = 9;  // k_finalize: vertices, payload, output bytes, 5 codec classes, assembler
+constexpr int FINAL_TOTALS = 9;  // [0] vertices (assembler) [1] payload bytes [2] output bytes (container walk + assembler) [3..7] algorithmic bytes per codec class, [8] assembler (profiling only)
 constexpr int K1_WARPS = 8;
 constexpr int K1_SCAN_BLOCK = 1024;
 
@@ -81,7 +81,7 @@ cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end /*nullable*/
 cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                   const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
                                   ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer,
-                                  const SegState* seg, cudaStream_t st);
+                                  const SegState* seg, uint64_t* totals /* [FINAL_TOTALS] */, cudaStream_t st);
 // One codec class over ITS dense task list (pass 1: small streams by threads; pass 2: queued large streams, a warp each).
 // counters: 3 zeroed words (see covt_kernels.cu); big_queue: n_tasks words. seg != nullptr (batch path): the task count is
 // seg->seg_total[COL_CLASS0 + class], n_tasks only bounds the grids, and every stream's status is also written to
@@ -90,13 +90,13 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
                                 const SegState* seg, covt_layer* layers, int sm_count, int blocks_per_sm, cudaStream_t st);
 const char* op_class_name(int op_class);
 cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
-                                   uint32_t* work_counter, const SegState* seg, int sm_count, cudaStream_t st);
+                                   uint32_t* work_counter, const SegState* seg, uint64_t* totals /* [FINAL_TOTALS] */, int sm_count, cudaStream_t st);
 // k1a_aggregate + 3 segmented-scan kernels + k1b_decode; block_states needs ceil(n_chunks / K1_SCAN_BLOCK) entries
 cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks,
                                     ChunkState* states, ChunkState* block_states, cudaStream_t st);
-cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags,
-                            uint32_t* tile_status, uint64_t* totals /* [FINAL_TOTALS], see k_finalize */, const SegState* seg,
-                            cudaStream_t st);
+// per-tile status; with COVT_FLAG_PROFILE_KERNELS also the algorithmic bytes per kernel (totals[3 ..])
+cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t n_layers_bound, uint32_t flags,
+                            uint32_t* tile_status, uint64_t* totals /* [FINAL_TOTALS] */, const SegState* seg, cudaStream_t st);
 uint32_t host_resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags);
 int host_op_class_of(uint32_t op);  // OpClass of a covt_op, -1 for COVT_OP_NONE
 

@@ -10,7 +10,7 @@
 //   k_assemble_layers              : one warp per layer (CovtParser.convertGeometryColumn :135-274)
 //   k1a_aggregate / k1b_decode     : large varint streams of the stream API in 512-byte chunks over the whole GPU, with a
 //                                    segmented scan over (count, sumEven, sumOdd) in between (DecodingUtils.java:55-112,394-409)
-//   k_finalize                     : per-tile status + totals
+//   k_tile_status / k_alg_bytes    : per-tile status; algorithmic bytes per kernel (profiling only)
 #include "covt_assemble.cuh"
 #include "covt_internal.h"
 #include "covt_streams.cuh"
@@ -181,12 +181,14 @@ k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tile
 __global__ void __launch_bounds__(K0_BLOCK)
 k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols, ResultBuffers bufs, covt_layer* layers,
-               DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer, const SegState* seg)
+               DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer, const SegState* seg, uint64_t* totals)
 {
     __shared__ uint32_t s_lite[LITE_WORDS * K0_BLOCK];
     __shared__ uint64_t s_run[TILE_COLS * K0_BLOCK];
     const uint32_t t = blockIdx.x * K0_BLOCK + threadIdx.x;
-    if (t >= n_tiles || seg->overflow) return;
+    if (seg->overflow) return;
+    uint64_t payload_bytes = 0, stream_out_bytes = 0;  // -> totals[1], totals[2] (covt_timing)
+    if (t < n_tiles) {
     const Lite lite = {s_lite + threadIdx.x};
     uint64_t* run = s_run + threadIdx.x;
     // tile_cols holds exclusive prefixes inside this segment; seg->base = totals of the segments before it
@@ -232,6 +234,10 @@ k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_til
                     if (!layer_status) layer_status = COVT_ERR_UNSUPPORTED_ENCODING;
                 }
             }
+            if (have) {
+                payload_bytes += lite.bl(s);
+                stream_out_bytes += (s == COVT_SLOT_VBUF ? lite_vbuf_ints(lite, H.geom_ct, flags) : (uint64_t)lite.nv(s)) * kBufElemSizeDev(slot_buf(s));
+            }
             push((uint32_t)off);
             push((uint32_t)(off >> 32));
             push(have ? lite.bl(s) : 0u);
@@ -269,6 +275,16 @@ k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_til
         dst[1] = make_uint4(H.num_columns, layer_status, H.geom_ct | (num_bits << 8) | (lite.has(COVT_SLOT_ID) ? 1u << 16 : 0u), H.name_length);
         run[0] += 1;
     });
+    }
+    // payload / decoded-stream bytes of the batch: one pair of atomics per warp
+    for (int d = 16; d >= 1; d >>= 1) {
+        payload_bytes += __shfl_down_sync(FULL, payload_bytes, d);
+        stream_out_bytes += __shfl_down_sync(FULL, stream_out_bytes, d);
+    }
+    if ((threadIdx.x & 31u) == 0 && payload_bytes) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[1]), (unsigned long long)payload_bytes);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[2]), (unsigned long long)stream_out_bytes);
+    }
 }
 
 // =================================================================================================
@@ -345,12 +361,23 @@ constexpr int PFOR_BIG_WARP_SMEM = (404 + LEAN_STAGE_WORDS) * 4;  // pass 2: blo
 template <int CLASS> __host__ __device__ constexpr uint32_t class_group() { return (CLASS == CLASS_VARINT32 || CLASS == CLASS_PFOR) ? 1u : 32u; }
 template <int CLASS> __host__ __device__ constexpr int class_warp_smem() { return CLASS == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM; }
 
-__device__ __forceinline__ uint32_t warp_next_work(uint32_t* counter)
-{
-    uint32_t v = 0;
-    if (lane_id() == 0) v = atomicAdd(counter, 1u);
-    return __shfl_sync(FULL, v, 0);
-}
+// Work tickets. Every warp of a grid draws its items from ONE counter; at 2.4 M items per launch the same-address atomics alone are a
+// millisecond of serialised L2 time (one atomic unit per address), and each ticket is a ~300-cycle round trip at the head of the
+// warp's dependent chain (ticket -> task record -> stream bytes). So a warp takes TICKET_BATCH consecutive items per atomic.
+constexpr uint32_t TICKET_BATCH = 4;
+struct WarpTickets {
+    uint32_t next = 0, end = 0;
+    __device__ __forceinline__ uint32_t take(uint32_t* counter)
+    {
+        if (next == end) {  // warp-uniform
+            uint32_t v = 0;
+            if (lane_id() == 0) v = atomicAdd(counter, TICKET_BATCH);
+            next = __shfl_sync(FULL, v, 0);
+            end = next + TICKET_BATCH;
+        }
+        return next++;
+    }
+};
 
 template <int CLASS, bool BIG = false>
 __device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, StreamOutcome& o)
@@ -417,15 +444,22 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     uint8_t* wsm = smem + warp * class_warp_smem<CLASS>();
+    // batch path (layers != nullptr): a stream's outcome goes to its slot of the layer record, and only when it is NOT ok — the
+    // container walk initialised every status to COVT_OK, so the common case costs no scattered store at all.
+    // stream path: status and bytes consumed go back to the task, which the host reads.
     auto report = [&](uint32_t i, const DeviceTask& d, const StreamOutcome& o) {
-        tasks[i].status = o.status;
-        tasks[i].consumed = o.consumed;
-        if (layers) layers[d.ref / COVT_NUM_SLOTS].streams[d.ref % COVT_NUM_SLOTS].status = o.status;
+        if (layers) {
+            if (o.status != COVT_OK) layers[d.ref / COVT_NUM_SLOTS].streams[d.ref % COVT_NUM_SLOTS].status = o.status;
+        } else {
+            tasks[i].status = o.status;
+            tasks[i].consumed = o.consumed;
+        }
     };
     constexpr uint32_t GROUP = class_group<CLASS>();
     const uint32_t n_groups = (n_tasks + GROUP - 1u) / GROUP;
+    WarpTickets tickets;
     for (;;) {
-        const uint32_t g = warp_next_work(work_counter);
+        const uint32_t g = tickets.take(work_counter);
         if (g >= n_groups) break;
         const uint32_t mine = g * GROUP + lane;
         const bool have = lane < GROUP && mine < n_tasks;
@@ -483,7 +517,10 @@ k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counte
     const uint32_t n = *big_count;
     if (n == 0u) return;  // nothing queued (batches of small tiles): skip the 7 000 same-address ticket atomics of an idle grid
     for (;;) {
-        const uint32_t q = warp_next_work(work_counter);
+        // (one item per ticket here: the queued streams are few and large, balance matters more than the atomic)
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(work_counter, 1u);
+        q = __shfl_sync(FULL, q, 0);
         if (q >= n) break;
         const uint32_t i = big_queue[q];
         const DeviceTask dw = tasks[i];
@@ -492,9 +529,12 @@ k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counte
         decode_one<CLASS, true>(t, wsm, o);
         __syncwarp();
         if (lane == 0) {
-            tasks[i].status = o.status;
-            tasks[i].consumed = o.consumed;
-            if (layers) layers[dw.ref / COVT_NUM_SLOTS].streams[dw.ref % COVT_NUM_SLOTS].status = o.status;
+            if (layers) {
+                if (o.status != COVT_OK) layers[dw.ref / COVT_NUM_SLOTS].streams[dw.ref % COVT_NUM_SLOTS].status = o.status;
+            } else {
+                tasks[i].status = o.status;
+                tasks[i].consumed = o.consumed;
+            }
         }
     }
 }
@@ -504,15 +544,17 @@ k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counte
 // =================================================================================================
 template <int MINB>
 __global__ void __launch_bounds__(DEC_WARPS * 32, MINB)
-k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter, const SegState* seg)
+k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter, const SegState* seg, uint64_t* totals)
 {
     if (seg->overflow) return;
+    uint64_t sum_vertices = 0, sum_out_bytes = 0;  // lane 0: -> totals[0], totals[2]
     covt_layer* layers = all_layers + seg->seg_layer_base;
     const uint32_t n_layers = seg->seg_layers;
     __shared__ uint32_t s_asm[DEC_WARPS][ASM_SMEM_WORDS + 6];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    WarpTickets tickets;
     for (;;) {
-        const uint32_t l = warp_next_work(work_counter);
+        const uint32_t l = tickets.take(work_counter);
         if (l >= n_layers) break;
         covt_layer* L = &layers[l];
         uint32_t layer_status = L->status;
@@ -560,8 +602,15 @@ k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, ui
             L->n_rings = ar.n_rings;
             L->n_vertices = ar.n_vertices;
             L->n_coords = ar.n_coords;
+            sum_vertices += ar.n_vertices;
+            if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && layer_status == COVT_OK)
+                sum_out_bytes += 4ull * ((L->streams[COVT_SLOT_TYPES].num_values + 1ull) + (ar.n_parts + 1ull) + (ar.n_rings + 1ull)) + 8ull * ar.n_coords;
         }
         __syncwarp();
+    }
+    if (lane == 0 && (sum_vertices | sum_out_bytes)) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[0]), (unsigned long long)sum_vertices);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[2]), (unsigned long long)sum_out_bytes);
     }
 }
 
@@ -842,47 +891,49 @@ __global__ void k_seg_end(SegState* seg, uint32_t* first_layer_end)
     if (i == 0 && first_layer_end) *first_layer_end = (uint32_t)seg->base[0];
 }
 
-__global__ void k_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags, uint32_t* tile_status, uint64_t* totals,
-                           const SegState* seg)
+// tile status = first layer error, unless the container walk already failed
+__global__ void k_tile_status(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t* tile_status, const SegState* seg)
+{
+    if (seg->overflow) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint32_t st = tile_status[t];
+    if (st) return;
+    for (uint32_t l = first_layer[t]; l < first_layer[t + 1] && !st; l++) st = layers[l].status;
+    if (st) tile_status[t] = st;
+}
+
+// COVT_FLAG_PROFILE_KERNELS only: algorithmic bytes per kernel (payload read + decoded stream written, no padding, no
+// intermediates) -> totals[3 .. 7] per codec class, totals[8] assembler
+__global__ void k_alg_bytes(const covt_layer* layers, uint32_t n_layers_bound, uint32_t flags, uint64_t* totals, const SegState* seg)
 {
     if (seg->overflow) return;
     const uint8_t slot_es[COVT_NUM_SLOTS] = {8, 1, 4, 4, 4, 4, 4, 4};
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    // [0] vertices [1] payload bytes [2] output bytes [3..7] algorithmic bytes per codec class [8] assembler algorithmic bytes
-    uint64_t acc[FINAL_TOTALS];
-    for (int i = 0; i < FINAL_TOTALS; i++) acc[i] = 0;
-    if (t < n_tiles) {
-        uint32_t st = tile_status[t];
-        for (uint32_t l = first_layer[t]; l < first_layer[t + 1]; l++) {
-            const covt_layer& L = layers[l];
-            if (L.status && !st) st = L.status;
-            acc[0] += L.n_vertices;
-            // algorithmic bytes: payload read + decoded stream written, no padding, no intermediates
-            for (int s = 0; s < COVT_NUM_SLOTS; s++) {
-                if (L.streams[s].encoding == COVT_ENC_ABSENT) continue;
-                const uint64_t nv = s == COVT_SLOT_VBUF ? vbuf_ints_of(L, flags) : (uint64_t)L.streams[s].num_values;
-                const uint64_t ob = nv * slot_es[s];
-                acc[1] += L.streams[s].byte_length;
-                acc[2] += ob;
-                const int c = op_class_of(L.streams[s].op);
-                if (c >= 0) acc[3 + c] += L.streams[s].byte_length + ob;
-            }
-            if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && L.status == COVT_OK) {
-                const uint64_t F = slot_nv(L, COVT_SLOT_TYPES);
-                const uint64_t wr = 4ull * ((F + 1) + (L.n_parts + 1ull) + (L.n_rings + 1ull)) + 8ull * L.n_coords;
-                // reads: types, the three count streams, one offset per vertex for ICE layers, one (x,y) per output vertex
-                const uint64_t rd = F + 4ull * (slot_nv(L, COVT_SLOT_GEOM) + slot_nv(L, COVT_SLOT_PART) + slot_nv(L, COVT_SLOT_RING)) +
-                                    (L.streams[COVT_SLOT_VOFF].encoding != COVT_ENC_ABSENT ? 4ull * L.n_vertices : 0ull) + 8ull * L.n_coords;
-                acc[2] += wr;
-                acc[8] += wr + rd;
-            }
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_layers = (uint32_t)seg->base[0];
+    uint64_t acc[NUM_OP_CLASSES + 1];
+    for (int i = 0; i <= NUM_OP_CLASSES; i++) acc[i] = 0;
+    if (l < n_layers) {
+        const covt_layer& L = layers[l];
+        for (int s = 0; s < COVT_NUM_SLOTS; s++) {
+            if (L.streams[s].encoding == COVT_ENC_ABSENT) continue;
+            const uint64_t nv = s == COVT_SLOT_VBUF ? vbuf_ints_of(L, flags) : (uint64_t)L.streams[s].num_values;
+            const int c = op_class_of(L.streams[s].op);
+            if (c >= 0) acc[c] += L.streams[s].byte_length + nv * slot_es[s];
         }
-        tile_status[t] = st;
+        if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && L.status == COVT_OK) {
+            const uint64_t F = slot_nv(L, COVT_SLOT_TYPES);
+            const uint64_t wr = 4ull * ((F + 1) + (L.n_parts + 1ull) + (L.n_rings + 1ull)) + 8ull * L.n_coords;
+            // reads: types, the three count streams, one offset per vertex for ICE layers, one (x,y) per output vertex
+            const uint64_t rd = F + 4ull * (slot_nv(L, COVT_SLOT_GEOM) + slot_nv(L, COVT_SLOT_PART) + slot_nv(L, COVT_SLOT_RING)) +
+                                (L.streams[COVT_SLOT_VOFF].encoding != COVT_ENC_ABSENT ? 4ull * L.n_vertices : 0ull) + 8ull * L.n_coords;
+            acc[NUM_OP_CLASSES] += wr + rd;
+        }
     }
-    for (int i = 0; i < FINAL_TOTALS; i++) {
+    for (int i = 0; i <= NUM_OP_CLASSES; i++) {
         uint64_t v = acc[i];
         for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(FULL, v, d);
-        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(reinterpret_cast<unsigned long long*>(&totals[i]), (unsigned long long)v);
+        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(reinterpret_cast<unsigned long long*>(&totals[3 + i]), (unsigned long long)v);
     }
 }
 
@@ -894,7 +945,7 @@ cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offse
                                  uint32_t* tile_status, cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    k0_scan_tiles<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, tile_base, container, tj_fields, tj_layers, flags, tile_cols, tile_status);
+    k0_scan_tiles<<<(n_tiles + K0_BLOCK - 1) / K0_BLOCK, K0_BLOCK, 0, st>>>(blob, tile_offsets, n_tiles, tile_base, container, tj_fields, tj_layers, flags, tile_cols, tile_status);
     return cudaGetLastError();
 }
 
@@ -911,10 +962,10 @@ cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_
 cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                   const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols,
                                   ResultBuffers bufs, covt_layer* layers, DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer,
-                                  const SegState* seg, cudaStream_t st)
+                                  const SegState* seg, uint64_t* totals, cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    k0_fill_layers<<<(n_tiles + 127) / 128, 128, 0, st>>>(blob, tile_offsets, n_tiles, tile_base, container, tj_fields, tj_layers, flags, tile_cols, bufs, layers, tasks, class_off, first_layer, seg);
+    k0_fill_layers<<<(n_tiles + K0_BLOCK - 1) / K0_BLOCK, K0_BLOCK, 0, st>>>(blob, tile_offsets, n_tiles, tile_base, container, tj_fields, tj_layers, flags, tile_cols, bufs, layers, tasks, class_off, first_layer, seg, totals);
     return cudaGetLastError();
 }
 
@@ -986,11 +1037,11 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
 
 // n_layers_bound: upper bound of the segment's layer count (grid size only)
 cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
-                                   uint32_t* work_counter, const SegState* seg, int sm_count, cudaStream_t st)
+                                   uint32_t* work_counter, const SegState* seg, uint64_t* totals, int sm_count, cudaStream_t st)
 {
     if (!n_layers_bound) return cudaSuccess;
     // 32 registers, 16 blocks = 64 warps per SM: the assembler waits on dependent loads (profiles/r01_experiments.md)
-    k_assemble_layers<16><<<grid_for(sm_count, 16, n_layers_bound, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg);
+    k_assemble_layers<16><<<grid_for(sm_count, 16, n_layers_bound, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg, totals);
     return cudaGetLastError();
 }
 
@@ -1008,11 +1059,12 @@ cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* stream
     return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t flags,
+cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t n_layers_bound, uint32_t flags,
                             uint32_t* tile_status, uint64_t* totals, const SegState* seg, cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    k_finalize<<<(n_tiles + 127) / 128, 128, 0, st>>>(layers, first_layer, n_tiles, flags, tile_status, totals, seg);
+    k_tile_status<<<(n_tiles + 255) / 256, 256, 0, st>>>(layers, first_layer, n_tiles, tile_status, seg);
+    if ((flags & COVT_FLAG_PROFILE_KERNELS) && n_layers_bound) k_alg_bytes<<<(n_layers_bound + 255) / 256, 256, 0, st>>>(layers, n_layers_bound, flags, totals, seg);
     return cudaGetLastError();
 }
 

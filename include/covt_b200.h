@@ -273,7 +273,11 @@ typedef struct covt_result covt_result;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
 int32_t covt_abi_version(void);
-/* One context per GPU (one process per GPU; several contexts may coexist). device = CUDA ordinal. */
+/* One context per GPU; several contexts (on the same or on different GPUs) may coexist in one process. device = CUDA ordinal.
+ * THREADING: a context, its batches and its results must be used by ONE thread at a time (no internal locking: the pinned scratch,
+ * the device block cache and the error string are per context). Different contexts may be used from different threads at the same
+ * time — that is how covt_decode_batch_multi drives several GPUs — so a multi-threaded caller (e.g. a JVM thread pool) creates
+ * one context per thread. */
 int32_t covt_create(int32_t device, covt_ctx** out);
 void    covt_destroy(covt_ctx* ctx);
 /* Copies the last error message of this context (or of a failed covt_create when ctx == NULL). */
@@ -328,6 +332,34 @@ int32_t covt_host_unregister(covt_ctx* ctx, void* ptr);
 /* Splits tiles [0,n_tiles) into n_parts contiguous ranges balanced by payload bytes
  * (prefix sum over tile_offsets). starts has n_parts+1 entries. No collective: tiles share nothing. */
 int32_t covt_partition_tiles(const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t n_parts, uint32_t* starts);
+
+/* ---- multi-GPU batch scheduler: one call, N GPUs of one box ------------------------------------------ */
+/* Replaces the same single entry point (CovtParser.decodeCovt, CovtParser.java:53) for a caller that owns several GPUs from
+ * one process (a single JVM): the batch is cut into contiguous tile ranges balanced by payload bytes (covt_partition_tiles),
+ * range g is uploaded and decoded by GPU g on the scheduler's own host thread with that GPU's own context, streams and result
+ * arena. No collective and no peer traffic: tiles share nothing. Results stay resident on the GPU that decoded them; the
+ * result handle exposes one covt_result per GPU. A covt_multi handle serves one call at a time. */
+typedef struct covt_multi covt_multi;
+typedef struct covt_multi_result covt_multi_result;
+/* device_count == 0: every visible GPU. device_ids == NULL: ordinals 0 .. device_count-1. */
+int32_t covt_create_multi(uint32_t device_count, const int32_t* device_ids, covt_multi** out);
+void    covt_destroy_multi(covt_multi* m);
+int32_t covt_multi_last_error(covt_multi* m, char* buf, size_t buf_len);
+uint32_t covt_multi_device_count(const covt_multi* m);
+/* The single-GPU context of part `part` (owned by the scheduler), e.g. for covt_host_register / covt_trim. */
+int32_t covt_multi_context(covt_multi* m, uint32_t part, covt_ctx** ctx, int32_t* device);
+int32_t covt_decode_batch_multi(covt_multi* m, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles,
+                                uint32_t container, const covt_tilejson* tilejson, uint32_t flags, covt_multi_result** out);
+uint32_t covt_multi_result_parts(const covt_multi_result* res);
+/* Part `part` = tiles [first_tile, first_tile + n_tiles) of the batch, decoded on `device`. Tile indices inside the part's
+ * covt_result (covt_layer.tile, the status arrays) are relative to first_tile. The covt_result stays owned by the multi result. */
+int32_t covt_multi_result_part(const covt_multi_result* res, uint32_t part, covt_result** part_result, uint32_t* first_tile,
+                               uint32_t* n_tiles, int32_t* device);
+/* Times: maximum over the GPUs (they run side by side); counters: sums. */
+int32_t covt_multi_result_timing(const covt_multi_result* res, covt_timing* out);
+/* Device->host copy of buffer `which` of every part at once (one copy thread per GPU): part p -> host_dst[p]. */
+int32_t covt_multi_result_read(covt_multi_result* res, uint32_t which, void* const* host_dst);
+void    covt_multi_result_free(covt_multi_result* res);
 
 #ifdef __cplusplus
 }

@@ -416,3 +416,81 @@ def test_config2_rle_topology_variant(covt, oracle, gen, decoder, fixtures):
         util.compare_results_bulk(abi, res, res0, chunk_layers=4096, same_container=False)
         res.free()
         res0.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("two_gpus", [False, True])
+def test_multi_gpu_scheduler_one_call(covt, oracle, gen, fixtures, two_gpus):
+    """covt_decode_batch_multi: ONE call, the library cuts the batch into contiguous tile ranges balanced by payload bytes and
+    decodes them side by side, one context + host thread per part. two_gpus=False: three contexts on GPU 0 (what a 1-GPU box
+    can run); True: contexts on GPUs 0 and 1 in ONE process (skipped below 2 GPUs). Every part equals the oracle's decode of
+    the same tile range, the parts cover the batch exactly, and a concurrent device->host read-back of a buffer works."""
+    import torch
+    abi = covt.abi
+    if two_gpus and torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ids = [0, 1] if two_gpus else [0, 0, 0]
+    md = covt.MultiDecoder(ids)
+    try:
+        assert md.n_devices == len(ids)
+        small, soffs, truth = gen.tiles(123, 2500, gen.default_params())
+        big = [b for n, b in fixtures if n.startswith(("omt/5_", "omt/9_"))]
+        tiles = [bytes(small[int(soffs[i]):int(soffs[i + 1])]) for i in range(2500)] + big
+        blob, offs = util.concat_tiles(tiles)
+        flags = abi.FLAG_DEFAULT | abi.FLAG_ID_DVZZ_IS_RLE
+        for rep in range(2):  # the second call reuses every context's parked blocks
+            mr = md.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags)
+            assert len(mr.parts) == len(ids)
+            starts = covt.partition_tiles(offs, len(ids))
+            nxt = 0
+            verts = 0
+            for k, part in enumerate(mr.parts):
+                assert part["first_tile"] == nxt == int(starts[k]) and part["device"] == ids[k]
+                t0, n = part["first_tile"], part["n_tiles"]
+                nxt = t0 + n
+                b0 = int(offs[t0])
+                ref = oracle.decode_batch(blob[b0:int(offs[t0 + n])], offs[t0:t0 + n + 1] - np.uint64(b0), abi.CONTAINER_GEN2B, flags)
+                res = part["result"]
+                st, first = res.tile_status()
+                assert np.array_equal(first, ref.first_layer) and np.array_equal(st == 0, ref.tile_status == 0)
+                util.compare_results(abi, res, ref)
+                verts += int(res.layers["n_vertices"].sum())
+            assert nxt == len(tiles)
+            t = mr.timing()
+            assert t["vertices"] == verts and t["payload_bytes"] > 0 and t["decode_ms"] > 0
+            # all parts' coordinates back to the host at once
+            counts = [p["result"].device_buffer(abi.BUF_A_COORDS)[1] for p in mr.parts]
+            hosts = [np.empty(max(c, 1), np.int32) for c in counts]
+            mr.read_into(abi.BUF_A_COORDS, [h.ctypes.data for h in hosts])
+            for p, h, c in zip(mr.parts, hosts, counts):
+                assert np.array_equal(h[:c], p["result"].buffer(abi.BUF_A_COORDS))
+            mr.free()
+    finally:
+        md.close()
+
+
+@pytest.mark.gpu
+def test_one_context_per_thread(covt, oracle, gen):
+    """The threading contract of include/covt_b200.h: a context serves one thread at a time, different contexts run concurrently."""
+    import threading
+    abi = covt.abi
+    blob, offs, truth = gen.tiles(500, 1200, gen.default_params())
+    ref = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT)
+    errors = []
+
+    def work(k):
+        try:
+            dec = covt.Decoder(0)
+            for _ in range(3):
+                res = dec.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_DEFAULT)
+                util.compare_results(abi, res, ref)
+                res.free()
+            dec.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
