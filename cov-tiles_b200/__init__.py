@@ -45,6 +45,7 @@ ABI_SYMBOLS = [
     "covt_batch_decode", "covt_batch_free", "covt_decode_streams", "covt_batch_decode_streams", "covt_resolve_op",
     "covt_result_num_tiles", "covt_result_num_layers", "covt_result_layers", "covt_result_tile_status",
     "covt_result_buffer", "covt_result_read", "covt_result_timing", "covt_result_kernel_times", "covt_result_free",
+    "covt_result_prop_columns", "covt_result_prop_dictionaries", "covt_result_prop_buffer", "covt_result_prop_read",
     "covt_host_register", "covt_host_unregister", "covt_partition_tiles",
     "covt_create_multi", "covt_destroy_multi", "covt_multi_last_error", "covt_multi_device_count", "covt_multi_context",
     "covt_decode_batch_multi", "covt_multi_result_parts", "covt_multi_result_part", "covt_multi_result_timing",
@@ -83,6 +84,10 @@ def lib():
     L.covt_result_tile_status.argtypes = [vp, C.POINTER(C.POINTER(u32)), C.POINTER(C.POINTER(u32))]
     L.covt_result_buffer.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)]
     L.covt_result_read.argtypes = [vp, u32, u64, u64, vp]
+    L.covt_result_prop_columns.argtypes = [vp, C.POINTER(C.POINTER(abi.PropColumn)), C.POINTER(u32)]
+    L.covt_result_prop_dictionaries.argtypes = [vp, C.POINTER(C.POINTER(abi.PropDictionary)), C.POINTER(u32)]
+    L.covt_result_prop_buffer.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)]
+    L.covt_result_prop_read.argtypes = [vp, u32, u64, u64, vp]
     L.covt_result_timing.argtypes = [vp, C.POINTER(abi.Timing)]
     L.covt_result_kernel_times.argtypes = [vp, C.POINTER(abi.KernelTime), u32, C.POINTER(u32)]
     L.covt_result_free.argtypes = [vp]
@@ -200,6 +205,37 @@ class Result:
 
     def read_into(self, which, offset, count, host_ptr):
         self._dec._check(lib().covt_result_read(self._h, which, offset, count, host_ptr))
+
+    # ---- property columns (FLAG_DECODE_PROPERTIES) ----
+    def prop_columns(self):
+        """numpy structured array of covt_prop_column (one record per decoded property column / localized sub-column)."""
+        p, n = C.POINTER(abi.PropColumn)(), C.c_uint32()
+        self._dec._check(lib().covt_result_prop_columns(self._h, C.byref(p), C.byref(n)))
+        if not n.value:
+            return np.zeros(0, dtype=abi.PROP_COLUMN_DTYPE)
+        return np.frombuffer(C.string_at(p, n.value * C.sizeof(abi.PropColumn)), dtype=abi.PROP_COLUMN_DTYPE).copy()
+
+    def prop_dictionaries(self):
+        p, n = C.POINTER(abi.PropDictionary)(), C.c_uint32()
+        self._dec._check(lib().covt_result_prop_dictionaries(self._h, C.byref(p), C.byref(n)))
+        if not n.value:
+            return np.zeros(0, dtype=abi.PROP_DICTIONARY_DTYPE)
+        return np.frombuffer(C.string_at(p, n.value * C.sizeof(abi.PropDictionary)), dtype=abi.PROP_DICTIONARY_DTYPE).copy()
+
+    def prop_device_buffer(self, which):
+        p, n, es = C.c_void_p(), C.c_uint64(), C.c_uint32()
+        self._dec._check(lib().covt_result_prop_buffer(self._h, which, C.byref(p), C.byref(n), C.byref(es)))
+        return p.value or 0, n.value, es.value
+
+    def prop_buffer(self, which, offset=0, count=None):
+        """Host copy (numpy) of a property value buffer (abi.PBUF_*) or a slice of it."""
+        _, n, _ = self.prop_device_buffer(which)
+        if count is None:
+            count = n - offset
+        out = np.empty(count, dtype=abi.PBUF_DTYPES[which])
+        if count:
+            self._dec._check(lib().covt_result_prop_read(self._h, which, offset, count, out.ctypes.data))
+        return out
 
     def timing(self):
         t = abi.Timing()

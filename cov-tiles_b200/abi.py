@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # covt_stream_encoding
 ENC_PLAIN, ENC_VARINT, ENC_VARINT_ZIG_ZAG, ENC_VARINT_DELTA, ENC_VARINT_DELTA_ZIG_ZAG = 0, 1, 2, 3, 4
@@ -37,6 +37,7 @@ FLAG_ID_WIDTH_32 = 0x0008
 FLAG_ICE_VB_COUNT_IS_INTS = 0x0010
 FLAG_SKIP_ASSEMBLY = 0x0020
 FLAG_PROFILE_KERNELS = 0x0040
+FLAG_DECODE_PROPERTIES = 0x0080
 FLAG_DEFAULT = FLAG_CLOSE_RINGS
 # slots
 (SLOT_ID, SLOT_TYPES, SLOT_GEOM, SLOT_PART, SLOT_RING, SLOT_VOFF, SLOT_VBUF, SLOT_INDEX) = range(8)
@@ -58,17 +59,17 @@ SLOT_BUF = [BUF_S_IDS, BUF_S_GEOMETRY_TYPES, BUF_S_GEOMETRY_OFFSETS, BUF_S_PART_
 # ops
 (OP_NONE, OP_BYTE_RLE, OP_RLE_U32, OP_RLE_U64, OP_RLE_S64, OP_VARINT_U32, OP_VARINT_ZZ, OP_VARINT_ZZ_DELTA,
  OP_VARINT_ZZ_DELTA_XY, OP_VARINT_DELTA_MORTON, OP_VARINT_U64, OP_VARINT_ZZ_DELTA_64, OP_PFOR_ZZ_DELTA,
- OP_PFOR_ZZ_DELTA_XY, OP_PFOR_DELTA_MORTON, OP_VARINT_U32_AS_I64, OP_VARINT_ZZ_DELTA_AS_I64) = range(17)
+ OP_PFOR_ZZ_DELTA_XY, OP_PFOR_DELTA_MORTON, OP_VARINT_U32_AS_I64, OP_VARINT_ZZ_DELTA_AS_I64, OP_VARINT_ZZ_AS_I64) = range(18)
 OP_NAMES = ["none", "byte_rle", "rle_u32", "rle_u64", "rle_s64", "varint_u32", "varint_zz", "varint_zz_delta",
             "varint_zz_delta_xy", "varint_delta_morton", "varint_u64", "varint_zz_delta_64", "pfor_zz_delta",
-            "pfor_zz_delta_xy", "pfor_delta_morton", "varint_u32_as_i64", "varint_zz_delta_as_i64"]
+            "pfor_zz_delta_xy", "pfor_delta_morton", "varint_u32_as_i64", "varint_zz_delta_as_i64", "varint_zz_as_i64"]
 
 
 def op_elem_size(op):
     if op == OP_BYTE_RLE:
         return 1
     if op in (OP_RLE_U64, OP_RLE_S64, OP_VARINT_U64, OP_VARINT_ZZ_DELTA_64, OP_VARINT_U32_AS_I64,
-              OP_VARINT_ZZ_DELTA_AS_I64):
+              OP_VARINT_ZZ_DELTA_AS_I64, OP_VARINT_ZZ_AS_I64):
         return 8
     return 4
 
@@ -114,6 +115,63 @@ class Timing(C.Structure):
 class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("launches", C.c_uint32),
                 ("algorithmic_bytes", C.c_uint64)]
+
+
+# property columns (COVT_FLAG_DECODE_PROPERTIES)
+PV_NONE, PV_I64, PV_F32, PV_F64, PV_BOOL, PV_DICT_INDEX = range(6)
+(PBUF_VALIDITY, PBUF_I64, PBUF_F32, PBUF_F64, PBUF_BOOL, PBUF_DICT_INDEX, PBUF_DICT_OFFSETS) = range(7)
+NUM_PROP_BUFFERS = 7
+PBUF_DTYPES = [np.uint8, np.int64, np.float32, np.float64, np.uint8, np.int32, np.int32]
+
+
+class PropColumn(C.Structure):
+    _fields_ = [("tile", C.c_uint32), ("layer", C.c_uint32), ("name_offset", C.c_uint64), ("sub_offset", C.c_uint64),
+                ("name_length", C.c_uint32), ("sub_length", C.c_uint32), ("data_type", C.c_uint8), ("column_type", C.c_uint8),
+                ("value_kind", C.c_uint8), ("reserved", C.c_uint8), ("status", C.c_uint32), ("num_features", C.c_uint32),
+                ("num_values", C.c_uint32), ("validity_offset", C.c_uint64), ("values_offset", C.c_uint64),
+                ("dictionary", C.c_uint32), ("data_num_values", C.c_uint32)]
+
+
+class PropDictionary(C.Structure):
+    _fields_ = [("tile", C.c_uint32), ("layer", C.c_uint32), ("n_entries", C.c_uint32), ("status", C.c_uint32),
+                ("offsets_offset", C.c_uint64), ("bytes_offset", C.c_uint64), ("n_bytes", C.c_uint64)]
+
+
+PROP_COLUMN_DTYPE = np.dtype(PropColumn)
+PROP_DICTIONARY_DTYPE = np.dtype(PropDictionary)
+assert C.sizeof(PropColumn) == 72 and C.sizeof(PropDictionary) == 40, (C.sizeof(PropColumn), C.sizeof(PropDictionary))
+
+
+def prop_column_values(blob, c, validity, values, dict_offsets, dictionaries):
+    """List<Optional> view of one decoded property column (what CovtParser.decodePropertyColumn returns, CovtParser.java:276-377):
+    the value or None per feature. c: a PropColumn record (or a row of PROP_COLUMN_DTYPE); validity / values: the column's buffers
+    (values = the buffer of c's value_kind); dictionaries: the PropDictionary records. Host-side convenience for tests and callers."""
+    F = int(c["num_features"])
+    vo = int(c["validity_offset"])
+    valid = np.unpackbits(validity[vo:vo + (F + 7) // 8], bitorder="little")[:F].astype(bool)
+    n = int(c["num_values"])
+    o = int(c["values_offset"])
+    kind = int(c["value_kind"])
+    if kind == PV_BOOL:
+        dense = [bool(b) for b in np.unpackbits(values[o:o + (n + 7) // 8], bitorder="little")[:n]]
+    elif kind == PV_I64:
+        dense = [int(x) for x in values[o:o + n]]
+    elif kind in (PV_F32, PV_F64):
+        dense = [float(x) for x in values[o:o + n]]
+    elif kind == PV_DICT_INDEX:
+        d = dictionaries[int(c["dictionary"])]
+        oo, ne, bo, nb = int(d["offsets_offset"]), int(d["n_entries"]), int(d["bytes_offset"]), int(d["n_bytes"])
+        off = dict_offsets[oo:oo + ne + 1].astype(np.int64)
+        raw = bytes(blob[bo:bo + nb])
+        words = [raw[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(ne)]
+        dense = [words[i] for i in values[o:o + n]]
+    else:
+        dense = []
+    out = [None] * F
+    it = iter(dense)
+    for i in np.nonzero(valid)[0]:
+        out[i] = next(it)
+    return out
 
 
 LAYER_DTYPE = np.dtype(Layer)

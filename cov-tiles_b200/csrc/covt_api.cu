@@ -76,6 +76,15 @@ struct covt_result {
     covt_layer* h_layers = nullptr;      // pinned, lazily fetched
     uint32_t* h_tile_status = nullptr;   // pinned, lazily fetched
     uint32_t* h_first_layer = nullptr;
+    // property columns (COVT_FLAG_DECODE_PROPERTIES)
+    uint32_t n_prop_cols = 0, n_prop_dicts = 0;
+    covt_prop_column* d_prop_cols = nullptr;
+    covt_prop_dictionary* d_prop_dicts = nullptr;
+    void* prop_arena = nullptr;
+    void* pbufs[COVT_NUM_PROP_BUFFERS] = {};
+    uint64_t pcounts[COVT_NUM_PROP_BUFFERS] = {};
+    covt_prop_column* h_prop_cols = nullptr;       // pinned, lazily fetched
+    covt_prop_dictionary* h_prop_dicts = nullptr;
     covt_timing timing = {};
     std::vector<covt_kernel_time> kernel_times;
 };
@@ -232,6 +241,19 @@ struct Profiler {
 };
 
 }  // namespace
+
+// host copy of a record table of the result (pinned, fetched on first use)
+template <class T>
+static int32_t fetch_records(covt_result* res, T** host, const T* dev, uint64_t n)
+{
+    covt_ctx* ctx = res->ctx;
+    if (*host) return COVT_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(pinned_take(ctx, reinterpret_cast<void**>(host), std::max<uint64_t>(n, 1) * sizeof(T)));
+    if (n) CK(cudaMemcpyAsync(*host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return COVT_OK;
+}
 
 extern "C" {
 
@@ -396,6 +418,113 @@ void covt_batch_free(covt_batch* b)
 // ------------------------------------------------------------------------------------------------
 // decode of a batch resident in (or on its way to) HBM, one or more segments of tiles
 // ------------------------------------------------------------------------------------------------
+// Property columns of a batch that is resident in HBM (COVT_FLAG_DECODE_PROPERTIES): CovtParser.decodePropertyColumn
+// (CovtParser.java:276-390) for every property column of every tile, after the geometry path of the batch (kernels: covt_props.cuh).
+// One pass over all tiles: count -> scan -> ONE size read-back -> records + tasks -> the codec-class kernels -> finish.
+static int32_t decode_properties(covt_ctx* ctx, covt_batch* batch, uint32_t container, const covt_tilejson* tilejson, uint32_t flags, covt_result* R)
+{
+    const uint32_t n_tiles = batch->n_tiles;
+    cudaStream_t st = ctx->stream;
+    Profiler prof = {ctx, (flags & COVT_FLAG_PROFILE_KERNELS) != 0, {}};
+    uint64_t *d_pcols = nullptr, *d_block_sums = nullptr, *d_totals = nullptr;
+    uint32_t *d_tj = nullptr, *d_counter = nullptr, *d_aux = nullptr, *d_queue = nullptr;
+    DeviceTask* d_tasks = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int32_t rc = COVT_OK;
+    auto cleanup = [&]() {
+        dev_free(ctx, d_pcols); dev_free(ctx, d_block_sums); dev_free(ctx, d_totals); dev_free(ctx, d_tj); dev_free(ctx, d_counter);
+        dev_free(ctx, d_aux); dev_free(ctx, d_queue); dev_free(ctx, d_tasks);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    };
+#define CKP(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char m_[512];                                                                             \
+            snprintf(m_, sizeof(m_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = m_;                                                                            \
+            rc = e_ == cudaErrorMemoryAllocation ? COVT_ERR_OOM : COVT_ERR_CUDA;                      \
+            cudaStreamSynchronize(st);                                                                \
+            cleanup();                                                                                \
+            return rc;                                                                                \
+        }                                                                                             \
+    } while (0)
+    const uint32_t nb = (n_tiles + 255) / 256;
+    CKP(cudaEventCreate(&ev0));
+    CKP(cudaEventCreate(&ev1));
+    CKP(dev_alloc(ctx, &d_pcols, (uint64_t)PROP_COLS * n_tiles));
+    CKP(dev_alloc(ctx, &d_block_sums, (uint64_t)PROP_COLS * nb));
+    CKP(dev_alloc(ctx, &d_totals, PROP_COLS));
+    CKP(dev_alloc(ctx, &d_counter, 16));
+    uint32_t tj_layers = 0;
+    if (tilejson && tilejson->n_vector_layers && tilejson->n_fields) {
+        tj_layers = tilejson->n_vector_layers;
+        CKP(dev_alloc(ctx, &d_tj, tj_layers));
+        CKP(cudaMemcpyAsync(d_tj, tilejson->n_fields, tj_layers * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    CKP(cudaMemsetAsync(d_counter, 0, 16 * sizeof(uint32_t), st));
+    CKP(cudaEventRecord(ev0, st));
+    PropOut po = {};
+    prof.begin("k0_props_scan", 0);
+    CKP(launch_k0_props(false, batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, d_pcols, po, st));
+    CKP(launch_scan_tile_cols(d_pcols, n_tiles, d_block_sums, d_totals, st, PROP_COLS));
+    prof.end();
+    uint64_t* h = ctx->h_totals;  // pinned scratch (64 words)
+    CKP(cudaMemcpyAsync(h, d_totals, PROP_COLS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CKP(cudaStreamSynchronize(st));
+    const uint64_t n_cols = h[PROP_COL_COLUMNS], n_dicts = h[PROP_COL_DICTS];
+    uint64_t n_tasks = 0, class_n[NUM_OP_CLASSES];
+    for (int c = 0; c < NUM_OP_CLASSES; c++) { class_n[c] = h[PROP_COL_CLASS0 + c]; po.class_off[c] = n_tasks; n_tasks += class_n[c]; }
+    if (n_cols * PROP_AUX_WORDS + n_dicts > 0xffffff00ull || n_tasks > 0xffffff00ull) { cleanup(); return fail(ctx, COVT_ERR_INVALID_ARG, "too many property columns in one batch"); }
+    uint64_t arena_bytes = 0, buf_off[COVT_NUM_PROP_BUFFERS];
+    for (int b = 0; b < COVT_NUM_PROP_BUFFERS; b++) {
+        R->pcounts[b] = h[PROP_COL_BUF0 + b];
+        buf_off[b] = arena_bytes;
+        arena_bytes += (R->pcounts[b] * kPropBufElemSizeHost[b] + 64 + 255) & ~255ull;
+    }
+    R->n_prop_cols = (uint32_t)n_cols;
+    R->n_prop_dicts = (uint32_t)n_dicts;
+    CKP(dev_alloc_bytes(ctx, &R->prop_arena, arena_bytes + 256));
+    for (int b = 0; b < COVT_NUM_PROP_BUFFERS; b++) {
+        R->pbufs[b] = static_cast<uint8_t*>(R->prop_arena) + buf_off[b];
+        po.buf[b] = R->pbufs[b];
+    }
+    CKP(dev_alloc(ctx, &R->d_prop_cols, n_cols));
+    CKP(dev_alloc(ctx, &R->d_prop_dicts, n_dicts));
+    CKP(dev_alloc(ctx, &d_aux, n_cols * PROP_AUX_WORDS + n_dicts));
+    CKP(dev_alloc(ctx, &d_tasks, n_tasks));
+    CKP(dev_alloc(ctx, &d_queue, n_tasks));
+    po.cols = R->d_prop_cols;
+    po.dicts = R->d_prop_dicts;
+    po.aux = d_aux;
+    po.aux_dict_base = n_cols * PROP_AUX_WORDS;
+    po.tasks = d_tasks;
+    prof.begin("k0_props_fill", 0);
+    CKP(launch_k0_props(true, batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, d_pcols, po, st));
+    prof.end();
+    for (int c = 0; c < NUM_OP_CLASSES; c++) {
+        if (!class_n[c]) continue;
+        prof.begin((std::string(op_class_name(c)) + "_props").c_str(), 0);
+        CKP(launch_decode_class(c, batch->d_blob, d_tasks + po.class_off[c], (uint32_t)class_n[c], d_counter + 3 * c, d_queue + po.class_off[c], nullptr, d_aux,
+                                ctx->sm_count, 0, st));
+        prof.end();
+    }
+    prof.begin("k_prop_finish", 0);
+    CKP(launch_prop_finish(batch->d_blob, (uint32_t)n_cols, (uint32_t)n_dicts, po, st));
+    prof.end();
+    CKP(cudaEventRecord(ev1, st));
+    CKP(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    R->timing.decode_ms += ms;
+    R->timing.kernel_launches += 7 + 2 * NUM_OP_CLASSES;
+    prof.collect(R->kernel_times);
+    cleanup();
+#undef CKP
+    return COVT_OK;
+}
+
 // seg_starts: S+1 tile indices, every segment non-empty. uploaded: nullptr (the whole blob is resident) or one event per
 // segment, recorded on the copy stream after that segment's bytes and tile offsets arrived.
 // With S > 1 the capacities of the result buffers are extrapolated from segment 0 (bytes ratio + 10 %); if a later segment
@@ -416,7 +545,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     uint64_t *d_cols = nullptr, *d_block_sums = nullptr, *d_totals = nullptr;
-    uint32_t *d_tj = nullptr, *d_counter = nullptr;
+    uint32_t *d_tj = nullptr, *d_counter = nullptr, *d_tile_err = nullptr;
     SegState* d_seg = nullptr;
     DeviceTask* d_tasks = nullptr;
     uint32_t* d_queue = nullptr;  // large streams handed from pass 1 to pass 2 of a codec class (same layout as d_tasks)
@@ -430,6 +559,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         dev_free(ctx, d_totals);
         dev_free(ctx, d_tj);
         dev_free(ctx, d_counter);
+        dev_free(ctx, d_tile_err);
         dev_free(ctx, d_tasks);
         dev_free(ctx, d_queue);
         dev_free(ctx, d_seg);
@@ -460,6 +590,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
     CKR(dev_alloc(ctx, &d_seg, 1));
     CKR(dev_alloc(ctx, &R->d_tile_status, (uint64_t)n_tiles + 1));
     CKR(dev_alloc(ctx, &R->d_first_layer, (uint64_t)n_tiles + 2));
+    CKR(dev_alloc(ctx, &d_tile_err, (uint64_t)n_tiles + 1));
     uint32_t tj_layers = 0;
     if (tilejson && tilejson->n_vector_layers && tilejson->n_fields) {
         tj_layers = tilejson->n_vector_layers;
@@ -470,6 +601,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
     CKR(cudaMemsetAsync(d_counter, 0, 16 * sizeof(uint32_t), st));
     CKR(cudaMemsetAsync(d_seg, 0, sizeof(SegState), st));
     CKR(cudaMemsetAsync(R->d_first_layer, 0, ((uint64_t)n_tiles + 2) * sizeof(uint32_t), st));
+    CKR(cudaMemsetAsync(d_tile_err, 0xff, ((uint64_t)n_tiles + 1) * sizeof(uint32_t), st));
 
     CKR(cudaEventRecord(ev0, st));
     uint32_t launches = 0;
@@ -501,7 +633,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             }
             for (int c = 0; c < COL_CLASS0; c++)
                 hs->cap[c] = S > 1 ? (uint64_t)((double)ctx->h_totals[c] * scale) + 65536 : ctx->h_totals[c];
-            if (hs->cap[0] > 0x1ffffff0ull)  // DeviceTask::ref = layer * 8 + slot must fit 32 bits
+            if (hs->cap[0] > 0xffffffffull / (sizeof(covt_layer) / 4) - 1)  // DeviceTask::ref = word index into the layer table must fit 32 bits
                 { cleanup_tmp(); covt_result_free(R); return fail(ctx, COVT_ERR_INVALID_ARG, "too many layers in one batch"); }
             // the task lists are per segment: a segment that needs more entries than extrapolated counts as an overflow too
             const double seg_scale = S > 1 ? (double)max_seg_tiles / nt * 1.25 : 1.0;
@@ -541,7 +673,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             for (int c = 0; c < NUM_OP_CLASSES; c++) {
                 prof.begin(op_class_name(c), 0);
                 CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_off.off[c], (uint32_t)std::min<uint64_t>(task_cap[c], 0xffffff00ull), d_counter + 3 * c,
-                                        d_queue + class_off.off[c], d_seg, R->d_layers, ctx->sm_count, 0, st));
+                                        d_queue + class_off.off[c], d_seg, reinterpret_cast<uint32_t*>(R->d_layers), ctx->sm_count, 0, st));
                 prof.end();
             }
         } else {
@@ -554,21 +686,21 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
                 const int c = order[i];
                 CKR(cudaStreamWaitEvent(ctx->class_stream[c], ctx->ev_fork, 0));
                 CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_off.off[c], (uint32_t)std::min<uint64_t>(task_cap[c], 0xffffff00ull), d_counter + 3 * c,
-                                        d_queue + class_off.off[c], d_seg, R->d_layers, ctx->sm_count, share[c], ctx->class_stream[c]));
+                                        d_queue + class_off.off[c], d_seg, reinterpret_cast<uint32_t*>(R->d_layers), ctx->sm_count, share[c], ctx->class_stream[c]));
                 CKR(cudaEventRecord(ctx->ev_join[c], ctx->class_stream[c]));
                 CKR(cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
             }
         }
         // ---- geometry assembly ----
         prof.begin("k_assemble_layers", 0);
-        CKR(launch_assemble_layers(R->d_layers, (uint32_t)std::min<uint64_t>(layers_per_seg_bound, 0xffffff00ull), rb, flags, d_counter + 15, d_seg, d_totals + 16, ctx->sm_count, st));
+        CKR(launch_assemble_layers(R->d_layers, (uint32_t)std::min<uint64_t>(layers_per_seg_bound, 0xffffff00ull), rb, flags, d_counter + 15, d_seg, d_totals + 16, d_tile_err, ctx->sm_count, st));
         prof.end();
         CKR(launch_seg_end(d_seg, sg + 1 == S ? R->d_first_layer + n_tiles : nullptr, st));
         launches += 13;  // k_seg_begin, k0_fill_layers, 5 codec kernels + 4 second passes, k_assemble_layers, k_seg_end
     }
     if (n_tiles) {
         prof.begin("k_tile_status", 0);
-        CKR(launch_finalize(R->d_layers, R->d_first_layer, n_tiles, (uint32_t)std::min<uint64_t>(ctx->h_seg->cap[0], 0xffffff00ull), flags, R->d_tile_status, d_totals + 16, d_seg, st));
+        CKR(launch_finalize(R->d_layers, d_tile_err, n_tiles, (uint32_t)std::min<uint64_t>(ctx->h_seg->cap[0], 0xffffff00ull), flags, R->d_tile_status, d_totals + 16, d_seg, st));
         prof.end();
         launches += prof.on ? 2 : 1;  // k_tile_status (+ k_alg_bytes when profiling)
     }
@@ -610,7 +742,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             else if (r.name == "scan_tile_cols") r.alg_bytes = 2ull * n_tiles * TILE_COLS * 8;
             else if (r.name == "k0_fill_layers") r.alg_bytes = meta_bytes + (uint64_t)n_tiles * (8 + TILE_COLS * 8) + (uint64_t)R->n_layers * sizeof(covt_layer) + n_task_entries * sizeof(DeviceTask);
             else if (r.name == "k_assemble_layers") r.alg_bytes = ctx->h_totals[32 + 8];
-            else if (r.name == "k_tile_status") r.alg_bytes = (uint64_t)R->n_layers * 4 + (uint64_t)n_tiles * 12;
+            else if (r.name == "k_tile_status") r.alg_bytes = (uint64_t)n_tiles * 12;
             else for (int c = 0; c < NUM_OP_CLASSES; c++) if (r.name == op_class_name(c)) r.alg_bytes = ctx->h_totals[32 + 3 + c];
         }
         prof.collect(R->kernel_times);
@@ -619,6 +751,10 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
     R->timing.segments = S;
     cleanup_tmp();
 #undef CKR
+    if ((flags & COVT_FLAG_DECODE_PROPERTIES) && n_tiles) {
+        rc = decode_properties(ctx, batch, container, tilejson, flags, R);
+        if (rc != COVT_OK) { covt_result_free(R); return rc; }
+    }
     *out = R;
     return COVT_OK;
 }
@@ -1023,11 +1159,53 @@ int32_t covt_result_read(covt_result* res, uint32_t which, uint64_t elem_offset,
 {
     if (!res || which >= COVT_NUM_BUFFERS || (!host_dst && count)) return COVT_ERR_INVALID_ARG;
     covt_ctx* ctx = res->ctx;
-    if (elem_offset + count > res->counts[which]) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_result_read: range outside the buffer");
+    if (elem_offset > res->counts[which] || count > res->counts[which] - elem_offset) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_result_read: range outside the buffer");
     if (!count) return COVT_OK;
     CK(cudaSetDevice(ctx->device));
     const uint32_t es = kBufElemSize[which];
     CK(cudaMemcpyAsync(host_dst, reinterpret_cast<const uint8_t*>(res->bufs[which]) + elem_offset * es, count * es, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return COVT_OK;
+}
+
+int32_t covt_result_prop_columns(covt_result* res, const covt_prop_column** columns, uint32_t* n_columns)
+{
+    if (!res || !columns || !n_columns) return COVT_ERR_INVALID_ARG;
+    const int32_t rc = fetch_records(res, &res->h_prop_cols, res->d_prop_cols, res->n_prop_cols);
+    if (rc != COVT_OK) return rc;
+    *columns = res->h_prop_cols;
+    *n_columns = res->n_prop_cols;
+    return COVT_OK;
+}
+
+int32_t covt_result_prop_dictionaries(covt_result* res, const covt_prop_dictionary** dictionaries, uint32_t* n_dictionaries)
+{
+    if (!res || !dictionaries || !n_dictionaries) return COVT_ERR_INVALID_ARG;
+    const int32_t rc = fetch_records(res, &res->h_prop_dicts, res->d_prop_dicts, res->n_prop_dicts);
+    if (rc != COVT_OK) return rc;
+    *dictionaries = res->h_prop_dicts;
+    *n_dictionaries = res->n_prop_dicts;
+    return COVT_OK;
+}
+
+int32_t covt_result_prop_buffer(const covt_result* res, uint32_t which, const void** device_ptr, uint64_t* count, uint32_t* elem_size)
+{
+    if (!res || which >= COVT_NUM_PROP_BUFFERS) return COVT_ERR_INVALID_ARG;
+    if (device_ptr) *device_ptr = res->pbufs[which];
+    if (count) *count = res->pcounts[which];
+    if (elem_size) *elem_size = kPropBufElemSizeHost[which];
+    return COVT_OK;
+}
+
+int32_t covt_result_prop_read(covt_result* res, uint32_t which, uint64_t elem_offset, uint64_t count, void* host_dst)
+{
+    if (!res || which >= COVT_NUM_PROP_BUFFERS || (!host_dst && count)) return COVT_ERR_INVALID_ARG;
+    covt_ctx* ctx = res->ctx;
+    if (elem_offset > res->pcounts[which] || count > res->pcounts[which] - elem_offset) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_result_prop_read: range outside the buffer");
+    if (!count) return COVT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t es = kPropBufElemSizeHost[which];
+    CK(cudaMemcpyAsync(host_dst, reinterpret_cast<const uint8_t*>(res->pbufs[which]) + elem_offset * es, count * es, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return COVT_OK;
 }
@@ -1059,6 +1237,11 @@ void covt_result_free(covt_result* res)
     pinned_give(ctx, res->h_layers, std::max<uint64_t>(res->n_layers, 1) * sizeof(covt_layer));
     pinned_give(ctx, res->h_tile_status, ((uint64_t)res->n_tiles + 1) * sizeof(uint32_t));
     pinned_give(ctx, res->h_first_layer, ((uint64_t)res->n_tiles + 2) * sizeof(uint32_t));
+    dev_free(ctx, res->prop_arena);
+    dev_free(ctx, res->d_prop_cols);
+    dev_free(ctx, res->d_prop_dicts);
+    pinned_give(ctx, res->h_prop_cols, std::max<uint64_t>(res->n_prop_cols, 1) * sizeof(covt_prop_column));
+    pinned_give(ctx, res->h_prop_dicts, std::max<uint64_t>(res->n_prop_dicts, 1) * sizeof(covt_prop_dictionary));
     delete res;
 }
 

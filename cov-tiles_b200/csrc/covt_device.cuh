@@ -27,7 +27,8 @@ struct StreamTask {
     uint8_t op;            // covt_op
     uint8_t num_bits;      // Morton bits
     uint8_t no_shift;      // COVT_FLAG_MORTON_NO_SHIFT
-    uint8_t exact_length;  // 1: byte_length is the stream's exact size (container path); 0: an upper bound (DecodingUtils "pos" semantics)
+    uint8_t exact_length;  // 1: byte_length is the stream's exact size (container path); 0: an upper bound (DecodingUtils "pos" semantics);
+                           // 2: an upper bound, and ending anywhere else is COVT_ERR_COUNT_MISMATCH (property streams)
 };
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 

@@ -75,7 +75,8 @@ static const uint8_t kBufElemSize[COVT_NUM_BUFFERS] = {1, 8, 4, 4, 4, 4, 4, 4, 4
 cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                                  const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols,
                                  uint32_t* tile_status, cudaStream_t st);
-cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_t* block_sums, uint64_t* totals, cudaStream_t st);
+// exclusive scan over tiles of n_cols column-major columns (in place); block_sums: n_cols * ceil(n_tiles / 256) words; totals[n_cols]
+cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_t* block_sums, uint64_t* totals, cudaStream_t st, uint32_t n_cols = TILE_COLS);
 cudaError_t launch_seg_begin(SegState* seg, uint32_t* work_counters /*[WORK_COUNTERS]*/, cudaStream_t st);
 cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end /*nullable*/, cudaStream_t st);
 cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
@@ -84,19 +85,40 @@ cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offs
                                   const SegState* seg, uint64_t* totals /* [FINAL_TOTALS] */, cudaStream_t st);
 // One codec class over ITS dense task list (pass 1: small streams by threads; pass 2: queued large streams, a warp each).
 // counters: 3 zeroed words (see covt_kernels.cu); big_queue: n_tasks words. seg != nullptr (batch path): the task count is
-// seg->seg_total[COL_CLASS0 + class], n_tasks only bounds the grids, and every stream's status is also written to
-// layers[ref / 8].streams[ref % 8]. blocks_per_sm: 0 = fill the GPU with this kernel alone.
+// seg->seg_total[COL_CLASS0 + class] and n_tasks only bounds the grids. status_words != nullptr: a stream's status (when not OK) goes
+// to status_words[task.ref] (the layer table or the property-column records viewed as uint32 words); nullptr (stream path): status
+// and bytes consumed go back to the task. blocks_per_sm: 0 = fill the GPU with this kernel alone.
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* counters, uint32_t* big_queue,
-                                const SegState* seg, covt_layer* layers, int sm_count, int blocks_per_sm, cudaStream_t st);
+                                const SegState* seg, uint32_t* status_words, int sm_count, int blocks_per_sm, cudaStream_t st);
 const char* op_class_name(int op_class);
 cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
-                                   uint32_t* work_counter, const SegState* seg, uint64_t* totals /* [FINAL_TOTALS] */, int sm_count, cudaStream_t st);
+                                   uint32_t* work_counter, const SegState* seg, uint64_t* totals /* [FINAL_TOTALS] */,
+                                   uint32_t* tile_err /* [n_tiles of the batch], 0xffffffff = no failing layer */, int sm_count, cudaStream_t st);
 // k1a_aggregate + 3 segmented-scan kernels + k1b_decode; block_states needs ceil(n_chunks / K1_SCAN_BLOCK) entries
 cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks,
                                     ChunkState* states, ChunkState* block_states, cudaStream_t st);
 // per-tile status; with COVT_FLAG_PROFILE_KERNELS also the algorithmic bytes per kernel (totals[3 ..])
-cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t n_layers_bound, uint32_t flags,
+cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* tile_err, uint32_t n_tiles, uint32_t n_layers_bound, uint32_t flags,
                             uint32_t* tile_status, uint64_t* totals /* [FINAL_TOTALS] */, const SegState* seg, cudaStream_t st);
+// ---- property columns (covt_props.cuh) ----
+// per-tile columns of the property scan: 0 = columns, 1 = dictionaries, 2..8 = elements per value buffer, 9..13 = tasks per codec class
+constexpr int PROP_COL_COLUMNS = 0, PROP_COL_DICTS = 1, PROP_COL_BUF0 = 2, PROP_COL_CLASS0 = PROP_COL_BUF0 + COVT_NUM_PROP_BUFFERS;
+constexpr int PROP_COLS = PROP_COL_CLASS0 + NUM_OP_CLASSES_C;
+constexpr int PROP_AUX_WORDS = 8;  // per column: [0] PRESENT status [1] DATA status [2] flags [3] DATA byteLength [4,5] DATA offset
+static const uint8_t kPropBufElemSizeHost[COVT_NUM_PROP_BUFFERS] = {1, 8, 4, 8, 1, 4, 4};
+struct PropOut {
+    covt_prop_column* cols;
+    covt_prop_dictionary* dicts;
+    uint32_t* aux;             // PROP_AUX_WORDS words per column, then one status word per dictionary
+    uint64_t aux_dict_base;    // word index of dictionary 0's status
+    DeviceTask* tasks;
+    uint64_t class_off[NUM_OP_CLASSES_C];
+    void* buf[COVT_NUM_PROP_BUFFERS];
+};
+// fill = false: pcols[col * n_tiles + tile] = per-tile sums (out is not touched); fill = true: pcols holds the exclusive prefixes
+cudaError_t launch_k0_props(bool fill, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container, const uint32_t* tj_fields,
+                            uint32_t tj_layers, uint64_t* pcols, const PropOut& out, cudaStream_t st);
+cudaError_t launch_prop_finish(const uint8_t* blob, uint32_t n_cols, uint32_t n_dicts, const PropOut& out, cudaStream_t st);
 uint32_t host_resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags);
 int host_op_class_of(uint32_t op);  // OpClass of a covt_op, -1 for COVT_OP_NONE
 

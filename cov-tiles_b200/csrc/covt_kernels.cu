@@ -15,12 +15,16 @@
 #include "covt_internal.h"
 #include "covt_streams.cuh"
 #include "covt_walk.cuh"
+#include "covt_props.cuh"
 
 namespace covt {
 
 // =================================================================================================
 // result layout (DESIGN.md "result layout"): slice sizes of one layer in every result buffer
 // =================================================================================================
+// word index (uint32) of covt_layer[l].streams[s].status in the layer table = l * LAYER_WORDS + STREAM0_STATUS_WORD + s * STREAM_REF_WORDS
+constexpr uint32_t LAYER_WORDS = sizeof(covt_layer) / 4, STREAM_REF_WORDS = sizeof(covt_stream_ref) / 4;
+constexpr uint32_t STREAM0_STATUS_WORD = (offsetof(covt_layer, streams) + offsetof(covt_stream_ref, status)) / 4;
 __host__ __device__ inline uint32_t kBufElemSizeDev(int b)
 {
     return (b == COVT_BUF_S_GEOMETRY_TYPES || b == COVT_BUF_STREAM_ARENA) ? 1u : (b == COVT_BUF_S_IDS ? 8u : 4u);
@@ -84,7 +88,8 @@ __host__ __device__ inline int op_class_of(uint32_t op)
     case COVT_OP_BYTE_RLE: return CLASS_BYTE_RLE;
     case COVT_OP_RLE_U32: case COVT_OP_RLE_U64: case COVT_OP_RLE_S64: return CLASS_RLE;
     case COVT_OP_VARINT_U32: case COVT_OP_VARINT_ZZ: case COVT_OP_VARINT_ZZ_DELTA: case COVT_OP_VARINT_ZZ_DELTA_XY:
-    case COVT_OP_VARINT_DELTA_MORTON: case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: return CLASS_VARINT32;
+    case COVT_OP_VARINT_DELTA_MORTON: case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: case COVT_OP_VARINT_ZZ_AS_I64:
+        return CLASS_VARINT32;
     case COVT_OP_VARINT_U64: case COVT_OP_VARINT_ZZ_DELTA_64: return CLASS_VARINT64;
     case COVT_OP_PFOR_ZZ_DELTA: case COVT_OP_PFOR_ZZ_DELTA_XY: case COVT_OP_PFOR_DELTA_MORTON: return CLASS_PFOR;
     default: return -1;
@@ -145,35 +150,39 @@ __device__ __forceinline__ uint64_t lite_slice_size(const Lite& lite, uint32_t g
     }
 }
 
-// pass 1: layers per tile + slice sizes per result buffer + tasks per codec class (column-major: col * n_tiles + tile)
+// pass 1: layers per tile + slice sizes per result buffer + tasks per codec class (column-major: col * n_tiles + tile).
+// The per-tile sums live in REGISTERS (every index below is a compile-time constant after unrolling; the codec class, the one
+// run-time index, is matched by an unrolled compare): as shared-memory arrays (19 x 8 B x 128 threads on top of the layer scratch)
+// they took 31 KB per block, i.e. 217 KB of the SM's 256 KB L1/shared array at 7 resident blocks, which left no L1 for the header
+// bytes — every byte load of the walk went to L2 (ncu: lts sectors == l1tex sectors, k0_scan_tiles 0.75 -> 2.16 ms per 1 M tiles).
 __global__ void __launch_bounds__(K0_BLOCK)
 k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
               const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols, uint32_t* tile_status)
 {
     __shared__ uint32_t s_lite[LITE_WORDS * K0_BLOCK];
-    __shared__ uint64_t s_acc[TILE_COLS * K0_BLOCK];
     const uint32_t t = blockIdx.x * K0_BLOCK + threadIdx.x;
     if (t >= n_tiles) return;
     const Lite lite = {s_lite + threadIdx.x};
-    uint64_t* acc = s_acc + threadIdx.x;
+    uint64_t acc[TILE_COLS];
 #pragma unroll
-    for (int i = 0; i < TILE_COLS; i++) acc[i * K0_BLOCK] = 0;
+    for (int i = 0; i < TILE_COLS; i++) acc[i] = 0;
     NoProps props;
     const uint32_t st = walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, lite, props,
                                   [&](uint32_t, const LayerHead& H) {
                                       acc[0] += 1;
 #pragma unroll
                                       for (int b = 0; b < COVT_NUM_BUFFERS; b++)
-                                          acc[(1 + b) * K0_BLOCK] += align_elems(lite_slice_size(lite, H.geom_ct, flags, b), kBufElemSizeDev(b));
+                                          acc[1 + b] += align_elems(lite_slice_size(lite, H.geom_ct, flags, b), kBufElemSizeDev(b));
 #pragma unroll
                                       for (int s = 0; s < COVT_NUM_SLOTS; s++) {
                                           const int c = lite.has(s) ? op_class_of(resolve_op(slot_stream_type(s), lite.enc(s), H.geom_ct, flags)) : -1;
-                                          if (c >= 0) acc[(COL_CLASS0 + c) * K0_BLOCK] += 1;
+#pragma unroll
+                                          for (int k = 0; k < NUM_OP_CLASSES; k++) acc[COL_CLASS0 + k] += (c == k) ? 1u : 0u;
                                       }
                                   });
     tile_status[t] = st;
 #pragma unroll
-    for (int i = 0; i < TILE_COLS; i++) tile_cols[(uint64_t)i * n_tiles + t] = acc[i * K0_BLOCK];
+    for (int i = 0; i < TILE_COLS; i++) tile_cols[(uint64_t)i * n_tiles + t] = acc[i];
 }
 
 // pass 2: the covt_layer table with result offsets (tile_cols now holds exclusive prefixes) and one decode task per present stream,
@@ -184,18 +193,17 @@ k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_til
                DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer, const SegState* seg, uint64_t* totals)
 {
     __shared__ uint32_t s_lite[LITE_WORDS * K0_BLOCK];
-    __shared__ uint64_t s_run[TILE_COLS * K0_BLOCK];
     const uint32_t t = blockIdx.x * K0_BLOCK + threadIdx.x;
     if (seg->overflow) return;
     uint64_t payload_bytes = 0, stream_out_bytes = 0;  // -> totals[1], totals[2] (covt_timing)
     if (t < n_tiles) {
     const Lite lite = {s_lite + threadIdx.x};
-    uint64_t* run = s_run + threadIdx.x;
-    // tile_cols holds exclusive prefixes inside this segment; seg->base = totals of the segments before it
-    // (the class columns stay segment-local: the task lists are rebuilt for every segment)
+    // running positions of the tile, in registers (see k0_scan_tiles). tile_cols holds exclusive prefixes inside this segment;
+    // seg->base = totals of the segments before it (the class columns stay segment-local: the task lists are rebuilt for every segment)
+    uint64_t run[TILE_COLS];
 #pragma unroll
     for (int i = 0; i < TILE_COLS; i++)
-        run[i * K0_BLOCK] = tile_cols[(uint64_t)i * n_tiles + t] + (i < COL_CLASS0 ? seg->base[i] : class_off.off[i - COL_CLASS0]);
+        run[i] = tile_cols[(uint64_t)i * n_tiles + t] + (i < COL_CLASS0 ? seg->base[i] : class_off.off[i - COL_CLASS0]);
     first_layer[t] = (uint32_t)run[0];
     const uint32_t tile = t + tile_base;
     NoProps props;
@@ -250,23 +258,26 @@ k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_til
                 const int b = slot_buf(s);
                 uint32_t nv = lite.nv(s);
                 if (s == COVT_SLOT_VBUF && H.geom_ct == COVT_CT_ICE && !(flags & COVT_FLAG_ICE_VB_COUNT_IS_INTS)) nv *= 2;
-                const uint64_t dptr = reinterpret_cast<uint64_t>(bufs.ptr[b]) + run[(1 + b) * K0_BLOCK] * kBufElemSizeDev(b);
-                uint2* tp = reinterpret_cast<uint2*>(&tasks[run[(COL_CLASS0 + c) * K0_BLOCK]]);
-                run[(COL_CLASS0 + c) * K0_BLOCK] += 1;
+                const uint64_t dptr = reinterpret_cast<uint64_t>(bufs.ptr[b]) + run[1 + b] * kBufElemSizeDev(b);
+                uint64_t task_slot = 0;
+#pragma unroll
+                for (int k = 0; k < NUM_OP_CLASSES; k++)
+                    if (c == k) { task_slot = run[COL_CLASS0 + k]; run[COL_CLASS0 + k] += 1; }
+                uint2* tp = reinterpret_cast<uint2*>(&tasks[task_slot]);
                 tp[0] = make_uint2((uint32_t)off, (uint32_t)(off >> 32));
                 tp[1] = make_uint2((uint32_t)dptr, (uint32_t)(dptr >> 32));
                 tp[2] = make_uint2(lite.bl(s), nv);
                 tp[3] = make_uint2(op | (num_bits << 8) | ((flags & COVT_FLAG_MORTON_NO_SHIFT) ? 1u << 16 : 0u) | (1u << 24), COVT_OK);
-                tp[4] = make_uint2(0u, layer * COVT_NUM_SLOTS + (uint32_t)s);
+                tp[4] = make_uint2(0u, layer * LAYER_WORDS + STREAM0_STATUS_WORD + (uint32_t)s * STREAM_REF_WORDS);
             }
         }
         // out[13]: element offset of the layer's slice in every result buffer
 #pragma unroll
         for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
-            const uint64_t o = run[(1 + b) * K0_BLOCK];
+            const uint64_t o = run[1 + b];
             push((uint32_t)o);
             push((uint32_t)(o >> 32));
-            run[(1 + b) * K0_BLOCK] = o + align_elems(lite_slice_size(lite, H.geom_ct, flags, b), kBufElemSizeDev(b));
+            run[1 + b] = o + align_elems(lite_slice_size(lite, H.geom_ct, flags, b), kBufElemSizeDev(b));
         }
         push(0u); push(0u); push(0u); push(0u);  // n_parts, n_rings, n_vertices, n_coords: written by the assembler
         push((uint32_t)cap_parts);
@@ -392,8 +403,9 @@ __device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, Strea
         else warp_rle_stream<int64_t, true>(t, o);
     } else if (CLASS == CLASS_VARINT32) {
         if (t.op == COVT_OP_VARINT_ZZ_DELTA_XY && (t.num_values & 1u)) { o.status = COVT_ERR_COUNT_MISMATCH; return; }
-        const bool widen = t.op == COVT_OP_VARINT_U32_AS_I64 || t.op == COVT_OP_VARINT_ZZ_DELTA_AS_I64;
-        const int post = t.op == COVT_OP_VARINT_U32_AS_I64 ? POST_PLAIN : (t.op == COVT_OP_VARINT_ZZ_DELTA_AS_I64 ? POST_ZZ_DELTA : post_kind_of_op(t.op));
+        const bool widen = t.op == COVT_OP_VARINT_U32_AS_I64 || t.op == COVT_OP_VARINT_ZZ_DELTA_AS_I64 || t.op == COVT_OP_VARINT_ZZ_AS_I64;
+        const int post = t.op == COVT_OP_VARINT_U32_AS_I64 ? POST_PLAIN : (t.op == COVT_OP_VARINT_ZZ_DELTA_AS_I64 ? POST_ZZ_DELTA :
+                         (t.op == COVT_OP_VARINT_ZZ_AS_I64 ? POST_ZZ : post_kind_of_op(t.op)));
         warp_varint32_stream(t, stage, o, post, widen);
     } else if (CLASS == CLASS_VARINT64) {
         if (t.op == COVT_OP_VARINT_U64) warp_varint64_stream<false>(t, reinterpret_cast<uint64_t*>(wsm), o);
@@ -402,6 +414,22 @@ __device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, Strea
         if (t.op == COVT_OP_PFOR_ZZ_DELTA_XY && (t.num_values & 1u)) { o.status = COVT_ERR_COUNT_MISMATCH; return; }
         if (!BIG) warp_pfor_stream_smem(t, stage, stage + PFOR_SMEM_WORDS + 4, o, post_kind_of_op(t.op));
         else warp_pfor_stream(t, stage, o, post_kind_of_op(t.op));  // larger than the window: read the page through global memory
+    }
+}
+
+// Where a stream's outcome goes. Batch path (status_words != nullptr): word d.ref of the status table — the status field of the
+// stream's slot in the layer table, or of a property column's record — and only when it is NOT ok: the container walk initialised
+// every status to COVT_OK, so the common case costs no scattered store at all. Stream path: status and bytes consumed go back to
+// the task, which the host reads. exact_length == 2 (property streams): the stream must end exactly at its byteLength.
+__device__ __forceinline__ void report_outcome(DeviceTask* tasks, uint32_t i, const DeviceTask& d, const StreamOutcome& o, uint32_t* status_words)
+{
+    uint32_t st = o.status;
+    if (d.exact_length == 2 && (st == COVT_OK || st == COVT_ERR_VARINT_OVERLONG) && o.consumed != d.byte_length) st = COVT_ERR_COUNT_MISMATCH;
+    if (status_words) {
+        if (st != COVT_OK) status_words[d.ref] = st;
+    } else {
+        tasks[i].status = st;
+        tasks[i].consumed = o.consumed;
     }
 }
 
@@ -435,7 +463,7 @@ __device__ __forceinline__ StreamTask make_stream_task(const uint8_t* blob, cons
 // (fixture sweep: k_decode_rle 7.2 ms for 2.3 GB of output, the 60 000-value id streams of one tile land in one group).
 template <int CLASS, int MINB>
 __global__ void __launch_bounds__(DEC_WARPS * 32, MINB)
-k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uint32_t* work_counter, const SegState* seg, covt_layer* layers,
+k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uint32_t* work_counter, const SegState* seg, uint32_t* status_words,
                uint32_t* big_queue, uint32_t* big_count)
 {
     // batch path: the task count of the current segment lives on the device (the host never learns it in the pipelined mode)
@@ -444,17 +472,7 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     uint8_t* wsm = smem + warp * class_warp_smem<CLASS>();
-    // batch path (layers != nullptr): a stream's outcome goes to its slot of the layer record, and only when it is NOT ok — the
-    // container walk initialised every status to COVT_OK, so the common case costs no scattered store at all.
-    // stream path: status and bytes consumed go back to the task, which the host reads.
-    auto report = [&](uint32_t i, const DeviceTask& d, const StreamOutcome& o) {
-        if (layers) {
-            if (o.status != COVT_OK) layers[d.ref / COVT_NUM_SLOTS].streams[d.ref % COVT_NUM_SLOTS].status = o.status;
-        } else {
-            tasks[i].status = o.status;
-            tasks[i].consumed = o.consumed;
-        }
-    };
+    auto report = [&](uint32_t i, const DeviceTask& d, const StreamOutcome& o) { report_outcome(tasks, i, d, o, status_words); };
     constexpr uint32_t GROUP = class_group<CLASS>();
     const uint32_t n_groups = (n_tasks + GROUP - 1u) / GROUP;
     WarpTickets tickets;
@@ -507,7 +525,7 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
 // Pass 2: one warp per queued large stream
 template <int CLASS>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counter, const SegState* seg, covt_layer* layers,
+k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counter, const SegState* seg, uint32_t* status_words,
                    const uint32_t* big_queue, const uint32_t* big_count)
 {
     if (seg && seg->overflow) return;
@@ -528,14 +546,7 @@ k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counte
         StreamOutcome o;
         decode_one<CLASS, true>(t, wsm, o);
         __syncwarp();
-        if (lane == 0) {
-            if (layers) {
-                if (o.status != COVT_OK) layers[dw.ref / COVT_NUM_SLOTS].streams[dw.ref % COVT_NUM_SLOTS].status = o.status;
-            } else {
-                tasks[i].status = o.status;
-                tasks[i].consumed = o.consumed;
-            }
-        }
+        if (lane == 0) report_outcome(tasks, i, dw, o, status_words);
     }
 }
 
@@ -544,7 +555,8 @@ k_decode_class_big(const uint8_t* blob, DeviceTask* tasks, uint32_t* work_counte
 // =================================================================================================
 template <int MINB>
 __global__ void __launch_bounds__(DEC_WARPS * 32, MINB)
-k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter, const SegState* seg, uint64_t* totals)
+k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, uint32_t* work_counter, const SegState* seg, uint64_t* totals,
+                  uint32_t* tile_err)
 {
     if (seg->overflow) return;
     uint64_t sum_vertices = 0, sum_out_bytes = 0;  // lane 0: -> totals[0], totals[2]
@@ -597,6 +609,8 @@ k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, ui
             if (ar.status != COVT_OK) layer_status = ar.status;
         }
         if (lane == 0) {
+            // first failing layer of the tile (lowest layer index wins): k_tile_status turns the key into the tile's status
+            if (layer_status) atomicMin(&tile_err[L->tile], (min(L->layer_index, 0xffffffu) << 8) | (layer_status & 0xffu));
             L->status = layer_status;
             L->n_parts = ar.n_parts;
             L->n_rings = ar.n_rings;
@@ -891,16 +905,15 @@ __global__ void k_seg_end(SegState* seg, uint32_t* first_layer_end)
     if (i == 0 && first_layer_end) *first_layer_end = (uint32_t)seg->base[0];
 }
 
-// tile status = first layer error, unless the container walk already failed
-__global__ void k_tile_status(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t* tile_status, const SegState* seg)
+// tile status = first layer error (the key the assembler left in tile_err), unless the container walk already failed.
+// (A pass over the layer table instead cost 0.45 ms per 1 M tiles: 2.1 M scattered 4-byte reads of 368-byte records.)
+__global__ void k_tile_status(const uint32_t* tile_err, uint32_t n_tiles, uint32_t* tile_status, const SegState* seg)
 {
     if (seg->overflow) return;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    uint32_t st = tile_status[t];
-    if (st) return;
-    for (uint32_t l = first_layer[t]; l < first_layer[t + 1] && !st; l++) st = layers[l].status;
-    if (st) tile_status[t] = st;
+    const uint32_t e = tile_err[t];
+    if (e != 0xffffffffu && tile_status[t] == COVT_OK) tile_status[t] = e & 0xffu;
 }
 
 // COVT_FLAG_PROFILE_KERNELS only: algorithmic bytes per kernel (payload read + decoded stream written, no padding, no
@@ -949,13 +962,30 @@ cudaError_t launch_k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offse
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_t* block_sums, uint64_t* totals, cudaStream_t st)
+cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_t* block_sums, uint64_t* totals, cudaStream_t st, uint32_t n_cols)
 {
     if (!n_tiles) return cudaSuccess;
     const uint32_t nb = (n_tiles + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    scan_block_sums<<<dim3(nb, TILE_COLS), SCAN_BLOCK, 0, st>>>(tile_cols, n_tiles, block_sums);
-    scan_block_prefix<<<TILE_COLS, SCAN_BLOCK, 0, st>>>(block_sums, nb, totals);
-    scan_apply<<<dim3(nb, TILE_COLS), SCAN_BLOCK, 0, st>>>(tile_cols, n_tiles, block_sums);
+    scan_block_sums<<<dim3(nb, n_cols), SCAN_BLOCK, 0, st>>>(tile_cols, n_tiles, block_sums);
+    scan_block_prefix<<<n_cols, SCAN_BLOCK, 0, st>>>(block_sums, nb, totals);
+    scan_apply<<<dim3(nb, n_cols), SCAN_BLOCK, 0, st>>>(tile_cols, n_tiles, block_sums);
+    return cudaGetLastError();
+}
+
+// ---- property columns (covt_props.cuh) ----
+cudaError_t launch_k0_props(bool fill, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container, const uint32_t* tj_fields,
+                            uint32_t tj_layers, uint64_t* pcols, const PropOut& out, cudaStream_t st)
+{
+    if (!n_tiles) return cudaSuccess;
+    const uint32_t grid = (n_tiles + K0_BLOCK - 1) / K0_BLOCK;
+    if (fill) k0_props<true><<<grid, K0_BLOCK, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, pcols, out);
+    else k0_props<false><<<grid, K0_BLOCK, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, pcols, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_prop_finish(const uint8_t* blob, uint32_t n_cols, uint32_t n_dicts, const PropOut& out, cudaStream_t st)
+{
+    if (n_dicts) k_prop_finish_dicts<<<(n_dicts + 3) / 4, 128, 0, st>>>(out.dicts, n_dicts, out.aux, out.aux_dict_base, static_cast<int32_t*>(out.buf[COVT_PBUF_DICT_OFFSETS]));
+    if (n_cols) k_prop_finish_columns<<<(n_cols + 3) / 4, 128, 0, st>>>(blob, out.cols, n_cols, out.aux, out.dicts, out);
     return cudaGetLastError();
 }
 
@@ -997,7 +1027,7 @@ cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end, cudaStream_
 // counters: [0] group ticket of pass 1, [1] queue length, [2] ticket of pass 2 (all zero before the launch).
 // big_queue: n_tasks words (unused by the classes that decode every stream with a warp in pass 1).
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* counters, uint32_t* big_queue,
-                                const SegState* seg, covt_layer* layers, int sm_count, int blocks_per_sm, cudaStream_t st)
+                                const SegState* seg, uint32_t* layers, int sm_count, int blocks_per_sm, cudaStream_t st)
 {
     if (!n_tasks) return cudaSuccess;
     // Byte-RLE and RLE never touch the warp stage
@@ -1037,11 +1067,11 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
 
 // n_layers_bound: upper bound of the segment's layer count (grid size only)
 cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
-                                   uint32_t* work_counter, const SegState* seg, uint64_t* totals, int sm_count, cudaStream_t st)
+                                   uint32_t* work_counter, const SegState* seg, uint64_t* totals, uint32_t* tile_err, int sm_count, cudaStream_t st)
 {
     if (!n_layers_bound) return cudaSuccess;
     // 32 registers, 16 blocks = 64 warps per SM: the assembler waits on dependent loads (profiles/r01_experiments.md)
-    k_assemble_layers<16><<<grid_for(sm_count, 16, n_layers_bound, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg, totals);
+    k_assemble_layers<16><<<grid_for(sm_count, 16, n_layers_bound, DEC_WARPS), DEC_WARPS * 32, 0, st>>>(layers, bufs, flags, work_counter, seg, totals, tile_err);
     return cudaGetLastError();
 }
 
@@ -1059,11 +1089,11 @@ cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* stream
     return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* first_layer, uint32_t n_tiles, uint32_t n_layers_bound, uint32_t flags,
+cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* tile_err, uint32_t n_tiles, uint32_t n_layers_bound, uint32_t flags,
                             uint32_t* tile_status, uint64_t* totals, const SegState* seg, cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    k_tile_status<<<(n_tiles + 255) / 256, 256, 0, st>>>(layers, first_layer, n_tiles, tile_status, seg);
+    k_tile_status<<<(n_tiles + 255) / 256, 256, 0, st>>>(tile_err, n_tiles, tile_status, seg);
     if ((flags & COVT_FLAG_PROFILE_KERNELS) && n_layers_bound) k_alg_bytes<<<(n_layers_bound + 255) / 256, 256, 0, st>>>(layers, n_layers_bound, flags, totals, seg);
     return cudaGetLastError();
 }

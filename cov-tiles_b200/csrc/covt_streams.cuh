@@ -54,7 +54,7 @@ __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t*
         bounds(lo16, hi16);
         LeanLane L = lean_front(win, head_f != 0u || end_in_chunk < WARP_CHUNK_BYTES, lo16, hi16, halo_in, w, acc, mul, lane_ov);
         L.excl = warp_exclusive_scan(L.cnt, L.total);
-        if (!t.exact_length || L.total - head_f - (WARP_CHUNK_BYTES - end_in_chunk) > remaining) {
+        if (t.exact_length != 1 || L.total - head_f - (WARP_CHUNK_BYTES - end_in_chunk) > remaining) {
             // DecodingUtils "pos" semantics: bytes after the last requested value belong to somebody else (and a stream with an
             // exact length that holds MORE values than numValues is read no further either: what follows must not raise the
             // overlong flag). Find the terminator of value #remaining; if it lies in this chunk, the stream ends there.
@@ -88,7 +88,7 @@ __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t*
         __syncwarp();
         produced += n;
     }
-    out.consumed = t.exact_length ? t.byte_length : consumed;
+    out.consumed = t.exact_length == 1 ? t.byte_length : consumed;
     if (produced < t.num_values) out.status = COVT_ERR_TRUNCATED;  // Java: ArrayIndexOutOfBounds
     else if (__any_sync(FULL, (ov >> 28) & 1u)) out.status = COVT_ERR_VARINT_OVERLONG;
     else out.status = COVT_OK;
@@ -490,7 +490,7 @@ __device__ __forceinline__ void thread_varint64_stream(const StreamTask& t, bool
     }
     if (status == COVT_OK && overlong) status = COVT_ERR_VARINT_OVERLONG;
     out.status = status;
-    out.consumed = t.exact_length ? t.byte_length : pos;
+    out.consumed = t.exact_length == 1 ? t.byte_length : pos;
 }
 
 // =================================================================================================

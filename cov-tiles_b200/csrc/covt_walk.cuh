@@ -119,12 +119,14 @@ struct LayerHead {
 };
 
 // What a walker does with property columns. want() == false: they are only hopped over.
-//   begin_column(name_offset, name_length, data_type /*covt_column_data_type*/, column_type)
+//   set_layer(layer_index)                                                                          before a layer is walked
+//   begin_column(name_offset, name_length, data_type /*covt_column_data_type, 0xFF = unknown*/, column_type, num_features)
 //   stream(stream_type, sub_offset, sub_length, num_values, byte_length, encoding, payload_offset)   in payload order
 //   end_column()
 struct NoProps {
     __device__ __forceinline__ bool want() const { return false; }
-    __device__ __forceinline__ void begin_column(uint64_t, uint32_t, uint32_t, uint32_t) {}
+    __device__ __forceinline__ void set_layer(uint32_t) {}
+    __device__ __forceinline__ void begin_column(uint64_t, uint32_t, uint32_t, uint32_t, uint32_t) {}
     __device__ __forceinline__ void stream(uint32_t, uint64_t, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t) {}
     __device__ __forceinline__ void end_column() {}
 };
@@ -261,7 +263,7 @@ __device__ uint32_t walk_layer_gen2b(Cursor& c, const Lite& lite, LayerHead& H, 
             const bool is_geom = name_is(blob, noff, nlen, "geometry");
             if (is_id) { H.id_offset = p; p += id_bytes; }
             else if (is_geom) { H.geom_offset = p; p += geom_bytes; }
-            else props.begin_column(noff, nlen, dt_of_gen2(dt2), column_type);
+            else props.begin_column(noff, nlen, dt_of_gen2(dt2), column_type, H.num_features);
             for (uint32_t si = 0; si < num_streams; si++) {
                 uint64_t soff; uint32_t slen;
                 c_string(m, soff, slen);
@@ -401,7 +403,7 @@ __device__ uint32_t walk_layer_gen3(Cursor& c, const uint32_t* tj_fields, uint32
             if (is_id) { H.id_offset = p; p += id_bytes; }
             else if (is_geom) { H.geom_offset = p; p += geom_bytes; }
             else {
-                props.begin_column(noff, nlen, data_type, column_type);
+                props.begin_column(noff, nlen, data_type, column_type, H.num_features);
                 if (data_type != COVT_DT_BOOLEAN) {
                     uint64_t q = p;
                     if (!byte_rle_span(blob, q, c.end, (H.num_features + 7u) / 8u)) return COVT_ERR_TRUNCATED;
@@ -415,7 +417,9 @@ __device__ uint32_t walk_layer_gen3(Cursor& c, const uint32_t* tj_fields, uint32
                 const uint32_t nv = c_varint(m);
                 const uint32_t bl = c_varint(m);
                 if (prop) {
-                    props.stream(stream_type, 0, 0, nv, bl, stream_desc & 0xFu, p);
+                    // BOOLEAN data = one bit per FEATURE whatever numValues says (CovtParser.java:280-283 reads ceil(numFeatures / 8) bytes)
+                    props.stream(stream_type, 0, 0, (data_type == COVT_DT_BOOLEAN && stream_type == COVT_ST_DATA) ? H.num_features : nv, bl,
+                                 stream_desc & 0xFu, p);
                     p += bl;
                 }
                 if (m.err || gen3_last_stream(data_type, column_type, stream_type)) break;
@@ -441,6 +445,7 @@ __device__ __forceinline__ uint32_t walk_tile(const uint8_t* blob, uint64_t begi
         const uint32_t num_layers = c_varint(c);
         if (c.err) return COVT_ERR_TRUNCATED;
         for (uint32_t li = 0; li < num_layers; li++) {
+            props.set_layer(li);
             const uint32_t st = walk_layer_gen2b(c, lite, H, props);
             if (st != COVT_OK) return st;
             on_layer(li, H);
@@ -449,6 +454,7 @@ __device__ __forceinline__ uint32_t walk_tile(const uint8_t* blob, uint64_t begi
     }
     uint32_t li = 0;
     while (c.p < end) {
+        props.set_layer(li);
         const uint32_t st = walk_layer_gen3(c, tj_fields, tj_layers, lite, H, props);
         if (st != COVT_OK) return st;
         on_layer(li, H);

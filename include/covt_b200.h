@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define COVT_ABI_VERSION 2
+#define COVT_ABI_VERSION 3
 
 /* ---- wire enums (ordinals identical to the Java enums) ------------------------------------ */
 
@@ -127,6 +127,7 @@ enum covt_status {
 #define COVT_FLAG_ICE_VB_COUNT_IS_INTS   0x0010u /* emulate HEAD decoder for ColumnType.ICE (CovtParser.java:499-505): numValues counts ints */
 #define COVT_FLAG_SKIP_ASSEMBLY          0x0020u /* decode streams only */
 #define COVT_FLAG_PROFILE_KERNELS        0x0040u /* record one CUDA event pair per kernel launch (serialises nothing, adds events) */
+#define COVT_FLAG_DECODE_PROPERTIES      0x0080u /* also decode the property columns (CovtParser.decodePropertyColumn, CovtParser.java:276-390) */
 #define COVT_FLAG_DEFAULT                (COVT_FLAG_CLOSE_RINGS)
 
 /* ---- slots of a layer's stream table ------------------------------------------------------- */
@@ -236,9 +237,56 @@ enum covt_op {
     COVT_OP_PFOR_ZZ_DELTA_XY = 13,     /* decodeFastPfor128DeltaCoordinates    -> i32 */
     COVT_OP_PFOR_DELTA_MORTON = 14,    /* decodeFastPfor128DeltaMortonCodes    -> i32 x2 */
     COVT_OP_VARINT_U32_AS_I64 = 15,    /* decodeVarint widened to long (ids, COVT_FLAG_ID_WIDTH_32) */
-    COVT_OP_VARINT_ZZ_DELTA_AS_I64 = 16,/* decodeZigZagDeltaVarint widened to long (ids, COVT_FLAG_ID_WIDTH_32) */
-    COVT_NUM_OPS = 17
+    COVT_OP_VARINT_ZZ_DELTA_AS_I64 = 16,/* decodeZigZagDeltaVarint widened to long (ids, COVT_FLAG_ID_WIDTH_32; INT_64 property data) */
+    COVT_OP_VARINT_ZZ_AS_I64 = 17,     /* decodeZigZagVarint widened to long (INT_64 property data, CovtParser.java:303-306) */
+    COVT_NUM_OPS = 18
 };
+
+/* ---- property columns (COVT_FLAG_DECODE_PROPERTIES) ------------------------------------------------
+ * Replaces CovtParser.decodePropertyColumn (CovtParser.java:276-390) + getStringDictionary (:379-390) with a columnar,
+ * Arrow-like result instead of List<Optional>: per column a VALIDITY bitmap (bit i = feature i has a value, java.util.BitSet
+ * order: byte i >> 3, bit i & 7) and the DENSE values of the features that have one. Strings are dictionary indices; a
+ * dictionary is an offsets array into the tile's own UTF-8 bytes, which stay in the input blob. Localized dictionary columns
+ * (gen-2b fixtures) are flattened: one column per sub-key, all pointing at the shared dictionary. */
+enum covt_prop_value_kind {
+    COVT_PV_NONE = 0, COVT_PV_I64 = 1, COVT_PV_F32 = 2, COVT_PV_F64 = 3,
+    COVT_PV_BOOL = 4,       /* dense bits, BitSet order */
+    COVT_PV_DICT_INDEX = 5  /* i32 indices into dictionaries[dictionary] */
+};
+enum covt_prop_buffer {
+    COVT_PBUF_VALIDITY = 0,     /* u8: ceil(num_features / 8) bytes per column */
+    COVT_PBUF_I64 = 1,          /* i64 */
+    COVT_PBUF_F32 = 2,          /* f32 (DecodingUtils.decodeFloatsLE :446-453) */
+    COVT_PBUF_F64 = 3,          /* f64 */
+    COVT_PBUF_BOOL = 4,         /* u8: ceil(num_values / 8) bytes per BOOLEAN column */
+    COVT_PBUF_DICT_INDEX = 5,   /* i32 */
+    COVT_PBUF_DICT_OFFSETS = 6, /* i32: n_entries + 1 byte offsets per dictionary, relative to its bytes_offset */
+    COVT_NUM_PROP_BUFFERS = 7
+};
+typedef struct covt_prop_column {
+    uint32_t tile, layer;        /* layer = index within the tile */
+    uint64_t name_offset;        /* column name in the blob; optimised gen-3: index into the TileJSON fields of the layer */
+    uint64_t sub_offset;         /* localized sub-key name in the blob (sub_length 0: not a localized sub-column) */
+    uint32_t name_length, sub_length;
+    uint8_t  data_type;          /* covt_column_data_type (HEAD ordinals) */
+    uint8_t  column_type;        /* covt_column_type */
+    uint8_t  value_kind;         /* covt_prop_value_kind */
+    uint8_t  reserved;
+    uint32_t status;             /* covt_status of the column */
+    uint32_t num_features;
+    uint32_t num_values;         /* set bits of the validity bitmap = dense values */
+    uint64_t validity_offset;    /* bytes into COVT_PBUF_VALIDITY */
+    uint64_t values_offset;      /* elements into the buffer of value_kind (COVT_PV_BOOL: BYTES into COVT_PBUF_BOOL) */
+    uint32_t dictionary;         /* COVT_PV_DICT_INDEX: index into the dictionaries */
+    uint32_t data_num_values;    /* numValues the data stream declares (the slice reserved at values_offset) */
+} covt_prop_column;
+typedef struct covt_prop_dictionary {
+    uint32_t tile, layer, n_entries;
+    uint32_t status;             /* covt_status of the length stream / offsets */
+    uint64_t offsets_offset;     /* elements into COVT_PBUF_DICT_OFFSETS: n_entries + 1 offsets relative to bytes_offset */
+    uint64_t bytes_offset;       /* the UTF-8 bytes of all entries, back to back, in the blob */
+    uint64_t n_bytes;
+} covt_prop_dictionary;
 
 /* Optional TileJSON side-car for optimised gen-3 metadata (CovtParser.java:583-590): only the number
  * of fields per vector layer matters to the decode path (column ids >= 2 index the fields). */
@@ -318,6 +366,12 @@ int32_t covt_result_buffer(const covt_result* res, uint32_t which, const void** 
                            uint32_t* elem_size);
 /* Device->host copy of count elements starting at elem_offset of buffer `which`. */
 int32_t covt_result_read(covt_result* res, uint32_t which, uint64_t elem_offset, uint64_t count, void* host_dst);
+/* Property columns (COVT_FLAG_DECODE_PROPERTIES; zero columns otherwise). Host copies of the records (pinned, fetched lazily),
+ * device pointer / read-back of the value buffers (covt_prop_buffer). */
+int32_t covt_result_prop_columns(covt_result* res, const covt_prop_column** columns, uint32_t* n_columns);
+int32_t covt_result_prop_dictionaries(covt_result* res, const covt_prop_dictionary** dictionaries, uint32_t* n_dictionaries);
+int32_t covt_result_prop_buffer(const covt_result* res, uint32_t which, const void** device_ptr, uint64_t* count, uint32_t* elem_size);
+int32_t covt_result_prop_read(covt_result* res, uint32_t which, uint64_t elem_offset, uint64_t count, void* host_dst);
 int32_t covt_result_timing(const covt_result* res, covt_timing* out);
 /* Fills up to cap entries, returns the number of distinct kernels in *n. */
 int32_t covt_result_kernel_times(const covt_result* res, covt_kernel_time* out, uint32_t cap, uint32_t* n);

@@ -711,7 +711,33 @@ static void layer_resolve_ops(covt_layer* L, uint32_t flags)
 }
 /* one entry per column, in metadata order */
 enum { COL_ID = 0, COL_GEOMETRY = 1, COL_PROPERTY = 2 };
-typedef struct { uint8_t kind; uint8_t data_type; uint64_t listed_bytes; } col_t;
+typedef struct { uint8_t kind; uint8_t data_type; uint64_t listed_bytes; uint64_t meta_pos; } col_t;
+
+/* property-column sink (defined with the property code at the end of this file); NULL = hop over the property payloads */
+typedef struct prop_sink prop_sink_t;
+static void sink_set_layer(prop_sink_t* k, uint32_t li);
+static void sink_begin_column(prop_sink_t* k, uint64_t noff, uint32_t nlen, uint32_t dt, uint32_t ct, uint32_t F);
+static void sink_stream(prop_sink_t* k, uint32_t st, uint64_t sub_off, uint32_t sub_len, uint32_t nv, uint32_t bl, uint32_t enc, uint64_t off);
+static void sink_end_column(prop_sink_t* k);
+static int name_starts(const uint8_t* b, uint64_t off, uint32_t len, const char* s)
+{
+    size_t n = strlen(s);
+    return len >= n && memcmp(b + off, s, n) == 0;
+}
+/* gen-2 data type byte of the column header -> COVT_DT_*; 0xFF = unknown */
+static uint32_t dt_of_gen2(uint32_t g)
+{
+    switch (g) {
+    case 0: return COVT_DT_STRING;
+    case 1: return COVT_DT_FLOAT;
+    case 2: return COVT_DT_DOUBLE;
+    case 3: return COVT_DT_INT_64;
+    case 4: return COVT_DT_UINT_64;
+    case 5: return COVT_DT_BOOLEAN;
+    case 6: return COVT_DT_GEOMETRY;
+    default: return 0xFFu;
+    }
+}
 
 /* Library policy shared with the product (result buffers are sized from numValues before anything is decoded): a stream that
  * claims more than 256 values per payload byte cannot decode with any codec of the path (the densest, FastPFOR at bit width 0,
@@ -727,7 +753,7 @@ static uint32_t nlz32(uint32_t v) { return v ? (uint32_t)__builtin_clz(v) : 32u;
  * per column: string name, byte dataType, byte columnType, varint numStreams | per stream: string name,
  * varint numValues, varint byteLength, byte StreamEncoding. Payload follows each layer's metadata. */
 static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, uint32_t flags, uint32_t tile,
-                           covt_layer* layers, uint32_t cap, uint32_t* n_layers, uint64_t* end_pos)
+                           covt_layer* layers, uint32_t cap, uint32_t* n_layers, uint64_t* end_pos, prop_sink_t* sink)
 {
     cur_t c = {blob, begin, end, 0};
     *n_layers = 0;
@@ -738,6 +764,7 @@ static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, ui
         if (*n_layers >= cap) return COVT_ERR_OOM;
         covt_layer* L = &layers[*n_layers];
         layer_init(L, tile, li);
+        sink_set_layer(sink, li);
         c_string(&c, &L->name_offset, &L->name_length);
         L->extent = c_varint(&c);
         L->num_features = c_varint(&c);
@@ -751,6 +778,7 @@ static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, ui
         int32_t rc = COVT_OK;
         for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
             uint64_t noff; uint32_t nlen;
+            cols[ci].meta_pos = c.p;
             c_string(&c, &noff, &nlen);
             uint32_t data_type = c_byte(&c);
             uint32_t column_type = c_byte(&c);
@@ -807,7 +835,37 @@ static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, ui
         for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
             if (cols[ci].kind == COL_ID) place_id(L, &p);
             else if (cols[ci].kind == COL_GEOMETRY) place_geometry(L, &p);
-            else p += cols[ci].listed_bytes;
+            else if (!sink) p += cols[ci].listed_bytes;
+            else {
+                /* the column's metadata once more (it parsed fine a moment ago): its streams in payload order. Stream names of
+                 * property columns: present, data, length, dictionary; localized dictionaries list pairs (present_<s>, <s>) and
+                 * share one length + dictionary (oracle/properties.py) */
+                cur_t m = {blob, cols[ci].meta_pos, end, 0};
+                uint64_t noff; uint32_t nlen;
+                c_string(&m, &noff, &nlen);
+                uint32_t dt2 = c_byte(&m);
+                uint32_t column_type = c_byte(&m);
+                uint32_t num_streams = c_varint(&m);
+                sink_begin_column(sink, noff, nlen, dt_of_gen2(dt2), column_type, L->num_features);
+                for (uint32_t si = 0; si < num_streams; si++) {
+                    uint64_t soff; uint32_t slen;
+                    c_string(&m, &soff, &slen);
+                    uint32_t nv = c_varint(&m);
+                    uint32_t bl = c_varint(&m);
+                    uint32_t enc = c_byte(&m);
+                    uint32_t st = COVT_ST_DATA;
+                    uint64_t sub_off = 0; uint32_t sub_len = 0;
+                    if (name_is(blob, soff, slen, "present")) st = COVT_ST_PRESENT;
+                    else if (name_is(blob, soff, slen, "data")) st = COVT_ST_DATA;
+                    else if (name_is(blob, soff, slen, "length")) st = COVT_ST_LENGTH;
+                    else if (name_is(blob, soff, slen, "dictionary")) st = COVT_ST_DICTIONARY;
+                    else if (name_starts(blob, soff, slen, "present_")) { st = COVT_ST_PRESENT; sub_off = soff + 8; sub_len = slen - 8; }
+                    else { st = COVT_ST_DATA; sub_off = soff; sub_len = slen; }
+                    sink_stream(sink, st, sub_off, sub_len, nv, bl, enc, p);
+                    p += bl;
+                }
+                sink_end_column(sink);
+            }
             if (p > end) rc = COVT_ERR_TRUNCATED;
         }
         free(cols);
@@ -838,7 +896,7 @@ static int byte_rle_span(const uint8_t* b, uint64_t p, uint64_t end, uint32_t n,
 
 /* gen-3: CovtParser.decodeLayerMetadata, CovtParser.java:574-652 (no tile header; loop until EOF :56). */
 static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, const covt_tilejson* tj, uint32_t flags,
-                          uint32_t tile, covt_layer* layers, uint32_t cap, uint32_t* n_layers, uint64_t* end_pos)
+                          uint32_t tile, covt_layer* layers, uint32_t cap, uint32_t* n_layers, uint64_t* end_pos, prop_sink_t* sink)
 {
     cur_t c = {blob, begin, end, 0};
     *n_layers = 0;
@@ -847,6 +905,7 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
         if (*n_layers >= cap) return COVT_ERR_OOM;
         covt_layer* L = &layers[*n_layers];
         layer_init(L, tile, li);
+        sink_set_layer(sink, li);
         uint32_t header = c_byte(&c);
         int optimized = header & 1; /* :575-578 */
         uint32_t n_fields = 0;
@@ -872,6 +931,7 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
         int32_t rc = COVT_OK;
         for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
             int is_id = 0, is_geom = 0;
+            cols[ci].meta_pos = c.p;
             if (optimized || ci == 0) { /* :604-614 */
                 uint32_t column_id = c_varint(&c);
                 if (column_id > 1) {
@@ -932,12 +992,42 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
         for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
             if (cols[ci].kind == COL_ID) place_id(L, &p);
             else if (cols[ci].kind == COL_GEOMETRY) place_geometry(L, &p);
-            else {
+            else if (!sink) {
                 if (cols[ci].data_type != COVT_DT_BOOLEAN) {
                     uint32_t nbytes = (L->num_features + 7) / 8;
                     if (byte_rle_span(blob, p, end, nbytes, &p)) { rc = COVT_ERR_TRUNCATED; break; }
                 }
                 p += cols[ci].listed_bytes;
+            } else {
+                /* the column's metadata once more (it parsed fine a moment ago): its streams in payload order */
+                cur_t m = {blob, cols[ci].meta_pos, end, 0};
+                uint64_t noff = 0; uint32_t nlen = 0;
+                if (optimized || ci == 0) noff = c_varint(&m) - 2; /* index into the TileJSON fields of the layer */
+                else c_string(&m, &noff, &nlen);
+                uint32_t column_desc = c_byte(&m);
+                uint32_t data_type = (column_desc >> 3) & 0xF, column_type = column_desc & 0x7;
+                sink_begin_column(sink, noff, nlen, data_type, column_type, L->num_features);
+                if (data_type != COVT_DT_BOOLEAN) {
+                    uint64_t q = p;
+                    if (byte_rle_span(blob, p, end, (L->num_features + 7) / 8, &q)) { rc = COVT_ERR_TRUNCATED; break; }
+                    sink_stream(sink, COVT_ST_PRESENT, 0, 0, L->num_features, (uint32_t)(q - p), COVT_ENC_BOOLEAN_RLE, p);
+                    p = q;
+                }
+                for (;;) {
+                    uint32_t stream_desc = c_byte(&m);
+                    uint32_t stream_type = stream_desc >> 4;
+                    uint32_t nv = c_varint(&m);
+                    uint32_t bl = c_varint(&m);
+                    /* BOOLEAN data = one bit per FEATURE whatever numValues says (CovtParser.java:280-283) */
+                    sink_stream(sink, stream_type, 0, 0, (data_type == COVT_DT_BOOLEAN && stream_type == COVT_ST_DATA) ? L->num_features : nv, bl,
+                                stream_desc & 0xF, p);
+                    p += bl;
+                    if (m.err) break;
+                    if (data_type == COVT_DT_GEOMETRY && stream_type == COVT_ST_VERTEX_BUFFER) break;
+                    else if (stream_type == COVT_ST_DATA && column_type == COVT_CT_PLAIN) break;
+                    else if (stream_type == COVT_ST_DICTIONARY) break;
+                }
+                sink_end_column(sink);
             }
             if (p > end) rc = COVT_ERR_TRUNCATED;
         }
@@ -958,8 +1048,8 @@ int32_t covt_oracle_parse_tile(const uint8_t* blob, uint64_t begin, uint64_t end
 {
     uint64_t ep = begin;
     int32_t rc;
-    if (container == COVT_CONTAINER_GEN2B) rc = parse_gen2b(blob, begin, end, flags, tile_index, layers, cap, n_layers, &ep);
-    else if (container == COVT_CONTAINER_GEN3) rc = parse_gen3(blob, begin, end, tj, flags, tile_index, layers, cap, n_layers, &ep);
+    if (container == COVT_CONTAINER_GEN2B) rc = parse_gen2b(blob, begin, end, flags, tile_index, layers, cap, n_layers, &ep, NULL);
+    else if (container == COVT_CONTAINER_GEN3) rc = parse_gen3(blob, begin, end, tj, flags, tile_index, layers, cap, n_layers, &ep, NULL);
     else return COVT_ERR_INVALID_ARG;
     if (end_pos) *end_pos = ep;
     return rc;
@@ -1359,10 +1449,17 @@ void covt_oracle_result_free(covt_oracle_result* r)
 }
 
 /* ---------------------------------------------------------------------------------------------
- * Property columns, gen-2b                      J/decoder/CovtParser.java:276-390
- * Layout facts established on the 129 fixtures and pinned on the partner MVT tiles by
- * tests/test_oracle_properties.py (see oracle/properties.py, the first statement of this code):
- * property payloads follow the geometry payload of their layer in column-metadata order.
+ * Property columns                               J/decoder/CovtParser.java:276-390
+ * Layout facts of the gen-2b container established on the 129 fixtures and pinned on the partner MVT tiles by
+ * tests/test_oracle_properties.py (see oracle/properties.py, the first statement of this code): property payloads follow the
+ * geometry payload of their layer in column-metadata order. gen-3 (HEAD): PRESENT streams are not listed
+ * (CovtConverter.java:434-436), BOOLEAN data holds one bit per feature (CovtParser.java:280-290).
+ *
+ * The container walkers above call the sink once per property column, in payload order. Column status = the first failure in
+ * this order: (1) metadata-only checks (missing stream, unsupported type / encoding, a stream that leaves its tile, counts no
+ * codec can reach, FLOAT size mismatch), (2) the dictionary's status, (3) the PRESENT stream (decode + exact consumption),
+ * (4) set bits of the validity bitmap != numValues of the data stream, (5) the DATA stream, (6) a dictionary index outside the
+ * dictionary. Every slice starts on a 16-byte boundary of its buffer, like the result layout of the geometry path.
  * ------------------------------------------------------------------------------------------- */
 typedef struct { void* p; uint64_t n, cap; size_t elem; } vec_t;
 static void* vec_grow(vec_t* v, uint64_t add)
@@ -1380,305 +1477,292 @@ static void* vec_grow(vec_t* v, uint64_t add)
     v->n += add;
     return at;
 }
-
-typedef struct { uint64_t noff; uint32_t nlen; uint32_t nv, bl, enc; uint64_t off; } pstream_t;
-
-/* gen-2 data type byte -> COVT_DT_* */
-static int dt_of_gen2(uint32_t g)
+/* a slice of n elements that starts (and ends) on a 16-byte boundary; returns its element offset */
+static int64_t vec_slice(vec_t* v, uint64_t n)
 {
-    switch (g) {
-    case 0: return COVT_DT_STRING;
-    case 1: return COVT_DT_FLOAT;
-    case 2: return COVT_DT_DOUBLE;
-    case 3: return COVT_DT_INT_64;
-    case 4: return COVT_DT_UINT_64;
-    case 5: return COVT_DT_BOOLEAN;
-    default: return -1;
-    }
+    uint64_t per = 16 / v->elem;
+    uint64_t padded = (n + per - 1) / per * per;
+    uint64_t at = v->n;
+    if (padded && !vec_grow(v, padded)) return -1;
+    return (int64_t)at;
 }
 
-static uint32_t popcount_bits(const uint8_t* b, uint32_t n_bits)
-{
-    uint32_t c = 0;
-    for (uint32_t i = 0; i < n_bits; i++) c += (b[i >> 3] >> (i & 7)) & 1u;
-    return c;
-}
-
+typedef struct { uint64_t off; uint32_t nv, bl, enc; int have; } ps_t;
+typedef struct { uint32_t st_present, st_data, fill_ones, present_decoded; } paux_t;
 typedef struct {
-    vec_t cols, dicts, validity, i64, f32, f64, bools, didx, doff;
+    vec_t cols, aux, dicts, dict_st, validity, i64, f32, f64, bools, didx, doff;
+    int oom;
 } props_build_t;
 
-/* present stream: BOOLEAN_RLE = Byte-RLE of ceil(F / 8) bitset bytes (CovtParser.java:295-296) */
-static int32_t prop_bitset(const uint8_t* blob, const pstream_t* s, uint32_t n_bits, vec_t* dst, uint64_t* at)
+struct prop_sink {
+    const uint8_t* blob;
+    uint64_t tile_end;
+    uint32_t tile;
+    int gen3;
+    props_build_t* B;
+    uint32_t layer, F, dt, ct, nlen, dict_index;
+    uint64_t noff;
+    int has_dict, localized;
+    ps_t P, D, L, Y, pend;
+    uint64_t pend_sub_off;
+    uint32_t pend_sub_len;
+};
+
+static int ps_in_tile(const prop_sink_t* k, const ps_t* s) { return s->off <= k->tile_end && (uint64_t)s->bl <= k->tile_end - s->off; }
+
+/* decode + exact consumption of one Byte-RLE stream into out[n] */
+static uint32_t prop_byte_rle(const uint8_t* blob, const ps_t* s, uint32_t n, uint8_t* out)
 {
-    uint32_t nbytes = (n_bits + 7) / 8;
-    *at = dst->n;
-    uint8_t* out = (uint8_t*)vec_grow(dst, nbytes);
-    if (!out && nbytes) return COVT_ERR_OOM;
     uint64_t pos = s->off;
-    int32_t rc = covt_oracle_decode_byte_rle(blob, s->off + s->bl, &pos, nbytes, out);
-    if (rc != COVT_OK) return rc;
+    int32_t rc = covt_oracle_decode_byte_rle(blob, s->off + s->bl, &pos, n, out);
+    if (rc != COVT_OK) return (uint32_t)rc;
+    return pos == s->off + s->bl ? COVT_OK : COVT_ERR_COUNT_MISMATCH;
+}
+/* decode + exact consumption of one RLE stream; out64 (n values) or out32 (narrowed like the Java (int) casts, :357, :383) */
+static uint32_t prop_rle(const uint8_t* blob, const ps_t* s, uint32_t n, int is_signed, int64_t* out64, int32_t* out32)
+{
+    int64_t* tmp = out64 ? out64 : (int64_t*)malloc(((size_t)n + 1) * sizeof(int64_t));
+    if (!tmp) return COVT_ERR_OOM;
+    uint64_t pos = s->off;
+    int32_t rc = covt_oracle_decode_rle(blob, s->off + s->bl, &pos, n, is_signed, tmp);
+    if (out32) for (uint32_t i = 0; i < n; i++) out32[i] = (int32_t)(uint32_t)(uint64_t)tmp[i];
+    if (!out64) free(tmp);
+    if (rc != COVT_OK) return (uint32_t)rc;
     return pos == s->off + s->bl ? COVT_OK : COVT_ERR_COUNT_MISMATCH;
 }
 
-static int32_t prop_rle(const uint8_t* blob, const pstream_t* s, int is_signed, int64_t* out)
+static void prop_emit(prop_sink_t* k, const ps_t* Ps, const ps_t* Ds, uint64_t sub_off, uint32_t sub_len, int orphan)
 {
-    uint64_t pos = s->off;
-    int32_t rc = covt_oracle_decode_rle(blob, s->off + s->bl, &pos, s->nv, is_signed, out);
-    if (rc != COVT_OK) return rc;
-    return pos == s->off + s->bl ? COVT_OK : COVT_ERR_COUNT_MISMATCH;
-}
+    props_build_t* B = k->B;
+    uint32_t st = COVT_OK, kind = COVT_PV_NONE, F = k->F, dt = k->dt, ct = k->ct;
+    uint32_t VB = (F + 7u) / 8u;
+    int use_p = 0, fill_ones = 0;
+    if (orphan || dt == 0xFFu || ct > COVT_CT_ICE_MORTON_CODE || !Ds->have) st = COVT_ERR_BAD_METADATA;
+    else if (dt == COVT_DT_BOOLEAN) {
+        kind = COVT_PV_BOOL;
+        if (!ps_in_tile(k, Ds) || (Ps->have && !ps_in_tile(k, Ps))) st = COVT_ERR_TRUNCATED;
+        else if (!plausible_count((Ds->nv + 7u) / 8u, Ds->bl)) st = COVT_ERR_TRUNCATED;
+        else if (Ps->have) { if (!plausible_count(VB, Ps->bl)) st = COVT_ERR_TRUNCATED; else use_p = 1; }
+        else if (Ds->nv != F) st = COVT_ERR_COUNT_MISMATCH; /* no present stream: every feature has a value (:280-290) */
+        else fill_ones = 1;
+    } else if (!Ps->have) st = COVT_ERR_BAD_METADATA;
+    else if (dt == COVT_DT_STRING) {
+        kind = COVT_PV_DICT_INDEX;
+        if (!k->has_dict) st = COVT_ERR_UNSUPPORTED_ENCODING; /* CovtParser.java:345-347 */
+        else if (!k->localized && (!k->L.have || !k->Y.have)) st = COVT_ERR_BAD_METADATA;
+        else if (!ps_in_tile(k, Ps) || !ps_in_tile(k, Ds) || !plausible_count(VB, Ps->bl) || !plausible_count(Ds->nv, Ds->bl)) st = COVT_ERR_TRUNCATED;
+        use_p = 1;
+    } else if (dt == COVT_DT_INT_64 || dt == COVT_DT_UINT_64) {
+        kind = COVT_PV_I64;
+        if (Ds->enc != COVT_ENC_RLE && Ds->enc != COVT_ENC_VARINT_ZIG_ZAG && Ds->enc != COVT_ENC_VARINT_DELTA_ZIG_ZAG && Ds->enc != COVT_ENC_VARINT)
+            st = COVT_ERR_UNSUPPORTED_ENCODING; /* :313-315 */
+        else if (!ps_in_tile(k, Ps) || !ps_in_tile(k, Ds) || !plausible_count(VB, Ps->bl) || !plausible_count(Ds->nv, Ds->bl)) st = COVT_ERR_TRUNCATED;
+        use_p = 1;
+    } else if (dt == COVT_DT_FLOAT || dt == COVT_DT_DOUBLE) {
+        uint32_t es = dt == COVT_DT_FLOAT ? 4u : 8u;
+        kind = dt == COVT_DT_FLOAT ? COVT_PV_F32 : COVT_PV_F64;
+        if (!ps_in_tile(k, Ps) || !ps_in_tile(k, Ds) || !plausible_count(VB, Ps->bl)) st = COVT_ERR_TRUNCATED;
+        else if ((uint64_t)Ds->nv * es != Ds->bl) st = COVT_ERR_COUNT_MISMATCH;
+        use_p = 1;
+    } else st = COVT_ERR_UNSUPPORTED_ENCODING; /* "Data type not supported", :368-370 */
 
-static const pstream_t* find_stream(const uint8_t* blob, const pstream_t* ss, uint32_t n, const char* name)
-{
-    for (uint32_t i = 0; i < n; i++)
-        if (name_is(blob, ss[i].noff, ss[i].nlen, name)) return &ss[i];
-    return NULL;
-}
-
-static covt_prop_column* new_column(props_build_t* B, uint32_t tile, uint32_t layer, uint64_t noff, uint32_t nlen, int dt, uint32_t ct, uint32_t F)
-{
     covt_prop_column* c = (covt_prop_column*)vec_grow(&B->cols, 1);
-    if (!c) return NULL;
-    c->tile = tile;
-    c->layer = layer;
-    c->name_offset = noff;
-    c->name_length = nlen;
+    paux_t* a = (paux_t*)vec_grow(&B->aux, 1);
+    if (!c || !a) { B->oom = 1; return; }
+    c->tile = k->tile;
+    c->layer = k->layer;
+    c->name_offset = k->noff;
+    c->name_length = k->nlen;
+    c->sub_offset = sub_len ? sub_off : 0;
+    c->sub_length = sub_len;
     c->data_type = (uint8_t)dt;
     c->column_type = (uint8_t)ct;
+    c->value_kind = (uint8_t)kind;
+    c->status = st;
     c->num_features = F;
-    return c;
-}
-
-/* RLE dictionary indices of the present features -> dict_index arena (CovtParser.java:350-365) */
-static int32_t prop_indices(const uint8_t* blob, props_build_t* B, covt_prop_column* c, const pstream_t* present, const pstream_t* data,
-                            uint32_t n_dict)
-{
-    c->value_kind = COVT_PV_DICT_INDEX;
-    int32_t rc = prop_bitset(blob, present, c->num_features, &B->validity, &c->validity_offset);
-    if (rc != COVT_OK) return rc;
-    c->num_values = popcount_bits((const uint8_t*)B->validity.p + c->validity_offset, c->num_features);
-    if (data->nv != c->num_values) return COVT_ERR_COUNT_MISMATCH;
-    int64_t* tmp = (int64_t*)malloc(((size_t)data->nv + 1) * sizeof(int64_t));
-    if (!tmp) return COVT_ERR_OOM;
-    rc = prop_rle(blob, data, 0, tmp);
-    c->values_offset = B->didx.n;
-    int32_t* out = (int32_t*)vec_grow(&B->didx, data->nv);
-    if (rc == COVT_OK && !out && data->nv) rc = COVT_ERR_OOM;
-    for (uint32_t i = 0; rc == COVT_OK && i < data->nv; i++) {
-        if (tmp[i] < 0 || (uint64_t)tmp[i] >= n_dict) rc = COVT_ERR_TOPOLOGY; /* Java: ArrayIndexOutOfBounds on dictionaryData[index] */
-        else out[i] = (int32_t)tmp[i];
+    c->dictionary = kind == COVT_PV_DICT_INDEX ? k->dict_index : 0;
+    c->validity_offset = B->validity.n;
+    vec_t* vb = kind == COVT_PV_BOOL ? &B->bools : kind == COVT_PV_DICT_INDEX ? &B->didx : kind == COVT_PV_I64 ? &B->i64 :
+                kind == COVT_PV_F32 ? &B->f32 : kind == COVT_PV_F64 ? &B->f64 : NULL;
+    c->values_offset = vb ? vb->n : 0;
+    if (st != COVT_OK) return;
+    c->data_num_values = Ds->nv;
+    const uint8_t* blob = k->blob;
+    int64_t v_at = vec_slice(&B->validity, VB);
+    uint64_t n_alloc = kind == COVT_PV_BOOL ? (Ds->nv + 7u) / 8u : Ds->nv;
+    int64_t d_at = vec_slice(vb, n_alloc);
+    if (v_at < 0 || d_at < 0) { B->oom = 1; c->status = COVT_ERR_OOM; return; }
+    a->fill_ones = (uint32_t)fill_ones;
+    if (use_p) {
+        a->st_present = prop_byte_rle(blob, Ps, VB, (uint8_t*)B->validity.p + v_at);
+        a->present_decoded = 1;
     }
-    free(tmp);
-    return rc;
-}
-
-/* length (RLE) + dictionary (UTF-8 bytes) -> dictionaries[], dict_offsets (CovtParser.java:379-390) */
-static int32_t prop_dictionary(const uint8_t* blob, props_build_t* B, uint32_t tile, uint32_t layer, const pstream_t* length, const pstream_t* dict,
-                               uint32_t* index)
-{
-    *index = (uint32_t)B->dicts.n;
-    covt_prop_dictionary* d = (covt_prop_dictionary*)vec_grow(&B->dicts, 1);
-    if (!d) return COVT_ERR_OOM;
-    d->tile = tile;
-    d->layer = layer;
-    d->n_entries = length->nv;
-    d->bytes_offset = dict->off;
-    d->n_bytes = dict->bl;
-    d->offsets_offset = B->doff.n;
-    int64_t* tmp = (int64_t*)malloc(((size_t)length->nv + 1) * sizeof(int64_t));
-    if (!tmp) return COVT_ERR_OOM;
-    int32_t rc = prop_rle(blob, length, 0, tmp);
-    int32_t* off = (int32_t*)vec_grow(&B->doff, (uint64_t)length->nv + 1);
-    if (rc == COVT_OK && !off) rc = COVT_ERR_OOM;
-    uint64_t run = 0;
-    for (uint32_t i = 0; rc == COVT_OK && i < length->nv; i++) {
-        if (tmp[i] < 0 || run + (uint64_t)tmp[i] > dict->bl) rc = COVT_ERR_TRUNCATED;
-        else { off[i] = (int32_t)run; run += (uint64_t)tmp[i]; }
-    }
-    if (rc == COVT_OK) {
-        off[length->nv] = (int32_t)run;
-        if (run != dict->bl) rc = COVT_ERR_COUNT_MISMATCH;
-    }
-    free(tmp);
-    return rc;
-}
-
-static int32_t prop_column(const uint8_t* blob, props_build_t* B, uint32_t tile, uint32_t layer, uint64_t noff, uint32_t nlen, int dt, uint32_t ct,
-                           uint32_t F, const pstream_t* ss, uint32_t n_streams)
-{
-    const pstream_t* present = find_stream(blob, ss, n_streams, "present");
-    const pstream_t* data = find_stream(blob, ss, n_streams, "data");
-    if (dt == COVT_DT_STRING && ct == COVT_CT_LOCALIZED_DICTIONARY) {
-        const pstream_t* length = find_stream(blob, ss, n_streams, "length");
-        const pstream_t* dict = find_stream(blob, ss, n_streams, "dictionary");
-        if (!length || !dict) return COVT_ERR_BAD_METADATA;
-        uint32_t di;
-        int32_t rc = prop_dictionary(blob, B, tile, layer, length, dict, &di);
-        /* pairs (present_<s>, <s>) in listed order */
-        for (uint32_t i = 0; i + 1 < n_streams; i++) {
-            const pstream_t* p = &ss[i];
-            if (p->nlen <= 8 || memcmp(blob + p->noff, "present_", 8) != 0) continue;
-            const pstream_t* sub = NULL;
-            for (uint32_t k = 0; k < n_streams; k++)
-                if (ss[k].nlen == p->nlen - 8 && memcmp(blob + ss[k].noff, blob + p->noff + 8, ss[k].nlen) == 0) { sub = &ss[k]; break; }
-            covt_prop_column* c = new_column(B, tile, layer, noff, nlen, dt, ct, F);
-            if (!c) return COVT_ERR_OOM;
-            c->sub_offset = p->noff + 8;
-            c->sub_length = p->nlen - 8;
-            c->dictionary = di;
-            c->status = rc != COVT_OK ? (uint32_t)rc : (sub ? (uint32_t)prop_indices(blob, B, c, p, sub, length->nv) : COVT_ERR_BAD_METADATA);
-        }
-        return COVT_OK;
-    }
-    covt_prop_column* c = new_column(B, tile, layer, noff, nlen, dt, ct, F);
-    if (!c) return COVT_ERR_OOM;
-    if (!data) { c->status = COVT_ERR_BAD_METADATA; return COVT_OK; }
-    int32_t rc = COVT_OK;
-    if (dt == COVT_DT_BOOLEAN) {
-        /* HEAD: data = bitset over all features, no present stream (CovtParser.java:280-290). The gen-2b fixtures list a present
-         * stream for most boolean columns; data then holds one bit per PRESENT feature (dense, like every other type). */
-        c->value_kind = COVT_PV_BOOL;
-        rc = prop_bitset(blob, data, data->nv, &B->bools, &c->values_offset);
-        if (rc == COVT_OK) {
-            if (present) rc = prop_bitset(blob, present, F, &B->validity, &c->validity_offset);
-            else {
-                c->validity_offset = B->validity.n;
-                uint8_t* v = (uint8_t*)vec_grow(&B->validity, (F + 7) / 8);
-                if (!v && F) rc = COVT_ERR_OOM;
-                for (uint32_t i = 0; rc == COVT_OK && i < F; i++) v[i >> 3] |= (uint8_t)(1u << (i & 7));
-            }
-        }
-        if (rc == COVT_OK) {
-            c->num_values = popcount_bits((const uint8_t*)B->validity.p + c->validity_offset, F);
-            if (data->nv != c->num_values) rc = COVT_ERR_COUNT_MISMATCH;
-        }
-        c->status = (uint32_t)rc;
-        return COVT_OK;
-    }
-    if (!present) { c->status = COVT_ERR_BAD_METADATA; return COVT_OK; }
-    if (dt == COVT_DT_STRING) {
-        if (ct != COVT_CT_DICTIONARY) { c->status = COVT_ERR_UNSUPPORTED_ENCODING; return COVT_OK; } /* CovtParser.java:345-347 */
-        const pstream_t* length = find_stream(blob, ss, n_streams, "length");
-        const pstream_t* dict = find_stream(blob, ss, n_streams, "dictionary");
-        if (!length || !dict) { c->status = COVT_ERR_BAD_METADATA; return COVT_OK; }
-        rc = prop_dictionary(blob, B, tile, layer, length, dict, &c->dictionary);
-        if (rc == COVT_OK) rc = prop_indices(blob, B, c, present, data, length->nv);
-        c->status = (uint32_t)rc;
-        return COVT_OK;
-    }
-    rc = prop_bitset(blob, present, F, &B->validity, &c->validity_offset);
-    if (rc == COVT_OK) {
-        c->num_values = popcount_bits((const uint8_t*)B->validity.p + c->validity_offset, F);
-        if (data->nv != c->num_values) rc = COVT_ERR_COUNT_MISMATCH;
-    }
-    if (rc == COVT_OK && (dt == COVT_DT_INT_64 || dt == COVT_DT_UINT_64)) {
-        c->value_kind = COVT_PV_I64;
-        c->values_offset = B->i64.n;
-        int64_t* out = (int64_t*)vec_grow(&B->i64, data->nv);
-        if (!out && data->nv) rc = COVT_ERR_OOM;
-        else if (data->enc == COVT_ENC_RLE) rc = prop_rle(blob, data, dt == COVT_DT_INT_64, out); /* :299-301 */
-        else if (data->enc == COVT_ENC_VARINT_ZIG_ZAG || data->enc == COVT_ENC_VARINT_DELTA_ZIG_ZAG || data->enc == COVT_ENC_VARINT) {
-            /* int varints widened to long (CovtParser.java:303-311, "TODO: refactor to use long instead of int") */
-            int32_t* tmp = (int32_t*)malloc(((size_t)data->nv + 1) * sizeof(int32_t));
-            uint64_t pos = data->off;
-            int overlong = 0;
-            if (!tmp) rc = COVT_ERR_OOM;
-            else if (data->enc == COVT_ENC_VARINT_ZIG_ZAG) rc = covt_oracle_decode_zigzag_varint(blob, data->off + data->bl, &pos, data->nv, tmp, &overlong);
-            else if (data->enc == COVT_ENC_VARINT_DELTA_ZIG_ZAG) rc = covt_oracle_decode_zigzag_delta_varint(blob, data->off + data->bl, &pos, data->nv, tmp, &overlong);
-            else rc = covt_oracle_decode_varint(blob, data->off + data->bl, &pos, data->nv, tmp, &overlong);
-            if (rc == COVT_OK && pos != data->off + data->bl) rc = COVT_ERR_COUNT_MISMATCH;
-            if (rc == COVT_OK && overlong) rc = COVT_ERR_VARINT_OVERLONG;
-            for (uint32_t i = 0; tmp && i < data->nv; i++) out[i] = (int64_t)tmp[i];
-            free(tmp);
-        } else rc = COVT_ERR_UNSUPPORTED_ENCODING; /* :313-315 */
-    } else if (rc == COVT_OK && (dt == COVT_DT_FLOAT || dt == COVT_DT_DOUBLE)) {
-        /* DecodingUtils.decodeFloatsLE :446-453: little-endian IEEE values of the present features */
-        const uint32_t es = dt == COVT_DT_FLOAT ? 4u : 8u;
-        c->value_kind = dt == COVT_DT_FLOAT ? COVT_PV_F32 : COVT_PV_F64;
-        vec_t* dst = dt == COVT_DT_FLOAT ? &B->f32 : &B->f64;
-        c->values_offset = dst->n;
-        if ((uint64_t)data->nv * es != data->bl) rc = COVT_ERR_COUNT_MISMATCH;
+    if (kind == COVT_PV_BOOL) a->st_data = prop_byte_rle(blob, Ds, (Ds->nv + 7u) / 8u, (uint8_t*)B->bools.p + d_at);
+    else if (kind == COVT_PV_DICT_INDEX) a->st_data = prop_rle(blob, Ds, Ds->nv, 0, NULL, (int32_t*)B->didx.p + d_at);
+    else if (kind == COVT_PV_I64) {
+        int64_t* out = (int64_t*)B->i64.p + d_at;
+        if (Ds->enc == COVT_ENC_RLE) a->st_data = prop_rle(blob, Ds, Ds->nv, dt == COVT_DT_INT_64, out, NULL); /* :299-301 */
         else {
-            void* out = vec_grow(dst, data->nv);
-            if (!out && data->nv) rc = COVT_ERR_OOM;
-            else memcpy(out, blob + data->off, data->bl); /* the hosts this runs on are little-endian */
+            /* int varints widened to long (CovtParser.java:303-311, "TODO: refactor to use long instead of int") */
+            int32_t* tmp = (int32_t*)malloc(((size_t)Ds->nv + 1) * sizeof(int32_t));
+            uint64_t pos = Ds->off;
+            int overlong = 0;
+            int32_t rc;
+            if (!tmp) { B->oom = 1; return; }
+            if (Ds->enc == COVT_ENC_VARINT_ZIG_ZAG) rc = covt_oracle_decode_zigzag_varint(blob, Ds->off + Ds->bl, &pos, Ds->nv, tmp, &overlong);
+            else if (Ds->enc == COVT_ENC_VARINT_DELTA_ZIG_ZAG) rc = covt_oracle_decode_zigzag_delta_varint(blob, Ds->off + Ds->bl, &pos, Ds->nv, tmp, &overlong);
+            else rc = covt_oracle_decode_varint(blob, Ds->off + Ds->bl, &pos, Ds->nv, tmp, &overlong);
+            if (rc == COVT_OK && pos != Ds->off + Ds->bl) rc = COVT_ERR_COUNT_MISMATCH;
+            if (rc == COVT_OK && overlong) rc = COVT_ERR_VARINT_OVERLONG;
+            for (uint32_t i = 0; i < Ds->nv; i++) out[i] = (int64_t)tmp[i];
+            free(tmp);
+            a->st_data = (uint32_t)rc;
         }
-    } else if (rc == COVT_OK) rc = COVT_ERR_UNSUPPORTED_ENCODING; /* "Data type not supported", :368-370 */
-    c->status = (uint32_t)rc;
-    return COVT_OK;
-}
-
-static int32_t props_of_tile(const uint8_t* blob, uint64_t begin, uint64_t end, uint32_t tile, props_build_t* B)
-{
-    cur_t c = {blob, begin, end, 0};
-    (void)c_varint(&c);
-    uint32_t num_layers = c_varint(&c);
-    if (c.err) return COVT_ERR_TRUNCATED;
-    for (uint32_t li = 0; li < num_layers; li++) {
-        uint64_t loff; uint32_t llen;
-        c_string(&c, &loff, &llen);
-        (void)c_varint(&c); /* extent */
-        uint32_t F = c_varint(&c);
-        uint32_t n_cols = c_varint(&c);
-        if (c.err) return COVT_ERR_TRUNCATED;
-        /* metadata of all columns first (the payload follows the whole layer header) */
-        typedef struct { uint64_t noff; uint32_t nlen, dt, ct, first, n; int is_id, is_geom; } pcol_t;
-        pcol_t* cols = (pcol_t*)calloc((size_t)n_cols + 1, sizeof(pcol_t));
-        vec_t streams = {NULL, 0, 0, sizeof(pstream_t)};
-        int32_t rc = cols ? COVT_OK : COVT_ERR_OOM;
-        for (uint32_t ci = 0; rc == COVT_OK && ci < n_cols; ci++) {
-            pcol_t* pc = &cols[ci];
-            c_string(&c, &pc->noff, &pc->nlen);
-            pc->dt = c_byte(&c);
-            pc->ct = c_byte(&c);
-            pc->n = c_varint(&c);
-            if (c.err) { rc = COVT_ERR_TRUNCATED; break; }
-            pc->is_id = ci == 0 && name_is(blob, pc->noff, pc->nlen, "id");
-            pc->is_geom = pc->dt == 6;
-            pc->first = (uint32_t)streams.n;
-            for (uint32_t si = 0; si < pc->n; si++) {
-                pstream_t* s = (pstream_t*)vec_grow(&streams, 1);
-                if (!s) { rc = COVT_ERR_OOM; break; }
-                c_string(&c, &s->noff, &s->nlen);
-                s->nv = c_varint(&c);
-                s->bl = c_varint(&c);
-                s->enc = c_byte(&c);
-                if (c.err) { rc = COVT_ERR_TRUNCATED; break; }
-            }
-        }
-        /* payload offsets: [id] | geometry (any order: only its total matters here) | property columns in metadata order */
-        uint64_t p = c.p;
-        for (uint32_t ci = 0; rc == COVT_OK && ci < n_cols; ci++)
-            for (uint32_t si = 0; si < cols[ci].n; si++) {
-                pstream_t* s = (pstream_t*)streams.p + cols[ci].first + si;
-                s->off = p;
-                p += s->bl;
-                if (p > end) { rc = COVT_ERR_TRUNCATED; break; }
-            }
-        for (uint32_t ci = 0; rc == COVT_OK && ci < n_cols; ci++) {
-            const pcol_t* pc = &cols[ci];
-            if (pc->is_id || pc->is_geom) continue;
-            int dt = dt_of_gen2(pc->dt);
-            if (dt < 0 || pc->ct > COVT_CT_ICE_MORTON_CODE) { rc = COVT_ERR_BAD_METADATA; break; }
-            rc = prop_column(blob, B, tile, li, pc->noff, pc->nlen, dt, pc->ct, F, (const pstream_t*)streams.p + pc->first, pc->n);
-        }
-        free(cols);
-        free(streams.p);
-        if (rc != COVT_OK) return rc;
-        c.p = p;
+    } else {
+        /* DecodingUtils.decodeFloatsLE :446-453: little-endian IEEE values of the present features (the hosts this runs on are little-endian) */
+        memcpy((uint8_t*)vb->p + (size_t)d_at * vb->elem, blob + Ds->off, Ds->bl);
     }
-    return c.p == end ? COVT_OK : COVT_ERR_TRUNCATED;
 }
 
-int32_t covt_oracle_decode_properties(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, covt_oracle_props** out)
+static void prop_emit_dictionary(prop_sink_t* k)
+{
+    props_build_t* B = k->B;
+    covt_prop_dictionary* d = (covt_prop_dictionary*)B->dicts.p + k->dict_index;
+    uint32_t* lst = (uint32_t*)B->dict_st.p + k->dict_index;
+    uint32_t st = COVT_OK, n = 0;
+    if (!k->L.have || !k->Y.have) st = COVT_ERR_BAD_METADATA;
+    else if (!ps_in_tile(k, &k->L) || !ps_in_tile(k, &k->Y)) st = COVT_ERR_TRUNCATED;
+    else {
+        n = k->gen3 ? k->Y.nv : k->L.nv; /* CovtParser.java:352: the DICTIONARY stream's numValues counts the entries */
+        if (!plausible_count(n, k->L.bl)) { st = COVT_ERR_TRUNCATED; n = 0; }
+    }
+    d->n_entries = n;
+    d->status = st;
+    d->offsets_offset = B->doff.n;
+    d->bytes_offset = st == COVT_OK ? k->Y.off : 0;
+    d->n_bytes = st == COVT_OK ? k->Y.bl : 0;
+    if (st != COVT_OK) return;
+    int64_t at = vec_slice(&B->doff, (uint64_t)n + 1);
+    if (at < 0) { B->oom = 1; d->status = COVT_ERR_OOM; return; }
+    *lst = prop_rle(k->blob, &k->L, n, 0, NULL, (int32_t*)B->doff.p + at + 1);
+}
+
+static void sink_set_layer(prop_sink_t* k, uint32_t li) { if (k) k->layer = li; }
+static void sink_begin_column(prop_sink_t* k, uint64_t noff, uint32_t nlen, uint32_t dt, uint32_t ct, uint32_t F)
+{
+    k->noff = noff; k->nlen = nlen; k->dt = dt; k->ct = ct; k->F = F;
+    k->P.have = k->D.have = k->L.have = k->Y.have = k->pend.have = 0;
+    k->has_dict = dt == COVT_DT_STRING && (ct == COVT_CT_DICTIONARY || ct == COVT_CT_LOCALIZED_DICTIONARY);
+    k->localized = dt == COVT_DT_STRING && ct == COVT_CT_LOCALIZED_DICTIONARY;
+    if (k->has_dict) {
+        /* the record exists from here on (sub-columns refer to it); it stays BAD_METADATA if the walk never ends the column */
+        k->dict_index = (uint32_t)k->B->dicts.n;
+        covt_prop_dictionary* d = (covt_prop_dictionary*)vec_grow(&k->B->dicts, 1);
+        uint32_t* lst = (uint32_t*)vec_grow(&k->B->dict_st, 1);
+        if (!d || !lst) { k->B->oom = 1; k->has_dict = 0; return; }
+        d->tile = k->tile;
+        d->layer = k->layer;
+        d->status = COVT_ERR_BAD_METADATA;
+    }
+}
+static void sink_stream(prop_sink_t* k, uint32_t st, uint64_t sub_off, uint32_t sub_len, uint32_t nv, uint32_t bl, uint32_t enc, uint64_t off)
+{
+    ps_t s = {off, nv, bl, enc, 1};
+    if (sub_len == 0) { /* present / data / length / dictionary: the first of each counts */
+        if (st == COVT_ST_PRESENT) { if (!k->P.have) k->P = s; }
+        else if (st == COVT_ST_DATA) { if (!k->D.have) k->D = s; }
+        else if (st == COVT_ST_LENGTH) { if (!k->L.have) k->L = s; }
+        else if (st == COVT_ST_DICTIONARY) { if (!k->Y.have) k->Y = s; }
+        return;
+    }
+    if (!k->localized) return; /* a stray named stream of a plain column: hopped over */
+    /* localized dictionary (gen-2b fixtures): pairs (present_<s>, <s>), adjacent, sharing the column's dictionary */
+    if (st == COVT_ST_PRESENT) {
+        if (k->pend.have) prop_emit(k, &k->pend, &k->pend, k->pend_sub_off, k->pend_sub_len, 1); /* no partner */
+        k->pend = s;
+        k->pend_sub_off = sub_off;
+        k->pend_sub_len = sub_len;
+        return;
+    }
+    if (!k->pend.have || k->pend_sub_len != sub_len || memcmp(k->blob + k->pend_sub_off, k->blob + sub_off, sub_len) != 0) return;
+    prop_emit(k, &k->pend, &s, k->pend_sub_off, k->pend_sub_len, 0);
+    k->pend.have = 0;
+}
+static void sink_end_column(prop_sink_t* k)
+{
+    if (k->localized) {
+        if (k->pend.have) prop_emit(k, &k->pend, &k->pend, k->pend_sub_off, k->pend_sub_len, 1);
+    } else prop_emit(k, &k->P, &k->D, 0, 0, 0);
+    if (k->has_dict) prop_emit_dictionary(k);
+}
+
+/* after every tile: dictionary offsets, then column statuses in the documented order */
+static void props_finish(props_build_t* B)
+{
+    covt_prop_dictionary* dicts = (covt_prop_dictionary*)B->dicts.p;
+    for (uint64_t i = 0; i < B->dicts.n; i++) {
+        covt_prop_dictionary* d = &dicts[i];
+        if (d->status != COVT_OK) continue;
+        uint32_t st = ((uint32_t*)B->dict_st.p)[i];
+        if (st == COVT_OK) {
+            int32_t* off = (int32_t*)B->doff.p + d->offsets_offset;
+            uint64_t run = 0;
+            int bad = 0;
+            for (uint32_t e = 0; e < d->n_entries; e++) {
+                int32_t len = off[e + 1]; /* (int)lengthStream[i], CovtParser.java:383 */
+                if (len < 0) { bad = 1; len = 0; }
+                run += (uint64_t)len;
+                if (run > d->n_bytes) bad = 1;
+                off[e + 1] = (int32_t)run;
+            }
+            off[0] = 0;
+            if (bad) st = COVT_ERR_TRUNCATED; /* a string would run past the dictionary bytes */
+            else if (run != d->n_bytes) st = COVT_ERR_COUNT_MISMATCH;
+        }
+        d->status = st;
+    }
+    covt_prop_column* cols = (covt_prop_column*)B->cols.p;
+    for (uint64_t i = 0; i < B->cols.n; i++) {
+        covt_prop_column* c = &cols[i];
+        const paux_t* a = (const paux_t*)B->aux.p + i;
+        if (c->status != COVT_OK) continue;
+        uint32_t st = COVT_OK, n_valid = 0, n_entries = 0, F = c->num_features, VB = (F + 7u) / 8u;
+        int present_ok = 1;
+        uint8_t* validity = (uint8_t*)B->validity.p + c->validity_offset;
+        if (c->value_kind == COVT_PV_DICT_INDEX) { st = dicts[c->dictionary].status; n_entries = dicts[c->dictionary].n_entries; }
+        if (a->fill_ones) {
+            for (uint32_t b = 0; b < F; b++) validity[b >> 3] |= (uint8_t)(1u << (b & 7));
+            n_valid = F;
+        } else if (a->st_present != COVT_OK) {
+            present_ok = 0;
+            if (st == COVT_OK) st = a->st_present;
+        } else {
+            for (uint32_t b = 0; b < F; b++) n_valid += (validity[b >> 3] >> (b & 7)) & 1u;
+        }
+        (void)VB;
+        if (st == COVT_OK && n_valid != c->data_num_values) st = COVT_ERR_COUNT_MISMATCH;
+        if (st == COVT_OK && a->st_data != COVT_OK) st = a->st_data;
+        if (st == COVT_OK && c->value_kind == COVT_PV_DICT_INDEX) {
+            const int32_t* idx = (const int32_t*)B->didx.p + c->values_offset;
+            for (uint32_t v = 0; v < c->data_num_values; v++)
+                if (idx[v] < 0 || (uint32_t)idx[v] >= n_entries) { st = COVT_ERR_TOPOLOGY; break; } /* ArrayIndexOutOfBounds, :357-358 */
+        }
+        c->status = st;
+        c->num_values = present_ok ? n_valid : 0;
+    }
+}
+
+int32_t covt_oracle_decode_properties(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                                      const covt_tilejson* tj, uint32_t flags, covt_oracle_props** out)
 {
     covt_oracle_props* R = (covt_oracle_props*)calloc(1, sizeof(covt_oracle_props));
     if (!R) return COVT_ERR_OOM;
     props_build_t B;
     memset(&B, 0, sizeof(B));
     B.cols.elem = sizeof(covt_prop_column);
+    B.aux.elem = sizeof(paux_t);
     B.dicts.elem = sizeof(covt_prop_dictionary);
+    B.dict_st.elem = sizeof(uint32_t);
     B.validity.elem = 1;
     B.i64.elem = sizeof(int64_t);
     B.f32.elem = sizeof(float);
@@ -1688,8 +1772,42 @@ int32_t covt_oracle_decode_properties(const uint8_t* blob, const uint64_t* tile_
     B.doff.elem = sizeof(int32_t);
     R->n_tiles = n_tiles;
     R->tile_status = (uint32_t*)calloc((size_t)n_tiles + 1, sizeof(uint32_t));
-    for (uint32_t t = 0; t < n_tiles; t++)
-        R->tile_status[t] = (uint32_t)props_of_tile(blob, tile_offsets[t], tile_offsets[t + 1], t, &B);
+    uint32_t cap = 4096;
+    covt_layer* layers = (covt_layer*)malloc(cap * sizeof(covt_layer));
+    int32_t rc = (R->tile_status && layers) ? COVT_OK : COVT_ERR_OOM;
+    for (uint32_t t = 0; rc == COVT_OK && t < n_tiles; t++) {
+        prop_sink_t k;
+        memset(&k, 0, sizeof(k));
+        k.blob = blob;
+        k.tile_end = tile_offsets[t + 1];
+        k.tile = t;
+        k.gen3 = container == COVT_CONTAINER_GEN3;
+        k.B = &B;
+        uint32_t nl = 0;
+        uint64_t ep = 0;
+        int32_t st;
+        for (;;) {
+            uint64_t n_cols0 = B.cols.n, n_dicts0 = B.dicts.n;
+            if (container == COVT_CONTAINER_GEN2B) st = parse_gen2b(blob, tile_offsets[t], tile_offsets[t + 1], flags, t, layers, cap, &nl, &ep, &k);
+            else if (container == COVT_CONTAINER_GEN3) st = parse_gen3(blob, tile_offsets[t], tile_offsets[t + 1], tj, flags, t, layers, cap, &nl, &ep, &k);
+            else { st = COVT_ERR_INVALID_ARG; rc = st; }
+            if (st != COVT_ERR_OOM || cap >= (1u << 24) || B.oom) break;
+            /* more layers than the scratch table holds: grow it and walk the tile again (its columns so far are dropped; the value
+             * arenas keep the abandoned slices, which nothing refers to) */
+            B.cols.n = n_cols0; B.aux.n = n_cols0; B.dicts.n = n_dicts0; B.dict_st.n = n_dicts0;
+            cap *= 4;
+            free(layers);
+            layers = (covt_layer*)malloc((size_t)cap * sizeof(covt_layer));
+            if (!layers) { rc = COVT_ERR_OOM; break; }
+        }
+        if (st == COVT_OK && container == COVT_CONTAINER_GEN2B && ep != tile_offsets[t + 1]) st = COVT_ERR_TRUNCATED;
+        R->tile_status[t] = (uint32_t)st;
+    }
+    free(layers);
+    if (B.oom) rc = COVT_ERR_OOM;
+    if (rc == COVT_OK) props_finish(&B);
+    free(B.aux.p);
+    free(B.dict_st.p);
     R->columns = (covt_prop_column*)B.cols.p;        R->n_columns = (uint32_t)B.cols.n;
     R->dictionaries = (covt_prop_dictionary*)B.dicts.p; R->n_dictionaries = (uint32_t)B.dicts.n;
     R->validity = (uint8_t*)B.validity.p;            R->validity_bytes = B.validity.n;
@@ -1699,6 +1817,7 @@ int32_t covt_oracle_decode_properties(const uint8_t* blob, const uint64_t* tile_
     R->bools = (uint8_t*)B.bools.p;                  R->bool_bytes = B.bools.n;
     R->dict_index = (int32_t*)B.didx.p;              R->n_dict_index = B.didx.n;
     R->dict_offsets = (int32_t*)B.doff.p;            R->n_dict_offsets = B.doff.n;
+    if (rc != COVT_OK) { covt_oracle_props_free(R); return rc; }
     *out = R;
     return COVT_OK;
 }

@@ -88,39 +88,16 @@ int32_t covt_oracle_decode_batch_timed(const uint8_t* blob, const uint64_t* tile
                                        uint64_t* payload_bytes, uint64_t* vertices, uint64_t* checksum);
 void covt_oracle_result_free(covt_oracle_result* r);
 
-/* ---- property columns (gen-2b container) -------------------------------------------------------------------
- * CovtParser.decodePropertyColumn (J/decoder/CovtParser.java:276-390) restated with a columnar, Arrow-like result instead of
- * List<Optional>: per column a validity bitmap (bit i = feature i has a value, java.util.BitSet order) and the DENSE values of
- * the features that have one. Localized dictionary columns are flattened: one column per sub-key, all pointing at the shared
- * dictionary. Strings are dictionary indices; a dictionary is an offsets array into the tile's own UTF-8 bytes (left in the
- * input blob). This is the layout the GPU path for property columns is meant to produce; test infrastructure like the rest. */
-enum { COVT_PV_NONE = 0, COVT_PV_I64 = 1, COVT_PV_F32 = 2, COVT_PV_F64 = 3, COVT_PV_BOOL = 4, COVT_PV_DICT_INDEX = 5 };
-typedef struct covt_prop_column {
-    uint32_t tile, layer;        /* layer = index within the tile */
-    uint64_t name_offset;        /* column name in the blob */
-    uint64_t sub_offset;         /* localized sub-key name in the blob (sub_length 0: not a localized sub-column) */
-    uint32_t name_length, sub_length;
-    uint8_t  data_type;          /* COVT_DT_* (HEAD ordinals) */
-    uint8_t  column_type;        /* COVT_CT_* */
-    uint8_t  value_kind;         /* COVT_PV_* */
-    uint8_t  reserved;
-    uint32_t status;             /* covt_status of the column */
-    uint32_t num_features;
-    uint32_t num_values;         /* set bits of the validity bitmap = dense values */
-    uint64_t validity_offset;    /* bytes into validity[], ceil(num_features / 8) bytes */
-    uint64_t values_offset;      /* elements into the arena of value_kind (COVT_PV_BOOL: BYTES into bools[], num_values dense bits) */
-    uint32_t dictionary;         /* COVT_PV_DICT_INDEX: index into dictionaries[] */
-    uint32_t reserved2;
-} covt_prop_column;
-typedef struct covt_prop_dictionary {
-    uint32_t tile, layer, n_entries, reserved;
-    uint64_t offsets_offset;     /* elements into dict_offsets[]: n_entries + 1 byte offsets relative to bytes_offset */
-    uint64_t bytes_offset;       /* the UTF-8 bytes of all entries, back to back, in the blob */
-    uint64_t n_bytes;
-} covt_prop_dictionary;
+/* ---- property columns -----------------------------------------------------------------------------------------
+ * CovtParser.decodePropertyColumn (J/decoder/CovtParser.java:276-390) restated with the columnar, Arrow-like result of
+ * include/covt_b200.h (covt_prop_column, covt_prop_dictionary, the seven value buffers): per column a validity bitmap (bit i =
+ * feature i has a value, java.util.BitSet order) and the DENSE values of the features that have one. Localized dictionary columns
+ * are flattened: one column per sub-key, all pointing at the shared dictionary. Strings are dictionary indices; a dictionary is an
+ * offsets array into the tile's own UTF-8 bytes (left in the input blob). gen-2b and gen-3 containers; test infrastructure like the
+ * rest. */
 typedef struct covt_oracle_props {
     uint32_t n_tiles, n_columns, n_dictionaries, reserved;
-    uint32_t* tile_status;       /* [n_tiles] status of the property walk of each tile */
+    uint32_t* tile_status;       /* [n_tiles] status of the container walk of each tile (the same walk as the geometry path) */
     covt_prop_column* columns;
     covt_prop_dictionary* dictionaries;
     uint8_t* validity;  uint64_t validity_bytes;
@@ -131,7 +108,8 @@ typedef struct covt_oracle_props {
     int32_t* dict_index; uint64_t n_dict_index;
     int32_t* dict_offsets; uint64_t n_dict_offsets;
 } covt_oracle_props;
-int32_t covt_oracle_decode_properties(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, covt_oracle_props** out);
+int32_t covt_oracle_decode_properties(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                                      const covt_tilejson* tj, uint32_t flags, covt_oracle_props** out);
 void covt_oracle_props_free(covt_oracle_props* p);
 uint32_t covt_oracle_buffer_elem_size(uint32_t which);
 

@@ -180,18 +180,8 @@ def decode_morton(code, num_bits, no_shift=False):
     return x.value, y.value
 
 
-# ---- property columns (covt_oracle_decode_properties: SURVEY 8 f1, gen-2b) ---------------------------------------------------
-class PropColumn(C.Structure):
-    _fields_ = [("tile", C.c_uint32), ("layer", C.c_uint32), ("name_offset", C.c_uint64), ("sub_offset", C.c_uint64),
-                ("name_length", C.c_uint32), ("sub_length", C.c_uint32), ("data_type", C.c_uint8), ("column_type", C.c_uint8),
-                ("value_kind", C.c_uint8), ("reserved", C.c_uint8), ("status", C.c_uint32), ("num_features", C.c_uint32),
-                ("num_values", C.c_uint32), ("validity_offset", C.c_uint64), ("values_offset", C.c_uint64),
-                ("dictionary", C.c_uint32), ("reserved2", C.c_uint32)]
-
-
-class PropDictionary(C.Structure):
-    _fields_ = [("tile", C.c_uint32), ("layer", C.c_uint32), ("n_entries", C.c_uint32), ("reserved", C.c_uint32),
-                ("offsets_offset", C.c_uint64), ("bytes_offset", C.c_uint64), ("n_bytes", C.c_uint64)]
+# ---- property columns (covt_oracle_decode_properties: SURVEY 8 f1) -----------------------------------------------------------
+PropColumn, PropDictionary = abi.PropColumn, abi.PropDictionary
 
 
 class OracleProps(C.Structure):
@@ -207,7 +197,7 @@ PV_NONE, PV_I64, PV_F32, PV_F64, PV_BOOL, PV_DICT_INDEX = range(6)
 
 
 class PropsResult:
-    """Host copy of a covt_oracle_props: `columns` / `dictionaries` structured arrays + the value arenas."""
+    """Host copy of a covt_oracle_props: `columns` / `dictionaries` structured arrays + the value buffers (indexed by abi.PBUF_*)."""
 
     def __init__(self, ptr):
         r = ptr.contents
@@ -215,9 +205,10 @@ class PropsResult:
         def arr(p, n, dt):
             return _copy_from(p, n * np.dtype(dt).itemsize, dt) if n else np.zeros(0, dtype=dt)
         self.tile_status = arr(r.tile_status, r.n_tiles, np.uint32)
-        self.columns = [PropColumn.from_buffer_copy(C.string_at(C.addressof(r.columns[i]), C.sizeof(PropColumn))) for i in range(r.n_columns)]
-        self.dictionaries = [PropDictionary.from_buffer_copy(C.string_at(C.addressof(r.dictionaries[i]), C.sizeof(PropDictionary)))
-                             for i in range(r.n_dictionaries)]
+        self.columns = (np.frombuffer(C.string_at(r.columns, r.n_columns * C.sizeof(PropColumn)), dtype=abi.PROP_COLUMN_DTYPE).copy()
+                        if r.n_columns else np.zeros(0, dtype=abi.PROP_COLUMN_DTYPE))
+        self.dictionaries = (np.frombuffer(C.string_at(r.dictionaries, r.n_dictionaries * C.sizeof(PropDictionary)), dtype=abi.PROP_DICTIONARY_DTYPE).copy()
+                             if r.n_dictionaries else np.zeros(0, dtype=abi.PROP_DICTIONARY_DTYPE))
         self.validity = arr(r.validity, r.validity_bytes, np.uint8)
         self.i64 = arr(r.i64, r.n_i64, np.int64)
         self.f32 = arr(r.f32, r.n_f32, np.float32)
@@ -225,46 +216,29 @@ class PropsResult:
         self.bools = arr(r.bools, r.bool_bytes, np.uint8)
         self.dict_index = arr(r.dict_index, r.n_dict_index, np.int32)
         self.dict_offsets = arr(r.dict_offsets, r.n_dict_offsets, np.int32)
+        self.buffers = [self.validity, self.i64, self.f32, self.f64, self.bools, self.dict_index, self.dict_offsets]
         lib().covt_oracle_props_free(ptr)
+
+    def values_buffer(self, c):
+        return {PV_I64: self.i64, PV_F32: self.f32, PV_F64: self.f64, PV_BOOL: self.bools, PV_DICT_INDEX: self.dict_index}.get(int(c["value_kind"]), self.i64)
 
     def column_values(self, blob, c):
         """List<Optional> view of one column (CovtParser.decodePropertyColumn): value or None per feature."""
-        F = c.num_features
-        valid = np.unpackbits(self.validity[c.validity_offset:c.validity_offset + (F + 7) // 8], bitorder="little")[:F].astype(bool)
-        n = c.num_values
-        if c.value_kind == PV_BOOL:
-            dense = [bool(b) for b in np.unpackbits(self.bools[c.values_offset:c.values_offset + (n + 7) // 8], bitorder="little")[:n]]
-        elif c.value_kind == PV_I64:
-            dense = [int(x) for x in self.i64[c.values_offset:c.values_offset + n]]
-        elif c.value_kind == PV_F32:
-            dense = [float(x) for x in self.f32[c.values_offset:c.values_offset + n]]
-        elif c.value_kind == PV_F64:
-            dense = [float(x) for x in self.f64[c.values_offset:c.values_offset + n]]
-        elif c.value_kind == PV_DICT_INDEX:
-            d = self.dictionaries[c.dictionary]
-            off = self.dict_offsets[d.offsets_offset:d.offsets_offset + d.n_entries + 1].astype(np.int64) + d.bytes_offset
-            raw = bytes(blob[int(d.bytes_offset):int(d.bytes_offset + d.n_bytes)])
-            words = [raw[int(off[i] - d.bytes_offset):int(off[i + 1] - d.bytes_offset)].decode("utf-8") for i in range(d.n_entries)]
-            dense = [words[i] for i in self.dict_index[c.values_offset:c.values_offset + n]]
-        else:
-            dense = []
-        out = [None] * F
-        it = iter(dense)
-        for i in np.nonzero(valid)[0]:
-            out[i] = next(it)
-        return out
+        return abi.prop_column_values(blob, c, self.validity, self.values_buffer(c), self.dict_offsets, self.dictionaries)
 
 
-def decode_properties(blob, tile_offsets):
+def decode_properties(blob, tile_offsets, container=abi.CONTAINER_GEN2B, flags=abi.FLAG_DEFAULT, n_fields=None):
     b = _as_u8(blob)
     offs = np.ascontiguousarray(tile_offsets, dtype=np.uint64)
     out = C.POINTER(OracleProps)()
     L = lib()
-    L.covt_oracle_decode_properties.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(OracleProps))]
+    L.covt_oracle_decode_properties.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(OracleProps))]
     L.covt_oracle_decode_properties.restype = C.c_int32
     L.covt_oracle_props_free.argtypes = [C.POINTER(OracleProps)]
     L.covt_oracle_props_free.restype = None
-    rc = L.covt_oracle_decode_properties(b.ctypes.data, offs.ctypes.data, len(offs) - 1, C.byref(out))
+    tj, keep = make_tilejson(n_fields)
+    rc = L.covt_oracle_decode_properties(b.ctypes.data, offs.ctypes.data, len(offs) - 1, container,
+                                         C.cast(C.byref(tj), C.c_void_p) if tj is not None else None, flags, C.byref(out))
     if rc != 0:
         raise RuntimeError("covt_oracle_decode_properties failed: %d" % rc)
     return PropsResult(out)

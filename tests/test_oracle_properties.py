@@ -72,7 +72,7 @@ def test_c_property_oracle_equals_the_pinned_statement(oracle, fixtures):
     assert not res.tile_status.any()
     by_tile = {}
     for c in res.columns:
-        by_tile.setdefault(c.tile, []).append(c)
+        by_tile.setdefault(int(c["tile"]), []).append(c)
     n_cols = 0
     kinds = set()
     for t, (name, data) in enumerate(fixtures):
@@ -80,13 +80,10 @@ def test_c_property_oracle_equals_the_pinned_statement(oracle, fixtures):
         layers = P.walk_gen2b(bytes(data))
         got = {}
         for c in by_tile.get(t, []):
-            assert c.status == 0, (name, c.layer, c.status)
-            key = bytes(blob[int(c.name_offset):int(c.name_offset) + c.name_length]).decode("utf-8")
-            if c.sub_length:
-                sub = bytes(blob[int(c.sub_offset):int(c.sub_offset) + c.sub_length]).decode("utf-8")
-                key = key if sub == key else key + ":" + sub
-            got.setdefault(c.layer, {})[key] = res.column_values(blob, c)
-            kinds.add(c.value_kind)
+            assert c["status"] == 0, (name, c["layer"], c["status"])
+            key = util.prop_column_key(blob, c)
+            got.setdefault(int(c["layer"]), {})[key] = res.column_values(blob, c)
+            kinds.add(int(c["value_kind"]))
         for li, (layer_name, props) in enumerate(want):
             assert layers[li]["name"] == layer_name
             g = got.get(li, {})
@@ -97,3 +94,4 @@ def test_c_property_oracle_equals_the_pinned_statement(oracle, fixtures):
                                                   if not isinstance(y, (str, bool)) else x == y for x, y in zip(a, col)), (name, layer_name, key)
                 n_cols += 1
     assert n_cols >= 13000 and {oracle.PV_I64, oracle.PV_F32, oracle.PV_BOOL, oracle.PV_DICT_INDEX} <= kinds
+    assert not res.dictionaries["status"].any()

@@ -105,6 +105,15 @@ def compare_results(abi, got, want, blob=None, check_assembled=True, same_contai
     return n
 
 
+def prop_column_key(blob, c):
+    """MVT-style key of a decoded property column record (covt_prop_column): `<column>` or `<column>:<sub-key>`."""
+    key = bytes(blob[int(c["name_offset"]):int(c["name_offset"]) + int(c["name_length"])]).decode("utf-8")
+    if c["sub_length"]:
+        sub = bytes(blob[int(c["sub_offset"]):int(c["sub_offset"]) + int(c["sub_length"])]).decode("utf-8")
+        key = key if sub == key else key + ":" + sub
+    return key
+
+
 # ---- gen-2b -> gen-3 metadata-only re-wrap (SURVEY §8c "gen-3 inputs") ---------------------------------
 def _varint(v):
     out = bytearray()
@@ -307,3 +316,69 @@ def compare_results_bulk(abi, got, want, chunk_layers=1 << 16, same_container=Tr
                 n_elems += int(inside.sum())
         del g, w
     return int(layer_ok.sum()), n_elems
+
+
+# ---- property columns ------------------------------------------------------------------------------------------
+class GpuProps:
+    """Host copy of the property-column part of a product Result, with the oracle PropsResult's attribute names."""
+
+    def __init__(self, abi, res):
+        self.columns = res.prop_columns()
+        self.dictionaries = res.prop_dictionaries()
+        self.buffers = [res.prop_buffer(b) for b in range(abi.NUM_PROP_BUFFERS)]
+        self.validity, self.i64, self.f32, self.f64, self.bools, self.dict_index, self.dict_offsets = self.buffers
+        self.tile_status = res.tile_status()[0]
+
+
+def compare_props(abi, blob, got, want):
+    """Property columns of the product (GpuProps) vs the oracle (oracle.PropsResult): records, statuses, validity bitmaps, dense
+    values and dictionary offsets, column by column (slices sit at the same offsets: both sides pad every slice to 16 bytes).
+    Returns (columns compared, columns both sides accept)."""
+    # (tile statuses are compared by compare_results: the product's include the first layer error, the oracle's property walk reports
+    # the container walk alone)
+    gc, wc = got.columns, want.columns
+    assert len(gc) == len(wc), "column count %d != %d" % (len(gc), len(wc))
+    gd, wd = got.dictionaries, want.dictionaries
+    assert len(gd) == len(wd), "dictionary count %d != %d" % (len(gd), len(wd))
+    for f in ("tile", "layer", "name_offset", "sub_offset", "name_length", "sub_length", "data_type", "column_type", "value_kind",
+              "num_features", "dictionary"):
+        assert np.array_equal(gc[f], wc[f]), "column field %s differs at %s" % (f, np.nonzero(gc[f] != wc[f])[0][:5])
+    if not np.array_equal(gc["status"], wc["status"]):
+        bad = np.nonzero(gc["status"] != wc["status"])[0]
+        raise AssertionError("column status differs at %s: got %s want %s (kinds %s)" % (bad[:8], gc["status"][bad[:8]], wc["status"][bad[:8]], wc["value_kind"][bad[:8]]))
+    for f in ("tile", "layer"):
+        assert np.array_equal(gd[f], wd[f]), "dictionary field %s differs" % f
+    if not np.array_equal(gd["status"], wd["status"]):
+        bad = np.nonzero(gd["status"] != wd["status"])[0]
+        raise AssertionError("dictionary status differs at %s: got %s want %s" % (bad[:8], gd["status"][bad[:8]], wd["status"][bad[:8]]))
+    ok_d = wd["status"] == 0
+    for f in ("n_entries", "offsets_offset", "bytes_offset", "n_bytes"):
+        assert np.array_equal(gd[f][ok_d], wd[f][ok_d]), "dictionary field %s differs" % f
+    for i in np.nonzero(ok_d)[0]:
+        o, n = int(wd["offsets_offset"][i]), int(wd["n_entries"][i]) + 1
+        assert np.array_equal(got.dict_offsets[o:o + n], want.dict_offsets[o:o + n]), "offsets of dictionary %d differ" % i
+    ok = wc["status"] == 0
+    for f in ("num_values", "validity_offset", "values_offset", "data_num_values"):
+        assert np.array_equal(gc[f][ok], wc[f][ok]), "column field %s differs at %s" % (f, np.nonzero(gc[f][ok] != wc[f][ok])[0][:5])
+    kind_buf = {abi.PV_I64: abi.PBUF_I64, abi.PV_F32: abi.PBUF_F32, abi.PV_F64: abi.PBUF_F64, abi.PV_BOOL: abi.PBUF_BOOL,
+                abi.PV_DICT_INDEX: abi.PBUF_DICT_INDEX}
+    for i in np.nonzero(ok)[0]:
+        c = wc[i]
+        F, n = int(c["num_features"]), int(c["num_values"])
+        vo = int(c["validity_offset"])
+        gv, wv = got.validity[vo:vo + (F + 7) // 8].copy(), want.validity[vo:vo + (F + 7) // 8].copy()
+        if F & 7 and len(gv):  # bits behind the last feature are don't-care
+            gv[-1] &= (1 << (F & 7)) - 1
+            wv[-1] &= (1 << (F & 7)) - 1
+        assert np.array_equal(gv, wv), "validity of column %d differs" % i
+        b = kind_buf[int(c["value_kind"])]
+        o = int(c["values_offset"])
+        if b == abi.PBUF_BOOL:
+            ga = np.unpackbits(got.buffers[b][o:o + (n + 7) // 8], bitorder="little")[:n]
+            wa = np.unpackbits(want.buffers[b][o:o + (n + 7) // 8], bitorder="little")[:n]
+        else:
+            ga, wa = got.buffers[b][o:o + n], want.buffers[b][o:o + n]
+        if b in (abi.PBUF_F32, abi.PBUF_F64):  # bit patterns (NaNs included)
+            ga, wa = ga.view(np.uint32 if b == abi.PBUF_F32 else np.uint64), wa.view(np.uint32 if b == abi.PBUF_F32 else np.uint64)
+        assert np.array_equal(ga, wa), "values of column %d (kind %d, tile %d) differ" % (i, c["value_kind"], c["tile"])
+    return len(wc), int(ok.sum())
