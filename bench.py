@@ -4,14 +4,19 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tiles|fixtures|varint1g] [--impl reference]
 
 One "step" = one pass of the hot path (container walk, every stream codec, geometry assembly) over one batch.
-Default workload = BASELINE config 5: 1 048 576 synthetic mixed-geometry gen-2b tiles per GPU, seed = tile index
-(weak scaling: rank r decodes tiles [r*T, (r+1)*T); tiles share nothing, so there is no collective on the data path).
+Default workload = BASELINE config 5: ONE batch of 1 048 576 synthetic mixed-geometry gen-2b tiles (seed = tile index) PARTITIONED by
+tile index over the N GPUs (strong scaling: covt_partition_tiles cuts contiguous ranges balanced by payload bytes, rank r decodes
+range r; tiles share nothing, so there is no collective on the data path). --scaling weak: every rank its own --tiles tiles.
 
   value      compressed GB/s, whole job, inputs already resident in HBM, timed with CUDA events on the library's
              launching stream (first kernel start -> last kernel end), max over ranks
   e2e        the same metric through the reference-facing C-ABI call covt_decode_batch with HOST (pinned) buffers:
              host->device copy, decode and the device->host read of the per-tile status + layer index inside the timed region
-  roofline   dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM copy peak
+  e2e_host   e2e plus the device->host read of the assembled GeoArrow-style buffers and ids into pinned memory (what a
+             List<Layer> caller with a host-side consumer gets)
+  h2d_ceiling  a bare pinned->device copy of the same bytes on all ranks at once: what the box gives the e2e figure at most
+  library_scheduler (N > 1)  the same host batch through ONE covt_decode_batch_multi call from rank 0 over all N GPUs
+  roofline   dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM copy peak (+ roofline.step: whole step)
   cpu_baseline / --impl reference: the CPU oracle (C restatement of the reference Java decoder; no JVM in this image)
              timed on the box's host cores — test infrastructure used only as the checker/baseline, never as the product.
 """
@@ -193,7 +198,7 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as O
     abi = O.abi
-    blob, offs, truth, cfg, container, flags = build_workload(args, 0, for_cpu=True)
+    blob, offs, truth, cfg, container, flags = build_workload(args, 0, for_cpu=args.scaling == "strong")
     threads = os.cpu_count() or 1
     if args.workload == "varint1g":
         threads = 1  # one delta chain: sequential on the CPU
@@ -203,12 +208,13 @@ def run_reference(args, rank, world):
         def one_step():
             vals, st_, cons = O.decode_stream(blob[:sample + 8], abi.OP_VARINT_ZZ_DELTA_XY, num_values=nv)
             return cons, len(vals) // 2
-        cfg["sample"] = "the first %d values of the stream per step, one thread" % nv
+        sample_note = "the first %d values of the stream per step, one thread" % nv
     else:
         def one_step():
             rc, p, v, _cs = O.decode_batch_timed(blob, offs, container, flags, n_threads=threads)
             return p, v
-        cfg["sample"] = "%d tiles per step (the rank-0 batch of the GPU arm)" % (len(offs) - 1)
+        sample_note = "%d tiles per step (%s)" % (len(offs) - 1, "the whole batch the GPU arm partitions" if scaling_of(args) == "strong" else "the rank-0 batch of the GPU arm")
+    cfg.update({"container": "gen-2b", "flags": "CLOSE_RINGS"})
     for _ in range(args.warmup):
         one_step()
     t0 = time.perf_counter()
@@ -220,24 +226,82 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     gbps = pb / dt / 1e9
     line = {"impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": cfg.get("data", "synthetic"), "config": cfg,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": scaling_of(args),
+            "vs_baseline": None, "dtype": "int32", "data": cfg.pop("data", "synthetic"), "config": cfg,
             "mvertices_per_s": vx / dt / 1e6,
+            "workload_stats": {"payload_bytes": pb / args.steps, "vertices": vx / args.steps},
             "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": threads, "kind": "port",
-                             "sample": cfg["sample"] + "; C restatement of the Java decoder (JVM unavailable), -O2, pthreads"},
+                             "sample": sample_note + "; C restatement of the Java decoder (JVM unavailable), -O2, pthreads"},
             "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
 
-def build_workload(args, rank, for_cpu=False):
+def scaling_of(args):
+    return "strong" if (args.workload == "tiles" and args.scaling == "strong") else "weak"
+
+
+def run_library_scheduler(args, covt, abi, world, container, flags):
+    """Rank 0 alone: the whole host batch through ONE covt_decode_batch_multi call (the library's batch scheduler: one host thread
+    + context + pinned staging per GPU, covt_partition_tiles on the call path). The other ranks wait at a barrier meanwhile."""
+    import torch
+    blob, offs, truth = make_tiles(0, args.tiles)
+    pinned = torch.empty(len(blob), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = blob
+    payload = None
+    md = covt.MultiDecoder(list(range(world)))
+    try:
+        def one():
+            res = md.decode_batch(pinned.numpy(), offs, container, flags)
+            t = res.timing()
+            verts = 0
+            for p in res.parts:
+                p["result"].touch_tile_status()
+            res.free()
+            return t
+        for _ in range(2):
+            one()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            t = one()
+        dt = (time.perf_counter() - t0) / args.steps
+        payload = t["payload_bytes"]
+        return {"n_gpus": md.n_devices, "ms_per_call": dt * 1e3, "e2e_GBps": payload / dt / 1e9, "device_ms_max_over_gpus": t["decode_ms"],
+                "h2d_ms_max_over_gpus": t["h2d_ms"], "vertices": t["vertices"], "ok": t["vertices"] == truth["vertices"],
+                "note": "one process, one call, N GPUs: covt_decode_batch_multi from rank 0 with host input (pinned) while the other ranks idle"}
+    finally:
+        md.close() if hasattr(md, "close") else None
+
+
+def build_workload(args, rank, for_cpu=False, world=1, sync=None):
+    """-> blob, tile offsets, truth, config, container, flags of THIS rank's share. sync(): a barrier over the ranks (strong
+    scaling: rank 0 generates the one batch into the disk cache, the others read it)."""
     import covt_loader
-    abi = covt_loader.load().abi
+    covt = covt_loader.load()
+    abi = covt.abi
     flags = abi.FLAG_DEFAULT
     container = abi.CONTAINER_GEN2B
-    if args.workload == "tiles":
+    if args.workload == "tiles" and (args.scaling == "strong" or for_cpu):
+        n = args.tiles
+        if rank == 0 or sync is None:
+            blob, offs, truth = make_tiles(0, n)
+        if sync is not None and world > 1:
+            sync()
+            if rank != 0:
+                blob, offs, truth = make_tiles(0, n)  # from the cache rank 0 wrote (generated again if the disk was full)
+        cfg = {"workload": "config5: ONE batch of %d synthetic mixed-geometry gen-2b tiles, seed = tile index, 2 layers/tile, "
+                           "partitioned by tile index over the GPUs" % n,
+               "tiles": n, "partition": "covt_partition_tiles: contiguous tile ranges balanced by payload bytes, no collective",
+               "l2": "inputs (%.2f GB) and outputs far larger than the 126 MB L2" % (len(blob) / 1e9)}
+        truth = dict(truth, whole_batch=True)
+        if world > 1 and not for_cpu:
+            starts = covt.partition_tiles(offs, world)  # the batch scheduler's split (host only)
+            t0, t1 = int(starts[rank]), int(starts[rank + 1])
+            blob = blob[int(offs[t0]):int(offs[t1])].copy()
+            offs = (offs[t0:t1 + 1] - offs[t0]).astype(np.uint64)
+    elif args.workload == "tiles":
         n = args.tiles
         blob, offs, truth = make_tiles(rank * n, n)
-        cfg = {"workload": "config5: %d synthetic mixed-geometry gen-2b tiles per GPU, seed = tile index, 2 layers/tile" % n,
+        cfg = {"workload": "config5 (weak scaling): %d synthetic mixed-geometry gen-2b tiles per GPU, seed = tile index, 2 layers/tile" % n,
                "tiles_per_gpu": n, "partition": "tile index ranges, no collective", "l2": "inputs (%.2f GB) and outputs far larger than the 126 MB L2" % (len(blob) / 1e9)}
     elif args.workload == "fixtures":
         decode_pfor = None
@@ -326,7 +390,10 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dec = covt.Decoder(local_rank)  # raises without the CUDA library / device: no CPU fallback
 
-    blob_np, offs, truth, cfg, container, flags = build_workload(args, rank)
+    def sync_ranks():
+        if world > 1:
+            dist.barrier()
+    blob_np, offs, truth, cfg, container, flags = build_workload(args, rank, world=world, sync=sync_ranks)
     n_tiles = len(offs) - 1
     # pinned host copy of the inputs (what a caller hands to covt_decode_batch)
     pinned = torch.empty(len(blob_np), dtype=torch.uint8, pin_memory=True)
@@ -414,8 +481,15 @@ def run_gpu(args, rank, world, local_rank):
     bad_tiles = int((st != 0).sum())
     if truth is not None and not stream_mode:
         L = r.layers
-        assert int(L["n_vertices"].sum()) == truth["vertices"], "decoded vertex count differs from what was encoded"
-        assert int(L["n_rings"].sum()) == truth["rings"] and int(L["n_parts"].sum()) == truth["parts"]
+        sums = torch.tensor([int(L["n_vertices"].sum()), int(L["n_rings"].sum()), int(L["n_parts"].sum())], dtype=torch.float64, device="cuda")
+        if world > 1 and truth.get("whole_batch"):
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)  # the truth counts belong to the whole batch, the ranks hold its partitions
+        assert int(sums[0].item()) == truth["vertices"], "decoded vertex count differs from what was encoded"
+        assert int(sums[1].item()) == truth["rings"] and int(sums[2].item()) == truth["parts"]
+    # what a host-side consumer reads back: the assembled GeoArrow-style buffers + ids (element counts of this rank's result)
+    host_bufs = [] if stream_mode else [abi.BUF_S_IDS, abi.BUF_S_GEOMETRY_TYPES, abi.BUF_A_GEOM_OFFSETS, abi.BUF_A_PART_OFFSETS,
+                                        abi.BUF_A_RING_OFFSETS, abi.BUF_A_COORDS]
+    host_counts = {b: r.device_buffer(b)[1] for b in host_bufs}
     r.free()
     batch.free()
 
@@ -435,14 +509,69 @@ def run_gpu(args, rank, world, local_rank):
     h2d_bytes = pinned.numel() + offs_pinned.numel() * 8
     d2h_bytes = n_tiles * 4 + (n_tiles + 1) * 4 + (1 + abi.NUM_BUFFERS + 4) * 8
 
+    # ---------------- the ceiling of e2e: a bare pinned->device copy of the same bytes, all ranks at once ----------------
+    dev_in = torch.empty(pinned.numel(), dtype=torch.uint8, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        dev_in.copy_(pinned, non_blocking=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        dev_in.copy_(pinned, non_blocking=True)
+    ev1.record()
+    barrier()
+    h2d_copy_ms = ev0.elapsed_time(ev1)
+    del dev_in
+
+    # ---------------- end to end INTO HOST MEMORY: the same call + the read-back of the assembled buffers and ids ----------------
+    e2e_host_s, d2h_host_bytes = 0.0, 0
+    if host_bufs and not args.no_e2e_host:
+        sizes = {b: host_counts[b] * np.dtype(abi.BUF_DTYPES[b]).itemsize for b in host_bufs}
+        try:
+            host_out = {b: torch.empty(max(int(sizes[b] * 1.02) + 4096, 16), dtype=torch.uint8, pin_memory=True) for b in host_bufs}
+        except Exception as e:  # not enough lockable host memory on this box: report the figure as absent, not as a failure
+            log("[bench] e2e_host skipped:", e)
+            host_out = None
+        if host_out is not None:
+            def host_step():
+                r = runner.decode_batch_raw(blob_ptr, offs_ptr, n_tiles, container, flags)
+                r.touch_tile_status()
+                got = 0
+                for b in host_bufs:
+                    cnt = r.device_buffer(b)[1]
+                    r.read_into(b, 0, cnt, host_out[b].data_ptr())
+                    got += cnt * np.dtype(abi.BUF_DTYPES[b]).itemsize
+                r.free()
+                return got
+            host_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                d2h_host_bytes = host_step()
+            barrier()
+            e2e_host_s = time.perf_counter() - t0
+            del host_out
+
     # ---------------- reduce over ranks ----------------
-    tt = torch.tensor([dev_ms, e2e_s * 1e3, wall_ms], dtype=torch.float64, device="cuda")
-    ss = torch.tensor([payload, verts, outb, launches, bad_tiles], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([dev_ms, e2e_s * 1e3, wall_ms, h2d_copy_ms, e2e_host_s * 1e3], dtype=torch.float64, device="cuda")
+    ss = torch.tensor([payload, verts, outb, launches, bad_tiles, h2d_bytes, d2h_bytes, d2h_host_bytes], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ss, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max, wall_ms_max = [float(x) for x in tt.tolist()]
-    payload_all, verts_all, outb_all, launches_all, bad_all = [float(x) for x in ss.tolist()]
+    dev_ms_max, e2e_ms_max, wall_ms_max, h2d_copy_ms_max, e2e_host_ms_max = [float(x) for x in tt.tolist()]
+    payload_all, verts_all, outb_all, launches_all, bad_all, h2d_all, d2h_all, d2h_host_all = [float(x) for x in ss.tolist()]
+
+    # ---------------- N > 1: the in-library batch scheduler, ONE call from ONE process over all N GPUs ----------------
+    sched = None
+    if world > 1 and args.workload == "tiles" and args.scaling == "strong" and not args.no_scheduler:
+        del pinned, offs_pinned
+        barrier()
+        if rank == 0:
+            try:
+                sched = run_library_scheduler(args, covt, abi, world, container, flags)
+            except Exception as e:
+                sched = {"unavailable": str(e)[:200]}
+        barrier()
 
     if rank == 0:
         peak, peak_src = read_peaks()
@@ -492,18 +621,36 @@ def run_gpu(args, rank, world, local_rank):
             cpu = {"value": pb / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port", "mvertices_per_s": vx / dt / 1e6,
                    "sample": "one pass over the same %d tiles (%.2f GB payload, %.1f s); C restatement of the reference Java "
                              "decoder (JVM unavailable), -O2, pthreads" % (n_tiles, pb / 1e9, dt)}
-        if numa_node is not None:
-            cfg["host_binding"] = "each rank bound to the NUMA node of its GPU"
-        cfg.update({"container": "gen-2b", "flags": "CLOSE_RINGS", "payload_bytes_per_gpu": payload, "vertices_per_gpu": verts,
-                    "output_bytes_per_gpu": outb, "bad_tiles": bad_all})
+        host_binding = "each rank bound to the NUMA node of its GPU" if numa_node is not None else None
+        cfg.update({"container": "gen-2b", "flags": "CLOSE_RINGS"})
+        stats = {"payload_bytes": payload_all, "vertices": verts_all, "output_bytes": outb_all, "bad_tiles": bad_all,
+                 "payload_bytes_rank0": payload, "vertices_rank0": verts, "output_bytes_rank0": outb, "tiles_rank0": n_tiles}
+        if args.workload == "fixtures" and bad_all:
+            stats["bad_tiles_cause"] = ("the committed omt/4_8_10 tile: its water_name layer labels a varint-coded ICE vertex buffer as FastPFOR "
+                                      "(SURVEY 0-8b); one per replica, COVT_ERR_COUNT_MISMATCH like the oracle")
+        h2d_ceiling = h2d_all * steps / (h2d_copy_ms_max * 1e-3) / 1e9 if h2d_copy_ms_max > 0 else None
+        e2e_ms = e2e_ms_max / steps
+        e2e = {"value": payload_all * steps / (e2e_ms_max * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d_all),
+               "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_ms,
+               "mvertices_per_s": verts_all * steps / (e2e_ms_max * 1e-3) / 1e6,
+               "h2d_ceiling_GBps": h2d_ceiling, "h2d_copy_ms_per_step": h2d_copy_ms_max / steps,
+               "h2d_GBps_in_call": h2d_all / (e2e_ms * 1e-3) / 1e9,
+               "fraction_of_h2d_ceiling": (h2d_all / (e2e_ms * 1e-3) / 1e9) / h2d_ceiling if h2d_ceiling else None,
+               "note": "results stay device-resident (GeoArrow-style buffers); the device->host read is the per-tile status + layer index. "
+                       "h2d_ceiling = a bare pinned->device copy of the same input bytes on all ranks at once"}
+        e2e_host = None
+        if e2e_host_ms_max > 0:
+            e2e_host = {"value": payload_all * steps / (e2e_host_ms_max * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_host_ms_max / steps,
+                        "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all + d2h_host_all),
+                        "mvertices_per_s": verts_all * steps / (e2e_host_ms_max * 1e-3) / 1e6,
+                        "note": "e2e + the read-back of ids, geometry types and the assembled geom/part/ring offsets + coordinates into pinned "
+                                "host memory (covt_result_read): what a List<Layer> caller with a host-side consumer gets"}
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-                "data": cfg.pop("data"), "config": cfg, "mvertices_per_s": mverts, "wall_ms_per_step": wall_ms_max / steps,
-                "roofline": roof, "cpu_baseline": cpu,
-                "e2e": {"value": payload_all * steps / (e2e_ms_max * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms_max / steps,
-                        "mvertices_per_s": verts_all * steps / (e2e_ms_max * 1e-3) / 1e6,
-                        "note": "results stay device-resident (GeoArrow-style buffers); the device->host read is the per-tile status + layer index"},
+                "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": scaling_of(args), "vs_baseline": None, "dtype": "int32",
+                "data": cfg.pop("data"), "config": cfg, "workload_stats": stats, "host_binding": host_binding,
+                "mvertices_per_s": mverts, "wall_ms_per_step": wall_ms_max / steps,
+                "step_roofline_frac": roof["step"]["frac"] if roof else None,
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_host": e2e_host, "library_scheduler": sched,
                 "gpu_launches": int(launches_all), "clocks": clocks}
         emit(line)
     if world > 1:
@@ -536,6 +683,10 @@ def main():
     ap.add_argument("--replicas", type=int, default=256, help="fixture-sweep replicas (config 2)")
     ap.add_argument("--rle-topology", action="store_true", help="config 2 with every topology stream as ORC RLE (BASELINE wording)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="tiles workload on N GPUs: strong = ONE batch of --tiles tiles partitioned over the GPUs (BASELINE config 5); weak = --tiles per GPU")
+    ap.add_argument("--no-e2e-host", action="store_true", help="skip the end-to-end-into-host-memory leg (it pins as much host memory as the results take)")
+    ap.add_argument("--no-scheduler", action="store_true", help="N > 1: skip the covt_decode_batch_multi leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

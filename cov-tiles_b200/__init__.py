@@ -19,7 +19,7 @@ from . import abi  # noqa: F401
 from .abi import *  # noqa: F401,F403
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libcovt_b200.so")
+_LIB_PATH = os.environ.get("COVT_LIB") or os.path.join(_HERE, "libcovt_b200.so")  # COVT_LIB: an experiment build of the same library
 _lib = None
 
 

@@ -149,29 +149,25 @@ def prop_column_values(blob, c, validity, values, dict_offsets, dictionaries):
     F = int(c["num_features"])
     vo = int(c["validity_offset"])
     valid = np.unpackbits(validity[vo:vo + (F + 7) // 8], bitorder="little")[:F].astype(bool)
-    n = int(c["num_values"])
     o = int(c["values_offset"])
     kind = int(c["value_kind"])
+    # one value slot per feature (Arrow layout): slot i belongs to feature i, slots of absent values hold 0
     if kind == PV_BOOL:
-        dense = [bool(b) for b in np.unpackbits(values[o:o + (n + 7) // 8], bitorder="little")[:n]]
+        slots = [bool(b) for b in np.unpackbits(values[o:o + (F + 7) // 8], bitorder="little")[:F]]
     elif kind == PV_I64:
-        dense = [int(x) for x in values[o:o + n]]
+        slots = [int(x) for x in values[o:o + F]]
     elif kind in (PV_F32, PV_F64):
-        dense = [float(x) for x in values[o:o + n]]
+        slots = [float(x) for x in values[o:o + F]]
     elif kind == PV_DICT_INDEX:
         d = dictionaries[int(c["dictionary"])]
         oo, ne, bo, nb = int(d["offsets_offset"]), int(d["n_entries"]), int(d["bytes_offset"]), int(d["n_bytes"])
         off = dict_offsets[oo:oo + ne + 1].astype(np.int64)
         raw = bytes(blob[bo:bo + nb])
         words = [raw[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(ne)]
-        dense = [words[i] for i in values[o:o + n]]
+        slots = [words[i] if v else None for i, v in zip(values[o:o + F], valid)]
     else:
-        dense = []
-    out = [None] * F
-    it = iter(dense)
-    for i in np.nonzero(valid)[0]:
-        out[i] = next(it)
-    return out
+        slots = [None] * F
+    return [s if v else None for s, v in zip(slots, valid)]
 
 
 LAYER_DTYPE = np.dtype(Layer)

@@ -206,10 +206,18 @@ struct Profiler {
         KernelRecord r;
         r.name = name;
         r.alg_bytes = alg_bytes;
-        cudaEventCreate(&r.a);
-        cudaEventCreate(&r.b);
+        r.a = take_event();
+        r.b = take_event();
         cudaEventRecord(r.a, ctx->stream);
         recs.push_back(r);
+    }
+    // timing events are pooled in the context: a profiled decode records ~25 pairs
+    cudaEvent_t take_event()
+    {
+        cudaEvent_t e = nullptr;
+        if (!ctx->event_pool.empty()) { e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
     }
     void end()
     {
@@ -221,8 +229,8 @@ struct Profiler {
         for (auto& r : recs) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, r.a, r.b);
-            cudaEventDestroy(r.a);
-            cudaEventDestroy(r.b);
+            ctx->event_pool.push_back(r.a);
+            ctx->event_pool.push_back(r.b);
             bool merged = false;
             for (auto& k : out)
                 if (r.name == k.name) { k.ms += ms; k.launches++; k.algorithmic_bytes += r.alg_bytes; merged = true; break; }
@@ -323,6 +331,7 @@ void covt_destroy(covt_ctx* ctx)
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     if (ctx->h_seg) cudaFreeHost(ctx->h_seg);
     for (auto& b : ctx->pinned_cache) cudaFreeHost(b.first);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
         if (ctx->class_stream[c]) cudaStreamDestroy(ctx->class_stream[c]);
@@ -383,25 +392,30 @@ int32_t covt_batch_upload(covt_ctx* ctx, const uint8_t* blob, const uint64_t* ti
     b->ctx = ctx;
     b->n_tiles = n_tiles;
     b->blob_len = tile_offsets[n_tiles];
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    cudaError_t e;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    step(cudaEventCreate(&e0));
+    step(cudaEventCreate(&e1));
     // 256 bytes of zero padding: kernels read whole 16-byte windows and one word past unaligned words
-    if ((e = dev_alloc_bytes(ctx, reinterpret_cast<void**>(&b->d_blob), b->blob_len + 256)) != cudaSuccess ||
-        (e = dev_alloc(ctx, &b->d_tile_offsets, (uint64_t)n_tiles + 1)) != cudaSuccess) {
-        delete b;
+    step(dev_alloc_bytes(ctx, reinterpret_cast<void**>(&b->d_blob), b->blob_len + 256));
+    step(dev_alloc(ctx, &b->d_tile_offsets, (uint64_t)n_tiles + 1));
+    if (e == cudaSuccess) {
+        step(cudaEventRecord(e0, ctx->stream));
+        step(cudaMemsetAsync(b->d_blob + b->blob_len, 0, 256, ctx->stream));
+        if (b->blob_len) step(cudaMemcpyAsync(b->d_blob, blob, b->blob_len, cudaMemcpyHostToDevice, ctx->stream));
+        step(cudaMemcpyAsync(b->d_tile_offsets, tile_offsets, ((uint64_t)n_tiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        step(cudaEventRecord(e1, ctx->stream));
+        step(cudaStreamSynchronize(ctx->stream));
+    }
+    if (e == cudaSuccess) cudaEventElapsedTime(&b->h2d_ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e != cudaSuccess) {  // every error path gives the device blocks and the batch object back
+        cudaStreamSynchronize(ctx->stream);
+        covt_batch_free(b);
         CK(e);
     }
-    CK(cudaEventRecord(e0, ctx->stream));
-    CK(cudaMemsetAsync(b->d_blob + b->blob_len, 0, 256, ctx->stream));
-    if (b->blob_len) CK(cudaMemcpyAsync(b->d_blob, blob, b->blob_len, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(b->d_tile_offsets, tile_offsets, ((uint64_t)n_tiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(e1, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&b->h2d_ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     *out = b;
     return COVT_OK;
 }
@@ -702,7 +716,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         prof.begin("k_tile_status", 0);
         CKR(launch_finalize(R->d_layers, d_tile_err, n_tiles, (uint32_t)std::min<uint64_t>(ctx->h_seg->cap[0], 0xffffff00ull), flags, R->d_tile_status, d_totals + 16, d_seg, st));
         prof.end();
-        launches += prof.on ? 2 : 1;  // k_tile_status (+ k_alg_bytes when profiling)
+        launches += prof.on ? 3 : 2;  // k_tile_status, k_layer_totals (+ k_alg_bytes when profiling)
     }
     CKR(cudaEventRecord(ev1, st));
     CKR(cudaMemcpyAsync(ctx->h_totals + 32, d_totals + 16, FINAL_TOTALS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -866,7 +880,7 @@ static uint32_t op_elem_size(uint32_t op)
     switch (op) {
     case COVT_OP_BYTE_RLE: return 1;
     case COVT_OP_RLE_U64: case COVT_OP_RLE_S64: case COVT_OP_VARINT_U64: case COVT_OP_VARINT_ZZ_DELTA_64:
-    case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: return 8;
+    case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: case COVT_OP_VARINT_ZZ_AS_I64: return 8;
     default: return 4;
     }
 }
@@ -913,7 +927,11 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
         d.out_count = 0;
         d.out_offset = arena;
         if (op == COVT_OP_NONE || op >= COVT_NUM_OPS) { d.status = COVT_ERR_UNSUPPORTED_ENCODING; t.status = d.status; continue; }
-        if (d.byte_offset + d.byte_length > batch->blob_len) { d.status = COVT_ERR_TRUNCATED; t.status = d.status; continue; }
+        // (overflow-safe: the descriptors come from untrusted callers)
+        if (d.byte_offset > batch->blob_len || d.byte_length > batch->blob_len - d.byte_offset) { d.status = COVT_ERR_TRUNCATED; t.status = d.status; continue; }
+        // the same policy as the container walk: a request for more than 256 values per payload byte cannot decode with any codec of
+        // the path, and must not be able to reserve gigabytes of output
+        if ((uint64_t)d.num_values > 256ull * ((uint64_t)d.byte_length + 16ull)) { d.status = COVT_ERR_TRUNCATED; t.status = d.status; continue; }
         const bool morton = op == COVT_OP_VARINT_DELTA_MORTON || op == COVT_OP_PFOR_DELTA_MORTON;
         const uint64_t cnt = morton ? 2ull * d.num_values : d.num_values;
         d.out_count = cnt;
@@ -967,6 +985,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     ChunkState* d_states = nullptr;
     uint32_t* d_counter = nullptr;
     uint32_t* d_queue = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int32_t rc = COVT_OK;
     auto cleanup_tmp = [&]() {
         dev_free(ctx, d_tasks);
@@ -975,6 +994,8 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
         dev_free(ctx, d_states);
         dev_free(ctx, d_counter);
         dev_free(ctx, d_queue);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
     };
 #define CKR(call)                                                                                     \
     do {                                                                                              \
@@ -989,7 +1010,6 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
             return rc;                                                                                \
         }                                                                                             \
     } while (0)
-    cudaEvent_t ev0, ev1;
     CKR(cudaEventCreate(&ev0));
     CKR(cudaEventCreate(&ev1));
     R->counts[COVT_BUF_STREAM_ARENA] = arena;
@@ -1053,8 +1073,6 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
     if (n) CKR(cudaMemcpyAsync(sorted.data(), d_tasks, (uint64_t)n * sizeof(DeviceTask), cudaMemcpyDeviceToHost, st));
     CKR(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&R->timing.decode_ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     for (uint32_t i = 0; i < n; i++) {
         if (descs[i].status != COVT_OK) { descs[i].out_count = 0; continue; }
         const DeviceTask& t = sorted[pos_of[i]];
@@ -1097,19 +1115,11 @@ int32_t covt_result_layers(covt_result* res, const covt_layer** layers)
     covt_ctx* ctx = res->ctx;
     CK(cudaSetDevice(ctx->device));
     if (!res->h_layers) {
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0);
-        cudaEventCreate(&e1);
+        const double t0 = now_ms();  // (host clock around a synchronous copy: no events to leak on the error paths)
         CK(pinned_take(ctx, reinterpret_cast<void**>(&res->h_layers), std::max<uint64_t>(res->n_layers, 1) * sizeof(covt_layer)));
-        cudaEventRecord(e0, ctx->stream);
         if (res->n_layers) CK(cudaMemcpyAsync(res->h_layers, res->d_layers, (uint64_t)res->n_layers * sizeof(covt_layer), cudaMemcpyDeviceToHost, ctx->stream));
-        cudaEventRecord(e1, ctx->stream);
         CK(cudaStreamSynchronize(ctx->stream));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        res->timing.d2h_ms += ms;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
+        res->timing.d2h_ms += (float)(now_ms() - t0);
     }
     *layers = res->h_layers;
     return COVT_OK;
@@ -1121,25 +1131,17 @@ int32_t covt_result_tile_status(covt_result* res, const uint32_t** status, const
     covt_ctx* ctx = res->ctx;
     CK(cudaSetDevice(ctx->device));
     if (!res->h_tile_status) {
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0);
-        cudaEventCreate(&e1);
+        const double t0 = now_ms();
         CK(pinned_take(ctx, reinterpret_cast<void**>(&res->h_tile_status), ((uint64_t)res->n_tiles + 1) * sizeof(uint32_t)));
         CK(pinned_take(ctx, reinterpret_cast<void**>(&res->h_first_layer), ((uint64_t)res->n_tiles + 2) * sizeof(uint32_t)));
-        cudaEventRecord(e0, ctx->stream);
         if (res->n_tiles && res->d_tile_status) {
             CK(cudaMemcpyAsync(res->h_tile_status, res->d_tile_status, (uint64_t)res->n_tiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(res->h_first_layer, res->d_first_layer, ((uint64_t)res->n_tiles + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         } else {
             res->h_first_layer[0] = 0;
         }
-        cudaEventRecord(e1, ctx->stream);
         CK(cudaStreamSynchronize(ctx->stream));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        res->timing.d2h_ms += ms;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
+        res->timing.d2h_ms += (float)(now_ms() - t0);
     }
     if (status) *status = res->h_tile_status;
     if (first_layer) *first_layer = res->h_first_layer;

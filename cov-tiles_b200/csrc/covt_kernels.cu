@@ -375,16 +375,17 @@ template <int CLASS> __host__ __device__ constexpr int class_warp_smem() { retur
 // Work tickets. Every warp of a grid draws its items from ONE counter; at 2.4 M items per launch the same-address atomics alone are a
 // millisecond of serialised L2 time (one atomic unit per address), and each ticket is a ~300-cycle round trip at the head of the
 // warp's dependent chain (ticket -> task record -> stream bytes). So a warp takes TICKET_BATCH consecutive items per atomic.
-constexpr uint32_t TICKET_BATCH = 4;
+// (The lane-per-stream classes take ONE group of 32 streams per ticket: with 4, byte_rle went 0.71 -> 0.78 ms and varint64 1.01 -> 1.11 ms
+// per 1 M tiles — a group already is 32 streams, and the longest group of a batch of four decides when the warp is done.)
+template <uint32_t TICKET_BATCH>  // a power of two; the counters start at 0, so every batch starts at a multiple of it
 struct WarpTickets {
-    uint32_t next = 0, end = 0;
+    uint32_t next = 0;  // ONE register of state: a batch is used up when next is a multiple of TICKET_BATCH again
     __device__ __forceinline__ uint32_t take(uint32_t* counter)
     {
-        if (next == end) {  // warp-uniform
+        if ((next & (TICKET_BATCH - 1u)) == 0u) {  // warp-uniform
             uint32_t v = 0;
             if (lane_id() == 0) v = atomicAdd(counter, TICKET_BATCH);
             next = __shfl_sync(FULL, v, 0);
-            end = next + TICKET_BATCH;
         }
         return next++;
     }
@@ -475,7 +476,7 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
     auto report = [&](uint32_t i, const DeviceTask& d, const StreamOutcome& o) { report_outcome(tasks, i, d, o, status_words); };
     constexpr uint32_t GROUP = class_group<CLASS>();
     const uint32_t n_groups = (n_tasks + GROUP - 1u) / GROUP;
-    WarpTickets tickets;
+    WarpTickets<(GROUP == 1u ? 4u : 1u)> tickets;
     for (;;) {
         const uint32_t g = tickets.take(work_counter);
         if (g >= n_groups) break;
@@ -559,12 +560,14 @@ k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, ui
                   uint32_t* tile_err)
 {
     if (seg->overflow) return;
-    uint64_t sum_vertices = 0, sum_out_bytes = 0;  // lane 0: -> totals[0], totals[2]
     covt_layer* layers = all_layers + seg->seg_layer_base;
     const uint32_t n_layers = seg->seg_layers;
     __shared__ uint32_t s_asm[DEC_WARPS][ASM_SMEM_WORDS + 6];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    WarpTickets tickets;
+    // One layer per ticket, and no running sums in this kernel (k_layer_totals adds up the layer table afterwards). Measured per 1 M
+    // tiles: sums of vertices / output bytes kept per warp (registers or shared memory) 4.96 -> 5.61 ms; 4 layers per ticket 5.14 ->
+    // 5.61 ms (neighbouring warps no longer work on neighbouring layers, whose output slices are adjacent).
+    WarpTickets<1> tickets;
     for (;;) {
         const uint32_t l = tickets.take(work_counter);
         if (l >= n_layers) break;
@@ -616,15 +619,31 @@ k_assemble_layers(covt_layer* all_layers, ResultBuffers bufs, uint32_t flags, ui
             L->n_rings = ar.n_rings;
             L->n_vertices = ar.n_vertices;
             L->n_coords = ar.n_coords;
-            sum_vertices += ar.n_vertices;
-            if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && layer_status == COVT_OK)
-                sum_out_bytes += 4ull * ((L->streams[COVT_SLOT_TYPES].num_values + 1ull) + (ar.n_parts + 1ull) + (ar.n_rings + 1ull)) + 8ull * ar.n_coords;
         }
         __syncwarp();
     }
-    if (lane == 0 && (sum_vertices | sum_out_bytes)) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[0]), (unsigned long long)sum_vertices);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[2]), (unsigned long long)sum_out_bytes);
+}
+
+// totals[0] += assembled vertices, totals[2] += bytes of the assembled buffers: one thread per layer of the finished batch
+__global__ void k_layer_totals(const covt_layer* layers, uint32_t flags, uint64_t* totals, const SegState* seg)
+{
+    if (seg->overflow) return;
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_layers = (uint32_t)seg->base[0];
+    uint64_t v = 0, b = 0;
+    if (l < n_layers) {
+        const covt_layer& L = layers[l];
+        v = L.n_vertices;
+        if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && L.status == COVT_OK)
+            b = 4ull * ((L.streams[COVT_SLOT_TYPES].num_values + 1ull) + (L.n_parts + 1ull) + (L.n_rings + 1ull)) + 8ull * L.n_coords;
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        v += __shfl_down_sync(FULL, v, d);
+        b += __shfl_down_sync(FULL, b, d);
+    }
+    if ((threadIdx.x & 31u) == 0 && (v | b)) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[0]), (unsigned long long)v);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[2]), (unsigned long long)b);
     }
 }
 
@@ -1094,6 +1113,7 @@ cudaError_t launch_finalize(const covt_layer* layers, const uint32_t* tile_err, 
 {
     if (!n_tiles) return cudaSuccess;
     k_tile_status<<<(n_tiles + 255) / 256, 256, 0, st>>>(tile_err, n_tiles, tile_status, seg);
+    if (n_layers_bound) k_layer_totals<<<(n_layers_bound + 255) / 256, 256, 0, st>>>(layers, flags, totals, seg);
     if ((flags & COVT_FLAG_PROFILE_KERNELS) && n_layers_bound) k_alg_bytes<<<(n_layers_bound + 255) / 256, 256, 0, st>>>(layers, n_layers_bound, flags, totals, seg);
     return cudaGetLastError();
 }

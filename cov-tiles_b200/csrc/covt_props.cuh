@@ -13,7 +13,8 @@
 //                            32-bit varints widened to i64 (INT_64 data, CovtParser.java:303-311)
 //   k_prop_finish_dicts    : lengths -> offsets (exclusive scan), checked against the dictionary's byteLength
 //   k_prop_finish_columns  : validity popcount vs the data stream's numValues, FLOAT/DOUBLE copy (DecodingUtils.decodeFloatsLE
-//                            :446-453), dictionary index range check, column status
+//                            :446-453), dictionary index range check, column status, null expansion (dense values -> one slot per
+//                            feature: validity bitmap + values = the Arrow layout)
 //
 // Column status = the first failure in this order (oracle/covt_oracle.c follows the same order): (1) metadata-only checks (missing
 // stream, unsupported type / encoding, a stream that leaves its tile, counts no codec can reach, FLOAT size mismatch), (2) the
@@ -151,16 +152,17 @@ struct PropWalk {
             kind = COVT_PV_BOOL;
             if (!in_tile(Ds) || (Ps.have && !in_tile(Ps))) st = COVT_ERR_TRUNCATED;
             else if (!plausible_count((Ds.nv + 7u) / 8u, Ds.bl)) st = COVT_ERR_TRUNCATED;
-            else if (Ps.have) { if (!plausible_count(VB, Ps.bl)) st = COVT_ERR_TRUNCATED; else useP = true; }
+            else if (Ps.have) { if (!plausible_count(VB, Ps.bl)) st = COVT_ERR_TRUNCATED; else if (Ds.nv > F) st = COVT_ERR_COUNT_MISMATCH; else useP = true; }
             else if (Ds.nv != F) st = COVT_ERR_COUNT_MISMATCH;  // no present stream: every feature has a value (CovtParser.java:280-290)
             else flags |= PROP_AUX_FILL_ONES;
-            vbuf = COVT_PBUF_BOOL; nvals = (Ds.nv + 7u) / 8u; d_count = (Ds.nv + 7u) / 8u; opD = COVT_OP_BYTE_RLE;
+            vbuf = COVT_PBUF_BOOL; nvals = VB; d_count = (Ds.nv + 7u) / 8u; opD = COVT_OP_BYTE_RLE;
         } else if (!Ps.have) st = COVT_ERR_BAD_METADATA;
         else if (dt == COVT_DT_STRING) {
             if (!has_dict) st = COVT_ERR_UNSUPPORTED_ENCODING;  // CovtParser.java:345-347
             else if (!localized && (!L.have || !Y.have)) st = COVT_ERR_BAD_METADATA;
             else if (!in_tile(Ps) || !in_tile(Ds) || !plausible_count(VB, Ps.bl) || !plausible_count(Ds.nv, Ds.bl)) st = COVT_ERR_TRUNCATED;
-            kind = COVT_PV_DICT_INDEX; vbuf = COVT_PBUF_DICT_INDEX; nvals = Ds.nv; d_count = Ds.nv; opD = COVT_OP_RLE_U32; useP = true;
+            else if (Ds.nv > F) st = COVT_ERR_COUNT_MISMATCH;
+            kind = COVT_PV_DICT_INDEX; vbuf = COVT_PBUF_DICT_INDEX; nvals = F; d_count = Ds.nv; opD = COVT_OP_RLE_U32; useP = true;
         } else if (dt == COVT_DT_INT_64 || dt == COVT_DT_UINT_64) {
             kind = COVT_PV_I64;
             if (Ds.enc == COVT_ENC_RLE) opD = dt == COVT_DT_INT_64 ? COVT_OP_RLE_S64 : COVT_OP_RLE_U64;  // :299-301
@@ -169,13 +171,14 @@ struct PropWalk {
             else if (Ds.enc == COVT_ENC_VARINT) opD = COVT_OP_VARINT_U32_AS_I64;
             else st = COVT_ERR_UNSUPPORTED_ENCODING;                                                      // :313-315
             if (!st && (!in_tile(Ps) || !in_tile(Ds) || !plausible_count(VB, Ps.bl) || !plausible_count(Ds.nv, Ds.bl))) st = COVT_ERR_TRUNCATED;
-            vbuf = COVT_PBUF_I64; nvals = Ds.nv; d_count = Ds.nv; useP = true;
+            if (!st && Ds.nv > F) st = COVT_ERR_COUNT_MISMATCH;
+            vbuf = COVT_PBUF_I64; nvals = F; d_count = Ds.nv; useP = true;
         } else if (dt == COVT_DT_FLOAT || dt == COVT_DT_DOUBLE) {
             const uint32_t es = dt == COVT_DT_FLOAT ? 4u : 8u;
             kind = dt == COVT_DT_FLOAT ? COVT_PV_F32 : COVT_PV_F64;
             if (!in_tile(Ps) || !in_tile(Ds) || !plausible_count(VB, Ps.bl)) st = COVT_ERR_TRUNCATED;
-            else if ((uint64_t)Ds.nv * es != Ds.bl) st = COVT_ERR_COUNT_MISMATCH;
-            vbuf = dt == COVT_DT_FLOAT ? COVT_PBUF_F32 : COVT_PBUF_F64; nvals = Ds.nv; flags |= PROP_AUX_COPY; useP = true;
+            else if ((uint64_t)Ds.nv * es != Ds.bl || Ds.nv > F) st = COVT_ERR_COUNT_MISMATCH;
+            vbuf = dt == COVT_DT_FLOAT ? COVT_PBUF_F32 : COVT_PBUF_F64; nvals = F; flags |= PROP_AUX_COPY; useP = true;
         } else st = COVT_ERR_UNSUPPORTED_ENCODING;  // "Data type not supported", :368-370
         if (st != COVT_OK) { nvals = 0; opD = COVT_OP_NONE; flags = 0; useP = false; }
         const uint64_t vbytes = st == COVT_OK ? VB : 0u;
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(128) k_prop_finish_columns(const uint8_t* blob
         uint32_t* dst = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(out.buf[C.value_kind == COVT_PV_F32 ? COVT_PBUF_F32 : COVT_PBUF_F64]) +
                                                     C.values_offset * (C.value_kind == COVT_PV_F32 ? 4u : 8u));
         for (uint32_t w = lane; w < data_bl / 4u; w += 32) dst[w] = ld_u32_unaligned(blob + data_off + 4ull * w);
+        __syncwarp();
     }
     if (st == COVT_OK && st_data != COVT_OK) st = st_data;
     if (st == COVT_OK && C.value_kind == COVT_PV_DICT_INDEX) {
@@ -340,6 +344,42 @@ __global__ void __launch_bounds__(128) k_prop_finish_columns(const uint8_t* blob
         bool oob = false;
         for (uint32_t i = lane; i < C.data_num_values; i += 32) { const int32_t v = idx[i]; oob = oob || v < 0 || (uint32_t)v >= n_entries; }
         if (__any_sync(FULL, oob)) st = COVT_ERR_TOPOLOGY;  // Java: ArrayIndexOutOfBounds on dictionaryData[index], :357-358
+    }
+    // Null expansion (CovtParser.java:317-326, 331-340, 354-364: one Optional per feature): the dense values of the present features
+    // sit at the front of the column's F-element slice; spread them to their features' slots, zero the others — the Arrow layout
+    // (validity bitmap + one value slot per row). In place and back to front: feature i takes dense value rank(i) <= i, so a chunk of
+    // 32 features only reads slots that no later-processed (lower) chunk still needs, and never one a higher chunk has overwritten.
+    if (st == COVT_OK && n_valid != F && F != 0u) {
+        __syncwarp();
+        const uint32_t* vwords = reinterpret_cast<const uint32_t*>(validity);  // the slice is 16-byte aligned and padded
+        uint32_t remaining = n_valid;
+        void* vals = static_cast<uint8_t*>(out.buf[C.value_kind]) + C.values_offset * kPropBufElemSize(C.value_kind);  // COVT_PV_x == COVT_PBUF_x for x = 1..5
+        for (int64_t base = (int64_t)((F - 1u) / 32u) * 32; base >= 0; base -= 32) {
+            const uint32_t i = (uint32_t)base + lane;
+            uint32_t m = vwords[base >> 5];
+            if ((uint32_t)base + 32u > F) m &= (1u << (F - (uint32_t)base)) - 1u;
+            remaining -= (uint32_t)__popc(m);
+            const bool valid = (m >> lane) & 1u;
+            const uint32_t rank = remaining + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            if (C.value_kind == COVT_PV_BOOL) {
+                const uint8_t* bits = static_cast<const uint8_t*>(vals);
+                const uint32_t bit = valid ? (bits[rank >> 3] >> (rank & 7u)) & 1u : 0u;
+                const uint32_t word = __ballot_sync(FULL, bit != 0u);
+                __syncwarp();
+                if (lane == 0) static_cast<uint32_t*>(vals)[base >> 5] = word;
+            } else if (C.value_kind == COVT_PV_I64 || C.value_kind == COVT_PV_F64) {
+                uint64_t* a = static_cast<uint64_t*>(vals);
+                const uint64_t v = valid ? a[rank] : 0ull;
+                __syncwarp();
+                if (i < F) a[i] = v;
+            } else {
+                uint32_t* a = static_cast<uint32_t*>(vals);
+                const uint32_t v = valid ? a[rank] : 0u;
+                __syncwarp();
+                if (i < F) a[i] = v;
+            }
+            __syncwarp();
+        }
     }
     if (lane == 0) {
         cols[c].status = st;

@@ -239,7 +239,10 @@ __device__ __forceinline__ void lean_rows4_dispatch(int post, bool widen, uint32
         if (widen) lean_rows4<POST_PLAIN, true>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);
         else lean_rows4<POST_PLAIN, false>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);
         break;
-    case POST_ZZ: lean_rows4<POST_ZZ, false>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift); break;
+    case POST_ZZ:
+        if (widen) lean_rows4<POST_ZZ, true>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);
+        else lean_rows4<POST_ZZ, false>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);
+        break;
     case POST_ZZ_DELTA:
         if (widen) lean_rows4<POST_ZZ_DELTA, true>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);
         else lean_rows4<POST_ZZ_DELTA, false>(A, s4, n, dst, index0, cx, cy, num_bits, no_shift);

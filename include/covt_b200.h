@@ -243,11 +243,12 @@ enum covt_op {
 };
 
 /* ---- property columns (COVT_FLAG_DECODE_PROPERTIES) ------------------------------------------------
- * Replaces CovtParser.decodePropertyColumn (CovtParser.java:276-390) + getStringDictionary (:379-390) with a columnar,
- * Arrow-like result instead of List<Optional>: per column a VALIDITY bitmap (bit i = feature i has a value, java.util.BitSet
- * order: byte i >> 3, bit i & 7) and the DENSE values of the features that have one. Strings are dictionary indices; a
- * dictionary is an offsets array into the tile's own UTF-8 bytes, which stay in the input blob. Localized dictionary columns
- * (gen-2b fixtures) are flattened: one column per sub-key, all pointing at the shared dictionary. */
+ * Replaces CovtParser.decodePropertyColumn (CovtParser.java:276-390) + getStringDictionary (:379-390) with a columnar result
+ * in the Apache Arrow layout instead of List<Optional>: per column a VALIDITY bitmap (bit i = feature i has a value; byte i >> 3,
+ * bit i & 7 = java.util.BitSet order = Arrow's) and ONE VALUE SLOT PER FEATURE (the slots of features without a value hold 0) —
+ * the null expansion of CovtParser.java:317-326,331-340,354-364 done on the device. Strings are dictionary indices; a dictionary
+ * is an int32 offsets array into the tile's own UTF-8 bytes, which stay in the input blob (Arrow utf8 layout). Localized
+ * dictionary columns (gen-2b fixtures) are flattened: one column per sub-key, all pointing at the shared dictionary. */
 enum covt_prop_value_kind {
     COVT_PV_NONE = 0, COVT_PV_I64 = 1, COVT_PV_F32 = 2, COVT_PV_F64 = 3,
     COVT_PV_BOOL = 4,       /* dense bits, BitSet order */
@@ -258,7 +259,7 @@ enum covt_prop_buffer {
     COVT_PBUF_I64 = 1,          /* i64 */
     COVT_PBUF_F32 = 2,          /* f32 (DecodingUtils.decodeFloatsLE :446-453) */
     COVT_PBUF_F64 = 3,          /* f64 */
-    COVT_PBUF_BOOL = 4,         /* u8: ceil(num_values / 8) bytes per BOOLEAN column */
+    COVT_PBUF_BOOL = 4,         /* u8: ceil(num_features / 8) bytes per BOOLEAN column (bit i = value of feature i) */
     COVT_PBUF_DICT_INDEX = 5,   /* i32 */
     COVT_PBUF_DICT_OFFSETS = 6, /* i32: n_entries + 1 byte offsets per dictionary, relative to its bytes_offset */
     COVT_NUM_PROP_BUFFERS = 7
@@ -274,11 +275,11 @@ typedef struct covt_prop_column {
     uint8_t  reserved;
     uint32_t status;             /* covt_status of the column */
     uint32_t num_features;
-    uint32_t num_values;         /* set bits of the validity bitmap = dense values */
+    uint32_t num_values;         /* set bits of the validity bitmap = features that have a value */
     uint64_t validity_offset;    /* bytes into COVT_PBUF_VALIDITY */
-    uint64_t values_offset;      /* elements into the buffer of value_kind (COVT_PV_BOOL: BYTES into COVT_PBUF_BOOL) */
+    uint64_t values_offset;      /* elements into the buffer of value_kind: num_features slots (COVT_PV_BOOL: BYTES into COVT_PBUF_BOOL) */
     uint32_t dictionary;         /* COVT_PV_DICT_INDEX: index into the dictionaries */
-    uint32_t data_num_values;    /* numValues the data stream declares (the slice reserved at values_offset) */
+    uint32_t data_num_values;    /* numValues the data stream declares (== num_values for a column with status COVT_OK) */
 } covt_prop_column;
 typedef struct covt_prop_dictionary {
     uint32_t tile, layer, n_entries;

@@ -562,7 +562,7 @@ uint32_t covt_oracle_op_elem_size(uint32_t op)
     switch (op) {
     case COVT_OP_BYTE_RLE: return 1;
     case COVT_OP_RLE_U64: case COVT_OP_RLE_S64: case COVT_OP_VARINT_U64: case COVT_OP_VARINT_ZZ_DELTA_64:
-    case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: return 8;
+    case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: case COVT_OP_VARINT_ZZ_AS_I64: return 8;
     default: return 4;
     }
 }
@@ -598,11 +598,12 @@ static int32_t decode_op(const uint8_t* blob, uint64_t limit, uint64_t* pos, uin
     case COVT_OP_VARINT_DELTA_MORTON: rc = covt_oracle_decode_delta_varint_morton_codes(blob, limit, pos, n, num_bits, no_shift, (int32_t*)out, &overlong); break;
     case COVT_OP_VARINT_U64: rc = covt_oracle_decode_varint64(blob, limit, pos, n, (int64_t*)out, &overlong); break;
     case COVT_OP_VARINT_ZZ_DELTA_64: rc = covt_oracle_decode_zigzag_delta_varint64(blob, limit, pos, n, (int64_t*)out, &overlong); break;
-    case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: {
-        /* Arrays.stream(int[]).mapToLong(i -> i), CovtParser.java:560,566 */
+    case COVT_OP_VARINT_U32_AS_I64: case COVT_OP_VARINT_ZZ_DELTA_AS_I64: case COVT_OP_VARINT_ZZ_AS_I64: {
+        /* Arrays.stream(int[]).mapToLong(i -> i), CovtParser.java:560,566 (ids) and :305-306,310-311 (INT_64 property data) */
         int32_t* tmp = (int32_t*)malloc(((size_t)n + 1) * sizeof(int32_t));
         rc = op == COVT_OP_VARINT_U32_AS_I64 ? covt_oracle_decode_varint(blob, limit, pos, n, tmp, &overlong)
-                                             : covt_oracle_decode_zigzag_delta_varint(blob, limit, pos, n, tmp, &overlong);
+             : op == COVT_OP_VARINT_ZZ_AS_I64 ? covt_oracle_decode_zigzag_varint(blob, limit, pos, n, tmp, &overlong)
+                                              : covt_oracle_decode_zigzag_delta_varint(blob, limit, pos, n, tmp, &overlong);
         if (rc == COVT_OK) for (uint32_t i = 0; i < n; i++) ((int64_t*)out)[i] = (int64_t)tmp[i];
         free(tmp);
         break;
@@ -623,10 +624,12 @@ int32_t covt_oracle_decode_stream(const uint8_t* blob, uint64_t blob_len, covt_s
     d->status = COVT_OK;
     d->bytes_consumed = 0;
     d->out_count = 0;
-    if (op == COVT_OP_NONE) { d->status = COVT_ERR_UNSUPPORTED_ENCODING; return COVT_OK; }
+    if (op == COVT_OP_NONE || op >= COVT_NUM_OPS) { d->status = COVT_ERR_UNSUPPORTED_ENCODING; return COVT_OK; }
+    if (d->byte_offset > blob_len || d->byte_length > blob_len - d->byte_offset) { d->status = COVT_ERR_TRUNCATED; return COVT_OK; }
+    /* library policy shared with the product (see plausible_count): more than 256 values per payload byte cannot decode */
+    if ((uint64_t)d->num_values > 256ull * ((uint64_t)d->byte_length + 16ull)) { d->status = COVT_ERR_TRUNCATED; return COVT_OK; }
     uint64_t cnt = covt_oracle_op_out_count(op, d->num_values);
     if (cnt * covt_oracle_op_elem_size(op) > out_cap_bytes) return COVT_ERR_INVALID_ARG;
-    if (d->byte_offset + d->byte_length > blob_len) { d->status = COVT_ERR_TRUNCATED; return COVT_OK; }
     uint64_t pos = d->byte_offset;
     int32_t rc = decode_op(blob, d->byte_offset + d->byte_length, &pos, op, d->num_values, d->byte_length, d->num_bits, flags, out);
     d->status = (uint32_t)rc;
@@ -1542,7 +1545,7 @@ static void prop_emit(prop_sink_t* k, const ps_t* Ps, const ps_t* Ds, uint64_t s
         kind = COVT_PV_BOOL;
         if (!ps_in_tile(k, Ds) || (Ps->have && !ps_in_tile(k, Ps))) st = COVT_ERR_TRUNCATED;
         else if (!plausible_count((Ds->nv + 7u) / 8u, Ds->bl)) st = COVT_ERR_TRUNCATED;
-        else if (Ps->have) { if (!plausible_count(VB, Ps->bl)) st = COVT_ERR_TRUNCATED; else use_p = 1; }
+        else if (Ps->have) { if (!plausible_count(VB, Ps->bl)) st = COVT_ERR_TRUNCATED; else if (Ds->nv > F) st = COVT_ERR_COUNT_MISMATCH; else use_p = 1; }
         else if (Ds->nv != F) st = COVT_ERR_COUNT_MISMATCH; /* no present stream: every feature has a value (:280-290) */
         else fill_ones = 1;
     } else if (!Ps->have) st = COVT_ERR_BAD_METADATA;
@@ -1551,18 +1554,20 @@ static void prop_emit(prop_sink_t* k, const ps_t* Ps, const ps_t* Ds, uint64_t s
         if (!k->has_dict) st = COVT_ERR_UNSUPPORTED_ENCODING; /* CovtParser.java:345-347 */
         else if (!k->localized && (!k->L.have || !k->Y.have)) st = COVT_ERR_BAD_METADATA;
         else if (!ps_in_tile(k, Ps) || !ps_in_tile(k, Ds) || !plausible_count(VB, Ps->bl) || !plausible_count(Ds->nv, Ds->bl)) st = COVT_ERR_TRUNCATED;
+        else if (Ds->nv > F) st = COVT_ERR_COUNT_MISMATCH;
         use_p = 1;
     } else if (dt == COVT_DT_INT_64 || dt == COVT_DT_UINT_64) {
         kind = COVT_PV_I64;
         if (Ds->enc != COVT_ENC_RLE && Ds->enc != COVT_ENC_VARINT_ZIG_ZAG && Ds->enc != COVT_ENC_VARINT_DELTA_ZIG_ZAG && Ds->enc != COVT_ENC_VARINT)
             st = COVT_ERR_UNSUPPORTED_ENCODING; /* :313-315 */
         else if (!ps_in_tile(k, Ps) || !ps_in_tile(k, Ds) || !plausible_count(VB, Ps->bl) || !plausible_count(Ds->nv, Ds->bl)) st = COVT_ERR_TRUNCATED;
+        else if (Ds->nv > F) st = COVT_ERR_COUNT_MISMATCH;
         use_p = 1;
     } else if (dt == COVT_DT_FLOAT || dt == COVT_DT_DOUBLE) {
         uint32_t es = dt == COVT_DT_FLOAT ? 4u : 8u;
         kind = dt == COVT_DT_FLOAT ? COVT_PV_F32 : COVT_PV_F64;
         if (!ps_in_tile(k, Ps) || !ps_in_tile(k, Ds) || !plausible_count(VB, Ps->bl)) st = COVT_ERR_TRUNCATED;
-        else if ((uint64_t)Ds->nv * es != Ds->bl) st = COVT_ERR_COUNT_MISMATCH;
+        else if ((uint64_t)Ds->nv * es != Ds->bl || Ds->nv > F) st = COVT_ERR_COUNT_MISMATCH;
         use_p = 1;
     } else st = COVT_ERR_UNSUPPORTED_ENCODING; /* "Data type not supported", :368-370 */
 
@@ -1589,7 +1594,7 @@ static void prop_emit(prop_sink_t* k, const ps_t* Ps, const ps_t* Ds, uint64_t s
     c->data_num_values = Ds->nv;
     const uint8_t* blob = k->blob;
     int64_t v_at = vec_slice(&B->validity, VB);
-    uint64_t n_alloc = kind == COVT_PV_BOOL ? (Ds->nv + 7u) / 8u : Ds->nv;
+    uint64_t n_alloc = kind == COVT_PV_BOOL ? VB : F; /* one slot per feature (the dense values are spread out by props_finish) */
     int64_t d_at = vec_slice(vb, n_alloc);
     if (v_at < 0 || d_at < 0) { B->oom = 1; c->status = COVT_ERR_OOM; return; }
     a->fill_ones = (uint32_t)fill_ones;
@@ -1739,7 +1744,6 @@ static void props_finish(props_build_t* B)
         } else {
             for (uint32_t b = 0; b < F; b++) n_valid += (validity[b >> 3] >> (b & 7)) & 1u;
         }
-        (void)VB;
         if (st == COVT_OK && n_valid != c->data_num_values) st = COVT_ERR_COUNT_MISMATCH;
         if (st == COVT_OK && a->st_data != COVT_OK) st = a->st_data;
         if (st == COVT_OK && c->value_kind == COVT_PV_DICT_INDEX) {
@@ -1749,6 +1753,26 @@ static void props_finish(props_build_t* B)
         }
         c->status = st;
         c->num_values = present_ok ? n_valid : 0;
+        /* null expansion (CovtParser.java:317-326, 331-340, 354-364: one Optional per feature): the dense values sit at the front
+         * of the column's F-slot slice; spread them to their features' slots back to front, zero the others (the Arrow layout) */
+        if (st == COVT_OK && n_valid != F) {
+            uint32_t r = n_valid;
+            if (c->value_kind == COVT_PV_BOOL) {
+                uint8_t* bits = (uint8_t*)B->bools.p + c->values_offset;
+                uint8_t* tmp = (uint8_t*)calloc((size_t)VB + 1, 1);
+                if (!tmp) { B->oom = 1; return; }
+                for (uint32_t f = F; f-- > 0;)
+                    if ((validity[f >> 3] >> (f & 7)) & 1u) { r--; if ((bits[r >> 3] >> (r & 7)) & 1u) tmp[f >> 3] |= (uint8_t)(1u << (f & 7)); }
+                memcpy(bits, tmp, VB);
+                free(tmp);
+            } else if (c->value_kind == COVT_PV_I64 || c->value_kind == COVT_PV_F64) {
+                uint64_t* a = (uint64_t*)(c->value_kind == COVT_PV_I64 ? B->i64.p : B->f64.p) + c->values_offset;
+                for (uint32_t f = F; f-- > 0;) a[f] = ((validity[f >> 3] >> (f & 7)) & 1u) ? a[--r] : 0;
+            } else {
+                uint32_t* a = (uint32_t*)(c->value_kind == COVT_PV_F32 ? B->f32.p : B->didx.p) + c->values_offset;
+                for (uint32_t f = F; f-- > 0;) a[f] = ((validity[f >> 3] >> (f & 7)) & 1u) ? a[--r] : 0;
+            }
+        }
     }
 }
 

@@ -23,9 +23,11 @@ def test_reference_arm_prints_one_json_line():
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "covt_tile_batch_decode_compressed_GBps" and d["unit"] == "GB/s"
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["config"]["workload"].startswith("config5: 4096 synthetic") and "model" not in d["config"]
+    assert d["config"]["workload"].startswith("config5: ONE batch of 4096 synthetic") and "model" not in d["config"]
+    # the keys of `config` are the ones the GPU arm prints too (the driver compares the two dicts)
+    assert sorted(d["config"]) == ["container", "flags", "l2", "partition", "tiles", "workload"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == "GB/s" and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -115,6 +115,7 @@ def test_varint64_and_id_ops(covt, oracle, gen, decoder):
         small = rng.integers(0, 1 << 27, n).astype(np.int64)
         cases.append((abi.OP_VARINT_U32_AS_I64, gen.encode_varints(small), n, 0, False))
         cases.append((abi.OP_VARINT_ZZ_DELTA_AS_I64, gen.encode_varints(np.cumsum(rng.integers(-99, 99, n)), zigzag=True, delta=True), n, 0, False))
+        cases.append((abi.OP_VARINT_ZZ_AS_I64, gen.encode_varints(rng.integers(-(1 << 20), 1 << 20, n), zigzag=True, delta=False), n, 0, False))
     # extremes
     ext = np.array([0, 1, -1, (1 << 63) - 1, -(1 << 63), 1 << 35, 127, 128], dtype=np.int64)
     cases.append((abi.OP_VARINT_U64, gen.encode_varints(ext), len(ext), 0, False))

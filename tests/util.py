@@ -373,11 +373,11 @@ def compare_props(abi, blob, got, want):
         assert np.array_equal(gv, wv), "validity of column %d differs" % i
         b = kind_buf[int(c["value_kind"])]
         o = int(c["values_offset"])
-        if b == abi.PBUF_BOOL:
-            ga = np.unpackbits(got.buffers[b][o:o + (n + 7) // 8], bitorder="little")[:n]
-            wa = np.unpackbits(want.buffers[b][o:o + (n + 7) // 8], bitorder="little")[:n]
+        if b == abi.PBUF_BOOL:  # one slot (bit) per feature, zero where the feature has no value
+            ga = np.unpackbits(got.buffers[b][o:o + (F + 7) // 8], bitorder="little")[:F]
+            wa = np.unpackbits(want.buffers[b][o:o + (F + 7) // 8], bitorder="little")[:F]
         else:
-            ga, wa = got.buffers[b][o:o + n], want.buffers[b][o:o + n]
+            ga, wa = got.buffers[b][o:o + F], want.buffers[b][o:o + F]
         if b in (abi.PBUF_F32, abi.PBUF_F64):  # bit patterns (NaNs included)
             ga, wa = ga.view(np.uint32 if b == abi.PBUF_F32 else np.uint64), wa.view(np.uint32 if b == abi.PBUF_F32 else np.uint64)
         assert np.array_equal(ga, wa), "values of column %d (kind %d, tile %d) differ" % (i, c["value_kind"], c["tile"])

@@ -1,13 +1,16 @@
 #!/usr/bin/env python3
 """Per source line: executed warp instructions and stall samples of one kernel of an .ncu-rep (needs -lineinfo + --import-source on).
-usage: ncu_lines.py report.ncu-rep kernel-regex [top_n]"""
+usage: ncu_lines.py report.ncu-rep kernel-regex|launch-index [top_n]"""
 import csv
 import subprocess
 import sys
 
 
 def main(path, kernel, top=40):
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel, "--print-source", "sass,cuda"],
+    sel = ["--kernel-id", ":::" + kernel] if kernel.isdigit() else ["--kernel-name", "regex:" + kernel]
+    if kernel.isdigit():  # the N-th profiled launch of the report (0-based): ncu has no direct flag, so filter by its launch-skip
+        sel = ["--launch-skip", kernel, "--launch-count", "1"]
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"] + sel + ["--print-source", "sass,cuda"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     fname = ""
