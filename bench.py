@@ -211,7 +211,10 @@ def run_reference(args, rank, world):
         sample_note = "the first %d values of the stream per step, one thread" % nv
     else:
         def one_step():
-            rc, p, v, _cs = O.decode_batch_timed(blob, offs, container, flags, n_threads=threads)
+            rc, p, v, _cs = O.decode_batch_timed(blob, offs, container, flags & ~abi.FLAG_DECODE_PROPERTIES, n_threads=threads)
+            if flags & abi.FLAG_DECODE_PROPERTIES:  # (the property oracle is single-threaded: the batch is walked once more)
+                pr = O.decode_properties(blob, offs, container, flags)
+                p += int(pr.payload_bytes)
             return p, v
         sample_note = "%d tiles per step (%s)" % (len(offs) - 1, "the whole batch the GPU arm partitions" if scaling_of(args) == "strong" else "the rank-0 batch of the GPU arm")
     cfg.update({"container": "gen-2b", "flags": "CLOSE_RINGS"})
@@ -322,8 +325,11 @@ def build_workload(args, rank, for_cpu=False, world=1, sync=None):
                 return vals
         blob, offs, truth = make_fixture_sweep(args.replicas, decode_pfor)
         flags |= abi.FLAG_ID_DVZZ_IS_RLE
-        cfg = {"workload": "config2%s: the reference's 91 gen-2b OMT fixture tiles z2-z14 in one batch, x%d replicas" % (
-            " (RLE topology streams: FastPFOR topology transcoded to ORC RLE)" if args.rle_topology else "", args.replicas),
+        if args.props:
+            flags |= abi.FLAG_DECODE_PROPERTIES
+        cfg = {"workload": "config2%s%s: the reference's 91 gen-2b OMT fixture tiles z2-z14 in one batch, x%d replicas" % (
+            " (RLE topology streams: FastPFOR topology transcoded to ORC RLE)" if args.rle_topology else "",
+            " + property columns (COVT_FLAG_DECODE_PROPERTIES)" if args.props else "", args.replicas),
                "l2": "inputs larger than L2"}
     elif args.workload == "varint1g":
         from tools.gen import gen as G
@@ -565,12 +571,15 @@ def run_gpu(args, rank, world, local_rank):
     sched = None
     if world > 1 and args.workload == "tiles" and args.scaling == "strong" and not args.no_scheduler:
         del pinned, offs_pinned
+        # the other ranks must wait on the HOST: an NCCL barrier would park a spinning kernel on the GPUs the scheduler is using
+        cpu_group = dist.new_group(backend="gloo")
         barrier()
         if rank == 0:
             try:
                 sched = run_library_scheduler(args, covt, abi, world, container, flags)
             except Exception as e:
                 sched = {"unavailable": str(e)[:200]}
+        dist.barrier(group=cpu_group)
         barrier()
 
     if rank == 0:
@@ -682,6 +691,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=1 << 20, help="tiles per GPU (config 5: 1 048 576)")
     ap.add_argument("--replicas", type=int, default=256, help="fixture-sweep replicas (config 2)")
     ap.add_argument("--rle-topology", action="store_true", help="config 2 with every topology stream as ORC RLE (BASELINE wording)")
+    ap.add_argument("--props", action="store_true", help="config 2 with the property columns decoded too (SURVEY 8 f1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="tiles workload on N GPUs: strong = ONE batch of --tiles tiles partitioned over the GPUs (BASELINE config 5); weak = --tiles per GPU")

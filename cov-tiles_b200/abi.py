@@ -91,7 +91,7 @@ class Layer(C.Structure):
                 ("streams", StreamRef * NUM_SLOTS), ("out", C.c_uint64 * NUM_BUFFERS),
                 ("n_parts", C.c_uint32), ("n_rings", C.c_uint32), ("n_vertices", C.c_uint32),
                 ("n_coords", C.c_uint32), ("cap_parts", C.c_uint32), ("cap_rings", C.c_uint32),
-                ("reserved2", C.c_uint32 * 2)]
+                ("header_offset", C.c_uint64)]
 
 
 class StreamDesc(C.Structure):

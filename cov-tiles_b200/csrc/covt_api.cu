@@ -437,7 +437,8 @@ void covt_batch_free(covt_batch* b)
 // One pass over all tiles: count -> scan -> ONE size read-back -> records + tasks -> the codec-class kernels -> finish.
 static int32_t decode_properties(covt_ctx* ctx, covt_batch* batch, uint32_t container, const covt_tilejson* tilejson, uint32_t flags, covt_result* R)
 {
-    const uint32_t n_tiles = batch->n_tiles;
+    const uint32_t n_layers = R->n_layers;
+    if (!n_layers) return COVT_OK;
     cudaStream_t st = ctx->stream;
     Profiler prof = {ctx, (flags & COVT_FLAG_PROFILE_KERNELS) != 0, {}};
     uint64_t *d_pcols = nullptr, *d_block_sums = nullptr, *d_totals = nullptr;
@@ -464,12 +465,13 @@ static int32_t decode_properties(covt_ctx* ctx, covt_batch* batch, uint32_t cont
             return rc;                                                                                \
         }                                                                                             \
     } while (0)
-    const uint32_t nb = (n_tiles + 255) / 256;
+    const uint32_t nb = (n_layers + 255) / 256;
     CKP(cudaEventCreate(&ev0));
     CKP(cudaEventCreate(&ev1));
-    CKP(dev_alloc(ctx, &d_pcols, (uint64_t)PROP_COLS * n_tiles));
+    CKP(dev_alloc(ctx, &d_pcols, (uint64_t)PROP_COLS * n_layers));
     CKP(dev_alloc(ctx, &d_block_sums, (uint64_t)PROP_COLS * nb));
-    CKP(dev_alloc(ctx, &d_totals, PROP_COLS));
+    CKP(dev_alloc(ctx, &d_totals, PROP_COLS + 2));
+    CKP(cudaMemsetAsync(d_totals, 0, (PROP_COLS + 2) * sizeof(uint64_t), st));
     CKP(dev_alloc(ctx, &d_counter, 16));
     uint32_t tj_layers = 0;
     if (tilejson && tilejson->n_vector_layers && tilejson->n_fields) {
@@ -481,8 +483,8 @@ static int32_t decode_properties(covt_ctx* ctx, covt_batch* batch, uint32_t cont
     CKP(cudaEventRecord(ev0, st));
     PropOut po = {};
     prof.begin("k0_props_scan", 0);
-    CKP(launch_k0_props(false, batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, d_pcols, po, st));
-    CKP(launch_scan_tile_cols(d_pcols, n_tiles, d_block_sums, d_totals, st, PROP_COLS));
+    CKP(launch_k0_props(false, batch->d_blob, batch->d_tile_offsets, R->d_layers, n_layers, container, d_tj, tj_layers, d_pcols, po, d_totals + PROP_COLS, st));
+    CKP(launch_scan_tile_cols(d_pcols, n_layers, d_block_sums, d_totals, st, PROP_COLS));
     prof.end();
     uint64_t* h = ctx->h_totals;  // pinned scratch (64 words)
     CKP(cudaMemcpyAsync(h, d_totals, PROP_COLS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -515,7 +517,7 @@ static int32_t decode_properties(covt_ctx* ctx, covt_batch* batch, uint32_t cont
     po.aux_dict_base = n_cols * PROP_AUX_WORDS;
     po.tasks = d_tasks;
     prof.begin("k0_props_fill", 0);
-    CKP(launch_k0_props(true, batch->d_blob, batch->d_tile_offsets, n_tiles, container, d_tj, tj_layers, d_pcols, po, st));
+    CKP(launch_k0_props(true, batch->d_blob, batch->d_tile_offsets, R->d_layers, n_layers, container, d_tj, tj_layers, d_pcols, po, d_totals + PROP_COLS, st));
     prof.end();
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
         if (!class_n[c]) continue;
@@ -528,10 +530,13 @@ static int32_t decode_properties(covt_ctx* ctx, covt_batch* batch, uint32_t cont
     CKP(launch_prop_finish(batch->d_blob, (uint32_t)n_cols, (uint32_t)n_dicts, po, st));
     prof.end();
     CKP(cudaEventRecord(ev1, st));
+    CKP(cudaMemcpyAsync(h, d_totals + PROP_COLS, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CKP(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     R->timing.decode_ms += ms;
+    R->timing.payload_bytes += h[0];  // property streams count like geometry streams: compressed bytes read
+    R->timing.output_bytes += h[1];
     R->timing.kernel_launches += 7 + 2 * NUM_OP_CLASSES;
     prof.collect(R->kernel_times);
     cleanup();

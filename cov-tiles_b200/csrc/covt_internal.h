@@ -115,9 +115,11 @@ struct PropOut {
     uint64_t class_off[NUM_OP_CLASSES_C];
     void* buf[COVT_NUM_PROP_BUFFERS];
 };
-// fill = false: pcols[col * n_tiles + tile] = per-tile sums (out is not touched); fill = true: pcols holds the exclusive prefixes
-cudaError_t launch_k0_props(bool fill, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container, const uint32_t* tj_fields,
-                            uint32_t tj_layers, uint64_t* pcols, const PropOut& out, cudaStream_t st);
+// One thread per layer of the layer table. fill = false: pcols[col * n_layers + layer] = per-layer sums (out is not touched);
+// fill = true: pcols holds the exclusive prefixes. totals (fill only): [0] += payload bytes of the property streams, [1] += bytes
+// of the property buffers written
+cudaError_t launch_k0_props(bool fill, const uint8_t* blob, const uint64_t* tile_offsets, const covt_layer* layers, uint32_t n_layers, uint32_t container,
+                            const uint32_t* tj_fields, uint32_t tj_layers, uint64_t* pcols, const PropOut& out, uint64_t* totals, cudaStream_t st);
 cudaError_t launch_prop_finish(const uint8_t* blob, uint32_t n_cols, uint32_t n_dicts, const PropOut& out, cudaStream_t st);
 uint32_t host_resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags);
 int host_op_class_of(uint32_t op);  // OpClass of a covt_op, -1 for COVT_OP_NONE

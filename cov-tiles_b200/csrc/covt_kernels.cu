@@ -282,7 +282,7 @@ k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_til
         push(0u); push(0u); push(0u); push(0u);  // n_parts, n_rings, n_vertices, n_coords: written by the assembler
         push((uint32_t)cap_parts);
         push((uint32_t)cap_rings);
-        push(0u); push(0u);
+        push((uint32_t)H.layer_start); push((uint32_t)(H.layer_start >> 32));  // header_offset
         dst[1] = make_uint4(H.num_columns, layer_status, H.geom_ct | (num_bits << 8) | (lite.has(COVT_SLOT_ID) ? 1u << 16 : 0u), H.name_length);
         run[0] += 1;
     });
@@ -370,7 +370,8 @@ constexpr int DEC_WARP_SMEM = WARP_SMEM_BYTES;
 constexpr int PFOR_WARP_SMEM = (PFOR_SMEM_WORDS + 4 + LEAN_STAGE_WORDS) * 4;
 constexpr int PFOR_BIG_WARP_SMEM = (404 + LEAN_STAGE_WORDS) * 4;  // pass 2: block window + container window + value stage (warp_pfor_stream)
 template <int CLASS> __host__ __device__ constexpr uint32_t class_group() { return (CLASS == CLASS_VARINT32 || CLASS == CLASS_PFOR) ? 1u : 32u; }
-template <int CLASS> __host__ __device__ constexpr int class_warp_smem() { return CLASS == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM; }
+constexpr int RLE_BIG_WARP_SMEM = RLE_WIN_WORDS * 4;  // pass 2 of the RLE class: the literal-group window (warp_rle_literals)
+template <int CLASS> __host__ __device__ constexpr int class_warp_smem() { return CLASS == CLASS_PFOR ? PFOR_WARP_SMEM : (CLASS == CLASS_RLE ? RLE_BIG_WARP_SMEM : DEC_WARP_SMEM); }
 
 // Work tickets. Every warp of a grid draws its items from ONE counter; at 2.4 M items per launch the same-address atomics alone are a
 // millisecond of serialised L2 time (one atomic unit per address), and each ticket is a ~300-cycle round trip at the head of the
@@ -399,9 +400,9 @@ __device__ __forceinline__ void decode_one(const StreamTask& t, void* wsm, Strea
     o.consumed = 0;
     if (CLASS == CLASS_BYTE_RLE) warp_byte_rle_stream(t, o);
     else if (CLASS == CLASS_RLE) {
-        if (t.op == COVT_OP_RLE_U32) warp_rle_stream<int32_t, false>(t, o);
-        else if (t.op == COVT_OP_RLE_U64) warp_rle_stream<int64_t, false>(t, o);
-        else warp_rle_stream<int64_t, true>(t, o);
+        if (t.op == COVT_OP_RLE_U32) warp_rle_stream<int32_t, false>(t, o, stage);
+        else if (t.op == COVT_OP_RLE_U64) warp_rle_stream<int64_t, false>(t, o, stage);
+        else warp_rle_stream<int64_t, true>(t, o, stage);
     } else if (CLASS == CLASS_VARINT32) {
         if (t.op == COVT_OP_VARINT_ZZ_DELTA_XY && (t.num_values & 1u)) { o.status = COVT_ERR_COUNT_MISMATCH; return; }
         const bool widen = t.op == COVT_OP_VARINT_U32_AS_I64 || t.op == COVT_OP_VARINT_ZZ_DELTA_AS_I64 || t.op == COVT_OP_VARINT_ZZ_AS_I64;
@@ -476,7 +477,10 @@ k_decode_class(const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks_arg, uin
     auto report = [&](uint32_t i, const DeviceTask& d, const StreamOutcome& o) { report_outcome(tasks, i, d, o, status_words); };
     constexpr uint32_t GROUP = class_group<CLASS>();
     const uint32_t n_groups = (n_tasks + GROUP - 1u) / GROUP;
-    WarpTickets<(GROUP == 1u ? 4u : 1u)> tickets;
+#ifndef WARP_CLASS_TICKETS
+#define WARP_CLASS_TICKETS 4u
+#endif
+    WarpTickets<(GROUP == 1u ? WARP_CLASS_TICKETS : 1u)> tickets;
     for (;;) {
         const uint32_t g = tickets.take(work_counter);
         if (g >= n_groups) break;
@@ -992,13 +996,13 @@ cudaError_t launch_scan_tile_cols(uint64_t* tile_cols, uint32_t n_tiles, uint64_
 }
 
 // ---- property columns (covt_props.cuh) ----
-cudaError_t launch_k0_props(bool fill, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container, const uint32_t* tj_fields,
-                            uint32_t tj_layers, uint64_t* pcols, const PropOut& out, cudaStream_t st)
+cudaError_t launch_k0_props(bool fill, const uint8_t* blob, const uint64_t* tile_offsets, const covt_layer* layers, uint32_t n_layers, uint32_t container,
+                            const uint32_t* tj_fields, uint32_t tj_layers, uint64_t* pcols, const PropOut& out, uint64_t* totals, cudaStream_t st)
 {
-    if (!n_tiles) return cudaSuccess;
-    const uint32_t grid = (n_tiles + K0_BLOCK - 1) / K0_BLOCK;
-    if (fill) k0_props<true><<<grid, K0_BLOCK, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, pcols, out);
-    else k0_props<false><<<grid, K0_BLOCK, 0, st>>>(blob, tile_offsets, n_tiles, container, tj_fields, tj_layers, pcols, out);
+    if (!n_layers) return cudaSuccess;
+    const uint32_t grid = (n_layers + K0_BLOCK - 1) / K0_BLOCK;
+    if (fill) k0_props<true><<<grid, K0_BLOCK, 0, st>>>(blob, tile_offsets, layers, n_layers, container, tj_fields, tj_layers, pcols, out, totals);
+    else k0_props<false><<<grid, K0_BLOCK, 0, st>>>(blob, tile_offsets, layers, n_layers, container, tj_fields, tj_layers, pcols, out, totals);
     return cudaGetLastError();
 }
 cudaError_t launch_prop_finish(const uint8_t* blob, uint32_t n_cols, uint32_t n_dicts, const PropOut& out, cudaStream_t st)
@@ -1066,7 +1070,7 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
         break;
     case CLASS_RLE:
         COVT_PASS1(CLASS_RLE, 1, big_queue, c1);
-        k_decode_class_big<CLASS_RLE><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
+        k_decode_class_big<CLASS_RLE><<<grid_big, DEC_WARPS * 32, DEC_WARPS * RLE_BIG_WARP_SMEM, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
         break;
     case CLASS_VARINT32: COVT_PASS1(CLASS_VARINT32, 8, nullptr, nullptr); break;
     case CLASS_VARINT64:

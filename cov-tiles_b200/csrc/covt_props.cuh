@@ -6,8 +6,9 @@
 // array into the tile's own UTF-8 bytes. The stream codecs are the ones of the geometry path (covt_streams.cuh): property streams
 // become decode tasks of the same codec-class kernels.
 //
-//   k0_props<false>        : container walk (covt_walk.cuh, Props hooks) counting columns, dictionaries, buffer slices and tasks per tile
-//   (column scan)          : exclusive prefixes -> every tile knows where its records, slices and tasks go
+//   k0_props<false>        : walk of every layer's metadata (covt_walk.cuh, Props hooks; one thread per layer of the layer table the
+//                            geometry pass wrote) counting columns, dictionaries, buffer slices and tasks per layer
+//   (column scan)          : exclusive prefixes -> every layer knows where its records, slices and tasks go
 //   k0_props<true>         : the same walk writing the column / dictionary records and one decode task per stream
 //   k_decode_class<...>    : Byte-RLE (present bitsets, BOOLEAN data), RLE (INT_64 data, dictionary indices, dictionary lengths),
 //                            32-bit varints widened to i64 (INT_64 data, CovtParser.java:303-311)
@@ -46,6 +47,7 @@ struct PropWalk {
     bool gen3;
     PropOut out;
     uint64_t cnt[PROP_COLS];  // pass 1: sums of the tile; pass 2: running positions (start = exclusive prefix)
+    uint64_t payload_bytes = 0, output_bytes = 0;  // of the streams handed to the decoders / the slices reserved (covt_timing)
     // layer / column being walked
     uint32_t layer = 0, F = 0, dt = 0, ct = 0, nlen = 0, dict_index = 0;
     uint64_t noff = 0;
@@ -116,6 +118,7 @@ struct PropWalk {
     __device__ void push_task(uint32_t op, const PStream& s, uint32_t num_values, void* dst, uint64_t ref)
     {
         const int c = op_class_of_prop(op);
+        payload_bytes += s.bl;
         if (FILL) {
             DeviceTask t;
             t.src_offset = s.off;
@@ -190,6 +193,8 @@ struct PropWalk {
             d_off = cnt[PROP_COL_BUF0 + vbuf];
             cnt[PROP_COL_BUF0 + vbuf] += prop_align(nvals, kPropBufElemSize(vbuf));
         }
+        output_bytes += vbytes + nvals * (vbuf >= 0 ? kPropBufElemSize(vbuf) : 0u);
+        if (flags & PROP_AUX_COPY) payload_bytes += Ds.bl;  // FLOAT / DOUBLE data is copied by the finish kernel, not by a decode task
         if (FILL) {
             covt_prop_column r;
             r.tile = tile; r.layer = layer;
@@ -224,6 +229,7 @@ struct PropWalk {
         }
         const uint64_t o_off = cnt[PROP_COL_BUF0 + COVT_PBUF_DICT_OFFSETS];
         cnt[PROP_COL_BUF0 + COVT_PBUF_DICT_OFFSETS] += prop_align(st == COVT_OK ? (uint64_t)n + 1u : 0u, 4);
+        if (st == COVT_OK) { output_bytes += 4ull * ((uint64_t)n + 1u); payload_bytes += Y.bl; }  // (the dictionary bytes stay in the blob: read by the consumer)
         if (FILL) {
             covt_prop_dictionary d;
             d.tile = tile; d.layer = layer; d.n_entries = n; d.status = st;
@@ -238,28 +244,42 @@ struct PropWalk {
     }
 };
 
-// pass 1 (FILL = false): pcols[col * n_tiles + tile] = the tile's sums; pass 2 (FILL = true): pcols holds exclusive prefixes
+// ONE THREAD PER LAYER of the finished geometry pass (the layer table holds where every complete layer's metadata starts): real
+// tiles are few and large — the 91 OMT fixture tiles carry ~12 layers and ~100 property columns each — so a thread per tile left
+// the GPU with 5 warps per SM walking 14 KB of metadata each (k0_props 4.5 + 5.1 ms per 23 296 tiles). Property columns exist for
+// complete layers only (a tile whose walk fails keeps the columns of the layers before the failure, like its geometry).
+// pass 1 (FILL = false): pcols[col * n_layers + layer] = the layer's sums; pass 2 (FILL = true): pcols holds exclusive prefixes
 template <bool FILL>
 __global__ void __launch_bounds__(K0_BLOCK)
-k0_props(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container, const uint32_t* tj_fields, uint32_t tj_layers,
-         uint64_t* pcols, PropOut out)
+k0_props(const uint8_t* blob, const uint64_t* tile_offsets, const covt_layer* layers, uint32_t n_layers, uint32_t container, const uint32_t* tj_fields,
+         uint32_t tj_layers, uint64_t* pcols, PropOut out, uint64_t* totals /* FILL: [0] += payload bytes, [1] += output bytes */)
 {
     __shared__ uint32_t s_lite[LITE_WORDS * K0_BLOCK];
-    const uint32_t t = blockIdx.x * K0_BLOCK + threadIdx.x;
-    if (t >= n_tiles) return;
+    const uint32_t l = blockIdx.x * K0_BLOCK + threadIdx.x;
+    if (l >= n_layers) return;
     const Lite lite = {s_lite + threadIdx.x};
+    const uint32_t tile = layers[l].tile;
+    const uint64_t start = layers[l].header_offset;
     PropWalk<FILL> pw;
     pw.blob = blob;
-    pw.tile_end = tile_offsets[t + 1];
-    pw.tile = t;
+    pw.tile_end = tile_offsets[tile + 1];
+    pw.tile = tile;
     pw.gen3 = container == COVT_CONTAINER_GEN3;
     pw.out = out;
 #pragma unroll
-    for (int i = 0; i < PROP_COLS; i++) pw.cnt[i] = FILL ? pcols[(uint64_t)i * n_tiles + t] + (i >= PROP_COL_CLASS0 ? out.class_off[i - PROP_COL_CLASS0] : 0ull) : 0ull;
-    walk_tile(blob, tile_offsets[t], tile_offsets[t + 1], container, tj_fields, tj_layers, lite, pw, [](uint32_t, const LayerHead&) {});
+    for (int i = 0; i < PROP_COLS; i++) pw.cnt[i] = FILL ? pcols[(uint64_t)i * n_layers + l] + (i >= PROP_COL_CLASS0 ? out.class_off[i - PROP_COL_CLASS0] : 0ull) : 0ull;
+    if (layers[l].num_columns > (layers[l].has_id ? 2u : 1u)) {  // (a layer without property columns: nothing to walk)
+        Cursor c = {blob, start, pw.tile_end, false};
+        LayerHead H;
+        pw.set_layer(layers[l].layer_index);
+        (void)walk_layer(c, container, tj_fields, tj_layers, lite, H, pw);  // parsed fine a moment ago: the layer is in the table
+    }
     if (!FILL) {
 #pragma unroll
-        for (int i = 0; i < PROP_COLS; i++) pcols[(uint64_t)i * n_tiles + t] = pw.cnt[i];
+        for (int i = 0; i < PROP_COLS; i++) pcols[(uint64_t)i * n_layers + l] = pw.cnt[i];
+    } else if (pw.payload_bytes | pw.output_bytes) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[0]), (unsigned long long)pw.payload_bytes);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&totals[1]), (unsigned long long)pw.output_bytes);
     }
 }
 
@@ -322,11 +342,14 @@ __global__ void __launch_bounds__(128) k_prop_finish_columns(const uint8_t* blob
         present_ok = false;
         if (st == COVT_OK) st = st_present;
     } else {
+        // (whole 32-bit words: the slice is 16-byte aligned and padded; bits behind the last feature are masked off)
+        const uint32_t* vw = reinterpret_cast<const uint32_t*>(validity);
+        const uint32_t nw = (F + 31u) / 32u;
         uint32_t cnt = 0;
-        for (uint32_t i = lane; i < VB; i += 32) {
-            uint32_t b = validity[i];
-            if (i + 1u == VB && (F & 7u)) b &= (1u << (F & 7u)) - 1u;
-            cnt += __popc(b);
+        for (uint32_t w = lane; w < nw; w += 32) {
+            uint32_t m = vw[w];
+            if (w + 1u == nw && (F & 31u)) m &= (1u << (F & 31u)) - 1u;
+            cnt += __popc(m);
         }
         n_valid = __reduce_add_sync(FULL, cnt);
     }
@@ -354,29 +377,54 @@ __global__ void __launch_bounds__(128) k_prop_finish_columns(const uint8_t* blob
         const uint32_t* vwords = reinterpret_cast<const uint32_t*>(validity);  // the slice is 16-byte aligned and padded
         uint32_t remaining = n_valid;
         void* vals = static_cast<uint8_t*>(out.buf[C.value_kind]) + C.values_offset * kPropBufElemSize(C.value_kind);  // COVT_PV_x == COVT_PBUF_x for x = 1..5
-        for (int64_t base = (int64_t)((F - 1u) / 32u) * 32; base >= 0; base -= 32) {
-            const uint32_t i = (uint32_t)base + lane;
-            uint32_t m = vwords[base >> 5];
-            if ((uint32_t)base + 32u > F) m &= (1u << (F - (uint32_t)base)) - 1u;
-            remaining -= (uint32_t)__popc(m);
-            const bool valid = (m >> lane) & 1u;
-            const uint32_t rank = remaining + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        const int32_t last_chunk = (int32_t)((F - 1u) / 32u);
+        constexpr int U = 8;  // chunks of 32 features per trip: their loads are in flight together (a 45 000-feature column is 1 400 chunks)
+        for (int32_t top = last_chunk; top >= 0; top -= U) {
+            uint32_t m[U], before[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) {
+                const int32_t ch = top - k;
+                m[k] = ch >= 0 ? vwords[ch] : 0u;
+                if (ch == last_chunk && (F & 31u)) m[k] &= (1u << (F & 31u)) - 1u;
+            }
+#pragma unroll
+            for (int k = 0; k < U; k++) { remaining -= (uint32_t)__popc(m[k]); before[k] = remaining; }
+            const uint32_t lt = (1u << lane) - 1u;
             if (C.value_kind == COVT_PV_BOOL) {
                 const uint8_t* bits = static_cast<const uint8_t*>(vals);
-                const uint32_t bit = valid ? (bits[rank >> 3] >> (rank & 7u)) & 1u : 0u;
-                const uint32_t word = __ballot_sync(FULL, bit != 0u);
+                uint32_t word[U];
+#pragma unroll
+                for (int k = 0; k < U; k++) {
+                    const uint32_t rank = before[k] + (uint32_t)__popc(m[k] & lt);
+                    const uint32_t bit = ((m[k] >> lane) & 1u) ? (bits[rank >> 3] >> (rank & 7u)) & 1u : 0u;
+                    word[k] = __ballot_sync(FULL, bit != 0u);
+                }
                 __syncwarp();
-                if (lane == 0) static_cast<uint32_t*>(vals)[base >> 5] = word;
+#pragma unroll
+                for (int k = 0; k < U; k++)
+                    if (lane == (unsigned)k && top - k >= 0) static_cast<uint32_t*>(vals)[top - k] = word[k];
             } else if (C.value_kind == COVT_PV_I64 || C.value_kind == COVT_PV_F64) {
                 uint64_t* a = static_cast<uint64_t*>(vals);
-                const uint64_t v = valid ? a[rank] : 0ull;
+                uint64_t v[U];
+#pragma unroll
+                for (int k = 0; k < U; k++) v[k] = ((m[k] >> lane) & 1u) ? a[before[k] + (uint32_t)__popc(m[k] & lt)] : 0ull;
                 __syncwarp();
-                if (i < F) a[i] = v;
+#pragma unroll
+                for (int k = 0; k < U; k++) {
+                    const int64_t i = ((int64_t)(top - k) << 5) + lane;
+                    if (top - k >= 0 && i < (int64_t)F) a[i] = v[k];
+                }
             } else {
                 uint32_t* a = static_cast<uint32_t*>(vals);
-                const uint32_t v = valid ? a[rank] : 0u;
+                uint32_t v[U];
+#pragma unroll
+                for (int k = 0; k < U; k++) v[k] = ((m[k] >> lane) & 1u) ? a[before[k] + (uint32_t)__popc(m[k] & lt)] : 0u;
                 __syncwarp();
-                if (i < F) a[i] = v;
+#pragma unroll
+                for (int k = 0; k < U; k++) {
+                    const int64_t i = ((int64_t)(top - k) << 5) + lane;
+                    if (top - k >= 0 && i < (int64_t)F) a[i] = v[k];
+                }
             }
             __syncwarp();
         }

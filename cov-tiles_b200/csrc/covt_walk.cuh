@@ -16,7 +16,10 @@
 
 namespace covt {
 
-constexpr int K0_BLOCK = 128;
+#ifndef K0_BLOCK_THREADS
+#define K0_BLOCK_THREADS 64
+#endif
+constexpr int K0_BLOCK = K0_BLOCK_THREADS;
 
 struct Cursor { const uint8_t* b; uint64_t p, end; bool err; };
 
@@ -111,6 +114,7 @@ struct Lite {
 };
 
 struct LayerHead {
+    uint64_t layer_start;   // blob offset of the first byte of the layer's metadata
     uint64_t name_offset;   // blob offset of the UTF-8 layer name; optimised gen-3: the TileJSON layerId
     uint32_t name_length, extent, num_features, num_columns;
     uint32_t geom_ct;       // covt_column_type of the geometry column
@@ -195,6 +199,7 @@ __device__ uint32_t walk_layer_gen2b(Cursor& c, const Lite& lite, LayerHead& H, 
 {
     const uint8_t* blob = c.b;
     lite.clear();
+    H.layer_start = c.p;
     c_string(c, H.name_offset, H.name_length);
     H.extent = c_varint(c);
     H.num_features = c_varint(c);
@@ -333,6 +338,7 @@ __device__ uint32_t walk_layer_gen3(Cursor& c, const uint32_t* tj_fields, uint32
 {
     const uint8_t* blob = c.b;
     lite.clear();
+    H.layer_start = c.p;
     const uint32_t header = c_byte(c);
     const bool optimized = header & 1u;  // :575-578
     uint32_t n_fields = 0;
@@ -431,6 +437,15 @@ __device__ uint32_t walk_layer_gen3(Cursor& c, const uint32_t* tj_fields, uint32
     if (p > c.end) return COVT_ERR_TRUNCATED;
     c.p = p;
     return COVT_OK;
+}
+
+// One layer at c.p (either grammar); on COVT_OK c.p is the first byte after the layer's payload.
+template <class Props>
+__device__ __forceinline__ uint32_t walk_layer(Cursor& c, uint32_t container, const uint32_t* tj_fields, uint32_t tj_layers, const Lite& lite,
+                                               LayerHead& H, Props& props)
+{
+    if (container == COVT_CONTAINER_GEN2B) return walk_layer_gen2b(c, lite, H, props);
+    return walk_layer_gen3(c, tj_fields, tj_layers, lite, H, props);
 }
 
 // Walks one tile; on_layer(layer_index, lite, H) is called for every complete layer. Returns the tile status.

@@ -198,7 +198,7 @@ typedef struct covt_layer {
     uint32_t n_coords;          /* V': vertices written to A_COORDS (V + closed rings) */
     uint32_t cap_parts;         /* allocation of the A_PART_OFFSETS slice minus 1 */
     uint32_t cap_rings;         /* allocation of the A_RING_OFFSETS slice minus 1 */
-    uint32_t reserved2[2];
+    uint64_t header_offset;     /* absolute blob offset of the first byte of this layer's metadata */
 } covt_layer;
 
 /* Stream-level request: one DecodingUtils call. */

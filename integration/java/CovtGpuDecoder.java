@@ -27,6 +27,20 @@ public final class CovtGpuDecoder implements AutoCloseable {
     private static final MethodHandle RESULT_BUFFER = h("covt_result_buffer", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle RESULT_READ = h("covt_result_read", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG, JAVA_LONG, ADDRESS));
     private static final MethodHandle RESULT_FREE = h("covt_result_free", FunctionDescriptor.ofVoid(ADDRESS));
+    // property columns (COVT_FLAG_DECODE_PROPERTIES): CovtParser.decodePropertyColumn, CovtParser.java:276-390
+    private static final MethodHandle RESULT_PROP_COLUMNS = h("covt_result_prop_columns", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle RESULT_PROP_DICTIONARIES = h("covt_result_prop_dictionaries", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle RESULT_PROP_READ = h("covt_result_prop_read", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG, JAVA_LONG, ADDRESS));
+    // the library's batch scheduler: one call, several GPUs of one box (one JVM)
+    private static final MethodHandle CREATE_MULTI = h("covt_create_multi", FunctionDescriptor.of(JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle DECODE_BATCH_MULTI = h("covt_decode_batch_multi",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle MULTI_RESULT_PART = h("covt_multi_result_part",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle MULTI_RESULT_FREE = h("covt_multi_result_free", FunctionDescriptor.ofVoid(ADDRESS));
+    private static final MethodHandle DESTROY_MULTI = h("covt_destroy_multi", FunctionDescriptor.ofVoid(ADDRESS));
+    public static final long PROP_COLUMN_BYTES = 72, PROP_DICTIONARY_BYTES = 40;  // sizeof(covt_prop_column / covt_prop_dictionary)
+    public static final int FLAG_DECODE_PROPERTIES = 0x80;
     private static final MethodHandle DECODE_STREAMS = h("covt_decode_streams",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
 
@@ -112,6 +126,29 @@ public final class CovtGpuDecoder implements AutoCloseable {
                 int rc = (int) RESULT_READ.invokeExact(res, which, elemOffset, count, host);
                 if (rc != 0) throw new IllegalArgumentException(lastError(ctx));
                 return host.asSlice(0, 4 * count).toArray(JAVA_INT);
+            }
+        }
+        /** The covt_prop_column records of the batch (72 bytes each, layout in include/covt_b200.h): one per property column. */
+        public MemorySegment propertyColumns(int[] count) throws Throwable {
+            try (Arena a = Arena.ofConfined()) {
+                MemorySegment p = a.allocate(ADDRESS), n = a.allocate(JAVA_INT);
+                int rc = (int) RESULT_PROP_COLUMNS.invokeExact(res, p, n);
+                if (rc != 0) throw new IllegalArgumentException(lastError(ctx));
+                count[0] = n.get(JAVA_INT, 0);
+                return p.get(ADDRESS, 0).reinterpret(PROP_COLUMN_BYTES * count[0]);
+            }
+        }
+        /** INT_64 property column -> Optional-like long[] + present[] (CovtParser.java:296-326): slot i belongs to feature i. */
+        public long[] readLongColumn(MemorySegment col, boolean[] present) throws Throwable {
+            try (Arena a = Arena.ofConfined()) {
+                int F = col.get(JAVA_INT, 40);                                   // num_features
+                long validityOffset = col.get(JAVA_LONG, 48), valuesOffset = col.get(JAVA_LONG, 56);
+                MemorySegment bits = a.allocate(Math.max((F + 7) / 8, 1)), vals = a.allocate(JAVA_LONG, Math.max(F, 1));
+                int rc = (int) RESULT_PROP_READ.invokeExact(res, 0 /*COVT_PBUF_VALIDITY*/, validityOffset, (long) ((F + 7) / 8), bits);
+                if (rc == 0) rc = (int) RESULT_PROP_READ.invokeExact(res, 1 /*COVT_PBUF_I64*/, valuesOffset, (long) F, vals);
+                if (rc != 0) throw new IllegalArgumentException(lastError(ctx));
+                for (int i = 0; i < F; i++) present[i] = ((bits.get(JAVA_BYTE, i >> 3) >> (i & 7)) & 1) != 0;
+                return vals.asSlice(0, 8L * F).toArray(JAVA_LONG);
             }
         }
         @Override public void close() { try { RESULT_FREE.invokeExact(res); } catch (Throwable t) { throw sneaky(t); } }

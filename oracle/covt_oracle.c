@@ -722,6 +722,10 @@ static void sink_set_layer(prop_sink_t* k, uint32_t li);
 static void sink_begin_column(prop_sink_t* k, uint64_t noff, uint32_t nlen, uint32_t dt, uint32_t ct, uint32_t F);
 static void sink_stream(prop_sink_t* k, uint32_t st, uint64_t sub_off, uint32_t sub_len, uint32_t nv, uint32_t bl, uint32_t enc, uint64_t off);
 static void sink_end_column(prop_sink_t* k);
+/* property columns exist for COMPLETE layers only: a layer whose walk fails takes back what it emitted */
+typedef struct { uint64_t n[11]; uint64_t payload_bytes; } sink_mark_t;
+static void sink_mark(prop_sink_t* k, sink_mark_t* m);
+static void sink_rollback(prop_sink_t* k, const sink_mark_t* m);
 static int name_starts(const uint8_t* b, uint64_t off, uint32_t len, const char* s)
 {
     size_t n = strlen(s);
@@ -768,6 +772,7 @@ static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, ui
         covt_layer* L = &layers[*n_layers];
         layer_init(L, tile, li);
         sink_set_layer(sink, li);
+        const uint64_t layer_start = c.p;
         c_string(&c, &L->name_offset, &L->name_length);
         L->extent = c_varint(&c);
         L->num_features = c_varint(&c);
@@ -835,6 +840,8 @@ static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, ui
             rc = COVT_ERR_BAD_METADATA;
         /* payloads in column-metadata order */
         uint64_t p = c.p;
+        sink_mark_t mark;
+        sink_mark(sink, &mark);
         for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
             if (cols[ci].kind == COL_ID) place_id(L, &p);
             else if (cols[ci].kind == COL_GEOMETRY) place_geometry(L, &p);
@@ -872,7 +879,8 @@ static int32_t parse_gen2b(const uint8_t* blob, uint64_t begin, uint64_t end, ui
             if (p > end) rc = COVT_ERR_TRUNCATED;
         }
         free(cols);
-        if (rc != COVT_OK) return rc;
+        if (rc != COVT_OK) { sink_rollback(sink, &mark); return rc; }
+        L->header_offset = layer_start;
         layer_resolve_ops(L, flags);
         c.p = p;
         (*n_layers)++;
@@ -909,6 +917,7 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
         covt_layer* L = &layers[*n_layers];
         layer_init(L, tile, li);
         sink_set_layer(sink, li);
+        const uint64_t layer_start = c.p;
         uint32_t header = c_byte(&c);
         int optimized = header & 1; /* :575-578 */
         uint32_t n_fields = 0;
@@ -992,6 +1001,8 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
         /* payloads in column-metadata order. Property columns: BOOLEAN = listed data stream only (CovtParser.java:280-290);
          * every other type = unlisted Byte-RLE present stream of ceil(numFeatures/8) bytes (:295) + its listed streams */
         uint64_t p = c.p;
+        sink_mark_t mark;
+        sink_mark(sink, &mark);
         for (uint32_t ci = 0; ci < L->num_columns && rc == COVT_OK; ci++) {
             if (cols[ci].kind == COL_ID) place_id(L, &p);
             else if (cols[ci].kind == COL_GEOMETRY) place_geometry(L, &p);
@@ -1035,7 +1046,8 @@ static int32_t parse_gen3(const uint8_t* blob, uint64_t begin, uint64_t end, con
             if (p > end) rc = COVT_ERR_TRUNCATED;
         }
         free(cols);
-        if (rc != COVT_OK) return rc;
+        if (rc != COVT_OK) { sink_rollback(sink, &mark); return rc; }
+        L->header_offset = layer_start;
         layer_resolve_ops(L, flags);
         c.p = p;
         (*n_layers)++;
@@ -1494,6 +1506,7 @@ typedef struct { uint64_t off; uint32_t nv, bl, enc; int have; } ps_t;
 typedef struct { uint32_t st_present, st_data, fill_ones, present_decoded; } paux_t;
 typedef struct {
     vec_t cols, aux, dicts, dict_st, validity, i64, f32, f64, bools, didx, doff;
+    uint64_t payload_bytes;
     int oom;
 } props_build_t;
 
@@ -1598,6 +1611,7 @@ static void prop_emit(prop_sink_t* k, const ps_t* Ps, const ps_t* Ds, uint64_t s
     int64_t d_at = vec_slice(vb, n_alloc);
     if (v_at < 0 || d_at < 0) { B->oom = 1; c->status = COVT_ERR_OOM; return; }
     a->fill_ones = (uint32_t)fill_ones;
+    B->payload_bytes += (use_p ? Ps->bl : 0u) + (uint64_t)Ds->bl;
     if (use_p) {
         a->st_present = prop_byte_rle(blob, Ps, VB, (uint8_t*)B->validity.p + v_at);
         a->present_decoded = 1;
@@ -1649,10 +1663,27 @@ static void prop_emit_dictionary(prop_sink_t* k)
     if (st != COVT_OK) return;
     int64_t at = vec_slice(&B->doff, (uint64_t)n + 1);
     if (at < 0) { B->oom = 1; d->status = COVT_ERR_OOM; return; }
+    B->payload_bytes += (uint64_t)k->L.bl + k->Y.bl;
     *lst = prop_rle(k->blob, &k->L, n, 0, NULL, (int32_t*)B->doff.p + at + 1);
 }
 
 static void sink_set_layer(prop_sink_t* k, uint32_t li) { if (k) k->layer = li; }
+static void sink_mark(prop_sink_t* k, sink_mark_t* m)
+{
+    if (!k) return;
+    props_build_t* B = k->B;
+    vec_t* v[11] = {&B->cols, &B->aux, &B->dicts, &B->dict_st, &B->validity, &B->i64, &B->f32, &B->f64, &B->bools, &B->didx, &B->doff};
+    for (int i = 0; i < 11; i++) m->n[i] = v[i]->n;
+    m->payload_bytes = B->payload_bytes;
+}
+static void sink_rollback(prop_sink_t* k, const sink_mark_t* m)
+{
+    if (!k) return;
+    props_build_t* B = k->B;
+    vec_t* v[11] = {&B->cols, &B->aux, &B->dicts, &B->dict_st, &B->validity, &B->i64, &B->f32, &B->f64, &B->bools, &B->didx, &B->doff};
+    for (int i = 0; i < 11; i++) v[i]->n = m->n[i];
+    B->payload_bytes = m->payload_bytes;
+}
 static void sink_begin_column(prop_sink_t* k, uint64_t noff, uint32_t nlen, uint32_t dt, uint32_t ct, uint32_t F)
 {
     k->noff = noff; k->nlen = nlen; k->dt = dt; k->ct = ct; k->F = F;
@@ -1841,6 +1872,7 @@ int32_t covt_oracle_decode_properties(const uint8_t* blob, const uint64_t* tile_
     R->bools = (uint8_t*)B.bools.p;                  R->bool_bytes = B.bools.n;
     R->dict_index = (int32_t*)B.didx.p;              R->n_dict_index = B.didx.n;
     R->dict_offsets = (int32_t*)B.doff.p;            R->n_dict_offsets = B.doff.n;
+    R->payload_bytes = B.payload_bytes;
     if (rc != COVT_OK) { covt_oracle_props_free(R); return rc; }
     *out = R;
     return COVT_OK;

@@ -107,6 +107,7 @@ typedef struct covt_oracle_props {
     uint8_t* bools;     uint64_t bool_bytes;
     int32_t* dict_index; uint64_t n_dict_index;
     int32_t* dict_offsets; uint64_t n_dict_offsets;
+    uint64_t payload_bytes;      /* byteLength of every property stream handed to a codec (+ dictionary bytes): the metric's unit */
 } covt_oracle_props;
 int32_t covt_oracle_decode_properties(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
                                       const covt_tilejson* tj, uint32_t flags, covt_oracle_props** out);

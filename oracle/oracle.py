@@ -190,7 +190,8 @@ class OracleProps(C.Structure):
                 ("validity", C.POINTER(C.c_uint8)), ("validity_bytes", C.c_uint64), ("i64", C.POINTER(C.c_int64)), ("n_i64", C.c_uint64),
                 ("f32", C.POINTER(C.c_float)), ("n_f32", C.c_uint64), ("f64", C.POINTER(C.c_double)), ("n_f64", C.c_uint64),
                 ("bools", C.POINTER(C.c_uint8)), ("bool_bytes", C.c_uint64), ("dict_index", C.POINTER(C.c_int32)),
-                ("n_dict_index", C.c_uint64), ("dict_offsets", C.POINTER(C.c_int32)), ("n_dict_offsets", C.c_uint64)]
+                ("n_dict_index", C.c_uint64), ("dict_offsets", C.POINTER(C.c_int32)), ("n_dict_offsets", C.c_uint64),
+                ("payload_bytes", C.c_uint64)]
 
 
 PV_NONE, PV_I64, PV_F32, PV_F64, PV_BOOL, PV_DICT_INDEX = range(6)
@@ -205,6 +206,7 @@ class PropsResult:
         def arr(p, n, dt):
             return _copy_from(p, n * np.dtype(dt).itemsize, dt) if n else np.zeros(0, dtype=dt)
         self.tile_status = arr(r.tile_status, r.n_tiles, np.uint32)
+        self.payload_bytes = int(r.payload_bytes)
         self.columns = (np.frombuffer(C.string_at(r.columns, r.n_columns * C.sizeof(PropColumn)), dtype=abi.PROP_COLUMN_DTYPE).copy()
                         if r.n_columns else np.zeros(0, dtype=abi.PROP_COLUMN_DTYPE))
         self.dictionaries = (np.frombuffer(C.string_at(r.dictionaries, r.n_dictionaries * C.sizeof(PropDictionary)), dtype=abi.PROP_DICTIONARY_DTYPE).copy()

@@ -39,6 +39,8 @@ def test_property_columns_of_all_fixtures_vs_oracle(covt, oracle, decoder, fixtu
     assert {abi.PV_I64, abi.PV_F32, abi.PV_BOOL, abi.PV_DICT_INDEX} <= kinds
     ref = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags)
     util.compare_results(abi, res, ref)
+    # the metric's unit: compressed bytes of every decoded stream, geometry + properties
+    assert res.timing()["payload_bytes"] == ref.payload_bytes + want.payload_bytes and want.payload_bytes > 2_000_000
     res.free()
     # without the flag: no property columns, no property buffers
     res = decoder.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags)
