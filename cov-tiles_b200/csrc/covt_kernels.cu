@@ -960,9 +960,10 @@ __global__ void k_alg_bytes(const covt_layer* layers, uint32_t n_layers_bound, u
         if (!(flags & COVT_FLAG_SKIP_ASSEMBLY) && L.status == COVT_OK) {
             const uint64_t F = slot_nv(L, COVT_SLOT_TYPES);
             const uint64_t wr = 4ull * ((F + 1) + (L.n_parts + 1ull) + (L.n_rings + 1ull)) + 8ull * L.n_coords;
-            // reads: types, the three count streams, one offset per vertex for ICE layers, one (x,y) per output vertex
+            // SURVEY §8(d) unit cost of the assembler: 4 B offset read + 8 B coordinate written per vertex (+ 8 B gathered through L2
+            // for ICE layers); the PLAIN vertices it re-reads from S_VERTEX_BUFFER are an intermediate round trip, not algorithmic bytes
             const uint64_t rd = F + 4ull * (slot_nv(L, COVT_SLOT_GEOM) + slot_nv(L, COVT_SLOT_PART) + slot_nv(L, COVT_SLOT_RING)) +
-                                (L.streams[COVT_SLOT_VOFF].encoding != COVT_ENC_ABSENT ? 4ull * L.n_vertices : 0ull) + 8ull * L.n_coords;
+                                (L.streams[COVT_SLOT_VOFF].encoding != COVT_ENC_ABSENT ? (4ull + 8ull) * L.n_vertices : 0ull);
             acc[NUM_OP_CLASSES] += wr + rd;
         }
     }

@@ -44,10 +44,16 @@ def test_struct_layout_matches_header(covt, tmp_path):
                     'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(covt_stream_ref), sizeof(covt_layer), sizeof(covt_stream_desc),'
                     ' sizeof(covt_timing), sizeof(covt_kernel_time), sizeof(covt_tilejson));\n'
                     'printf("%zu %zu %zu %zu\\n", offsetof(covt_layer, streams), offsetof(covt_layer, out), offsetof(covt_layer, n_parts),'
-                    ' offsetof(covt_stream_desc, out_offset));\nreturn 0;}\n')
+                    ' offsetof(covt_stream_desc, out_offset));\n'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(covt_prop_column), sizeof(covt_prop_dictionary), offsetof(covt_prop_column, status),'
+                    ' offsetof(covt_prop_column, validity_offset), offsetof(covt_prop_column, data_num_values), offsetof(covt_prop_dictionary, offsets_offset),'
+                    ' offsetof(covt_layer, header_offset));\nreturn 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
-    a, b = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    a, b, c = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    assert [int(x) for x in c.split()] == [C.sizeof(abi.PropColumn), C.sizeof(abi.PropDictionary), abi.PropColumn.status.offset,
+                                            abi.PropColumn.validity_offset.offset, abi.PropColumn.data_num_values.offset,
+                                            abi.PropDictionary.offsets_offset.offset, abi.Layer.header_offset.offset]
     assert [int(x) for x in a.split()] == [C.sizeof(abi.StreamRef), C.sizeof(abi.Layer), C.sizeof(abi.StreamDesc),
                                             C.sizeof(abi.Timing), C.sizeof(abi.KernelTime), C.sizeof(abi.TileJson)]
     assert [int(x) for x in b.split()] == [abi.Layer.streams.offset, abi.Layer.out.offset, abi.Layer.n_parts.offset,

@@ -140,3 +140,54 @@ def test_property_mutation_fuzz_against_oracle(covt, oracle, gen, decoder, fixtu
     ref = oracle.decode_batch(blob, offs, container, flags)
     util.compare_results(abi, res, ref)
     res.free()
+
+
+def test_property_columns_through_the_pipelined_host_path(covt, oracle, fixtures, monkeypatch):
+    """covt_decode_batch uploads and decodes in segments; the property pass runs once over the layer table of the whole batch.
+    Fixture tiles x3 in many small segments (and again after a capacity retry: small synthetic-size tiles first, big ones last)."""
+    abi = covt.abi
+    monkeypatch.setenv("COVT_SEG_BYTES", str(1 << 20))
+    monkeypatch.setenv("COVT_MAX_SEGMENTS", "64")
+    monkeypatch.setenv("COVT_SEG_MIN_TILES", "16")
+    dec = covt.Decoder(0)
+    try:
+        flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+        tiles = sorted([b for n, b in fixtures if n.startswith("omt/")], key=len) * 3
+        blob, offs = util.concat_tiles(tiles)
+        res, got, want = _decode_props_both(covt, oracle, dec, blob, offs, abi.CONTAINER_GEN2B, flags)
+        t = res.timing()
+        assert t["segments"] >= 4
+        n, n_ok = util.compare_props(abi, blob, got, want)
+        assert n > 20000 and n_ok == n
+        util.compare_results(abi, res, oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags))
+        res.free()
+    finally:
+        dec.close()
+
+
+def test_property_columns_two_gpus_one_call(covt, oracle, fixtures):
+    """The library's batch scheduler passes the flag through: every part of the multi-GPU result carries the property columns of
+    its tile range (tile indices relative to the part)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    abi = covt.abi
+    flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+    tiles = [b for n, b in fixtures if n.startswith("omt/")]
+    blob, offs = util.concat_tiles(tiles)
+    md = covt.MultiDecoder([0, 1])
+    try:
+        mres = md.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags | abi.FLAG_DECODE_PROPERTIES)
+        total = 0
+        for p in mres.parts:
+            t0, n = p["first_tile"], p["n_tiles"]
+            sub_blob = blob[int(offs[t0]):int(offs[t0 + n])]
+            sub_offs = offs[t0:t0 + n + 1] - offs[t0]
+            want = oracle.decode_properties(sub_blob, sub_offs, abi.CONTAINER_GEN2B, flags)
+            k, k_ok = util.compare_props(abi, sub_blob, util.GpuProps(abi, p["result"]), want)
+            assert k_ok == k
+            total += k
+        assert total > 9000
+        mres.free()
+    finally:
+        md.close()

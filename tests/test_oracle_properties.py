@@ -10,6 +10,8 @@ The 27 Bing tiles have no partner: their FLOAT and BOOLEAN columns are only chec
 import json
 import os
 
+import numpy as np
+
 import canon
 import util
 
@@ -95,3 +97,44 @@ def test_c_property_oracle_equals_the_pinned_statement(oracle, fixtures):
                 n_cols += 1
     assert n_cols >= 13000 and {oracle.PV_I64, oracle.PV_F32, oracle.PV_BOOL, oracle.PV_DICT_INDEX} <= kinds
     assert not res.dictionaries["status"].any()
+
+
+def test_gen3_property_columns_equal_gen2b(oracle, gen, fixtures):
+    """The HEAD container (CovtParser.decodeLayerMetadata :574-652 + decodePropertyColumn :276-390: unlisted Byte-RLE present streams,
+    BOOLEAN data as one bit per feature): gen-3 re-wraps of fixture tiles, optimised metadata and not, decode to the values of the
+    gen-2b tiles they were made from (localized dictionaries, which HEAD cannot write, are dropped by the re-wrap)."""
+    import covt_loader
+    abi = covt_loader.load().abi
+    names = [n for n, _ in fixtures if n.startswith(("omt/5_", "omt/10_", "amazon/6_", "bing/"))][:16]
+    fx = dict(fixtures)
+    blob2, offs2 = util.concat_tiles([fx[n] for n in names])
+    w2 = oracle.decode_properties(blob2, offs2, abi.CONTAINER_GEN2B)
+    keep = [c for c in w2.columns if c["column_type"] != abi.CT_LOCALIZED_DICTIONARY]
+    for optimized in (False, True):
+        tiles, n_fields = [], None
+        for n in names:
+            t, nf = util.rewrap_gen3(abi, oracle, fx[n], optimized=optimized, props=True, gen=gen)
+            if optimized:
+                n_fields = nf if n_fields is None else [max(a, b) for a, b in zip(n_fields + [0] * (len(nf) - len(n_fields)), nf + [0] * (len(n_fields) - len(nf)))]
+            tiles.append(t)
+        blob, offs = util.concat_tiles(tiles)
+        w = oracle.decode_properties(blob, offs, abi.CONTAINER_GEN3, n_fields=n_fields)
+        assert not w.tile_status.any() and not w.columns["status"].any() and len(w.columns) == len(keep) > 400
+        for a, c in zip(w.columns, keep):
+            va, vc = w.column_values(blob, a), w2.column_values(blob2, c)
+            if a["value_kind"] == abi.PV_BOOL:  # HEAD booleans have no nulls: the re-wrap writes an absent value as false
+                vc = [bool(v) for v in vc]
+            assert va == vc, (util.prop_column_key(blob2, c), va[:6], vc[:6])
+
+
+def test_property_columns_exist_for_complete_layers_only(oracle, fixtures):
+    """A tile cut in the middle of a layer keeps the property columns of the layers before it, nothing of the broken one."""
+    name, data = next((n, b) for n, b in fixtures if n == "omt/5_16_21")
+    full = oracle.decode_properties(*util.concat_tiles([data]))
+    rc, layers, _ = oracle.parse_tile(np.frombuffer(data, np.uint8), 0, flags=0)
+    cut = int(layers[3]["streams"][1]["byte_offset"]) + 5  # inside the payload of layer 3
+    part = oracle.decode_properties(*util.concat_tiles([data[:cut]]))
+    assert part.tile_status[0] != 0
+    n_before = int((full.columns["layer"] < 3).sum())
+    assert len(part.columns) == n_before > 0 and set(int(x) for x in part.columns["layer"]) == {0, 1, 2}
+    assert np.array_equal(part.columns["status"], full.columns["status"][:n_before])
