@@ -297,10 +297,10 @@ def build_workload(args, rank, for_cpu=False, world=1, sync=None):
                "l2": "inputs (%.2f GB) and outputs far larger than the 126 MB L2" % (len(blob) / 1e9)}
         truth = dict(truth, whole_batch=True)
         if world > 1 and not for_cpu:
-            starts = covt.partition_tiles(offs, world)  # the batch scheduler's split (host only)
-            t0, t1 = int(starts[rank]), int(starts[rank + 1])
-            blob = blob[int(offs[t0]):int(offs[t1])].copy()
-            offs = (offs[t0:t1 + 1] - offs[t0]).astype(np.uint64)
+            # this rank's range of the ONE batch: covt_partition_tiles (the split the library scheduler makes inside
+            # covt_decode_batch_multi) through the one-process-per-GPU helper of the package
+            blob, offs, _first_tile = covt.scheduler.rank_slice(blob, offs, rank, world)
+            blob, offs = blob.copy(), offs.astype(np.uint64)
     elif args.workload == "tiles":
         n = args.tiles
         blob, offs, truth = make_tiles(rank * n, n)

@@ -141,9 +141,11 @@ class Result:
         self._layers = None
 
     def free(self):
-        if self._h:
+        # (a result outlives its context only by accident — e.g. an exception between decode and free followed by Decoder.close();
+        # the context owned the device blocks, so there is nothing left to give back and the handle must not be touched)
+        if self._h and getattr(self._dec, "_h", None):
             lib().covt_result_free(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
@@ -575,3 +577,4 @@ class CovtParser:
             })
         res.free()
         return layers
+from . import scheduler  # noqa: E402,F401  (one-process-per-GPU helpers over partition_tiles)

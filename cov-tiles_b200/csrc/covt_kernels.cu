@@ -901,6 +901,69 @@ k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, ui
     lean_rows4_dispatch(S.post, false, A, s4, min(n_here, room), S.dst, P.count, cx, cy, S.num_bits, S.no_shift != 0);
 }
 
+// Error path of the large streams. k1b_decode reports COVT_ERR_VARINT_OVERLONG when a value with four continuation bytes lies
+// before the stream's numValues-th terminator. The Java reader ends such a value after its 4th byte (DecodingUtils.java:157-186),
+// so it counts more values than there are terminators: the stream may reach numValues earlier than the terminator count says
+// (other bytes consumed) or where the terminator count falls short — or run out of bytes (COVT_ERR_TRUNCATED). One block per
+// stream redoes the count the way Java reads. A run (the bytes after a terminator up to and including the next terminator)
+// parses the same wherever the parse started before it, so every thread owns the runs that START in its slice of the stream.
+constexpr int K1_RESOLVE_THREADS = 256;
+struct JavaRunWalk { uint64_t p; uint32_t count; bool truncated; };
+// walks the runs that start in [p, hi); stops early once `limit` values are complete (p = right after that value)
+__device__ __forceinline__ JavaRunWalk java_walk_runs(const uint8_t* src, uint64_t p, uint64_t hi, uint64_t len, uint64_t limit)
+{
+    JavaRunWalk w{p, 0u, false};
+    uint64_t count = 0;
+    while (w.p < hi && w.p < len && count < limit) {
+        for (;;) {  // one Java value per trip; leaves at the run's terminator
+            int k = 0;
+            bool term = false;
+            while (k < 4 && w.p < len) { k++; if (!(src[w.p++] & 0x80u)) { term = true; break; } }
+            if (!term && k < 4) { w.truncated = true; w.count = (uint32_t)count; return w; }  // the bytes end inside a value
+            count++;
+            if (term || count >= limit) break;
+            if (w.p >= len) break;  // ended on a 4-byte value
+        }
+    }
+    w.count = (uint32_t)umin64(count, 0xffffffffull);
+    return w;
+}
+__global__ void __launch_bounds__(K1_RESOLVE_THREADS) k1_resolve_overlong(const uint8_t* blob, const BigStream* streams)
+{
+    const BigStream S = streams[blockIdx.x];
+    if (*S.status_out != (uint32_t)COVT_ERR_VARINT_OVERLONG) return;  // (block-uniform)
+    __shared__ uint64_t s_count[K1_RESOLVE_THREADS];
+    __shared__ uint64_t s_start[K1_RESOLVE_THREADS];
+    const uint8_t* src = blob + S.src_offset;
+    const uint64_t len = S.byte_length;
+    const uint64_t per = (len + K1_RESOLVE_THREADS - 1) / K1_RESOLVE_THREADS;
+    const uint64_t lo = umin64(len, per * threadIdx.x), hi = umin64(len, lo + per);
+    uint64_t p = lo;  // first run start in the slice
+    if (p > 0) while (p < hi && (src[p - 1] & 0x80u)) p++;
+    if (p > 0 && p == hi && hi > lo && (src[p - 1] & 0x80u)) p = len;  // no run starts here
+    if (lo == hi) p = len;
+    const JavaRunWalk w = java_walk_runs(src, p, hi, len, ~0ull);
+    s_count[threadIdx.x] = w.count;
+    s_start[threadIdx.x] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t before = 0;
+        uint32_t status = COVT_ERR_TRUNCATED, consumed = (uint32_t)len;
+        for (int t = 0; t < K1_RESOLVE_THREADS; t++) {
+            if (before + s_count[t] >= S.num_values) {  // value #num_values ends in a run of slice t
+                const uint64_t per_t = umin64(len, per * (uint64_t)t + per);
+                const JavaRunWalk f = java_walk_runs(src, s_start[t], per_t, len, S.num_values - before);
+                status = COVT_ERR_VARINT_OVERLONG;
+                consumed = (uint32_t)f.p;
+                break;
+            }
+            before += s_count[t];
+        }
+        *S.status_out = status;
+        if (S.consumed_out) *S.consumed_out = consumed;
+    }
+}
+
 // =================================================================================================
 // finalize: tile status = first layer error (unless the container walk already failed), totals
 // =================================================================================================
@@ -1110,6 +1173,7 @@ cudaError_t launch_k1_varint_stream(const uint8_t* blob, const BigStream* stream
     k1_scan_blocks<<<1, K1_SCAN_BLOCK, 0, st>>>(block_states, nb);
     k1_scan_apply<<<nb, K1_SCAN_BLOCK, 0, st>>>(states, n_chunks, block_states);
     k1b_decode<<<grid, K1_WARPS * 32, 0, st>>>(blob, streams, n_streams, n_chunks, states);
+    k1_resolve_overlong<<<n_streams, K1_RESOLVE_THREADS, 0, st>>>(blob, streams);  // error path only: returns at once otherwise
     return cudaGetLastError();
 }
 

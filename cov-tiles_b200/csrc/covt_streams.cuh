@@ -29,6 +29,22 @@ __device__ __forceinline__ uint32_t chunk_cut_position(uint32_t emit, uint32_t l
     return __shfl_sync(FULL, pos, __ffs(b) - 1);
 }
 
+// The Java int-varint reader (DecodingUtils.java:157-186: at most 4 bytes, the 4th byte ends the value whatever its MSB says) over
+// a stream that holds a value with four continuation bytes, sequentially: COVT_ERR_TRUNCATED when the bytes end before value
+// #num_values does, else COVT_ERR_VARINT_OVERLONG and the bytes consumed. Error path only (one thread).
+__device__ __noinline__ void java_varint32_recount(const uint8_t* src, uint64_t byte_length, uint32_t num_values, uint32_t& status, uint32_t& consumed)
+{
+    uint64_t p = 0;
+    for (uint32_t i = 0; i < num_values; i++) {
+        for (int k = 0; k < 4; k++) {
+            if (p >= byte_length) { status = COVT_ERR_TRUNCATED; consumed = (uint32_t)p; return; }
+            if (!(src[p++] & 0x80u)) break;
+        }
+    }
+    status = COVT_ERR_VARINT_OVERLONG;
+    consumed = (uint32_t)p;
+}
+
 __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t* stage, StreamOutcome& out, const int post, const bool widen)
 {
     const unsigned lane = lane_id();
@@ -89,8 +105,17 @@ __device__ __noinline__ void warp_varint32_stream(const StreamTask& t, uint32_t*
         produced += n;
     }
     out.consumed = t.exact_length == 1 ? t.byte_length : consumed;
-    if (produced < t.num_values) out.status = COVT_ERR_TRUNCATED;  // Java: ArrayIndexOutOfBounds
-    else if (__any_sync(FULL, (ov >> 28) & 1u)) out.status = COVT_ERR_VARINT_OVERLONG;
+    if (__any_sync(FULL, (ov >> 28) & 1u)) {
+        // Error path. A value with four continuation bytes: the Java reader stops after the 4th byte whatever its MSB says
+        // (DecodingUtils.java:157-186), so it counts MORE values than there are terminators and may reach numValues where the
+        // terminator count falls short (or end earlier). Status and bytes consumed follow the Java reader exactly: one lane walks
+        // the stream the way it does. (The values of such a stream are unspecified, see COVT_ERR_VARINT_OVERLONG.)
+        uint32_t st = 0, cons = 0;
+        if (lane == 0) java_varint32_recount(t.src, t.byte_length, t.num_values, st, cons);
+        out.status = __shfl_sync(FULL, st, 0);
+        cons = __shfl_sync(FULL, cons, 0);
+        if (t.exact_length != 1) out.consumed = cons;
+    } else if (produced < t.num_values) out.status = COVT_ERR_TRUNCATED;  // Java: ArrayIndexOutOfBounds
     else out.status = COVT_OK;
 }
 

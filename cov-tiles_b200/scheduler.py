@@ -1,4 +1,6 @@
-"""Batch scheduler: partitions independent tiles by tile index across the GPUs of one box.
+"""One-process-per-GPU view of the batch scheduler: which contiguous tile range of ONE host batch a rank decodes.
+The split is covt_partition_tiles — the same call the in-library scheduler (covt_decode_batch_multi, csrc/covt_multi.cu: one
+process, N GPUs) makes; bench.py uses rank_slice under torchrun, tests/test_partition_gloo.py covers it with gloo on CPU.
 
 Tiles share nothing (CovtParser.java:56-131 keeps no cross-layer state; every delta chain starts from 0,
 DecodingUtils.java:57,97-98,396), so the data path has NO collective: rank g decodes the contiguous tile range

@@ -328,6 +328,8 @@ int32_t covt_abi_version(void);
  * time — that is how covt_decode_batch_multi drives several GPUs — so a multi-threaded caller (e.g. a JVM thread pool) creates
  * one context per thread. */
 int32_t covt_create(int32_t device, covt_ctx** out);
+/* Free the context's batches and results first: they borrow its streams and device blocks (a result freed after its context is
+ * undefined behaviour, like free() after the allocator is gone). */
 void    covt_destroy(covt_ctx* ctx);
 /* Copies the last error message of this context (or of a failed covt_create when ctx == NULL). */
 int32_t covt_last_error(covt_ctx* ctx, char* buf, size_t buf_len);

@@ -185,6 +185,40 @@ def test_malformed_streams(covt, oracle, gen, decoder):
     _batch_check(covt, oracle, decoder, cases)
 
 
+def test_overlong_varints_follow_the_java_reader(covt, oracle, gen, decoder):
+    """A value with four continuation bytes: the Java reader ends it after the 4th byte (DecodingUtils.java:157-186), so it counts
+    more values than the stream has terminators. Status (OVERLONG vs TRUNCATED) and bytes consumed equal the oracle's exactly,
+    in the warp-per-stream decoder and in the large-stream kernels (found by the property-column fuzzer, seed 307)."""
+    abi = covt.abi
+    five = [0x80, 0x80, 0x80, 0x80, 0x01]
+    small = [
+        ([0xCE, 0xB9, 0xA9, 0xB8, 0x01], 2), ([0xCE, 0xB9, 0xA9, 0xB8], 2), ([0xCE, 0xB9, 0xA9, 0xB8], 1), (five * 10, 10), (five * 10, 20),
+        (five * 10, 21), ([1, 2, 3] + five + [4, 5], 6), ([1, 2, 3] + five + [4, 5], 7), ([1, 2, 3] + five + [4, 5], 8),
+        ([0x80] * 9 + [1, 2], 3), ([0x80] * 9 + [1, 2], 4), ([0x80] * 9 + [1, 2], 5), ([0x80] * 700 + [1], 176), ([0x80] * 700 + [1], 177),
+    ]
+    enc, vals = gen.varint_stream((1 << 18) + 4096, seed=5)
+    enc = np.asarray(enc, dtype=np.uint8)
+    for at in (100, 200_001):  # an overlong run early / late in a large stream (decoded over many CTAs)
+        while enc[at - 1] & 0x80:
+            at += 1
+        big = np.concatenate([enc[:at], np.array([0x81] * 6 + [0x01], np.uint8), enc[at:]])
+        for n in (vals, vals + 1, vals + 2, vals + 3, vals // 2):
+            small.append((big, n))
+    flagged = 0
+    for op in (abi.OP_VARINT_ZZ_DELTA, abi.OP_VARINT_U32, abi.OP_VARINT_ZZ_DELTA_AS_I64):
+        for payload, n in small:
+            payload = np.asarray(payload, dtype=np.uint8)
+            if len(payload) > 4096 and op != abi.OP_VARINT_ZZ_DELTA:
+                continue
+            blob = np.concatenate([np.zeros(5, np.uint8), payload, np.zeros(64, np.uint8)])
+            got, st, cons = decoder.decode_stream(blob, op, byte_offset=5, byte_length=len(payload), num_values=n)
+            want, wst, wcons = oracle.decode_stream(blob, op, byte_offset=5, byte_length=len(payload), num_values=n)
+            assert (st, cons) == (wst, wcons), "op %s, %d bytes, n=%d: status/consumed %s vs oracle %s" % (
+                abi.OP_NAMES[op], len(payload), n, (st, cons), (wst, wcons))
+            flagged += wst in (abi.ERR_VARINT_OVERLONG, abi.ERR_TRUNCATED)
+    assert flagged >= 60
+
+
 @pytest.mark.parametrize("post", ["OP_VARINT_ZZ_DELTA_XY", "OP_VARINT_ZZ_DELTA", "OP_VARINT_DELTA_MORTON", "OP_VARINT_ZZ", "OP_VARINT_U32"])
 def test_large_varint_streams_lookback_kernel(covt, oracle, gen, decoder, post):
     """Streams >= 256 KiB take the multi-CTA decoupled-look-back kernel; several streams per launch, any alignment."""

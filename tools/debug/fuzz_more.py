@@ -78,5 +78,21 @@ for seed in range(first, first + count):
                         open(os.path.join(ROOT, "gpurun_out", "fuzz_tile_%d_%s_%x.bin" % (seed, label, flags)), "wb").write(
                             bytes(blob[int(offs[t]):int(offs[t + 1])]))
             res.free()
+    # property columns: mutants of fixture tiles (and of their gen-3 re-wraps) that keep their property columns
+    pbase = [b for _, b in sorted([(n, b) for n, b in fixtures if n.startswith(("omt/", "bing/", "amazon/")) and not n.startswith("omt/8_")],
+                                  key=lambda t: len(t[1]))[seed % 30: seed % 30 + 6]]
+    for label, base, container in (("props gen-2b", pbase, abi.CONTAINER_GEN2B),
+                                   ("props gen-3", [util.rewrap_gen3(abi, O, b, props=True, gen=G)[0] for b in pbase], abi.CONTAINER_GEN3)):
+        flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+        tiles, good = tgb._mutants(np.random.default_rng(seed), base, 800, 40)
+        blob, offs = util.concat_tiles(tiles)
+        res = dec.decode_batch(blob, offs, container, flags | abi.FLAG_DECODE_PROPERTIES)
+        try:
+            util.compare_props(abi, blob, util.GpuProps(abi, res), O.decode_properties(blob, offs, container, flags))
+            util.compare_results(abi, res, O.decode_batch(blob, offs, container, flags))
+        except AssertionError as e:
+            bad += 1
+            print("%s seed %d: %s" % (label, seed, str(e)[:300]))
+        res.free()
     print("seed %d done" % seed, flush=True)
 print("discrepancies:", bad)
