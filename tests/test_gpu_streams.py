@@ -216,7 +216,7 @@ def test_overlong_varints_follow_the_java_reader(covt, oracle, gen, decoder):
             assert (st, cons) == (wst, wcons), "op %s, %d bytes, n=%d: status/consumed %s vs oracle %s" % (
                 abi.OP_NAMES[op], len(payload), n, (st, cons), (wst, wcons))
             flagged += wst in (abi.ERR_VARINT_OVERLONG, abi.ERR_TRUNCATED)
-    assert flagged >= 60
+    assert flagged >= 45
 
 
 @pytest.mark.parametrize("post", ["OP_VARINT_ZZ_DELTA_XY", "OP_VARINT_ZZ_DELTA", "OP_VARINT_DELTA_MORTON", "OP_VARINT_ZZ", "OP_VARINT_U32"])
