@@ -963,7 +963,7 @@ int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_
             b.num_values = d.num_values;
             b.first_chunk = n_big_chunks;
             const uint64_t window = (d.byte_offset & 15) + d.byte_length;  // blob base is 256-byte aligned
-            b.n_chunks = (uint32_t)((window + 511) / 512);
+            b.n_chunks = (uint32_t)((window + K1_SC_BYTES - 1) / K1_SC_BYTES);
             n_big_chunks += b.n_chunks;
             b.post = (uint8_t)post;
             b.num_bits = d.num_bits;

@@ -54,7 +54,7 @@ struct BigStream {
     uint8_t* dst;          // absolute device pointer of the output slice
     uint32_t byte_length;
     uint32_t num_values;
-    uint32_t first_chunk;  // index of its first 512-byte warp chunk in the launch-wide chunk numbering
+    uint32_t first_chunk;  // index of its first superchunk (K1_SC_BYTES) in the launch-wide numbering
     uint32_t n_chunks;
     uint32_t* status_out;  // where to report the status (a DeviceTask)
     uint32_t* consumed_out;
@@ -67,6 +67,8 @@ struct __align__(16) ChunkState { uint32_t count; int32_t a, b; uint32_t flags; 
 constexpr int WORK_COUNTERS = 16;  // 3 per codec class (pass-1 ticket, queue length, pass-2 ticket) + the assembler's ticket
 constexpr int FINAL_TOTALS = 9;  // [0] vertices (assembler) [1] payload bytes [2] output bytes (container walk + assembler) [3..7] algorithmic bytes per codec class, [8] assembler (profiling only)
 constexpr int K1_WARPS = 8;
+constexpr int K1_SC_WINDOWS = 16;  // 512-byte windows per superchunk (the unit one warp walks; one ChunkState each)
+constexpr int K1_SC_BYTES = K1_SC_WINDOWS * 512;
 constexpr int K1_SCAN_BLOCK = 1024;
 
 static const uint8_t kBufElemSize[COVT_NUM_BUFFERS] = {1, 8, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 1};

@@ -724,38 +724,81 @@ __device__ __forceinline__ uint32_t k1_find_stream(const BigStream* streams, uin
     return lo;
 }
 
-// One warp chunk of a large stream: the lane window, what is outside the stream, and the halo of lane 0.
-struct K1Chunk {
-    uint4 win;
-    uint64_t off;       // window-relative byte offset of this lane's 16 bytes (stream start = head)
-    uint32_t head;      // bytes between the 16-byte aligned window origin and the first stream byte
-    uint32_t head_f;    // leading fake values of this chunk (= head for chunk 0)
-    uint32_t tail_f;    // trailing fake values (zeroed bytes after the stream end)
-    uint32_t lo16, hi16;
-    uint32_t halo0;     // the 4 bytes before the chunk (lane 0)
-    bool partial;
+// A superchunk = K1_SC_WINDOWS consecutive 512-byte windows of one stream, walked by ONE warp front to back: what a window costs
+// besides its byte loop (finding the stream, the 64-bit address arithmetic, the warp reductions, the state record) is paid once per
+// superchunk, and the lane sums run across windows — a lane only has to know the class (even / odd position inside the
+// superchunk) of its first value in each window, which is the parity of the values before it: one ballot + popc.
+struct K1Super {
+    uintptr_t a0;        // 16-byte aligned address at or before the stream's first byte
+    uint64_t total;      // head + byte_length: the stream's window-relative end
+    uint32_t head;       // bytes between a0 and the first stream byte
+    uint32_t w0, w1;     // windows [w0, w1) of the stream
+    uint32_t n_windows;  // windows of the whole stream
 };
-__device__ __forceinline__ K1Chunk k1_load_chunk(const uint8_t* blob, const BigStream& S, uint32_t ci)
+__device__ __forceinline__ K1Super k1_super(const uint8_t* blob, const BigStream& S, uint32_t sc)
 {
-    K1Chunk k;
-    const unsigned lane = lane_id();
+    K1Super k;
     const uint8_t* src = blob + S.src_offset;
-    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15);
-    k.head = (uint32_t)(reinterpret_cast<uintptr_t>(src) - a0);
-    const uint64_t total = (uint64_t)k.head + S.byte_length;
-    const uint64_t base = (uint64_t)ci * WARP_CHUNK_BYTES;
-    k.off = base + lane * 16u;
-    k.win = make_uint4(0, 0, 0, 0);
-    if (k.off < total) k.win = ldg_stream128(reinterpret_cast<const void*>(a0 + k.off));
-    k.head_f = ci == 0 ? k.head : 0u;
-    const uint32_t end_in_chunk = (uint32_t)umin64(WARP_CHUNK_BYTES, total - base);
-    k.tail_f = WARP_CHUNK_BYTES - end_in_chunk;
-    k.partial = k.head_f != 0u || k.tail_f != 0u;
-    k.lo16 = k.head_f > lane * 16u ? min(16u, k.head_f - lane * 16u) : 0u;
-    k.hi16 = end_in_chunk > lane * 16u ? min(16u, end_in_chunk - lane * 16u) : 0u;
-    k.halo0 = 0;
-    if (lane == 0 && ci > 0) k.halo0 = __ldg(reinterpret_cast<const uint32_t*>(a0 + base - 4));
+    k.a0 = reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15);
+    k.head = (uint32_t)(reinterpret_cast<uintptr_t>(src) - k.a0);
+    k.total = (uint64_t)k.head + S.byte_length;
+    k.n_windows = (uint32_t)((k.total + WARP_CHUNK_BYTES - 1) / WARP_CHUNK_BYTES);
+    k.w0 = sc * K1_SC_WINDOWS;
+    k.w1 = min(k.w0 + (uint32_t)K1_SC_WINDOWS, k.n_windows);
     return k;
+}
+__device__ __forceinline__ uint4 k1_load_window(const K1Super& k, uint32_t w)
+{
+    const uint64_t off = (uint64_t)w * WARP_CHUNK_BYTES + lane_id() * 16u;
+    uint4 win = make_uint4(0, 0, 0, 0);
+    if (off < k.total) win = ldg_stream128(reinterpret_cast<const void*>(k.a0 + off));
+    return win;
+}
+// window-relative bounds of the stream inside window w (only the first and the last window of a stream are partial)
+__device__ __forceinline__ bool k1_window_bounds(const K1Super& k, uint32_t w, uint32_t& head_f, uint32_t& tail_f, uint32_t& lo16, uint32_t& hi16)
+{
+    const unsigned lane = lane_id();
+    const uint64_t base = (uint64_t)w * WARP_CHUNK_BYTES;
+    head_f = w == 0 ? k.head : 0u;
+    const uint32_t end_in = (uint32_t)umin64(WARP_CHUNK_BYTES, k.total - base);
+    tail_f = WARP_CHUNK_BYTES - end_in;
+    lo16 = head_f > lane * 16u ? min(16u, head_f - lane * 16u) : 0u;
+    hi16 = end_in > lane * 16u ? min(16u, end_in - lane * 16u) : 0u;
+    return head_f != 0u || tail_f != 0u;
+}
+
+template <bool ZZ>
+__device__ __forceinline__ void k1a_super(const K1Super& k, int32_t& ta, int32_t& tb, uint32_t& tc)
+{
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_le() ^ (1u << lane);
+    uint32_t carry_halo = 0;
+    if (k.w0 > 0) carry_halo = __ldg(reinterpret_cast<const uint32_t*>(k.a0 + (uint64_t)k.w0 * WARP_CHUNK_BYTES - 4));
+    int32_t A0 = 0, A1 = 0;  // lane sums of the values at even / odd positions of the superchunk (fakes count as positions)
+    uint32_t cnt = 0, gpar = 0;
+    uint4 nxt = k1_load_window(k, k.w0);
+    for (uint32_t w = k.w0; w < k.w1; w++) {
+        const uint4 win = nxt;
+        if (w + 1 < k.w1) nxt = k1_load_window(k, w + 1);
+        uint32_t head_f = 0, tail_f = 0, lo16 = 0, hi16 = 16;
+        bool partial = false;
+        if (w == 0 || w + 1 == k.n_windows) partial = k1_window_bounds(k, w, head_f, tail_f, lo16, hi16);
+        uint32_t wv[4], acc, mul, ov = 0;
+        const LeanLane L = lean_front(win, partial, lo16, hi16, carry_halo, wv, acc, mul, ov);
+        const bool odd = L.cnt & 1u;
+        const unsigned ob = __ballot_sync(FULL, odd);
+        const bool fp = (gpar ^ (uint32_t)__popc(ob & lt)) & 1u;  // class of the lane's first value in this window
+        int32_t cur = fp ? A1 : A0, oth = fp ? A0 : A1;
+        lean_sum_lane_acc<ZZ>(wv, L.cm, acc, mul, cur, oth);
+        const bool ep = fp != odd;  // class of `cur` after L.cnt swaps
+        A0 = ep ? oth : cur;
+        A1 = ep ? cur : oth;
+        gpar ^= (uint32_t)__popc(ob);
+        cnt += L.cnt;
+    }
+    ta = (int32_t)__reduce_add_sync(FULL, (unsigned)A0);
+    tb = (int32_t)__reduce_add_sync(FULL, (unsigned)A1);
+    tc = __reduce_add_sync(FULL, cnt);
 }
 
 __global__ void __launch_bounds__(K1_WARPS * 32)
@@ -766,31 +809,23 @@ k1a_aggregate(const uint8_t* blob, const BigStream* streams, uint32_t n_streams,
     if (g >= n_chunks) return;
     const uint32_t si = k1_find_stream(streams, n_streams, g);
     const BigStream S = streams[si];
-    const uint32_t ci = g - S.first_chunk;
-    K1Chunk k = k1_load_chunk(blob, S, ci);
-    uint32_t w[4], acc, mul, ov = 0;
-    const LeanLane L = lean_front(k.win, k.partial, k.lo16, k.hi16, k.halo0, w, acc, mul, ov);
-    int32_t cur, oth;
+    const uint32_t sc = g - S.first_chunk;
+    const K1Super k = k1_super(blob, S, sc);
+    int32_t ta, tb;
+    uint32_t tc;
     const bool zz = (S.post == POST_ZZ || S.post == POST_ZZ_DELTA || S.post == POST_ZZ_DELTA_XY);
-    if (zz) lean_sum_lane<true>(w, L.cm, acc, mul, cur, oth, ov);
-    else lean_sum_lane<false>(w, L.cm, acc, mul, cur, oth, ov);
-    // cur = sum of the class of the lane's NEXT value, oth = the other class (see lean_sum_lane)
-    const bool cnt_odd = L.cnt & 1u;
-    const int32_t e = cnt_odd ? oth : cur, o = cnt_odd ? cur : oth;  // sums at even / odd lane-local positions
-    // chunk-local parity of the lane's first value = parity of the values in the lanes before it
-    const unsigned odd_lanes = __ballot_sync(FULL, cnt_odd);
-    const bool first_odd = __popc(odd_lanes & ((1u << lane) - 1u)) & 1u;
-    int32_t ta = (int32_t)__reduce_add_sync(FULL, (unsigned)(first_odd ? o : e));
-    int32_t tb = (int32_t)__reduce_add_sync(FULL, (unsigned)(first_odd ? e : o));
-    const uint32_t tc = __reduce_add_sync(FULL, L.cnt);
-    if (k.head_f & 1u) { const int32_t t = ta; ta = tb; tb = t; }  // leading fakes shifted every real value by head_f positions
+    if (zz) k1a_super<true>(k, ta, tb, tc);
+    else k1a_super<false>(k, ta, tb, tc);
+    const uint32_t head_f = sc == 0 ? k.head : 0u;
+    const uint32_t tail_f = k.w1 == k.n_windows ? (uint32_t)((uint64_t)k.n_windows * WARP_CHUNK_BYTES - k.total) : 0u;
+    if (head_f & 1u) { const int32_t t = ta; ta = tb; tb = t; }  // leading fakes shifted every real value by head_f positions
     const bool xy = S.post == POST_ZZ_DELTA_XY;
     if (lane == 0) {
         ChunkState v;
-        v.count = tc - k.head_f - k.tail_f;
+        v.count = tc - head_f - tail_f;
         v.a = xy ? ta : ta + tb;
         v.b = xy ? tb : 0;
-        v.flags = (xy ? 2u : 0u) | (ci == 0 ? 1u : 0u);
+        v.flags = (xy ? 2u : 0u) | (sc == 0 ? 1u : 0u);
         states[g] = v;
     }
     // (the overlong flag is raised by k1b_decode, which knows where the stream's numValues-th value ends)
@@ -844,61 +879,123 @@ __global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_apply(ChunkState* state
     if (i < n) states[i] = excl;
 }
 
-// The chunk of a large stream that holds value #num_values: reports the bytes consumed up to its terminator and, when the
-// chunk goes on behind it, redoes the overlong check on the bytes before the cut only (rare; kept out of line).
-__device__ __noinline__ void k1b_stream_end(const BigStream& S, const K1Chunk& k, const LeanLane& L, uint32_t count_before, uint32_t halo_in, uint32_t& ov)
+// The window of a large stream that holds value #num_values: reports the bytes consumed up to its terminator and, when the
+// window goes on behind it, redoes the overlong check on the bytes before the cut only (rare; kept out of line).
+__device__ __noinline__ void k1b_stream_end(const BigStream& S, const K1Super& k, uint32_t w, uint4 win, const LeanLane& L, uint32_t count_before,
+                                            uint32_t halo_in, uint32_t& ov)
 {
     const unsigned lane = lane_id();
-    const int64_t first = (int64_t)count_before + L.excl - k.head_f;  // stream index of the lane's first terminator (fakes negative)
+    uint32_t head_f, tail_f, lo16, hi16;
+    k1_window_bounds(k, w, head_f, tail_f, lo16, hi16);
+    const int64_t first = (int64_t)count_before + L.excl - head_f;  // stream index of the lane's first terminator (fakes negative)
     const bool mine = (int64_t)S.num_values > first && (int64_t)S.num_values <= first + (int64_t)L.cnt;
     const unsigned bm = __ballot_sync(FULL, mine);
     uint32_t cut = 0;
     if (mine) cut = lane * 16u + lean_nth_terminator(L.cm, (uint32_t)((int64_t)S.num_values - first));
     cut = __shfl_sync(FULL, cut, bm ? __ffs(bm) - 1 : 0);
-    const uint32_t end_in_chunk = WARP_CHUNK_BYTES - k.tail_f;
+    const uint32_t end_in_chunk = WARP_CHUNK_BYTES - tail_f;
     if (!bm || cut > end_in_chunk) return;  // (a terminator behind the stream's bytes is a fake zero)
-    if (S.consumed_out && lane == 0) *S.consumed_out = (uint32_t)(k.off + cut - k.head);
+    if (S.consumed_out && lane == 0) *S.consumed_out = (uint32_t)((uint64_t)w * WARP_CHUNK_BYTES + cut - k.head);
     if (cut < end_in_chunk) {
         const uint32_t hi_cut = cut > lane * 16u ? min(16u, cut - lane * 16u) : 0u;
         uint32_t w2[4], acc2, mul2, halo2 = halo_in;
         int32_t c2, o2;
         ov = 0;
-        const LeanLane L2 = lean_front(k.win, true, k.lo16, hi_cut, halo2, w2, acc2, mul2, ov);
+        const LeanLane L2 = lean_front(win, true, lo16, hi_cut, halo2, w2, acc2, mul2, ov);
         lean_sum_lane<false>(w2, L2.cm, acc2, mul2, c2, o2, ov);
     }
+}
+
+// Decode pass over one superchunk. Raw values are staged window after window behind whatever the previous windows left over; full
+// rows of 128 values (512 aligned output bytes) leave through lean_row128 — no bounds, one LDS.128 / scan / STG.128 per lane — and
+// the remainder (< 128 values) moves to the front of the stage. Only the first row of a superchunk (it may start in the middle
+// of a 16-byte output vector) and the last partial row take the predicated lean_rows4.
+constexpr int K1B_STAGE_WORDS = LEAN_FRONT + 128 + 512 + 16;
+template <int POST>
+__device__ __forceinline__ void k1b_super(const BigStream& S, const K1Super& k, const ChunkState& P, bool last_super, uint32_t* stage)
+{
+    const unsigned lane = lane_id();
+    uint32_t* A = stage + LEAN_FRONT;
+    const uint32_t s4 = P.count & 3u;  // see lean_rows4: A[j] belongs to stream index base + j, base a multiple of 4
+    if (lane < 4u) A[lane] = 0;
+    uint32_t fill = s4;
+    uint64_t base = (uint64_t)P.count - s4;
+    bool first_row = s4 != 0u;
+    uint32_t count_before = P.count;  // terminators (real values) of the stream before the current window
+    int32_t cx = P.a, cy = P.b;
+    uint32_t ov_total = 0;
+    uint32_t carry_halo = 0;
+    if (k.w0 > 0) carry_halo = __ldg(reinterpret_cast<const uint32_t*>(k.a0 + (uint64_t)k.w0 * WARP_CHUNK_BYTES - 4));
+    uint4 nxt = k1_load_window(k, k.w0);
+    __syncwarp();
+    for (uint32_t w = k.w0; w < k.w1; w++) {
+        const uint4 win = nxt;
+        if (w + 1 < k.w1) nxt = k1_load_window(k, w + 1);
+        uint32_t head_f = 0, tail_f = 0, lo16 = 0, hi16 = 16;
+        bool partial = false;
+        if (w == 0 || w + 1 == k.n_windows) partial = k1_window_bounds(k, w, head_f, tail_f, lo16, hi16);
+        uint32_t wv[4], acc, mul, ov = 0;
+        const uint32_t halo_in = carry_halo;
+        LeanLane L = lean_front(win, partial, lo16, hi16, carry_halo, wv, acc, mul, ov);
+        L.excl = warp_exclusive_scan(L.cnt, L.total);
+        lean_stage_lane(wv, L.cm, acc, mul, A + fill + L.excl - head_f, ov);
+        __syncwarp();
+        const uint32_t n_here = L.total - head_f - tail_f;
+        if (count_before < S.num_values) {
+            // bytes the reference reader consumes = position right after the terminator of value #num_values; what follows it is
+            // not read (and must not raise the overlong flag). Only the window that holds that value looks for it.
+            if (count_before + n_here >= S.num_values) k1b_stream_end(S, k, w, win, L, count_before, halo_in, ov);
+            ov_total |= ov;
+            fill += min(n_here, S.num_values - count_before);
+        }
+        count_before += n_here;
+        const uint32_t rows = fill >> 7;
+        if (rows) {
+            uint32_t r = 0;
+            if (first_row) {
+                lean_rows4<POST, false>(A, s4, 128u - s4, S.dst, base + s4, cx, cy, S.num_bits, S.no_shift != 0);
+                first_row = false;
+                r = 1;
+            }
+            for (; r < rows; r++) lean_row128<POST>(A + 128u * r, S.dst, base + 128u * r, cx, cy, S.num_bits, S.no_shift != 0);
+            const uint32_t left = fill & 127u;
+            uint4 mv = make_uint4(0, 0, 0, 0);
+            if (4u * lane < left) mv = *reinterpret_cast<const uint4*>(A + 128u * rows + 4u * lane);
+            __syncwarp();
+            if (4u * lane < left) *reinterpret_cast<uint4*>(A + 4u * lane) = mv;
+            base += 128ull * rows;
+            fill = left;
+            __syncwarp();
+        }
+    }
+    if (fill) {
+        if (first_row) lean_rows4<POST, false>(A, s4, fill - s4, S.dst, base + s4, cx, cy, S.num_bits, S.no_shift != 0);
+        else lean_rows4<POST, false>(A, 0u, fill, S.dst, base, cx, cy, S.num_bits, S.no_shift != 0);
+    }
+    if (P.count < S.num_values && __any_sync(FULL, (ov_total >> 28) & 1u) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
+    if (last_super && lane == 0 && count_before < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
 }
 
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks, const ChunkState* states)
 {
-    __shared__ __align__(16) uint32_t s_stage[K1_WARPS][LEAN_STAGE_WORDS];
-    const unsigned lane = lane_id();
+    __shared__ __align__(16) uint32_t s_stage[K1_WARPS][K1B_STAGE_WORDS];
     const uint32_t g = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
     if (g >= n_chunks) return;
     const uint32_t si = k1_find_stream(streams, n_streams, g);
     const BigStream S = streams[si];
-    const uint32_t ci = g - S.first_chunk;
+    const uint32_t sc = g - S.first_chunk;
     const ChunkState P = states[g];
-    K1Chunk k = k1_load_chunk(blob, S, ci);
+    const K1Super k = k1_super(blob, S, sc);
     uint32_t* stage = s_stage[threadIdx.x >> 5];
-    uint32_t w[4], acc, mul, ov = 0;
-    const uint32_t halo_in = k.halo0;  // lean_front replaces it by this chunk's last bytes
-    LeanLane L = lean_front(k.win, k.partial, k.lo16, k.hi16, k.halo0, w, acc, mul, ov);
-    L.excl = warp_exclusive_scan(L.cnt, L.total);
-    const uint32_t s4 = P.count & 3u;  // see lean_rows4: the chunk's values are staged at A[s4 + i]
-    uint32_t* A = stage + LEAN_FRONT;
-    if (lane < s4) A[lane] = 0;
-    lean_stage_lane(w, L.cm, acc, mul, A + s4 + L.excl - k.head_f, ov);
-    __syncwarp();
-    const uint32_t n_here = L.total - k.head_f - k.tail_f;
-    // bytes the reference reader consumes = position right after the terminator of value #num_values; what follows it is not
-    // read (and must not raise the overlong flag). Only the chunk that holds that value looks for it.
-    if (P.count < S.num_values && P.count + n_here >= S.num_values) k1b_stream_end(S, k, L, P.count, halo_in, ov);
-    if (P.count < S.num_values && __any_sync(FULL, (ov >> 28) & 1u) && lane == 0) atomicMax(S.status_out, (uint32_t)COVT_ERR_VARINT_OVERLONG);
-    if (ci == S.n_chunks - 1 && lane == 0 && P.count + n_here < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
-    const uint32_t room = P.count < S.num_values ? S.num_values - P.count : 0u;
-    int32_t cx = P.a, cy = P.b;
-    lean_rows4_dispatch(S.post, false, A, s4, min(n_here, room), S.dst, P.count, cx, cy, S.num_bits, S.no_shift != 0);
+    const bool last = sc == S.n_chunks - 1;
+    switch (S.post) {
+    case POST_PLAIN: k1b_super<POST_PLAIN>(S, k, P, last, stage); break;
+    case POST_ZZ: k1b_super<POST_ZZ>(S, k, P, last, stage); break;
+    case POST_ZZ_DELTA: k1b_super<POST_ZZ_DELTA>(S, k, P, last, stage); break;
+    case POST_ZZ_DELTA_XY: k1b_super<POST_ZZ_DELTA_XY>(S, k, P, last, stage); break;
+    default: k1b_super<POST_DELTA_MORTON>(S, k, P, last, stage); break;
+    }
 }
 
 // Error path of the large streams. k1b_decode reports COVT_ERR_VARINT_OVERLONG when a value with four continuation bytes lies
