@@ -774,6 +774,7 @@ __device__ __forceinline__ void k1a_super(const K1Super& k, int32_t& ta, int32_t
     const unsigned lt = lanemask_le() ^ (1u << lane);
     uint32_t carry_halo = 0;
     if (k.w0 > 0) carry_halo = __ldg(reinterpret_cast<const uint32_t*>(k.a0 + (uint64_t)k.w0 * WARP_CHUNK_BYTES - 4));
+    const uint32_t halo_first = carry_halo;
     int32_t A0 = 0, A1 = 0;  // lane sums of the values at even / odd positions of the superchunk (fakes count as positions)
     uint32_t cnt = 0, gpar = 0;
     uint4 nxt = k1_load_window(k, k.w0);
@@ -783,13 +784,18 @@ __device__ __forceinline__ void k1a_super(const K1Super& k, int32_t& ta, int32_t
         uint32_t head_f = 0, tail_f = 0, lo16 = 0, hi16 = 16;
         bool partial = false;
         if (w == 0 || w + 1 == k.n_windows) partial = k1_window_bounds(k, w, head_f, tail_f, lo16, hi16);
-        uint32_t wv[4], acc, mul, ov = 0;
-        const LeanLane L = lean_front(win, partial, lo16, hi16, carry_halo, wv, acc, mul, ov);
+        uint32_t wv[4];
+        wv[0] = win.x; wv[1] = win.y; wv[2] = win.z; wv[3] = win.w;
+        if (partial) lean_mask_window(wv, lo16, hi16);  // warp-uniform branch
+        LeanLane L;
+        L.cm = cont_mask_scattered(wv);
+        L.cnt = 16u - (uint32_t)__popc(L.cm);
+        const uint32_t halo = lean_halo(wv[3], carry_halo);
         const bool odd = L.cnt & 1u;
         const unsigned ob = __ballot_sync(FULL, odd);
         const bool fp = (gpar ^ (uint32_t)__popc(ob & lt)) & 1u;  // class of the lane's first value in this window
         int32_t cur = fp ? A1 : A0, oth = fp ? A0 : A1;
-        lean_sum_lane_acc<ZZ>(wv, L.cm, acc, mul, cur, oth);
+        lean_sum_lane_lin<ZZ>(wv, L.cm, lean_lin_carry_in<ZZ>(halo), cur, oth);
         const bool ep = fp != odd;  // class of `cur` after L.cnt swaps
         A0 = ep ? oth : cur;
         A1 = ep ? cur : oth;
@@ -799,6 +805,15 @@ __device__ __forceinline__ void k1a_super(const K1Super& k, int32_t& ta, int32_t
     ta = (int32_t)__reduce_add_sync(FULL, (unsigned)A0);
     tb = (int32_t)__reduce_add_sync(FULL, (unsigned)A1);
     tc = __reduce_add_sync(FULL, cnt);
+    // Every byte added its term where it lies, but a value belongs to the superchunk that holds its terminator: the bytes of a value
+    // that began before this superchunk come in (class 0: it is the superchunk's first value), those of a value that is still open
+    // at its end go out (class = parity of the values counted so far).
+    uint32_t acc, mul, ov = 0;
+    lean_carry_in(halo_first, acc, mul, ov);
+    ta += ZZ ? zigzag_decode32(acc) : (int32_t)acc;
+    lean_carry_in(carry_halo, acc, mul, ov);
+    const int32_t z_out = ZZ ? zigzag_decode32(acc) : (int32_t)acc;
+    if (gpar & 1u) tb -= z_out; else ta -= z_out;
 }
 
 __global__ void __launch_bounds__(K1_WARPS * 32)
@@ -880,21 +895,22 @@ __global__ void __launch_bounds__(K1_SCAN_BLOCK) k1_scan_apply(ChunkState* state
 }
 
 // The window of a large stream that holds value #num_values: reports the bytes consumed up to its terminator and, when the
-// window goes on behind it, redoes the overlong check on the bytes before the cut only (rare; kept out of line).
-__device__ __noinline__ void k1b_stream_end(const BigStream& S, const K1Super& k, uint32_t w, uint4 win, const LeanLane& L, uint32_t count_before,
-                                            uint32_t halo_in, uint32_t& ov)
+// window goes on behind it, redoes the overlong check on the bytes before the cut only; returns the window's overlong bits.
+// Rare and out of line; everything by value so that the caller keeps nothing in local memory for it.
+__device__ __noinline__ uint32_t k1b_stream_end(BigStream S, K1Super k, uint32_t w, uint4 win, uint32_t cm, uint32_t cnt, uint32_t excl,
+                                                uint32_t count_before, uint32_t halo_in, uint32_t ov)
 {
     const unsigned lane = lane_id();
     uint32_t head_f, tail_f, lo16, hi16;
     k1_window_bounds(k, w, head_f, tail_f, lo16, hi16);
-    const int64_t first = (int64_t)count_before + L.excl - head_f;  // stream index of the lane's first terminator (fakes negative)
-    const bool mine = (int64_t)S.num_values > first && (int64_t)S.num_values <= first + (int64_t)L.cnt;
+    const int64_t first = (int64_t)count_before + excl - head_f;  // stream index of the lane's first terminator (fakes negative)
+    const bool mine = (int64_t)S.num_values > first && (int64_t)S.num_values <= first + (int64_t)cnt;
     const unsigned bm = __ballot_sync(FULL, mine);
     uint32_t cut = 0;
-    if (mine) cut = lane * 16u + lean_nth_terminator(L.cm, (uint32_t)((int64_t)S.num_values - first));
+    if (mine) cut = lane * 16u + lean_nth_terminator(cm, (uint32_t)((int64_t)S.num_values - first));
     cut = __shfl_sync(FULL, cut, bm ? __ffs(bm) - 1 : 0);
     const uint32_t end_in_chunk = WARP_CHUNK_BYTES - tail_f;
-    if (!bm || cut > end_in_chunk) return;  // (a terminator behind the stream's bytes is a fake zero)
+    if (!bm || cut > end_in_chunk) return ov;  // (a terminator behind the stream's bytes is a fake zero)
     if (S.consumed_out && lane == 0) *S.consumed_out = (uint32_t)((uint64_t)w * WARP_CHUNK_BYTES + cut - k.head);
     if (cut < end_in_chunk) {
         const uint32_t hi_cut = cut > lane * 16u ? min(16u, cut - lane * 16u) : 0u;
@@ -904,13 +920,15 @@ __device__ __noinline__ void k1b_stream_end(const BigStream& S, const K1Super& k
         const LeanLane L2 = lean_front(win, true, lo16, hi_cut, halo2, w2, acc2, mul2, ov);
         lean_sum_lane<false>(w2, L2.cm, acc2, mul2, c2, o2, ov);
     }
+    return ov;
 }
 
 // Decode pass over one superchunk. Raw values are staged window after window behind whatever the previous windows left over; full
-// rows of 128 values (512 aligned output bytes) leave through lean_row128 — no bounds, one LDS.128 / scan / STG.128 per lane — and
-// the remainder (< 128 values) moves to the front of the stage. Only the first row of a superchunk (it may start in the middle
+// rows of 256 values (1 KiB of output) leave through lean_row256 — no bounds, two LDS.128 / one scan / two STG.128 per lane — and
+// the remainder (< 256 values) moves to the front of the stage. Only the first row of a superchunk (it may start in the middle
 // of a 16-byte output vector) and the last partial row take the predicated lean_rows4.
-constexpr int K1B_STAGE_WORDS = LEAN_FRONT + 128 + 512 + 16;
+constexpr int K1B_ROW = 256;
+constexpr int K1B_STAGE_WORDS = LEAN_FRONT + K1B_ROW + 512 + 16;
 template <int POST>
 __device__ __forceinline__ void k1b_super(const BigStream& S, const K1Super& k, const ChunkState& P, bool last_super, uint32_t* stage)
 {
@@ -944,26 +962,28 @@ __device__ __forceinline__ void k1b_super(const BigStream& S, const K1Super& k, 
         if (count_before < S.num_values) {
             // bytes the reference reader consumes = position right after the terminator of value #num_values; what follows it is
             // not read (and must not raise the overlong flag). Only the window that holds that value looks for it.
-            if (count_before + n_here >= S.num_values) k1b_stream_end(S, k, w, win, L, count_before, halo_in, ov);
+            if (count_before + n_here >= S.num_values) ov = k1b_stream_end(S, k, w, win, L.cm, L.cnt, L.excl, count_before, halo_in, ov);
             ov_total |= ov;
             fill += min(n_here, S.num_values - count_before);
         }
         count_before += n_here;
-        const uint32_t rows = fill >> 7;
-        if (rows) {
+        if (fill >= (uint32_t)K1B_ROW) {
+            const uint32_t rows = fill / K1B_ROW;  // 1 or 2
             uint32_t r = 0;
             if (first_row) {
-                lean_rows4<POST, false>(A, s4, 128u - s4, S.dst, base + s4, cx, cy, S.num_bits, S.no_shift != 0);
+                lean_rows4<POST, false>(A, s4, K1B_ROW - s4, S.dst, base + s4, cx, cy, S.num_bits, S.no_shift != 0);
                 first_row = false;
                 r = 1;
             }
-            for (; r < rows; r++) lean_row128<POST>(A + 128u * r, S.dst, base + 128u * r, cx, cy, S.num_bits, S.no_shift != 0);
-            const uint32_t left = fill & 127u;
-            uint4 mv = make_uint4(0, 0, 0, 0);
-            if (4u * lane < left) mv = *reinterpret_cast<const uint4*>(A + 128u * rows + 4u * lane);
+            for (; r < rows; r++) lean_row256<POST>(A + K1B_ROW * r, S.dst, base + K1B_ROW * r, cx, cy, S.num_bits, S.no_shift != 0);
+            const uint32_t left = fill - rows * K1B_ROW;
+            uint4 mv0 = make_uint4(0, 0, 0, 0), mv1 = mv0;
+            if (4u * lane < left) mv0 = *reinterpret_cast<const uint4*>(A + K1B_ROW * rows + 4u * lane);
+            if (128u + 4u * lane < left) mv1 = *reinterpret_cast<const uint4*>(A + K1B_ROW * rows + 128u + 4u * lane);
             __syncwarp();
-            if (4u * lane < left) *reinterpret_cast<uint4*>(A + 4u * lane) = mv;
-            base += 128ull * rows;
+            if (4u * lane < left) *reinterpret_cast<uint4*>(A + 4u * lane) = mv0;
+            if (128u + 4u * lane < left) *reinterpret_cast<uint4*>(A + 128u + 4u * lane) = mv1;
+            base += (uint64_t)K1B_ROW * rows;
             fill = left;
             __syncwarp();
         }
@@ -976,7 +996,10 @@ __device__ __forceinline__ void k1b_super(const BigStream& S, const K1Super& k, 
     if (last_super && lane == 0 && count_before < S.num_values) atomicMax(S.status_out, (uint32_t)COVT_ERR_TRUNCATED);
 }
 
-__global__ void __launch_bounds__(K1_WARPS * 32)
+#ifndef K1B_MIN_BLOCKS
+#define K1B_MIN_BLOCKS 4  // 64 registers: 32 warps per SM (measured: 1.83 ms vs 1.95 ms at 87 registers / 16 warps on the 1 GiB stream)
+#endif
+__global__ void __launch_bounds__(K1_WARPS * 32, K1B_MIN_BLOCKS)
 k1b_decode(const uint8_t* blob, const BigStream* streams, uint32_t n_streams, uint32_t n_chunks, const ChunkState* states)
 {
     __shared__ __align__(16) uint32_t s_stage[K1_WARPS][K1B_STAGE_WORDS];

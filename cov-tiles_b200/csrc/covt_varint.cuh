@@ -121,6 +121,61 @@ __device__ __forceinline__ void lean_sum_lane_acc(const uint32_t w[4], uint32_t 
     }
 }
 
+// The aggregate pass without per-byte values: zigzag decode is linear in the payload bytes once the sign is known —
+//   zz(v) = s * (v >> 1) - b,  b = bit 0 of the value's FIRST byte, s = 1 - 2b,  v >> 1 = (p0 >> 1) + sum_{k>=1} p_k << (7k - 1)
+// — so every byte adds its own term q * m to the running sum of its value's class (first byte: q = p0 >> 1, m = s, and -b;
+// byte k >= 1: q = p_k, m = s << (7k - 1)), all exact mod 2^32 like the Java int sums. No accumulator, no per-byte zigzag: the
+// multiply-adds run on the FMA pipe, which the byte loops otherwise leave half idle (the ALU pipe is what bounds them).
+// A value that started in an earlier lane continues with the multiplier derived from the halo (its earlier bytes were added by the
+// lanes that hold them). ZZ = false: plain sums (m = 1 << 7k).
+struct LinCarry { uint32_t m; bool first; };  // multiplier of the lane's first byte / "the lane's first byte starts a value"
+template <bool ZZ>
+__device__ __forceinline__ LinCarry lean_lin_carry_in(uint32_t halo)
+{
+    const uint32_t hterm = ~halo & 0x80808080u;
+    const uint32_t k = hterm ? (uint32_t)(__clz(hterm) >> 3) : 4u;  // trailing continuation bytes before the lane
+    LinCarry c;
+    c.first = k == 0u;
+    if (ZZ) {
+        const uint32_t b = (halo >> ((32u - 8u * k) & 31u)) & 1u;   // bit 0 of the value's first byte (k >= 1)
+        c.m = (1u - 2u * b) << ((7u * k - 1u) & 31u);
+    } else {
+        c.m = 1u << (7u * k);
+    }
+    return c;
+}
+template <bool ZZ>
+__device__ __forceinline__ void lean_sum_lane_lin(const uint32_t w[4], uint32_t cm, LinCarry c, int32_t& cur, int32_t& oth)
+{
+    uint32_t wm[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) wm[q] = w[q] & 0x7f7f7f7fu;
+    uint32_t sm = c.m;
+    bool first = c.first;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t p = __byte_perm(wm[j >> 2], 0u, 0x4440u + (j & 3));
+        const bool term = (cm & cont_bit_of_byte(j)) == 0u;
+        uint32_t q = p, m = sm;
+        if (ZZ) {
+            if (first) {
+                const uint32_t b = p & 1u;
+                q = p >> 1;
+                m = 1u - 2u * b;
+                cur -= (int32_t)b;
+            }
+            cur += (int32_t)(q * m);
+            sm = first ? m << 6 : m << 7;
+        } else {
+            if (first) m = 1u;
+            cur += (int32_t)(q * m);
+            sm = m << 7;
+        }
+        if (term) { const int32_t t = cur; cur = oth; oth = t; }
+        first = term;
+    }
+}
+
 struct LeanLane {
     uint32_t cm;     // scattered continuation mask of the lane window (after masking)
     uint32_t cnt;    // terminators in the lane window, fakes included
@@ -298,6 +353,65 @@ __device__ __forceinline__ void lean_row128(const uint32_t* A, void* dst, uint64
         *reinterpret_cast<int4*>(out + 2) = make_int4(m2.x, m2.y, m3.x, m3.y);
     } else {
         *reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(dst) + e) = make_int4(o0, o1, o2, o3);
+    }
+}
+
+// Two full rows at once: A[0 .. 256) are 256 consecutive raw values, eight per lane (two LDS.128 with a 2-way bank conflict, which
+// costs load-store cycles the kernel has to spare) — ONE warp scan per 256 values instead of two, and 32 contiguous output bytes
+// per lane.
+template <int POST>
+__device__ __forceinline__ void lean_row256(const uint32_t* A, void* dst, uint64_t e0, int32_t& cx, int32_t& cy, uint32_t num_bits, bool no_shift)
+{
+    const unsigned lane = lane_id();
+    const uint4 r0 = *reinterpret_cast<const uint4*>(A + 8u * lane), r1 = *reinterpret_cast<const uint4*>(A + 8u * lane + 4u);
+    int32_t d[8] = {(int32_t)r0.x, (int32_t)r0.y, (int32_t)r0.z, (int32_t)r0.w, (int32_t)r1.x, (int32_t)r1.y, (int32_t)r1.z, (int32_t)r1.w};
+    if (POST != POST_PLAIN && POST != POST_DELTA_MORTON) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) d[i] = zigzag_decode32((uint32_t)d[i]);
+    }
+    int32_t o[8];
+    if (POST == POST_ZZ_DELTA_XY) {
+        const int32_t sx = (d[0] + d[2]) + (d[4] + d[6]), sy = (d[1] + d[3]) + (d[5] + d[7]);
+        int32_t ix = sx, iy = sy;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const int32_t tx = __shfl_up_sync(FULL, ix, k), ty = __shfl_up_sync(FULL, iy, k);
+            if (lane >= (unsigned)k) { ix += tx; iy += ty; }
+        }
+        o[0] = cx + (ix - sx) + d[0];
+        o[1] = cy + (iy - sy) + d[1];
+#pragma unroll
+        for (int i = 2; i < 8; i++) o[i] = o[i - 2] + d[i];
+        cx += __shfl_sync(FULL, ix, 31);
+        cy += __shfl_sync(FULL, iy, 31);
+    } else if (POST == POST_ZZ_DELTA || POST == POST_DELTA_MORTON) {
+        const int32_t sm = ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
+        int32_t is = sm;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const int32_t t = __shfl_up_sync(FULL, is, k);
+            if (lane >= (unsigned)k) is += t;
+        }
+        o[0] = cx + (is - sm) + d[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) o[i] = o[i - 1] + d[i];
+        cx += __shfl_sync(FULL, is, 31);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = d[i];
+    }
+    const uint64_t e = e0 + 8u * lane;
+    if (POST == POST_DELTA_MORTON) {
+        int4* out = reinterpret_cast<int4*>(reinterpret_cast<int2*>(dst) + e);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int2 m0 = morton_decode(o[2 * i], num_bits, no_shift), m1 = morton_decode(o[2 * i + 1], num_bits, no_shift);
+            out[i] = make_int4(m0.x, m0.y, m1.x, m1.y);
+        }
+    } else {
+        int4* out = reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(dst) + e);
+        out[0] = make_int4(o[0], o[1], o[2], o[3]);
+        out[1] = make_int4(o[4], o[5], o[6], o[7]);
     }
 }
 
