@@ -40,7 +40,7 @@ struct covt_ctx {
     uint64_t* h_totals = nullptr;  // pinned scratch for the one device->host size read-back
     covt::SegState* h_seg = nullptr;     // pinned mirror of the device-side segment state
     uint64_t seg_bytes = 64ull << 20;    // minimum upload/decode segment size of covt_decode_batch (env COVT_SEG_BYTES overrides: tests)
-    uint32_t max_segments = 8;           // env COVT_MAX_SEGMENTS overrides
+    uint32_t max_segments = 24;          // env COVT_MAX_SEGMENTS overrides (1 M tiles end to end: 8 -> 54.4 ms, 16 -> 53.5, 24 -> 53.2, 32 -> 53.3)
     uint32_t seg_min_tiles = 32768;      // env COVT_SEG_MIN_TILES overrides
     bool debug = false;                  // env COVT_DEBUG: host-side phase times on stderr
     bool serial_classes = true;          // env COVT_CONCURRENT=1 runs the five codec kernels side by side on their own streams
@@ -801,8 +801,8 @@ int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* ti
     // segments of ~SEG_BYTES, balanced by payload bytes, every one non-empty
     // Every segment costs ~1 ms of fixed kernel time (13 launches that are latency-bound at small sizes), and a segment must hold
     // enough tiles to fill the GPU (a kernel cannot finish before its largest stream, which one warp decodes), so use few, large
-    // segments: at most 8, at least seg_bytes and 32768 tiles each. Measured on B200: 1 M tiles / 2.77 GB — 1 segment 76.5 ms,
-    // 8 segments 56.4 ms, 57 segments 84 ms per call (the host->device copy alone takes 50.4 ms); the 91 OMT fixture tiles x256
+    // segments: at most 24, at least seg_bytes and 32768 tiles each. Measured on B200: 1 M tiles / 2.77 GB — 1 segment 76.5 ms,
+    // 8 segments 54.4 ms, 24 segments 53.2 ms per call (the host->device copy alone takes 49.8 ms); the 91 OMT fixture tiles x256
     // (23 296 tiles of 122 KB, layers of up to 60 000 features) — 8 segments 199 ms, 1 segment ~90 ms.
     const uint64_t SEG_BYTES = std::max<uint64_t>(ctx->seg_bytes, 4096);
     uint32_t want = (uint32_t)std::min<uint64_t>(ctx->max_segments, std::max<uint64_t>(1, (blob_len - tile_offsets[0]) / SEG_BYTES));

@@ -155,7 +155,13 @@ __device__ __forceinline__ uint64_t lite_slice_size(const Lite& lite, uint32_t g
 // run-time index, is matched by an unrolled compare): as shared-memory arrays (19 x 8 B x 128 threads on top of the layer scratch)
 // they took 31 KB per block, i.e. 217 KB of the SM's 256 KB L1/shared array at 7 resident blocks, which left no L1 for the header
 // bytes — every byte load of the walk went to L2 (ncu: lts sectors == l1tex sectors, k0_scan_tiles 0.75 -> 2.16 ms per 1 M tiles).
-__global__ void __launch_bounds__(K0_BLOCK)
+#ifndef K0_SCAN_MINB
+#define K0_SCAN_MINB 1
+#endif
+#ifndef K0_FILL_MINB
+#define K0_FILL_MINB 1
+#endif
+__global__ void __launch_bounds__(K0_BLOCK, K0_SCAN_MINB)
 k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
               const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, uint64_t* tile_cols, uint32_t* tile_status)
 {
@@ -187,7 +193,7 @@ k0_scan_tiles(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tile
 
 // pass 2: the covt_layer table with result offsets (tile_cols now holds exclusive prefixes) and one decode task per present stream,
 // appended to the dense list of its codec class
-__global__ void __launch_bounds__(K0_BLOCK)
+__global__ void __launch_bounds__(K0_BLOCK, K0_FILL_MINB)
 k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t tile_base, uint32_t container,
                const uint32_t* tj_fields, uint32_t tj_layers, uint32_t flags, const uint64_t* tile_cols, ResultBuffers bufs, covt_layer* layers,
                DeviceTask* tasks, ClassOffsets class_off, uint32_t* first_layer, const SegState* seg, uint64_t* totals)
