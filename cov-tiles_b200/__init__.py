@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
 # every symbol include/covt_b200.h declares
 ABI_SYMBOLS = [
     "covt_abi_version", "covt_create", "covt_destroy", "covt_last_error", "covt_trim", "covt_decode_batch", "covt_batch_upload",
-    "covt_batch_decode", "covt_batch_free", "covt_decode_streams", "covt_batch_decode_streams", "covt_resolve_op",
+    "covt_batch_decode", "covt_batch_free", "covt_decode_streams", "covt_batch_decode_streams", "covt_encode_streams", "covt_resolve_op",
     "covt_result_num_tiles", "covt_result_num_layers", "covt_result_layers", "covt_result_tile_status",
     "covt_result_buffer", "covt_result_read", "covt_result_timing", "covt_result_kernel_times", "covt_result_free",
     "covt_result_prop_columns", "covt_result_prop_dictionaries", "covt_result_prop_buffer", "covt_result_prop_read",
@@ -75,6 +75,7 @@ def lib():
     L.covt_batch_free.restype = None
     L.covt_decode_streams.argtypes = [vp, vp, u64, C.POINTER(abi.StreamDesc), u32, u32, C.POINTER(vp)]
     L.covt_batch_decode_streams.argtypes = [vp, vp, C.POINTER(abi.StreamDesc), u32, u32, C.POINTER(vp)]
+    L.covt_encode_streams.argtypes = [vp, vp, u64, C.POINTER(abi.EncodeDesc), u32, u32, C.POINTER(vp)]
     L.covt_resolve_op.argtypes = [u32, u32, u32, u32]
     L.covt_result_num_tiles.argtypes = [vp]
     L.covt_result_num_tiles.restype = u32
@@ -358,6 +359,26 @@ class Decoder:
             self._check(lib().covt_decode_streams(self._h, _ptr(b), b.size, descs, n, flags, C.byref(h)))
         return Result(self, h)
 
+    def encode_streams(self, values, descs, flags=abi.FLAG_DEFAULT):
+        """values: one host buffer (any dtype, viewed as bytes); descs: ctypes array of abi.EncodeDesc (filled in place).
+        Returns a Result whose BUF_STREAM_ARENA holds the encoded streams."""
+        h = C.c_void_p()
+        v = np.ascontiguousarray(values).view(np.uint8).reshape(-1)
+        self._check(lib().covt_encode_streams(self._h, _ptr(v), v.size, descs, len(descs), flags, C.byref(h)))
+        return Result(self, h)
+
+    def encode_stream(self, values, op, num_bits=0, flags=abi.FLAG_DEFAULT):
+        """One EncodingUtils call: the values a stream of `op` decodes to -> (its bytes, status). Morton ops take an (n, 2) int32 array."""
+        v = np.ascontiguousarray(values, dtype=np.int32 if op in (abi.OP_VARINT_DELTA_MORTON, abi.OP_PFOR_DELTA_MORTON) else abi.op_dtype(op))
+        n = len(v) if op in (abi.OP_VARINT_DELTA_MORTON, abi.OP_PFOR_DELTA_MORTON) and v.ndim == 2 else v.size
+        descs = (abi.EncodeDesc * 1)()
+        descs[0] = abi.EncodeDesc(value_offset=0, num_values=n, op=op, num_bits=num_bits)
+        res = self.encode_streams(v, descs, flags)
+        d = descs[0]
+        raw = res.buffer(abi.BUF_STREAM_ARENA, d.out_offset, d.byte_length) if d.byte_length else np.zeros(0, np.uint8)
+        res.free()
+        return raw.copy(), d.status
+
     def decode_stream(self, blob, op=0, *, byte_offset=0, byte_length=None, num_values, stream_type=0, encoding=0,
                       column_type=0, num_bits=0, flags=abi.FLAG_DEFAULT):
         """One DecodingUtils call. Returns (values ndarray, status, bytes_consumed)."""
@@ -488,6 +509,59 @@ def default_decoder(device=0):
     if device not in _default:
         _default[device] = Decoder(device)
     return _default[device]
+
+
+class EncodingUtils:
+    """Same names and argument meaning as J/converter/EncodingUtils.java (the static encoders), on the GPU."""
+
+    @staticmethod
+    def _run(op, values, num_bits=0):
+        raw, st = default_decoder().encode_stream(values, op, num_bits=num_bits)
+        if st != abi.OK:
+            raise CovtError(st, "stream encode failed")
+        return raw
+
+    @staticmethod
+    def encodeVarints(values, zigZag, delta):  # EncodingUtils.java:39 (long[] in; 64-bit LEB128)
+        v = np.asarray(values, dtype=np.int64)
+        if zigZag and delta:
+            return EncodingUtils._run(abi.OP_VARINT_ZZ_DELTA_64, v)
+        if not zigZag and not delta:
+            return EncodingUtils._run(abi.OP_VARINT_U64, v)
+        if zigZag:  # zigzag without delta: 32-bit values only (INT_64 property data, CovtParser.java:303-306)
+            return EncodingUtils._run(abi.OP_VARINT_ZZ, v.astype(np.int32))
+        raise CovtError(abi.ERR_UNSUPPORTED_ENCODING, "delta without zigzag is only written for Morton codes (encodeMortonDeltaVarints)")
+
+    @staticmethod
+    def encodeZigZagDeltaCoordinates(vertices):  # :190-211 + encodeVarints(.., false, false): the PLAIN vertex buffer
+        return EncodingUtils._run(abi.OP_VARINT_ZZ_DELTA_XY, np.asarray(vertices, dtype=np.int32).reshape(-1))
+
+    @staticmethod
+    def encodeRle(values, signed):  # :123
+        return EncodingUtils._run(abi.OP_RLE_S64 if signed else abi.OP_RLE_U64, np.asarray(values, dtype=np.int64))
+
+    @staticmethod
+    def encodeByteRle(values):  # :136
+        return EncodingUtils._run(abi.OP_BYTE_RLE, np.asarray(values, dtype=np.uint8))
+
+    @staticmethod
+    def encodeFastPfor128(values, zigZag=True, delta=True):  # :149 (topology streams: zigzag + delta)
+        if not (zigZag and delta):
+            raise CovtError(abi.ERR_UNSUPPORTED_ENCODING, "the decode path reads FastPFOR streams as zigzag deltas (coordinates: "
+                            "encodeFastPfor128Coordinates, Morton codes: encodeMortonFastPfor128)")
+        return EncodingUtils._run(abi.OP_PFOR_ZZ_DELTA, np.asarray(values, dtype=np.int32))
+
+    @staticmethod
+    def encodeFastPfor128Coordinates(vertices):  # encodeZigZagDeltaCoordinates + encodeFastPfor128(.., false, false)
+        return EncodingUtils._run(abi.OP_PFOR_ZZ_DELTA_XY, np.asarray(vertices, dtype=np.int32).reshape(-1))
+
+    @staticmethod
+    def encodeMortonDeltaVarints(vertices, numBits):  # GeometryUtils.encodeMorton + encodeVarints(codes, false, true)
+        return EncodingUtils._run(abi.OP_VARINT_DELTA_MORTON, np.asarray(vertices, dtype=np.int32).reshape(-1, 2), num_bits=numBits)
+
+    @staticmethod
+    def encodeMortonFastPfor128(vertices, numBits):  # GeometryUtils.encodeMorton + encodeFastPfor128(codes, false, true)
+        return EncodingUtils._run(abi.OP_PFOR_DELTA_MORTON, np.asarray(vertices, dtype=np.int32).reshape(-1, 2), num_bits=numBits)
 
 
 class DecodingUtils:

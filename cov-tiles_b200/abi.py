@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # covt_stream_encoding
 ENC_PLAIN, ENC_VARINT, ENC_VARINT_ZIG_ZAG, ENC_VARINT_DELTA, ENC_VARINT_DELTA_ZIG_ZAG = 0, 1, 2, 3, 4
@@ -102,6 +102,12 @@ class StreamDesc(C.Structure):
                 ("out_offset", C.c_uint64), ("out_count", C.c_uint64)]
 
 
+class EncodeDesc(C.Structure):
+    """covt_encode_desc: one EncodingUtils call (value_offset in BYTES into the values buffer)."""
+    _fields_ = [("value_offset", C.c_uint64), ("num_values", C.c_uint32), ("op", C.c_uint8), ("num_bits", C.c_uint8),
+                ("reserved", C.c_uint8 * 2), ("out_offset", C.c_uint64), ("byte_length", C.c_uint32), ("status", C.c_uint32)]
+
+
 class TileJson(C.Structure):
     _fields_ = [("n_vector_layers", C.c_uint32), ("n_fields", C.POINTER(C.c_uint32))]
 
@@ -173,3 +179,4 @@ def prop_column_values(blob, c, validity, values, dict_offsets, dictionaries):
 LAYER_DTYPE = np.dtype(Layer)
 STREAM_DESC_DTYPE = np.dtype(StreamDesc)
 assert C.sizeof(StreamRef) == 24 and C.sizeof(StreamDesc) == 48, (C.sizeof(StreamRef), C.sizeof(StreamDesc))
+assert C.sizeof(EncodeDesc) == 32, C.sizeof(EncodeDesc)

@@ -1109,6 +1109,161 @@ int32_t covt_decode_streams(covt_ctx* ctx, const uint8_t* blob, uint64_t blob_le
 }
 
 // ------------------------------------------------------------------------------------------------
+// stream encoders: the inverse of the decode ops, EncodingUtils.java:39-230 on the GPU (covt_encode.cu)
+// ------------------------------------------------------------------------------------------------
+int32_t covt_encode_streams(covt_ctx* ctx, const void* values, uint64_t values_bytes, covt_encode_desc* descs, uint32_t n, uint32_t flags,
+                            covt_result** out)
+{
+    if (!ctx || !out || (!descs && n) || (!values && values_bytes)) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_encode_streams: bad argument");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<EncPiece> pieces[3];  // 0 = varint pieces, 1 = RLE / Byte-RLE streams, 2 = FastPFOR streams
+    uint64_t scratch[3] = {0, 0, 0}, in_bytes = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        covt_encode_desc& d = descs[i];
+        d.status = COVT_OK;
+        d.out_offset = 0;
+        d.byte_length = 0;
+        const uint32_t op = d.op;
+        int kind = -1;
+        uint64_t elem = 4, cap = 0;
+        const uint64_t nv = d.num_values;
+        switch (op) {
+        case COVT_OP_VARINT_U32: case COVT_OP_VARINT_ZZ: case COVT_OP_VARINT_ZZ_DELTA: case COVT_OP_VARINT_ZZ_DELTA_XY: kind = 0; elem = 4; cap = 5; break;
+        case COVT_OP_VARINT_DELTA_MORTON: kind = 0; elem = 8; cap = 10; break;
+        case COVT_OP_VARINT_U64: case COVT_OP_VARINT_ZZ_DELTA_64: kind = 0; elem = 8; cap = 10; break;
+        case COVT_OP_BYTE_RLE: kind = 1; elem = 1; cap = nv + nv / 128 + 8; break;
+        case COVT_OP_RLE_U32: kind = 1; elem = 4; cap = 10 * nv + nv / 128 + 16; break;
+        case COVT_OP_RLE_U64: case COVT_OP_RLE_S64: kind = 1; elem = 8; cap = 10 * nv + nv / 128 + 16; break;
+        case COVT_OP_PFOR_ZZ_DELTA: case COVT_OP_PFOR_ZZ_DELTA_XY: kind = 2; elem = 4; break;
+        case COVT_OP_PFOR_DELTA_MORTON: kind = 2; elem = 8; break;
+        default: break;
+        }
+        if (kind < 0) { d.status = COVT_ERR_UNSUPPORTED_ENCODING; continue; }
+        if (d.value_offset > values_bytes || nv * elem > values_bytes - d.value_offset || (d.value_offset % elem) != 0 ||
+            (op == COVT_OP_VARINT_ZZ_DELTA_XY || op == COVT_OP_PFOR_ZZ_DELTA_XY) && (nv & 1u)) {
+            d.status = COVT_ERR_INVALID_ARG;
+            continue;
+        }
+        in_bytes += nv * elem;
+        EncPiece p;
+        memset(&p, 0, sizeof(p));
+        p.stream_values = d.value_offset;
+        p.stream = i;
+        p.op = (uint8_t)op;
+        p.num_bits = d.num_bits;
+        if (kind == 0) {
+            for (uint64_t f = 0; f < nv || f == 0; f += ENC_VARINT_PIECE) {
+                p.first_index = (uint32_t)f;
+                p.num_values = (uint32_t)std::min<uint64_t>(ENC_VARINT_PIECE, nv - f);
+                p.scratch = reinterpret_cast<uint8_t*>(scratch[0]);  // offset for now
+                scratch[0] += ((uint64_t)p.num_values * cap + 64 + 15) & ~15ull;
+                pieces[0].push_back(p);
+                if (nv == 0) break;
+            }
+        } else {
+            if (kind == 2) cap = 16 * nv + 1024 * (nv / 65536 + 1) + 2048;  // words <= ~2.3 n + per-page headers (see k_enc_pfor)
+            p.num_values = d.num_values;
+            p.scratch = reinterpret_cast<uint8_t*>(scratch[kind]);
+            scratch[kind] += (cap + 64 + 15) & ~15ull;
+            pieces[kind].push_back(p);
+        }
+    }
+    const uint32_t np[3] = {(uint32_t)pieces[0].size(), (uint32_t)pieces[1].size(), (uint32_t)pieces[2].size()};
+    const uint32_t n_pieces = np[0] + np[1] + np[2];
+    covt_result* R = new covt_result();
+    R->ctx = ctx;
+    uint8_t* d_values = nullptr;
+    uint8_t* d_scratch = nullptr;
+    EncPiece* d_pieces = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    int32_t rc = COVT_OK;
+    auto cleanup_tmp = [&]() {
+        dev_free(ctx, d_values);
+        dev_free(ctx, d_scratch);
+        dev_free(ctx, d_pieces);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (ev2) cudaEventDestroy(ev2);
+    };
+#define CKE(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char m_[512];                                                                             \
+            snprintf(m_, sizeof(m_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = m_;                                                                            \
+            rc = e_ == cudaErrorMemoryAllocation ? COVT_ERR_OOM : COVT_ERR_CUDA;                      \
+            cudaStreamSynchronize(st);                                                                \
+            cleanup_tmp();                                                                            \
+            covt_result_free(R);                                                                      \
+            return rc;                                                                                \
+        }                                                                                             \
+    } while (0)
+    CKE(cudaEventCreate(&ev0));
+    CKE(cudaEventCreate(&ev1));
+    CKE(cudaEventCreate(&ev2));
+    const uint64_t scratch_total = scratch[0] + scratch[1] + scratch[2];
+    CKE(dev_alloc_bytes(ctx, reinterpret_cast<void**>(&d_values), values_bytes + 64));
+    CKE(dev_alloc_bytes(ctx, reinterpret_cast<void**>(&d_scratch), scratch_total + 64));
+    CKE(dev_alloc(ctx, &d_pieces, std::max<uint32_t>(n_pieces, 1)));
+    std::vector<EncPiece> all;
+    all.reserve(n_pieces);
+    {
+        uint64_t base = 0;
+        for (int k = 0; k < 3; k++) {
+            for (auto& p : pieces[k]) { p.scratch = d_scratch + base + reinterpret_cast<uintptr_t>(p.scratch); all.push_back(p); }
+            base += scratch[k];
+        }
+    }
+    CKE(cudaEventRecord(ev0, st));
+    if (values_bytes) CKE(cudaMemcpyAsync(d_values, values, values_bytes, cudaMemcpyHostToDevice, st));
+    if (n_pieces) CKE(cudaMemcpyAsync(d_pieces, all.data(), (uint64_t)n_pieces * sizeof(EncPiece), cudaMemcpyHostToDevice, st));
+    if (scratch[2]) CKE(cudaMemsetAsync(d_scratch + scratch[0] + scratch[1], 0, scratch[2], st));  // FastPFOR words are OR-ed together
+    CKE(cudaEventRecord(ev1, st));
+    CKE(launch_encode_pieces(d_values, d_pieces, np[0], d_pieces + np[0], np[1], d_pieces + np[0] + np[1], np[2], flags, st));
+    if (n_pieces) CKE(cudaMemcpyAsync(all.data(), d_pieces, (uint64_t)n_pieces * sizeof(EncPiece), cudaMemcpyDeviceToHost, st));
+    CKE(cudaStreamSynchronize(st));
+    // final place of every stream (16-byte aligned, in descriptor order) and of every piece inside its stream
+    std::vector<uint64_t> stream_len(n, 0);
+    for (auto& p : all) stream_len[p.stream] += p.byte_length;
+    uint64_t arena = 0, out_bytes = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (descs[i].status != COVT_OK) continue;
+        if (stream_len[i] > 0xffffffffull) { descs[i].status = COVT_ERR_INVALID_ARG; stream_len[i] = 0; continue; }
+        descs[i].out_offset = arena;
+        descs[i].byte_length = (uint32_t)stream_len[i];
+        out_bytes += stream_len[i];
+        arena += (stream_len[i] + 15) & ~15ull;
+    }
+    {
+        std::vector<uint64_t> cursor(n, 0);
+        for (auto& p : all) {  // (the pieces of a stream are in order inside their kind)
+            p.out_offset = descs[p.stream].out_offset + cursor[p.stream];
+            cursor[p.stream] += p.byte_length;
+            if (descs[p.stream].status != COVT_OK) p.byte_length = 0;
+        }
+    }
+    R->counts[COVT_BUF_STREAM_ARENA] = arena;
+    CKE(dev_alloc_bytes(ctx, &R->arena, arena + 64));
+    R->bufs[COVT_BUF_STREAM_ARENA] = R->arena;
+    if (n_pieces) CKE(cudaMemcpyAsync(d_pieces, all.data(), (uint64_t)n_pieces * sizeof(EncPiece), cudaMemcpyHostToDevice, st));
+    CKE(launch_encode_compact(d_pieces, n_pieces, reinterpret_cast<uint8_t*>(R->arena), st));
+    CKE(cudaEventRecord(ev2, st));
+    CKE(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&R->timing.h2d_ms, ev0, ev1);
+    cudaEventElapsedTime(&R->timing.decode_ms, ev1, ev2);  // (device time of the encode: kernels + the size read-back between them)
+    R->timing.payload_bytes = out_bytes;  // compressed bytes written
+    R->timing.output_bytes = in_bytes;    // value bytes read
+    R->timing.kernel_launches = (np[0] ? 1 : 0) + (np[1] ? 1 : 0) + (np[2] ? 1 : 0) + (n_pieces ? 1 : 0);
+    cleanup_tmp();
+#undef CKE
+    *out = R;
+    return COVT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // results
 // ------------------------------------------------------------------------------------------------
 uint32_t covt_result_num_tiles(const covt_result* res) { return res ? res->n_tiles : 0; }

@@ -123,6 +123,23 @@ struct PropOut {
 cudaError_t launch_k0_props(bool fill, const uint8_t* blob, const uint64_t* tile_offsets, const covt_layer* layers, uint32_t n_layers, uint32_t container,
                             const uint32_t* tj_fields, uint32_t tj_layers, uint64_t* pcols, const PropOut& out, uint64_t* totals, cudaStream_t st);
 cudaError_t launch_prop_finish(const uint8_t* blob, uint32_t n_cols, uint32_t n_dicts, const PropOut& out, cudaStream_t st);
+// ---- stream encoders (covt_encode.cu) ----
+constexpr uint32_t ENC_VARINT_PIECE = 4096;  // values per piece of a varint stream (one warp)
+// One unit of encode work: a range of a varint stream, or a whole RLE / Byte-RLE / FastPFOR stream.
+struct EncPiece {
+    uint64_t stream_values;  // byte offset of the STREAM's first value in the device copy of the caller's values
+    uint8_t* scratch;        // 16-byte aligned, bounded range the piece is written to (FastPFOR: zeroed)
+    uint64_t out_offset;     // byte offset of the piece in the result arena (set by the host between encode and compaction)
+    uint32_t first_index;    // index of the piece's first value in its stream (the value before it feeds its delta)
+    uint32_t num_values;
+    uint32_t byte_length;    // out
+    uint32_t status;         // out
+    uint32_t stream;         // index of the covt_encode_desc
+    uint8_t op, num_bits, pad[2];
+};
+cudaError_t launch_encode_pieces(const uint8_t* values, EncPiece* varint_pieces, uint32_t n_varint, EncPiece* rle_pieces, uint32_t n_rle,
+                                 EncPiece* pfor_pieces, uint32_t n_pfor, uint32_t flags, cudaStream_t st);
+cudaError_t launch_encode_compact(const EncPiece* pieces, uint32_t n_pieces, uint8_t* arena, cudaStream_t st);
 uint32_t host_resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags);
 int host_op_class_of(uint32_t op);  // OpClass of a covt_op, -1 for COVT_OP_NONE
 

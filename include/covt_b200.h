@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define COVT_ABI_VERSION 3
+#define COVT_ABI_VERSION 4
 
 /* ---- wire enums (ordinals identical to the Java enums) ------------------------------------ */
 
@@ -219,6 +219,29 @@ typedef struct covt_stream_desc {
     uint64_t out_count;       /* out: decoded elements (ints; 2 per vertex for Morton ops; bytes for Byte-RLE) */
 } covt_stream_desc;
 
+/* Stream-level ENCODE request: one EncodingUtils call. The stream is named by the covt_op that DECODES it; the
+ * values are what that op produces (u8 for Byte-RLE, i32 / i64 as the covt_op table says, x,y int pairs for the Morton ops) and
+ * the bytes are what the reference's encoder writes for them:
+ *   COVT_OP_BYTE_RLE                     EncodingUtils.encodeByteRle :136-147 (orc RunLengthByteWriter)
+ *   COVT_OP_RLE_U32 / _U64 / _S64        EncodingUtils.encodeRle :123-134 (orc RunLengthIntegerWriter; signed = zigzag LEB128)
+ *   COVT_OP_VARINT_U32 / _ZZ / _ZZ_DELTA EncodingUtils.encodeVarints(values, zigZag, delta) :39-55 (64-bit arithmetic on the widened ints)
+ *   COVT_OP_VARINT_ZZ_DELTA_XY           encodeZigZagDeltaCoordinates :190-211, then encodeVarints(.., false, false)
+ *   COVT_OP_VARINT_U64 / _ZZ_DELTA_64    encodeVarints on longs (id columns)
+ *   COVT_OP_PFOR_ZZ_DELTA / _XY          encodeFastPfor128 :149-188 (Composition(FastPFOR, VariableByte), big-endian words)
+ *   COVT_OP_VARINT_DELTA_MORTON / COVT_OP_PFOR_DELTA_MORTON   GeometryUtils.encodeMorton :23-32 of every vertex, deltas without
+ *                                        zigzag (CovtConverter.java:939-948); num_values = vertices
+ * (the _AS_I64 ops are decode-side width emulations: encode with the 32-bit op). */
+typedef struct covt_encode_desc {
+    uint64_t value_offset;    /* in: BYTE offset of the stream's first value in `values` (aligned to the value size) */
+    uint32_t num_values;      /* in: values (Morton ops: vertices, two ints each) */
+    uint8_t  op;              /* in: covt_op */
+    uint8_t  num_bits;        /* in: Morton bits */
+    uint8_t  reserved[2];
+    uint64_t out_offset;      /* out: byte offset of the encoded stream in COVT_BUF_STREAM_ARENA (16-byte aligned) */
+    uint32_t byte_length;     /* out: its byteLength */
+    uint32_t status;          /* out */
+} covt_encode_desc;
+
 /* Decode routines = rows a1..a10 of SURVEY §8a. */
 enum covt_op {
     COVT_OP_NONE = 0,
@@ -355,6 +378,12 @@ int32_t covt_decode_streams(covt_ctx* ctx, const uint8_t* blob, uint64_t blob_le
                             uint32_t n_streams, uint32_t flags, covt_result** out);
 int32_t covt_batch_decode_streams(covt_ctx* ctx, covt_batch* batch, covt_stream_desc* descs, uint32_t n_streams,
                                   uint32_t flags, covt_result** out);
+/* Encodes n streams of host `values` on the GPU; the encoded bytes are COVT_BUF_STREAM_ARENA of the result (device-resident, read
+ * with covt_result_read). flags: COVT_FLAG_MORTON_NO_SHIFT. covt_timing of the result: h2d_ms = upload of the values, decode_ms =
+ * device time of the encode, payload_bytes = bytes written, output_bytes = value bytes read. Replaces the static encoders of
+ * EncodingUtils (J/converter/EncodingUtils.java:39-230). */
+int32_t covt_encode_streams(covt_ctx* ctx, const void* values, uint64_t values_bytes, covt_encode_desc* descs, uint32_t n_streams,
+                            uint32_t flags, covt_result** out);
 /* Dispatch table of CovtParser.decodeGeometryColumn / decodedIds: which routine decodes a stream. */
 int32_t covt_resolve_op(uint32_t stream_type, uint32_t encoding, uint32_t column_type, uint32_t flags);
 

@@ -47,10 +47,14 @@ def test_struct_layout_matches_header(covt, tmp_path):
                     ' offsetof(covt_stream_desc, out_offset));\n'
                     'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(covt_prop_column), sizeof(covt_prop_dictionary), offsetof(covt_prop_column, status),'
                     ' offsetof(covt_prop_column, validity_offset), offsetof(covt_prop_column, data_num_values), offsetof(covt_prop_dictionary, offsets_offset),'
-                    ' offsetof(covt_layer, header_offset));\nreturn 0;}\n')
+                    ' offsetof(covt_layer, header_offset));\n'
+                    'printf("%zu %zu %zu %zu\\n", sizeof(covt_encode_desc), offsetof(covt_encode_desc, op), offsetof(covt_encode_desc, out_offset),'
+                    ' offsetof(covt_encode_desc, status));\nreturn 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
-    a, b, c = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    a, b, c, d = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    assert [int(x) for x in d.split()] == [C.sizeof(abi.EncodeDesc), abi.EncodeDesc.op.offset, abi.EncodeDesc.out_offset.offset,
+                                            abi.EncodeDesc.status.offset]
     assert [int(x) for x in c.split()] == [C.sizeof(abi.PropColumn), C.sizeof(abi.PropDictionary), abi.PropColumn.status.offset,
                                             abi.PropColumn.validity_offset.offset, abi.PropColumn.data_num_values.offset,
                                             abi.PropDictionary.offsets_offset.offset, abi.Layer.header_offset.offset]
