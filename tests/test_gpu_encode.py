@@ -134,7 +134,7 @@ def test_morton_encoders(covt, gen, decoder, nbits, no_shift):
     rng = np.random.default_rng(14 + nbits)
     flags = abi.FLAG_DEFAULT | (abi.FLAG_MORTON_NO_SHIFT if no_shift else 0)
     cases, want, verts = [], [], []
-    half = (2 << (nbits - 2)) // 2
+    half = (1 << (nbits - 1)) if no_shift else (2 << (nbits - 2)) // 2  # no_shift: the decoder sign-extends the num_bits-bit value
     for n in [0, 1, 2, 33, 255, 256, 257, 4097, 70000]:
         x = rng.integers(0, 1 << nbits, n) - half
         y = rng.integers(0, 1 << nbits, n) - half
