@@ -41,6 +41,14 @@ public final class CovtGpuDecoder implements AutoCloseable {
     private static final MethodHandle DESTROY_MULTI = h("covt_destroy_multi", FunctionDescriptor.ofVoid(ADDRESS));
     public static final long PROP_COLUMN_BYTES = 72, PROP_DICTIONARY_BYTES = 40;  // sizeof(covt_prop_column / covt_prop_dictionary)
     public static final int FLAG_DECODE_PROPERTIES = 0x80;
+    // the stream ENCODERS: EncodingUtils.encodeVarints / encodeRle / encodeByteRle / encodeFastPfor128 (EncodingUtils.java:39-230)
+    private static final MethodHandle ENCODE_STREAMS = h("covt_encode_streams",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
+    /** covt_encode_desc (32 bytes): value_offset (bytes), num_values, op = the covt_op that decodes the stream, num_bits | out_offset, byte_length, status. */
+    public static final StructLayout ENCODE_DESC = MemoryLayout.structLayout(
+        JAVA_LONG.withName("value_offset"), JAVA_INT.withName("num_values"), JAVA_BYTE.withName("op"), JAVA_BYTE.withName("num_bits"),
+        MemoryLayout.paddingLayout(2), JAVA_LONG.withName("out_offset"), JAVA_INT.withName("byte_length"), JAVA_INT.withName("status"));
+    public static final int OP_RLE_U64 = 3, OP_RLE_S64 = 4;
     private static final MethodHandle DECODE_STREAMS = h("covt_decode_streams",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
 
@@ -105,6 +113,24 @@ public final class CovtGpuDecoder implements AutoCloseable {
             RESULT_FREE.invokeExact(res);
             pos.add(d.get(JAVA_INT, 28));                 // bytes_consumed: what the Java reader advanced pos by
             return host.toArray(JAVA_INT);
+        } catch (Throwable t) { throw sneaky(t); }
+    }
+
+    /** EncodingUtils.encodeRle(long[] values, boolean signed) (EncodingUtils.java:123-134) on the GPU; the other encoders differ in op and value type only. */
+    public byte[] encodeRle(long[] values, boolean signed) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment v = a.allocateFrom(JAVA_LONG, values);
+            MemorySegment d = a.allocate(ENCODE_DESC);
+            d.set(JAVA_LONG, 0, 0L); d.set(JAVA_INT, 8, values.length); d.set(JAVA_BYTE, 12, (byte) (signed ? OP_RLE_S64 : OP_RLE_U64));
+            MemorySegment out = a.allocate(ADDRESS);
+            int rc = (int) ENCODE_STREAMS.invokeExact(ctx, v, 8L * values.length, d, 1, 0, out);
+            if (rc != 0 || d.get(JAVA_INT, 28) != 0) throw new IllegalArgumentException("stream encode failed: " + lastError(ctx));
+            MemorySegment res = out.get(ADDRESS, 0);
+            int n = d.get(JAVA_INT, 24);
+            MemorySegment host = a.allocate(JAVA_BYTE, Math.max(n, 1));
+            rc = (int) RESULT_READ.invokeExact(res, 12 /*COVT_BUF_STREAM_ARENA*/, d.get(JAVA_LONG, 16), (long) n, host);
+            RESULT_FREE.invokeExact(res);
+            return host.asSlice(0, n).toArray(JAVA_BYTE);
         } catch (Throwable t) { throw sneaky(t); }
     }
 
