@@ -41,7 +41,8 @@ def build(force=False, verbose=False):
 
 # every symbol include/covt_b200.h declares
 ABI_SYMBOLS = [
-    "covt_abi_version", "covt_create", "covt_destroy", "covt_last_error", "covt_trim", "covt_decode_batch", "covt_batch_upload",
+    "covt_abi_version", "covt_create", "covt_destroy", "covt_last_error", "covt_trim", "covt_decode_batch", "covt_decode_batch_to_host",
+    "covt_batch_upload",
     "covt_batch_decode", "covt_batch_free", "covt_decode_streams", "covt_batch_decode_streams", "covt_encode_streams", "covt_resolve_op",
     "covt_result_num_tiles", "covt_result_num_layers", "covt_result_layers", "covt_result_tile_status",
     "covt_result_buffer", "covt_result_read", "covt_result_timing", "covt_result_kernel_times", "covt_result_free",
@@ -69,6 +70,7 @@ def lib():
     L.covt_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.covt_trim.argtypes = [vp]
     L.covt_decode_batch.argtypes = [vp, vp, vp, u32, u32, C.POINTER(abi.TileJson), u32, C.POINTER(vp)]
+    L.covt_decode_batch_to_host.argtypes = [vp, vp, vp, u32, u32, C.POINTER(abi.TileJson), u32, C.POINTER(abi.HostSink), C.POINTER(vp)]
     L.covt_batch_upload.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
     L.covt_batch_decode.argtypes = [vp, vp, u32, C.POINTER(abi.TileJson), u32, C.POINTER(vp)]
     L.covt_batch_free.argtypes = [vp]
@@ -346,6 +348,24 @@ class Decoder:
         h = C.c_void_p()
         self._check(lib().covt_decode_batch(self._h, blob_ptr, tile_offsets_ptr, n_tiles, container, None, flags, C.byref(h)))
         return Result(self, h)
+
+    def decode_batch_to_host_raw(self, blob_ptr, tile_offsets_ptr, n_tiles, sink, container=abi.CONTAINER_GEN2B, flags=abi.FLAG_DEFAULT):
+        """covt_decode_batch_to_host: like decode_batch_raw, and every buffer the abi.HostSink names lands in its (page-locked) host
+        memory, copied back segment by segment while later segments are uploaded and decoded."""
+        h = C.c_void_p()
+        self._check(lib().covt_decode_batch_to_host(self._h, blob_ptr, tile_offsets_ptr, n_tiles, container, None, flags, C.byref(sink), C.byref(h)))
+        return Result(self, h)
+
+    def decode_batch_to_host(self, blob, tile_offsets, host_arrays, container=abi.CONTAINER_GEN2B, flags=abi.FLAG_DEFAULT):
+        """host_arrays: {buffer id: numpy array of that buffer's dtype} (page-locked memory for overlap; any memory works)."""
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        offs = np.ascontiguousarray(tile_offsets, dtype=np.uint64)
+        sink = abi.HostSink()
+        for which, a in host_arrays.items():
+            assert a.dtype == np.dtype(abi.BUF_DTYPES[which]) and a.flags["C_CONTIGUOUS"]
+            sink.ptr[which] = a.ctypes.data
+            sink.capacity[which] = a.size
+        return self.decode_batch_to_host_raw(_ptr(b), offs.ctypes.data, len(offs) - 1, sink, container, flags)
 
     # ---- stream path ------------------------------------------------------------------------
     def decode_streams(self, blob_or_batch, descs, flags=abi.FLAG_DEFAULT):

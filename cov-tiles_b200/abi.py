@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # covt_stream_encoding
 ENC_PLAIN, ENC_VARINT, ENC_VARINT_ZIG_ZAG, ENC_VARINT_DELTA, ENC_VARINT_DELTA_ZIG_ZAG = 0, 1, 2, 3, 4
@@ -106,6 +106,11 @@ class EncodeDesc(C.Structure):
     """covt_encode_desc: one EncodingUtils call (value_offset in BYTES into the values buffer)."""
     _fields_ = [("value_offset", C.c_uint64), ("num_values", C.c_uint32), ("op", C.c_uint8), ("num_bits", C.c_uint8),
                 ("reserved", C.c_uint8 * 2), ("out_offset", C.c_uint64), ("byte_length", C.c_uint32), ("status", C.c_uint32)]
+
+
+class HostSink(C.Structure):
+    """covt_host_sink: page-locked host destinations (and capacities in elements) per result buffer; NULL = not wanted."""
+    _fields_ = [("ptr", C.c_void_p * 13), ("capacity", C.c_uint64 * 13)]
 
 
 class TileJson(C.Structure):

@@ -36,6 +36,7 @@ struct covt_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;       // kernels, allocations, result read-backs
     cudaStream_t copy_stream = nullptr;  // host->device segments of covt_decode_batch, overlapped with the kernels
+    cudaStream_t out_stream = nullptr;   // device->host segments of covt_decode_batch_to_host (PCIe is full duplex: its own stream)
     std::string err;
     uint64_t* h_totals = nullptr;  // pinned scratch for the one device->host size read-back
     covt::SegState* h_seg = nullptr;     // pinned mirror of the device-side segment state
@@ -333,6 +334,7 @@ void covt_destroy(covt_ctx* ctx)
     for (auto& b : ctx->pinned_cache) cudaFreeHost(b.first);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
         if (ctx->class_stream[c]) cudaStreamDestroy(ctx->class_stream[c]);
         if (ctx->ev_join[c]) cudaEventDestroy(ctx->ev_join[c]);
@@ -551,7 +553,7 @@ static int32_t decode_properties(covt_ctx* ctx, covt_batch* batch, uint32_t cont
 // segment with exact sizes (correct, only slower).
 static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t container, const covt_tilejson* tilejson, uint32_t flags,
                                const std::vector<uint32_t>& seg_starts, const uint64_t* h_tile_offsets,
-                               const std::vector<cudaEvent_t>* uploaded, covt_result** out)
+                               const std::vector<cudaEvent_t>* uploaded, covt_result** out, const covt_host_sink* sink = nullptr)
 {
     *out = nullptr;
     const uint32_t n_tiles = batch->n_tiles;
@@ -562,6 +564,41 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
     R->n_tiles = n_tiles;
     Profiler prof = {ctx, (flags & COVT_FLAG_PROFILE_KERNELS) != 0, {}};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // Host sink (covt_decode_batch_to_host): the slice of every wanted buffer that a segment produced goes to the caller's
+    // page-locked memory on its own stream while later segments are uploaded and decoded. The host learns a segment's element
+    // totals from a snapshot of SegState::base copied right behind the segment's kernels; it waits for segment i-1's snapshot
+    // only after it has queued segment i, so the GPU never runs dry.
+    uint64_t* h_snap = nullptr;                 // pinned: S x TILE_COLS running totals
+    std::vector<cudaEvent_t> seg_done(sink ? seg_starts.size() - 1 : 0, nullptr);
+    cudaEvent_t ev_out0 = nullptr, ev_out1 = nullptr;
+    uint64_t sink_prev[COVT_NUM_BUFFERS] = {};  // elements of every buffer already sent
+    bool sink_small = false;
+    auto sink_cleanup = [&]() {
+        for (auto e : seg_done) if (e) cudaEventDestroy(e);
+        if (ev_out0) cudaEventDestroy(ev_out0);
+        if (ev_out1) cudaEventDestroy(ev_out1);
+        if (h_snap) pinned_give(ctx, h_snap, (seg_starts.size() - 1) * TILE_COLS * sizeof(uint64_t));
+        h_snap = nullptr;
+    };
+    // sends what segment sg added to the wanted buffers (R->bufs are known from segment 0 on); returns the first CUDA error
+    auto sink_send = [&](uint32_t sg) -> cudaError_t {
+        cudaError_t e = cudaEventSynchronize(seg_done[sg]);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(ctx->out_stream, seg_done[sg], 0)) != cudaSuccess) return e;
+        const uint64_t* base = h_snap + (uint64_t)sg * TILE_COLS;
+        for (int b = 0; b < COVT_NUM_BUFFERS; b++) {
+            if (!sink->ptr[b]) continue;
+            const uint64_t end = base[1 + b];
+            if (end > sink->capacity[b]) { sink_small = true; continue; }
+            if (end <= sink_prev[b]) continue;
+            const uint64_t es = kBufElemSize[b];
+            e = cudaMemcpyAsync(static_cast<uint8_t*>(sink->ptr[b]) + sink_prev[b] * es, static_cast<const uint8_t*>(R->bufs[b]) + sink_prev[b] * es,
+                                (end - sink_prev[b]) * es, cudaMemcpyDeviceToHost, ctx->out_stream);
+            if (e != cudaSuccess) return e;
+            sink_prev[b] = end;
+        }
+        return cudaSuccess;
+    };
 
     uint64_t *d_cols = nullptr, *d_block_sums = nullptr, *d_totals = nullptr;
     uint32_t *d_tj = nullptr, *d_counter = nullptr, *d_tile_err = nullptr;
@@ -584,6 +621,8 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         dev_free(ctx, d_seg);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (sink && ctx->out_stream) cudaStreamSynchronize(ctx->out_stream);
+        sink_cleanup();
     };
 #define CKR(call)                                                                                     \
     do {                                                                                              \
@@ -602,6 +641,14 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
 
     CKR(cudaEventCreate(&ev0));
     CKR(cudaEventCreate(&ev1));
+    if (sink) {
+        if (!ctx->out_stream) CKR(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+        CKR(pinned_take(ctx, reinterpret_cast<void**>(&h_snap), (uint64_t)S * TILE_COLS * sizeof(uint64_t)));
+        for (auto& e : seg_done) CKR(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CKR(cudaEventCreate(&ev_out0));
+        CKR(cudaEventCreate(&ev_out1));
+        CKR(cudaEventRecord(ev_out0, ctx->out_stream));
+    }
     CKR(dev_alloc(ctx, &d_cols, (uint64_t)TILE_COLS * max_seg_tiles));
     CKR(dev_alloc(ctx, &d_block_sums, (uint64_t)TILE_COLS * nb));
     CKR(dev_alloc(ctx, &d_totals, 32));
@@ -716,7 +763,13 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         prof.end();
         CKR(launch_seg_end(d_seg, sg + 1 == S ? R->d_first_layer + n_tiles : nullptr, st));
         launches += 13;  // k_seg_begin, k0_fill_layers, 5 codec kernels + 4 second passes, k_assemble_layers, k_seg_end
+        if (sink) {
+            CKR(cudaMemcpyAsync(h_snap + (uint64_t)sg * TILE_COLS, d_seg->base, TILE_COLS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CKR(cudaEventRecord(seg_done[sg], st));
+            if (sg > 0) CKR(sink_send(sg - 1));  // (segment sg is queued: the GPU stays busy while the host waits for sg - 1)
+        }
     }
+    if (sink && S && n_tiles) CKR(sink_send(S - 1));
     if (n_tiles) {
         prof.begin("k_tile_status", 0);
         CKR(launch_finalize(R->d_layers, d_tile_err, n_tiles, (uint32_t)std::min<uint64_t>(ctx->h_seg->cap[0], 0xffffff00ull), flags, R->d_tile_status, d_totals + 16, d_seg, st));
@@ -736,11 +789,26 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         if (S == 1) return fail(ctx, COVT_ERR_CUDA, "internal error: exact capacities overflowed");
         ctx->overflow_retries++;
         std::vector<uint32_t> one = {0u, n_tiles};
-        rc = decode_segments(ctx, batch, container, tilejson, flags, one, h_tile_offsets, nullptr, out);
+        rc = decode_segments(ctx, batch, container, tilejson, flags, one, h_tile_offsets, nullptr, out, sink);
         if (rc == COVT_OK) (*out)->timing.capacity_retries = 1;
         return rc;
     }
     cudaEventElapsedTime(&R->timing.decode_ms, ev0, ev1);
+    if (sink) {
+        CKR(cudaEventRecord(ev_out1, ctx->out_stream));
+        CKR(cudaStreamSynchronize(ctx->out_stream));
+        cudaEventElapsedTime(&R->timing.d2h_ms, ev_out0, ev_out1);
+        if (sink_small) {
+            char m_[256];
+            uint64_t need[COVT_NUM_BUFFERS];
+            for (int b = 0; b < COVT_NUM_BUFFERS; b++) need[b] = ctx->h_seg->base[1 + b];
+            snprintf(m_, sizeof(m_), "covt_decode_batch_to_host: a sink buffer is too small (coords need %llu elements, ids %llu)",
+                     (unsigned long long)need[COVT_BUF_A_COORDS], (unsigned long long)need[COVT_BUF_S_IDS]);
+            cleanup_tmp();
+            covt_result_free(R);
+            return fail(ctx, COVT_ERR_INVALID_ARG, m_);
+        }
+    }
     R->n_layers = (uint32_t)ctx->h_seg->base[0];
     for (int b = 0; b < COVT_NUM_BUFFERS; b++) R->counts[b] = ctx->h_seg->base[1 + b];
     R->timing.h2d_ms = batch->h2d_ms;
@@ -789,8 +857,21 @@ int32_t covt_batch_decode(covt_ctx* ctx, covt_batch* batch, uint32_t container, 
 }
 
 // Host input: the blob goes up in segments on the copy stream while earlier segments are being decoded.
+static int32_t decode_batch_host(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                                 const covt_tilejson* tilejson, uint32_t flags, const covt_host_sink* sink, covt_result** out);
 int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
                           const covt_tilejson* tilejson, uint32_t flags, covt_result** out)
+{
+    return decode_batch_host(ctx, blob, tile_offsets, n_tiles, container, tilejson, flags, nullptr, out);
+}
+int32_t covt_decode_batch_to_host(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                                  const covt_tilejson* tilejson, uint32_t flags, const covt_host_sink* sink, covt_result** out)
+{
+    if (!sink) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_decode_batch_to_host: null sink");
+    return decode_batch_host(ctx, blob, tile_offsets, n_tiles, container, tilejson, flags, sink, out);
+}
+static int32_t decode_batch_host(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles, uint32_t container,
+                                 const covt_tilejson* tilejson, uint32_t flags, const covt_host_sink* sink, covt_result** out)
 {
     if (!ctx || !out || (!blob && n_tiles) || !tile_offsets) return fail(ctx, COVT_ERR_INVALID_ARG, "covt_decode_batch: null argument");
     if (container != COVT_CONTAINER_GEN2B && container != COVT_CONTAINER_GEN3) return fail(ctx, COVT_ERR_INVALID_ARG, "unknown container kind");
@@ -818,7 +899,8 @@ int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* ti
         covt_batch* b = nullptr;
         int32_t rc = covt_batch_upload(ctx, blob, tile_offsets, n_tiles, &b);
         if (rc != COVT_OK) return rc;
-        rc = covt_batch_decode(ctx, b, container, tilejson, flags, out);
+        std::vector<uint32_t> one = {0u, n_tiles};
+        rc = decode_segments(ctx, b, container, tilejson, flags, one, nullptr, nullptr, out, sink);
         covt_batch_free(b);
         return rc;
     }
@@ -865,7 +947,7 @@ int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* ti
         CK(e);
     }
     const double t_enq = now_ms();
-    int32_t rc = decode_segments(ctx, b, container, tilejson, flags, starts, tile_offsets, &evs, out);
+    int32_t rc = decode_segments(ctx, b, container, tilejson, flags, starts, tile_offsets, &evs, out, sink);
     cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->debug) fprintf(stderr, "[covt] covt_decode_batch: enqueue uploads %.2f ms, decode_segments %.2f ms\n", t_enq - t_call0, now_ms() - t_enq);
     if (rc == COVT_OK) {

@@ -206,7 +206,7 @@ struct PropWalk {
             r.num_values = 0;
             r.validity_offset = v_off;
             r.values_offset = d_off;
-            r.dictionary = kind == COVT_PV_DICT_INDEX ? dict_index : 0u;
+            r.dictionary = (kind == COVT_PV_DICT_INDEX && has_dict) ? dict_index : 0u;  // (a STRING column of another column type has none: status UNSUPPORTED_ENCODING)
             r.data_num_values = st == COVT_OK ? Ds.nv : 0u;
             out.cols[col] = r;
             uint32_t* a = out.aux + col * PROP_AUX_WORDS;

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define COVT_ABI_VERSION 4
+#define COVT_ABI_VERSION 5
 
 /* ---- wire enums (ordinals identical to the Java enums) ------------------------------------ */
 
@@ -301,7 +301,7 @@ typedef struct covt_prop_column {
     uint32_t num_values;         /* set bits of the validity bitmap = features that have a value */
     uint64_t validity_offset;    /* bytes into COVT_PBUF_VALIDITY */
     uint64_t values_offset;      /* elements into the buffer of value_kind: num_features slots (COVT_PV_BOOL: BYTES into COVT_PBUF_BOOL) */
-    uint32_t dictionary;         /* COVT_PV_DICT_INDEX: index into the dictionaries */
+    uint32_t dictionary;         /* COVT_PV_DICT_INDEX: index into the dictionaries (0 for a column without a dictionary of its own) */
     uint32_t data_num_values;    /* numValues the data stream declares (== num_values for a column with status COVT_OK) */
 } covt_prop_column;
 typedef struct covt_prop_dictionary {
@@ -366,6 +366,19 @@ int32_t covt_trim(covt_ctx* ctx);
  * are being decoded; the result is one set of buffers whatever the segmentation. */
 int32_t covt_decode_batch(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles,
                           uint32_t container, const covt_tilejson* tilejson, uint32_t flags, covt_result** out);
+/* The same with the results delivered to HOST memory: every buffer the sink names (ptr != NULL; page-locked memory, capacity in
+ * elements) receives the decoded buffer, segment by segment on its own stream while later segments are still being uploaded and
+ * decoded (PCIe is full duplex) — what a List<Layer> caller with a host-side consumer needs (CovtParser.java:87-102 materialises
+ * JTS objects on the host). The result still owns the device-resident buffers, layer table and statuses; covt_timing.d2h_ms =
+ * first to last device->host copy. A sink buffer that is too small fails the call with COVT_ERR_INVALID_ARG (the message names the
+ * sizes needed). */
+typedef struct covt_host_sink {
+    void*    ptr[COVT_NUM_BUFFERS];
+    uint64_t capacity[COVT_NUM_BUFFERS];
+} covt_host_sink;
+int32_t covt_decode_batch_to_host(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles,
+                                  uint32_t container, const covt_tilejson* tilejson, uint32_t flags, const covt_host_sink* sink,
+                                  covt_result** out);
 /* The same in two steps so that host->device transfer is timed apart from device-resident decode. */
 int32_t covt_batch_upload(covt_ctx* ctx, const uint8_t* blob, const uint64_t* tile_offsets, uint32_t n_tiles,
                           covt_batch** out);

@@ -1598,7 +1598,7 @@ static void prop_emit(prop_sink_t* k, const ps_t* Ps, const ps_t* Ds, uint64_t s
     c->value_kind = (uint8_t)kind;
     c->status = st;
     c->num_features = F;
-    c->dictionary = kind == COVT_PV_DICT_INDEX ? k->dict_index : 0;
+    c->dictionary = (kind == COVT_PV_DICT_INDEX && k->has_dict) ? k->dict_index : 0; /* (no dictionary of its own: 0, status UNSUPPORTED_ENCODING) */
     c->validity_offset = B->validity.n;
     vec_t* vb = kind == COVT_PV_BOOL ? &B->bools : kind == COVT_PV_DICT_INDEX ? &B->didx : kind == COVT_PV_I64 ? &B->i64 :
                 kind == COVT_PV_F32 ? &B->f32 : kind == COVT_PV_F64 ? &B->f64 : NULL;

@@ -494,3 +494,43 @@ def test_one_context_per_thread(covt, oracle, gen):
     for t in th:
         t.join()
     assert not errors, errors
+
+
+def test_decode_batch_to_host_delivers_the_same_buffers(covt, oracle, fixtures, gen, monkeypatch):
+    """covt_decode_batch_to_host: the buffers named by the sink land in host memory, read back segment by segment while later
+    segments are uploaded and decoded — same bytes as covt_result_read of the device-resident result, in one and in many segments,
+    and through the capacity retry; a sink that is too small fails the call."""
+    abi = covt.abi
+    synth_blob, synth_offs, _ = gen.tiles(7000, 3000, gen.default_params())
+    fx = util.concat_tiles([b for n, b in fixtures if n.startswith("omt/")] * 2)
+    for blob, offs, seg_bytes in ((synth_blob, synth_offs, None), (synth_blob, synth_offs, 1 << 19), (fx[0], fx[1], 1 << 20)):
+        if seg_bytes:
+            monkeypatch.setenv("COVT_SEG_BYTES", str(seg_bytes))
+            monkeypatch.setenv("COVT_MAX_SEGMENTS", "64")
+            monkeypatch.setenv("COVT_SEG_MIN_TILES", "1")
+        else:
+            monkeypatch.delenv("COVT_SEG_BYTES", raising=False)
+        dec = covt.Decoder(0)
+        try:
+            flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+            ref = dec.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags)
+            wanted = [abi.BUF_S_IDS, abi.BUF_S_GEOMETRY_TYPES, abi.BUF_A_GEOM_OFFSETS, abi.BUF_A_PART_OFFSETS, abi.BUF_A_RING_OFFSETS, abi.BUF_A_COORDS]
+            host = {b: np.full(ref.device_buffer(b)[1] + 5, 0x5A, dtype=abi.BUF_DTYPES[b]) for b in wanted}
+            res = dec.decode_batch_to_host(blob, offs, host, abi.CONTAINER_GEN2B, flags)
+            t = res.timing()
+            if seg_bytes:
+                assert t["segments"] >= 4 or t["capacity_retries"] == 1
+            for b in wanted:
+                n = ref.device_buffer(b)[1]
+                assert res.device_buffer(b)[1] == n
+                assert np.array_equal(host[b][:n], ref.buffer(b)), abi.BUF_NAMES[b]
+                assert (host[b][n:].view(np.uint8) == 0x5A).all()  # nothing written behind the buffer's end
+            util.compare_results(abi, res, oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags))
+            res.free()
+            small = dict(host)
+            small[abi.BUF_A_COORDS] = np.zeros(max(ref.device_buffer(abi.BUF_A_COORDS)[1] - 1, 0), dtype=np.int32)
+            with pytest.raises(covt.CovtError):
+                dec.decode_batch_to_host(blob, offs, small, abi.CONTAINER_GEN2B, flags)
+            ref.free()
+        finally:
+            dec.close()
