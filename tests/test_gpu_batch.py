@@ -523,8 +523,9 @@ def test_decode_batch_to_host_delivers_the_same_buffers(covt, oracle, fixtures, 
             for b in wanted:
                 n = ref.device_buffer(b)[1]
                 assert res.device_buffer(b)[1] == n
-                assert np.array_equal(host[b][:n], ref.buffer(b)), abi.BUF_NAMES[b]
-                assert (host[b][n:].view(np.uint8) == 0x5A).all()  # nothing written behind the buffer's end
+                # (byte-identical to the device-resident buffer of the SAME result: the alignment gaps between layer slices are never written)
+                assert np.array_equal(host[b][:n], res.buffer(b)), abi.BUF_NAMES[b]
+                assert (host[b][n:] == 0x5A).all()  # nothing written behind the buffer's end
             util.compare_results(abi, res, oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags))
             res.free()
             small = dict(host)
