@@ -40,7 +40,9 @@ struct Worker {
     Job job;
     int32_t rc = COVT_OK;
     covt_result* res = nullptr;
-    std::vector<uint64_t> offs;  // re-based tile offsets of the range
+    uint64_t* offs = nullptr;    // re-based tile offsets of the range, PAGE-LOCKED: covt_decode_batch copies them up segment by segment on
+                                 // its copy stream, and a copy from pageable memory would stall that stream's host side behind the blob copies
+    size_t offs_cap = 0;
     std::string err;
     double wall_ms = 0.0;
 };
@@ -64,11 +66,22 @@ void worker_main(Worker* w)
         const double t_start = now_ms();
         const uint32_t n = j.t1 - j.t0;
         const uint64_t base = j.tile_offsets[j.t0];
-        w->offs.resize((size_t)n + 1);
-        for (uint32_t i = 0; i <= n; i++) w->offs[i] = j.tile_offsets[j.t0 + i] - base;
+        if (w->offs_cap < (size_t)n + 1) {
+            if (w->offs) cudaFreeHost(w->offs);
+            w->offs = nullptr;
+            w->offs_cap = 0;
+            const size_t cap = ((size_t)n + 1) * 5 / 4 + 1024;
+            if (cudaMallocHost(reinterpret_cast<void**>(&w->offs), cap * sizeof(uint64_t)) == cudaSuccess) w->offs_cap = cap;
+        }
         w->res = nullptr;
-        w->rc = covt_decode_batch(w->ctx, j.blob + base, w->offs.data(), n, j.container, j.tilejson, j.flags, &w->res);
-        if (w->rc != COVT_OK) {
+        if (!w->offs) {
+            w->rc = COVT_ERR_OOM;
+            w->err = "cudaMallocHost failed for the re-based tile offsets";
+        } else {
+            for (uint32_t i = 0; i <= n; i++) w->offs[i] = j.tile_offsets[j.t0 + i] - base;
+            w->rc = covt_decode_batch(w->ctx, j.blob + base, w->offs, n, j.container, j.tilejson, j.flags, &w->res);
+        }
+        if (w->rc != COVT_OK && w->offs) {
             char buf[512];
             covt_last_error(w->ctx, buf, sizeof(buf));
             w->err = buf;
@@ -151,6 +164,7 @@ void covt_destroy_multi(covt_multi* M)
         }
         w->cv.notify_all();
         if (w->thread.joinable()) w->thread.join();
+        if (w->offs) { cudaSetDevice(w->device); cudaFreeHost(w->offs); }
         covt_destroy(w->ctx);
         delete w;
     }
