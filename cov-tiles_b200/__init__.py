@@ -672,3 +672,4 @@ class CovtParser:
         res.free()
         return layers
 from . import scheduler  # noqa: E402,F401  (one-process-per-GPU helpers over partition_tiles)
+from .converter import CovtConverter  # noqa: E402,F401  (the tile writer over the GPU stream encoders)

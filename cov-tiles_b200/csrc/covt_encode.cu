@@ -65,11 +65,13 @@ __device__ __forceinline__ uint64_t enc_varint_code(const void* values, uint64_t
 }
 
 // =================================================================================================
-// LEB128 writer: one warp per piece, 32 values per trip. Lengths come from clz, places from a warp scan; the bytes cross a small
-// shared-memory stage so that they leave as 16-byte vectors (the remainder of a trip waits at the front of the stage).
+// LEB128 writer: one warp per piece, 128 values per trip (four consecutive values per lane). Lengths come from clz, places from a
+// warp scan; the bytes cross a small shared-memory stage so that they leave as 16-byte vectors (the remainder of a trip waits at
+// the front of the stage).
 // =================================================================================================
 constexpr int ENC_WARPS = 4;
-constexpr int ENC_STAGE_BYTES = 16 + 32 * 10 + 16;
+constexpr int ENC_VPL = 4;                                       // values per lane and trip
+constexpr int ENC_STAGE_BYTES = 16 + 32 * ENC_VPL * 10 + 16;
 
 __global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_varint(const uint8_t* values, EncPiece* pieces, uint32_t n_pieces, uint32_t flags)
 {
@@ -84,21 +86,33 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_varint(const uint8_t* va
     uint32_t fill = 0;
     uint64_t flushed = 0;
     uint8_t* out = P.scratch;
-    for (uint32_t i0 = 0; i0 < P.num_values; i0 += 32) {
-        const bool valid = i0 + lane < P.num_values;
-        uint64_t u = 0;
-        if (valid) u = enc_varint_code(stream_values, (uint64_t)P.first_index + i0 + lane, P.op, P.num_bits, no_shift);
-        const uint32_t len = valid ? (u ? (uint32_t)(70 - __clzll((long long)u)) / 7u : 1u) : 0u;
+    for (uint32_t i0 = 0; i0 < P.num_values; i0 += 32 * ENC_VPL) {
+        // four consecutive values per lane: one warp scan and one flush per 128 values
+        uint64_t u[ENC_VPL];
+        uint32_t len[ENC_VPL], lane_len = 0;
+#pragma unroll
+        for (int q = 0; q < ENC_VPL; q++) {
+            const uint32_t i = i0 + ENC_VPL * lane + q;
+            const bool valid = i < P.num_values;
+            u[q] = valid ? enc_varint_code(stream_values, (uint64_t)P.first_index + i, P.op, P.num_bits, no_shift) : 0ull;
+            len[q] = valid ? (u[q] ? (uint32_t)(70 - __clzll((long long)u[q])) / 7u : 1u) : 0u;
+            lane_len += len[q];
+        }
         uint32_t total;
-        const uint32_t at = fill + warp_exclusive_scan(len, total);
-        for (uint32_t k = 0; k < len; k++) {
-            stage[at + k] = (uint8_t)((u & 0x7fu) | (k + 1 < len ? 0x80u : 0u));
-            u >>= 7;
+        uint32_t at = fill + warp_exclusive_scan(lane_len, total);
+#pragma unroll
+        for (int q = 0; q < ENC_VPL; q++) {
+            uint64_t x = u[q];
+            for (uint32_t k = 0; k < len[q]; k++) {
+                stage[at + k] = (uint8_t)((x & 0x7fu) | (k + 1 < len[q] ? 0x80u : 0u));
+                x >>= 7;
+            }
+            at += len[q];
         }
         fill += total;
         __syncwarp();
         const uint32_t nvec = fill >> 4;
-        if (lane < nvec) reinterpret_cast<uint4*>(out + flushed)[lane] = reinterpret_cast<const uint4*>(stage)[lane];
+        for (uint32_t i = lane; i < nvec; i += 32) reinterpret_cast<uint4*>(out + flushed)[i] = reinterpret_cast<const uint4*>(stage)[i];
         const uint32_t rem = fill & 15u;
         uint8_t keep = 0;
         if (lane < rem) keep = stage[16u * nvec + lane];

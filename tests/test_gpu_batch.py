@@ -535,3 +535,29 @@ def test_decode_batch_to_host_delivers_the_same_buffers(covt, oracle, fixtures, 
             ref.free()
         finally:
             dec.close()
+
+
+def test_decreasing_tile_offsets_are_rejected(covt, gen, monkeypatch):
+    """tile_offsets are checked segment by segment while the upload is already running: a batch whose offsets go backwards anywhere
+    fails with INVALID_ARG (one segment and many), and the context decodes the next batch as if nothing had happened."""
+    abi = covt.abi
+    blob, offs, _ = gen.tiles(100, 4000, gen.default_params())
+    for seg_bytes in (None, 1 << 18):
+        if seg_bytes:
+            monkeypatch.setenv("COVT_SEG_BYTES", str(seg_bytes))
+            monkeypatch.setenv("COVT_MAX_SEGMENTS", "64")
+            monkeypatch.setenv("COVT_SEG_MIN_TILES", "1")
+        dec = covt.Decoder(0)
+        try:
+            for at in (1, 2000, 3999):
+                bad = offs.copy()
+                bad[at] = bad[at + 1] + 7 if at + 1 < len(bad) - 1 else bad[at - 1] - 1
+                with pytest.raises(covt.CovtError) as ei:
+                    dec.decode_batch(blob, bad, abi.CONTAINER_GEN2B, abi.FLAG_CLOSE_RINGS)
+                assert ei.value.code == abi.ERR_INVALID_ARG
+            res = dec.decode_batch(blob, offs, abi.CONTAINER_GEN2B, abi.FLAG_CLOSE_RINGS)
+            st, _ = res.tile_status()
+            assert not st.any()
+            res.free()
+        finally:
+            dec.close()
