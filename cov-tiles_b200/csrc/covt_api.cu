@@ -37,6 +37,9 @@ struct covt_ctx {
     cudaStream_t stream = nullptr;       // kernels, allocations, result read-backs
     cudaStream_t copy_stream = nullptr;  // host->device segments of covt_decode_batch, overlapped with the kernels
     cudaStream_t out_stream = nullptr;   // device->host segments of covt_decode_batch_to_host (PCIe is full duplex: its own stream)
+    cudaStream_t big_stream = nullptr;   // second passes of the codec classes (large streams, a warp each): beside the next class's first pass
+    cudaEvent_t ev_pass1[covt::NUM_OP_CLASSES] = {}, ev_big_done = nullptr;
+    bool side_big = true;                // env COVT_SERIAL_BIG=1: second passes on the main stream (round-1 behaviour)
     std::string err;
     uint64_t* h_totals = nullptr;  // pinned scratch for the one device->host size read-back
     covt::SegState* h_seg = nullptr;     // pinned mirror of the device-side segment state
@@ -301,6 +304,10 @@ int32_t covt_create(int32_t device, covt_ctx** out)
     if (const char* sb = getenv("COVT_SEG_BYTES")) { const long long v = atoll(sb); if (v > 0) ctx->seg_bytes = (uint64_t)v; }
     ctx->debug = getenv("COVT_DEBUG") != nullptr;
     ctx->serial_classes = getenv("COVT_CONCURRENT") == nullptr;
+    ctx->side_big = getenv("COVT_SERIAL_BIG") == nullptr;
+    if ((e = cudaStreamCreateWithFlags(&ctx->big_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (auto& ev : ctx->ev_pass1) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_big_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
         if ((e = cudaStreamCreateWithFlags(&ctx->class_stream[c], cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_join[c], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -335,6 +342,9 @@ void covt_destroy(covt_ctx* ctx)
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
+    if (ctx->big_stream) cudaStreamDestroy(ctx->big_stream);
+    for (auto& e : ctx->ev_pass1) if (e) cudaEventDestroy(e);
+    if (ctx->ev_big_done) cudaEventDestroy(ctx->ev_big_done);
     for (int c = 0; c < NUM_OP_CLASSES; c++) {
         if (ctx->class_stream[c]) cudaStreamDestroy(ctx->class_stream[c]);
         if (ctx->ev_join[c]) cudaEventDestroy(ctx->ev_join[c]);
@@ -633,6 +643,7 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
             ctx->err = m_;                                                                            \
             rc = e_ == cudaErrorMemoryAllocation ? COVT_ERR_OOM : COVT_ERR_CUDA;                      \
             cudaStreamSynchronize(st);                                                                \
+            if (ctx->big_stream) cudaStreamSynchronize(ctx->big_stream);                              \
             cleanup_tmp();                                                                            \
             covt_result_free(R);                                                                      \
             return rc;                                                                                \
@@ -736,11 +747,18 @@ static int32_t decode_segments(covt_ctx* ctx, covt_batch* batch, uint32_t contai
         prof.end();
         // ---- every stream of every layer: one kernel per codec class ----
         if (prof.on || ctx->serial_classes) {
+            // (profiling brackets every class with events on the main stream: everything stays there)
+            const bool side = ctx->side_big && !prof.on;
             for (int c = 0; c < NUM_OP_CLASSES; c++) {
                 prof.begin(op_class_name(c), 0);
                 CKR(launch_decode_class(c, batch->d_blob, d_tasks + class_off.off[c], (uint32_t)std::min<uint64_t>(task_cap[c], 0xffffff00ull), d_counter + 3 * c,
-                                        d_queue + class_off.off[c], d_seg, reinterpret_cast<uint32_t*>(R->d_layers), ctx->sm_count, 0, st));
+                                        d_queue + class_off.off[c], d_seg, reinterpret_cast<uint32_t*>(R->d_layers), ctx->sm_count, 0, st,
+                                        side ? ctx->big_stream : nullptr, ctx->ev_pass1[c]));
                 prof.end();
+            }
+            if (side) {  // the assembler reads what the second passes wrote
+                CKR(cudaEventRecord(ctx->ev_big_done, ctx->big_stream));
+                CKR(cudaStreamWaitEvent(st, ctx->ev_big_done, 0));
             }
         } else {
             // experiment (off by default, see covt_ctx::serial_classes): the five codec kernels are independent, run them

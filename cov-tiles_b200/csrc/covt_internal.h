@@ -91,7 +91,8 @@ cudaError_t launch_k0_fill_layers(const uint8_t* blob, const uint64_t* tile_offs
 // to status_words[task.ref] (the layer table or the property-column records viewed as uint32 words); nullptr (stream path): status
 // and bytes consumed go back to the task. blocks_per_sm: 0 = fill the GPU with this kernel alone.
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* counters, uint32_t* big_queue,
-                                const SegState* seg, uint32_t* status_words, int sm_count, int blocks_per_sm, cudaStream_t st);
+                                const SegState* seg, uint32_t* status_words, int sm_count, int blocks_per_sm, cudaStream_t st,
+                                cudaStream_t big_st = nullptr /* second pass on its own stream, after pass1_done */, cudaEvent_t pass1_done = nullptr);
 const char* op_class_name(int op_class);
 cudaError_t launch_assemble_layers(covt_layer* layers, uint32_t n_layers_bound, ResultBuffers bufs, uint32_t flags,
                                    uint32_t* work_counter, const SegState* seg, uint64_t* totals /* [FINAL_TOTALS] */,

@@ -1240,9 +1240,14 @@ cudaError_t launch_seg_end(SegState* seg, uint32_t* first_layer_end, cudaStream_
 // counters: [0] group ticket of pass 1, [1] queue length, [2] ticket of pass 2 (all zero before the launch).
 // big_queue: n_tasks words (unused by the classes that decode every stream with a warp in pass 1).
 cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* tasks, uint32_t n_tasks, uint32_t* counters, uint32_t* big_queue,
-                                const SegState* seg, uint32_t* layers, int sm_count, int blocks_per_sm, cudaStream_t st)
+                                const SegState* seg, uint32_t* layers, int sm_count, int blocks_per_sm, cudaStream_t st, cudaStream_t big_st,
+                                cudaEvent_t pass1_done)
 {
     if (!n_tasks) return cudaSuccess;
+    // The second pass (queued large streams, a warp each) is a latency-bound tail with few warps: on its own stream it runs beside
+    // the first pass of the NEXT codec class instead of holding the whole GPU for itself.
+    cudaStream_t st2 = st;
+    const bool side = big_st != nullptr && op_class != CLASS_VARINT32;
     // Byte-RLE and RLE never touch the warp stage
     const int smem = (op_class == CLASS_BYTE_RLE || op_class == CLASS_RLE) ? 0 : DEC_WARPS * (op_class == CLASS_PFOR ? PFOR_WARP_SMEM : DEC_WARP_SMEM);
     const int per_sm = blocks_per_sm > 0 ? blocks_per_sm : (op_class == CLASS_PFOR ? 8 : 12);
@@ -1252,25 +1257,31 @@ cudaError_t launch_decode_class(int op_class, const uint8_t* blob, DeviceTask* t
     uint32_t *c0 = counters, *c1 = counters + 1, *c2 = counters + 2;
     // Minimum resident blocks per SM (profiles/r01_experiments.md): the 32-bit varint and FastPFOR kernels are capped at 64
     // registers (8 blocks = 32 warps per SM; below that the chunk decoder spills), the thread-per-stream kernels need no cap.
-#define COVT_PASS1(C, MINB, q, qc) k_decode_class<C, MINB><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc)
+#define COVT_PASS1(C, MINB, q, qc)                                                                             \
+    k_decode_class<C, MINB><<<grid, DEC_WARPS * 32, smem, st>>>(blob, tasks, n_tasks, c0, seg, layers, q, qc); \
+    if (side) {                                                                                                \
+        cudaEventRecord(pass1_done, st);                                                                       \
+        cudaStreamWaitEvent(big_st, pass1_done, 0);                                                            \
+        st2 = big_st;                                                                                          \
+    }
     switch (op_class) {
     case CLASS_BYTE_RLE:
         COVT_PASS1(CLASS_BYTE_RLE, 1, big_queue, c1);
-        k_decode_class_big<CLASS_BYTE_RLE><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
+        k_decode_class_big<CLASS_BYTE_RLE><<<grid_big, DEC_WARPS * 32, smem, st2>>>(blob, tasks, c2, seg, layers, big_queue, c1);
         break;
     case CLASS_RLE:
         COVT_PASS1(CLASS_RLE, 1, big_queue, c1);
-        k_decode_class_big<CLASS_RLE><<<grid_big, DEC_WARPS * 32, DEC_WARPS * RLE_BIG_WARP_SMEM, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
+        k_decode_class_big<CLASS_RLE><<<grid_big, DEC_WARPS * 32, DEC_WARPS * RLE_BIG_WARP_SMEM, st2>>>(blob, tasks, c2, seg, layers, big_queue, c1);
         break;
     case CLASS_VARINT32: COVT_PASS1(CLASS_VARINT32, 8, nullptr, nullptr); break;
     case CLASS_VARINT64:
         COVT_PASS1(CLASS_VARINT64, 1, big_queue, c1);
-        k_decode_class_big<CLASS_VARINT64><<<grid_big, DEC_WARPS * 32, smem, st>>>(blob, tasks, c2, seg, layers, big_queue, c1);
+        k_decode_class_big<CLASS_VARINT64><<<grid_big, DEC_WARPS * 32, smem, st2>>>(blob, tasks, c2, seg, layers, big_queue, c1);
         break;
     case CLASS_PFOR:
         COVT_PASS1(CLASS_PFOR, 8, big_queue, c1);
-        k_decode_class_big<CLASS_PFOR><<<grid_for(sm_count, 12, n_tasks, DEC_WARPS), DEC_WARPS * 32, DEC_WARPS * PFOR_BIG_WARP_SMEM, st>>>(blob, tasks, c2, seg, layers,
-                                                                                                                                      big_queue, c1);
+        k_decode_class_big<CLASS_PFOR><<<grid_for(sm_count, 12, n_tasks, DEC_WARPS), DEC_WARPS * 32, DEC_WARPS * PFOR_BIG_WARP_SMEM, st2>>>(blob, tasks, c2, seg, layers,
+                                                                                                                                       big_queue, c1);
         break;
     default: return cudaErrorInvalidValue;
     }

@@ -103,24 +103,6 @@ __device__ __forceinline__ void lean_sum_lane(const uint32_t w[4], uint32_t cm, 
     oth_out = oth;
 }
 
-// The same loop adding onto running sums that live across windows (k1a_aggregate walks many windows per warp): in: `cur` = the sum
-// of the class of the lane's first value, `oth` = the other class; out: after the lane's terminators swapped them that many times.
-template <bool ZZ>
-__device__ __forceinline__ void lean_sum_lane_acc(const uint32_t w[4], uint32_t cm, uint32_t acc, uint32_t mul, int32_t& cur, int32_t& oth)
-{
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const uint32_t p = (w[j >> 2] >> (8 * (j & 3))) & 0x7fu;
-        const uint32_t v = p * mul + acc;
-        const bool term = (cm & cont_bit_of_byte(j)) == 0u;
-        const int32_t t = cur + (ZZ ? zigzag_decode32(v) : (int32_t)v);
-        cur = term ? oth : cur;
-        oth = term ? t : oth;
-        acc = term ? 0u : v;
-        mul = term ? 1u : mul << 7;
-    }
-}
-
 // The aggregate pass without per-byte values: zigzag decode is linear in the payload bytes once the sign is known —
 //   zz(v) = s * (v >> 1) - b,  b = bit 0 of the value's FIRST byte, s = 1 - 2b,  v >> 1 = (p0 >> 1) + sum_{k>=1} p_k << (7k - 1)
 // — so every byte adds its own term q * m to the running sum of its value's class (first byte: q = p0 >> 1, m = s, and -b;
@@ -303,62 +285,10 @@ __device__ __forceinline__ void lean_rows4(uint32_t* A, uint32_t s4, uint32_t n,
     }
 }
 
-// One FULL row: A[0 .. 128) are 128 consecutive raw values whose first stream index e0 is a multiple of 4 — no bounds, no
-// partial vectors (the large-stream decode pass emits nothing else between the first and the last row of a superchunk).
-template <int POST>
-__device__ __forceinline__ void lean_row128(const uint32_t* A, void* dst, uint64_t e0, int32_t& cx, int32_t& cy, uint32_t num_bits, bool no_shift)
-{
-    const unsigned lane = lane_id();
-    const uint4 raw = *reinterpret_cast<const uint4*>(A + 4u * lane);
-    int32_t d0, d1, d2, d3;
-    if (POST == POST_PLAIN || POST == POST_DELTA_MORTON) { d0 = (int32_t)raw.x; d1 = (int32_t)raw.y; d2 = (int32_t)raw.z; d3 = (int32_t)raw.w; }
-    else { d0 = zigzag_decode32(raw.x); d1 = zigzag_decode32(raw.y); d2 = zigzag_decode32(raw.z); d3 = zigzag_decode32(raw.w); }
-    int32_t o0, o1, o2, o3;
-    if (POST == POST_ZZ_DELTA_XY) {
-        const int32_t sx = d0 + d2, sy = d1 + d3;
-        int32_t ix = sx, iy = sy;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int32_t tx = __shfl_up_sync(FULL, ix, d), ty = __shfl_up_sync(FULL, iy, d);
-            if (lane >= (unsigned)d) { ix += tx; iy += ty; }
-        }
-        o0 = cx + (ix - sx) + d0;
-        o1 = cy + (iy - sy) + d1;
-        o2 = o0 + d2;
-        o3 = o1 + d3;
-        cx += __shfl_sync(FULL, ix, 31);
-        cy += __shfl_sync(FULL, iy, 31);
-    } else if (POST == POST_ZZ_DELTA || POST == POST_DELTA_MORTON) {
-        const int32_t sm = d0 + d1 + d2 + d3;
-        int32_t is = sm;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int32_t t = __shfl_up_sync(FULL, is, d);
-            if (lane >= (unsigned)d) is += t;
-        }
-        o0 = cx + (is - sm) + d0;
-        o1 = o0 + d1;
-        o2 = o1 + d2;
-        o3 = o2 + d3;
-        cx += __shfl_sync(FULL, is, 31);
-    } else {
-        o0 = d0; o1 = d1; o2 = d2; o3 = d3;
-    }
-    const uint64_t e = e0 + 4u * lane;
-    if (POST == POST_DELTA_MORTON) {
-        int2* out = reinterpret_cast<int2*>(dst) + e;
-        const int2 m0 = morton_decode(o0, num_bits, no_shift), m1 = morton_decode(o1, num_bits, no_shift);
-        const int2 m2 = morton_decode(o2, num_bits, no_shift), m3 = morton_decode(o3, num_bits, no_shift);
-        *reinterpret_cast<int4*>(out) = make_int4(m0.x, m0.y, m1.x, m1.y);
-        *reinterpret_cast<int4*>(out + 2) = make_int4(m2.x, m2.y, m3.x, m3.y);
-    } else {
-        *reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(dst) + e) = make_int4(o0, o1, o2, o3);
-    }
-}
-
-// Two full rows at once: A[0 .. 256) are 256 consecutive raw values, eight per lane (two LDS.128 with a 2-way bank conflict, which
-// costs load-store cycles the kernel has to spare) — ONE warp scan per 256 values instead of two, and 32 contiguous output bytes
-// per lane.
+// Two full rows at once: A[0 .. 256) are 256 consecutive raw values whose first stream index e0 is a multiple of 4 — no bounds, no
+// partial vectors (the large-stream decode pass emits nothing else between the first and the last row of a superchunk). Eight
+// values per lane (two LDS.128 with a 2-way bank conflict, which costs load-store cycles the kernel has to spare): ONE warp scan
+// per 256 values instead of two, and 32 contiguous output bytes per lane.
 template <int POST>
 __device__ __forceinline__ void lean_row256(const uint32_t* A, void* dst, uint64_t e0, int32_t& cx, int32_t& cy, uint32_t num_bits, bool no_shift)
 {
