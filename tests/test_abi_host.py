@@ -122,6 +122,18 @@ def test_partition_tiles(covt):
     assert s[0] == 0 and s[-1] == 3 and np.all(np.diff(s.astype(np.int64)) >= 0)
     s = covt.partition_tiles(np.array([0], np.uint64), 4)
     assert list(s) == [0, 0, 0, 0, 0]
+    # the definition, against a plain restatement: part p starts at the first tile whose start offset reaches p / n_parts of the bytes
+    # (many empty tiles = runs of equal offsets; a first offset that is not 0)
+    for trial in range(20):
+        sizes = rng.integers(0, 50, 3000) * (rng.random(3000) < 0.4)
+        offs = np.zeros(len(sizes) + 1, np.uint64)
+        offs[1:] = np.cumsum(sizes)
+        offs += np.uint64(trial * 1000)
+        for parts in (2, 5, 24, 64):
+            base, total = int(offs[0]), int(offs[-1] - offs[0])
+            want = [0] + [int(np.searchsorted(offs[:-1], base + total * p // parts, side="left")) for p in range(1, parts)] + [len(sizes)]
+            want = list(np.maximum.accumulate(want))
+            assert list(covt.partition_tiles(offs, parts)) == want
 
 
 def test_java_binding_names_every_symbol_it_binds(covt):
