@@ -41,6 +41,11 @@ public final class CovtGpuDecoder implements AutoCloseable {
     private static final MethodHandle DESTROY_MULTI = h("covt_destroy_multi", FunctionDescriptor.ofVoid(ADDRESS));
     public static final long PROP_COLUMN_BYTES = 72, PROP_DICTIONARY_BYTES = 40;  // sizeof(covt_prop_column / covt_prop_dictionary)
     public static final int FLAG_DECODE_PROPERTIES = 0x80;
+    // results delivered to host memory while later segments upload and decode (covt_host_sink: 13 pointers + 13 capacities in elements)
+    private static final MethodHandle DECODE_BATCH_TO_HOST = h("covt_decode_batch_to_host",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    public static final StructLayout HOST_SINK = MemoryLayout.structLayout(
+        MemoryLayout.sequenceLayout(13, ADDRESS).withName("ptr"), MemoryLayout.sequenceLayout(13, JAVA_LONG).withName("capacity"));
     // the stream ENCODERS: EncodingUtils.encodeVarints / encodeRle / encodeByteRle / encodeFastPfor128 (EncodingUtils.java:39-230)
     private static final MethodHandle ENCODE_STREAMS = h("covt_encode_streams",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
