@@ -203,6 +203,63 @@ def test_every_fixture_stream_reencodes_to_its_own_bytes(covt, decoder, fixtures
     res.free()
 
 
+def test_every_property_stream_of_the_fixtures_reencodes_to_its_own_bytes(covt, decoder, fixtures):
+    """The other 26 000+ codec streams of the fixture tiles — present bitsets, BOOLEAN / INT_64 data, dictionary indices and entry
+    lengths of the property columns: each one decodes through covt_decode_streams and re-encodes through covt_encode_streams to
+    the bytes the reference converter wrote (one call each for all of them). The stream list comes from the gen-2b walker of the
+    test infrastructure (oracle/properties.py: names, encodings, offsets); no CPU codec is involved."""
+    from oracle import properties as P
+    abi = covt.abi
+    tiles = [b for _, b in fixtures]
+    blob, offs = util.concat_tiles(tiles)
+    want = []  # (op, absolute offset, byte length, values to decode)
+    for t, tile in enumerate(tiles):
+        base = int(offs[t])
+        for L in P.walk_gen2b(bytes(tile)):
+            for c in L["columns"]:
+                if c["data_type"] == P.DT2_GEOMETRY or (c["name"] == "id" and c is L["columns"][0]):
+                    continue
+                dt = c["data_type"]
+                for st in c["streams"]:
+                    name, enc, nv = st["name"], st["encoding"], st["num_values"]
+                    op, n = None, nv
+                    if enc == abi.ENC_BOOLEAN_RLE:
+                        op, n = abi.OP_BYTE_RLE, (nv + 7) // 8  # a java.util.BitSet as bytes
+                    elif name == "dictionary" or dt in (P.DT2_FLOAT, P.DT2_DOUBLE) or enc == abi.ENC_PLAIN:
+                        continue  # raw bytes, no codec
+                    elif enc == abi.ENC_RLE:
+                        op = abi.OP_RLE_S64 if (dt == P.DT2_INT_64 and name == "data") else abi.OP_RLE_U64
+                    elif enc == abi.ENC_VARINT_ZIG_ZAG:
+                        op = abi.OP_VARINT_ZZ
+                    elif enc == abi.ENC_VARINT_DELTA_ZIG_ZAG:
+                        op = abi.OP_VARINT_ZZ_DELTA
+                    elif enc == abi.ENC_VARINT:
+                        op = abi.OP_VARINT_U32
+                    assert op is not None, (c["name"], name, enc)
+                    want.append((op, base + st["offset"], st["byte_length"], n))
+    assert len(want) > 20000
+    descs = (abi.StreamDesc * len(want))()
+    for i, (op, off, bl, n) in enumerate(want):
+        descs[i] = abi.StreamDesc(byte_offset=off, byte_length=bl, num_values=n, op=op)
+    padded = np.concatenate([blob, np.zeros(64, np.uint8)])
+    res = decoder.decode_streams(padded, descs)
+    arena = res.buffer(abi.BUF_STREAM_ARENA)
+    cases = []
+    for i, (op, off, bl, n) in enumerate(want):
+        d = descs[i]
+        assert d.status == 0 and d.bytes_consumed == bl, "stream %d op %s: status %d, consumed %d of %d" % (i, abi.OP_NAMES[op], d.status, d.bytes_consumed, bl)
+        dt = np.dtype(abi.op_dtype(op))
+        cases.append((op, arena[d.out_offset:d.out_offset + d.out_count * dt.itemsize].view(dt).copy(), 0))
+    res.free()
+    got = _encode_many(covt, decoder, cases)
+    seen = {}
+    for (op, off, bl, n), enc in zip(want, got):
+        assert len(enc) == bl and np.array_equal(enc, blob[off:off + bl]), "op %s, %d values at %d: re-encoding differs (%d vs %d bytes)" % (
+            abi.OP_NAMES[op], n, off, len(enc), bl)
+        seen[abi.OP_NAMES[op]] = seen.get(abi.OP_NAMES[op], 0) + 1
+    assert seen.get("byte_rle", 0) > 9000 and seen.get("rle_u64", 0) > 9000 and seen.get("rle_s64", 0) > 100, seen
+
+
 def test_encoding_utils_mirror_and_round_trip(covt, decoder):
     """The host-side mirror of EncodingUtils (same names) and DecodingUtils, there and back."""
     E, D = covt.EncodingUtils, covt.DecodingUtils
