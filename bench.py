@@ -462,8 +462,9 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     clocks = sampler.stop()
-    # per-kernel breakdown: a separate pass with one CUDA event pair per kernel, codec kernels serialised (in the timed pass
-    # above they run side by side on their own streams, so their individual durations would overlap)
+    # per-kernel breakdown: a separate pass with one CUDA event pair per kernel, everything on the main stream (in the timed pass
+    # above the codec classes run one after the other too, but the SECOND pass of a class — its queued large streams — runs on a side
+    # stream beside the next class's first pass, so individual durations would overlap)
     ktimes = {}
     prof_ms = 0.0
     for _ in range(args.steps):
