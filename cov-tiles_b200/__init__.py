@@ -211,6 +211,26 @@ class Result:
     def read_into(self, which, offset, count, host_ptr):
         self._dec._check(lib().covt_result_read(self._h, which, offset, count, host_ptr))
 
+    def to_arrow(self, blob, with_props=True):
+        """[(tile index, layer name, pyarrow.Table)]: id, geometry_type, the GeoArrow-nested geometry and (with FLAG_DECODE_PROPERTIES)
+        the property columns of every decoded layer, wrapped around host copies of the result buffers (see arrow.py)."""
+        from . import arrow
+
+        class _Lazy(dict):
+            def __missing__(s, which):
+                s[which] = self.buffer(which)
+                return s[which]
+
+        props = None
+        if with_props and len(self.prop_columns()):
+            class _P:
+                pass
+            props = _P()
+            props.columns, props.dictionaries = self.prop_columns(), self.prop_dictionaries()
+            props.buffers = [self.prop_buffer(b) for b in range(abi.NUM_PROP_BUFFERS)]
+            props.validity, props.dict_offsets = props.buffers[abi.PBUF_VALIDITY], props.buffers[abi.PBUF_DICT_OFFSETS]
+        return arrow.layer_tables(np.ascontiguousarray(blob, dtype=np.uint8), self.layers, _Lazy(), props)
+
     # ---- property columns (FLAG_DECODE_PROPERTIES) ----
     def prop_columns(self):
         """numpy structured array of covt_prop_column (one record per decoded property column / localized sub-column)."""

@@ -191,3 +191,28 @@ def test_property_columns_two_gpus_one_call(covt, oracle, fixtures):
         mres.free()
     finally:
         md.close()
+
+
+def test_result_to_arrow_equals_the_oracle_tables(covt, oracle, decoder, fixtures):
+    """Result.to_arrow: the decoded layers as pyarrow Tables (GeoArrow-nested geometry, ids, property columns) wrapped around host copies
+    of the GPU buffers = the same tables built from the oracle's results (tests/test_arrow.py checks those against the canonical forms)."""
+    pa = pytest.importorskip("pyarrow")
+    from importlib import import_module
+    arrow = import_module(covt.__name__ + ".arrow")
+    abi = covt.abi
+    tiles = [b for n, b in fixtures if n.startswith(("omt/5_", "omt/10_", "amazon/"))]
+    blob, offs = util.concat_tiles(tiles)
+    flags = abi.FLAG_CLOSE_RINGS | abi.FLAG_ID_DVZZ_IS_RLE
+    res = decoder.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags | abi.FLAG_DECODE_PROPERTIES)
+    got = res.to_arrow(blob)
+    ref = oracle.decode_batch(blob, offs, abi.CONTAINER_GEN2B, flags)
+    want = arrow.layer_tables(blob, ref.layers, {b: ref.buffer(b) for b in range(abi.NUM_BUFFERS - 1)},
+                              oracle.decode_properties(blob, offs, abi.CONTAINER_GEN2B, flags))
+    assert len(got) == len(want) > 100
+    n_cols = 0
+    for (t1, n1, T1), (t2, n2, T2) in zip(got, want):
+        assert (t1, n1) == (t2, n2) and T1.column_names == T2.column_names
+        assert T1.equals(T2), (t1, n1)
+        n_cols += T1.num_columns
+    assert n_cols > 1500
+    res.free()
