@@ -14,6 +14,13 @@
  *                                              decodeZigZagDeltaVarintCoordinates :95, decodeRle :257, decodeByteRle :275/:290,
  *                                              decodeFastPfor128ZigZagDelta :316, decodeFastPfor128DeltaCoordinates :349,
  *                                              decodeDeltaVarintMortonCodes :394, decodeFastPfor128DeltaMortonCodes :411
+ *   covt_decode_batch_to_host                <- the same call for a host-side consumer (CovtParser.java:87-102 builds its objects on the
+ *                                              host): result buffers delivered to page-locked memory while the batch still uploads
+ *   covt_encode_streams                      <- the static stream encoders of EncodingUtils  J/converter/EncodingUtils.java
+ *                                              encodeVarints :39, encodeRle :123, encodeByteRle :136, encodeFastPfor128 :149,
+ *                                              encodeZigZagDeltaCoordinates :190; GeometryUtils.encodeMorton J/converter/GeometryUtils.java:23
+ *   covt_result_prop_*                       <- CovtParser.decodePropertyColumn :276-390 (columnar, Arrow layout)
+ *   covt_create_multi / covt_decode_batch_multi  the batch scheduler: one call, the GPUs of one box (no reference counterpart)
  *   covt_stream_desc / covt_stream_ref       <- StreamMetadata(streamEncoding,numValues,byteLength)  J/converter/StreamMetadata.java:3
  *   enum values                              <- ordinals of StreamEncoding.java:3-16, StreamType.java:3-16, ColumnType.java:3-9,
  *                                              ColumnDataType.java:3-21, GeometryType (CovtParser.java:20-27): the ordinals ARE the wire values
