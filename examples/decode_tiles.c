@@ -81,6 +81,49 @@ int main(int argc, char** argv)
                (const char*)blob + L->name_offset, L->num_features, L->n_parts, L->n_rings, L->n_vertices, L->n_coords, L->status,
                (unsigned long long)h);
     }
+    /* ... and the other direction (EncodingUtils.encodeByteRle, EncodingUtils.java:136): the decoded geometry_types stream of every layer,
+     * encoded again on the GPU in ONE covt_encode_streams call, must give back the bytes of the tile */
+    {
+        uint64_t total = 0;
+        uint32_t n_enc = 0;
+        for (uint32_t l = 0; l < n_layers; l++)
+            if (layers[l].status == COVT_OK) { total += (layers[l].num_features + 7u) & ~7ull; n_enc++; }
+        uint8_t* values = (uint8_t*)calloc(total + 8, 1);
+        covt_encode_desc* descs = (covt_encode_desc*)calloc(n_enc + 1, sizeof(covt_encode_desc));
+        uint64_t at = 0;
+        uint32_t k = 0;
+        for (uint32_t l = 0; l < n_layers; l++) {
+            const covt_layer* L = &layers[l];
+            if (L->status != COVT_OK) continue;
+            if (L->num_features && (rc = covt_result_read(res, COVT_BUF_S_GEOMETRY_TYPES, L->out[COVT_BUF_S_GEOMETRY_TYPES], L->num_features, values + at)) != COVT_OK)
+                die(ctx, "covt_result_read", rc);
+            descs[k].value_offset = at;
+            descs[k].num_values = L->num_features;
+            descs[k].op = COVT_OP_BYTE_RLE;
+            at += (L->num_features + 7u) & ~7ull;
+            k++;
+        }
+        covt_result* enc = NULL;
+        if ((rc = covt_encode_streams(ctx, values, total, descs, n_enc, COVT_FLAG_DEFAULT, &enc)) != COVT_OK) die(ctx, "covt_encode_streams", rc);
+        uint32_t same = 0;
+        k = 0;
+        for (uint32_t l = 0; l < n_layers; l++) {
+            const covt_layer* L = &layers[l];
+            if (L->status != COVT_OK) continue;
+            const covt_stream_ref* S = &L->streams[COVT_SLOT_TYPES];
+            uint8_t* bytes = (uint8_t*)malloc(descs[k].byte_length + 1);
+            if (descs[k].status == COVT_OK && descs[k].byte_length &&
+                (rc = covt_result_read(enc, COVT_BUF_STREAM_ARENA, descs[k].out_offset, descs[k].byte_length, bytes)) != COVT_OK)
+                die(ctx, "covt_result_read", rc);
+            same += descs[k].status == COVT_OK && descs[k].byte_length == S->byte_length && !memcmp(bytes, blob + S->byte_offset, S->byte_length);
+            free(bytes);
+            k++;
+        }
+        fprintf(stderr, "re-encoded %u geometry_types streams on the GPU: %u identical to the tile bytes\n", n_enc, same);
+        covt_result_free(enc);
+        free(descs);
+        free(values);
+    }
     covt_timing t;
     covt_result_timing(res, &t);
     fprintf(stderr, "%u tiles, %u layers: upload %.3f ms, decode %.3f ms (%u kernel launches), %.1f MB of stream payload, %llu vertices\n",

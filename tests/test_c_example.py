@@ -71,3 +71,7 @@ def test_c_example_output_equals_oracle(example_binary, oracle, fixtures, tmp_pa
         assert int(ln[9], 16) == _fnv(coords[o:o + 2 * ncoords]), name
         checked += 1
     assert checked > 20
+    # the example also encodes every decoded geometry_types stream again on the GPU (covt_encode_streams from plain C)
+    import re
+    m = re.search(r"re-encoded (\d+) geometry_types streams on the GPU: (\d+) identical", p.stderr)
+    assert m and int(m.group(1)) == checked and m.group(1) == m.group(2), p.stderr
